@@ -1,0 +1,175 @@
+/*
+ * vaeb_b200.h -- C-ABI of the B200-native AEVB hot path (drop-in boundary).
+ *
+ * The reference (budzianowski/VAEB) has no native plugin ABI: its hot path is entered
+ * through two Theano-compiled Python callables, `update(index)` and `validate(x)`
+ * (VAEB.py:408-422), built by `VAEB.getGradient` (VAEB.py:370-424).  This header is the
+ * C-ABI that sits directly beneath those callables.  Every entry point names the
+ * reference interface it replaces (file:line under the reference root).  The reference-side
+ * binding (a ctypes stub in VAEB.py) is shown in INTEGRATION.md; the shipped host mirror
+ * is vaeb_b200/model.py.
+ *
+ * Conventions: plain pointers and sizes, no torch types.  All `float*` arguments are HOST
+ * pointers unless named `d_*` / documented as device.  Matrices are row-major fp32.
+ * Parameter tensors follow the reference list order
+ *   [W3,W4,W5,W1,W2,(W6),b3,b4,b5,b1,b2,(b6)]            (VAEB.py:111-115)
+ * with weights stored [in,out].  Every function returns 0 on success or a VAEB_E* code;
+ * `vaeb_last_error()` returns a thread-local message.  A handle is bound to one GPU and is
+ * not re-entrant.  There is no CPU fallback: without a CUDA device `vaeb_create` fails.
+ */
+#ifndef VAEB_B200_H_
+#define VAEB_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAEB_OK 0
+#define VAEB_EINVAL 1   /* bad argument / unsupported configuration      */
+#define VAEB_ECUDA 2    /* CUDA runtime error (message has the details)  */
+#define VAEB_ENCCL 3    /* NCCL error or communicator not attached       */
+#define VAEB_ESTATE 4   /* call sequence error (e.g. no data uploaded)   */
+
+/* estimator -- which bound `getGradient` builds (VAEB.py:378-383) */
+#define VAEB_EST_LB 0           /* getLB   VAEB.py:332-346 */
+#define VAEB_EST_LA 1           /* getLA   VAEB.py:315-330 (--generic_estimator) */
+#define VAEB_EST_FVB 2          /* getFVBL VAEB.py:349-367 exactly as shipped: weights NOT sampled */
+#define VAEB_EST_FVB_SAMPLED 3  /* getFVBL with sample_variational_params (VAEB.py:127-129) live */
+
+/* variant -- which script's objective/update scalars */
+#define VAEB_VARIANT_VAEB 0       /* VAEB.py: sum objective, -0.5*sum(p^2) prior, Adagrad        */
+#define VAEB_VARIANT_FULLBAYES 1  /* VAEBfullbayes.py:139-145,169-185: mean objective, no prior, */
+                                  /* extra -lr*1e-6*p^2 in the update                            */
+
+/* precision -- arithmetic of the dense layers */
+#define VAEB_PREC_FP32 0   /* fp32 FFMA tiles (parity tier 1e-4)                          */
+#define VAEB_PREC_BF16 1   /* tcgen05 bf16 operands, fp32 TMEM accumulation (1e-2 tier)   */
+
+/* eps source */
+#define VAEB_EPS_PHILOX 0    /* on-device Philox4x32-10 + Box-Muller                      */
+#define VAEB_EPS_INJECTED 1  /* caller passes eps (the reference's host RNG draws)         */
+
+typedef struct vaeb_handle vaeb_handle;
+
+/* Mirrors the constructor VAEB.__init__ (VAEB.py:132-152). */
+typedef struct vaeb_config {
+  int32_t input_dim;      /* D  = x_train.shape[1]                      (VAEB.py:135) */
+  int32_t hidden_units;   /* H                                          (VAEB.py:136) */
+  int32_t latent_size;    /* Z                                          (VAEB.py:137) */
+  int32_t batch_size;     /* M  rows per update()                       (VAEB.py:140) */
+  int32_t L;              /* samples of z per datapoint                 (VAEB.py:143) */
+  int32_t continuous;     /* 1 Gaussian decoder, 0 Bernoulli            (VAEB.py:138) */
+  int32_t estimator;      /* VAEB_EST_*                                              */
+  int32_t variant;        /* VAEB_VARIANT_*                                          */
+  int32_t precision;      /* VAEB_PREC_*                                             */
+  int32_t device;         /* CUDA ordinal                                            */
+  float learning_rate;    /*                                            (VAEB.py:139) */
+  float adagrad_eps;      /* 1e-6                                       (VAEB.py:144) */
+  float prior_scale;      /* 1.0: -0.5*scale*sum(p^2)                   (VAEB.py:386) */
+  float sigma_vb_init;    /* 1e-3 fullVBSigmaInit                       (VAEB.py:146) */
+  uint64_t seed;          /* Philox key (reference: RandomStreams(seed=10), VAEB.py:158) */
+} vaeb_config;
+
+const char* vaeb_last_error(void);
+int vaeb_version(void);
+
+/* VAEB.__init__ (VAEB.py:132-187): allocates the flat params / ADA / grads buffers
+ * (VAEB.py:178-182) and workspaces on cfg->device.  Parameters start at zero: the host
+ * mirror draws the reference initialisation (VAEB.py:50-115) and calls vaeb_set_params. */
+int vaeb_create(const vaeb_config* cfg, vaeb_handle** out);
+int vaeb_destroy(vaeb_handle* h);
+
+/* Use an existing cudaStream_t for all work (NULL: the handle's own stream). */
+int vaeb_set_stream(vaeb_handle* h, void* cuda_stream);
+int vaeb_synchronize(vaeb_handle* h);
+
+/* self.params / self.ADA / self.full_variational_params access (VAEB.py:111-125,178-182).
+ * `which`: 0 params, 1 ADA accumulators, 2 gradients of the last step (criterion incl. prior),
+ *          3 variational means, 4 variational sigmas, 5 ADA of means, 6 ADA of sigmas,
+ *          7 gradients w.r.t. means, 8 gradients w.r.t. sigmas  (3..8: FVB estimators only).
+ * `tensors[i]` points at host storage of tensor i in reference order. */
+int vaeb_num_tensors(vaeb_handle* h, int32_t* n_tensors, int64_t* n_elements);
+int vaeb_tensor_shape(vaeb_handle* h, int32_t i, int32_t* rows, int32_t* cols);
+int vaeb_set_tensors(vaeb_handle* h, int32_t which, const float* const* tensors);
+int vaeb_get_tensors(vaeb_handle* h, int32_t which, float* const* tensors);
+/* Device address of a flat buffer (`which` as above) for zero-copy plumbing (e.g. wrapping as
+ * a tensor for torch.distributed). */
+int vaeb_device_buffer(vaeb_handle* h, int32_t which, void** d_ptr, int64_t* n_elements);
+
+/* `x_train = th.shared(...)` (VAEB.py:184): copies x[N,D] to the device once. */
+int vaeb_upload_data(vaeb_handle* h, const float* x, int64_t n_rows);
+
+/* `update(index)` (VAEB.py:408-415): one AEVB step on rows [index*M,(index+1)*M) of the
+ * resident data: forward, bound, backward, prior, Adagrad.  *elbo_out = SGVB/M computed
+ * with the PRE-update parameters (VAEBfullbayes variant: the mean objective).  eps: NULL for
+ * Philox, else host eps[L,M,Z] (the draws of `srng.normal`, VAEB.py:42).  Synchronous. */
+int vaeb_update(vaeb_handle* h, int64_t index, const float* eps, float* elbo_out);
+
+/* As vaeb_update, but the minibatch x[rows,D] comes from HOST memory in this call (the
+ * end-to-end path: H2D copy of the inputs + D2H of the result inside the call). */
+int vaeb_update_host(vaeb_handle* h, const float* x, int64_t rows, const float* eps, float* elbo_out);
+
+/* The inner loop of train_model (VAEB.py:577-579) as ONE call: `n` updates in the order
+ * `batch_order[0..n)` with no host synchronisation between them; elbo_out[n] receives each
+ * step's SGVB/M.  Philox eps only. */
+int vaeb_update_many(vaeb_handle* h, const int32_t* batch_order, int32_t n, float* elbo_out);
+
+/* `validate(x)` (VAEB.py:418-422): SGVB of x[n,D] (a SUM over rows; the caller divides,
+ * VAEB.py:582).  No parameter update.  per_row_out (NULL or float[n]) receives the
+ * per-datapoint bound.  eps: NULL for Philox, else host eps[L,n,Z]. */
+int vaeb_validate(vaeb_handle* h, const float* x, int64_t n, const float* eps,
+                  float* sgvb_out, float* per_row_out);
+
+/* Forward+backward only: fills the gradient buffer (`which`=2 / 7,8) without the Adagrad
+ * update; the parity tests read per-tensor gradients through this.  x==NULL: rows of the
+ * resident data starting at index*M. */
+int vaeb_gradients(vaeb_handle* h, const float* x, int64_t rows, int64_t index, const float* eps,
+                   const float* zeta, float* sgvb_out, float* per_row_out);
+/* The Adagrad update alone (VAEB.py:426-444) on the current gradient buffer. */
+int vaeb_apply_update(vaeb_handle* h);
+
+/* Importance-sampled marginal likelihood (new capability named by the north star; the
+ * integrand is getLA's, VAEB.py:319-327): log p^(x_i) = logsumexp_l(log w_il) - log L for
+ * x[n,D].  eps: NULL (Philox keyed by (row_offset+i, l, j): results do not depend on how
+ * rows are sharded over GPUs) or host eps[n,L,Z].  logw_out: NULL or float[n*L]. */
+int vaeb_is_logpx(vaeb_handle* h, const float* x, int64_t n, int32_t L, const float* eps,
+                  int64_t row_offset, float* logpx_out, float* logw_out);
+
+/* `reconstruct(x, n_samples)` deterministic part (VAEB.py:267-292): decoder means averaged
+ * over n_samples reparameterised z (n_samples<=0: decode mu).  y_out[n,D]; for the Gaussian
+ * decoder lv_out[n,D] receives the averaged log-variance output (else may be NULL). */
+int vaeb_reconstruct(vaeb_handle* h, const float* x, int64_t n, int32_t n_samples,
+                     const float* eps, float* y_out, float* lv_out);
+
+/* Dense tanh layers of the AE-side builders (degenerate-vae/mlp.py:66-74 ConstructMLP):
+ * out = f(...f(x.W0+b0)...Wk+bk), f = tanh on every layer (act=1) or identity on the last
+ * (act_last=0: logpdf.py:72-73 OutToReal; 2: sigmoid, logpdf.py:46-47 OutToProbs). */
+int vaeb_mlp_forward(vaeb_handle* h, const float* x, int64_t n, int32_t n_layers,
+                     const int32_t* dims /* n_layers+1 */, const float* const* W,
+                     const float* const* b, int32_t act_last, float* out);
+
+/* Philox eps exactly as the kernels draw it (for parity tests of the RNG itself):
+ * out[n] = N(0,1) for flat elements first_elem.. of (stream, step, sample). */
+int vaeb_philox_normal(vaeb_handle* h, int32_t stream, uint32_t step, uint32_t sample,
+                       int64_t first_elem, int64_t n, float* out);
+int vaeb_set_step_counter(vaeb_handle* h, uint32_t step);
+
+/* Data-parallel training (new): one handle per rank/GPU.  Rank 0 makes an id,
+ * the host plumbing broadcasts the 128 bytes, every rank attaches.  After attaching,
+ * vaeb_update* all-reduces (sum) the flat gradient and the bound over ranks before the
+ * prior and the Adagrad update, so `batch_size` is the PER-RANK share of the global batch.
+ * `nccl_library` = path of libnccl.so.2 to dlopen (the one torch bundles). */
+int vaeb_comm_unique_id(const char* nccl_library, uint8_t id_out[128]);
+int vaeb_comm_attach(vaeb_handle* h, const char* nccl_library, const uint8_t id[128],
+                     int32_t rank, int32_t world_size);
+int vaeb_comm_detach(vaeb_handle* h);
+
+/* Counters for the bench: kernels launched by this handle since creation. */
+int vaeb_launch_count(vaeb_handle* h, int64_t* n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAEB_B200_H_ */

@@ -1,0 +1,724 @@
+// C-ABI of include/vaeb_b200.h: handle management and the orchestration of one AEVB step.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "launchers.h"
+#include "philox.cuh"
+
+int dec2_col_tiles(int rows, int D);  // kernels_gemm.cu
+
+static thread_local std::string g_last_error;
+void vaeb_set_error(const std::string& msg) { g_last_error = msg; }
+
+#define VAEB_LAUNCH(expr)                                                     \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess) {                                                  \
+      vaeb_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+      return VAEB_ECUDA;                                                      \
+    }                                                                         \
+  } while (0)
+
+namespace {
+
+void build_layout(Layout& l, int D, int H, int Z, bool cont) {
+  int i = 0;
+  auto add = [&](int& idx, int r, int c) { idx = i; l.rows[i] = r; l.cols[i] = c; ++i; };
+  l.iW6 = l.ib6 = -1;
+  add(l.iW3, D, H); add(l.iW4, H, Z); add(l.iW5, H, Z); add(l.iW1, Z, H); add(l.iW2, H, D);
+  if (cont) add(l.iW6, H, D);
+  add(l.ib3, 1, H); add(l.ib4, 1, Z); add(l.ib5, 1, Z); add(l.ib1, 1, H); add(l.ib2, 1, D);
+  if (cont) add(l.ib6, 1, D);
+  l.n = i;
+  int64_t off = 0;
+  for (int t = 0; t < l.n; ++t) { l.off[t] = off; off += (int64_t)l.rows[t] * l.cols[t]; }
+  l.total = off;
+  l.padded = (off + 3) / 4 * 4;
+}
+
+bool is_fvb(const vaeb_handle* h) {
+  return h->cfg.estimator == VAEB_EST_FVB || h->cfg.estimator == VAEB_EST_FVB_SAMPLED;
+}
+
+int alloc_flat(float** p, int64_t n, float fill = 0.f) {
+  VAEB_CUDA(cudaMalloc((void**)p, (size_t)n * sizeof(float)));
+  if (fill == 0.f) {
+    VAEB_CUDA(cudaMemset(*p, 0, (size_t)n * sizeof(float)));
+  } else {
+    std::vector<float> tmp((size_t)n, fill);
+    VAEB_CUDA(cudaMemcpy(*p, tmp.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  return VAEB_OK;
+}
+
+int grow(float** p, int64_t* cap, int64_t need) {
+  if (need <= *cap) return VAEB_OK;
+  if (*p) VAEB_CUDA(cudaFree(*p));
+  *p = nullptr;
+  VAEB_CUDA(cudaMalloc((void**)p, (size_t)need * sizeof(float)));
+  *cap = need;
+  return VAEB_OK;
+}
+
+void free_ws(Workspace& w) {
+  float** all[] = {&w.h_e, &w.mu, &w.ls, &w.eps, &w.z, &w.h_d, &w.da2, &w.dlv, &w.da1, &w.dz, &w.dmu, &w.dls,
+                   &w.da3, &w.partial, &w.row_aux, &w.per_row, &w.dec_aux, &w.logw};
+  for (float** p : all) { if (*p) cudaFree(*p); *p = nullptr; }
+  w.cap_enc = w.cap_dec = 0;
+  w.with_grads = false;
+}
+
+int ensure_ws(vaeb_handle* h, int64_t enc, int64_t dec, bool grads) {
+  Workspace& w = h->ws;
+  if (enc <= w.cap_enc && dec <= w.cap_dec && (!grads || w.with_grads)) return VAEB_OK;
+  VAEB_CUDA(cudaStreamSynchronize(h->stream));
+  enc = std::max(enc, w.cap_enc);
+  dec = std::max(dec, w.cap_dec);
+  grads = grads || w.with_grads;
+  free_ws(w);
+  const int D = h->D, H = h->H, Z = h->Z;
+  const int64_t T = (D + 31) / 32;
+  auto A = [&](float** p, int64_t n) -> int {
+    VAEB_CUDA(cudaMalloc((void**)p, (size_t)std::max<int64_t>(n, 1) * sizeof(float)));
+    return VAEB_OK;
+  };
+  VAEB_TRY(A(&w.h_e, enc * H)); VAEB_TRY(A(&w.mu, enc * Z)); VAEB_TRY(A(&w.ls, enc * Z));
+  VAEB_TRY(A(&w.row_aux, enc)); VAEB_TRY(A(&w.per_row, enc));
+  VAEB_TRY(A(&w.eps, dec * Z)); VAEB_TRY(A(&w.z, dec * Z)); VAEB_TRY(A(&w.h_d, dec * H));
+  VAEB_TRY(A(&w.partial, dec * T)); VAEB_TRY(A(&w.dec_aux, dec)); VAEB_TRY(A(&w.logw, dec));
+  if (grads) {
+    VAEB_TRY(A(&w.da2, dec * D));
+    if (h->cont) VAEB_TRY(A(&w.dlv, dec * D));
+    VAEB_TRY(A(&w.da1, dec * H)); VAEB_TRY(A(&w.dz, dec * Z));
+    VAEB_TRY(A(&w.dmu, enc * Z)); VAEB_TRY(A(&w.dls, enc * Z)); VAEB_TRY(A(&w.da3, enc * H));
+  }
+  w.cap_enc = enc; w.cap_dec = dec; w.with_grads = grads;
+  return VAEB_OK;
+}
+
+inline float* T_(vaeb_handle* h, float* base, int idx) { return base + h->lay.off[idx]; }
+inline const float* T_(vaeb_handle* h, const float* base, int idx) { return base + h->lay.off[idx]; }
+
+// Forward (+ backward into `grads`) of the graph of VAEB.getGradient for x[rows,D] on device.
+int forward_backward(vaeb_handle* h, const float* theta, const float* x, int rows, int L, bool want_grads, float w,
+                     EpsSource src, float* grads, int* n_tiles) {
+  const Layout& l = h->lay;
+  Workspace& s = h->ws;
+  const int D = h->D, H = h->H, Z = h->Z;
+  const int R = rows * L;
+  const int la = h->cfg.estimator == VAEB_EST_LA ? 1 : 0;
+  cudaStream_t st = h->stream;
+  int64_t* lc = &h->launches;
+  // encoder, VAEB.py:245-251
+  VAEB_LAUNCH(launch_dense_act(st, lc, x, rows, D, T_(h, theta, l.iW3), T_(h, theta, l.ib3), H, 1, s.h_e));
+  VAEB_LAUNCH(launch_enc2(st, lc, s.h_e, rows, H, T_(h, theta, l.iW4), T_(h, theta, l.ib4), T_(h, theta, l.iW5),
+                          T_(h, theta, l.ib5), Z, L, la, src, s.mu, s.ls, s.eps, s.z, s.row_aux));
+  // decoder + log-likelihood, VAEB.py:253-265,302-313
+  VAEB_LAUNCH(launch_dense_act(st, lc, s.z, R, Z, T_(h, theta, l.iW1), T_(h, theta, l.ib1), H, 1, s.h_d));
+  const float scale = w / (float)L;
+  const float* W6 = h->cont ? T_(h, theta, l.iW6) : nullptr;
+  const float* b6 = h->cont ? T_(h, theta, l.ib6) : nullptr;
+  VAEB_LAUNCH(launch_dec2_loglik(st, lc, h->cont, s.h_d, R, H, T_(h, theta, l.iW2), T_(h, theta, l.ib2), W6, b6, D, x,
+                                 1, rows, scale, want_grads ? s.da2 : nullptr, want_grads ? s.dlv : nullptr,
+                                 s.partial, n_tiles));
+  if (!want_grads) return VAEB_OK;
+  // backward (T.grad, VAEB.py:397); formulas in SURVEY.md 8a
+  VAEB_LAUNCH(launch_wgrad(st, lc, s.h_d, R, H, s.da2, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2)));
+  if (h->cont) VAEB_LAUNCH(launch_wgrad(st, lc, s.h_d, R, H, s.dlv, D, T_(h, grads, l.iW6), T_(h, grads, l.ib6)));
+  VAEB_LAUNCH(launch_dgrad_tanh(st, lc, s.da2, T_(h, theta, l.iW2), h->cont ? s.dlv : nullptr, W6, R, D, H, s.h_d,
+                                s.da1));
+  VAEB_LAUNCH(launch_wgrad(st, lc, s.z, R, Z, s.da1, H, T_(h, grads, l.iW1), T_(h, grads, l.ib1)));
+  VAEB_LAUNCH(launch_dgrad(st, lc, s.da1, T_(h, theta, l.iW1), R, H, Z, s.dz));
+  VAEB_LAUNCH(launch_dprep(st, lc, s.dz, s.z, s.eps, s.mu, s.ls, rows, Z, L, la, w, s.dmu, s.dls));
+  VAEB_LAUNCH(launch_wgrad(st, lc, s.h_e, rows, H, s.dmu, Z, T_(h, grads, l.iW4), T_(h, grads, l.ib4)));
+  VAEB_LAUNCH(launch_wgrad(st, lc, s.h_e, rows, H, s.dls, Z, T_(h, grads, l.iW5), T_(h, grads, l.ib5)));
+  VAEB_LAUNCH(launch_dgrad_tanh(st, lc, s.dmu, T_(h, theta, l.iW4), s.dls, T_(h, theta, l.iW5), rows, Z, H, s.h_e,
+                                s.da3));
+  VAEB_LAUNCH(launch_wgrad(st, lc, x, rows, D, s.da3, H, T_(h, grads, l.iW3), T_(h, grads, l.ib3)));
+  return VAEB_OK;
+}
+
+int ensure_scalars(vaeb_handle* h, int n) {
+  if (n <= h->scalars_cap) return VAEB_OK;
+  VAEB_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->d_scalars) VAEB_CUDA(cudaFree(h->d_scalars));
+  if (h->h_scalars) VAEB_CUDA(cudaFreeHost(h->h_scalars));
+  VAEB_CUDA(cudaMalloc((void**)&h->d_scalars, (size_t)n * sizeof(float)));
+  VAEB_CUDA(cudaMallocHost((void**)&h->h_scalars, (size_t)n * sizeof(float)));
+  h->scalars_cap = n;
+  return VAEB_OK;
+}
+
+int stage_in(vaeb_handle* h, float** dbuf, int64_t* cap, const float* host, int64_t n) {
+  VAEB_TRY(grow(dbuf, cap, n));
+  VAEB_CUDA(cudaMemcpyAsync(*dbuf, host, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  return VAEB_OK;
+}
+
+int all_reduce_grads(vaeb_handle* h) {
+  if (h->world <= 1) return VAEB_OK;
+  const int r = h->nccl.AllReduce(h->d_grads, h->d_grads, (size_t)(h->lay.padded + 4), /*ncclFloat32*/ 7,
+                                  /*ncclSum*/ 0, h->comm, h->stream);
+  if (r != 0) {
+    vaeb_set_error(std::string("ncclAllReduce: ") + (h->nccl.GetErrorString ? h->nccl.GetErrorString(r) : "?"));
+    return VAEB_ENCCL;
+  }
+  return VAEB_OK;
+}
+
+// One update on device-resident rows; the scalar lands in d_scalars[slot].
+int enqueue_update(vaeb_handle* h, const float* d_xrows, int rows, const float* d_eps, const float* d_zeta,
+                   int slot, bool apply) {
+  const Layout& l = h->lay;
+  const int L = h->L;
+  VAEB_TRY(ensure_ws(h, rows, (int64_t)rows * L, true));
+  EpsSource src{d_eps, h->cfg.seed, VAEB_STREAM_TRAIN, h->step, (int64_t)h->rank * rows};
+  cudaStream_t st = h->stream;
+  int64_t* lc = &h->launches;
+  int tiles = 0;
+  float* base = h->d_grads + l.padded;
+  const int64_t n4 = l.padded / 4;
+  const float Mg = (float)rows * (float)h->world;
+  if (!is_fvb(h)) {
+    const bool fb = h->cfg.variant == VAEB_VARIANT_FULLBAYES;
+    const float w = fb ? 1.0f / Mg : 1.0f;
+    VAEB_TRY(forward_backward(h, h->d_params, d_xrows, rows, L, true, w, src, h->d_grads, &tiles));
+    VAEB_LAUNCH(launch_finalize(st, lc, h->ws.partial, tiles, h->ws.row_aux, rows, L, h->ws.per_row, base, 1.0f,
+                                nullptr, 0, Mg, nullptr));
+    VAEB_TRY(all_reduce_grads(h));
+    const float prior = fb ? 0.f : h->cfg.prior_scale;
+    if (apply) {
+      VAEB_LAUNCH(launch_adagrad(st, lc, h->d_params, h->d_ada, h->d_grads, n4, h->cfg.learning_rate,
+                                 h->cfg.adagrad_eps, prior, fb ? h->cfg.learning_rate * 1e-6f : 0.f, base, 1.0f, Mg,
+                                 h->d_scalars + slot));
+      h->grads_have_prior = false;
+    } else {
+      VAEB_LAUNCH(launch_add_prior(st, lc, h->d_grads, h->d_params, n4, prior, base, 1.0f, Mg, h->d_scalars + slot));
+      h->grads_have_prior = true;
+    }
+  } else {
+    VAEB_REQUIRE(h->world == 1, "full-VB estimators are single-GPU (replicas only)");
+    const bool sampled = h->cfg.estimator == VAEB_EST_FVB_SAMPLED;
+    const float* theta = h->d_params;  // VAEB.py:119,352: frozen MAP parameters, weights never sampled
+    if (sampled) {
+      VAEB_LAUNCH(launch_sample_theta(st, lc, h->d_vmu, h->d_vsig, d_zeta, h->cfg.seed, h->step, l.total, h->d_theta,
+                                      h->d_zeta));
+      theta = h->d_theta;
+    }
+    VAEB_LAUNCH(launch_theta_prior(st, lc, h->d_vmu, h->d_vsig, l.total, h->d_tprior));
+    VAEB_TRY(forward_backward(h, theta, d_xrows, rows, L, sampled, (float)rows, src, h->d_grads, &tiles));
+    // SGVB = x.shape[0]*(sum logp + sum KL) + thetaPrior (VAEB.py:364); update returns SGVB/M
+    VAEB_LAUNCH(launch_finalize(st, lc, h->ws.partial, tiles, h->ws.row_aux, rows, L, h->ws.per_row, base,
+                                (float)rows, h->d_tprior, VAEB_TP_BLOCKS, apply ? (float)rows : 1.0f,
+                                h->d_scalars + slot));
+    VAEB_LAUNCH(launch_fvb_adagrad(st, lc, h->d_vmu, h->d_vsig, h->d_ada_mu, h->d_ada_sig, h->d_grads, h->d_zeta,
+                                   sampled ? 1 : 0, l.total, h->cfg.learning_rate, h->cfg.adagrad_eps,
+                                   h->cfg.prior_scale, h->d_gmu, h->d_gsig, apply ? 1 : 0));
+  }
+  ++h->step;
+  return VAEB_OK;
+}
+
+int read_scalars(vaeb_handle* h, int n, float* out) {
+  VAEB_CUDA(cudaMemcpyAsync(h->h_scalars, h->d_scalars, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  VAEB_CUDA(cudaStreamSynchronize(h->stream));
+  std::memcpy(out, h->h_scalars, (size_t)n * sizeof(float));
+  return VAEB_OK;
+}
+
+float* flat_by_which(vaeb_handle* h, int which) {
+  switch (which) {
+    case 0: return h->d_params;
+    case 1: return h->d_ada;
+    case 2: return h->d_grads;
+    case 3: return h->d_vmu;
+    case 4: return h->d_vsig;
+    case 5: return h->d_ada_mu;
+    case 6: return h->d_ada_sig;
+    case 7: return h->d_gmu;
+    case 8: return h->d_gsig;
+    default: return nullptr;
+  }
+}
+
+int load_nccl(NcclApi& api, const char* path) {
+  if (api.lib) return VAEB_OK;
+  api.lib = dlopen(path && path[0] ? path : "libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!api.lib) { vaeb_set_error(std::string("dlopen nccl: ") + dlerror()); return VAEB_ENCCL; }
+  api.GetUniqueId = (int (*)(void*))dlsym(api.lib, "ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(api.lib, "ncclCommInitRank");
+  api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+  api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
+  api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) {
+    vaeb_set_error("nccl library lacks a required symbol");
+    return VAEB_ENCCL;
+  }
+  return VAEB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vaeb_last_error(void) { return g_last_error.c_str(); }
+int vaeb_version(void) { return 100; }
+
+int vaeb_create(const vaeb_config* cfg, vaeb_handle** out) {
+  VAEB_REQUIRE(cfg && out, "null argument");
+  VAEB_REQUIRE(cfg->input_dim > 0 && cfg->hidden_units > 0 && cfg->latent_size > 0, "dimensions must be positive");
+  VAEB_REQUIRE(cfg->batch_size > 0 && cfg->L > 0, "batch_size and L must be positive");
+  VAEB_REQUIRE(cfg->estimator >= 0 && cfg->estimator <= 3, "unknown estimator");
+  VAEB_REQUIRE(cfg->variant == 0 || cfg->variant == 1, "unknown variant");
+  VAEB_REQUIRE(cfg->precision == VAEB_PREC_FP32 || cfg->precision == VAEB_PREC_BF16, "unknown precision");
+  const bool fvb = cfg->estimator >= VAEB_EST_FVB;
+  // getFVBL overwrites `mu` inside the sample loop (VAEB.py:361): undefined for L > 1
+  VAEB_REQUIRE(!(fvb && cfg->L != 1), "full-VB bound is only defined for L == 1 (VAEB.py:361)");
+  VAEB_REQUIRE(!(fvb && cfg->variant != VAEB_VARIANT_VAEB), "full-VB exists only in VAEB.py");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    vaeb_set_error(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)");
+    return VAEB_ECUDA;
+  }
+  VAEB_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "device ordinal out of range");
+  VAEB_CUDA(cudaSetDevice(cfg->device));
+  vaeb_handle* h = new vaeb_handle();
+  h->cfg = *cfg;
+  h->D = cfg->input_dim; h->H = cfg->hidden_units; h->Z = cfg->latent_size; h->M = cfg->batch_size; h->L = cfg->L;
+  h->cont = cfg->continuous != 0;
+  build_layout(h->lay, h->D, h->H, h->Z, h->cont);
+  VAEB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  const int64_t n = h->lay.padded + 4;
+  VAEB_TRY(alloc_flat(&h->d_params, n));
+  VAEB_TRY(alloc_flat(&h->d_ada, n));
+  VAEB_TRY(alloc_flat(&h->d_grads, n));
+  if (fvb) {
+    VAEB_TRY(alloc_flat(&h->d_vmu, n));
+    VAEB_TRY(alloc_flat(&h->d_vsig, n, cfg->sigma_vb_init));
+    VAEB_TRY(alloc_flat(&h->d_ada_mu, n));
+    VAEB_TRY(alloc_flat(&h->d_ada_sig, n));
+    VAEB_TRY(alloc_flat(&h->d_gmu, n));
+    VAEB_TRY(alloc_flat(&h->d_gsig, n));
+    VAEB_TRY(alloc_flat(&h->d_theta, n));
+    VAEB_TRY(alloc_flat(&h->d_zeta, n));
+    VAEB_TRY(alloc_flat(&h->d_tprior, VAEB_TP_BLOCKS));
+  }
+  VAEB_TRY(ensure_scalars(h, 1024));
+  *out = h;
+  return VAEB_OK;
+}
+
+int vaeb_destroy(vaeb_handle* h) {
+  if (!h) return VAEB_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
+  free_ws(h->ws);
+  float* bufs[] = {h->d_params, h->d_ada, h->d_grads, h->d_vmu, h->d_vsig, h->d_ada_mu, h->d_ada_sig, h->d_gmu,
+                   h->d_gsig, h->d_theta, h->d_zeta, h->d_tprior, h->d_x, h->d_stage, h->d_stage2, h->d_out,
+                   h->d_scalars};
+  for (float* p : bufs) if (p) cudaFree(p);
+  if (h->h_scalars) cudaFreeHost(h->h_scalars);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return VAEB_OK;
+}
+
+int vaeb_set_stream(vaeb_handle* h, void* cuda_stream) {
+  VAEB_REQUIRE(h, "null handle");
+  VAEB_CUDA(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return VAEB_OK;
+}
+
+int vaeb_synchronize(vaeb_handle* h) {
+  VAEB_REQUIRE(h, "null handle");
+  VAEB_CUDA(cudaStreamSynchronize(h->stream));
+  return VAEB_OK;
+}
+
+int vaeb_num_tensors(vaeb_handle* h, int32_t* n_tensors, int64_t* n_elements) {
+  VAEB_REQUIRE(h, "null handle");
+  if (n_tensors) *n_tensors = h->lay.n;
+  if (n_elements) *n_elements = h->lay.total;
+  return VAEB_OK;
+}
+
+int vaeb_tensor_shape(vaeb_handle* h, int32_t i, int32_t* rows, int32_t* cols) {
+  VAEB_REQUIRE(h && i >= 0 && i < h->lay.n, "tensor index out of range");
+  if (rows) *rows = h->lay.rows[i];
+  if (cols) *cols = h->lay.cols[i];
+  return VAEB_OK;
+}
+
+int vaeb_set_tensors(vaeb_handle* h, int32_t which, const float* const* tensors) {
+  VAEB_REQUIRE(h && tensors, "null argument");
+  float* flat = flat_by_which(h, which);
+  VAEB_REQUIRE(flat, "buffer not available for this estimator");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  for (int t = 0; t < h->lay.n; ++t) {
+    const size_t n = (size_t)h->lay.rows[t] * h->lay.cols[t];
+    VAEB_CUDA(cudaMemcpyAsync(flat + h->lay.off[t], tensors[t], n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  }
+  VAEB_CUDA(cudaStreamSynchronize(h->stream));
+  return VAEB_OK;
+}
+
+int vaeb_get_tensors(vaeb_handle* h, int32_t which, float* const* tensors) {
+  VAEB_REQUIRE(h && tensors, "null argument");
+  float* flat = flat_by_which(h, which);
+  VAEB_REQUIRE(flat, "buffer not available for this estimator");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  for (int t = 0; t < h->lay.n; ++t) {
+    const size_t n = (size_t)h->lay.rows[t] * h->lay.cols[t];
+    VAEB_CUDA(cudaMemcpyAsync(tensors[t], flat + h->lay.off[t], n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  }
+  VAEB_CUDA(cudaStreamSynchronize(h->stream));
+  return VAEB_OK;
+}
+
+int vaeb_device_buffer(vaeb_handle* h, int32_t which, void** d_ptr, int64_t* n_elements) {
+  VAEB_REQUIRE(h && d_ptr, "null argument");
+  float* flat = flat_by_which(h, which);
+  VAEB_REQUIRE(flat, "buffer not available for this estimator");
+  *d_ptr = flat;
+  if (n_elements) *n_elements = h->lay.padded;
+  return VAEB_OK;
+}
+
+int vaeb_upload_data(vaeb_handle* h, const float* x, int64_t n_rows) {
+  VAEB_REQUIRE(h && x && n_rows > 0, "null data or no rows");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  VAEB_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->d_x) VAEB_CUDA(cudaFree(h->d_x));
+  h->d_x = nullptr;
+  const size_t bytes = (size_t)n_rows * h->D * sizeof(float);
+  VAEB_CUDA(cudaMalloc((void**)&h->d_x, bytes));
+  VAEB_CUDA(cudaMemcpy(h->d_x, x, bytes, cudaMemcpyHostToDevice));
+  h->n_data = n_rows;
+  return VAEB_OK;
+}
+
+static int stage_eps_zeta(vaeb_handle* h, const float* eps, int64_t n_eps, const float** d_eps) {
+  *d_eps = nullptr;
+  if (eps) { VAEB_TRY(stage_in(h, &h->d_stage2, &h->stage2_cap, eps, n_eps)); *d_eps = h->d_stage2; }
+  return VAEB_OK;
+}
+
+int vaeb_update(vaeb_handle* h, int64_t index, const float* eps, float* elbo_out) {
+  VAEB_REQUIRE(h && elbo_out, "null argument");
+  if (!h->d_x) { vaeb_set_error("vaeb_update before vaeb_upload_data"); return VAEB_ESTATE; }
+  VAEB_REQUIRE(index >= 0 && (index + 1) * (int64_t)h->M <= h->n_data, "batch index outside the resident data");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  const float* d_eps;
+  VAEB_TRY(stage_eps_zeta(h, eps, (int64_t)h->L * h->M * h->Z, &d_eps));
+  VAEB_TRY(enqueue_update(h, h->d_x + (size_t)index * h->M * h->D, h->M, d_eps, nullptr, 0, true));
+  return read_scalars(h, 1, elbo_out);
+}
+
+int vaeb_update_host(vaeb_handle* h, const float* x, int64_t rows, const float* eps, float* elbo_out) {
+  VAEB_REQUIRE(h && x && elbo_out && rows > 0, "null argument");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  VAEB_TRY(stage_in(h, &h->d_stage, &h->stage_cap, x, rows * h->D));
+  const float* d_eps;
+  VAEB_TRY(stage_eps_zeta(h, eps, (int64_t)h->L * rows * h->Z, &d_eps));
+  VAEB_TRY(enqueue_update(h, h->d_stage, (int)rows, d_eps, nullptr, 0, true));
+  return read_scalars(h, 1, elbo_out);
+}
+
+int vaeb_update_many(vaeb_handle* h, const int32_t* batch_order, int32_t n, float* elbo_out) {
+  VAEB_REQUIRE(h && batch_order && elbo_out && n > 0, "null argument");
+  if (!h->d_x) { vaeb_set_error("vaeb_update_many before vaeb_upload_data"); return VAEB_ESTATE; }
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  VAEB_TRY(ensure_scalars(h, n));
+  for (int i = 0; i < n; ++i) {
+    const int64_t index = batch_order[i];
+    VAEB_REQUIRE(index >= 0 && (index + 1) * (int64_t)h->M <= h->n_data, "batch index outside the resident data");
+    VAEB_TRY(enqueue_update(h, h->d_x + (size_t)index * h->M * h->D, h->M, nullptr, nullptr, i, true));
+  }
+  return read_scalars(h, n, elbo_out);
+}
+
+int vaeb_gradients(vaeb_handle* h, const float* x, int64_t rows, int64_t index, const float* eps, const float* zeta,
+                   float* sgvb_out, float* per_row_out) {
+  VAEB_REQUIRE(h && rows > 0, "null argument");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  const float* d_x;
+  if (x) {
+    VAEB_TRY(stage_in(h, &h->d_stage, &h->stage_cap, x, rows * h->D));
+    d_x = h->d_stage;
+  } else {
+    if (!h->d_x) { vaeb_set_error("vaeb_gradients(x=NULL) before vaeb_upload_data"); return VAEB_ESTATE; }
+    VAEB_REQUIRE(index >= 0 && index * (int64_t)h->M + rows <= h->n_data, "rows outside the resident data");
+    d_x = h->d_x + (size_t)index * h->M * h->D;
+  }
+  const float* d_eps;
+  VAEB_TRY(stage_eps_zeta(h, eps, (int64_t)h->L * rows * h->Z, &d_eps));
+  const float* d_zeta = nullptr;
+  if (zeta) {
+    // the flat zeta (tightly packed, reference tensor order) is staged in d_out
+    VAEB_TRY(grow(&h->d_out, &h->out_cap, h->lay.padded));
+    VAEB_CUDA(cudaMemcpyAsync(h->d_out, zeta, (size_t)h->lay.total * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    d_zeta = h->d_out;
+  }
+  VAEB_TRY(enqueue_update(h, d_x, (int)rows, d_eps, d_zeta, 0, false));
+  // slot 0 holds base/Mg (non-FVB: written by finalize when !apply) or the SGVB (FVB)
+  float v = 0.f;
+  VAEB_TRY(read_scalars(h, 1, &v));
+  if (sgvb_out) {
+    if (is_fvb(h)) *sgvb_out = v;
+    else if (h->cfg.variant == VAEB_VARIANT_FULLBAYES) *sgvb_out = v;          // the mean objective
+    else *sgvb_out = v * (float)rows * (float)h->world;                       // back to the sum
+  }
+  if (per_row_out) {
+    VAEB_CUDA(cudaMemcpy(per_row_out, h->ws.per_row, (size_t)rows * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  return VAEB_OK;
+}
+
+int vaeb_apply_update(vaeb_handle* h) {
+  VAEB_REQUIRE(h, "null handle");
+  VAEB_REQUIRE(!is_fvb(h), "vaeb_apply_update: use vaeb_update for the full-VB estimators");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  const bool fb = h->cfg.variant == VAEB_VARIANT_FULLBAYES;
+  const float prior = (fb || h->grads_have_prior) ? 0.f : h->cfg.prior_scale;
+  VAEB_LAUNCH(launch_adagrad(h->stream, &h->launches, h->d_params, h->d_ada, h->d_grads, h->lay.padded / 4,
+                             h->cfg.learning_rate, h->cfg.adagrad_eps, prior,
+                             fb ? h->cfg.learning_rate * 1e-6f : 0.f, h->d_grads + h->lay.padded, 1.f, 1.f, nullptr));
+  VAEB_CUDA(cudaStreamSynchronize(h->stream));
+  return VAEB_OK;
+}
+
+int vaeb_validate(vaeb_handle* h, const float* x, int64_t n, const float* eps, float* sgvb_out, float* per_row_out) {
+  VAEB_REQUIRE(h && x && sgvb_out && n > 0, "null argument");
+  VAEB_REQUIRE(n * (int64_t)h->L < (int64_t)1 << 31, "too many rows for one validate call");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  const int L = h->L;
+  VAEB_TRY(ensure_ws(h, n, n * L, false));
+  VAEB_TRY(stage_in(h, &h->d_stage, &h->stage_cap, x, n * h->D));
+  const float* d_eps;
+  VAEB_TRY(stage_eps_zeta(h, eps, (int64_t)L * n * h->Z, &d_eps));
+  // validate shares the eps stream with update in the reference (VAEB.py:158); here it
+  // draws from its own Philox stream keyed by the same step counter
+  EpsSource src{d_eps, h->cfg.seed, VAEB_STREAM_EVAL, h->step, 0};
+  int tiles = 0;
+  const float* theta = h->d_params;
+  float mult = 1.f, div = 1.f;
+  const float* tp = nullptr;
+  if (is_fvb(h)) {
+    if (h->cfg.estimator == VAEB_EST_FVB_SAMPLED) {
+      VAEB_LAUNCH(launch_sample_theta(h->stream, &h->launches, h->d_vmu, h->d_vsig, nullptr, h->cfg.seed, h->step,
+                                      h->lay.total, h->d_theta, h->d_zeta));
+      theta = h->d_theta;
+    }
+    VAEB_LAUNCH(launch_theta_prior(h->stream, &h->launches, h->d_vmu, h->d_vsig, h->lay.total, h->d_tprior));
+    mult = (float)n;                     // x.shape[0], VAEB.py:364
+    tp = h->d_tprior;
+  } else if (h->cfg.variant == VAEB_VARIANT_FULLBAYES) {
+    div = (float)n;                      // T.mean, VAEBfullbayes.py:142
+  }
+  VAEB_TRY(forward_backward(h, theta, h->d_stage, (int)n, L, false, 1.f, src, nullptr, &tiles));
+  VAEB_LAUNCH(launch_finalize(h->stream, &h->launches, h->ws.partial, tiles, h->ws.row_aux, (int)n, L, h->ws.per_row,
+                              h->d_grads + h->lay.padded, mult, tp, VAEB_TP_BLOCKS, div, h->d_scalars));
+  ++h->step;
+  VAEB_TRY(read_scalars(h, 1, sgvb_out));
+  if (per_row_out)
+    VAEB_CUDA(cudaMemcpy(per_row_out, h->ws.per_row, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  return VAEB_OK;
+}
+
+int vaeb_is_logpx(vaeb_handle* h, const float* x, int64_t n, int32_t L, const float* eps, int64_t row_offset,
+                  float* logpx_out, float* logw_out) {
+  VAEB_REQUIRE(h && x && logpx_out && n > 0 && L > 0, "null argument");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  const Layout& l = h->lay;
+  const int D = h->D, H = h->H, Z = h->Z;
+  const int64_t chunk_rows = (int64_t)1 << 17;
+  const int pc = (int)std::max<int64_t>(1, std::min<int64_t>(n, chunk_rows / L));   // points per chunk
+  VAEB_REQUIRE((int64_t)pc * L < (int64_t)1 << 31, "L too large");
+  VAEB_TRY(ensure_ws(h, pc, (int64_t)pc * L, false));
+  VAEB_TRY(grow(&h->d_out, &h->out_cap, pc));
+  cudaStream_t st = h->stream;
+  int64_t* lc = &h->launches;
+  const float* th = h->d_params;
+  std::vector<float> tmp;
+  for (int64_t i0 = 0; i0 < n; i0 += pc) {
+    const int c = (int)std::min<int64_t>(pc, n - i0);
+    const int R = c * L;
+    VAEB_TRY(stage_in(h, &h->d_stage, &h->stage_cap, x + i0 * D, (int64_t)c * D));
+    const float* d_eps = nullptr;
+    if (eps) { VAEB_TRY(stage_in(h, &h->d_stage2, &h->stage2_cap, eps + i0 * L * Z, (int64_t)R * Z)); d_eps = h->d_stage2; }
+    EpsSource src{d_eps, h->cfg.seed, VAEB_STREAM_IS, 0u, row_offset + i0};
+    Workspace& s = h->ws;
+    VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage, c, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, 1, s.h_e));
+    VAEB_LAUNCH(launch_enc2(st, lc, s.h_e, c, H, T_(h, th, l.iW4), T_(h, th, l.ib4), T_(h, th, l.iW5),
+                            T_(h, th, l.ib5), Z, 0, 0, src, s.mu, s.ls, s.eps, s.z, s.row_aux));
+    VAEB_LAUNCH(launch_is_sample(st, lc, s.mu, s.ls, c, L, Z, src, s.z, s.dec_aux));
+    VAEB_LAUNCH(launch_dense_act(st, lc, s.z, R, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, 1, s.h_d));
+    int tiles = 0;
+    VAEB_LAUNCH(launch_dec2_loglik(st, lc, h->cont, s.h_d, R, H, T_(h, th, l.iW2), T_(h, th, l.ib2),
+                                   h->cont ? T_(h, th, l.iW6) : nullptr, h->cont ? T_(h, th, l.ib6) : nullptr, D,
+                                   h->d_stage, L, c, 1.f, nullptr, nullptr, s.partial, &tiles));
+    VAEB_LAUNCH(launch_is_reduce(st, lc, s.partial, tiles, s.dec_aux, c, L, s.logw, h->d_out));
+    VAEB_CUDA(cudaMemcpyAsync(logpx_out + i0, h->d_out, (size_t)c * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (logw_out)
+      VAEB_CUDA(cudaMemcpyAsync(logw_out + i0 * L, s.logw, (size_t)R * sizeof(float), cudaMemcpyDeviceToHost, st));
+    VAEB_CUDA(cudaStreamSynchronize(st));
+  }
+  return VAEB_OK;
+}
+
+int vaeb_reconstruct(vaeb_handle* h, const float* x, int64_t n, int32_t n_samples, const float* eps, float* y_out,
+                     float* lv_out) {
+  VAEB_REQUIRE(h && x && y_out && n > 0, "null argument");
+  VAEB_REQUIRE(!h->cont || lv_out, "the Gaussian decoder also returns its log-variance output");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  const Layout& l = h->lay;
+  const int D = h->D, H = h->H, Z = h->Z;
+  VAEB_TRY(ensure_ws(h, n, n, false));
+  VAEB_TRY(stage_in(h, &h->d_stage, &h->stage_cap, x, n * D));
+  const int ns = std::max(n_samples, 0);
+  const float* d_eps = nullptr;
+  if (eps && ns > 0) { VAEB_TRY(stage_in(h, &h->d_stage2, &h->stage2_cap, eps, (int64_t)ns * n * Z)); d_eps = h->d_stage2; }
+  VAEB_TRY(grow(&h->d_out, &h->out_cap, 2 * n * D));
+  float* d_y = h->d_out;
+  float* d_lv = h->d_out + n * D;
+  cudaStream_t st = h->stream;
+  int64_t* lc = &h->launches;
+  const float* th = h->d_params;
+  Workspace& s = h->ws;
+  EpsSource src{d_eps, h->cfg.seed, VAEB_STREAM_RECON, h->step, 0};
+  VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage, (int)n, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, 1, s.h_e));
+  VAEB_LAUNCH(launch_enc2(st, lc, s.h_e, (int)n, H, T_(h, th, l.iW4), T_(h, th, l.ib4), T_(h, th, l.iW5),
+                          T_(h, th, l.ib5), Z, 0, 0, src, s.mu, s.ls, s.eps, s.z, s.row_aux));
+  const float* W6 = h->cont ? T_(h, th, l.iW6) : nullptr;
+  const float* b6 = h->cont ? T_(h, th, l.ib6) : nullptr;
+  const int passes = std::max(ns, 1);
+  for (int sidx = 0; sidx < passes; ++sidx) {
+    const float* zin = s.mu;                                  // n_samples <= 0: decode mu (VAEB.py:269-270)
+    if (ns > 0) {
+      VAEB_LAUNCH(launch_recon_sample(st, lc, s.mu, s.ls, (int)n, Z, src, sidx, (int)n, s.z));
+      zin = s.z;
+    }
+    VAEB_LAUNCH(launch_dense_act(st, lc, zin, (int)n, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, 1, s.h_d));
+    VAEB_LAUNCH(launch_dec2_recon(st, lc, h->cont, s.h_d, (int)n, H, T_(h, th, l.iW2), T_(h, th, l.ib2), W6, b6, D,
+                                  d_y, d_lv, 1.0f / (float)passes, sidx == 0));
+  }
+  ++h->step;
+  VAEB_CUDA(cudaMemcpyAsync(y_out, d_y, (size_t)n * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (h->cont)
+    VAEB_CUDA(cudaMemcpyAsync(lv_out, d_lv, (size_t)n * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+  VAEB_CUDA(cudaStreamSynchronize(st));
+  return VAEB_OK;
+}
+
+int vaeb_mlp_forward(vaeb_handle* h, const float* x, int64_t n, int32_t n_layers, const int32_t* dims,
+                     const float* const* W, const float* const* b, int32_t act_last, float* out) {
+  VAEB_REQUIRE(h && x && dims && W && b && out && n > 0 && n_layers > 0, "null argument");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  int maxd = 0;
+  int64_t wtot = 0;
+  for (int i = 0; i <= n_layers; ++i) maxd = std::max(maxd, dims[i]);
+  for (int i = 0; i < n_layers; ++i) wtot += (int64_t)dims[i] * dims[i + 1] + dims[i + 1];
+  float *d_a = nullptr, *d_b = nullptr, *d_w = nullptr;
+  VAEB_CUDA(cudaMalloc((void**)&d_a, (size_t)n * maxd * sizeof(float)));
+  VAEB_CUDA(cudaMalloc((void**)&d_b, (size_t)n * maxd * sizeof(float)));
+  VAEB_CUDA(cudaMalloc((void**)&d_w, (size_t)wtot * sizeof(float)));
+  int rc = VAEB_OK;
+  do {
+    if (cudaMemcpyAsync(d_a, x, (size_t)n * dims[0] * sizeof(float), cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { rc = VAEB_ECUDA; break; }
+    int64_t o = 0;
+    float* cur = d_a; float* nxt = d_b;
+    for (int i = 0; i < n_layers && rc == VAEB_OK; ++i) {
+      const int64_t nw = (int64_t)dims[i] * dims[i + 1];
+      cudaMemcpyAsync(d_w + o, W[i], (size_t)nw * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+      cudaMemcpyAsync(d_w + o + nw, b[i], (size_t)dims[i + 1] * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+      const int act = (i + 1 < n_layers) ? 1 : act_last;
+      if (launch_dense_act(h->stream, &h->launches, cur, (int)n, dims[i], d_w + o, d_w + o + nw, dims[i + 1], act, nxt) != cudaSuccess) { rc = VAEB_ECUDA; break; }
+      o += nw + dims[i + 1];
+      std::swap(cur, nxt);
+    }
+    if (rc != VAEB_OK) break;
+    if (cudaMemcpyAsync(out, cur, (size_t)n * dims[n_layers] * sizeof(float), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { rc = VAEB_ECUDA; break; }
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) rc = VAEB_ECUDA;
+  } while (0);
+  if (rc != VAEB_OK) vaeb_set_error(std::string("vaeb_mlp_forward: ") + cudaGetErrorString(cudaGetLastError()));
+  cudaFree(d_a); cudaFree(d_b); cudaFree(d_w);
+  return rc;
+}
+
+int vaeb_philox_normal(vaeb_handle* h, int32_t stream, uint32_t step, uint32_t sample, int64_t first_elem, int64_t n,
+                       float* out) {
+  VAEB_REQUIRE(h && out && n > 0, "null argument");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  VAEB_TRY(grow(&h->d_out, &h->out_cap, n));
+  VAEB_LAUNCH(launch_philox_fill(h->stream, &h->launches, h->cfg.seed, (uint32_t)stream, step, sample, first_elem, n,
+                                 h->d_out));
+  VAEB_CUDA(cudaMemcpyAsync(out, h->d_out, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  VAEB_CUDA(cudaStreamSynchronize(h->stream));
+  return VAEB_OK;
+}
+
+int vaeb_set_step_counter(vaeb_handle* h, uint32_t step) {
+  VAEB_REQUIRE(h, "null handle");
+  h->step = step;
+  return VAEB_OK;
+}
+
+int vaeb_comm_unique_id(const char* nccl_library, uint8_t id_out[128]) {
+  VAEB_REQUIRE(id_out, "null argument");
+  static NcclApi api;
+  VAEB_TRY(load_nccl(api, nccl_library));
+  NcclId id;
+  std::memset(&id, 0, sizeof(id));
+  const int r = api.GetUniqueId(&id);
+  if (r != 0) { vaeb_set_error(std::string("ncclGetUniqueId: ") + (api.GetErrorString ? api.GetErrorString(r) : "?")); return VAEB_ENCCL; }
+  std::memcpy(id_out, &id, 128);
+  return VAEB_OK;
+}
+
+int vaeb_comm_attach(vaeb_handle* h, const char* nccl_library, const uint8_t id[128], int32_t rank,
+                     int32_t world_size) {
+  VAEB_REQUIRE(h && id && world_size >= 1 && rank >= 0 && rank < world_size, "bad communicator arguments");
+  VAEB_REQUIRE(!is_fvb(h), "full-VB estimators are single-GPU (replicas only)");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  VAEB_TRY(load_nccl(h->nccl, nccl_library));
+  NcclId nid;
+  std::memcpy(&nid, id, 128);
+  const int r = h->nccl.CommInitRank(&h->comm, world_size, nid, rank);
+  if (r != 0) {
+    vaeb_set_error(std::string("ncclCommInitRank: ") + (h->nccl.GetErrorString ? h->nccl.GetErrorString(r) : "?"));
+    return VAEB_ENCCL;
+  }
+  h->rank = rank;
+  h->world = world_size;
+  return VAEB_OK;
+}
+
+int vaeb_comm_detach(vaeb_handle* h) {
+  VAEB_REQUIRE(h, "null handle");
+  if (h->comm) {
+    VAEB_CUDA(cudaStreamSynchronize(h->stream));
+    h->nccl.CommDestroy(h->comm);
+    h->comm = nullptr;
+  }
+  h->rank = 0;
+  h->world = 1;
+  return VAEB_OK;
+}
+
+int vaeb_launch_count(vaeb_handle* h, int64_t* n_launches) {
+  VAEB_REQUIRE(h && n_launches, "null argument");
+  *n_launches = h->launches;
+  return VAEB_OK;
+}
+
+}  // extern "C"

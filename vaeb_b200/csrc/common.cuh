@@ -1,0 +1,91 @@
+// Handle, flat-buffer layout and error plumbing shared by the translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/vaeb_b200.h"
+
+void vaeb_set_error(const std::string& msg);
+
+#define VAEB_CUDA(expr)                                                                      \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      vaeb_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                     ":" + std::to_string(__LINE__) + ")");                                  \
+      return VAEB_ECUDA;                                                                     \
+    }                                                                                        \
+  } while (0)
+
+#define VAEB_TRY(expr)            \
+  do {                            \
+    int _r = (expr);              \
+    if (_r != VAEB_OK) return _r; \
+  } while (0)
+
+#define VAEB_REQUIRE(cond, msg)                  \
+  do {                                           \
+    if (!(cond)) {                               \
+      vaeb_set_error(std::string("invalid argument: ") + (msg)); \
+      return VAEB_EINVAL;                        \
+    }                                            \
+  } while (0)
+
+// Tensor indices in the reference's list order (VAEB.py:111-115).
+struct Layout {
+  int n = 0;                 // 10 (Bernoulli) or 12 (Gaussian)
+  int rows[12], cols[12];
+  int64_t off[12];           // element offset inside the flat buffer (tightly packed)
+  int64_t total = 0;         // P
+  int64_t padded = 0;        // P rounded up to a multiple of 4 (float4 kernels)
+  int iW3, iW4, iW5, iW1, iW2, iW6, ib3, ib4, ib5, ib1, ib2, ib6;
+};
+
+// NCCL entry points resolved with dlopen (no link-time dependency; the host passes the path
+// of the libnccl.so.2 that torch bundles).
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId /* ncclUniqueId by value: 128 bytes */, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+struct Workspace {
+  int64_t cap_enc = 0, cap_dec = 0;   // rows the buffers hold (encoder rows, decoder rows)
+  bool with_grads = false;
+  float *h_e = nullptr, *mu = nullptr, *ls = nullptr, *eps = nullptr, *z = nullptr, *h_d = nullptr;
+  float *da2 = nullptr, *dlv = nullptr, *da1 = nullptr, *dz = nullptr, *dmu = nullptr, *dls = nullptr, *da3 = nullptr;
+  float *partial = nullptr, *row_aux = nullptr, *per_row = nullptr, *dec_aux = nullptr, *logw = nullptr;
+};
+
+struct vaeb_handle {
+  vaeb_config cfg;
+  int D, H, Z, M, L;
+  bool cont;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  Layout lay;
+  // flat buffers: [padded + 4]; slot [padded] of d_grads carries the bound for the all-reduce
+  float *d_params = nullptr, *d_ada = nullptr, *d_grads = nullptr;
+  float *d_vmu = nullptr, *d_vsig = nullptr, *d_ada_mu = nullptr, *d_ada_sig = nullptr;
+  float *d_gmu = nullptr, *d_gsig = nullptr, *d_theta = nullptr, *d_zeta = nullptr;
+  float* d_tprior = nullptr;          // [TP_BLOCKS] partial sums of thetaPrior
+  float* d_x = nullptr; int64_t n_data = 0;
+  Workspace ws;
+  float* d_stage = nullptr; int64_t stage_cap = 0;       // device staging for host inputs
+  float* d_stage2 = nullptr; int64_t stage2_cap = 0;     // eps staging
+  float* d_out = nullptr; int64_t out_cap = 0;           // device staging for outputs
+  float* d_scalars = nullptr; float* h_scalars = nullptr; int scalars_cap = 0;
+  float* h_pinned = nullptr; int64_t pinned_cap = 0;     // pinned bounce buffer for H2D of inputs
+  uint32_t step = 0;
+  int64_t launches = 0;
+  bool grads_have_prior = false;
+  // data parallel
+  NcclApi nccl; void* comm = nullptr; int rank = 0, world = 1;
+};
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -1,0 +1,82 @@
+// Host-side launchers of the fp32 kernels (implemented in kernels_gemm.cu / kernels_small.cu).
+// Every launcher enqueues on `st`, bumps *launches by the kernels it started and returns a
+// cudaError_t from cudaGetLastError().
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+// ---- dense layers (kernels_gemm.cu) ---------------------------------------------------
+// out[rows,N] = act(in[rows,K] . W[K,N] + b)          VAEB.py:246,254 ; mlp.py:66-74
+cudaError_t launch_dense_act(cudaStream_t st, int64_t* launches, const float* in, int rows, int K,
+                             const float* W, const float* b, int N, int act, float* out);
+// Decoder output layer fused with the log-likelihood (VAEB.py:257-263,302-313).
+// partial[rows, *n_col_tiles] receives per-tile row sums.  da (and dlv) == nullptr: eval.
+cudaError_t launch_dec2_loglik(cudaStream_t st, int64_t* launches, bool continuous, const float* h_d, int rows,
+                               int H, const float* W2, const float* b2, const float* W6, const float* b6, int D,
+                               const float* x, int x_div, int x_mod, float scale, float* da, float* dlv,
+                               float* partial, int* n_col_tiles);
+// reconstruct accumulation (VAEB.py:282-292)
+cudaError_t launch_dec2_recon(cudaStream_t st, int64_t* launches, bool continuous, const float* h_d, int rows,
+                              int H, const float* W2, const float* b2, const float* W6, const float* b6, int D,
+                              float* y, float* lv, float inv_n, int first);
+// gW[K,N] = in[rows,K]^T . d[rows,N], gb[N] = colsum(d)   (weight + bias gradient in one GEMM)
+cudaError_t launch_wgrad(cudaStream_t st, int64_t* launches, const float* in, int rows, int K, const float* d,
+                         int N, float* gW, float* gb);
+// out[rows,K] = (d[rows,N] . W[K,N]^T (+ d2 . W2^T)) * (1 - h^2)
+cudaError_t launch_dgrad_tanh(cudaStream_t st, int64_t* launches, const float* d, const float* W,
+                              const float* d2, const float* W2, int rows, int N, int K, const float* h, float* out);
+// out[rows,K] = d[rows,N] . W[K,N]^T
+cudaError_t launch_dgrad(cudaStream_t st, int64_t* launches, const float* d, const float* W, int rows, int N,
+                         int K, float* out);
+
+// ---- small fused kernels (kernels_small.cu) -----------------------------------------
+struct EpsSource {
+  const float* injected;   // device eps or nullptr
+  uint64_t seed; uint32_t stream; uint32_t step; int64_t row_offset;
+};
+// mu, ls = h_e.W4+b4, h_e.W5+b5 (VAEB.py:248-249); if L>0 also eps, z = mu+exp(.5 ls) eps
+// (VAEB.py:41-47) for l<L with rows laid out [L,rows,Z]; row_aux[rows] = KL row (VAEB.py:343)
+// for LB or (1/L) sum_l (log p(z) - log q(z|x)) (VAEB.py:322-325) for LA.
+cudaError_t launch_enc2(cudaStream_t st, int64_t* launches, const float* h_e, int rows, int H, const float* W4,
+                        const float* b4, const float* W5, const float* b5, int Z, int L, int la, EpsSource src,
+                        float* mu, float* ls, float* eps, float* z, float* row_aux);
+// importance-sampling rows r = i*L + l: eps, z and aux[r] = log p(z) - log q(z|x)
+cudaError_t launch_is_sample(cudaStream_t st, int64_t* launches, const float* mu, const float* ls, int n, int L,
+                             int Z, EpsSource src, float* z, float* aux);
+// reconstruct: z[rows,Z] = mu + exp(.5 ls) * eps(sample)
+cudaError_t launch_recon_sample(cudaStream_t st, int64_t* launches, const float* mu, const float* ls, int rows,
+                                int Z, EpsSource src, int sample, int n_rows_total, float* z);
+// encoder-side gradient assembly: dz[L,rows,Z] -> dmu, dls (SURVEY 8a backward formulas)
+cudaError_t launch_dprep(cudaStream_t st, int64_t* launches, const float* dz, const float* z, const float* eps,
+                         const float* mu, const float* ls, int rows, int Z, int L, int la, float w,
+                         float* dmu, float* dls);
+// per_row[m] = (1/L) sum_l sum_t partial[(l*rows+m), t] + row_aux[m]; base = sum_m per_row;
+// scalar_out (nullable) = (mult*base + sum(tprior[0..n_tprior)))/div
+cudaError_t launch_finalize(cudaStream_t st, int64_t* launches, const float* partial, int n_tiles,
+                            const float* row_aux, int rows, int L, float* per_row, float* base_out,
+                            float mult, const float* tprior, int n_tprior, float div, float* scalar_out);
+// logw[r] = sum_t partial[r,t] + aux[r];  logp[i] = logsumexp_l logw[i*L+l] - log L
+cudaError_t launch_is_reduce(cudaStream_t st, int64_t* launches, const float* partial, int n_tiles,
+                             const float* aux, int n, int L, float* logw, float* logp);
+// g -= prior*p  (VAEB.py:389-390); thread 0 also writes (mult*base)/div to scalar_out if non-null
+cudaError_t launch_add_prior(cudaStream_t st, int64_t* launches, float* g, const float* p, int64_t n4, float prior,
+                             const float* base, float mult, float div, float* scalar_out);
+// Adagrad (VAEB.py:426-444; VAEBfullbayes.py:183-184 with p2 = lr*1e-6) over the flat buffer.
+// If scalar_out != nullptr thread 0 also writes (mult*base + tprior)/div.
+cudaError_t launch_adagrad(cudaStream_t st, int64_t* launches, float* p, float* acc, const float* g, int64_t n4,
+                           float lr, float eps, float prior, float p2, const float* base, float mult, float div,
+                           float* scalar_out);
+#define VAEB_TP_BLOCKS 128
+// thetaPrior partials (VAEB.py:359-363) over n real elements
+cudaError_t launch_theta_prior(cudaStream_t st, int64_t* launches, const float* vmu, const float* vsig, int64_t n,
+                               float* partials);
+// theta = mu + |sigma| * zeta  (VAEB.py:127-129); zeta injected or Philox; zeta_out always written
+cudaError_t launch_sample_theta(cudaStream_t st, int64_t* launches, const float* vmu, const float* vsig,
+                                const float* zeta_in, uint64_t seed, uint32_t step, int64_t n, float* theta,
+                                float* zeta_out);
+// Adagrad on the variational parameters (VAEB.py:391-393,399,436-442)
+cudaError_t launch_fvb_adagrad(cudaStream_t st, int64_t* launches, float* vmu, float* vsig, float* ada_mu,
+                               float* ada_sig, const float* gtheta, const float* zeta, int sampled, int64_t n,
+                               float lr, float eps, float prior, float* gmu, float* gsig, int apply);
+cudaError_t launch_philox_fill(cudaStream_t st, int64_t* launches, uint64_t seed, uint32_t stream, uint32_t step,
+                               uint32_t sample, int64_t first, int64_t n, float* out);

@@ -1,0 +1,53 @@
+"""Single-node multi-GPU plumbing: one process per GPU, `torch.distributed` for rendezvous,
+NCCL (attached inside the C library) for the gradient all-reduce, plain sharding for the
+importance-sampling estimator.  Nothing here touches the data path."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def broadcast_bytes(payload, src=0):
+    """Broadcast a bytes object from `src` through the default process group."""
+    import torch.distributed as dist
+    obj = [payload]
+    dist.broadcast_object_list(obj, src=src)
+    return obj[0]
+
+
+def attach_data_parallel(model):
+    """Give `model` (one per rank, built on this rank's GPU with batch_size = per-rank share)
+    an NCCL communicator: afterwards every update all-reduces gradients and the bound."""
+    import torch.distributed as dist
+    from .model import comm_unique_id
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = comm_unique_id() if rank == 0 else None
+    uid = broadcast_bytes(uid, 0)
+    model.attach_comm(uid, rank, world)
+    return rank, world
+
+
+def shard_rows(n, rank, world):
+    """Contiguous block of rows owned by `rank` (N/G points per GPU)."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def sharded_log_px(model, x, L, rank, world, gather=True):
+    """IS estimator over the shard of x owned by this rank.  Philox counters are keyed by the
+    GLOBAL row, so the concatenated result is identical for any world size."""
+    lo, hi = shard_rows(len(x), rank, world)
+    local = model.log_px(x[lo:hi], L=L, row_offset=lo) if hi > lo else np.empty(0, np.float32)
+    if not gather or world == 1:
+        return local
+    import torch
+    import torch.distributed as dist
+    outs = [None] * world
+    dist.all_gather_object(outs, local)
+    return np.concatenate(outs)
