@@ -166,6 +166,13 @@ int vaeb_comm_attach(vaeb_handle* h, const char* nccl_library, const uint8_t id[
                      int32_t rank, int32_t world_size);
 int vaeb_comm_detach(vaeb_handle* h);
 
+/* Measurement aid for bench.py: runs the phases of one update on batch `index` one at a time,
+ * each launched `iters` times back to back between two CUDA events on the handle's stream.
+ * ms[i] = mean duration of phase i, flops[i]/bytes[i] = its ALGORITHMIC work per launch,
+ * names + 48*i = its name.  The model state is restored afterwards. */
+int vaeb_profile_update(vaeb_handle* h, int64_t index, int32_t iters, int32_t max_phases, int32_t* n_phases,
+                        float* ms, double* flops, double* bytes, char* names);
+
 /* Counters for the bench: kernels launched by this handle since creation. */
 int vaeb_launch_count(vaeb_handle* h, int64_t* n_launches);
 

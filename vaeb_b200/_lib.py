@@ -55,6 +55,8 @@ EXPORTS = {
     "vaeb_comm_unique_id": (C.c_int, [C.c_char_p, C.c_void_p]),
     "vaeb_comm_attach": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int32, C.c_int32]),
     "vaeb_comm_detach": (C.c_int, [C.c_void_p]),
+    "vaeb_profile_update": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "vaeb_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
 }
 

@@ -24,6 +24,35 @@ void vaeb_set_error(const std::string& msg) { g_last_error = msg; }
     }                                                                         \
   } while (0)
 
+// Per-phase profiling (vaeb_profile_update): every phase launch of one step is repeated `iters`
+// times between two CUDA events on the handle's stream.
+struct PhaseProf {
+  int iters = 1;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  std::vector<std::string> names;
+  std::vector<float> ms;
+  std::vector<double> flops, bytes;
+};
+static thread_local PhaseProf* g_prof = nullptr;
+
+#define PH(NAME, FLOPS, BYTES, EXPR)                                                   \
+  do {                                                                                 \
+    if (g_prof) {                                                                      \
+      VAEB_CUDA(cudaEventRecord(g_prof->e0, h->stream));                               \
+      for (int _i = 0; _i < g_prof->iters; ++_i) VAEB_LAUNCH(EXPR);                    \
+      VAEB_CUDA(cudaEventRecord(g_prof->e1, h->stream));                               \
+      VAEB_CUDA(cudaEventSynchronize(g_prof->e1));                                     \
+      float _ms = 0.f;                                                                 \
+      VAEB_CUDA(cudaEventElapsedTime(&_ms, g_prof->e0, g_prof->e1));                   \
+      g_prof->names.push_back(NAME);                                                   \
+      g_prof->ms.push_back(_ms / (float)g_prof->iters);                                \
+      g_prof->flops.push_back((double)(FLOPS));                                        \
+      g_prof->bytes.push_back((double)(BYTES));                                        \
+    } else {                                                                           \
+      VAEB_LAUNCH(EXPR);                                                               \
+    }                                                                                  \
+  } while (0)
+
 namespace {
 
 void build_layout(Layout& l, int D, int H, int Z, bool cont) {
@@ -114,32 +143,46 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   const int la = h->cfg.estimator == VAEB_EST_LA ? 1 : 0;
   cudaStream_t st = h->stream;
   int64_t* lc = &h->launches;
+  const double dR = R, dr = rows, dD = D, dH = H, dZ = Z, c = h->cont ? 2.0 : 1.0;
   // encoder, VAEB.py:245-251
-  VAEB_LAUNCH(launch_dense_act(st, lc, x, rows, D, T_(h, theta, l.iW3), T_(h, theta, l.ib3), H, 1, s.h_e));
-  VAEB_LAUNCH(launch_enc2(st, lc, s.h_e, rows, H, T_(h, theta, l.iW4), T_(h, theta, l.ib4), T_(h, theta, l.iW5),
-                          T_(h, theta, l.ib5), Z, L, la, src, s.mu, s.ls, s.eps, s.z, s.row_aux));
+  PH("enc1 x.W3+tanh", 2 * dr * dD * dH, 4 * (dr * dD + dD * dH + dr * dH),
+     launch_dense_act(st, lc, x, rows, D, T_(h, theta, l.iW3), T_(h, theta, l.ib3), H, 1, s.h_e));
+  PH("enc2 mu,ls+reparam+KL", 4 * dr * dH * dZ, 4 * (dr * dH + 2 * dH * dZ + 2 * dr * dZ + 2 * dR * dZ),
+     launch_enc2(st, lc, s.h_e, rows, H, T_(h, theta, l.iW4), T_(h, theta, l.ib4), T_(h, theta, l.iW5),
+                 T_(h, theta, l.ib5), Z, L, la, src, s.mu, s.ls, s.eps, s.z, s.row_aux));
   // decoder + log-likelihood, VAEB.py:253-265,302-313
-  VAEB_LAUNCH(launch_dense_act(st, lc, s.z, R, Z, T_(h, theta, l.iW1), T_(h, theta, l.ib1), H, 1, s.h_d));
+  PH("dec1 z.W1+tanh", 2 * dR * dZ * dH, 4 * (dR * dZ + dZ * dH + dR * dH),
+     launch_dense_act(st, lc, s.z, R, Z, T_(h, theta, l.iW1), T_(h, theta, l.ib1), H, 1, s.h_d));
   const float scale = w / (float)L;
   const float* W6 = h->cont ? T_(h, theta, l.iW6) : nullptr;
   const float* b6 = h->cont ? T_(h, theta, l.ib6) : nullptr;
-  VAEB_LAUNCH(launch_dec2_loglik(st, lc, h->cont, s.h_d, R, H, T_(h, theta, l.iW2), T_(h, theta, l.ib2), W6, b6, D, x,
-                                 1, rows, scale, want_grads ? s.da2 : nullptr, want_grads ? s.dlv : nullptr,
-                                 s.partial, n_tiles));
+  PH("dec2 h.W2+loglik", 2 * dR * dH * dD * c,
+     4 * (dR * dH + c * dH * dD + dr * dD + (want_grads ? c * dR * dD : 0.0)),
+     launch_dec2_loglik(st, lc, h->cont, s.h_d, R, H, T_(h, theta, l.iW2), T_(h, theta, l.ib2), W6, b6, D, x, 1, rows,
+                        scale, want_grads ? s.da2 : nullptr, want_grads ? s.dlv : nullptr, s.partial, n_tiles));
   if (!want_grads) return VAEB_OK;
   // backward (T.grad, VAEB.py:397); formulas in SURVEY.md 8a
-  VAEB_LAUNCH(launch_wgrad(st, lc, s.h_d, R, H, s.da2, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2)));
-  if (h->cont) VAEB_LAUNCH(launch_wgrad(st, lc, s.h_d, R, H, s.dlv, D, T_(h, grads, l.iW6), T_(h, grads, l.ib6)));
-  VAEB_LAUNCH(launch_dgrad_tanh(st, lc, s.da2, T_(h, theta, l.iW2), h->cont ? s.dlv : nullptr, W6, R, D, H, s.h_d,
-                                s.da1));
-  VAEB_LAUNCH(launch_wgrad(st, lc, s.z, R, Z, s.da1, H, T_(h, grads, l.iW1), T_(h, grads, l.ib1)));
-  VAEB_LAUNCH(launch_dgrad(st, lc, s.da1, T_(h, theta, l.iW1), R, H, Z, s.dz));
-  VAEB_LAUNCH(launch_dprep(st, lc, s.dz, s.z, s.eps, s.mu, s.ls, rows, Z, L, la, w, s.dmu, s.dls));
-  VAEB_LAUNCH(launch_wgrad(st, lc, s.h_e, rows, H, s.dmu, Z, T_(h, grads, l.iW4), T_(h, grads, l.ib4)));
-  VAEB_LAUNCH(launch_wgrad(st, lc, s.h_e, rows, H, s.dls, Z, T_(h, grads, l.iW5), T_(h, grads, l.ib5)));
-  VAEB_LAUNCH(launch_dgrad_tanh(st, lc, s.dmu, T_(h, theta, l.iW4), s.dls, T_(h, theta, l.iW5), rows, Z, H, s.h_e,
-                                s.da3));
-  VAEB_LAUNCH(launch_wgrad(st, lc, x, rows, D, s.da3, H, T_(h, grads, l.iW3), T_(h, grads, l.ib3)));
+  PH("wgrad W2,b2", 2 * dR * dH * dD, 4 * (dR * dH + dR * dD + dH * dD),
+     launch_wgrad(st, lc, s.h_d, R, H, s.da2, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2)));
+  if (h->cont)
+    PH("wgrad W6,b6", 2 * dR * dH * dD, 4 * (dR * dH + dR * dD + dH * dD),
+       launch_wgrad(st, lc, s.h_d, R, H, s.dlv, D, T_(h, grads, l.iW6), T_(h, grads, l.ib6)));
+  PH("dgrad h_d (.W2^T)*(1-h^2)", 2 * dR * dH * dD * c, 4 * (c * dR * dD + c * dH * dD + 2 * dR * dH),
+     launch_dgrad_tanh(st, lc, s.da2, T_(h, theta, l.iW2), h->cont ? s.dlv : nullptr, W6, R, D, H, s.h_d, s.da1));
+  PH("wgrad W1,b1", 2 * dR * dZ * dH, 4 * (dR * dZ + dR * dH + dZ * dH),
+     launch_wgrad(st, lc, s.z, R, Z, s.da1, H, T_(h, grads, l.iW1), T_(h, grads, l.ib1)));
+  PH("dgrad z (.W1^T)", 2 * dR * dZ * dH, 4 * (dR * dH + dZ * dH + dR * dZ),
+     launch_dgrad(st, lc, s.da1, T_(h, theta, l.iW1), R, H, Z, s.dz));
+  PH("dprep dmu,dls", 0, 4 * (3 * dR * dZ + 4 * dr * dZ),
+     launch_dprep(st, lc, s.dz, s.z, s.eps, s.mu, s.ls, rows, Z, L, la, w, s.dmu, s.dls));
+  PH("wgrad W4,b4", 2 * dr * dH * dZ, 4 * (dr * dH + dr * dZ + dH * dZ),
+     launch_wgrad(st, lc, s.h_e, rows, H, s.dmu, Z, T_(h, grads, l.iW4), T_(h, grads, l.ib4)));
+  PH("wgrad W5,b5", 2 * dr * dH * dZ, 4 * (dr * dH + dr * dZ + dH * dZ),
+     launch_wgrad(st, lc, s.h_e, rows, H, s.dls, Z, T_(h, grads, l.iW5), T_(h, grads, l.ib5)));
+  PH("dgrad h_e (.W45^T)*(1-h^2)", 4 * dr * dH * dZ, 4 * (2 * dr * dZ + 2 * dH * dZ + 2 * dr * dH),
+     launch_dgrad_tanh(st, lc, s.dmu, T_(h, theta, l.iW4), s.dls, T_(h, theta, l.iW5), rows, Z, H, s.h_e, s.da3));
+  PH("wgrad W3,b3", 2 * dr * dD * dH, 4 * (dr * dD + dr * dH + dD * dH),
+     launch_wgrad(st, lc, x, rows, D, s.da3, H, T_(h, grads, l.iW3), T_(h, grads, l.ib3)));
   return VAEB_OK;
 }
 
@@ -188,14 +231,15 @@ int enqueue_update(vaeb_handle* h, const float* d_xrows, int rows, const float* 
     const bool fb = h->cfg.variant == VAEB_VARIANT_FULLBAYES;
     const float w = fb ? 1.0f / Mg : 1.0f;
     VAEB_TRY(forward_backward(h, h->d_params, d_xrows, rows, L, true, w, src, h->d_grads, &tiles));
-    VAEB_LAUNCH(launch_finalize(st, lc, h->ws.partial, tiles, h->ws.row_aux, rows, L, h->ws.per_row, base, 1.0f,
-                                nullptr, 0, Mg, nullptr));
+    PH("finalize bound", 0, 4.0 * rows * L * tiles,
+       launch_finalize(st, lc, h->ws.partial, tiles, h->ws.row_aux, rows, L, h->ws.per_row, base, 1.0f, nullptr, 0,
+                       Mg, nullptr));
     VAEB_TRY(all_reduce_grads(h));
     const float prior = fb ? 0.f : h->cfg.prior_scale;
     if (apply) {
-      VAEB_LAUNCH(launch_adagrad(st, lc, h->d_params, h->d_ada, h->d_grads, n4, h->cfg.learning_rate,
-                                 h->cfg.adagrad_eps, prior, fb ? h->cfg.learning_rate * 1e-6f : 0.f, base, 1.0f, Mg,
-                                 h->d_scalars + slot));
+      PH("adagrad+prior (flat)", 0, 20.0 * (double)l.total,
+         launch_adagrad(st, lc, h->d_params, h->d_ada, h->d_grads, n4, h->cfg.learning_rate, h->cfg.adagrad_eps,
+                        prior, fb ? h->cfg.learning_rate * 1e-6f : 0.f, base, 1.0f, Mg, h->d_scalars + slot));
       h->grads_have_prior = false;
     } else {
       VAEB_LAUNCH(launch_add_prior(st, lc, h->d_grads, h->d_params, n4, prior, base, 1.0f, Mg, h->d_scalars + slot));
@@ -566,7 +610,7 @@ int vaeb_is_logpx(vaeb_handle* h, const float* x, int64_t n, int32_t L, const fl
     int tiles = 0;
     VAEB_LAUNCH(launch_dec2_loglik(st, lc, h->cont, s.h_d, R, H, T_(h, th, l.iW2), T_(h, th, l.ib2),
                                    h->cont ? T_(h, th, l.iW6) : nullptr, h->cont ? T_(h, th, l.ib6) : nullptr, D,
-                                   h->d_stage, L, c, 1.f, nullptr, nullptr, s.partial, &tiles));
+                                   h->d_stage, L, c, 1.f, nullptr, nullptr, s.partial, &tiles, true));
     VAEB_LAUNCH(launch_is_reduce(st, lc, s.partial, tiles, s.dec_aux, c, L, s.logw, h->d_out));
     VAEB_CUDA(cudaMemcpyAsync(logpx_out + i0, h->d_out, (size_t)c * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (logw_out)
@@ -712,6 +756,47 @@ int vaeb_comm_detach(vaeb_handle* h) {
   }
   h->rank = 0;
   h->world = 1;
+  return VAEB_OK;
+}
+
+int vaeb_profile_update(vaeb_handle* h, int64_t index, int32_t iters, int32_t max_phases, int32_t* n_phases,
+                        float* ms, double* flops, double* bytes, char* names) {
+  VAEB_REQUIRE(h && n_phases && ms && flops && bytes && names && iters > 0 && max_phases > 0, "null argument");
+  VAEB_REQUIRE(!is_fvb(h) && h->world == 1, "profiling covers the single-GPU LB/LA step");
+  if (!h->d_x) { vaeb_set_error("vaeb_profile_update before vaeb_upload_data"); return VAEB_ESTATE; }
+  VAEB_REQUIRE(index >= 0 && (index + 1) * (int64_t)h->M <= h->n_data, "batch index outside the resident data");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  // the repeated Adagrad launches must not disturb the model: back params/ADA up
+  const size_t nb = (size_t)(h->lay.padded + 4) * sizeof(float);
+  float *bp = nullptr, *ba = nullptr;
+  VAEB_CUDA(cudaMalloc((void**)&bp, nb));
+  VAEB_CUDA(cudaMalloc((void**)&ba, nb));
+  VAEB_CUDA(cudaMemcpyAsync(bp, h->d_params, nb, cudaMemcpyDeviceToDevice, h->stream));
+  VAEB_CUDA(cudaMemcpyAsync(ba, h->d_ada, nb, cudaMemcpyDeviceToDevice, h->stream));
+  PhaseProf prof;
+  prof.iters = iters;
+  VAEB_CUDA(cudaEventCreate(&prof.e0));
+  VAEB_CUDA(cudaEventCreate(&prof.e1));
+  const uint32_t step0 = h->step;
+  const int64_t launches0 = h->launches;
+  g_prof = &prof;
+  const int rc = enqueue_update(h, h->d_x + (size_t)index * h->M * h->D, h->M, nullptr, nullptr, 0, true);
+  g_prof = nullptr;
+  h->step = step0;
+  h->launches = launches0;
+  cudaMemcpyAsync(h->d_params, bp, nb, cudaMemcpyDeviceToDevice, h->stream);
+  cudaMemcpyAsync(h->d_ada, ba, nb, cudaMemcpyDeviceToDevice, h->stream);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(bp); cudaFree(ba);
+  cudaEventDestroy(prof.e0); cudaEventDestroy(prof.e1);
+  if (rc != VAEB_OK) return rc;
+  const int n = std::min<int>((int)prof.ms.size(), max_phases);
+  *n_phases = n;
+  for (int i = 0; i < n; ++i) {
+    ms[i] = prof.ms[i]; flops[i] = prof.flops[i]; bytes[i] = prof.bytes[i];
+    std::strncpy(names + 48 * i, prof.names[i].c_str(), 47);
+    names[48 * i + 47] = 0;
+  }
   return VAEB_OK;
 }
 

@@ -13,9 +13,9 @@ inline bool use_big_tiles(int M, int N) {
 
 template <bool TA, bool TB, bool ONES, bool DUAL, bool TWO, class Epi>
 cudaError_t run_gemm(cudaStream_t st, int64_t* launches, const GemmOperands& g, const Epi& epi, float* partial,
-                     int* n_col_tiles) {
+                     int* n_col_tiles, bool force_big = false) {
   if (g.M <= 0 || g.N <= 0) return cudaSuccess;
-  if (use_big_tiles(g.M, g.N)) {
+  if (force_big || use_big_tiles(g.M, g.N)) {
     dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
     if (n_col_tiles) *n_col_tiles = grid.x;
     gemm_f32_kernel<64, 64, 4, 4, TA, TB, ONES, DUAL, TWO, Epi><<<grid, 256, 0, st>>>(g, epi, partial);
@@ -42,14 +42,16 @@ cudaError_t launch_dense_act(cudaStream_t st, int64_t* launches, const float* in
 cudaError_t launch_dec2_loglik(cudaStream_t st, int64_t* launches, bool continuous, const float* h_d, int rows,
                                int H, const float* W2, const float* b2, const float* W6, const float* b6, int D,
                                const float* x, int x_div, int x_mod, float scale, float* da, float* dlv,
-                               float* partial, int* n_col_tiles) {
+                               float* partial, int* n_col_tiles, bool fixed_tiles) {
+  // fixed_tiles: the row sums must not depend on how many rows share the launch (the
+  // importance-sampling estimator is bit-identical for any sharding of the test points)
   GemmOperands g{h_d, W2, nullptr, W6, H, D, rows, D, H};
   if (continuous) {
     EpiGaussian epi{b2, b6, x, D, x_div, x_mod, scale, da, dlv, D};
-    return run_gemm<false, false, false, true, false>(st, launches, g, epi, partial, n_col_tiles);
+    return run_gemm<false, false, false, true, false>(st, launches, g, epi, partial, n_col_tiles, fixed_tiles);
   }
   EpiBernoulli epi{b2, x, D, x_div, x_mod, scale, da, D};
-  return run_gemm<false, false, false, false, false>(st, launches, g, epi, partial, n_col_tiles);
+  return run_gemm<false, false, false, false, false>(st, launches, g, epi, partial, n_col_tiles, fixed_tiles);
 }
 
 cudaError_t launch_dec2_recon(cudaStream_t st, int64_t* launches, bool continuous, const float* h_d, int rows,

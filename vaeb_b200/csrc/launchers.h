@@ -14,7 +14,7 @@ cudaError_t launch_dense_act(cudaStream_t st, int64_t* launches, const float* in
 cudaError_t launch_dec2_loglik(cudaStream_t st, int64_t* launches, bool continuous, const float* h_d, int rows,
                                int H, const float* W2, const float* b2, const float* W6, const float* b6, int D,
                                const float* x, int x_div, int x_mod, float scale, float* da, float* dlv,
-                               float* partial, int* n_col_tiles);
+                               float* partial, int* n_col_tiles, bool fixed_tiles = false);
 // reconstruct accumulation (VAEB.py:282-292)
 cudaError_t launch_dec2_recon(cudaStream_t st, int64_t* launches, bool continuous, const float* h_d, int rows,
                               int H, const float* W2, const float* b2, const float* W6, const float* b6, int D,

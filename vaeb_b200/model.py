@@ -304,6 +304,17 @@ class VAEB(object):
     def synchronize(self):
         _lib.check(self._lib.vaeb_synchronize(self._h))
 
+    def profile_update(self, index=0, iters=20):
+        """[(phase name, ms per launch, algorithmic flops, algorithmic bytes)] of one update."""
+        cap = 32
+        n = C.c_int32()
+        t = np.zeros(cap, np.float32); fl = np.zeros(cap, np.float64); by = np.zeros(cap, np.float64)
+        names = C.create_string_buffer(48 * cap)
+        _lib.check(self._lib.vaeb_profile_update(self._h, int(index), int(iters), cap, C.byref(n), _ptr(t), _ptr(fl),
+                                                 _ptr(by), C.cast(names, C.c_void_p)))
+        return [(names.raw[48 * i:48 * i + 48].split(b"\0")[0].decode(), float(t[i]), float(fl[i]), float(by[i]))
+                for i in range(n.value)]
+
     def launch_count(self):
         n = C.c_int64()
         _lib.check(self._lib.vaeb_launch_count(self._h, C.byref(n)))
