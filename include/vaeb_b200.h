@@ -173,6 +173,12 @@ int vaeb_comm_detach(vaeb_handle* h);
 int vaeb_profile_update(vaeb_handle* h, int64_t index, int32_t iters, int32_t max_phases, int32_t* n_phases,
                         float* ms, double* flops, double* bytes, char* names);
 
+/* Self-test of the tcgen05/TMA GEMM building block: C[M,N] = bf16(A[M,K]) . bf16(B[K,N]) with fp32
+ * TMEM accumulation.  a_mn_major / b_mn_major choose the memory layout handed to TMA (0: the
+ * contraction index is contiguous, 1: the M resp. N index is contiguous), block_n the UMMA N. */
+int vaeb_tc_gemm_test(int32_t device, int32_t M, int32_t N, int32_t K, int32_t a_mn_major, int32_t b_mn_major,
+                      int32_t block_n, const float* A, const float* B, float* C);
+
 /* Counters for the bench: kernels launched by this handle since creation. */
 int vaeb_launch_count(vaeb_handle* h, int64_t* n_launches);
 

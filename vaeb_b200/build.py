@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
     srcs = _sources()
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(_compile, srcs))
-    r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-ldl", "-lcuda"], capture_output=True, text=True)
+    r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-ldl"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     with open(stamp_file, "w") as f:
