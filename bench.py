@@ -49,46 +49,57 @@ def measured_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML DURING the timed region (a thread in
+    this process: spawning nvidia-smi in a loop contends with kernel launches for the driver)."""
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period_s=0.05):
+        self.index, self.period, self.rows, self.stop = index, period_s, [], threading.Event()
+        self.max_mhz, self.t = None, None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.t = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _sample(self):
+        nv = self.nv
+        try:
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), int(reasons)))
+
+    def _loop(self):
+        while not self.stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self.stop.wait(self.period)
 
     def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
+        if self.t:
+            try:
+                self._sample()
+            except Exception:
+                pass
+            self.stop.set()
             self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({n for r in self.rows for bit, n in names.items() if r[1] & bit})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm)}
 
 
 def make_problem(seed=15485863):
@@ -169,7 +180,8 @@ def run_own(args):
 
     import vaeb_b200
     x = make_problem()
-    model = vaeb_b200.VAEB(x, False, H, Z, M, L, 0.01, False, False, device=local, seed=10 + rank)
+    model = vaeb_b200.VAEB(x, False, H, Z, M, L, 0.01, False, False, device=local, seed=10 + rank,
+                           precision=args.precision)
     stream = torch.cuda.current_stream()
     model.set_stream(stream.cuda_stream)
     nb = N_TRAIN // M
@@ -250,13 +262,14 @@ def run_own(args):
                    "sample": "%d update() steps (%.1f s) of the numpy fp32 restatement in oracle/" % (done, dt)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
+                "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (hi+lo operands, fp32 accumulate)", "bf16": "bf16"}[args.precision],
+                "data": "synthetic",
                 "config": {"workload": "c2: MNIST-shape Bernoulli VAE D=784 H=500 Z=20, M=100, L=1, Adagrad; one step "
                                        "= one update() on 100 rows; N>1 = independent replicas (M=100 does not shard)",
                            "rows_resident": N_TRAIN,
                            "l2": "x_train (157 MB) exceeds the 126 MB L2 and minibatches are visited in shuffled "
                                  "order; the 3.3 MB parameter/ADA/gradient buffers stay L2-resident as in real training",
-                           "eps": "Philox4x32-10 on device", "precision": "fp32"},
+                           "eps": "Philox4x32-10 on device", "precision": args.precision},
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": M * D * 4, "d2h_bytes_per_step": 4,
                         "steps": Ke, "ms_per_step": ms_e2e / Ke,
@@ -280,6 +293,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "bf16"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

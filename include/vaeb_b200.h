@@ -46,6 +46,7 @@ extern "C" {
 /* precision -- arithmetic of the dense layers */
 #define VAEB_PREC_FP32 0   /* fp32 FFMA tiles (parity tier 1e-4)                          */
 #define VAEB_PREC_BF16 1   /* tcgen05 bf16 operands, fp32 TMEM accumulation (1e-2 tier)   */
+#define VAEB_PREC_BF16X3 2 /* tcgen05, operands as bf16 hi+lo, 3 MMAs per k-step: fp32-tier */
 
 /* eps source */
 #define VAEB_EPS_PHILOX 0    /* on-device Philox4x32-10 + Box-Muller                      */

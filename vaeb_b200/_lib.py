@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libvaeb_b200.so")
 
 EST_LB, EST_LA, EST_FVB, EST_FVB_SAMPLED = 0, 1, 2, 3
 VARIANT_VAEB, VARIANT_FULLBAYES = 0, 1
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
 
 # buffers addressable through vaeb_{get,set}_tensors
 BUF_PARAMS, BUF_ADA, BUF_GRADS, BUF_VMU, BUF_VSIG, BUF_ADA_MU, BUF_ADA_SIG, BUF_GMU, BUF_GSIG = range(9)

@@ -96,7 +96,7 @@ int grow(float** p, int64_t* cap, int64_t need) {
 
 void free_ws(Workspace& w) {
   float** all[] = {&w.h_e, &w.mu, &w.ls, &w.eps, &w.z, &w.h_d, &w.da2, &w.dlv, &w.da1, &w.dz, &w.dmu, &w.dls,
-                   &w.da3, &w.partial, &w.row_aux, &w.per_row, &w.dec_aux, &w.logw};
+                   &w.da3, &w.partial, &w.row_aux, &w.per_row, &w.dec_aux, &w.logw, &w.wg_scratch};
   for (float** p : all) { if (*p) cudaFree(*p); *p = nullptr; }
   w.cap_enc = w.cap_dec = 0;
   w.with_grads = false;
@@ -125,17 +125,81 @@ int ensure_ws(vaeb_handle* h, int64_t enc, int64_t dec, bool grads) {
     if (h->cont) VAEB_TRY(A(&w.dlv, dec * D));
     VAEB_TRY(A(&w.da1, dec * H)); VAEB_TRY(A(&w.dz, dec * Z));
     VAEB_TRY(A(&w.dmu, enc * Z)); VAEB_TRY(A(&w.dls, enc * Z)); VAEB_TRY(A(&w.da3, enc * H));
+    VAEB_TRY(A(&w.wg_scratch, (int64_t)small_wgrad_scratch_elems((int)enc, H, Z)));
   }
   w.cap_enc = enc; w.cap_dec = dec; w.with_grads = grads;
+  return VAEB_OK;
+}
+
+int grow_bytes(void** p, size_t bytes) {
+  if (*p) VAEB_CUDA(cudaFree(*p));
+  *p = nullptr;
+  VAEB_CUDA(cudaMalloc(p, bytes));
+  return VAEB_OK;
+}
+
+inline int round8(int v) { return (v + 7) / 8 * 8; }
+
+// Allocate / grow the bf16 mirrors for `R` decoder rows and `rows` encoder rows.
+int tc_ensure(vaeb_handle* h, int64_t rows, int64_t R) {
+  TcState& t = h->tc;
+  TcBuffers& b = t.data;
+  const int D = h->D, H = h->H;
+  const bool lo = t.ns == 2;
+  if (b.ldh == 0) {
+    b.ldh = round8(H + 1); b.ldd = round8(D + 1); b.ldx = b.ldd;
+    VAEB_TRY(grow_bytes(&b.w3h, (size_t)D * b.ldh * 2));
+    VAEB_TRY(grow_bytes(&b.w2h, (size_t)H * b.ldd * 2));
+    VAEB_CUDA(cudaMemsetAsync(b.w3h, 0, (size_t)D * b.ldh * 2, h->stream));
+    VAEB_CUDA(cudaMemsetAsync(b.w2h, 0, (size_t)H * b.ldd * 2, h->stream));
+    if (lo) {
+      VAEB_TRY(grow_bytes(&b.w3l, (size_t)D * b.ldh * 2));
+      VAEB_TRY(grow_bytes(&b.w2l, (size_t)H * b.ldd * 2));
+      VAEB_CUDA(cudaMemsetAsync(b.w3l, 0, (size_t)D * b.ldh * 2, h->stream));
+      VAEB_CUDA(cudaMemsetAsync(b.w2l, 0, (size_t)H * b.ldd * 2, h->stream));
+    }
+  }
+  if (R > t.cap_R) {
+    VAEB_CUDA(cudaStreamSynchronize(h->stream));
+    VAEB_TRY(grow_bytes(&b.hdh, (size_t)R * b.ldh * 2));
+    VAEB_TRY(grow_bytes(&b.da2h, (size_t)R * b.ldd * 2));
+    if (lo) {
+      VAEB_TRY(grow_bytes(&b.hdl, (size_t)R * b.ldh * 2));
+      VAEB_TRY(grow_bytes(&b.da2l, (size_t)R * b.ldd * 2));
+    }
+    // zero padding + the ones column at H (bias row of the W2 weight-gradient GEMM)
+    VAEB_LAUNCH(tc_split_matrix(h->stream, &h->launches, nullptr, R, 0, 0, b.hdh, b.hdl, b.ldh, H));
+    VAEB_CUDA(cudaMemsetAsync(b.da2h, 0, (size_t)R * b.ldd * 2, h->stream));
+    if (lo) VAEB_CUDA(cudaMemsetAsync(b.da2l, 0, (size_t)R * b.ldd * 2, h->stream));
+    t.cap_R = R;
+    t.key_rows = -1;
+  }
+  if (rows > t.cap_rows) {
+    VAEB_CUDA(cudaStreamSynchronize(h->stream));
+    VAEB_TRY(grow_bytes(&b.da3h, (size_t)rows * b.ldh * 2));
+    VAEB_CUDA(cudaMemsetAsync(b.da3h, 0, (size_t)rows * b.ldh * 2, h->stream));
+    if (lo) {
+      VAEB_TRY(grow_bytes(&b.da3l, (size_t)rows * b.ldh * 2));
+      VAEB_CUDA(cudaMemsetAsync(b.da3l, 0, (size_t)rows * b.ldh * 2, h->stream));
+    }
+    t.cap_rows = rows;
+    t.key_rows = -1;
+  }
   return VAEB_OK;
 }
 
 inline float* T_(vaeb_handle* h, float* base, int idx) { return base + h->lay.off[idx]; }
 inline const float* T_(vaeb_handle* h, const float* base, int idx) { return base + h->lay.off[idx]; }
 
+// Where the bound of a step goes: base (sum of per-row bounds) always; the scalar
+// (mult*base + sum(tprior))/div if scalar_out != nullptr.
+struct BoundOut {
+  float* base_out; float mult; const float* tprior; int n_tprior; float div; float* scalar_out;
+};
+
 // Forward (+ backward into `grads`) of the graph of VAEB.getGradient for x[rows,D] on device.
 int forward_backward(vaeb_handle* h, const float* theta, const float* x, int rows, int L, bool want_grads, float w,
-                     EpsSource src, float* grads, int* n_tiles) {
+                     EpsSource src, float* grads, const BoundOut& bo) {
   const Layout& l = h->lay;
   Workspace& s = h->ws;
   const int D = h->D, H = h->H, Z = h->Z;
@@ -143,46 +207,111 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   const int la = h->cfg.estimator == VAEB_EST_LA ? 1 : 0;
   cudaStream_t st = h->stream;
   int64_t* lc = &h->launches;
+  int tiles = 0;
   const double dR = R, dr = rows, dD = D, dH = H, dZ = Z, c = h->cont ? 2.0 : 1.0;
-  // encoder, VAEB.py:245-251
-  PH("enc1 x.W3+tanh", 2 * dr * dD * dH, 4 * (dr * dD + dD * dH + dr * dH),
-     launch_dense_act(st, lc, x, rows, D, T_(h, theta, l.iW3), T_(h, theta, l.ib3), H, 1, s.h_e));
-  PH("enc2 mu,ls+reparam+KL", 4 * dr * dH * dZ, 4 * (dr * dH + 2 * dH * dZ + 2 * dr * dZ + 2 * dR * dZ),
-     launch_enc2(st, lc, s.h_e, rows, H, T_(h, theta, l.iW4), T_(h, theta, l.ib4), T_(h, theta, l.iW5),
-                 T_(h, theta, l.ib5), Z, L, la, src, s.mu, s.ls, s.eps, s.z, s.row_aux));
-  // decoder + log-likelihood, VAEB.py:253-265,302-313
-  PH("dec1 z.W1+tanh", 2 * dR * dZ * dH, 4 * (dR * dZ + dZ * dH + dR * dH),
-     launch_dense_act(st, lc, s.z, R, Z, T_(h, theta, l.iW1), T_(h, theta, l.ib1), H, 1, s.h_d));
+  // ---- tensor-core path: mirrors, descriptors -------------------------------------------------
+  const bool tcp = h->tc.active;
+  TcState& t = h->tc;
+  int x_row_off = 0, bn = 64;
+  if (tcp) {
+    VAEB_TRY(tc_ensure(h, rows, R));
+    bn = R >= 1024 ? 128 : 64;
+    TcBuffers b = t.data;
+    int64_t rows_data;
+    const bool resident = h->d_x && x >= h->d_x && x < h->d_x + (size_t)h->n_data * D;
+    if (resident) {
+      x_row_off = (int)((x - h->d_x) / D);
+      rows_data = h->n_data;
+    } else {
+      // x was staged from the host for this call: mirror it now
+      if (rows > t.cap_stage) {
+        VAEB_CUDA(cudaStreamSynchronize(st));
+        VAEB_TRY(grow_bytes(&t.xsh, (size_t)rows * b.ldx * 2));
+        if (t.ns == 2) VAEB_TRY(grow_bytes(&t.xsl, (size_t)rows * b.ldx * 2));
+        t.cap_stage = rows;
+        t.key_rows = -1;
+      }
+      PH("mirror staged x", 0, 4.0 * dr * dD,
+         tc_split_matrix(st, lc, x, rows, D, D, t.xsh, t.xsl, b.ldx, D));
+      b.xh = t.xsh; b.xl = t.xsl;
+      rows_data = rows;
+    }
+    if (t.key_rows != rows || t.key_R != R || t.key_data != rows_data || t.key_bn != bn || t.key_x != b.xh) {
+      VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bn));
+      t.key_rows = rows; t.key_R = R; t.key_data = rows_data; t.key_bn = bn; t.key_x = b.xh;
+    }
+    PH("mirror W3,W2 -> bf16", 0, 12.0 * dD * dH,
+       tc_mirror_weights(st, lc, T_(h, theta, l.iW3), b.w3h, b.w3l, D, H, b.ldh, T_(h, theta, l.iW2), b.w2h, b.w2l,
+                         b.ldd));
+  }
+  const TcBuffers& tb = t.data;
+  // encoder hidden layer, VAEB.py:246
+  if (tcp)
+    PH("enc1 x.W3+tanh [tcgen05]", 2 * dr * dD * dH, 2.0 * t.ns * (dr * dD + dD * dH) + 4 * dr * dH,
+       tc_enc1(st, lc, t.maps, t.ns, bn, rows, D, H, x_row_off, T_(h, theta, l.ib3), s.h_e));
+  else
+    PH("enc1 x.W3+tanh", 2 * dr * dD * dH, 4 * (dr * dD + dD * dH + dr * dH),
+       launch_dense_act(st, lc, x, rows, D, T_(h, theta, l.iW3), T_(h, theta, l.ib3), H, 1, s.h_e));
+  // latent heads + reparameterisation + row terms + decoder hidden layer, VAEB.py:248-254,41-47,343
+  PH("latent fwd (enc2,reparam,KL,dec1)", 4 * dr * dH * dZ + 2 * dR * dZ * dH,
+     4 * (dr * dH + 3 * dH * dZ + 2 * dr * dZ + 2 * dR * dZ + dR * dH),
+     launch_latent_fwd(st, lc, s.h_e, rows, H, T_(h, theta, l.iW4), T_(h, theta, l.ib4), T_(h, theta, l.iW5),
+                       T_(h, theta, l.ib5), T_(h, theta, l.iW1), T_(h, theta, l.ib1), Z, L, la, src, s.mu, s.ls,
+                       s.eps, s.z, s.row_aux, s.h_d, tcp ? tb.hdh : nullptr, tcp ? tb.hdl : nullptr, tb.ldh));
+  // decoder output layer + log-likelihood, VAEB.py:257-263,302-313
   const float scale = w / (float)L;
   const float* W6 = h->cont ? T_(h, theta, l.iW6) : nullptr;
   const float* b6 = h->cont ? T_(h, theta, l.ib6) : nullptr;
-  PH("dec2 h.W2+loglik", 2 * dR * dH * dD * c,
-     4 * (dR * dH + c * dH * dD + dr * dD + (want_grads ? c * dR * dD : 0.0)),
-     launch_dec2_loglik(st, lc, h->cont, s.h_d, R, H, T_(h, theta, l.iW2), T_(h, theta, l.ib2), W6, b6, D, x, 1, rows,
-                        scale, want_grads ? s.da2 : nullptr, want_grads ? s.dlv : nullptr, s.partial, n_tiles));
-  if (!want_grads) return VAEB_OK;
+  if (tcp)
+    PH("dec2 h.W2+loglik [tcgen05]", 2 * dR * dH * dD,
+       2.0 * t.ns * (dR * dH + dH * dD) + 4 * dr * dD + (want_grads ? 2.0 * t.ns * dR * dD : 0.0),
+       tc_dec2_bernoulli(st, lc, t.maps, t.ns, bn, R, H, D, T_(h, theta, l.ib2), x, 1, rows, scale,
+                         want_grads ? tb.da2h : nullptr, want_grads ? tb.da2l : nullptr, tb.ldd, s.partial, &tiles));
+  else
+    PH("dec2 h.W2+loglik", 2 * dR * dH * dD * c,
+       4 * (dR * dH + c * dH * dD + dr * dD + (want_grads ? c * dR * dD : 0.0)),
+       launch_dec2_loglik(st, lc, h->cont, s.h_d, R, H, T_(h, theta, l.iW2), T_(h, theta, l.ib2), W6, b6, D, x, 1,
+                          rows, scale, want_grads ? s.da2 : nullptr, want_grads ? s.dlv : nullptr, s.partial,
+                          &tiles));
+  if (!want_grads) {
+    PH("finalize bound", 0, 4.0 * R * tiles,
+       launch_finalize(st, lc, s.partial, tiles, s.row_aux, rows, L, s.per_row, bo.base_out, bo.mult, bo.tprior,
+                       bo.n_tprior, bo.div, bo.scalar_out));
+    return VAEB_OK;
+  }
   // backward (T.grad, VAEB.py:397); formulas in SURVEY.md 8a
-  PH("wgrad W2,b2", 2 * dR * dH * dD, 4 * (dR * dH + dR * dD + dH * dD),
-     launch_wgrad(st, lc, s.h_d, R, H, s.da2, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2)));
-  if (h->cont)
-    PH("wgrad W6,b6", 2 * dR * dH * dD, 4 * (dR * dH + dR * dD + dH * dD),
-       launch_wgrad(st, lc, s.h_d, R, H, s.dlv, D, T_(h, grads, l.iW6), T_(h, grads, l.ib6)));
-  PH("dgrad h_d (.W2^T)*(1-h^2)", 2 * dR * dH * dD * c, 4 * (c * dR * dD + c * dH * dD + 2 * dR * dH),
-     launch_dgrad_tanh(st, lc, s.da2, T_(h, theta, l.iW2), h->cont ? s.dlv : nullptr, W6, R, D, H, s.h_d, s.da1));
-  PH("wgrad W1,b1", 2 * dR * dZ * dH, 4 * (dR * dZ + dR * dH + dZ * dH),
-     launch_wgrad(st, lc, s.z, R, Z, s.da1, H, T_(h, grads, l.iW1), T_(h, grads, l.ib1)));
-  PH("dgrad z (.W1^T)", 2 * dR * dZ * dH, 4 * (dR * dH + dZ * dH + dR * dZ),
-     launch_dgrad(st, lc, s.da1, T_(h, theta, l.iW1), R, H, Z, s.dz));
-  PH("dprep dmu,dls", 0, 4 * (3 * dR * dZ + 4 * dr * dZ),
-     launch_dprep(st, lc, s.dz, s.z, s.eps, s.mu, s.ls, rows, Z, L, la, w, s.dmu, s.dls));
-  PH("wgrad W4,b4", 2 * dr * dH * dZ, 4 * (dr * dH + dr * dZ + dH * dZ),
-     launch_wgrad(st, lc, s.h_e, rows, H, s.dmu, Z, T_(h, grads, l.iW4), T_(h, grads, l.ib4)));
-  PH("wgrad W5,b5", 2 * dr * dH * dZ, 4 * (dr * dH + dr * dZ + dH * dZ),
-     launch_wgrad(st, lc, s.h_e, rows, H, s.dls, Z, T_(h, grads, l.iW5), T_(h, grads, l.ib5)));
-  PH("dgrad h_e (.W45^T)*(1-h^2)", 4 * dr * dH * dZ, 4 * (2 * dr * dZ + 2 * dH * dZ + 2 * dr * dH),
-     launch_dgrad_tanh(st, lc, s.dmu, T_(h, theta, l.iW4), s.dls, T_(h, theta, l.iW5), rows, Z, H, s.h_e, s.da3));
-  PH("wgrad W3,b3", 2 * dr * dD * dH, 4 * (dr * dD + dr * dH + dD * dH),
-     launch_wgrad(st, lc, x, rows, D, s.da3, H, T_(h, grads, l.iW3), T_(h, grads, l.ib3)));
+  if (tcp) {
+    PH("wgrad W2,b2 [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dH + dR * dD) + 4 * dH * dD,
+       tc_wgrad2(st, lc, t.maps, t.ns, bn, R, H, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2)));
+    PH("dgrad h_d (.W2^T)*(1-h^2) [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dD + dH * dD) + 8 * dR * dH,
+       tc_dgrad_hd(st, lc, t.maps, t.ns, bn, R, D, H, s.h_d, s.da1));
+  } else {
+    PH("wgrad W2,b2", 2 * dR * dH * dD, 4 * (dR * dH + dR * dD + dH * dD),
+       launch_wgrad(st, lc, s.h_d, R, H, s.da2, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2)));
+    if (h->cont)
+      PH("wgrad W6,b6", 2 * dR * dH * dD, 4 * (dR * dH + dR * dD + dH * dD),
+         launch_wgrad(st, lc, s.h_d, R, H, s.dlv, D, T_(h, grads, l.iW6), T_(h, grads, l.ib6)));
+    PH("dgrad h_d (.W2^T)*(1-h^2)", 2 * dR * dH * dD * c, 4 * (c * dR * dD + c * dH * dD + 2 * dR * dH),
+       launch_dgrad_tanh(st, lc, s.da2, T_(h, theta, l.iW2), h->cont ? s.dlv : nullptr, W6, R, D, H, s.h_d, s.da1));
+  }
+  PH("latent bwd (dz,dmu,dls,da3,bound)", 2 * dR * dZ * dH + 4 * dr * dH * dZ,
+     4 * (dR * dH + 3 * dZ * dH + 2 * dr * dH + 3 * dR * dZ + dR * tiles),
+     launch_latent_bwd(st, lc, s.da1, T_(h, theta, l.iW1), T_(h, theta, l.iW4), T_(h, theta, l.iW5), s.h_e, s.z, s.eps,
+                       s.mu, s.ls, rows, H, Z, L, la, w, s.dmu, s.dls, s.da3, tcp ? tb.da3h : nullptr,
+                       tcp ? tb.da3l : nullptr, tb.ldh, s.partial, tiles,
+                       s.row_aux, s.per_row, h->d_counter, bo.base_out, bo.mult, bo.tprior, bo.n_tprior, bo.div,
+                       bo.scalar_out));
+  PH("wgrad W1,b1,W4,b4,W5,b5", 2 * dR * dZ * dH + 4 * dr * dH * dZ,
+     4 * (dR * dZ + dR * dH + dr * dH + 2 * dr * dZ + 3 * dH * dZ),
+     launch_small_wgrad(st, lc, s.z, s.da1, R, s.h_e, s.dmu, s.dls, rows, H, Z, T_(h, grads, l.iW1),
+                        T_(h, grads, l.ib1), T_(h, grads, l.iW4), T_(h, grads, l.ib4), T_(h, grads, l.iW5),
+                        T_(h, grads, l.ib5), s.wg_scratch));
+  if (tcp)
+    PH("wgrad W3,b3 [tcgen05]", 2 * dr * dD * dH, 2.0 * t.ns * (dr * dD + dr * dH) + 4 * dD * dH,
+       tc_wgrad3(st, lc, t.maps, t.ns, bn, rows, D, H, x_row_off, T_(h, grads, l.iW3), T_(h, grads, l.ib3)));
+  else
+    PH("wgrad W3,b3", 2 * dr * dD * dH, 4 * (dr * dD + dr * dH + dD * dH),
+       launch_wgrad(st, lc, x, rows, D, s.da3, H, T_(h, grads, l.iW3), T_(h, grads, l.ib3)));
   return VAEB_OK;
 }
 
@@ -223,26 +352,26 @@ int enqueue_update(vaeb_handle* h, const float* d_xrows, int rows, const float* 
   EpsSource src{d_eps, h->cfg.seed, VAEB_STREAM_TRAIN, h->step, (int64_t)h->rank * rows};
   cudaStream_t st = h->stream;
   int64_t* lc = &h->launches;
-  int tiles = 0;
   float* base = h->d_grads + l.padded;
   const int64_t n4 = l.padded / 4;
   const float Mg = (float)rows * (float)h->world;
   if (!is_fvb(h)) {
     const bool fb = h->cfg.variant == VAEB_VARIANT_FULLBAYES;
     const float w = fb ? 1.0f / Mg : 1.0f;
-    VAEB_TRY(forward_backward(h, h->d_params, d_xrows, rows, L, true, w, src, h->d_grads, &tiles));
-    PH("finalize bound", 0, 4.0 * rows * L * tiles,
-       launch_finalize(st, lc, h->ws.partial, tiles, h->ws.row_aux, rows, L, h->ws.per_row, base, 1.0f, nullptr, 0,
-                       Mg, nullptr));
+    const bool dp = h->world > 1;
+    BoundOut bo{base, 1.0f, nullptr, 0, Mg, dp ? nullptr : h->d_scalars + slot};
+    VAEB_TRY(forward_backward(h, h->d_params, d_xrows, rows, L, true, w, src, h->d_grads, bo));
     VAEB_TRY(all_reduce_grads(h));
     const float prior = fb ? 0.f : h->cfg.prior_scale;
     if (apply) {
       PH("adagrad+prior (flat)", 0, 20.0 * (double)l.total,
          launch_adagrad(st, lc, h->d_params, h->d_ada, h->d_grads, n4, h->cfg.learning_rate, h->cfg.adagrad_eps,
-                        prior, fb ? h->cfg.learning_rate * 1e-6f : 0.f, base, 1.0f, Mg, h->d_scalars + slot));
+                        prior, fb ? h->cfg.learning_rate * 1e-6f : 0.f, base, 1.0f, Mg,
+                        dp ? h->d_scalars + slot : nullptr));
       h->grads_have_prior = false;
     } else {
-      VAEB_LAUNCH(launch_add_prior(st, lc, h->d_grads, h->d_params, n4, prior, base, 1.0f, Mg, h->d_scalars + slot));
+      VAEB_LAUNCH(launch_add_prior(st, lc, h->d_grads, h->d_params, n4, prior, base, 1.0f, Mg,
+                                   dp ? h->d_scalars + slot : nullptr));
       h->grads_have_prior = true;
     }
   } else {
@@ -255,11 +384,9 @@ int enqueue_update(vaeb_handle* h, const float* d_xrows, int rows, const float* 
       theta = h->d_theta;
     }
     VAEB_LAUNCH(launch_theta_prior(st, lc, h->d_vmu, h->d_vsig, l.total, h->d_tprior));
-    VAEB_TRY(forward_backward(h, theta, d_xrows, rows, L, sampled, (float)rows, src, h->d_grads, &tiles));
     // SGVB = x.shape[0]*(sum logp + sum KL) + thetaPrior (VAEB.py:364); update returns SGVB/M
-    VAEB_LAUNCH(launch_finalize(st, lc, h->ws.partial, tiles, h->ws.row_aux, rows, L, h->ws.per_row, base,
-                                (float)rows, h->d_tprior, VAEB_TP_BLOCKS, apply ? (float)rows : 1.0f,
-                                h->d_scalars + slot));
+    BoundOut bo{base, (float)rows, h->d_tprior, VAEB_TP_BLOCKS, apply ? (float)rows : 1.0f, h->d_scalars + slot};
+    VAEB_TRY(forward_backward(h, theta, d_xrows, rows, L, sampled, (float)rows, src, h->d_grads, bo));
     VAEB_LAUNCH(launch_fvb_adagrad(st, lc, h->d_vmu, h->d_vsig, h->d_ada_mu, h->d_ada_sig, h->d_grads, h->d_zeta,
                                    sampled ? 1 : 0, l.total, h->cfg.learning_rate, h->cfg.adagrad_eps,
                                    h->cfg.prior_scale, h->d_gmu, h->d_gsig, apply ? 1 : 0));
@@ -319,7 +446,9 @@ int vaeb_create(const vaeb_config* cfg, vaeb_handle** out) {
   VAEB_REQUIRE(cfg->batch_size > 0 && cfg->L > 0, "batch_size and L must be positive");
   VAEB_REQUIRE(cfg->estimator >= 0 && cfg->estimator <= 3, "unknown estimator");
   VAEB_REQUIRE(cfg->variant == 0 || cfg->variant == 1, "unknown variant");
-  VAEB_REQUIRE(cfg->precision == VAEB_PREC_FP32 || cfg->precision == VAEB_PREC_BF16, "unknown precision");
+  VAEB_REQUIRE(cfg->precision >= VAEB_PREC_FP32 && cfg->precision <= VAEB_PREC_BF16X3, "unknown precision");
+  VAEB_REQUIRE(cfg->precision == VAEB_PREC_FP32 || !cfg->continuous,
+               "the tensor-core precisions cover the Bernoulli decoder; use fp32 for the Gaussian decoder");
   const bool fvb = cfg->estimator >= VAEB_EST_FVB;
   // getFVBL overwrites `mu` inside the sample loop (VAEB.py:361): undefined for L > 1
   VAEB_REQUIRE(!(fvb && cfg->L != 1), "full-VB bound is only defined for L == 1 (VAEB.py:361)");
@@ -337,6 +466,8 @@ int vaeb_create(const vaeb_config* cfg, vaeb_handle** out) {
   h->D = cfg->input_dim; h->H = cfg->hidden_units; h->Z = cfg->latent_size; h->M = cfg->batch_size; h->L = cfg->L;
   h->cont = cfg->continuous != 0;
   build_layout(h->lay, h->D, h->H, h->Z, h->cont);
+  h->tc.active = cfg->precision != VAEB_PREC_FP32;
+  h->tc.ns = cfg->precision == VAEB_PREC_BF16X3 ? 2 : 1;
   VAEB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
   const int64_t n = h->lay.padded + 4;
@@ -354,6 +485,8 @@ int vaeb_create(const vaeb_config* cfg, vaeb_handle** out) {
     VAEB_TRY(alloc_flat(&h->d_zeta, n));
     VAEB_TRY(alloc_flat(&h->d_tprior, VAEB_TP_BLOCKS));
   }
+  VAEB_CUDA(cudaMalloc((void**)&h->d_counter, sizeof(unsigned int)));
+  VAEB_CUDA(cudaMemset(h->d_counter, 0, sizeof(unsigned int)));
   VAEB_TRY(ensure_scalars(h, 1024));
   *out = h;
   return VAEB_OK;
@@ -369,6 +502,12 @@ int vaeb_destroy(vaeb_handle* h) {
                    h->d_gsig, h->d_theta, h->d_zeta, h->d_tprior, h->d_x, h->d_stage, h->d_stage2, h->d_out,
                    h->d_scalars};
   for (float* p : bufs) if (p) cudaFree(p);
+  if (h->d_counter) cudaFree(h->d_counter);
+  {
+    TcBuffers& b = h->tc.data;
+    void* tb[] = {b.xh, b.xl, b.w3h, b.w3l, b.w2h, b.w2l, b.hdh, b.hdl, b.da2h, b.da2l, b.da3h, b.da3l, h->tc.xsh, h->tc.xsl};
+    for (void* q : tb) if (q) cudaFree(q);
+  }
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -448,6 +587,16 @@ int vaeb_upload_data(vaeb_handle* h, const float* x, int64_t n_rows) {
   VAEB_CUDA(cudaMalloc((void**)&h->d_x, bytes));
   VAEB_CUDA(cudaMemcpy(h->d_x, x, bytes, cudaMemcpyHostToDevice));
   h->n_data = n_rows;
+  if (h->tc.active) {
+    TcState& t = h->tc;
+    VAEB_TRY(tc_ensure(h, 1, 1));
+    VAEB_TRY(grow_bytes(&t.data.xh, (size_t)n_rows * t.data.ldx * 2));
+    if (t.ns == 2) VAEB_TRY(grow_bytes(&t.data.xl, (size_t)n_rows * t.data.ldx * 2));
+    VAEB_LAUNCH(tc_split_matrix(h->stream, &h->launches, h->d_x, n_rows, h->D, h->D, t.data.xh, t.data.xl, t.data.ldx,
+                                h->D));
+    VAEB_CUDA(cudaStreamSynchronize(h->stream));
+    t.key_rows = -1;
+  }
   return VAEB_OK;
 }
 
@@ -553,7 +702,6 @@ int vaeb_validate(vaeb_handle* h, const float* x, int64_t n, const float* eps, f
   // validate shares the eps stream with update in the reference (VAEB.py:158); here it
   // draws from its own Philox stream keyed by the same step counter
   EpsSource src{d_eps, h->cfg.seed, VAEB_STREAM_EVAL, h->step, 0};
-  int tiles = 0;
   const float* theta = h->d_params;
   float mult = 1.f, div = 1.f;
   const float* tp = nullptr;
@@ -569,9 +717,8 @@ int vaeb_validate(vaeb_handle* h, const float* x, int64_t n, const float* eps, f
   } else if (h->cfg.variant == VAEB_VARIANT_FULLBAYES) {
     div = (float)n;                      // T.mean, VAEBfullbayes.py:142
   }
-  VAEB_TRY(forward_backward(h, theta, h->d_stage, (int)n, L, false, 1.f, src, nullptr, &tiles));
-  VAEB_LAUNCH(launch_finalize(h->stream, &h->launches, h->ws.partial, tiles, h->ws.row_aux, (int)n, L, h->ws.per_row,
-                              h->d_grads + h->lay.padded, mult, tp, VAEB_TP_BLOCKS, div, h->d_scalars));
+  BoundOut bo{h->d_grads + h->lay.padded, mult, tp, VAEB_TP_BLOCKS, div, h->d_scalars};
+  VAEB_TRY(forward_backward(h, theta, h->d_stage, (int)n, L, false, 1.f, src, nullptr, bo));
   ++h->step;
   VAEB_TRY(read_scalars(h, 1, sgvb_out));
   if (per_row_out)

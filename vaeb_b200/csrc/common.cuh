@@ -6,6 +6,7 @@
 #include <string>
 
 #include "../../include/vaeb_b200.h"
+#include "tc_layers.h"
 
 void vaeb_set_error(const std::string& msg);
 
@@ -61,10 +62,23 @@ struct Workspace {
   float *h_e = nullptr, *mu = nullptr, *ls = nullptr, *eps = nullptr, *z = nullptr, *h_d = nullptr;
   float *da2 = nullptr, *dlv = nullptr, *da1 = nullptr, *dz = nullptr, *dmu = nullptr, *dls = nullptr, *da3 = nullptr;
   float *partial = nullptr, *row_aux = nullptr, *per_row = nullptr, *dec_aux = nullptr, *logw = nullptr;
+  float* wg_scratch = nullptr;        // row-chunk partials of the thin weight gradients (large batches)
+};
+
+// Tensor-core path state: bf16 (hi/lo) mirrors and their TMA descriptors.
+struct TcState {
+  bool active = false;
+  int ns = 1;                              // 1: bf16, 2: bf16 hi+lo (three MMAs per k-step)
+  TcBuffers data;                          // mirrors with the resident dataset as x
+  void *xsh = nullptr, *xsl = nullptr;     // mirror of a staged (host-supplied) batch
+  int64_t cap_data = 0, cap_stage = 0, cap_R = 0, cap_rows = 0;
+  TcMaps maps;
+  int64_t key_rows = -1, key_R = -1, key_data = -1; int key_bn = 0; const void* key_x = nullptr;
 };
 
 struct vaeb_handle {
   vaeb_config cfg;
+  TcState tc;
   int D, H, Z, M, L;
   bool cont;
   cudaStream_t stream = nullptr, own_stream = nullptr;
@@ -74,6 +88,7 @@ struct vaeb_handle {
   float *d_vmu = nullptr, *d_vsig = nullptr, *d_ada_mu = nullptr, *d_ada_sig = nullptr;
   float *d_gmu = nullptr, *d_gsig = nullptr, *d_theta = nullptr, *d_zeta = nullptr;
   float* d_tprior = nullptr;          // [TP_BLOCKS] partial sums of thetaPrior
+  unsigned int* d_counter = nullptr;  // last-block-done counter of latent_bwd
   float* d_x = nullptr; int64_t n_data = 0;
   Workspace ws;
   float* d_stage = nullptr; int64_t stage_cap = 0;       // device staging for host inputs

@@ -1,0 +1,42 @@
+// Host interface of the tcgen05 layer kernels (tc_layers.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#define TC_LAYER_MAPS_BYTES 512   // four CUtensorMap (hi/lo of A and B)
+
+struct TcBuffers {   // bf16 mirrors; *l == nullptr in plain-bf16 mode
+  void *xh = nullptr, *xl = nullptr;       // data rows          [rows_data, ldx], ones column at D
+  void *w3h = nullptr, *w3l = nullptr;     // W3                 [D, ldh]
+  void *w2h = nullptr, *w2l = nullptr;     // W2                 [H, ldd]
+  void *hdh = nullptr, *hdl = nullptr;     // h_d                [R, ldh], ones column at H
+  void *da2h = nullptr, *da2l = nullptr;   // d bound / d a      [R, ldd]
+  void *da3h = nullptr, *da3l = nullptr;   // d bound / d a3     [rows, ldh]
+  int ldx = 0, ldh = 0, ldd = 0;
+};
+
+struct TcMaps {
+  alignas(64) unsigned char enc1[TC_LAYER_MAPS_BYTES];
+  alignas(64) unsigned char dec2[TC_LAYER_MAPS_BYTES];
+  alignas(64) unsigned char dgrad[TC_LAYER_MAPS_BYTES];
+  alignas(64) unsigned char wgrad2[TC_LAYER_MAPS_BYTES];
+  alignas(64) unsigned char wgrad3[TC_LAYER_MAPS_BYTES];
+};
+
+int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn);
+
+cudaError_t tc_split_matrix(cudaStream_t st, int64_t* launches, const float* src, int64_t rows, int cols, int ld_src,
+                            void* hi, void* lo, int ld_dst, int ones_col);
+cudaError_t tc_mirror_weights(cudaStream_t st, int64_t* launches, const float* w3, void* w3h, void* w3l, int D, int H,
+                              int ldh, const float* w2, void* w2h, void* w2l, int ldd);
+cudaError_t tc_enc1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int D, int H,
+                    int x_row_off, const float* b3, float* h_e);
+cudaError_t tc_dec2_bernoulli(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
+                              const float* b2, const float* x, int x_div, int x_mod, float scale, void* da_hi,
+                              void* da_lo, int ldda, float* partial, int* n_tiles);
+cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int D, int H,
+                        const float* h_d, float* da1);
+cudaError_t tc_wgrad2(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
+                      float* gW2, float* gb2);
+cudaError_t tc_wgrad3(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int D, int H,
+                      int x_row_off, float* gW3, float* gb3);

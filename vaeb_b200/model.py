@@ -65,7 +65,8 @@ def _as_array(p):
 class VAEB(object):
     # extension keywords (all keyword-only, defaults keep the reference behaviour):
     #   device         CUDA ordinal
-    #   precision      'fp32' (FFMA tiles, 1e-4 tier) | 'bf16' (tcgen05, 1e-2 tier)
+    #   precision      'fp32' (FFMA tiles, 1e-4 tier) | 'bf16' (tcgen05, 1e-2 tier) |
+    #                  'bf16x3' (tcgen05 with hi/lo operand split, 1e-4 tier)
     #   eps_mode       'philox' on-device noise | 'theano' host RandomStreams emulation
     #   sample_weights full-VB with sample_variational_params live (VAEB.py:127-129)
     #   variant        'vaeb' | 'fullbayes' (VAEBfullbayes.py objective/update scalars)
@@ -112,7 +113,7 @@ class VAEB(object):
             input_dim=self.input_size, hidden_units=hidden_units, latent_size=latent_size, batch_size=batch_size,
             L=L, continuous=int(self.continuous), estimator=est,
             variant=_lib.VARIANT_FULLBAYES if variant == "fullbayes" else _lib.VARIANT_VAEB,
-            precision={"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}[precision], device=device,
+            precision={"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "bf16x3": _lib.PREC_BF16X3}[precision], device=device,
             learning_rate=learning_rate, adagrad_eps=self.eps, prior_scale=1.0,
             sigma_vb_init=self.fullVBSigmaInit, seed=seed)
         self._h = C.c_void_p()
