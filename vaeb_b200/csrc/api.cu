@@ -111,7 +111,7 @@ int ensure_ws(vaeb_handle* h, int64_t enc, int64_t dec, bool grads) {
   grads = grads || w.with_grads;
   free_ws(w);
   const int D = h->D, H = h->H, Z = h->Z;
-  const int64_t T = (D + 31) / 32;
+  const int64_t T = std::max<int64_t>((D + 31) / 32, 4 * ((D + 63) / 64));   // row-sum partials per row
   auto A = [&](float** p, int64_t n) -> int {
     VAEB_CUDA(cudaMalloc((void**)p, (size_t)std::max<int64_t>(n, 1) * sizeof(float)));
     return VAEB_OK;
@@ -253,9 +253,11 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
     PH("enc1 x.W3+tanh", 2 * dr * dD * dH, 4 * (dr * dD + dD * dH + dr * dH),
        launch_dense_act(st, lc, x, rows, D, T_(h, theta, l.iW3), T_(h, theta, l.ib3), H, 1, s.h_e));
   // latent heads + reparameterisation + row terms + decoder hidden layer, VAEB.py:248-254,41-47,343
+  PH("transpose W4,W5", 0, 16 * dH * dZ,
+     launch_transpose_heads(st, lc, T_(h, theta, l.iW4), T_(h, theta, l.iW5), H, Z, h->d_w45t));
   PH("latent fwd (enc2,reparam,KL,dec1)", 4 * dr * dH * dZ + 2 * dR * dZ * dH,
      4 * (dr * dH + 3 * dH * dZ + 2 * dr * dZ + 2 * dR * dZ + dR * dH),
-     launch_latent_fwd(st, lc, s.h_e, rows, H, T_(h, theta, l.iW4), T_(h, theta, l.ib4), T_(h, theta, l.iW5),
+     launch_latent_fwd(st, lc, s.h_e, rows, H, h->d_w45t, T_(h, theta, l.ib4),
                        T_(h, theta, l.ib5), T_(h, theta, l.iW1), T_(h, theta, l.ib1), Z, L, la, src, s.mu, s.ls,
                        s.eps, s.z, s.row_aux, s.h_d, tcp ? tb.hdh : nullptr, tcp ? tb.hdl : nullptr, tb.ldh));
   // decoder output layer + log-likelihood, VAEB.py:257-263,302-313
@@ -296,7 +298,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   }
   PH("latent bwd (dz,dmu,dls,da3,bound)", 2 * dR * dZ * dH + 4 * dr * dH * dZ,
      4 * (dR * dH + 3 * dZ * dH + 2 * dr * dH + 3 * dR * dZ + dR * tiles),
-     launch_latent_bwd(st, lc, s.da1, T_(h, theta, l.iW1), T_(h, theta, l.iW4), T_(h, theta, l.iW5), s.h_e, s.z, s.eps,
+     launch_latent_bwd(st, lc, s.da1, T_(h, theta, l.iW1), h->d_w45t, s.h_e, s.z, s.eps,
                        s.mu, s.ls, rows, H, Z, L, la, w, s.dmu, s.dls, s.da3, tcp ? tb.da3h : nullptr,
                        tcp ? tb.da3l : nullptr, tb.ldh, s.partial, tiles,
                        s.row_aux, s.per_row, h->d_counter, bo.base_out, bo.mult, bo.tprior, bo.n_tprior, bo.div,
@@ -486,6 +488,7 @@ int vaeb_create(const vaeb_config* cfg, vaeb_handle** out) {
     VAEB_TRY(alloc_flat(&h->d_tprior, VAEB_TP_BLOCKS));
   }
   VAEB_CUDA(cudaMalloc((void**)&h->d_counter, sizeof(unsigned int)));
+  VAEB_CUDA(cudaMalloc((void**)&h->d_w45t, (size_t)2 * h->Z * h->H * sizeof(float)));
   VAEB_CUDA(cudaMemset(h->d_counter, 0, sizeof(unsigned int)));
   VAEB_TRY(ensure_scalars(h, 1024));
   *out = h;
@@ -503,6 +506,7 @@ int vaeb_destroy(vaeb_handle* h) {
                    h->d_scalars};
   for (float* p : bufs) if (p) cudaFree(p);
   if (h->d_counter) cudaFree(h->d_counter);
+  if (h->d_w45t) cudaFree(h->d_w45t);
   {
     TcBuffers& b = h->tc.data;
     void* tb[] = {b.xh, b.xl, b.w3h, b.w3l, b.w2h, b.w2l, b.hdh, b.hdl, b.da2h, b.da2l, b.da3h, b.da3l, h->tc.xsh, h->tc.xsl};

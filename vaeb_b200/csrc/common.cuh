@@ -89,6 +89,7 @@ struct vaeb_handle {
   float *d_gmu = nullptr, *d_gsig = nullptr, *d_theta = nullptr, *d_zeta = nullptr;
   float* d_tprior = nullptr;          // [TP_BLOCKS] partial sums of thetaPrior
   unsigned int* d_counter = nullptr;  // last-block-done counter of latent_bwd
+  float* d_w45t = nullptr;            // [2Z, H] transposed latent-head weights of the current theta
   float* d_x = nullptr; int64_t n_data = 0;
   Workspace ws;
   float* d_stage = nullptr; int64_t stage_cap = 0;       // device staging for host inputs

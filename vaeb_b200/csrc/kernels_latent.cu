@@ -14,7 +14,8 @@
 
 namespace {
 
-constexpr int MAX_WARPS = 16;
+constexpr int NWARPS = 16;          // 512 threads per block
+constexpr int NTHREADS = NWARPS * 32;
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -28,68 +29,91 @@ __device__ __forceinline__ void store_split(__nv_bfloat16* hi, __nv_bfloat16* lo
   if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
-// acc[q] += sum_{k = lane, lane+32, ...} a[k] * Wm[k*ldw + c0 + q]   (q < nq <= 8), 4 k's in flight
-__device__ __forceinline__ void dot8_strided(const float* __restrict__ a, int K, const float* __restrict__ Wm,
-                                             int ldw, int c0, int nq, int lane, float acc[8]) {
-  for (int k0 = lane; k0 < K; k0 += 128) {
-    float av[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) av[u] = (k0 + 32 * u < K) ? a[k0 + 32 * u] : 0.f;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int k = min(k0 + 32 * u, K - 1);
-      const float* wr = Wm + (size_t)k * ldw + c0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (q < nq) acc[q] = fmaf(av[u], wr[q], acc[q]);
-    }
-  }
+// W45T = [W4^T ; W5^T] ([2Z, H], H contiguous): both latent heads and their backward read the
+// head weights with the hidden index contiguous (coalesced over lanes).
+__global__ void __launch_bounds__(256)
+transpose_heads_kernel(const float* __restrict__ W4, const float* __restrict__ W5, int H, int Z,
+                       float* __restrict__ w45t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * Z * H) return;
+  const int o = i / H, k = i % H;
+  w45t[i] = (o < Z) ? W4[(size_t)k * Z + o] : W5[(size_t)k * Z + (o - Z)];
 }
 
-// One block per datapoint.  Warps split the 2Z head outputs in chunks of 8 (phase 1); warp 0 does the
-// reparameterisation (phase 2); all threads share the decoder hidden layer (phase 3).
-__global__ void __launch_bounds__(MAX_WARPS * 32)
-latent_fwd_kernel(const float* __restrict__ h_e, int rows, int H, const float* __restrict__ W4,
-                  const float* __restrict__ b4, const float* __restrict__ W5, const float* __restrict__ b5,
-                  const float* __restrict__ W1, const float* __restrict__ b1, int Z, int L, int la, EpsSource src,
-                  float* __restrict__ mu, float* __restrict__ ls, float* __restrict__ eps, float* __restrict__ z,
+// A block owns RB datapoints.  Phase 1: the 2Z head pre-activations; warps split (chunk of 8
+// outputs) x (slice of the hidden index), every weight is loaded once per block and reused for
+// the RB rows.  Phase 2: reparameterisation + row terms (one thread per (row, j)).  Phase 3:
+// decoder hidden layer, one thread per hidden unit, W1 column held in registers across the rows.
+template <int RB>
+__global__ void __launch_bounds__(NTHREADS)
+latent_fwd_kernel(const float* __restrict__ h_e, int rows, int H, const float* __restrict__ w45t,
+                  const float* __restrict__ b4, const float* __restrict__ b5, const float* __restrict__ W1,
+                  const float* __restrict__ b1, int Z, int L, int la, EpsSource src, float* __restrict__ mu,
+                  float* __restrict__ ls, float* __restrict__ eps, float* __restrict__ z,
                   float* __restrict__ row_aux, float* __restrict__ h_d, __nv_bfloat16* __restrict__ hd_hi,
-                  __nv_bfloat16* __restrict__ hd_lo, int ld_mirror) {
+                  __nv_bfloat16* __restrict__ hd_lo, int ld_mirror, int KS) {
   extern __shared__ float sm[];
-  float* out = sm;            // [2Z] mu | ls
-  float* zs = sm + 2 * Z;     // [Z] z of the current sample
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  const int m = blockIdx.x;
-  const float* hr = h_e + (size_t)m * H;
-  const int cpm = (Z + 7) / 8;                 // chunks per head matrix
-  for (int c = warp; c < 2 * cpm; c += nwarps) {
-    const int mat = c / cpm, c0 = (c % cpm) * 8, nq = min(8, Z - c0);
-    float acc[8];
+  const int Z2 = 2 * Z;
+  float* part = sm;                         // [KS][RB][2Z]
+  float* out = part + KS * RB * Z2;         // [RB][2Z] mu | ls
+  float* zs = out + RB * Z2;                // [RB][Z]  z of the current sample
+  float* terms = zs + RB * Z;               // [RB][Z]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * RB;
+  const int nchunks = (Z2 + 7) / 8;
+  for (int task = warp; task < nchunks * KS; task += NWARPS) {
+    const int c0 = (task % nchunks) * 8, sl = task / nchunks;
+    const int nq = min(8, Z2 - c0);
+    const int k_lo = (int)(((long)H * sl) / KS), k_hi = (int)(((long)H * (sl + 1)) / KS);
+    float acc[RB][8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-    dot8_strided(hr, H, mat ? W5 : W4, Z, c0, nq, lane, acc);
+    for (int r = 0; r < RB; ++r)
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float t = warp_sum(acc[q]);
-      if (lane == 0 && q < nq) out[mat * Z + c0 + q] = t + (mat ? b5[c0 + q] : b4[c0 + q]);
+      for (int q = 0; q < 8; ++q) acc[r][q] = 0.f;
+    for (int k = k_lo + lane; k < k_hi; k += 32) {
+      float wv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) wv[q] = (q < nq) ? w45t[(size_t)(c0 + q) * H + k] : 0.f;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const float hv = (m0 + r < rows) ? h_e[(size_t)(m0 + r) * H + k] : 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[r][q] = fmaf(hv, wv[q], acc[r][q]);
+      }
     }
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float t = warp_sum(acc[r][q]);
+        if (lane == 0 && q < nq) part[(sl * RB + r) * Z2 + c0 + q] = t;
+      }
   }
   __syncthreads();
-  float term = 0.f, la_acc = 0.f;
-  if (warp == 0) {
-    for (int j = lane; j < Z; j += 32) {
-      const float am = out[j], al = out[Z + j];
+  for (int i = threadIdx.x; i < RB * Z2; i += NTHREADS) {
+    const int o = i % Z2;
+    float t = (o < Z) ? b4[o] : b5[o - Z];
+    for (int sl = 0; sl < KS; ++sl) t += part[sl * RB * Z2 + i];
+    out[i] = t;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < RB * Z; i += NTHREADS) {
+    const int r = i / Z, j = i % Z, m = m0 + r;
+    float term = 0.f;
+    if (m < rows) {
+      const float am = out[r * Z2 + j], al = out[r * Z2 + Z + j];
       mu[(size_t)m * Z + j] = am;
       ls[(size_t)m * Z + j] = al;
-      if (!la) term += 0.5f * (1.0f + al - am * am - expf(al));
+      if (!la) term = 0.5f * (1.0f + al - am * am - expf(al));
     }
+    terms[i] = term;
   }
   for (int l = 0; l < L; ++l) {
-    const size_t r = (size_t)l * rows + m;
-    if (warp == 0) {
-      for (int j = lane; j < Z; j += 32) {
-        const float am = out[j], al = out[Z + j];
-        const size_t o2 = r * Z + j;
+    for (int i = threadIdx.x; i < RB * Z; i += NTHREADS) {
+      const int r = i / Z, j = i % Z, m = m0 + r;
+      if (m < rows) {
+        const float am = out[r * Z2 + j], al = out[r * Z2 + Z + j];
+        const size_t o2 = ((size_t)l * rows + m) * Z + j;
         const float e = src.injected
                             ? src.injected[o2]
                             : philox_normal1(src.seed, src.stream, src.step, (uint32_t)l,
@@ -97,24 +121,37 @@ latent_fwd_kernel(const float* __restrict__ h_e, int rows, int H, const float* _
         const float zv = am + expf(0.5f * al) * e;
         eps[o2] = e;
         z[o2] = zv;
-        zs[j] = zv;
-        la_acc += -0.5f * zv * zv + 0.5f * al + 0.5f * e * e;
+        zs[i] = zv;
+        if (la) terms[i] += (-0.5f * zv * zv + 0.5f * al + 0.5f * e * e) / (float)L;
       }
     }
     __syncthreads();
-    for (int n = threadIdx.x; n < H; n += blockDim.x) {
-      float a = b1[n];
-      for (int j = 0; j < Z; ++j) a = fmaf(zs[j], W1[(size_t)j * H + n], a);
-      const float hv = tanhf(a);
-      h_d[r * H + n] = hv;
-      if (hd_hi) store_split(hd_hi, hd_lo, r * ld_mirror + n, hv);
+    for (int n = threadIdx.x; n < H; n += NTHREADS) {
+      float a[RB];
+      const float bn = b1[n];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) a[r] = bn;
+      for (int j = 0; j < Z; ++j) {
+        const float wv = W1[(size_t)j * H + n];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) a[r] = fmaf(zs[r * Z + j], wv, a[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        if (m0 + r < rows) {
+          const size_t rr = (size_t)l * rows + m0 + r;
+          const float hv = tanhf(a[r]);
+          h_d[rr * H + n] = hv;
+          if (hd_hi) store_split(hd_hi, hd_lo, rr * ld_mirror + n, hv);
+        }
+      }
     }
     __syncthreads();
   }
-  if (warp == 0) {
-    if (la && L > 0) term = la_acc / (float)L;
-    term = warp_sum(term);
-    if (lane == 0) row_aux[m] = term;
+  if (threadIdx.x < RB && m0 + threadIdx.x < rows) {
+    float t = 0.f;
+    for (int j = 0; j < Z; ++j) t += terms[threadIdx.x * Z + j];
+    row_aux[m0 + threadIdx.x] = t;
   }
 }
 
@@ -134,102 +171,127 @@ __device__ float block_total(const float* __restrict__ v, int n, float* red) {
   return s;
 }
 
-// One block per datapoint: dz by warps (chunks of 8 latent dims), dmu/dls by warp 0, da3 and the
-// bound by all threads; the last block to finish totals the per-row bounds in a fixed order.
-__global__ void __launch_bounds__(MAX_WARPS * 32)
-latent_bwd_kernel(const float* __restrict__ da1, const float* __restrict__ W1, const float* __restrict__ W4,
-                  const float* __restrict__ W5, const float* __restrict__ h_e, const float* __restrict__ z,
-                  const float* __restrict__ eps, const float* __restrict__ mu, const float* __restrict__ ls,
-                  int rows, int H, int Z, int L, int la, float w, float* __restrict__ dmu, float* __restrict__ dls,
-                  float* __restrict__ da3, __nv_bfloat16* __restrict__ da3_hi, __nv_bfloat16* __restrict__ da3_lo,
-                  int ld_mirror, const float* __restrict__ partial, int n_tiles, const float* __restrict__ row_aux,
+// A block owns RB datapoints: dz (warps split latent chunks x hidden slices), dmu/dls, da3 (one
+// thread per hidden unit, head weights held in registers across the rows), the per-row bound; the
+// last block to finish totals the per-row bounds in a fixed order.
+template <int RB>
+__global__ void __launch_bounds__(NTHREADS)
+latent_bwd_kernel(const float* __restrict__ da1, const float* __restrict__ W1, const float* __restrict__ w45t,
+                  const float* __restrict__ h_e, const float* __restrict__ z, const float* __restrict__ eps,
+                  const float* __restrict__ mu, const float* __restrict__ ls, int rows, int H, int Z, int L, int la,
+                  float w, float* __restrict__ dmu, float* __restrict__ dls, float* __restrict__ da3,
+                  __nv_bfloat16* __restrict__ da3_hi, __nv_bfloat16* __restrict__ da3_lo, int ld_mirror,
+                  const float* __restrict__ partial, int n_tiles, const float* __restrict__ row_aux,
                   float* __restrict__ per_row, unsigned int* __restrict__ counter, float* __restrict__ base_out,
                   float mult, const float* __restrict__ tprior, int n_tprior, float div,
-                  float* __restrict__ scalar_out) {
+                  float* __restrict__ scalar_out, int NSL) {
   extern __shared__ float sm[];
-  __shared__ float red[MAX_WARPS];
+  __shared__ float red[NWARPS];
   __shared__ int is_last;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  float* dm = sm;          // [Z] dmu
-  float* dl = dm + Z;      // [Z] dls
-  float* dzs = dl + Z;     // [Z] dz of the current sample
-  const int m = blockIdx.x;
+  float* part = sm;                    // [NSL][RB][Z]
+  float* dm = part + NSL * RB * Z;     // [RB][Z] dmu
+  float* dl = dm + RB * Z;             // [RB][Z] dls
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * RB;
   const float s = w / (float)L;
-  for (int j = threadIdx.x; j < Z; j += blockDim.x) { dm[j] = 0.f; dl[j] = 0.f; }
-  __syncthreads();
+  const int nchunks = (Z + 7) / 8;
+  for (int i = threadIdx.x; i < RB * Z; i += NTHREADS) { dm[i] = 0.f; dl[i] = 0.f; }
   for (int l = 0; l < L; ++l) {
-    const size_t r = (size_t)l * rows + m;
-    const float* dr = da1 + r * H;
-    // dz[j] = sum_n da1[r,n] W1[j,n]: W1 rows are contiguous in n, 4 n's in flight per lane
-    for (int c0 = warp * 8; c0 < Z; c0 += nwarps * 8) {
+    // dz[r][j] = sum_n da1[(l,m0+r), n] W1[j, n]
+    for (int task = warp; task < nchunks * NSL; task += NWARPS) {
+      const int c0 = (task % nchunks) * 8, sl = task / nchunks;
       const int nq = min(8, Z - c0);
-      float acc[8];
+      const int n_lo = (int)(((long)H * sl) / NSL), n_hi = (int)(((long)H * (sl + 1)) / NSL);
+      float acc[RB][8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-      for (int n0 = lane; n0 < H; n0 += 128) {
+      for (int r = 0; r < RB; ++r)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int n = n0 + 32 * u;
-          if (n < H) {
-            const float dv = dr[n];
+        for (int q = 0; q < 8; ++q) acc[r][q] = 0.f;
+      for (int n = n_lo + lane; n < n_hi; n += 32) {
+        float wv[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (q < nq) acc[q] = fmaf(dv, W1[(size_t)(c0 + q) * H + n], acc[q]);
-          }
+        for (int q = 0; q < 8; ++q) wv[q] = (q < nq) ? W1[(size_t)(c0 + q) * H + n] : 0.f;
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const float dv = (m0 + r < rows) ? da1[((size_t)l * rows + m0 + r) * H + n] : 0.f;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[r][q] = fmaf(dv, wv[q], acc[r][q]);
         }
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float t = warp_sum(acc[q]);
-        if (lane == 0 && q < nq) dzs[c0 + q] = t;
+      for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float t = warp_sum(acc[r][q]);
+          if (lane == 0 && q < nq) part[(sl * RB + r) * Z + c0 + q] = t;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RB * Z; i += NTHREADS) {
+      const int r = i / Z, j = i % Z, m = m0 + r;
+      if (m < rows) {
+        float d = 0.f;
+        for (int sl = 0; sl < NSL; ++sl) d += part[sl * RB * Z + i];
+        const size_t o2 = ((size_t)l * rows + m) * Z + j;
+        if (la) d -= s * z[o2];
+        const float sd = expf(0.5f * ls[(size_t)m * Z + j]);
+        dm[i] += d;
+        dl[i] += d * (0.5f * sd * eps[o2]);
       }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < Z; j += blockDim.x) {
-      const size_t o2 = r * Z + j;
-      float d = dzs[j];
-      if (la) d -= s * z[o2];
-      const float sd = expf(0.5f * ls[(size_t)m * Z + j]);
-      dm[j] += d;
-      dl[j] += d * (0.5f * sd * eps[o2]);
-    }
-    __syncthreads();
   }
-  for (int j = threadIdx.x; j < Z; j += blockDim.x) {
-    const float lsv = ls[(size_t)m * Z + j], muv = mu[(size_t)m * Z + j];
-    float a = dm[j], b = dl[j];
-    if (la) {
-      b += w * 0.5f;
-    } else {
-      a -= w * muv;
-      b += w * 0.5f * (1.0f - expf(lsv));
+  for (int i = threadIdx.x; i < RB * Z; i += NTHREADS) {
+    const int r = i / Z, j = i % Z, m = m0 + r;
+    if (m < rows) {
+      const float lsv = ls[(size_t)m * Z + j], muv = mu[(size_t)m * Z + j];
+      float a = dm[i], b = dl[i];
+      if (la) {
+        b += w * 0.5f;
+      } else {
+        a -= w * muv;
+        b += w * 0.5f * (1.0f - expf(lsv));
+      }
+      dm[i] = a;
+      dl[i] = b;
+      dmu[(size_t)m * Z + j] = a;
+      dls[(size_t)m * Z + j] = b;
     }
-    dm[j] = a;
-    dl[j] = b;
-    dmu[(size_t)m * Z + j] = a;
-    dls[(size_t)m * Z + j] = b;
   }
   __syncthreads();
   // da3[m,n] = (sum_j dmu_j W4[n,j] + dls_j W5[n,j]) * (1 - h_e^2)
-  for (int n = threadIdx.x; n < H; n += blockDim.x) {
-    float a = 0.f;
-    const float* w4 = W4 + (size_t)n * Z;
-    const float* w5 = W5 + (size_t)n * Z;
-    for (int j = 0; j < Z; ++j) a = fmaf(dm[j], w4[j], fmaf(dl[j], w5[j], a));
-    const float hv = h_e[(size_t)m * H + n];
-    const float v = a * (1.0f - hv * hv);
-    da3[(size_t)m * H + n] = v;
-    if (da3_hi) store_split(da3_hi, da3_lo, (size_t)m * ld_mirror + n, v);
-  }
-  // per-datapoint bound: (1/L) sum_l sum_tiles partial + row_aux   (last warp)
-  if (warp == nwarps - 1) {
-    float t = 0.f;
-    for (int l = 0; l < L; ++l) {
-      const float* p = partial + ((size_t)l * rows + m) * n_tiles;
-      for (int q = lane; q < n_tiles; q += 32) t += p[q];
+  for (int n = threadIdx.x; n < H; n += NTHREADS) {
+    float a[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) a[r] = 0.f;
+    for (int j = 0; j < Z; ++j) {
+      const float w4 = w45t[(size_t)j * H + n], w5 = w45t[(size_t)(Z + j) * H + n];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) a[r] = fmaf(dm[r * Z + j], w4, fmaf(dl[r * Z + j], w5, a[r]));
     }
-    t = warp_sum(t);
-    if (lane == 0) per_row[m] = t / (float)L + row_aux[m];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const int m = m0 + r;
+      if (m < rows) {
+        const float hv = h_e[(size_t)m * H + n];
+        const float v = a[r] * (1.0f - hv * hv);
+        da3[(size_t)m * H + n] = v;
+        if (da3_hi) store_split(da3_hi, da3_lo, (size_t)m * ld_mirror + n, v);
+      }
+    }
+  }
+  // per-datapoint bound: (1/L) sum_l sum_tiles partial + row_aux   (one warp per row, from the top)
+  for (int r = NWARPS - 1 - warp; r < RB; r += NWARPS) {
+    const int m = m0 + r;
+    if (m < rows) {
+      float t = 0.f;
+      for (int l = 0; l < L; ++l) {
+        const float* p = partial + ((size_t)l * rows + m) * n_tiles;
+        for (int q = lane; q < n_tiles; q += 32) t += p[q];
+      }
+      t = warp_sum(t);
+      if (lane == 0) per_row[m] = t / (float)L + row_aux[m];
+    }
   }
   // the last block to finish totals the rows in a fixed order (deterministic)
   __threadfence();
@@ -345,33 +407,59 @@ small_wgrad_reduce_kernel(const float* __restrict__ scratch, int nchunks, int H,
 
 }  // namespace
 
-cudaError_t launch_latent_fwd(cudaStream_t st, int64_t* launches, const float* h_e, int rows, int H, const float* W4,
-                              const float* b4, const float* W5, const float* b5, const float* W1, const float* b1,
-                              int Z, int L, int la, EpsSource src, float* mu, float* ls, float* eps, float* z,
-                              float* row_aux, float* h_d, void* hd_hi, void* hd_lo, int ld_mirror) {
-  const size_t smem = (size_t)3 * Z * sizeof(float);
-  const int nw = max(4, min(MAX_WARPS, 2 * ((Z + 7) / 8)));
-  latent_fwd_kernel<<<rows, nw * 32, smem, st>>>(
-      h_e, rows, H, W4, b4, W5, b5, W1, b1, Z, L, la, src, mu, ls, eps, z, row_aux, h_d, (__nv_bfloat16*)hd_hi,
-      (__nv_bfloat16*)hd_lo, ld_mirror);
+cudaError_t launch_transpose_heads(cudaStream_t st, int64_t* launches, const float* W4, const float* W5, int H, int Z,
+                                   float* w45t) {
+  transpose_heads_kernel<<<(2 * Z * H + 255) / 256, 256, 0, st>>>(W4, W5, H, Z, w45t);
   ++*launches;
   return cudaGetLastError();
 }
 
-cudaError_t launch_latent_bwd(cudaStream_t st, int64_t* launches, const float* da1, const float* W1, const float* W4,
-                              const float* W5, const float* h_e, const float* z, const float* eps, const float* mu,
+cudaError_t launch_latent_fwd(cudaStream_t st, int64_t* launches, const float* h_e, int rows, int H,
+                              const float* w45t, const float* b4, const float* b5, const float* W1, const float* b1,
+                              int Z, int L, int la, EpsSource src, float* mu, float* ls, float* eps, float* z,
+                              float* row_aux, float* h_d, void* hd_hi, void* hd_lo, int ld_mirror) {
+  const int nchunks = (2 * Z + 7) / 8;
+  const int KS = max(1, NWARPS / nchunks);
+  ++*launches;
+  if (rows <= 512) {
+    const size_t smem = (size_t)((KS + 1) * 2 * Z + 2 * Z) * sizeof(float);
+    latent_fwd_kernel<1><<<rows, NTHREADS, smem, st>>>(h_e, rows, H, w45t, b4, b5, W1, b1, Z, L, la, src, mu, ls, eps,
+                                                      z, row_aux, h_d, (__nv_bfloat16*)hd_hi, (__nv_bfloat16*)hd_lo,
+                                                      ld_mirror, KS);
+  } else {
+    constexpr int RB = 8;
+    const size_t smem = (size_t)RB * ((KS + 1) * 2 * Z + 2 * Z) * sizeof(float);
+    latent_fwd_kernel<RB><<<(rows + RB - 1) / RB, NTHREADS, smem, st>>>(
+        h_e, rows, H, w45t, b4, b5, W1, b1, Z, L, la, src, mu, ls, eps, z, row_aux, h_d, (__nv_bfloat16*)hd_hi,
+        (__nv_bfloat16*)hd_lo, ld_mirror, KS);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_latent_bwd(cudaStream_t st, int64_t* launches, const float* da1, const float* W1,
+                              const float* w45t, const float* h_e, const float* z, const float* eps, const float* mu,
                               const float* ls, int rows, int H, int Z, int L, int la, float w, float* dmu, float* dls,
                               float* da3, void* da3_hi, void* da3_lo, int ld_mirror, const float* partial,
                               int n_tiles, const float* row_aux, float* per_row, unsigned int* counter,
                               float* base_out, float mult, const float* tprior, int n_tprior, float div,
                               float* scalar_out) {
-  const size_t smem = (size_t)3 * Z * sizeof(float);
-  const int nw = max(4, min(MAX_WARPS, (Z + 7) / 8 + 1));
-  latent_bwd_kernel<<<rows, nw * 32, smem, st>>>(
-      da1, W1, W4, W5, h_e, z, eps, mu, ls, rows, H, Z, L, la, w, dmu, dls, da3, (__nv_bfloat16*)da3_hi,
-      (__nv_bfloat16*)da3_lo, ld_mirror, partial, n_tiles, row_aux, per_row, counter, base_out, mult, tprior,
-      n_tprior, div, scalar_out);
+  const int nchunks = (Z + 7) / 8;
+  const int NSL = max(1, (NWARPS - 2) / nchunks);
   ++*launches;
+  if (rows <= 512) {
+    const size_t smem = (size_t)(NSL + 2) * Z * sizeof(float);
+    latent_bwd_kernel<1><<<rows, NTHREADS, smem, st>>>(
+        da1, W1, w45t, h_e, z, eps, mu, ls, rows, H, Z, L, la, w, dmu, dls, da3, (__nv_bfloat16*)da3_hi,
+        (__nv_bfloat16*)da3_lo, ld_mirror, partial, n_tiles, row_aux, per_row, counter, base_out, mult, tprior,
+        n_tprior, div, scalar_out, NSL);
+  } else {
+    constexpr int RB = 8;
+    const size_t smem = (size_t)RB * (NSL + 2) * Z * sizeof(float);
+    latent_bwd_kernel<RB><<<(rows + RB - 1) / RB, NTHREADS, smem, st>>>(
+        da1, W1, w45t, h_e, z, eps, mu, ls, rows, H, Z, L, la, w, dmu, dls, da3, (__nv_bfloat16*)da3_hi,
+        (__nv_bfloat16*)da3_lo, ld_mirror, partial, n_tiles, row_aux, per_row, counter, base_out, mult, tprior,
+        n_tprior, div, scalar_out, NSL);
+  }
   return cudaGetLastError();
 }
 

@@ -82,15 +82,18 @@ cudaError_t launch_philox_fill(cudaStream_t st, int64_t* launches, uint64_t seed
                                uint32_t sample, int64_t first, int64_t n, float* out);
 
 // ---- latent-layer kernels (kernels_latent.cu) ------------------------------------------
-// enc2 + reparameterisation + row terms + decoder hidden layer, one warp per datapoint.
+// w45t[2Z, H] = [W4^T ; W5^T]: head weights with the hidden index contiguous
+cudaError_t launch_transpose_heads(cudaStream_t st, int64_t* launches, const float* W4, const float* W5, int H, int Z,
+                                   float* w45t);
+// enc2 + reparameterisation + row terms + decoder hidden layer.
 // hd_hi/hd_lo: optional bf16 mirrors [L*rows, ld_mirror] of h_d for the tcgen05 GEMMs.
-cudaError_t launch_latent_fwd(cudaStream_t st, int64_t* launches, const float* h_e, int rows, int H, const float* W4,
-                              const float* b4, const float* W5, const float* b5, const float* W1, const float* b1,
+cudaError_t launch_latent_fwd(cudaStream_t st, int64_t* launches, const float* h_e, int rows, int H,
+                              const float* w45t, const float* b4, const float* b5, const float* W1, const float* b1,
                               int Z, int L, int la, EpsSource src, float* mu, float* ls, float* eps, float* z,
                               float* row_aux, float* h_d, void* hd_hi, void* hd_lo, int ld_mirror);
 // dz, dmu/dls, da3 and the bound (per row + deterministic total by the last block to finish).
-cudaError_t launch_latent_bwd(cudaStream_t st, int64_t* launches, const float* da1, const float* W1, const float* W4,
-                              const float* W5, const float* h_e, const float* z, const float* eps, const float* mu,
+cudaError_t launch_latent_bwd(cudaStream_t st, int64_t* launches, const float* da1, const float* W1,
+                              const float* w45t, const float* h_e, const float* z, const float* eps, const float* mu,
                               const float* ls, int rows, int H, int Z, int L, int la, float w, float* dmu, float* dls,
                               float* da3, void* da3_hi, void* da3_lo, int ld_mirror, const float* partial,
                               int n_tiles, const float* row_aux, float* per_row, unsigned int* counter,

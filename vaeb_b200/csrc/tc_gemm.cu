@@ -29,7 +29,9 @@ struct GemmSmem {
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(256, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
-               int M, int N, int K, int ldc) {
+               int M, int N, int K, int ldc, long long* __restrict__ dbg) {
+  const bool rec = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  if (rec && threadIdx.x == 0) dbg[0] = clock64();
   using S = GemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -55,6 +57,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (rec && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
@@ -62,6 +65,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
       tc::mbar_wait(&empty[s], ph ^ 1);
+      if (rec && kb < 16) dbg[8 + kb] = clock64();
       uint8_t* a = smem + s * S::STAGE_BYTES;
       uint8_t* b = a + S::A_BYTES;
       tc::mbar_expect_tx(&full[s], S::STAGE_BYTES);
@@ -84,6 +88,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t ph = (kb / STAGES) & 1;
       tc::mbar_wait(&full[s], ph);
       tc::tc_fence_after();
+      if (rec && kb < 16) dbg[24 + kb] = clock64();
       const uint32_t a = tc::smem_u32(smem + s * S::STAGE_BYTES);
       const uint32_t b = a + S::A_BYTES;
 #pragma unroll
@@ -95,10 +100,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc::umma_commit(&empty[s]);     // frees the smem slot once these MMAs have read it
     }
     tc::umma_commit(tmem_full);       // accumulator complete
+    if (rec) dbg[2] = clock64();
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> global =====
     tc::mbar_wait(tmem_full, 0);
     tc::tc_fence_after();
+    if (rec && threadIdx.x == 128) dbg[3] = clock64();
     const int q = warp & 3;                       // TMEM lane quarter of this warp
     const int row = m0 + q * 32 + lane;
 #pragma unroll 1
@@ -115,6 +122,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (rec && threadIdx.x == 0) dbg[4] = clock64();
   if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -142,12 +150,12 @@ uint16_t f32_to_bf16(float f) {   // round to nearest even
 
 template <int BN, bool A_MN, bool B_MN>
 int launch_tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, int M, int N, int K, int ldc,
-                   cudaStream_t st) {
+                   cudaStream_t st, long long* dbg = nullptr) {
   using S = GemmSmem<BN>;
   auto kfn = tc_gemm_kernel<BN, A_MN, B_MN>;
   VAEB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  kfn<<<grid, 256, S::TOTAL, st>>>(tmA, tmB, C, M, N, K, ldc);
+  kfn<<<grid, 256, S::TOTAL, st>>>(tmA, tmB, C, M, N, K, ldc, dbg);
   VAEB_CUDA(cudaGetLastError());
   return VAEB_OK;
 }
@@ -231,4 +239,43 @@ extern "C" int vaeb_tc_gemm_test(int32_t device, int32_t M, int32_t N, int32_t K
   }
   cudaFree(dA); cudaFree(dB); cudaFree(dC);
   return rc;
+}
+
+// Timeline probe of one GEMM launch (CTA 0): clock64 stamps written to dbg[40]
+//  [0] kernel start, [1] setup done, [2] last MMA issued, [3] accumulator ready, [4] epilogue done,
+//  [8+kb] producer got slot kb, [24+kb] consumer saw data of kb.  Returns also the event-timed duration of
+//  `iters` back-to-back launches.
+extern "C" int vaeb_tc_gemm_probe(int32_t device, int32_t M, int32_t N, int32_t K, int32_t a_mn_major,
+                                  int32_t b_mn_major, int32_t iters, int64_t* stamps, float* us_per_launch) {
+  VAEB_CUDA(cudaSetDevice(device));
+  void *dA = nullptr, *dB = nullptr; float* dC = nullptr; long long* dD = nullptr;
+  VAEB_CUDA(cudaMalloc(&dA, (size_t)M * K * 2)); VAEB_CUDA(cudaMalloc(&dB, (size_t)N * K * 2));
+  VAEB_CUDA(cudaMalloc((void**)&dC, (size_t)M * N * 4)); VAEB_CUDA(cudaMalloc((void**)&dD, 40 * 8));
+  VAEB_CUDA(cudaMemset(dA, 0, (size_t)M * K * 2)); VAEB_CUDA(cudaMemset(dB, 0, (size_t)N * K * 2));
+  VAEB_CUDA(cudaMemset(dD, 0, 40 * 8));
+  CUtensorMap tmA, tmB;
+  if (a_mn_major) VAEB_TRY(vaeb_make_tmap_bf16(&tmA, dA, K, M, M, 64));
+  else VAEB_TRY(vaeb_make_tmap_bf16(&tmA, dA, M, K, K, BM));
+  if (b_mn_major) VAEB_TRY(vaeb_make_tmap_bf16(&tmB, dB, K, N, N, 64));
+  else VAEB_TRY(vaeb_make_tmap_bf16(&tmB, dB, N, K, K, 64));
+  auto run = [&](long long* dbg) -> int {
+    if (a_mn_major && b_mn_major) return launch_tc_gemm<64, true, true>(tmA, tmB, dC, M, N, K, N, 0, dbg);
+    if (a_mn_major) return launch_tc_gemm<64, true, false>(tmA, tmB, dC, M, N, K, N, 0, dbg);
+    if (b_mn_major) return launch_tc_gemm<64, false, true>(tmA, tmB, dC, M, N, K, N, 0, dbg);
+    return launch_tc_gemm<64, false, false>(tmA, tmB, dC, M, N, K, N, 0, dbg);
+  };
+  for (int i = 0; i < 3; ++i) VAEB_TRY(run(nullptr));
+  VAEB_TRY(run(dD));
+  cudaEvent_t e0, e1;
+  VAEB_CUDA(cudaEventCreate(&e0)); VAEB_CUDA(cudaEventCreate(&e1));
+  VAEB_CUDA(cudaEventRecord(e0, 0));
+  for (int i = 0; i < iters; ++i) VAEB_TRY(run(nullptr));
+  VAEB_CUDA(cudaEventRecord(e1, 0));
+  VAEB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  VAEB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *us_per_launch = 1e3f * ms / iters;
+  VAEB_CUDA(cudaMemcpy(stamps, dD, 40 * 8, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dD);
+  return VAEB_OK;
 }

@@ -7,7 +7,9 @@
 //   dec2      a    = h_d.W2 + b2 -> Bernoulli log-lik, da  VAEB.py:263,311 A K-major,  B MN-major
 //   dgrad     da1  = (da.W2^T) * (1 - h_d^2)               T.grad :397     A K-major,  B K-major
 //   wgrad     gW   = [act|1]^T . delta (bias row included) T.grad :397     A MN-major, B MN-major
-// Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w4-7 epilogue.
+// Warp roles (640 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w4-19 epilogue (four
+// warps per TMEM lane quarter, each owning a quarter of the tile's columns: at M = 100 the whole
+// layer is 8-13 CTAs, so the elementwise epilogue needs all the threads it can get).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -18,6 +20,7 @@
 namespace {
 
 constexpr int BM = 128, BK = 64;
+constexpr int EPI_WARPS = 16, TC_THREADS = 128 + EPI_WARPS * 32;
 
 __device__ __forceinline__ float softplusf_(float a) { return fmaxf(a, 0.f) + log1pf(expf(-fabsf(a))); }
 __device__ __forceinline__ float sigmoidf_(float a) { return 1.0f / (1.0f + expf(-a)); }
@@ -27,14 +30,14 @@ __device__ __forceinline__ void put_split(__nv_bfloat16* hi, __nv_bfloat16* lo, 
   if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
-// ---- epilogues: one thread owns one accumulator row, 32 columns per call --------------------
+// ---- epilogues: one thread owns one accumulator row, 16 columns per call --------------------
 struct EpiTanh {            // out[row, col] = tanh(acc + bias[col])
   const float* bias; float* out; int ld;
   __device__ __forceinline__ void begin() {}
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
     if (!ok) return;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < 16; ++j)
       if (col0 + j < N) out[(size_t)row * ld + col0 + j] = tanhf(v[j] + bias[col0 + j]);
   }
   __device__ __forceinline__ void end(int, bool, int, int) {}
@@ -49,7 +52,7 @@ struct EpiBernoulliTc {     // VAEB.py:263,311: term = x*a - softplus(a); da = s
     if (!ok) return;
     const float* xr = x + (size_t)((row / x_div) % x_mod) * ldx;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < 16; ++j) {
       const int c = col0 + j;
       if (c < N) {
         const float a = v[j] + bias[c];
@@ -71,7 +74,7 @@ struct EpiWgradTc {         // rows < Hreal -> gW[Hreal, N]; row == Hreal (the o
     if (!ok) return;
     float* dst = row < Hreal ? gW + (size_t)row * ld : gb;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < 16; ++j)
       if (col0 + j < N) dst[col0 + j] = v[j];
   }
   __device__ __forceinline__ void end(int, bool, int, int) {}
@@ -83,7 +86,7 @@ struct EpiDgradTanh {       // out = acc * (1 - h^2)
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
     if (!ok) return;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < 16; ++j)
       if (col0 + j < N) {
         const float hv = h[(size_t)row * ld + col0 + j];
         out[(size_t)row * ld + col0 + j] = v[j] * (1.0f - hv * hv);
@@ -107,7 +110,7 @@ struct LayerMaps {            // hi/lo tensor maps of both operands (lo unused w
 };
 
 template <int BN, bool A_MN, bool B_MN, int NS, class Epi>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tc_layer_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, int K, int a_row_off) {
   using S = LayerSmem<BN, NS>;
   extern __shared__ uint8_t smem_raw[];
@@ -186,21 +189,22 @@ tc_layer_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, i
     }
     tc::umma_commit(tmem_full);
   } else if (warp >= 4) {
-    // ===== epilogue =====
-    const int q = warp & 3;
+    // ===== epilogue: warp e = warp-4 reads lane quarter e%4, column slice e/4 of the tile =====
+    const int q = warp & 3, cs = (warp - 4) >> 2;
+    constexpr int SLICE = BN / (EPI_WARPS / 4);
     const int row = m0 + q * 32 + lane;
     const bool ok = row < M;
     epi.begin();
     tc::mbar_wait(tmem_full, 0);
     tc::tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      float v[32];
-      tc::tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+    for (int c = cs * SLICE; c < (cs + 1) * SLICE; c += 16) {
+      float v[16];
+      tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
       tc::tmem_ld_wait();
       if (n0 + c < N) epi.chunk(row, ok, n0 + c, N, v);
     }
-    epi.end(row, ok, blockIdx.x, gridDim.x);
+    epi.end(row, ok, blockIdx.x * (EPI_WARPS / 4) + cs, gridDim.x * (EPI_WARPS / 4));
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -218,7 +222,7 @@ cudaError_t launch_layer(cudaStream_t st, const LayerMaps& maps, const Epi& epi,
     attr_done = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  kfn<<<grid, 256, S::TOTAL, st>>>(maps, epi, M, N, K, a_row_off);
+  kfn<<<grid, TC_THREADS, S::TOTAL, st>>>(maps, epi, M, N, K, a_row_off);
   return cudaGetLastError();
 }
 
@@ -326,7 +330,7 @@ cudaError_t tc_dec2_bernoulli(cudaStream_t st, int64_t* launches, const TcMaps& 
                               const float* b2, const float* x, int x_div, int x_mod, float scale, void* da_hi,
                               void* da_lo, int ldda, float* partial, int* n_tiles) {
   EpiBernoulliTc epi{b2, x, D, x_div, x_mod, scale, (__nv_bfloat16*)da_hi, (__nv_bfloat16*)da_lo, ldda, partial, 0.f};
-  *n_tiles = (D + bn - 1) / bn;
+  *n_tiles = ((D + bn - 1) / bn) * (EPI_WARPS / 4);
   ++*launches;
   return dispatch_layer<false, true>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.dec2), epi, R, D, H, 0);
 }
