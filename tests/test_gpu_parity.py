@@ -45,24 +45,28 @@ def _check_step(x, continuous, H, Z, M, L, est, params, seed):
     for a, b, n in zip(g, g_ref, O.param_names(continuous)):
         worst = max(worst, assert_close_tensor(a, b, RTOL, name="grad " + n))
     # update(): pre-update value returned, Adagrad applied.  Two checks:
-    #  (a) the Adagrad rule itself (VAEB.py:438-442) applied to the DEVICE gradient -- an exact
-    #      elementwise function, so it must hold everywhere to fp32 rounding;
+    #  (a) the Adagrad rule itself (VAEB.py:438-442).  update() runs the fused single-launch kernel,
+    #      whose gradient is summed in a different order than gradients()'s, so the rule is checked on
+    #      the gradient the update itself used: after the first step ADA = g^2 exactly, hence
+    #      |dp| = lr*sqrt(ADA)/(sqrt(ADA)+1e-6) must hold everywhere to fp32 rounding, sqrt(ADA) must
+    #      agree with |g| of gradients() at the gradient tolerance, and dp carries the sign of g;
     #  (b) end-to-end against the oracle's own update where the step is well conditioned: the
     #      first Adagrad step is lr*g/(|g|+1e-6), whose sensitivity 1e-6/(|g|+1e-6)^2 blows any
     #      gradient rounding error up wherever |g| ~ 0, so entries with |g| below 1e-3*||g||_inf
     #      are excluded from (b) (they are covered by (a) and by the gradient parity above).
     p_old = [q.copy() for q in o.params]
-    exp_params = [q.astype(np.float64) for q in m.get_params()]
-    exp_ada = [np.zeros_like(q) for q in exp_params]
-    O.adagrad_update(exp_params, exp_ada, [np.asarray(t, np.float64) for t in g], 0.01, 1e-6)
+    dev_old = [q.astype(np.float64) for q in m.get_params()]
     ret_ref = o.update(idx, eps)
     ret = m.update(idx, eps=eps)
     assert float(ret) == pytest.approx(ret_ref, rel=RTOL)
     new_params = m.get_params()
-    for a, b, n in zip(new_params, exp_params, O.param_names(continuous)):
-        np.testing.assert_allclose(a, b, rtol=2e-6, atol=2e-8, err_msg="adagrad rule " + n)
-    for a, b, n in zip(m._get_buffer(1), exp_ada, O.param_names(continuous)):
-        np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-30, err_msg="ada " + n)
+    for a, po, ada, gd, n in zip(new_params, dev_old, m._get_buffer(1), g, O.param_names(continuous)):
+        ga = np.sqrt(ada.astype(np.float64))
+        assert_close_tensor(ga, np.abs(np.asarray(gd, np.float64)), RTOL, name="sqrt(ada) " + n)
+        dp = a.astype(np.float64) - po
+        np.testing.assert_allclose(np.abs(dp), 0.01 * ga / (ga + 1e-6), rtol=1e-5, atol=2e-8, err_msg="adagrad rule " + n)
+        well = np.abs(gd) > 1e-3 * np.abs(gd).max()
+        assert np.array_equal(np.sign(dp[well]), np.sign(np.asarray(gd)[well])), "step sign " + n
     for a, b, gr, po, n in zip(new_params, o.params, g_ref, p_old, O.param_names(continuous)):
         well = np.abs(gr) > 1e-3 * np.abs(gr).max()
         np.testing.assert_allclose((a - po)[well], (b - po)[well], rtol=2e-3, atol=1e-7, err_msg="step " + n)

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -404,6 +405,26 @@ int read_scalars(vaeb_handle* h, int n, float* out) {
   return VAEB_OK;
 }
 
+// n updates through the fused single-launch kernel (fused_step.cu); scalars land in d_scalars[0..n)
+int fused_updates(vaeb_handle* h, const int32_t* batch_order, const float* d_xrows, int rows, int n,
+                  const float* d_eps) {
+  VAEB_TRY(ensure_ws(h, rows, rows, true));
+  const int* d_order = nullptr;
+  if (batch_order) {
+    FusedState& f = h->fused;
+    if (n > f.order_cap) {
+      VAEB_CUDA(cudaStreamSynchronize(h->stream));
+      if (f.d_order) VAEB_CUDA(cudaFree(f.d_order));
+      f.d_order = nullptr;
+      VAEB_CUDA(cudaMalloc((void**)&f.d_order, (size_t)n * sizeof(int)));
+      f.order_cap = n;
+    }
+    VAEB_CUDA(cudaMemcpyAsync(f.d_order, batch_order, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    d_order = f.d_order;
+  }
+  return fused_step_launch(h, d_order, d_xrows, rows, n, d_eps, 0, nullptr);
+}
+
 float* flat_by_which(vaeb_handle* h, int which) {
   switch (which) {
     case 0: return h->d_params;
@@ -468,6 +489,7 @@ int vaeb_create(const vaeb_config* cfg, vaeb_handle** out) {
   h->D = cfg->input_dim; h->H = cfg->hidden_units; h->Z = cfg->latent_size; h->M = cfg->batch_size; h->L = cfg->L;
   h->cont = cfg->continuous != 0;
   build_layout(h->lay, h->D, h->H, h->Z, h->cont);
+  { const char* e = getenv("VAEB_B200_FUSED"); h->fused_off = e && e[0] == '0'; }
   h->tc.active = cfg->precision != VAEB_PREC_FP32;
   h->tc.ns = cfg->precision == VAEB_PREC_BF16X3 ? 2 : 1;
   VAEB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -507,6 +529,11 @@ int vaeb_destroy(vaeb_handle* h) {
   for (float* p : bufs) if (p) cudaFree(p);
   if (h->d_counter) cudaFree(h->d_counter);
   if (h->d_w45t) cudaFree(h->d_w45t);
+  {
+    FusedState& f = h->fused;
+    void* fb[] = {f.bar, f.params_alt, f.partial, f.aux_part, f.d_order, f.d_timing};
+    for (void* q : fb) if (q) cudaFree(q);
+  }
   {
     TcBuffers& b = h->tc.data;
     void* tb[] = {b.xh, b.xl, b.w3h, b.w3l, b.w2h, b.w2l, b.hdh, b.hdl, b.da2h, b.da2l, b.da3h, b.da3l, h->tc.xsh, h->tc.xsl};
@@ -617,7 +644,10 @@ int vaeb_update(vaeb_handle* h, int64_t index, const float* eps, float* elbo_out
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
   const float* d_eps;
   VAEB_TRY(stage_eps_zeta(h, eps, (int64_t)h->L * h->M * h->Z, &d_eps));
-  VAEB_TRY(enqueue_update(h, h->d_x + (size_t)index * h->M * h->D, h->M, d_eps, nullptr, 0, true));
+  if (fused_step_supported(h, h->M))
+    VAEB_TRY(fused_updates(h, nullptr, h->d_x + (size_t)index * h->M * h->D, h->M, 1, d_eps));
+  else
+    VAEB_TRY(enqueue_update(h, h->d_x + (size_t)index * h->M * h->D, h->M, d_eps, nullptr, 0, true));
   return read_scalars(h, 1, elbo_out);
 }
 
@@ -627,7 +657,10 @@ int vaeb_update_host(vaeb_handle* h, const float* x, int64_t rows, const float* 
   VAEB_TRY(stage_in(h, &h->d_stage, &h->stage_cap, x, rows * h->D));
   const float* d_eps;
   VAEB_TRY(stage_eps_zeta(h, eps, (int64_t)h->L * rows * h->Z, &d_eps));
-  VAEB_TRY(enqueue_update(h, h->d_stage, (int)rows, d_eps, nullptr, 0, true));
+  if (fused_step_supported(h, (int)rows))
+    VAEB_TRY(fused_updates(h, nullptr, h->d_stage, (int)rows, 1, d_eps));
+  else
+    VAEB_TRY(enqueue_update(h, h->d_stage, (int)rows, d_eps, nullptr, 0, true));
   return read_scalars(h, 1, elbo_out);
 }
 
@@ -639,6 +672,13 @@ int vaeb_update_many(vaeb_handle* h, const int32_t* batch_order, int32_t n, floa
   for (int i = 0; i < n; ++i) {
     const int64_t index = batch_order[i];
     VAEB_REQUIRE(index >= 0 && (index + 1) * (int64_t)h->M <= h->n_data, "batch index outside the resident data");
+  }
+  if (fused_step_supported(h, h->M)) {
+    VAEB_TRY(fused_updates(h, batch_order, nullptr, h->M, n, nullptr));
+    return read_scalars(h, n, elbo_out);
+  }
+  for (int i = 0; i < n; ++i) {
+    const int64_t index = batch_order[i];
     VAEB_TRY(enqueue_update(h, h->d_x + (size_t)index * h->M * h->D, h->M, nullptr, nullptr, i, true));
   }
   return read_scalars(h, n, elbo_out);

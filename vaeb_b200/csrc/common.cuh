@@ -7,6 +7,7 @@
 
 #include "../../include/vaeb_b200.h"
 #include "tc_layers.h"
+#include "fused_step.cuh"
 
 void vaeb_set_error(const std::string& msg);
 
@@ -76,6 +77,20 @@ struct TcState {
   int64_t key_rows = -1, key_R = -1, key_data = -1; int key_bn = 0; const void* key_x = nullptr;
 };
 
+// State of the fused single-launch step (fused_step.cu).
+struct FusedState {
+  bool ready = false;
+  int n_sm = 0;
+  unsigned long long* bar = nullptr;       // grid-barrier counter (monotonic)
+  unsigned long long bar_count = 0;        // arrivals so far = the next launch's base
+  float* params_alt = nullptr;             // the other half of the parameter double buffer
+  float* partial = nullptr; float* aux_part = nullptr;
+  int* d_order = nullptr; int order_cap = 0;
+  long long* d_timing = nullptr; int timing_cap = 0;
+  int rows = -1;
+  fs::JobCfg job[fs::J_COUNT];
+};
+
 struct vaeb_handle {
   vaeb_config cfg;
   TcState tc;
@@ -100,6 +115,8 @@ struct vaeb_handle {
   uint32_t step = 0;
   int64_t launches = 0;
   bool grads_have_prior = false;
+  FusedState fused;
+  bool fused_off = false;             // VAEB_B200_FUSED=0: always use the per-layer kernels
   // data parallel
   NcclApi nccl; void* comm = nullptr; int rank = 0, world = 1;
 };

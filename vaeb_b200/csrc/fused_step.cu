@@ -1,0 +1,668 @@
+// The fused AEVB update: one persistent cooperative kernel for n whole steps (see fused_step.cuh).
+//
+// Work decomposition.  Every dense layer of the step is a "job": a grid of TM x TN output tiles
+// (TM = 8*TMT, TN = 4*TNT, per-thread micro tile TMT x TNT on a fixed 8x4 lane grid).  A tile is
+// owned by `ks` warps of ONE CTA, each contracting its own slice of the k index from global memory
+// (L2) through a private shared-memory stage; the ks partial tiles meet in shared memory and a
+// fused epilogue (tanh, reparameterisation, log-likelihood + deltas, tanh', Adagrad) writes the
+// result.  At M = 100 the outputs are skinny (100 x 500 / 100 x 784), so the jobs are cut into
+// ~148 CTA items of full contraction depth: no cross-CTA partial sums, results are deterministic.
+//
+// Dependencies between jobs are grid barriers (monotonic 64-bit counter, release/acquire at gpu
+// scope).  Data produced by other CTAs is always read with ld.global.cg (L2), never through L1.
+//
+// Parameters are double buffered: phase k reads theta from params[cur] while the weight-gradient
+// epilogues of the same step write Adagrad's theta' into params[cur^1] (the backward of a layer
+// still needs the old W while its gradient is being applied).  ADA is updated in place.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "fused_step.cuh"
+#include "philox.cuh"
+
+namespace fs {
+
+enum { A_MK = 0, A_KM = 1 };          // A(m,k) = A[m*lda + k]  |  A[k*lda + m]
+enum { B_KN = 0, B_NK = 1 };          // B(k,n) = B[k*ldb + n]  |  B[n*ldb + k]
+enum { PLAIN = 0, DUALK = 1, DUALN = 2 };
+// DUALK: k <  K0 -> (A0, B0), k >= K0 -> (A1, B1) at k - K0   (sum of two products)
+// DUALN: tile columns [0, TN/2) come from B0, [TN/2, TN) from B1 at the same n (two heads)
+
+struct Gemm {
+  const float* A0; const float* A1; int lda;
+  const float* B0; const float* B1; int ldb;
+  int M, N, K0, K1;
+  int ones_row;                       // A_KM: row index that reads as 1 (bias gradient), else -1
+  JobCfg c;
+};
+
+__device__ __forceinline__ float softplusf_(float a) { return fmaxf(a, 0.f) + log1pf(expf(-fabsf(a))); }
+__device__ __forceinline__ float sigmoidf_(float a) { return 1.0f / (1.0f + expf(-a)); }
+
+// ---------------------------------------------------------------------------------------------
+// operand staging: global (L2) -> registers -> this warp's shared-memory stage, k-major
+// ---------------------------------------------------------------------------------------------
+template <int TM, int AL, int MODE>
+__device__ __forceinline__ void load_A(const Gemm& g, int m0, int kc, int kv, int lane, float (&ra)[TM / 2]) {
+  if (AL == A_MK) {
+    const int kk = lane & 15, rp = lane >> 4;
+    int ko = kc + kk;
+    const float* src = g.A0;
+    if (MODE == DUALK && ko >= g.K0) { src = g.A1; ko -= g.K0; }
+    const bool kok = kk < kv;
+#pragma unroll
+    for (int j = 0; j < TM / 2; ++j) {
+      const int gm = m0 + 2 * j + rp;
+      ra[j] = (kok && gm < g.M) ? __ldcg(src + (size_t)gm * g.lda + ko) : 0.f;
+    }
+  } else {
+    const int m = (TM == 32) ? lane : (lane & 15);
+    const int gm = m0 + m;
+    const bool mok = gm < g.M, one = gm == g.ones_row;
+#pragma unroll
+    for (int j = 0; j < TM / 2; ++j) {
+      const int kk = (TM == 32) ? j : 2 * j + (lane >> 4);
+      const bool ok = mok && kk < kv;
+      ra[j] = ok ? (one ? 1.f : __ldcg(g.A0 + (size_t)(kc + kk) * g.lda + gm)) : 0.f;
+    }
+  }
+}
+
+template <int TM, int AL>
+__device__ __forceinline__ void store_A(float* sA, int lane, const float (&ra)[TM / 2]) {
+  constexpr int TMS = TM + 2;
+  if (AL == A_MK) {
+    const int kk = lane & 15, rp = lane >> 4;
+#pragma unroll
+    for (int j = 0; j < TM / 2; ++j) sA[kk * TMS + 2 * j + rp] = ra[j];
+  } else {
+    const int m = (TM == 32) ? lane : (lane & 15);
+#pragma unroll
+    for (int j = 0; j < TM / 2; ++j) {
+      const int kk = (TM == 32) ? j : 2 * j + (lane >> 4);
+      sA[kk * TMS + m] = ra[j];
+    }
+  }
+}
+
+template <int TN, int BL, int MODE>
+__device__ __forceinline__ void load_B(const Gemm& g, int n0, int kc, int kv, int lane, float (&rb)[TN / 2]) {
+  if (BL == B_KN) {
+#pragma unroll
+    for (int j = 0; j < TN / 2; ++j) {
+      const int e = lane + 32 * j;
+      const int kk = e / TN, c = e % TN;
+      int ko = kc + kk;
+      const float* src = g.B0;
+      int gn = n0 + c;
+      if (MODE == DUALN) {
+        if (c >= TN / 2) { src = g.B1; gn = n0 + c - TN / 2; }
+      } else if (MODE == DUALK) {
+        if (ko >= g.K0) { src = g.B1; ko -= g.K0; }
+      }
+      rb[j] = (kk < kv && gn < g.N) ? __ldcg(src + (size_t)ko * g.ldb + gn) : 0.f;
+    }
+  } else {
+    const int kk = lane & 15, cp = lane >> 4;
+    int ko = kc + kk;
+    const float* src = g.B0;
+    if (MODE == DUALK && ko >= g.K0) { src = g.B1; ko -= g.K0; }
+    const bool kok = kk < kv;
+#pragma unroll
+    for (int j = 0; j < TN / 2; ++j) {
+      const int gn = n0 + 2 * j + cp;
+      rb[j] = (kok && gn < g.N) ? __ldcg(src + (size_t)gn * g.ldb + ko) : 0.f;
+    }
+  }
+}
+
+template <int TN, int BL>
+__device__ __forceinline__ void store_B(float* sB, int lane, const float (&rb)[TN / 2]) {
+  constexpr int TNS = (BL == B_KN) ? TN : TN + 4;
+  if (BL == B_KN) {
+#pragma unroll
+    for (int j = 0; j < TN / 2; ++j) {
+      const int e = lane + 32 * j;
+      sB[(e / TN) * TNS + (e % TN)] = rb[j];
+    }
+  } else {
+    const int kk = lane & 15, cp = lane >> 4;
+#pragma unroll
+    for (int j = 0; j < TN / 2; ++j) sB[kk * TNS + 2 * j + cp] = rb[j];
+  }
+}
+
+// column of micro-tile entry j for lane column group cg: 16-wide blocks of float4 per lane, then
+// one 8-wide block of float2 per lane (TN = 16*NA4 + 8*NB2)
+template <int TNT>
+__device__ __forceinline__ int col_of(int j, int cg) {
+  constexpr int NA4 = TNT / 4;
+  return j < 4 * NA4 ? (j >> 2) * 16 + cg * 4 + (j & 3) : 16 * NA4 + cg * 2 + (j - 4 * NA4);
+}
+
+template <int TMT, int TNT, int TMS, int TNS>
+__device__ __forceinline__ void fma_step(const float* sA, const float* sB, int kk, int rg, int cg,
+                                         float (&acc)[TMT][TNT]) {
+  constexpr int NA4 = TNT / 4, NB2 = (TNT % 4) / 2;
+  float a[TMT], b[TNT];
+#pragma unroll
+  for (int i = 0; i < TMT / 2; ++i) {
+    const float2 t = *reinterpret_cast<const float2*>(sA + kk * TMS + rg * TMT + 2 * i);
+    a[2 * i] = t.x; a[2 * i + 1] = t.y;
+  }
+#pragma unroll
+  for (int q = 0; q < NA4; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(sB + kk * TNS + q * 16 + cg * 4);
+    b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+  }
+  if (NB2) {
+    const float2 t = *reinterpret_cast<const float2*>(sB + kk * TNS + NA4 * 16 + cg * 2);
+    b[4 * NA4] = t.x; b[4 * NA4 + 1] = t.y;
+  }
+#pragma unroll
+  for (int i = 0; i < TMT; ++i)
+#pragma unroll
+    for (int j = 0; j < TNT; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one CTA item of a job
+// ---------------------------------------------------------------------------------------------
+template <int TMT, int TNT, int AL, int BL, int MODE, class Epi>
+__device__ __forceinline__ void run_item(const Gemm& g, int item, const Epi& epi, float* smem) {
+  static_assert(TMT % 2 == 0 && TNT % 2 == 0, "micro tile");
+  constexpr int TM = 8 * TMT, TN = 4 * TNT;
+  constexpr int TMS = TM + 2, TNS = (BL == B_KN) ? TN : TN + 4;
+  constexpr int TNE = (MODE == DUALN) ? TN / 2 : TN;      // distinct output columns of a tile
+  static_assert(KC * (TMS + TNS) <= WBUF && TM * TN <= WBUF, "shared-memory stage too small");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ks = g.c.ks;
+  const int tl = warp / ks, ksi = warp - tl * ks;
+  const int tile = item * g.c.tpi + tl;
+  const bool active = tl < g.c.tpi && tile < g.c.tiles_m * g.c.tiles_n;
+  float* wbuf = smem + warp * WBUF;
+  int m0 = 0, n0 = 0, tn = 0;
+  if (active) {
+    const int tm = tile % g.c.tiles_m;
+    tn = tile / g.c.tiles_m;
+    m0 = tm * TM; n0 = tn * TNE;
+    const int K = g.K0 + g.K1;
+    const int k0 = (int)(((long long)K * ksi) / ks), k1 = (int)(((long long)K * (ksi + 1)) / ks);
+    const int rg = lane >> 2, cg = lane & 3;
+    float acc[TMT][TNT];
+#pragma unroll
+    for (int i = 0; i < TMT; ++i)
+#pragma unroll
+      for (int j = 0; j < TNT; ++j) acc[i][j] = 0.f;
+    float ra[TM / 2], rb[TN / 2];
+    float* sA = wbuf;
+    float* sB = wbuf + KC * TMS;
+    int kc = k0, kv = min(KC, k1 - k0);
+    if (kc < k1) {
+      load_A<TM, AL, MODE>(g, m0, kc, kv, lane, ra);
+      load_B<TN, BL, MODE>(g, n0, kc, kv, lane, rb);
+    }
+    while (kc < k1) {
+      __syncwarp();
+      store_A<TM, AL>(sA, lane, ra);
+      store_B<TN, BL>(sB, lane, rb);
+      __syncwarp();
+      const int kcn = kc + KC, kvn = min(KC, k1 - kcn);
+      if (kcn < k1) {                      // next chunk in flight while this one is contracted
+        load_A<TM, AL, MODE>(g, m0, kcn, kvn, lane, ra);
+        load_B<TN, BL, MODE>(g, n0, kcn, kvn, lane, rb);
+      }
+      if (kv == KC) {
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) fma_step<TMT, TNT, TMS, TNS>(sA, sB, kk, rg, cg, acc);
+      } else {
+#pragma unroll 1
+        for (int kk = 0; kk < kv; ++kk) fma_step<TMT, TNT, TMS, TNS>(sA, sB, kk, rg, cg, acc);
+      }
+      kc = kcn; kv = kvn;
+    }
+    __syncwarp();
+    // this warp's partial tile, row-major [TM][TN], over its own stage
+#pragma unroll
+    for (int i = 0; i < TMT; ++i)
+#pragma unroll
+      for (int j = 0; j < TNT; ++j) wbuf[(rg * TMT + i) * TN + col_of<TNT>(j, cg)] = acc[i][j];
+  }
+  __syncthreads();
+  const int gidx = ksi * 32 + lane, gsize = ks * 32;
+  float* gbuf = smem + (tl * ks) * WBUF;
+  if (active) {
+    for (int e = gidx; e < TM * TNE; e += gsize) {
+      const int row = e / TNE, c = e - row * TNE;
+      float v0 = 0.f, v1 = 0.f;
+      for (int s = 0; s < ks; ++s) {
+        v0 += gbuf[s * WBUF + row * TN + c];
+        if (MODE == DUALN) v1 += gbuf[s * WBUF + row * TN + TN / 2 + c];
+      }
+      const int gm = m0 + row, gn = n0 + c;
+      float term = 0.f;
+      if (gm < g.M && gn < g.N) term = epi.elem(gm, gn, v0, v1);
+      if (Epi::ROWSUM) gbuf[row * TN + c] = term;
+    }
+  }
+  if (Epi::ROWSUM) {
+    __syncthreads();
+    if (active && gidx < TM && m0 + gidx < g.M) {
+      float s = 0.f;
+      const int cmax = min(TNE, g.N - n0);
+      for (int c = 0; c < cmax; ++c) s += gbuf[gidx * TN + c];
+      epi.rowsum(m0 + gidx, tn, s);
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogues
+// ---------------------------------------------------------------------------------------------
+struct EpiTanh {                      // out = tanh(acc + bias[n])               VAEB.py:246,254
+  static constexpr bool ROWSUM = false;
+  const float* bias; float* out; int ld;
+  __device__ __forceinline__ float elem(int m, int n, float v, float) const {
+    out[(size_t)m * ld + n] = tanhf(v + __ldcg(bias + n));
+    return 0.f;
+  }
+  __device__ __forceinline__ void rowsum(int, int, float) const {}
+};
+
+struct EpiLatent {                    // VAEB.py:248-249 heads, :41-47 reparameterisation, :343 / :322-325 row terms
+  static constexpr bool ROWSUM = true;
+  const float* b4; const float* b5; const float* eps_inj;
+  uint64_t seed; uint32_t step; int64_t row_offset;
+  int Z, la, n_tiles;
+  float *mu, *ls, *eps, *z, *aux_part;
+  __device__ __forceinline__ float elem(int m, int j, float v0, float v1) const {
+    const float am = v0 + __ldcg(b4 + j), al = v1 + __ldcg(b5 + j);
+    const size_t o = (size_t)m * Z + j;
+    const float e = eps_inj ? __ldcg(eps_inj + o)
+                            : philox_normal1(seed, VAEB_STREAM_TRAIN, step, 0u, (uint64_t)((row_offset + m) * Z + j));
+    const float zv = am + expf(0.5f * al) * e;
+    mu[o] = am; ls[o] = al; eps[o] = e; z[o] = zv;
+    return la ? (-0.5f * zv * zv + 0.5f * al + 0.5f * e * e) : 0.5f * (1.0f + al - am * am - expf(al));
+  }
+  __device__ __forceinline__ void rowsum(int m, int tn, float s) const { aux_part[(size_t)m * n_tiles + tn] = s; }
+};
+
+struct EpiBernoulli {                 // VAEB.py:263,311: x*a - softplus(a); da = w*(x - sigmoid(a))
+  static constexpr bool ROWSUM = true;
+  const float* b2; const float* x; int D; float scale; float* da; float* partial; int n_tiles;
+  __device__ __forceinline__ float elem(int m, int n, float v, float) const {
+    const float a = v + __ldcg(b2 + n);
+    const float xv = __ldcg(x + (size_t)m * D + n);
+    da[(size_t)m * D + n] = scale * (xv - sigmoidf_(a));
+    return xv * a - softplusf_(a);
+  }
+  __device__ __forceinline__ void rowsum(int m, int tn, float s) const { partial[(size_t)m * n_tiles + tn] = s; }
+};
+
+struct EpiGaussian {                  // VAEB.py:257-258,306-307
+  static constexpr bool ROWSUM = true;
+  const float* b2; const float* b6; const float* x; int D; float scale; float* da; float* dlv; float* partial;
+  int n_tiles;
+  __device__ __forceinline__ float elem(int m, int n, float v0, float v1) const {
+    const float a = v0 + __ldcg(b2 + n), lv = v1 + __ldcg(b6 + n);
+    const float xv = __ldcg(x + (size_t)m * D + n);
+    const float mx = sigmoidf_(a);
+    const float d = xv - mx;
+    const float r = d * expf(-lv);
+    da[(size_t)m * D + n] = scale * r * mx * (1.0f - mx);
+    dlv[(size_t)m * D + n] = scale * (-0.5f + 0.5f * d * r);
+    return -0.91893853320467274178f - 0.5f * lv - 0.5f * d * r;
+  }
+  __device__ __forceinline__ void rowsum(int m, int tn, float s) const { partial[(size_t)m * n_tiles + tn] = s; }
+};
+
+struct EpiTanhBack {                  // out = acc * (1 - h^2)
+  static constexpr bool ROWSUM = false;
+  const float* h; float* out; int ld;
+  __device__ __forceinline__ float elem(int m, int n, float v, float) const {
+    const float hv = __ldcg(h + (size_t)m * ld + n);
+    out[(size_t)m * ld + n] = v * (1.0f - hv * hv);
+    return 0.f;
+  }
+  __device__ __forceinline__ void rowsum(int, int, float) const {}
+};
+
+struct EpiDz {                        // dz -> dmu, dls (SURVEY.md 8a backward formulas), L == 1
+  static constexpr bool ROWSUM = false;
+  const float *z, *eps, *mu, *ls; int Z, la; float w; float *dmu, *dls;
+  __device__ __forceinline__ float elem(int m, int j, float v, float) const {
+    const size_t o = (size_t)m * Z + j;
+    float d = v;
+    if (la) d -= w * __ldcg(z + o);
+    const float lsv = __ldcg(ls + o);
+    float a = d, b = d * (0.5f * expf(0.5f * lsv) * __ldcg(eps + o));
+    if (la) {
+      b += w * 0.5f;
+    } else {
+      a -= w * __ldcg(mu + o);
+      b += w * 0.5f * (1.0f - expf(lsv));
+    }
+    dmu[o] = a; dls[o] = b;
+    return 0.f;
+  }
+  __device__ __forceinline__ void rowsum(int, int, float) const {}
+};
+
+struct Hyper { float lr, eps, prior, p2; };
+
+__device__ __forceinline__ void adagrad_apply(const float* P, float* Pn, float* ada, size_t o, float g, const Hyper& hy) {
+  const float p = __ldcg(P + o);
+  g -= hy.prior * p;                                    // VAEB.py:389-390
+  const float a = __ldcg(ada + o) + g * g;              // VAEB.py:439
+  float np_ = p + hy.lr * g / (sqrtf(a) + hy.eps);      // VAEB.py:441
+  if (hy.p2 != 0.f) np_ -= hy.p2 * p * p;               // VAEBfullbayes.py:183-184
+  Pn[o] = np_;
+  ada[o] = a;
+}
+
+struct EpiAdagrad {                   // rows < nW: weight [nW, ld]; row == nW: the bias (ones row of A)
+  static constexpr bool ROWSUM = false;
+  const float* P; float* Pn; float* ada; int64_t oW, ob; int nW, ld; Hyper hy;
+  __device__ __forceinline__ float elem(int m, int n, float v, float) const {
+    const size_t o = m < nW ? (size_t)oW + (size_t)m * ld + n : (size_t)ob + n;
+    adagrad_apply(P, Pn, ada, o, v, hy);
+    return 0.f;
+  }
+  __device__ __forceinline__ void rowsum(int, int, float) const {}
+};
+
+struct EpiAdagrad2 {                  // two heads at once (W4|W5, b4|b5)
+  static constexpr bool ROWSUM = false;
+  const float* P; float* Pn; float* ada; int64_t oWa, oba, oWb, obb; int nW, ld; Hyper hy;
+  __device__ __forceinline__ float elem(int m, int n, float v0, float v1) const {
+    const size_t off = m < nW ? (size_t)m * ld + n : (size_t)n;
+    adagrad_apply(P, Pn, ada, (size_t)(m < nW ? oWa : oba) + off, v0, hy);
+    adagrad_apply(P, Pn, ada, (size_t)(m < nW ? oWb : obb) + off, v1, hy);
+    return 0.f;
+  }
+  __device__ __forceinline__ void rowsum(int, int, float) const {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// grid barrier + kernel
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(bar) : "memory");
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+#define FS_JOB(J) job_tmt(J), job_tnt(J)
+
+__global__ void __launch_bounds__(NT, 1) fused_step_kernel(const StepParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int D = p.D, H = p.H, Z = p.Z, M = p.M;
+  const int G = gridDim.x, cta = blockIdx.x;
+  unsigned long long target = p.bar_base;
+  const Hyper hy{p.lr, p.ada_eps, p.prior, p.p2};
+  const bool rec = p.timing != nullptr && cta == 0 && threadIdx.x == 0;
+
+  for (int s = 0; s < p.n_steps; ++s) {
+    const int cur = (p.parity0 + s) & 1;
+    const float* P = p.params[cur];
+    float* Pn = p.params[cur ^ 1];
+    const float* x = p.batch_order ? p.x_base + (size_t)__ldg(p.batch_order + s) * M * D : p.x_direct;
+    long long* tm = rec ? p.timing + (size_t)s * 9 : nullptr;
+    if (tm) tm[0] = gtime();
+
+    // ---- phase 1: encoder hidden layer ------------------------------------------------------
+    {
+      const Gemm g{x, nullptr, D, P + p.oW3, nullptr, H, M, H, D, 0, -1, p.job[J_ENC1]};
+      const EpiTanh epi{P + p.ob3, p.h_e, H};
+      for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_ENC1), A_MK, B_KN, PLAIN>(g, it, epi, smem);
+    }
+    grid_barrier(p.bar, target += G);
+    if (tm) tm[1] = gtime();
+
+    // ---- phase 2: latent heads, reparameterisation, KL / LA row terms -----------------------
+    {
+      const Gemm g{p.h_e, nullptr, H, P + p.oW4, P + p.oW5, Z, M, Z, H, 0, -1, p.job[J_ENC2]};
+      const EpiLatent epi{P + p.ob4, P + p.ob5, p.eps_inj, p.seed, p.step0 + (uint32_t)s, p.row_offset, Z, p.la,
+                          g.c.tiles_n, p.mu, p.ls, p.eps, p.z, p.aux_part};
+      for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_ENC2), A_MK, B_KN, DUALN>(g, it, epi, smem);
+    }
+    grid_barrier(p.bar, target += G);
+    if (tm) tm[2] = gtime();
+
+    // ---- phase 3: decoder hidden layer ------------------------------------------------------
+    {
+      const Gemm g{p.z, nullptr, Z, P + p.oW1, nullptr, H, M, H, Z, 0, -1, p.job[J_DEC1]};
+      const EpiTanh epi{P + p.ob1, p.h_d, H};
+      for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_DEC1), A_MK, B_KN, PLAIN>(g, it, epi, smem);
+    }
+    grid_barrier(p.bar, target += G);
+    if (tm) tm[3] = gtime();
+
+    // ---- phase 4: decoder output layer + log-likelihood + output deltas -----------------------
+    if (p.cont) {
+      const Gemm g{p.h_d, nullptr, H, P + p.oW2, P + p.oW6, D, M, D, H, 0, -1, p.job[J_DEC2]};
+      const EpiGaussian epi{P + p.ob2, P + p.ob6, x, D, p.w, p.da2, p.dlv, p.partial, g.c.tiles_n};
+      for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_DEC2), A_MK, B_KN, DUALN>(g, it, epi, smem);
+    } else {
+      const Gemm g{p.h_d, nullptr, H, P + p.oW2, nullptr, D, M, D, H, 0, -1, p.job[J_DEC2]};
+      const EpiBernoulli epi{P + p.ob2, x, D, p.w, p.da2, p.partial, g.c.tiles_n};
+      for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_DEC2), A_MK, B_KN, PLAIN>(g, it, epi, smem);
+    }
+    grid_barrier(p.bar, target += G);
+    if (tm) tm[4] = gtime();
+
+    // ---- phase 5: back through the decoder output layer -------------------------------------
+    {
+      const EpiTanhBack epi{p.h_d, p.da1, H};
+      if (p.cont) {
+        const Gemm g{p.da2, p.dlv, D, P + p.oW2, P + p.oW6, D, M, H, D, D, -1, p.job[J_DGRAD]};
+        for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_DGRAD), A_MK, B_NK, DUALK>(g, it, epi, smem);
+      } else {
+        const Gemm g{p.da2, nullptr, D, P + p.oW2, nullptr, D, M, H, D, 0, -1, p.job[J_DGRAD]};
+        for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_DGRAD), A_MK, B_NK, PLAIN>(g, it, epi, smem);
+      }
+    }
+    grid_barrier(p.bar, target += G);
+    if (tm) tm[5] = gtime();
+
+    // ---- phase 6: W2 (W6) update | dz -> dmu, dls | W1 update | the bound ---------------------
+    {
+      const Gemm g2{p.h_d, nullptr, H, p.da2, nullptr, D, H + 1, D, M, 0, H, p.job[J_WG2]};
+      const EpiAdagrad e2{P, Pn, p.ada, p.oW2, p.ob2, H, D, hy};
+      const Gemm g6{p.h_d, nullptr, H, p.dlv, nullptr, D, H + 1, D, M, 0, H, p.job[J_WG6]};
+      const EpiAdagrad e6{P, Pn, p.ada, p.oW6, p.ob6, H, D, hy};
+      const Gemm gz{p.da1, nullptr, H, P + p.oW1, nullptr, H, M, Z, H, 0, -1, p.job[J_DZ]};
+      const EpiDz ez{p.z, p.eps, p.mu, p.ls, Z, p.la, p.w, p.dmu, p.dls};
+      const Gemm g1{p.z, nullptr, Z, p.da1, nullptr, H, Z + 1, H, M, 0, Z, p.job[J_WG1]};
+      const EpiAdagrad e1{P, Pn, p.ada, p.oW1, p.ob1, Z, H, hy};
+      const int n2 = g2.c.n_items, n6 = p.cont ? g6.c.n_items : 0, nz = gz.c.n_items, n1 = g1.c.n_items;
+      const int total = n2 + n6 + nz + n1 + 1;
+      for (int it = cta; it < total; it += G) {
+        int i = it;
+        if (i < n2) { run_item<FS_JOB(J_WG2), A_KM, B_KN, PLAIN>(g2, i, e2, smem); continue; }
+        i -= n2;
+        if (i < n6) { run_item<FS_JOB(J_WG6), A_KM, B_KN, PLAIN>(g6, i, e6, smem); continue; }
+        i -= n6;
+        if (i < nz) { run_item<FS_JOB(J_DZ), A_MK, B_NK, PLAIN>(gz, i, ez, smem); continue; }
+        i -= nz;
+        if (i < n1) { run_item<FS_JOB(J_WG1), A_KM, B_KN, PLAIN>(g1, i, e1, smem); continue; }
+        // the bound of this step: fixed-order sum of the row partials (VAEB.py:340-344), / Mg
+        const int tc = p.job[J_DEC2].tiles_n, ta = p.job[J_ENC2].tiles_n;
+        float t = 0.f;
+        for (int r = threadIdx.x; r < M; r += NT) {
+          float rsum = 0.f;
+          for (int q = 0; q < tc; ++q) rsum += __ldcg(p.partial + (size_t)r * tc + q);
+          for (int q = 0; q < ta; ++q) rsum += __ldcg(p.aux_part + (size_t)r * ta + q);
+          t += rsum;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = t;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          float b = 0.f;
+          for (int wq = 0; wq < NW; ++wq) b += smem[wq];
+          p.scalars[s] = b / p.Mg;
+        }
+        __syncthreads();
+      }
+    }
+    grid_barrier(p.bar, target += G);
+    if (tm) tm[6] = gtime();
+
+    // ---- phase 7: back through the latent heads | W4, W5 update ---------------------------------
+    {
+      const Gemm gh{p.dmu, p.dls, Z, P + p.oW4, P + p.oW5, Z, M, H, Z, Z, -1, p.job[J_DHE]};
+      const EpiTanhBack eh{p.h_e, p.da3, H};
+      const Gemm g45{p.h_e, nullptr, H, p.dmu, p.dls, Z, H + 1, Z, M, 0, H, p.job[J_WG45]};
+      const EpiAdagrad2 e45{P, Pn, p.ada, p.oW4, p.ob4, p.oW5, p.ob5, H, Z, hy};
+      const int nh = gh.c.n_items, total = nh + g45.c.n_items;
+      for (int it = cta; it < total; it += G) {
+        if (it < nh) run_item<FS_JOB(J_DHE), A_MK, B_NK, DUALK>(gh, it, eh, smem);
+        else run_item<FS_JOB(J_WG45), A_KM, B_KN, DUALN>(g45, it - nh, e45, smem);
+      }
+    }
+    grid_barrier(p.bar, target += G);
+    if (tm) tm[7] = gtime();
+
+    // ---- phase 8: W3 update -------------------------------------------------------------------
+    {
+      const Gemm g{x, nullptr, D, p.da3, nullptr, H, D + 1, H, M, 0, D, p.job[J_WG3]};
+      const EpiAdagrad epi{P, Pn, p.ada, p.oW3, p.ob3, D, H, hy};
+      for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_WG3), A_KM, B_KN, PLAIN>(g, it, epi, smem);
+    }
+    grid_barrier(p.bar, target += G);
+    if (tm) tm[8] = gtime();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: decomposition of a job into CTA items
+// ---------------------------------------------------------------------------------------------
+static JobCfg plan_job(int job, int M, int N, int K, int n_cta, bool dual_n) {
+  const int TM = 8 * job_tmt(job), TN = 4 * job_tnt(job);
+  const int TNE = dual_n ? TN / 2 : TN;
+  JobCfg best{};
+  best.tiles_m = (M + TM - 1) / TM;
+  best.tiles_n = (N + TNE - 1) / TNE;
+  const int tiles = best.tiles_m * best.tiles_n;
+  double best_cost = 1e30;
+  const double fma = (double)job_tmt(job) * job_tnt(job) * 2.0;   // issue cycles per k per warp (one SMSP)
+  for (int ks = 1; ks <= NW; ks *= 2) {
+    for (int tpi = 1; tpi * ks <= NW; ++tpi) {
+      const int items = (tiles + tpi - 1) / tpi;
+      const int rounds = (items + n_cta - 1) / n_cta;
+      const int per_smsp = (ks * tpi + 3) / 4;
+      const double kper = std::ceil((double)K / ks);
+      const double cost = rounds * (per_smsp * kper * fma + 1500.0 + 40.0 * ks);
+      if (cost < best_cost) { best_cost = cost; best.ks = ks; best.tpi = tpi; best.n_items = items; }
+    }
+  }
+  return best;
+}
+
+}  // namespace fs
+
+bool fused_step_supported(const vaeb_handle* h, int rows) {
+  const int e = h->cfg.estimator;
+  return (e == VAEB_EST_LB || e == VAEB_EST_LA) && h->L == 1 && h->world == 1 &&
+         h->cfg.precision == VAEB_PREC_FP32 && rows >= 1 && rows <= 4096 && !h->fused_off;
+}
+
+int fused_step_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int rows, int n_steps,
+                      const float* d_eps, int slot0, long long* d_timing) {
+  using namespace fs;
+  FusedState& f = h->fused;
+  const Layout& l = h->lay;
+  const int D = h->D, H = h->H, Z = h->Z;
+  if (!f.ready) {
+    int dev = h->cfg.device, coop = 0;
+    VAEB_CUDA(cudaDeviceGetAttribute(&f.n_sm, cudaDevAttrMultiProcessorCount, dev));
+    VAEB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    VAEB_REQUIRE(coop != 0, "device lacks cooperative launch");
+    VAEB_CUDA(cudaFuncSetAttribute(fused_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    int occ = 0;
+    VAEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_step_kernel, NT, SMEM_BYTES));
+    VAEB_REQUIRE(occ >= 1, "fused step kernel does not fit on an SM");
+    VAEB_CUDA(cudaMalloc((void**)&f.bar, sizeof(unsigned long long)));
+    VAEB_CUDA(cudaMemset(f.bar, 0, sizeof(unsigned long long)));
+    const size_t nb = (size_t)(l.padded + 4) * sizeof(float);
+    VAEB_CUDA(cudaMalloc((void**)&f.params_alt, nb));
+    VAEB_CUDA(cudaMemset(f.params_alt, 0, nb));
+    f.ready = true;
+  }
+  if (rows != f.rows) {
+    VAEB_CUDA(cudaStreamSynchronize(h->stream));
+    if (f.partial) VAEB_CUDA(cudaFree(f.partial));
+    if (f.aux_part) VAEB_CUDA(cudaFree(f.aux_part));
+    f.partial = f.aux_part = nullptr;
+    const int G = f.n_sm;
+    f.job[J_ENC1] = plan_job(J_ENC1, rows, H, D, G, false);
+    f.job[J_ENC2] = plan_job(J_ENC2, rows, Z, H, G, true);
+    f.job[J_DEC1] = plan_job(J_DEC1, rows, H, Z, G, false);
+    f.job[J_DEC2] = plan_job(J_DEC2, rows, D, H, G, h->cont);
+    f.job[J_DGRAD] = plan_job(J_DGRAD, rows, H, h->cont ? 2 * D : D, G, false);
+    f.job[J_WG2] = plan_job(J_WG2, H + 1, D, rows, G, false);
+    f.job[J_WG6] = f.job[J_WG2];
+    f.job[J_DZ] = plan_job(J_DZ, rows, Z, H, G, false);
+    f.job[J_WG1] = plan_job(J_WG1, Z + 1, H, rows, G, false);
+    f.job[J_DHE] = plan_job(J_DHE, rows, H, 2 * Z, G, false);
+    f.job[J_WG45] = plan_job(J_WG45, H + 1, Z, rows, G, true);
+    f.job[J_WG3] = plan_job(J_WG3, D + 1, H, rows, G, false);
+    VAEB_CUDA(cudaMalloc((void**)&f.partial, (size_t)rows * f.job[J_DEC2].tiles_n * sizeof(float)));
+    VAEB_CUDA(cudaMalloc((void**)&f.aux_part, (size_t)rows * f.job[J_ENC2].tiles_n * sizeof(float)));
+    f.rows = rows;
+  }
+  const Workspace& s = h->ws;
+  StepParams p{};
+  p.D = D; p.H = H; p.Z = Z; p.M = rows;
+  p.cont = h->cont ? 1 : 0;
+  p.la = h->cfg.estimator == VAEB_EST_LA ? 1 : 0;
+  const bool fb = h->cfg.variant == VAEB_VARIANT_FULLBAYES;
+  p.w = fb ? 1.0f / (float)rows : 1.0f;
+  p.lr = h->cfg.learning_rate; p.ada_eps = h->cfg.adagrad_eps;
+  p.prior = fb ? 0.f : h->cfg.prior_scale;
+  p.p2 = fb ? h->cfg.learning_rate * 1e-6f : 0.f;
+  p.params[0] = h->d_params; p.params[1] = f.params_alt;
+  p.ada = h->d_ada;
+  p.oW3 = l.off[l.iW3]; p.oW4 = l.off[l.iW4]; p.oW5 = l.off[l.iW5]; p.oW1 = l.off[l.iW1]; p.oW2 = l.off[l.iW2];
+  p.ob3 = l.off[l.ib3]; p.ob4 = l.off[l.ib4]; p.ob5 = l.off[l.ib5]; p.ob1 = l.off[l.ib1]; p.ob2 = l.off[l.ib2];
+  p.oW6 = h->cont ? l.off[l.iW6] : 0; p.ob6 = h->cont ? l.off[l.ib6] : 0;
+  p.x_base = h->d_x; p.batch_order = d_order; p.x_direct = d_xrows;
+  p.eps_inj = d_eps;
+  p.seed = h->cfg.seed; p.step0 = h->step; p.row_offset = 0;
+  p.h_e = s.h_e; p.mu = s.mu; p.ls = s.ls; p.eps = s.eps; p.z = s.z; p.h_d = s.h_d;
+  p.da2 = s.da2; p.dlv = s.dlv; p.da1 = s.da1; p.dmu = s.dmu; p.dls = s.dls; p.da3 = s.da3;
+  p.partial = f.partial; p.aux_part = f.aux_part;
+  p.scalars = h->d_scalars + slot0; p.Mg = (float)rows;
+  p.n_steps = n_steps; p.parity0 = 0;
+  p.bar = f.bar; p.bar_base = f.bar_count;
+  p.timing = d_timing;
+  for (int j = 0; j < J_COUNT; ++j) p.job[j] = f.job[j];
+  void* args[] = {&p};
+  VAEB_CUDA(cudaLaunchCooperativeKernel((const void*)fused_step_kernel, dim3(f.n_sm), dim3(NT), args, SMEM_BYTES,
+                                        h->stream));
+  f.bar_count += (unsigned long long)f.n_sm * 8ull * (unsigned long long)n_steps;
+  ++h->launches;
+  h->step += (uint32_t)n_steps;
+  if (n_steps & 1) std::swap(h->d_params, f.params_alt);   // theta now lives in the other buffer
+  h->grads_have_prior = false;
+  return VAEB_OK;
+}
