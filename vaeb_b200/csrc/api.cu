@@ -964,30 +964,90 @@ int vaeb_profile_update(vaeb_handle* h, int64_t index, int32_t iters, int32_t ma
   VAEB_CUDA(cudaMalloc((void**)&ba, nb));
   VAEB_CUDA(cudaMemcpyAsync(bp, h->d_params, nb, cudaMemcpyDeviceToDevice, h->stream));
   VAEB_CUDA(cudaMemcpyAsync(ba, h->d_ada, nb, cudaMemcpyDeviceToDevice, h->stream));
-  PhaseProf prof;
-  prof.iters = iters;
-  VAEB_CUDA(cudaEventCreate(&prof.e0));
-  VAEB_CUDA(cudaEventCreate(&prof.e1));
   const uint32_t step0 = h->step;
   const int64_t launches0 = h->launches;
-  g_prof = &prof;
-  const int rc = enqueue_update(h, h->d_x + (size_t)index * h->M * h->D, h->M, nullptr, nullptr, 0, true);
-  g_prof = nullptr;
+  int rc = VAEB_OK;
+  int n = 0;
+  if (fused_step_supported(h, h->M)) {
+    // the fused kernel stamps %globaltimer at every phase boundary (CTA 0): ns per phase, averaged
+    // over `iters` consecutive updates of one launch (the first two are warm-up)
+    constexpr int NP = fs::N_PHASES;
+    static const char* const kNames[NP] = {
+        "P1 enc1 x.W3+tanh", "P2 heads+reparam+KL", "P3 dec1 z.W1+tanh", "P4 dec2 h.W2+loglik+delta",
+        "P5 dgrad (da.W2^T)*(1-h^2)", "P6 W2,W1 wgrad+Adagrad | dz | bound", "P7 dh_e | W4,W5 wgrad+Adagrad",
+        "P8 W3 wgrad+Adagrad"};
+    const int steps = iters + 2;
+    FusedState& f = h->fused;
+    if (steps * (NP + 1) > f.timing_cap) {
+      if (f.d_timing) cudaFree(f.d_timing);
+      f.d_timing = nullptr;
+      VAEB_CUDA(cudaMalloc((void**)&f.d_timing, (size_t)steps * (NP + 1) * sizeof(long long)));
+      f.timing_cap = steps * (NP + 1);
+    }
+    std::vector<int32_t> order((size_t)steps, (int32_t)index);
+    rc = ensure_ws(h, h->M, h->M, true);
+    const int* d_order = nullptr;
+    if (rc == VAEB_OK) {
+      if (steps > f.order_cap) {
+        if (f.d_order) cudaFree(f.d_order);
+        f.d_order = nullptr;
+        VAEB_CUDA(cudaMalloc((void**)&f.d_order, (size_t)steps * sizeof(int)));
+        f.order_cap = steps;
+      }
+      VAEB_CUDA(cudaMemcpyAsync(f.d_order, order.data(), (size_t)steps * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+      VAEB_CUDA(cudaStreamSynchronize(h->stream));
+      d_order = f.d_order;
+      VAEB_TRY(ensure_scalars(h, steps));
+      rc = fused_step_launch(h, d_order, nullptr, h->M, steps, nullptr, 0, f.d_timing);
+    }
+    std::vector<long long> tm((size_t)steps * (NP + 1));
+    if (rc == VAEB_OK) {
+      VAEB_CUDA(cudaMemcpyAsync(tm.data(), f.d_timing, tm.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+      VAEB_CUDA(cudaStreamSynchronize(h->stream));
+      const double dM = h->M, dD = h->D, dH = h->H, dZ = h->Z, c = h->cont ? 2.0 : 1.0, P = (double)h->lay.total;
+      const double fl[NP] = {2 * dM * dD * dH, 4 * dM * dH * dZ, 2 * dM * dZ * dH, 2 * dM * dH * dD * c, 2 * dM * dH * dD * c,
+                             2 * dM * dH * dD * c + 4 * dM * dZ * dH, 8 * dM * dH * dZ, 2 * dM * dD * dH};
+      const double by[NP] = {4 * (dM * dD + dD * dH + dM * dH), 4 * (dM * dH + 2 * dH * dZ + 4 * dM * dZ),
+                             4 * (dM * dZ + dZ * dH + dM * dH), 4 * (dM * dH + c * dH * dD + dM * dD + c * dM * dD),
+                             4 * (c * dM * dD + c * dH * dD + 2 * dM * dH),
+                             4 * (dM * dH + c * dM * dD + dM * dH + dM * dZ) + 16 * (c * dH * dD + dZ * dH),
+                             4 * (2 * dM * dZ + 2 * dH * dZ + 2 * dM * dH) + 16 * 2 * dH * dZ,
+                             4 * (dM * dD + dM * dH) + 16 * dD * dH};
+      (void)P;
+      n = std::min(NP, (int)max_phases);
+      for (int i = 0; i < n; ++i) {
+        double acc = 0;
+        for (int s = 2; s < steps; ++s) acc += (double)(tm[(size_t)s * (NP + 1) + i + 1] - tm[(size_t)s * (NP + 1) + i]);
+        ms[i] = (float)(acc / iters * 1e-6);
+        flops[i] = fl[i]; bytes[i] = by[i];
+        std::strncpy(names + 48 * i, kNames[i], 47);
+        names[48 * i + 47] = 0;
+      }
+    }
+  } else {
+    PhaseProf prof;
+    prof.iters = iters;
+    VAEB_CUDA(cudaEventCreate(&prof.e0));
+    VAEB_CUDA(cudaEventCreate(&prof.e1));
+    g_prof = &prof;
+    rc = enqueue_update(h, h->d_x + (size_t)index * h->M * h->D, h->M, nullptr, nullptr, 0, true);
+    g_prof = nullptr;
+    cudaEventDestroy(prof.e0); cudaEventDestroy(prof.e1);
+    n = std::min<int>((int)prof.ms.size(), max_phases);
+    for (int i = 0; i < n && rc == VAEB_OK; ++i) {
+      ms[i] = prof.ms[i]; flops[i] = prof.flops[i]; bytes[i] = prof.bytes[i];
+      std::strncpy(names + 48 * i, prof.names[i].c_str(), 47);
+      names[48 * i + 47] = 0;
+    }
+  }
   h->step = step0;
   h->launches = launches0;
   cudaMemcpyAsync(h->d_params, bp, nb, cudaMemcpyDeviceToDevice, h->stream);
   cudaMemcpyAsync(h->d_ada, ba, nb, cudaMemcpyDeviceToDevice, h->stream);
   cudaStreamSynchronize(h->stream);
   cudaFree(bp); cudaFree(ba);
-  cudaEventDestroy(prof.e0); cudaEventDestroy(prof.e1);
   if (rc != VAEB_OK) return rc;
-  const int n = std::min<int>((int)prof.ms.size(), max_phases);
   *n_phases = n;
-  for (int i = 0; i < n; ++i) {
-    ms[i] = prof.ms[i]; flops[i] = prof.flops[i]; bytes[i] = prof.bytes[i];
-    std::strncpy(names + 48 * i, prof.names[i].c_str(), 47);
-    names[48 * i + 47] = 0;
-  }
   return VAEB_OK;
 }
 

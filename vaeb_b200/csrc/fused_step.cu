@@ -29,221 +29,365 @@ enum { PLAIN = 0, DUALK = 1, DUALN = 2 };
 // DUALK: k <  K0 -> (A0, B0), k >= K0 -> (A1, B1) at k - K0   (sum of two products)
 // DUALN: tile columns [0, TN/2) come from B0, [TN/2, TN) from B1 at the same n (two heads)
 
+__device__ long long* g_dbg = nullptr;   // optional clock64 trace of CTA 0 (tools/dbg_fused.py)
+__device__ int g_dbg_n = 0;
+#define FS_STAMP(sign) do { if (dbg) g_dbg[g_dbg_n++] = (sign) * clock64(); } while (0)
+
 struct Gemm {
   const float* A0; const float* A1; int lda;
   const float* B0; const float* B1; int ldb;
   int M, N, K0, K1;
   int ones_row;                       // A_KM: row index that reads as 1 (bias gradient), else -1
   JobCfg c;
+  int avec, bvec;                     // operands may be staged with 16-byte copies
 };
+
+__device__ __forceinline__ bool al16(const float* q) { return q == nullptr || ((uintptr_t)q & 15) == 0; }
+// 16-byte staging is legal when both sources are aligned, the leading dimension is a multiple of four
+// floats and (for a contraction split over two sources) the split point is too
+__device__ __forceinline__ Gemm make_gemm(const float* A0, const float* A1, int lda, const float* B0, const float* B1,
+                                          int ldb, int M, int N, int K0, int K1, int ones_row, const JobCfg& c) {
+  Gemm g{A0, A1, lda, B0, B1, ldb, M, N, K0, K1, ones_row, c, 0, 0};
+  const bool ksplit_ok = K1 == 0 || (K0 & 3) == 0;
+  g.avec = al16(A0) && al16(A1) && (lda & 3) == 0 && ksplit_ok;
+  g.bvec = al16(B0) && al16(B1) && (ldb & 3) == 0 && ksplit_ok;
+  return g;
+}
 
 __device__ __forceinline__ float softplusf_(float a) { return fmaxf(a, 0.f) + log1pf(expf(-fabsf(a))); }
 __device__ __forceinline__ float sigmoidf_(float a) { return 1.0f / (1.0f + expf(-a)); }
 
 // ---------------------------------------------------------------------------------------------
-// operand staging: global (L2) -> registers -> this warp's shared-memory stage, k-major
+// operand staging: global (L2) -> this warp's shared-memory stage with cp.async (no staging
+// registers).  Layouts keep the source's contiguous index contiguous, so 16-byte copies apply
+// whenever the leading dimension and offsets are multiples of four floats (avec / bvec):
+//   A_KM  sA[kk*(TM+4) + m]      A_MK  sA[m*KSTR + kk]
+//   B_KN  sB[kk*TN + c]          B_NK  sB[c*KSTR + kk]
+// A chunk covers k in [kc, kc+kv); everything up to kv rounded up to four is zero filled.
 // ---------------------------------------------------------------------------------------------
-template <int TM, int AL, int MODE>
-__device__ __forceinline__ void load_A(const Gemm& g, int m0, int kc, int kv, int lane, float (&ra)[TM / 2]) {
-  if (AL == A_MK) {
-    const int kk = lane & 15, rp = lane >> 4;
-    int ko = kc + kk;
-    const float* src = g.A0;
-    if (MODE == DUALK && ko >= g.K0) { src = g.A1; ko -= g.K0; }
-    const bool kok = kk < kv;
-#pragma unroll
-    for (int j = 0; j < TM / 2; ++j) {
-      const int gm = m0 + 2 * j + rp;
-      ra[j] = (kok && gm < g.M) ? __ldcg(src + (size_t)gm * g.lda + ko) : 0.f;
-    }
-  } else {
-    const int m = (TM == 32) ? lane : (lane & 15);
-    const int gm = m0 + m;
-    const bool mok = gm < g.M, one = gm == g.ones_row;
-#pragma unroll
-    for (int j = 0; j < TM / 2; ++j) {
-      const int kk = (TM == 32) ? j : 2 * j + (lane >> 4);
-      const bool ok = mok && kk < kv;
-      ra[j] = ok ? (one ? 1.f : __ldcg(g.A0 + (size_t)(kc + kk) * g.lda + gm)) : 0.f;
-    }
-  }
-}
+constexpr int KSTR = KC + 4;
 
-template <int TM, int AL>
-__device__ __forceinline__ void store_A(float* sA, int lane, const float (&ra)[TM / 2]) {
-  constexpr int TMS = TM + 2;
-  if (AL == A_MK) {
-    const int kk = lane & 15, rp = lane >> 4;
-#pragma unroll
-    for (int j = 0; j < TM / 2; ++j) sA[kk * TMS + 2 * j + rp] = ra[j];
+__device__ __forceinline__ void cp4(float* dst, const float* src, int bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+               "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp16(float* dst, const float* src, int bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+               "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int TM, int AL, int MODE>
+__device__ __forceinline__ void issue_A(const Gemm& g, float* sA, int m0, int kc, int kv, int lane) {
+  const int kvr = (kv + 3) & ~3;
+  const int Mreal = g.ones_row >= 0 ? g.ones_row : g.M;     // the ones row is patched in after the copy lands
+  if (AL == A_KM) {
+    constexpr int TMS = TM + 4;
+    if (g.avec) {
+      constexpr int PR = TM / 4;                            // 16-byte pieces per k row
+      for (int idx = lane; idx < kvr * PR; idx += 32) {
+        const int kk = idx / PR, mq = idx - kk * PR;
+        const int gm = m0 + 4 * mq;
+        const int bytes = kk < kv ? 4 * max(0, min(4, Mreal - gm)) : 0;
+        cp16(sA + kk * TMS + 4 * mq, bytes ? g.A0 + (size_t)(kc + kk) * g.lda + gm : g.A0, bytes);
+      }
+    } else {
+      for (int idx = lane; idx < kvr * TM; idx += 32) {
+        const int kk = idx / TM, m = idx - kk * TM;
+        const int gm = m0 + m;
+        const bool ok = kk < kv && gm < Mreal;
+        cp4(sA + kk * TMS + m, ok ? g.A0 + (size_t)(kc + kk) * g.lda + gm : g.A0, ok ? 4 : 0);
+      }
+    }
   } else {
-    const int m = (TM == 32) ? lane : (lane & 15);
+    if (g.avec) {
 #pragma unroll
-    for (int j = 0; j < TM / 2; ++j) {
-      const int kk = (TM == 32) ? j : 2 * j + (lane >> 4);
-      sA[kk * TMS + m] = ra[j];
+      for (int t = 0; t < TM / 8; ++t) {
+        const int idx = lane + 32 * t;
+        const int m = idx >> 2, kk = (idx & 3) * 4;
+        if (kk < kvr) {
+          const int gm = m0 + m;
+          int ko = kc + kk;
+          const float* src = g.A0;
+          if (MODE == DUALK && ko >= g.K0) { src = g.A1; ko -= g.K0; }
+          const int bytes = gm < g.M ? 4 * max(0, min(4, kv - kk)) : 0;
+          cp16(sA + m * KSTR + kk, bytes ? src + (size_t)gm * g.lda + ko : g.A0, bytes);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < TM / 2; ++t) {
+        const int idx = lane + 32 * t;
+        const int m = idx >> 4, kk = idx & 15;
+        if (kk < kvr) {
+          const int gm = m0 + m;
+          int ko = kc + kk;
+          const float* src = g.A0;
+          if (MODE == DUALK && ko >= g.K0) { src = g.A1; ko -= g.K0; }
+          const bool ok = kk < kv && gm < g.M;
+          cp4(sA + m * KSTR + kk, ok ? src + (size_t)gm * g.lda + ko : g.A0, ok ? 4 : 0);
+        }
+      }
     }
   }
 }
 
 template <int TN, int BL, int MODE>
-__device__ __forceinline__ void load_B(const Gemm& g, int n0, int kc, int kv, int lane, float (&rb)[TN / 2]) {
+__device__ __forceinline__ void issue_B(const Gemm& g, float* sB, int n0, int kc, int kv, int lane) {
+  static_assert(!(BL == B_KN && MODE == DUALK) && !(BL == B_NK && MODE == DUALN), "unsupported operand mode");
+  const int kvr = (kv + 3) & ~3;
   if (BL == B_KN) {
-#pragma unroll
-    for (int j = 0; j < TN / 2; ++j) {
-      const int e = lane + 32 * j;
-      const int kk = e / TN, c = e % TN;
-      int ko = kc + kk;
-      const float* src = g.B0;
-      int gn = n0 + c;
-      if (MODE == DUALN) {
-        if (c >= TN / 2) { src = g.B1; gn = n0 + c - TN / 2; }
-      } else if (MODE == DUALK) {
-        if (ko >= g.K0) { src = g.B1; ko -= g.K0; }
+    if (g.bvec) {
+      constexpr int PR = TN / 4;
+      for (int idx = lane; idx < kvr * PR; idx += 32) {
+        const int kk = idx / PR, cq = idx - kk * PR;
+        int c = 4 * cq;
+        const float* src = g.B0;
+        if (MODE == DUALN && c >= TN / 2) { src = g.B1; c -= TN / 2; }
+        const int gn = n0 + c;
+        const int bytes = kk < kv ? 4 * max(0, min(4, g.N - gn)) : 0;
+        cp16(sB + kk * TN + 4 * cq, bytes ? src + (size_t)(kc + kk) * g.ldb + gn : g.B0, bytes);
       }
-      rb[j] = (kk < kv && gn < g.N) ? __ldcg(src + (size_t)ko * g.ldb + gn) : 0.f;
+    } else {
+      for (int idx = lane; idx < kvr * TN; idx += 32) {
+        const int kk = idx / TN, cc = idx - kk * TN;
+        int c = cc;
+        const float* src = g.B0;
+        if (MODE == DUALN && c >= TN / 2) { src = g.B1; c -= TN / 2; }
+        const int gn = n0 + c;
+        const bool ok = kk < kv && gn < g.N;
+        cp4(sB + kk * TN + cc, ok ? src + (size_t)(kc + kk) * g.ldb + gn : g.B0, ok ? 4 : 0);
+      }
     }
   } else {
-    const int kk = lane & 15, cp = lane >> 4;
-    int ko = kc + kk;
-    const float* src = g.B0;
-    if (MODE == DUALK && ko >= g.K0) { src = g.B1; ko -= g.K0; }
-    const bool kok = kk < kv;
+    if (g.bvec) {
 #pragma unroll
-    for (int j = 0; j < TN / 2; ++j) {
-      const int gn = n0 + 2 * j + cp;
-      rb[j] = (kok && gn < g.N) ? __ldcg(src + (size_t)gn * g.ldb + ko) : 0.f;
+      for (int t = 0; t < TN / 8; ++t) {
+        const int idx = lane + 32 * t;
+        const int c = idx >> 2, kk = (idx & 3) * 4;
+        if (kk < kvr) {
+          const int gn = n0 + c;
+          int ko = kc + kk;
+          const float* src = g.B0;
+          if (MODE == DUALK && ko >= g.K0) { src = g.B1; ko -= g.K0; }
+          const int bytes = gn < g.N ? 4 * max(0, min(4, kv - kk)) : 0;
+          cp16(sB + c * KSTR + kk, bytes ? src + (size_t)gn * g.ldb + ko : g.B0, bytes);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < TN / 2; ++t) {
+        const int idx = lane + 32 * t;
+        const int c = idx >> 4, kk = idx & 15;
+        if (kk < kvr) {
+          const int gn = n0 + c;
+          int ko = kc + kk;
+          const float* src = g.B0;
+          if (MODE == DUALK && ko >= g.K0) { src = g.B1; ko -= g.K0; }
+          const bool ok = kk < kv && gn < g.N;
+          cp4(sB + c * KSTR + kk, ok ? src + (size_t)gn * g.ldb + ko : g.B0, ok ? 4 : 0);
+        }
+      }
     }
   }
 }
 
-template <int TN, int BL>
-__device__ __forceinline__ void store_B(float* sB, int lane, const float (&rb)[TN / 2]) {
-  constexpr int TNS = (BL == B_KN) ? TN : TN + 4;
-  if (BL == B_KN) {
-#pragma unroll
-    for (int j = 0; j < TN / 2; ++j) {
-      const int e = lane + 32 * j;
-      sB[(e / TN) * TNS + (e % TN)] = rb[j];
-    }
-  } else {
-    const int kk = lane & 15, cp = lane >> 4;
-#pragma unroll
-    for (int j = 0; j < TN / 2; ++j) sB[kk * TNS + 2 * j + cp] = rb[j];
-  }
-}
-
-// column of micro-tile entry j for lane column group cg: 16-wide blocks of float4 per lane, then
-// one 8-wide block of float2 per lane (TN = 16*NA4 + 8*NB2)
-template <int TNT>
+// micro-tile entry -> tile row / column for lane (rg, cg).  Chosen per layout so that the fragment
+// loads are conflict free: k-major stages read TMT (TNT) consecutive floats, [m][k] / [n][k] stages
+// read float4 along k from rows rg + 8i (columns cg + 4j).
+template <int TMT, int AL>
+__device__ __forceinline__ int row_of(int i, int rg) { return AL == A_KM ? rg * TMT + i : rg + 8 * i; }
+template <int TNT, int BL>
 __device__ __forceinline__ int col_of(int j, int cg) {
   constexpr int NA4 = TNT / 4;
+  if (BL == B_NK) return cg + 4 * j;
   return j < 4 * NA4 ? (j >> 2) * 16 + cg * 4 + (j & 3) : 16 * NA4 + cg * 2 + (j - 4 * NA4);
 }
 
-template <int TMT, int TNT, int TMS, int TNS>
-__device__ __forceinline__ void fma_step(const float* sA, const float* sB, int kk, int rg, int cg,
+// four k steps of the contraction from one stage
+template <int TMT, int TNT, int AL, int BL>
+__device__ __forceinline__ void fma_quad(const float* sA, const float* sB, int kk, int rg, int cg,
                                          float (&acc)[TMT][TNT]) {
+  constexpr int TM = 8 * TMT, TN = 4 * TNT, TMS = TM + 4;
   constexpr int NA4 = TNT / 4, NB2 = (TNT % 4) / 2;
-  float a[TMT], b[TNT];
+  float am[AL == A_MK ? TMT : 1][4], bn[BL == B_NK ? TNT : 1][4];
+  if (AL == A_MK) {
 #pragma unroll
-  for (int i = 0; i < TMT / 2; ++i) {
-    const float2 t = *reinterpret_cast<const float2*>(sA + kk * TMS + rg * TMT + 2 * i);
-    a[2 * i] = t.x; a[2 * i + 1] = t.y;
+    for (int i = 0; i < TMT; ++i) {
+      const float4 t = *reinterpret_cast<const float4*>(sA + (rg + 8 * i) * KSTR + kk);
+      am[i][0] = t.x; am[i][1] = t.y; am[i][2] = t.z; am[i][3] = t.w;
+    }
+  }
+  if (BL == B_NK) {
+#pragma unroll
+    for (int j = 0; j < TNT; ++j) {
+      const float4 t = *reinterpret_cast<const float4*>(sB + (cg + 4 * j) * KSTR + kk);
+      bn[j][0] = t.x; bn[j][1] = t.y; bn[j][2] = t.z; bn[j][3] = t.w;
+    }
   }
 #pragma unroll
-  for (int q = 0; q < NA4; ++q) {
-    const float4 t = *reinterpret_cast<const float4*>(sB + kk * TNS + q * 16 + cg * 4);
-    b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
-  }
-  if (NB2) {
-    const float2 t = *reinterpret_cast<const float2*>(sB + kk * TNS + NA4 * 16 + cg * 2);
-    b[4 * NA4] = t.x; b[4 * NA4 + 1] = t.y;
-  }
+  for (int q = 0; q < 4; ++q) {
+    float a[TMT], b[TNT];
+    if (AL == A_MK) {
 #pragma unroll
-  for (int i = 0; i < TMT; ++i)
+      for (int i = 0; i < TMT; ++i) a[i] = am[i][q];
+    } else {
 #pragma unroll
-    for (int j = 0; j < TNT; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < TMT / 2; ++i) {
+        const float2 t = *reinterpret_cast<const float2*>(sA + (kk + q) * TMS + rg * TMT + 2 * i);
+        a[2 * i] = t.x; a[2 * i + 1] = t.y;
+      }
+    }
+    if (BL == B_NK) {
+#pragma unroll
+      for (int j = 0; j < TNT; ++j) b[j] = bn[j][q];
+    } else {
+#pragma unroll
+      for (int u = 0; u < NA4; ++u) {
+        const float4 t = *reinterpret_cast<const float4*>(sB + (kk + q) * TN + u * 16 + cg * 4);
+        b[4 * u] = t.x; b[4 * u + 1] = t.y; b[4 * u + 2] = t.z; b[4 * u + 3] = t.w;
+      }
+      if (NB2) {
+        const float2 t = *reinterpret_cast<const float2*>(sB + (kk + q) * TN + NA4 * 16 + cg * 2);
+        b[4 * NA4] = t.x; b[4 * NA4 + 1] = t.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < TMT; ++i)
+#pragma unroll
+      for (int j = 0; j < TNT; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
-// one CTA item of a job
+// one CTA item of a job.  tm_fixed >= 0: the item covers tiles (tm_fixed, item*tpi + tl) -- the
+// row-block chains, where one CTA runs two dependent layers for its own rows.
 // ---------------------------------------------------------------------------------------------
 template <int TMT, int TNT, int AL, int BL, int MODE, class Epi>
-__device__ __forceinline__ void run_item(const Gemm& g, int item, const Epi& epi, float* smem) {
+__device__ __forceinline__ void run_item(const Gemm& g, int item, const Epi& epi, float* smem, int tm_fixed = -1) {
   static_assert(TMT % 2 == 0 && TNT % 2 == 0, "micro tile");
   constexpr int TM = 8 * TMT, TN = 4 * TNT;
-  constexpr int TMS = TM + 2, TNS = (BL == B_KN) ? TN : TN + 4;
+  constexpr int SA = (AL == A_KM) ? KC * (TM + 4) : TM * KSTR;     // floats of one A stage
+  constexpr int SB = (BL == B_KN) ? KC * TN : TN * KSTR;
+  constexpr int STAGE = SA + SB;
   constexpr int TNE = (MODE == DUALN) ? TN / 2 : TN;      // distinct output columns of a tile
-  static_assert(KC * (TMS + TNS) <= WBUF && TM * TN <= WBUF, "shared-memory stage too small");
+  static_assert(NSTAGE * STAGE <= WBUF && TM * TN <= WBUF, "shared-memory stage too small");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ks = g.c.ks;
   const int tl = warp / ks, ksi = warp - tl * ks;
   const int tile = item * g.c.tpi + tl;
-  const bool active = tl < g.c.tpi && tile < g.c.tiles_m * g.c.tiles_n;
+  int tm, tn;
+  bool active = tl < g.c.tpi;
+  if (tm_fixed >= 0) { tm = tm_fixed; tn = tile; active = active && tn < g.c.tiles_n; }
+  else { tm = tile % g.c.tiles_m; tn = tile / g.c.tiles_m; active = active && tile < g.c.tiles_m * g.c.tiles_n; }
   float* wbuf = smem + warp * WBUF;
-  int m0 = 0, n0 = 0, tn = 0;
+  const int m0 = tm * TM, n0 = tn * TNE;
+  const bool dbg = g_dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  FS_STAMP(1);
   if (active) {
-    const int tm = tile % g.c.tiles_m;
-    tn = tile / g.c.tiles_m;
-    m0 = tm * TM; n0 = tn * TNE;
     const int K = g.K0 + g.K1;
-    const int k0 = (int)(((long long)K * ksi) / ks), k1 = (int)(((long long)K * (ksi + 1)) / ks);
+    // k slices start at multiples of four (16-byte copies along k stay aligned)
+    const int k0 = min(K, (int)((((long long)K * ksi) / ks + 3) & ~3LL));
+    const int k1 = ksi + 1 == ks ? K : min(K, (int)((((long long)K * (ksi + 1)) / ks + 3) & ~3LL));
     const int rg = lane >> 2, cg = lane & 3;
     float acc[TMT][TNT];
 #pragma unroll
     for (int i = 0; i < TMT; ++i)
 #pragma unroll
       for (int j = 0; j < TNT; ++j) acc[i][j] = 0.f;
-    float ra[TM / 2], rb[TN / 2];
-    float* sA = wbuf;
-    float* sB = wbuf + KC * TMS;
-    int kc = k0, kv = min(KC, k1 - k0);
-    if (kc < k1) {
-      load_A<TM, AL, MODE>(g, m0, kc, kv, lane, ra);
-      load_B<TN, BL, MODE>(g, n0, kc, kv, lane, rb);
-    }
-    while (kc < k1) {
-      __syncwarp();
-      store_A<TM, AL>(sA, lane, ra);
-      store_B<TN, BL>(sB, lane, rb);
-      __syncwarp();
-      const int kcn = kc + KC, kvn = min(KC, k1 - kcn);
-      if (kcn < k1) {                      // next chunk in flight while this one is contracted
-        load_A<TM, AL, MODE>(g, m0, kcn, kvn, lane, ra);
-        load_B<TN, BL, MODE>(g, n0, kcn, kvn, lane, rb);
-      }
-      if (kv == KC) {
-#pragma unroll
-        for (int kk = 0; kk < KC; ++kk) fma_step<TMT, TNT, TMS, TNS>(sA, sB, kk, rg, cg, acc);
-      } else {
+    const bool ones_here = AL == A_KM && g.ones_row >= m0 && g.ones_row < m0 + TM;
+    // NSTAGE-deep cp.async pipeline: chunks c+1 .. c+NSTAGE-1 are in flight while chunk c is contracted
+    const int nch = (k1 - k0 + KC - 1) / KC;
 #pragma unroll 1
-        for (int kk = 0; kk < kv; ++kk) fma_step<TMT, TNT, TMS, TNS>(sA, sB, kk, rg, cg, acc);
+    for (int c = 0; c < NSTAGE - 1; ++c) {
+      if (c < nch) {
+        const int kc = k0 + c * KC;
+        float* nA = wbuf + c * STAGE;
+        issue_A<TM, AL, MODE>(g, nA, m0, kc, min(KC, k1 - kc), lane);
+        issue_B<TN, BL, MODE>(g, nA + SA, n0, kc, min(KC, k1 - kc), lane);
       }
-      kc = kcn; kv = kvn;
+      cp_commit();
     }
-    __syncwarp();
+    FS_STAMP(1);
+    int st = 0;
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+      const int kc = k0 + c * KC;
+      const int kv = min(KC, k1 - kc);
+      float* sA = wbuf + st * STAGE;
+      float* sB = sA + SA;
+      {
+        const int cn = c + NSTAGE - 1;
+        if (cn < nch) {
+          const int kcn = k0 + cn * KC;
+          int sn = st + NSTAGE - 1; if (sn >= NSTAGE) sn -= NSTAGE;
+          float* nA = wbuf + sn * STAGE;
+          issue_A<TM, AL, MODE>(g, nA, m0, kcn, min(KC, k1 - kcn), lane);
+          issue_B<TN, BL, MODE>(g, nA + SA, n0, kcn, min(KC, k1 - kcn), lane);
+        }
+        cp_commit();
+      }
+      cp_wait<NSTAGE - 1>();
+      __syncwarp();
+      FS_STAMP(1);
+      if (ones_here) {                     // bias-gradient row of [act | 1]^T
+        if (lane < ((kv + 3) & ~3)) sA[lane * (TM + 4) + (g.ones_row - m0)] = lane < kv ? 1.f : 0.f;
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int kk = 0; kk < kv; kk += 4) fma_quad<TMT, TNT, AL, BL>(sA, sB, kk, rg, cg, acc);
+      __syncwarp();
+      FS_STAMP(1);
+      if (++st == NSTAGE) st = 0;
+    }
+    cp_wait<0>();
+    FS_STAMP(1);
     // this warp's partial tile, row-major [TM][TN], over its own stage
 #pragma unroll
     for (int i = 0; i < TMT; ++i)
 #pragma unroll
-      for (int j = 0; j < TNT; ++j) wbuf[(rg * TMT + i) * TN + col_of<TNT>(j, cg)] = acc[i][j];
+      for (int j = 0; j < TNT; ++j) wbuf[row_of<TMT, AL>(i, rg) * TN + col_of<TNT, BL>(j, cg)] = acc[i][j];
   }
   __syncthreads();
+  FS_STAMP(1);
   const int gidx = ksi * 32 + lane, gsize = ks * 32;
   float* gbuf = smem + (tl * ks) * WBUF;
   if (active) {
-    for (int e = gidx; e < TM * TNE; e += gsize) {
-      const int row = e / TNE, c = e - row * TNE;
-      float v0 = 0.f, v1 = 0.f;
-      for (int s = 0; s < ks; ++s) {
-        v0 += gbuf[s * WBUF + row * TN + c];
-        if (MODE == DUALN) v1 += gbuf[s * WBUF + row * TN + TN / 2 + c];
+    constexpr int U = 2;                   // elements in flight per thread: their global operands are
+#pragma unroll 1                           // requested before the partial tiles are summed
+    for (int e0 = gidx; e0 < TM * TNE; e0 += gsize * U) {
+      typename Epi::Pre pre[U];
+      int gm[U], gn[U], so[U];
+      bool ok[U], in[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * gsize;
+        in[u] = e < TM * TNE;
+        const int row = e / TNE, c = e - row * TNE;
+        so[u] = row * TN + c;
+        gm[u] = m0 + row; gn[u] = n0 + c;
+        ok[u] = in[u] && gm[u] < g.M && gn[u] < g.N;
+        if (ok[u]) pre[u] = epi.pre(gm[u], gn[u]);
       }
-      const int gm = m0 + row, gn = n0 + c;
-      float term = 0.f;
-      if (gm < g.M && gn < g.N) term = epi.elem(gm, gn, v0, v1);
-      if (Epi::ROWSUM) gbuf[row * TN + c] = term;
+      float v0[U], v1[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        v0[u] = 0.f; v1[u] = 0.f;
+        if (in[u]) {
+          for (int s = 0; s < ks; ++s) {
+            v0[u] += gbuf[s * WBUF + so[u]];
+            if (MODE == DUALN) v1[u] += gbuf[s * WBUF + so[u] + TN / 2];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float term = 0.f;
+        if (ok[u]) term = epi.elem(gm[u], gn[u], v0[u], v1[u], pre[u]);
+        if (Epi::ROWSUM && in[u]) gbuf[so[u]] = term;
+      }
     }
   }
   if (Epi::ROWSUM) {
@@ -255,17 +399,21 @@ __device__ __forceinline__ void run_item(const Gemm& g, int item, const Epi& epi
       epi.rowsum(m0 + gidx, tn, s);
     }
   }
+  FS_STAMP(1);
   __syncthreads();
+  FS_STAMP(1);
 }
 
 // ---------------------------------------------------------------------------------------------
-// epilogues
+// epilogues: pre() requests the global operands of one output element, elem() finishes it
 // ---------------------------------------------------------------------------------------------
 struct EpiTanh {                      // out = tanh(acc + bias[n])               VAEB.py:246,254
   static constexpr bool ROWSUM = false;
+  struct Pre { float b; };
   const float* bias; float* out; int ld;
-  __device__ __forceinline__ float elem(int m, int n, float v, float) const {
-    out[(size_t)m * ld + n] = tanhf(v + __ldcg(bias + n));
+  __device__ __forceinline__ Pre pre(int, int n) const { return Pre{__ldcg(bias + n)}; }
+  __device__ __forceinline__ float elem(int m, int n, float v, float, const Pre& q) const {
+    out[(size_t)m * ld + n] = tanhf(v + q.b);
     return 0.f;
   }
   __device__ __forceinline__ void rowsum(int, int, float) const {}
@@ -273,14 +421,18 @@ struct EpiTanh {                      // out = tanh(acc + bias[n])              
 
 struct EpiLatent {                    // VAEB.py:248-249 heads, :41-47 reparameterisation, :343 / :322-325 row terms
   static constexpr bool ROWSUM = true;
+  struct Pre { float b4, b5, e; };
   const float* b4; const float* b5; const float* eps_inj;
   uint64_t seed; uint32_t step; int64_t row_offset;
   int Z, la, n_tiles;
   float *mu, *ls, *eps, *z, *aux_part;
-  __device__ __forceinline__ float elem(int m, int j, float v0, float v1) const {
-    const float am = v0 + __ldcg(b4 + j), al = v1 + __ldcg(b5 + j);
+  __device__ __forceinline__ Pre pre(int m, int j) const {
+    return Pre{__ldcg(b4 + j), __ldcg(b5 + j), eps_inj ? __ldcg(eps_inj + (size_t)m * Z + j) : 0.f};
+  }
+  __device__ __forceinline__ float elem(int m, int j, float v0, float v1, const Pre& q) const {
+    const float am = v0 + q.b4, al = v1 + q.b5;
     const size_t o = (size_t)m * Z + j;
-    const float e = eps_inj ? __ldcg(eps_inj + o)
+    const float e = eps_inj ? q.e
                             : philox_normal1(seed, VAEB_STREAM_TRAIN, step, 0u, (uint64_t)((row_offset + m) * Z + j));
     const float zv = am + expf(0.5f * al) * e;
     mu[o] = am; ls[o] = al; eps[o] = e; z[o] = zv;
@@ -291,25 +443,29 @@ struct EpiLatent {                    // VAEB.py:248-249 heads, :41-47 reparamet
 
 struct EpiBernoulli {                 // VAEB.py:263,311: x*a - softplus(a); da = w*(x - sigmoid(a))
   static constexpr bool ROWSUM = true;
+  struct Pre { float b, x; };
   const float* b2; const float* x; int D; float scale; float* da; float* partial; int n_tiles;
-  __device__ __forceinline__ float elem(int m, int n, float v, float) const {
-    const float a = v + __ldcg(b2 + n);
-    const float xv = __ldcg(x + (size_t)m * D + n);
-    da[(size_t)m * D + n] = scale * (xv - sigmoidf_(a));
-    return xv * a - softplusf_(a);
+  __device__ __forceinline__ Pre pre(int m, int n) const { return Pre{__ldcg(b2 + n), __ldcg(x + (size_t)m * D + n)}; }
+  __device__ __forceinline__ float elem(int m, int n, float v, float, const Pre& q) const {
+    const float a = v + q.b;
+    da[(size_t)m * D + n] = scale * (q.x - sigmoidf_(a));
+    return q.x * a - softplusf_(a);
   }
   __device__ __forceinline__ void rowsum(int m, int tn, float s) const { partial[(size_t)m * n_tiles + tn] = s; }
 };
 
 struct EpiGaussian {                  // VAEB.py:257-258,306-307
   static constexpr bool ROWSUM = true;
+  struct Pre { float b2, b6, x; };
   const float* b2; const float* b6; const float* x; int D; float scale; float* da; float* dlv; float* partial;
   int n_tiles;
-  __device__ __forceinline__ float elem(int m, int n, float v0, float v1) const {
-    const float a = v0 + __ldcg(b2 + n), lv = v1 + __ldcg(b6 + n);
-    const float xv = __ldcg(x + (size_t)m * D + n);
+  __device__ __forceinline__ Pre pre(int m, int n) const {
+    return Pre{__ldcg(b2 + n), __ldcg(b6 + n), __ldcg(x + (size_t)m * D + n)};
+  }
+  __device__ __forceinline__ float elem(int m, int n, float v0, float v1, const Pre& q) const {
+    const float a = v0 + q.b2, lv = v1 + q.b6;
     const float mx = sigmoidf_(a);
-    const float d = xv - mx;
+    const float d = q.x - mx;
     const float r = d * expf(-lv);
     da[(size_t)m * D + n] = scale * r * mx * (1.0f - mx);
     dlv[(size_t)m * D + n] = scale * (-0.5f + 0.5f * d * r);
@@ -320,10 +476,11 @@ struct EpiGaussian {                  // VAEB.py:257-258,306-307
 
 struct EpiTanhBack {                  // out = acc * (1 - h^2)
   static constexpr bool ROWSUM = false;
+  struct Pre { float h; };
   const float* h; float* out; int ld;
-  __device__ __forceinline__ float elem(int m, int n, float v, float) const {
-    const float hv = __ldcg(h + (size_t)m * ld + n);
-    out[(size_t)m * ld + n] = v * (1.0f - hv * hv);
+  __device__ __forceinline__ Pre pre(int m, int n) const { return Pre{__ldcg(h + (size_t)m * ld + n)}; }
+  __device__ __forceinline__ float elem(int m, int n, float v, float, const Pre& q) const {
+    out[(size_t)m * ld + n] = v * (1.0f - q.h * q.h);
     return 0.f;
   }
   __device__ __forceinline__ void rowsum(int, int, float) const {}
@@ -331,18 +488,22 @@ struct EpiTanhBack {                  // out = acc * (1 - h^2)
 
 struct EpiDz {                        // dz -> dmu, dls (SURVEY.md 8a backward formulas), L == 1
   static constexpr bool ROWSUM = false;
+  struct Pre { float z, eps, mu, ls; };
   const float *z, *eps, *mu, *ls; int Z, la; float w; float *dmu, *dls;
-  __device__ __forceinline__ float elem(int m, int j, float v, float) const {
+  __device__ __forceinline__ Pre pre(int m, int j) const {
+    const size_t o = (size_t)m * Z + j;
+    return Pre{__ldcg(z + o), __ldcg(eps + o), __ldcg(mu + o), __ldcg(ls + o)};
+  }
+  __device__ __forceinline__ float elem(int m, int j, float v, float, const Pre& q) const {
     const size_t o = (size_t)m * Z + j;
     float d = v;
-    if (la) d -= w * __ldcg(z + o);
-    const float lsv = __ldcg(ls + o);
-    float a = d, b = d * (0.5f * expf(0.5f * lsv) * __ldcg(eps + o));
+    if (la) d -= w * q.z;
+    float a = d, b = d * (0.5f * expf(0.5f * q.ls) * q.eps);
     if (la) {
       b += w * 0.5f;
     } else {
-      a -= w * __ldcg(mu + o);
-      b += w * 0.5f * (1.0f - expf(lsv));
+      a -= w * q.mu;
+      b += w * 0.5f * (1.0f - expf(q.ls));
     }
     dmu[o] = a; dls[o] = b;
     return 0.f;
@@ -352,10 +513,9 @@ struct EpiDz {                        // dz -> dmu, dls (SURVEY.md 8a backward f
 
 struct Hyper { float lr, eps, prior, p2; };
 
-__device__ __forceinline__ void adagrad_apply(const float* P, float* Pn, float* ada, size_t o, float g, const Hyper& hy) {
-  const float p = __ldcg(P + o);
+__device__ __forceinline__ void adagrad_apply(float p, float a0, float* Pn, float* ada, size_t o, float g, const Hyper& hy) {
   g -= hy.prior * p;                                    // VAEB.py:389-390
-  const float a = __ldcg(ada + o) + g * g;              // VAEB.py:439
+  const float a = a0 + g * g;                           // VAEB.py:439
   float np_ = p + hy.lr * g / (sqrtf(a) + hy.eps);      // VAEB.py:441
   if (hy.p2 != 0.f) np_ -= hy.p2 * p * p;               // VAEBfullbayes.py:183-184
   Pn[o] = np_;
@@ -364,10 +524,17 @@ __device__ __forceinline__ void adagrad_apply(const float* P, float* Pn, float* 
 
 struct EpiAdagrad {                   // rows < nW: weight [nW, ld]; row == nW: the bias (ones row of A)
   static constexpr bool ROWSUM = false;
+  struct Pre { float p, a; };
   const float* P; float* Pn; float* ada; int64_t oW, ob; int nW, ld; Hyper hy;
-  __device__ __forceinline__ float elem(int m, int n, float v, float) const {
-    const size_t o = m < nW ? (size_t)oW + (size_t)m * ld + n : (size_t)ob + n;
-    adagrad_apply(P, Pn, ada, o, v, hy);
+  __device__ __forceinline__ size_t off(int m, int n) const {
+    return m < nW ? (size_t)oW + (size_t)m * ld + n : (size_t)ob + n;
+  }
+  __device__ __forceinline__ Pre pre(int m, int n) const {
+    const size_t o = off(m, n);
+    return Pre{__ldcg(P + o), __ldcg(ada + o)};
+  }
+  __device__ __forceinline__ float elem(int m, int n, float v, float, const Pre& q) const {
+    adagrad_apply(q.p, q.a, Pn, ada, off(m, n), v, hy);
     return 0.f;
   }
   __device__ __forceinline__ void rowsum(int, int, float) const {}
@@ -375,11 +542,17 @@ struct EpiAdagrad {                   // rows < nW: weight [nW, ld]; row == nW: 
 
 struct EpiAdagrad2 {                  // two heads at once (W4|W5, b4|b5)
   static constexpr bool ROWSUM = false;
+  struct Pre { float pa, aa, pb, ab; };
   const float* P; float* Pn; float* ada; int64_t oWa, oba, oWb, obb; int nW, ld; Hyper hy;
-  __device__ __forceinline__ float elem(int m, int n, float v0, float v1) const {
+  __device__ __forceinline__ Pre pre(int m, int n) const {
     const size_t off = m < nW ? (size_t)m * ld + n : (size_t)n;
-    adagrad_apply(P, Pn, ada, (size_t)(m < nW ? oWa : oba) + off, v0, hy);
-    adagrad_apply(P, Pn, ada, (size_t)(m < nW ? oWb : obb) + off, v1, hy);
+    const size_t oa = (size_t)(m < nW ? oWa : oba) + off, ob_ = (size_t)(m < nW ? oWb : obb) + off;
+    return Pre{__ldcg(P + oa), __ldcg(ada + oa), __ldcg(P + ob_), __ldcg(ada + ob_)};
+  }
+  __device__ __forceinline__ float elem(int m, int n, float v0, float v1, const Pre& q) const {
+    const size_t off = m < nW ? (size_t)m * ld + n : (size_t)n;
+    adagrad_apply(q.pa, q.aa, Pn, ada, (size_t)(m < nW ? oWa : oba) + off, v0, hy);
+    adagrad_apply(q.pb, q.ab, Pn, ada, (size_t)(m < nW ? oWb : obb) + off, v1, hy);
     return 0.f;
   }
   __device__ __forceinline__ void rowsum(int, int, float) const {}
@@ -389,17 +562,20 @@ struct EpiAdagrad2 {                  // two heads at once (W4|W5, b4|b5)
 // grid barrier + kernel
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target) {
+  const bool dbg = g_dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  FS_STAMP(-1);
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    // release: orders every write this CTA made before the bar.sync (cumulativity) before the arrival
     asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(bar) : "memory");
     unsigned long long v;
     do {
       asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
     } while (v < target);
-    __threadfence();
+    __threadfence();   // also drops this SM's L1 lines (4-byte cp.async.ca staging goes through L1)
   }
   __syncthreads();
+  FS_STAMP(-1);
 }
 
 __device__ __forceinline__ long long gtime() {
@@ -423,12 +599,12 @@ __global__ void __launch_bounds__(NT, 1) fused_step_kernel(const StepParams p) {
     const float* P = p.params[cur];
     float* Pn = p.params[cur ^ 1];
     const float* x = p.batch_order ? p.x_base + (size_t)__ldg(p.batch_order + s) * M * D : p.x_direct;
-    long long* tm = rec ? p.timing + (size_t)s * 9 : nullptr;
+    long long* tm = rec ? p.timing + (size_t)s * (N_PHASES + 1) : nullptr;
     if (tm) tm[0] = gtime();
 
     // ---- phase 1: encoder hidden layer ------------------------------------------------------
     {
-      const Gemm g{x, nullptr, D, P + p.oW3, nullptr, H, M, H, D, 0, -1, p.job[J_ENC1]};
+      const Gemm g = make_gemm(x, nullptr, D, P + p.oW3, nullptr, H, M, H, D, 0, -1, p.job[J_ENC1]);
       const EpiTanh epi{P + p.ob3, p.h_e, H};
       for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_ENC1), A_MK, B_KN, PLAIN>(g, it, epi, smem);
     }
@@ -437,7 +613,7 @@ __global__ void __launch_bounds__(NT, 1) fused_step_kernel(const StepParams p) {
 
     // ---- phase 2: latent heads, reparameterisation, KL / LA row terms -----------------------
     {
-      const Gemm g{p.h_e, nullptr, H, P + p.oW4, P + p.oW5, Z, M, Z, H, 0, -1, p.job[J_ENC2]};
+      const Gemm g = make_gemm(p.h_e, nullptr, H, P + p.oW4, P + p.oW5, Z, M, Z, H, 0, -1, p.job[J_ENC2]);
       const EpiLatent epi{P + p.ob4, P + p.ob5, p.eps_inj, p.seed, p.step0 + (uint32_t)s, p.row_offset, Z, p.la,
                           g.c.tiles_n, p.mu, p.ls, p.eps, p.z, p.aux_part};
       for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_ENC2), A_MK, B_KN, DUALN>(g, it, epi, smem);
@@ -447,7 +623,7 @@ __global__ void __launch_bounds__(NT, 1) fused_step_kernel(const StepParams p) {
 
     // ---- phase 3: decoder hidden layer ------------------------------------------------------
     {
-      const Gemm g{p.z, nullptr, Z, P + p.oW1, nullptr, H, M, H, Z, 0, -1, p.job[J_DEC1]};
+      const Gemm g = make_gemm(p.z, nullptr, Z, P + p.oW1, nullptr, H, M, H, Z, 0, -1, p.job[J_DEC1]);
       const EpiTanh epi{P + p.ob1, p.h_d, H};
       for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_DEC1), A_MK, B_KN, PLAIN>(g, it, epi, smem);
     }
@@ -456,11 +632,11 @@ __global__ void __launch_bounds__(NT, 1) fused_step_kernel(const StepParams p) {
 
     // ---- phase 4: decoder output layer + log-likelihood + output deltas -----------------------
     if (p.cont) {
-      const Gemm g{p.h_d, nullptr, H, P + p.oW2, P + p.oW6, D, M, D, H, 0, -1, p.job[J_DEC2]};
+      const Gemm g = make_gemm(p.h_d, nullptr, H, P + p.oW2, P + p.oW6, D, M, D, H, 0, -1, p.job[J_DEC2]);
       const EpiGaussian epi{P + p.ob2, P + p.ob6, x, D, p.w, p.da2, p.dlv, p.partial, g.c.tiles_n};
       for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_DEC2), A_MK, B_KN, DUALN>(g, it, epi, smem);
     } else {
-      const Gemm g{p.h_d, nullptr, H, P + p.oW2, nullptr, D, M, D, H, 0, -1, p.job[J_DEC2]};
+      const Gemm g = make_gemm(p.h_d, nullptr, H, P + p.oW2, nullptr, D, M, D, H, 0, -1, p.job[J_DEC2]);
       const EpiBernoulli epi{P + p.ob2, x, D, p.w, p.da2, p.partial, g.c.tiles_n};
       for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_DEC2), A_MK, B_KN, PLAIN>(g, it, epi, smem);
     }
@@ -471,10 +647,10 @@ __global__ void __launch_bounds__(NT, 1) fused_step_kernel(const StepParams p) {
     {
       const EpiTanhBack epi{p.h_d, p.da1, H};
       if (p.cont) {
-        const Gemm g{p.da2, p.dlv, D, P + p.oW2, P + p.oW6, D, M, H, D, D, -1, p.job[J_DGRAD]};
+        const Gemm g = make_gemm(p.da2, p.dlv, D, P + p.oW2, P + p.oW6, D, M, H, D, D, -1, p.job[J_DGRAD]);
         for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_DGRAD), A_MK, B_NK, DUALK>(g, it, epi, smem);
       } else {
-        const Gemm g{p.da2, nullptr, D, P + p.oW2, nullptr, D, M, H, D, 0, -1, p.job[J_DGRAD]};
+        const Gemm g = make_gemm(p.da2, nullptr, D, P + p.oW2, nullptr, D, M, H, D, 0, -1, p.job[J_DGRAD]);
         for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_DGRAD), A_MK, B_NK, PLAIN>(g, it, epi, smem);
       }
     }
@@ -483,13 +659,13 @@ __global__ void __launch_bounds__(NT, 1) fused_step_kernel(const StepParams p) {
 
     // ---- phase 6: W2 (W6) update | dz -> dmu, dls | W1 update | the bound ---------------------
     {
-      const Gemm g2{p.h_d, nullptr, H, p.da2, nullptr, D, H + 1, D, M, 0, H, p.job[J_WG2]};
+      const Gemm g2 = make_gemm(p.h_d, nullptr, H, p.da2, nullptr, D, H + 1, D, M, 0, H, p.job[J_WG2]);
       const EpiAdagrad e2{P, Pn, p.ada, p.oW2, p.ob2, H, D, hy};
-      const Gemm g6{p.h_d, nullptr, H, p.dlv, nullptr, D, H + 1, D, M, 0, H, p.job[J_WG6]};
+      const Gemm g6 = make_gemm(p.h_d, nullptr, H, p.dlv, nullptr, D, H + 1, D, M, 0, H, p.job[J_WG6]);
       const EpiAdagrad e6{P, Pn, p.ada, p.oW6, p.ob6, H, D, hy};
-      const Gemm gz{p.da1, nullptr, H, P + p.oW1, nullptr, H, M, Z, H, 0, -1, p.job[J_DZ]};
+      const Gemm gz = make_gemm(p.da1, nullptr, H, P + p.oW1, nullptr, H, M, Z, H, 0, -1, p.job[J_DZ]);
       const EpiDz ez{p.z, p.eps, p.mu, p.ls, Z, p.la, p.w, p.dmu, p.dls};
-      const Gemm g1{p.z, nullptr, Z, p.da1, nullptr, H, Z + 1, H, M, 0, Z, p.job[J_WG1]};
+      const Gemm g1 = make_gemm(p.z, nullptr, Z, p.da1, nullptr, H, Z + 1, H, M, 0, Z, p.job[J_WG1]);
       const EpiAdagrad e1{P, Pn, p.ada, p.oW1, p.ob1, Z, H, hy};
       const int n2 = g2.c.n_items, n6 = p.cont ? g6.c.n_items : 0, nz = gz.c.n_items, n1 = g1.c.n_items;
       const int total = n2 + n6 + nz + n1 + 1;
@@ -529,9 +705,9 @@ __global__ void __launch_bounds__(NT, 1) fused_step_kernel(const StepParams p) {
 
     // ---- phase 7: back through the latent heads | W4, W5 update ---------------------------------
     {
-      const Gemm gh{p.dmu, p.dls, Z, P + p.oW4, P + p.oW5, Z, M, H, Z, Z, -1, p.job[J_DHE]};
+      const Gemm gh = make_gemm(p.dmu, p.dls, Z, P + p.oW4, P + p.oW5, Z, M, H, Z, Z, -1, p.job[J_DHE]);
       const EpiTanhBack eh{p.h_e, p.da3, H};
-      const Gemm g45{p.h_e, nullptr, H, p.dmu, p.dls, Z, H + 1, Z, M, 0, H, p.job[J_WG45]};
+      const Gemm g45 = make_gemm(p.h_e, nullptr, H, p.dmu, p.dls, Z, H + 1, Z, M, 0, H, p.job[J_WG45]);
       const EpiAdagrad2 e45{P, Pn, p.ada, p.oW4, p.ob4, p.oW5, p.ob5, H, Z, hy};
       const int nh = gh.c.n_items, total = nh + g45.c.n_items;
       for (int it = cta; it < total; it += G) {
@@ -544,7 +720,7 @@ __global__ void __launch_bounds__(NT, 1) fused_step_kernel(const StepParams p) {
 
     // ---- phase 8: W3 update -------------------------------------------------------------------
     {
-      const Gemm g{x, nullptr, D, p.da3, nullptr, H, D + 1, H, M, 0, D, p.job[J_WG3]};
+      const Gemm g = make_gemm(x, nullptr, D, p.da3, nullptr, H, D + 1, H, M, 0, D, p.job[J_WG3]);
       const EpiAdagrad epi{P, Pn, p.ada, p.oW3, p.ob3, D, H, hy};
       for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_WG3), A_KM, B_KN, PLAIN>(g, it, epi, smem);
     }
@@ -571,7 +747,9 @@ static JobCfg plan_job(int job, int M, int N, int K, int n_cta, bool dual_n) {
       const int rounds = (items + n_cta - 1) / n_cta;
       const int per_smsp = (ks * tpi + 3) / 4;
       const double kper = std::ceil((double)K / ks);
-      const double cost = rounds * (per_smsp * kper * fma + 1500.0 + 40.0 * ks);
+      // a lone warp reaches ~40% of its scheduler's FFMA rate (issue latency, fragment loads); more
+      // resident warps hide it: time ~ (warps per scheduler + 1.5) * k steps * FFMAs per k step
+      const double cost = rounds * ((per_smsp + 1.5) * kper * fma + 1500.0 + 40.0 * ks);
       if (cost < best_cost) { best_cost = cost; best.ks = ks; best.tpi = tpi; best.n_items = items; }
     }
   }
@@ -659,10 +837,17 @@ int fused_step_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, 
   void* args[] = {&p};
   VAEB_CUDA(cudaLaunchCooperativeKernel((const void*)fused_step_kernel, dim3(f.n_sm), dim3(NT), args, SMEM_BYTES,
                                         h->stream));
-  f.bar_count += (unsigned long long)f.n_sm * 8ull * (unsigned long long)n_steps;
+  f.bar_count += (unsigned long long)f.n_sm * (unsigned long long)N_PHASES * (unsigned long long)n_steps;
   ++h->launches;
   h->step += (uint32_t)n_steps;
   if (n_steps & 1) std::swap(h->d_params, f.params_alt);   // theta now lives in the other buffer
   h->grads_have_prior = false;
   return VAEB_OK;
+}
+
+extern "C" int vaeb_fused_debug(long long* d_buf) {
+  int zero = 0;
+  cudaMemcpyToSymbol(fs::g_dbg, &d_buf, sizeof(d_buf));
+  cudaMemcpyToSymbol(fs::g_dbg_n, &zero, sizeof(int));
+  return 0;
 }

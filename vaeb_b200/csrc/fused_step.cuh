@@ -13,7 +13,9 @@ namespace fs {
 constexpr int NW = 16;            // warps per CTA
 constexpr int NT = NW * 32;       // threads per CTA
 constexpr int KC = 16;            // contraction chunk staged per warp
-constexpr int WBUF = 1280;        // floats of shared memory per warp (operand staging, then the tile)
+constexpr int NSTAGE = 2;          // cp.async stages per warp
+constexpr int WBUF = 960 * NSTAGE; // floats of shared memory per warp (operand stages, then the tile)
+constexpr int N_PHASES = 8;       // grid barriers per update
 constexpr size_t SMEM_BYTES = (size_t)NW * WBUF * sizeof(float) + 64;
 
 // tile jobs of one update, in phase order
@@ -67,7 +69,7 @@ struct StepParams {
   float* scalars; float Mg;       // scalars[s] = bound of step s / Mg
   int n_steps, parity0;
   unsigned long long* bar; unsigned long long bar_base;
-  long long* timing;              // nullptr or [n_steps*9] globaltimer stamps of CTA 0
+  long long* timing;              // nullptr or [n_steps*(N_PHASES+1)] globaltimer stamps of CTA 0
   JobCfg job[J_COUNT];
 };
 
