@@ -319,7 +319,10 @@ def run_own(args):
         tot = sum(p[1] for p in phases)
         roofline = {"kernel": "fs::fused_step_kernel (persistent cooperative kernel; one launch = %d updates)" % K,
                     "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                    "frac": ach / peaks["hbm_gbs"],
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+                    # (profiles/r1_fused_step_ncu_full.txt: 24.91 MB for a 50-update launch), scaled to K updates
+                    "traffic": 24.906496e6 / 50.0 * K,
                     "peak_source": peaks["source"] + " (copy bandwidth, MEASURED_PEAKS.json)",
                     "ms_per_launch": ms, "bytes_per_launch": bytes_per_update * K,
                     "bytes_per_update": bytes_per_update, "updates_per_launch": K,
