@@ -45,3 +45,43 @@ def test_tc_gemm_ragged_shapes(M, N, K):
 def test_tc_gemm_small_n_tile():
     Cm, ref = _run(128, 96, 256, 0, 0, 32)
     np.testing.assert_allclose(Cm, ref, rtol=2e-5, atol=2e-4)
+
+
+# ---- importance-sampled log p(x) on the tensor cores (is_tc.cu), bf16 tier ---------------------------
+def _is_case(D, H, Z, n, L, seed, scale):
+    import vaeb_b200
+    from oracle import vaeb_oracle as O
+    rng = np.random.RandomState(seed)
+    x = (rng.uniform(size=(n, D)) * (rng.uniform(size=(n, D)) < 0.3)).astype(np.float32)
+    params = [rng.normal(0, scale, s).astype(np.float32) for s in O.param_shapes(D, H, Z, False)]
+    eps = rng.normal(size=(n, L, Z)).astype(np.float32)
+    m = vaeb_b200.VAEB(x, False, H, Z, max(1, min(n, 4)), 1, 0.01, False, False, params, precision="bf16")
+    lp, lw = m.log_px(x, L=L, eps=eps, return_weights=True)
+    ref_lp, ref_lw = O.is_log_px([p.astype(np.float64) for p in params], x.astype(np.float64), eps.astype(np.float64), False)
+    m.close()
+    return lp, lw, ref_lp, ref_lw
+
+
+@pytest.mark.parametrize("D,H,Z,n,L", [(784, 500, 20, 5, 300), (37, 29, 3, 4, 130), (560, 200, 2, 3, 128), (100, 64, 8, 2, 7)])
+def test_is_logpx_tensor_core_matches_oracle(D, H, Z, n, L):
+    lp, lw, ref_lp, ref_lw = _is_case(D, H, Z, n, L, 11, 0.08)
+    # bf16 operands, fp32 accumulation: the 1e-2 tier (north star), per sample and per point
+    np.testing.assert_allclose(lw, ref_lw, rtol=1e-2, atol=1e-2)
+    np.testing.assert_allclose(lp, ref_lp, rtol=1e-2, atol=1e-2)
+
+
+def test_is_logpx_tensor_core_philox_sharding_invariance():
+    import vaeb_b200
+    from oracle import vaeb_oracle as O
+    D, H, Z, n, L = 784, 500, 20, 12, 700
+    rng = np.random.RandomState(2)
+    x = (rng.uniform(size=(n, D)) * (rng.uniform(size=(n, D)) < 0.2)).astype(np.float32)
+    params = [rng.normal(0, 0.05, s).astype(np.float32) for s in O.param_shapes(D, H, Z, False)]
+    m = vaeb_b200.VAEB(x, False, H, Z, 4, 1, 0.01, False, False, params, precision="bf16")
+    whole = m.log_px(x, L=L)
+    parts = np.concatenate([m.log_px(x[:5], L=L, row_offset=0), m.log_px(x[5:], L=L, row_offset=5)])
+    assert np.array_equal(whole, parts)                      # bit-identical for any sharding of the points
+    m32 = vaeb_b200.VAEB(x, False, H, Z, 4, 1, 0.01, False, False, params, precision="fp32")
+    ref = m32.log_px(x, L=L)                                 # same Philox draws, fp32 arithmetic
+    np.testing.assert_allclose(whole, ref, rtol=1e-2)
+    m.close(); m32.close()

@@ -12,6 +12,9 @@
 #include "philox.cuh"
 
 int dec2_col_tiles(int rows, int D);  // kernels_gemm.cu
+bool is_tc_supported(const vaeb_handle* h);   // is_tc.cu
+int is_tc_run(vaeb_handle* h, const float* d_x, const float* d_mu, const float* d_ls, int n, int L, const float* d_eps,
+              int64_t row_offset, float* d_logp, float* d_logw);
 
 static thread_local std::string g_last_error;
 void vaeb_set_error(const std::string& msg) { g_last_error = msg; }
@@ -776,10 +779,13 @@ int vaeb_is_logpx(vaeb_handle* h, const float* x, int64_t n, int32_t L, const fl
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
   const Layout& l = h->lay;
   const int D = h->D, H = h->H, Z = h->Z;
-  const int64_t chunk_rows = (int64_t)1 << 17;
-  const int pc = (int)std::max<int64_t>(1, std::min<int64_t>(n, chunk_rows / L));   // points per chunk
+  const bool tcp = is_tc_supported(h);
+  // points per chunk: the fp32 path materialises every decoder row, the tensor-core path only per-point data
+  const int64_t chunk_rows = (int64_t)1 << (tcp && logw_out ? 22 : 17);
+  const int pc = tcp && !logw_out ? (int)std::min<int64_t>(n, 8192)
+                                  : (int)std::max<int64_t>(1, std::min<int64_t>(n, chunk_rows / L));
   VAEB_REQUIRE((int64_t)pc * L < (int64_t)1 << 31, "L too large");
-  VAEB_TRY(ensure_ws(h, pc, (int64_t)pc * L, false));
+  VAEB_TRY(ensure_ws(h, pc, tcp && !logw_out ? pc : (int64_t)pc * L, false));
   VAEB_TRY(grow(&h->d_out, &h->out_cap, pc));
   cudaStream_t st = h->stream;
   int64_t* lc = &h->launches;
@@ -796,6 +802,15 @@ int vaeb_is_logpx(vaeb_handle* h, const float* x, int64_t n, int32_t L, const fl
     VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage, c, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, 1, s.h_e));
     VAEB_LAUNCH(launch_enc2(st, lc, s.h_e, c, H, T_(h, th, l.iW4), T_(h, th, l.ib4), T_(h, th, l.iW5),
                             T_(h, th, l.ib5), Z, 0, 0, src, s.mu, s.ls, s.eps, s.z, s.row_aux));
+    if (tcp) {
+      // decoder + log-likelihood + logsumexp in ONE tcgen05 kernel (is_tc.cu); bf16 operands
+      VAEB_TRY(is_tc_run(h, h->d_stage, s.mu, s.ls, c, L, d_eps, row_offset + i0, h->d_out, logw_out ? s.logw : nullptr));
+      VAEB_CUDA(cudaMemcpyAsync(logpx_out + i0, h->d_out, (size_t)c * sizeof(float), cudaMemcpyDeviceToHost, st));
+      if (logw_out)
+        VAEB_CUDA(cudaMemcpyAsync(logw_out + i0 * L, s.logw, (size_t)R * sizeof(float), cudaMemcpyDeviceToHost, st));
+      VAEB_CUDA(cudaStreamSynchronize(st));
+      continue;
+    }
     VAEB_LAUNCH(launch_is_sample(st, lc, s.mu, s.ls, c, L, Z, src, s.z, s.dec_aux));
     VAEB_LAUNCH(launch_dense_act(st, lc, s.z, R, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, 1, s.h_d));
     int tiles = 0;

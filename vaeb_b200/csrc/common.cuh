@@ -91,6 +91,15 @@ struct FusedState {
   fs::JobCfg job[fs::J_COUNT];
 };
 
+// State of the tensor-core importance-sampling estimator (is_tc.cu).
+struct IsTcState {
+  void* w2t = nullptr;                               // W2^T [D, KP] bf16
+  alignas(64) unsigned char map_full[128];           // CUtensorMap, boxes of 192 rows
+  alignas(64) unsigned char map_tail[128];           // CUtensorMap, boxes of the last chunk's rows
+  int n_sm = 0, n_chunks = 0, tail_cols = 0;
+  void* partial = nullptr; int64_t partial_cap = 0;  // per-tile (max, sum exp)
+};
+
 struct vaeb_handle {
   vaeb_config cfg;
   TcState tc;
@@ -116,6 +125,7 @@ struct vaeb_handle {
   int64_t launches = 0;
   bool grads_have_prior = false;
   FusedState fused;
+  IsTcState istc;
   bool fused_off = false;             // VAEB_B200_FUSED=0: always use the per-layer kernels
   // data parallel
   NcclApi nccl; void* comm = nullptr; int rank = 0, world = 1;
