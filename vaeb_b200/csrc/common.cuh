@@ -94,9 +94,10 @@ struct FusedState {
 // State of the tensor-core importance-sampling estimator (is_tc.cu).
 struct IsTcState {
   void* w2t = nullptr;                               // W2^T [D, KP] bf16
-  alignas(64) unsigned char map_full[128];           // CUtensorMap, boxes of 192 rows
-  alignas(64) unsigned char map_tail[128];           // CUtensorMap, boxes of the last chunk's rows
-  int n_sm = 0, n_chunks = 0, tail_cols = 0;
+  void* w1t = nullptr;                               // [W1^T | b1] [512, 64] bf16
+  alignas(64) unsigned char map_w1[128];             // CUtensorMap over w1t, boxes of 64 rows (one pass)
+  alignas(64) unsigned char map_full[128];           // CUtensorMap over w2t, boxes of `tail_cols` rows (one output chunk)
+  int n_sm = 0, n_chunks = 0, tail_cols = 0;         // tail_cols = chunk width NC (multiple of 16)
   void* partial = nullptr; int64_t partial_cap = 0;  // per-tile (max, sum exp)
 };
 

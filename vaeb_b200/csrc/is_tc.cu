@@ -1,17 +1,23 @@
 // Importance-sampled log p(x) on the 5th-generation tensor cores.
 //
 // One persistent kernel, one CTA per SM.  A work tile is 128 samples of ONE test point:
-//   z = mu + exp(.5 ls)*eps (Philox keyed by the global (point, sample, j))      -- producer warps
-//   h = tanh(z.W1 + b1), bf16, written straight into the UMMA K-major SWIZZLE_128B layout in shared
-//       memory: the decoder hidden layer never exists in HBM                       -- producer warps
+//   z = mu + exp(.5 ls)*eps (Philox keyed by the global (point, sample, j)), written as a bf16 [z|1]
+//       tile in the UMMA K-major SWIZZLE_128B layout                               -- producer warps
+//   pre = [z|1].[W1^T|b1] : tcgen05.mma, 64 hidden units per pass into one of four small TMEM
+//       accumulators (the bias rides along as contraction index Z)                 -- TMA + MMA warps
+//   h = tanh(pre) -> bf16 -> k block of the A tile in shared memory: the decoder hidden layer never
+//       exists in HBM                                                              -- producer warps
 //   a = h.W2 : tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM), W2^T streamed through a TMA
-//       ring of [192 n x 64 k] boxes, output swept in 192-column chunks, two TMEM accumulators so
-//       the epilogue of chunk c overlaps the MMAs of chunk c+1                     -- TMA + MMA warps
+//       ring of [NC n x 64 k] boxes, output swept in equal chunks of NC <= 128 columns (784 = 7 x 112),
+//       two TMEM accumulators so the epilogue of chunk c overlaps the MMAs of chunk c+1
 //   log w = sum_d x_d a_d - softplus(a_d) + log p(z) - log q(z|x), per sample; then the tile's
 //       (max, sum exp) pair -> partial[tile]                                       -- epilogue warps
+// The hidden layer of tile i+1 is computed while the LAST output chunk of tile i runs: that chunk is the
+// final reader of tile i's A blocks, each block is rewritten as soon as its MMAs retire (walk_items).
 // A finishing kernel folds the per-tile pairs of a point into log p^(x) = logsumexp - log L.
 // bf16 operands: the 1e-2 tier of the north star; the fp32 estimator (api.cu) stays the parity tier.
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "philox.cuh"
@@ -19,80 +25,135 @@
 
 namespace istc {
 
-constexpr int BM = 128, BK = 64, NC = 192, STAGES = 3;
+constexpr int BM = 128, BK = 64, NC_MAX = 128, STAGES = 4;
 constexpr int KB_MAX = 8;                       // hidden units padded to <= 512
-constexpr int ZMAX = 20;
+constexpr int ZMAX = 20;                        // latent size; the bias rides along as contraction index Z
+constexpr int ZG = 6;                           // groups of four contraction indices written per z row (24 >= Z + 1)
 constexpr int DMAX = 1024;
 constexpr int PROD_WARPS = 8, EPI_WARPS = 8;
 constexpr int THREADS = (4 + PROD_WARPS + EPI_WARPS) * 32;
 constexpr int A_BLOCK = BM * 128;               // bytes of one 64-wide k block of the A tile
-constexpr int B_STAGE = NC * 128;
-constexpr int TMEM_COLS = 512, ACC_STRIDE = 256;
+constexpr int B_STAGE = NC_MAX * 128;           // one ring stage: up to [128 rows x 64 k] bf16 (W2^T or W1^T box)
+constexpr int TMEM_COLS = 512;
+constexpr int W2T_PAD = 64;                     // W2^T row stride = KP + 64 elements: rows do not alias in L2
+constexpr int ACC_STRIDE = 128;                 // two accumulators of the output sweep: columns [0,128), [128,256)
+constexpr int MINI_COL0 = 256, MINI_BUFS = 4, MINI_N = 64;   // four 64-column accumulators of the hidden-layer GEMM
 
 struct Smem {                                   // offsets from a 1024-byte aligned base
-  static constexpr int A = 0;
-  static constexpr int B = A + KB_MAX * A_BLOCK;
-  static constexpr int ZS = B + STAGES * B_STAGE;            // [128][ZMAX] fp32
-  static constexpr int AUX = ZS + BM * ZMAX * 4;             // [2][128]
-  static constexpr int XB = AUX + 2 * BM * 4;                // [DMAX] float2 {b2[col], x[col]}; col >= D: {-1e30, 0}
+  static constexpr int A = 0;                                // h tile, 8 k blocks, UMMA K-major SW128
+  static constexpr int B = A + KB_MAX * A_BLOCK;             // TMA ring
+  static constexpr int ZB = B + STAGES * B_STAGE;            // [z | 1] tile, [128 x 64] bf16, K-major SW128
+  static constexpr int AUXP = ZB + BM * 128;                 // [128][ZG] partial prior/posterior terms
+  static constexpr int AUX = AUXP + BM * ZG * 4;             // [3][128]
+  static constexpr int XB = AUX + 3 * BM * 4;                // [DMAX] float2 {b2[col], x[col]}; col >= D: {-1e30, 0}
   static constexpr int ROWSUM = XB + DMAX * 8;               // [2][128]
   static constexpr int RED = ROWSUM + 2 * BM * 4;            // [8]
   static constexpr int BARS = RED + 64;                      // mbarriers
-  static constexpr int TOTAL = BARS + 256 + 1024;
+  static constexpr int TOTAL = BARS + 512 + 1024;
 };
 static_assert(Smem::TOTAL <= 232448, "shared memory budget");
 
 struct Params {
   int n_points, L, D, H, Z, KB;                 // KB = ceil(H / 64)
-  int tiles_per_point, n_chunks, tail_cols;     // output chunks of 192 columns, the last one `tail_cols` wide (multiple of 16)
+  int tiles_per_point, n_chunks, NC, zk;        // output chunks of NC columns (multiple of 16); zk = K=16 steps of [z|1]
   const float* x;                               // [n_points, D]
   const float* mu; const float* ls;             // [n_points, Z]
-  const float* W1; const float* b1; const float* b2;
+  const float* b2;
   const float* eps_inj;                         // [n_points, L, Z] or nullptr
   uint64_t seed; int64_t row_offset;
   float2* partial;                              // [n_points * tiles_per_point] (max, sum exp)
   float* logw_out;                              // nullptr or [n_points * L]
 };
 
-__device__ long long* g_is_dbg = nullptr;   // optional clock64 trace of CTA 0: [role][64]
-#define IS_STAMP(role, idx) do { if (g_is_dbg && blockIdx.x == 0 && (idx) < 64) g_is_dbg[(role) * 64 + (idx)] = clock64(); } while (0)
-
 __device__ __forceinline__ float tanh_approx(float v) {
   float r;
   asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
   return r;
 }
-// 16 accumulator columns of one row: rs += x*a - softplus(a), a = acc + b2; {b2, x} pairs at shared address xb
-__device__ __forceinline__ void fold16(const float (&v)[16], uint32_t xb, float& rs0, float& rs1) {
+// 8 accumulator columns of one row: rs += x*a - softplus(a), a = acc + b2; {b2, x} pairs at shared address xb
+__device__ __forceinline__ void fold8(const float (&v)[8], uint32_t xb, float& rs0, float& rs1) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    float bq, xq;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(bq), "=f"(xq) : "r"(xb + 8u * j));
-    const float a = v[j] + bq;
+  for (int j = 0; j < 8; j += 2) {
+    float b0, x0, b1, x1;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(x0), "=f"(b1), "=f"(x1) : "r"(xb + 8u * j));
+    const float a0 = v[j] + b0, a1 = v[j + 1] + b1;
     // softplus(a) = max(a,0) + ln2 * log2(1 + 2^(-|a| log2 e))
-    float t, lg;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(a) * -1.4426950408889634f));
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(1.0f + t));
-    const float sp = fmaf(lg, 0.6931471805599453f, fmaxf(a, 0.f));
-    if (j & 1) rs1 += fmaf(xq, a, -sp); else rs0 += fmaf(xq, a, -sp);
+    float t0, t1, l0, l1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fabsf(a0) * -1.4426950408889634f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fabsf(a1) * -1.4426950408889634f));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(1.0f + t0));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(1.0f + t1));
+    rs0 += fmaf(x0, a0, -fmaf(l0, 0.6931471805599453f, fmaxf(a0, 0.f)));
+    rs1 += fmaf(x1, a1, -fmaf(l1, 0.6931471805599453f, fmaxf(a1, 0.f)));
   }
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+// The order in which one CTA consumes ring stages, shared by the TMA and the MMA warp.  A "pass" is the
+// hidden-layer GEMM [z|1].W1^T for 64 hidden units of a tile (-> one k block of its A tile); a "w2" item is one
+// k block of one output chunk.  The passes of tile i+1 are interleaved with the LAST output chunk of tile i:
+// that chunk is the final reader of tile i's A blocks, so block kb can be rewritten as soon as its MMAs retire
+// (a_free[kb]) and the conversion of tile i+1 hides behind the rest of the sweep.  Pass j >= MINI_BUFS re-uses
+// the TMEM buffer of pass j-MINI_BUFS, whose conversion needs a_free[j-MINI_BUFS]: it is issued two k blocks later.
+template <class FPass, class FW2>
+__device__ __forceinline__ void walk_items(const Params& p, int n_tiles, FPass&& pass, FW2&& w2) {
+  if ((int)blockIdx.x >= n_tiles) return;
+  for (int j = 0; j < p.KB; ++j) pass(0u, j);
+  uint32_t ti = 0;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
+    const bool has_next = t + (int)gridDim.x < n_tiles;
+    for (int c = 0; c < p.n_chunks; ++c) {
+      const bool last = c == p.n_chunks - 1;
+      for (int kb = 0; kb < p.KB; ++kb) {
+        if (last && has_next) {
+          if (kb == 0) {
+            for (int j = 0; j < MINI_BUFS && j < p.KB; ++j) pass(ti + 1, j);
+          } else if (kb >= 2 && kb + 2 < p.KB) {
+            pass(ti + 1, kb + 2);
+          }
+        }
+        w2(ti, c, kb, last);
+      }
+    }
+  }
+}
+
+// Roles (640 threads): warp 0 TMA, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 producers
+// (z generation + TMEM -> tanh -> bf16 A tile conversion), warps 12-19 epilogue.
 __global__ void __launch_bounds__(THREADS, 1)
-is_tc_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_constant__ CUtensorMap map_tail, const Params p) {
+is_tc_kernel(const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_w1, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + Smem::BARS);
-  uint64_t* b_full = bars;                  // [STAGES]
-  uint64_t* b_empty = bars + STAGES;        // [STAGES]
-  uint64_t* a_full = bars + 2 * STAGES;
-  uint64_t* a_empty = a_full + 1;
-  uint64_t* acc_full = a_empty + 1;         // [2]
-  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint64_t* b_full = bars;                      // [STAGES]     TMA -> MMA
+  uint64_t* b_empty = b_full + STAGES;          // [STAGES]     MMA -> TMA
+  uint64_t* z_full = b_empty + STAGES;          //              producers -> MMA   ([z|1] tile written)
+  uint64_t* z_empty = z_full + 1;               //              MMA -> producers   (all passes of the tile retired)
+  uint64_t* mini_full = z_empty + 1;            // [MINI_BUFS]  MMA -> producers   (one pass of pre-activations in TMEM)
+  uint64_t* mini_empty = mini_full + MINI_BUFS; // [MINI_BUFS]  producers -> MMA
+  uint64_t* a_ready = mini_empty + MINI_BUFS;   // [KB_MAX]     producers -> MMA   (k block of the A tile written)
+  uint64_t* a_free = a_ready + KB_MAX;          // [KB_MAX]     MMA -> producers   (last chunk done with the k block)
+  uint64_t* acc_full = a_free + KB_MAX;         // [2]          MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 2;           // [2]          epilogue -> MMA
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
-  float* zs = (float*)(smem + Smem::ZS);
+  float* auxp = (float*)(smem + Smem::AUXP);
   float* aux_s = (float*)(smem + Smem::AUX);
   float2* xb = (float2*)(smem + Smem::XB);
   float* rowsum_s = (float*)(smem + Smem::ROWSUM);
@@ -102,193 +163,218 @@ is_tc_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_constant
   const int n_tiles = p.n_points * p.tiles_per_point;
 
   if (warp == 0 && lane == 0) {
-    tc::tma_prefetch_desc(&map_full);
-    tc::tma_prefetch_desc(&map_tail);
+    tc::tma_prefetch_desc(&map_w2);
+    tc::tma_prefetch_desc(&map_w1);
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
-    tc::mbar_init(a_full, PROD_WARPS);
-    tc::mbar_init(a_empty, 1);
+    tc::mbar_init(z_full, PROD_WARPS);
+    tc::mbar_init(z_empty, 1);
+    for (int b = 0; b < MINI_BUFS; ++b) { tc::mbar_init(&mini_full[b], 1); tc::mbar_init(&mini_empty[b], PROD_WARPS); }
+    for (int j = 0; j < KB_MAX; ++j) { tc::mbar_init(&a_ready[j], PROD_WARPS); tc::mbar_init(&a_free[j], 1); }
     for (int b = 0; b < 2; ++b) { tc::mbar_init(&acc_full[b], 1); tc::mbar_init(&acc_empty[b], EPI_WARPS); }
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc(tmem_slot, TMEM_COLS);
   // columns past D: b2 = -1e30 and x = 0 make x*a - softplus(a) exactly 0 (no per-element bounds test)
   for (int i = threadIdx.x; i < DMAX; i += THREADS) xb[i] = make_float2(i < p.D ? p.b2[i] : -1e30f, 0.f);
+  for (int i = threadIdx.x; i < BM * 128 / 16; i += THREADS)          // [z|1] tile: k >= 24 stays zero
+    reinterpret_cast<uint4*>(smem + Smem::ZB)[i] = make_uint4(0u, 0u, 0u, 0u);
+  tc::fence_proxy_async();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA: stream W2^T boxes [chunk rows x 64 k] =====
-    if (lane == 0) {
+    // ===== TMA: W1^T boxes of the passes and W2^T boxes of the sweep, in walk_items order =====
+    if (elect_one()) {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        for (int c = 0; c < p.n_chunks; ++c) {
-          const bool tail = c == p.n_chunks - 1 && p.tail_cols != NC;
-          const uint32_t bytes = (uint32_t)(tail ? p.tail_cols : NC) * 128u;
-          for (int kb = 0; kb < p.KB; ++kb, ++it) {
-            const int s = it % STAGES;
-            tc::mbar_wait(&b_empty[s], ((it / STAGES) & 1) ^ 1);
-            tc::mbar_expect_tx(&b_full[s], bytes);
-            tc::tma_load_2d(smem + Smem::B + s * B_STAGE, tail ? &map_tail : &map_full, &b_full[s], kb * BK, c * NC);
-          }
-        }
-      }
+      const uint32_t w2_bytes = (uint32_t)p.NC * 128u;
+      auto acquire = [&]() -> int {
+        const int s = it % STAGES;
+        tc::mbar_wait(&b_empty[s], ((it / STAGES) & 1) ^ 1);
+        ++it;
+        return s;
+      };
+      walk_items(p, n_tiles,
+        [&](uint32_t, int j) {
+          const int s = acquire();
+          tc::mbar_expect_tx(&b_full[s], (uint32_t)MINI_N * 128u);
+          tc::tma_load_2d(smem + Smem::B + s * B_STAGE, &map_w1, &b_full[s], 0, j * MINI_N);
+        },
+        [&](uint32_t, int c, int kb, bool) {
+          const int s = acquire();
+          tc::mbar_expect_tx(&b_full[s], w2_bytes);
+          tc::tma_load_2d(smem + Smem::B + s * B_STAGE, &map_w2, &b_full[s], kb * BK, c * p.NC);
+        });
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      uint32_t it = 0, acc_it = 0, tile_it = 0;
-      const uint32_t a_base = tc::smem_u32(smem + Smem::A);
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
-        tc::mbar_wait(a_full, tile_it & 1);
-        tc::tc_fence_after();
-        IS_STAMP(1, 2 * tile_it);
-        for (int c = 0; c < p.n_chunks; ++c, ++acc_it) {
-          const bool tail = c == p.n_chunks - 1 && p.tail_cols != NC;
-          const uint32_t idesc = tc::make_idesc_bf16(BM, tail ? p.tail_cols : NC, 0, 0);
-          const uint32_t buf = acc_it & 1;
-          tc::mbar_wait(&acc_empty[buf], ((acc_it >> 1) & 1) ^ 1);
+    // ===== MMA issuer: ONE elected lane runs the whole loop (its state stays on the uniform datapath) =====
+    if (elect_one()) {
+      uint32_t it = 0, acc_it = 0, mini_it = 0;
+      const uint64_t a_desc0 = tc::desc_kmajor(tc::smem_u32(smem + Smem::A), 0);
+      const uint64_t b_desc0 = tc::desc_kmajor(tc::smem_u32(smem + Smem::B), 0);
+      const uint64_t z_desc0 = tc::desc_kmajor(tc::smem_u32(smem + Smem::ZB), 0);
+      const uint32_t idesc_mini = tc::make_idesc_bf16(BM, MINI_N, 0, 0);
+      const uint32_t idesc = tc::make_idesc_bf16(BM, p.NC, 0, 0);
+      walk_items(p, n_tiles,
+        [&](uint32_t tseq, int j) {
+          if (j == 0) tc::mbar_wait(z_full, tseq & 1);
+          const int s = it % STAGES;
+          const uint32_t mb = mini_it % MINI_BUFS;
+          tc::mbar_wait(&b_full[s], (it / STAGES) & 1);
+          tc::mbar_wait(&mini_empty[mb], ((mini_it / MINI_BUFS) & 1) ^ 1);
           tc::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * ACC_STRIDE;
-          for (int kb = 0; kb < p.KB; ++kb, ++it) {
-            const int s = it % STAGES;
-            tc::mbar_wait(&b_full[s], (it / STAGES) & 1);
-            tc::tc_fence_after();
-            const uint32_t a = a_base + kb * A_BLOCK;
-            const uint32_t b = tc::smem_u32(smem + Smem::B + s * B_STAGE);
+          const uint32_t d = tmem_base + MINI_COL0 + mb * MINI_N;
+          const uint64_t b = b_desc0 + (uint64_t)(s * (B_STAGE >> 4));
+          for (int k = 0; k < p.zk; ++k)
+            tc::umma_bf16(d, z_desc0 + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc_mini, k ? 1u : 0u);
+          tc::umma_commit(&b_empty[s]);
+          tc::umma_commit(&mini_full[mb]);
+          if (j == p.KB - 1) tc::umma_commit(z_empty);
+          ++it; ++mini_it;
+        },
+        [&](uint32_t tseq, int c, int kb, bool last) {
+          const uint32_t buf = acc_it & 1;
+          if (kb == 0) tc::mbar_wait(&acc_empty[buf], ((acc_it >> 1) & 1) ^ 1);
+          if (c == 0) tc::mbar_wait(&a_ready[kb], tseq & 1);
+          const int s = it % STAGES;
+          tc::mbar_wait(&b_full[s], (it / STAGES) & 1);
+          tc::tc_fence_after();
+          const uint32_t d = tmem_base + buf * ACC_STRIDE;
+          const uint64_t a = a_desc0 + (uint64_t)(kb * (A_BLOCK >> 4));
+          const uint64_t b = b_desc0 + (uint64_t)(s * (B_STAGE >> 4));
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              tc::umma_bf16(d_tmem, tc::desc_kmajor(a, k), tc::desc_kmajor(b, k), idesc, (kb | k) != 0 ? 1u : 0u);
-            tc::umma_commit(&b_empty[s]);
-          }
-          tc::umma_commit(&acc_full[buf]);
-        }
-        tc::umma_commit(a_empty);        // every MMA that reads this A tile has completed
-        IS_STAMP(1, 2 * tile_it + 1);
-      }
+          for (int k = 0; k < BK / 16; ++k)
+            tc::umma_bf16(d, a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          tc::umma_commit(&b_empty[s]);
+          if (last) tc::umma_commit(&a_free[kb]);
+          if (kb == p.KB - 1) { tc::umma_commit(&acc_full[buf]); ++acc_it; }
+          ++it;
+        });
     }
+    __syncwarp();
   } else if (warp >= 4 && warp < 4 + PROD_WARPS) {
-    // ===== producers: z, aux, then h = tanh(z.W1 + b1) as the bf16 A tile =====
+    // ===== producers =====
     const int pw = warp - 4, pt = threadIdx.x - 128;           // pt in [0, 256)
-    const int Z = p.Z, H = p.H;
-    const int k0 = pw * 64 + 2 * lane;                         // this thread's two hidden units
-    float w1a[ZMAX], w1b[ZMAX];
-#pragma unroll
-    for (int j = 0; j < ZMAX; ++j) {
-      w1a[j] = (j < Z && k0 < H) ? p.W1[(size_t)j * H + k0] : 0.f;
-      w1b[j] = (j < Z && k0 + 1 < H) ? p.W1[(size_t)j * H + k0 + 1] : 0.f;
-    }
-    const float b1a = k0 < H ? p.b1[k0] : 0.f, b1b = k0 + 1 < H ? p.b1[k0 + 1] : 0.f;
-    uint32_t tile_it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
+    const int q = warp & 3, hsel = pw >> 2;                    // TMEM lane quarter, which 32-column half of a pass
+    const int Z = p.Z;
+    uint8_t* zb = smem + Smem::ZB;
+
+    // z, [z|1] bf16 tile and the prior/posterior row terms of tile `t` (tile counter `ti`)
+    auto make_z = [&](int t, uint32_t ti) {
       const int pi = t / p.tiles_per_point, l0 = (t - pi * p.tiles_per_point) * BM;
-      tc::mbar_wait(a_empty, (tile_it & 1) ^ 1);               // the previous tile's MMAs are done with A (and zs)
-      if (pt == 0) IS_STAMP(0, 3 * tile_it);
-      // --- z of every sample row: one task = (row, 4 consecutive latent dims) = one Philox call
-      float* aux_t = aux_s + (tile_it & 1) * BM;
-      {
-        constexpr int G = ZMAX / 4;
-        const bool quad = (Z & 3) == 0 && !p.eps_inj;          // element groups line up with Philox groups
-        for (int i = pt; i < BM * G; i += PROD_WARPS * 32) {
-          const int r = i / G, j0 = (i - r * G) * 4;
-          const int l = l0 + r;
-          float nrm[4] = {0.f, 0.f, 0.f, 0.f};
-          if (quad && j0 < Z)
-            philox_normal4(p.seed, VAEB_STREAM_IS, 0u, (uint32_t)l, (uint64_t)((p.row_offset + pi) * Z + j0) >> 2, nrm);
-          float4 zq;
-          float* zp = &zq.x;
+      tc::mbar_wait(z_empty, (ti & 1) ^ 1);
+      const bool quad = (Z & 3) == 0 && !p.eps_inj;            // element groups line up with Philox groups
+      for (int i = pt; i < BM * ZG; i += PROD_WARPS * 32) {
+        const int r = i / ZG, g = i - r * ZG, j0 = 4 * g;
+        const int l = l0 + r;
+        float nrm[4] = {0.f, 0.f, 0.f, 0.f};
+        if (quad && j0 < Z)
+          philox_normal4(p.seed, VAEB_STREAM_IS, 0u, (uint32_t)l, (uint64_t)((p.row_offset + pi) * Z + j0) >> 2, nrm);
+        float zq[4], a = 0.f;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int j = j0 + u;
-            float zv = 0.f;
-            if (j < Z) {
-              float e;
-              if (p.eps_inj) e = l < p.L ? p.eps_inj[((size_t)pi * p.L + l) * Z + j] : 0.f;
-              else if (quad) e = nrm[u];
-              else e = philox_normal1(p.seed, VAEB_STREAM_IS, 0u, (uint32_t)l, (uint64_t)((p.row_offset + pi) * Z + j));
-              zv = __ldg(p.mu + (size_t)pi * Z + j) + expf(0.5f * __ldg(p.ls + (size_t)pi * Z + j)) * e;
-            }
-            zp[u] = zv;
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u;
+          float zv = j == Z ? 1.0f : 0.f;                      // contraction index Z carries the bias b1
+          if (j < Z) {
+            float e;
+            if (p.eps_inj) e = l < p.L ? p.eps_inj[((size_t)pi * p.L + l) * Z + j] : 0.f;
+            else if (quad) e = nrm[u];
+            else e = philox_normal1(p.seed, VAEB_STREAM_IS, 0u, (uint32_t)l, (uint64_t)((p.row_offset + pi) * Z + j));
+            const float lsv = __ldg(p.ls + (size_t)pi * Z + j);
+            zv = __ldg(p.mu + (size_t)pi * Z + j) + expf(0.5f * lsv) * e;
+            a += -0.5f * zv * zv + 0.5f * lsv + 0.5f * e * e;  // log p(z) - log q(z|x), VAEB.py:322-325
           }
-          *reinterpret_cast<float4*>(zs + r * ZMAX + j0) = zq;
+          zq[u] = zv;
         }
+        auxp[r * ZG + g] = a;
+        // 4 bf16 = 8 bytes at columns [4g, 4g+4) of row r (16-byte chunk g/2, swizzled)
+        uint2 pk = make_uint2(pack_bf16(zq[0], zq[1]), pack_bf16(zq[2], zq[3]));
+        *reinterpret_cast<uint2*>(zb + r * 128 + ((((uint32_t)g >> 1) ^ ((uint32_t)r & 7u)) << 4) + (g & 1) * 8) = pk;
       }
+      tc::fence_proxy_async();
       named_bar(1, PROD_WARPS * 32);
-      if (pt < BM) {                                           // aux[r] = sum_j -z^2/2 + ls/2 + eps^2/2, eps = (z-mu)/sd
+      if (pt < BM) {
         float a = 0.f;
-        for (int j = 0; j < Z; ++j) {
-          const float lsv = __ldg(p.ls + (size_t)pi * Z + j), zv = zs[pt * ZMAX + j];
-          const float e = (zv - __ldg(p.mu + (size_t)pi * Z + j)) * expf(-0.5f * lsv);
-          a += -0.5f * zv * zv + 0.5f * lsv + 0.5f * e * e;
-        }
-        aux_t[pt] = a;
-      }
-      if (pt == 0) IS_STAMP(0, 3 * tile_it + 1);
-      // --- the A tile: warp pw fills k block pw (128 rows x 64 hidden units)
-      if (pw < p.KB) {
-        uint8_t* ablk = smem + Smem::A + pw * A_BLOCK;
-#pragma unroll 2
-        for (int r = 0; r < BM; ++r) {
-          float ha = b1a, hb = b1b;
-          const float4* zr = reinterpret_cast<const float4*>(zs + r * ZMAX);
 #pragma unroll
-          for (int q = 0; q < ZMAX / 4; ++q) {
-            const float4 zq = zr[q];
-            ha = fmaf(zq.x, w1a[4 * q], ha); hb = fmaf(zq.x, w1b[4 * q], hb);
-            ha = fmaf(zq.y, w1a[4 * q + 1], ha); hb = fmaf(zq.y, w1b[4 * q + 1], hb);
-            ha = fmaf(zq.z, w1a[4 * q + 2], ha); hb = fmaf(zq.z, w1b[4 * q + 2], hb);
-            ha = fmaf(zq.w, w1a[4 * q + 3], ha); hb = fmaf(zq.w, w1b[4 * q + 3], hb);
-          }
-          const __nv_bfloat162 hv = __floats2bfloat162_rn(tanh_approx(ha), tanh_approx(hb));
-          *reinterpret_cast<__nv_bfloat162*>(ablk + tc::sw128_offset(r, 2 * lane)) = hv;
-        }
+        for (int g = 0; g < ZG; ++g) a += auxp[pt * ZG + g];
+        aux_s[(ti % 3) * BM + pt] = a;
       }
-      tc::fence_proxy_async();                                 // generic-proxy writes -> visible to the MMA
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(a_full);
-      if (pt == 0) IS_STAMP(0, 3 * tile_it + 2);
+      if (lane == 0) tc::mbar_arrive(z_full);
+    };
+
+    uint32_t tile_it = 0, mini_it = 0;
+    if ((int)blockIdx.x < n_tiles) make_z(blockIdx.x, 0);
+    const int r = q * 32 + lane;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
+      // --- pre-activations -> tanh -> bf16 -> A tile: this warp owns rows [32q, 32q+32), columns [32 hsel, +32) of k block j
+      for (int j = 0; j < p.KB; ++j, ++mini_it) {
+        const uint32_t mb = mini_it % MINI_BUFS;
+        tc::mbar_wait(&mini_full[mb], (mini_it / MINI_BUFS) & 1);
+        tc::mbar_wait(&a_free[j], (tile_it & 1) ^ 1);          // the previous tile's last chunk has read this k block
+        tc::tc_fence_after();
+        const uint32_t taddr = tmem_base + MINI_COL0 + mb * MINI_N + hsel * 32 + ((uint32_t)(q * 32) << 16);
+        uint8_t* arow = smem + Smem::A + j * A_BLOCK + r * 128;
+        float v[32];
+        tc::tmem_ld32(taddr, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+          uint4 pk;
+          pk.x = pack_bf16(tanh_approx(v[8 * c16 + 0]), tanh_approx(v[8 * c16 + 1]));
+          pk.y = pack_bf16(tanh_approx(v[8 * c16 + 2]), tanh_approx(v[8 * c16 + 3]));
+          pk.z = pack_bf16(tanh_approx(v[8 * c16 + 4]), tanh_approx(v[8 * c16 + 5]));
+          pk.w = pack_bf16(tanh_approx(v[8 * c16 + 6]), tanh_approx(v[8 * c16 + 7]));
+          const uint32_t chunk = (uint32_t)(hsel * 4 + c16);
+          *reinterpret_cast<uint4*>(arow + ((chunk ^ ((uint32_t)r & 7u)) << 4)) = pk;
+        }
+        tc::fence_proxy_async();                               // generic-proxy writes -> visible to the MMA
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { tc::mbar_arrive(&mini_empty[mb]); tc::mbar_arrive(&a_ready[j]); }
+      }
+      // --- z of the NEXT tile while this tile's output sweep runs
+      const int tn = t + gridDim.x;
+      if (tn < n_tiles) make_z(tn, tile_it + 1);
     }
   } else if (warp >= 4 + PROD_WARPS) {
     // ===== epilogue: TMEM -> x*a - softplus(a) row sums -> log w -> tile (max, sum exp) =====
     const int e = warp - 4 - PROD_WARPS, q = warp & 3, ch = e >> 2;   // TMEM lane quarter = warp % 4
     const int et = threadIdx.x - (4 + PROD_WARPS) * 32;                // [0, 256)
     const int row = q * 32 + lane;
+    const int half = p.NC >> 1, n8 = half >> 3, c_lo = ch * half;      // NC is a multiple of 16
+    const uint32_t xb_addr = tc::smem_u32(xb);
     uint32_t acc_it = 0, tile_it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
       const int pi = t / p.tiles_per_point, l0 = (t - pi * p.tiles_per_point) * BM;
       for (int i = et; i < p.D; i += EPI_WARPS * 32) xb[i].y = p.x[(size_t)pi * p.D + i];
       named_bar(2, EPI_WARPS * 32);
-      const uint32_t xb_addr = tc::smem_u32(xb);
       float rs0 = 0.f, rs1 = 0.f;
       for (int c = 0; c < p.n_chunks; ++c, ++acc_it) {
-        const bool tail = c == p.n_chunks - 1 && p.tail_cols != NC;
-        const int width = tail ? p.tail_cols : NC;
         const uint32_t buf = acc_it & 1;
         tc::mbar_wait(&acc_full[buf], (acc_it >> 1) & 1);
         tc::tc_fence_after();
-        if (et == 0) IS_STAMP(2, 2 * acc_it);
-        const uint32_t taddr = tmem_base + buf * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-        // this warp's half of the chunk, 16 columns per TMEM load; the next load is in flight while
-        // the current 16 columns are folded
-        const int half = (width / 2 + 15) & ~15;
-        const int c_lo = ch * half, c_hi = min(width, c_lo + half);
-        float va[16], vb[16];
-        if (c_lo < c_hi) tc::tmem_ld16(taddr + (uint32_t)c_lo, va);
-        for (int cc = c_lo; cc < c_hi; cc += 32) {
+        const uint32_t taddr = tmem_base + buf * ACC_STRIDE + (uint32_t)c_lo + ((uint32_t)(q * 32) << 16);
+        const uint32_t xa = xb_addr + (uint32_t)(c * p.NC + c_lo) * 8u;
+        // this warp's half of the chunk, 8 columns per TMEM load; the next load is in flight while the
+        // current 8 columns are folded
+        float va[8], vb[8];
+        tmem_ld8(taddr, va);
+        for (int i = 0; i < n8; i += 2) {
           tc::tmem_ld_wait();
-          if (cc + 16 < c_hi) tc::tmem_ld16(taddr + (uint32_t)(cc + 16), vb);
-          fold16(va, xb_addr + (uint32_t)(c * NC + cc) * 8u, rs0, rs1);
-          if (cc + 16 < c_hi) {
+          if (i + 1 < n8) tmem_ld8(taddr + 8u * (i + 1), vb);
+          fold8(va, xa + 64u * i, rs0, rs1);
+          if (i + 1 < n8) {
             tc::tmem_ld_wait();
-            if (cc + 32 < c_hi) tc::tmem_ld16(taddr + (uint32_t)(cc + 32), va);
-            fold16(vb, xb_addr + (uint32_t)(c * NC + cc + 16) * 8u, rs0, rs1);
+            if (i + 2 < n8) tmem_ld8(taddr + 8u * (i + 2), va);
+            fold8(vb, xa + 64u * (i + 1), rs0, rs1);
           }
         }
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
-        if (et == 0) IS_STAMP(2, 2 * acc_it + 1);
       }
       const float rs = rs0 + rs1;
       rowsum_s[ch * BM + row] = rs;
@@ -296,7 +382,7 @@ is_tc_kernel(const __grid_constant__ CUtensorMap map_full, const __grid_constant
       if (ch == 0) {
         const int l = l0 + row;
         const bool valid = l < p.L;
-        const float lw = rowsum_s[row] + rowsum_s[BM + row] + aux_s[(tile_it & 1) * BM + row];
+        const float lw = rowsum_s[row] + rowsum_s[BM + row] + aux_s[(tile_it % 3) * BM + row];
         if (valid && p.logw_out) p.logw_out[(size_t)pi * p.L + l] = lw;
         float m = valid ? lw : -INFINITY;
 #pragma unroll
@@ -338,11 +424,24 @@ __global__ void is_tc_finish_kernel(const float2* __restrict__ partial, int n_po
 }
 
 // W2 [H, D] fp32 -> W2^T [D, KP] bf16 (k contiguous, zero padded to KP = 64*KB)
-__global__ void is_tc_prep_kernel(const float* __restrict__ W2, int H, int D, int KP, __nv_bfloat16* __restrict__ w2t) {
+__global__ void is_tc_prep_kernel(const float* __restrict__ W2, int H, int D, int KP, int ld,
+                                  __nv_bfloat16* __restrict__ w2t) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)D * KP) return;
   const int n = (int)(i / KP), k = (int)(i % KP);
-  w2t[i] = __float2bfloat16_rn(k < H ? W2[(size_t)k * D + n] : 0.f);
+  w2t[(size_t)n * ld + k] = __float2bfloat16_rn(k < H ? W2[(size_t)k * D + n] : 0.f);
+}
+
+// [W1^T | b1] as the B operand of the hidden-layer GEMM: w1t[n][k] bf16, n < KP hidden units, 64 contraction
+// slots: k < Z -> W1[k][n], k == Z -> b1[n], the rest (and rows n >= H) zero
+__global__ void is_tc_prep_w1_kernel(const float* __restrict__ W1, const float* __restrict__ b1, int H, int Z, int KP,
+                                     __nv_bfloat16* __restrict__ w1t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= KP * 64) return;
+  const int n = i >> 6, k = i & 63;
+  float v = 0.f;
+  if (n < H) v = k < Z ? W1[(size_t)k * H + n] : (k == Z ? b1[n] : 0.f);
+  w1t[i] = __float2bfloat16_rn(v);
 }
 
 }  // namespace istc
@@ -362,22 +461,28 @@ int is_tc_run(vaeb_handle* h, const float* d_x, const float* d_mu, const float* 
   IsTcState& s = h->istc;
   cudaStream_t st = h->stream;
   if (!s.w2t) {
-    VAEB_CUDA(cudaMalloc(&s.w2t, (size_t)D * KP * 2));
+    VAEB_CUDA(cudaMalloc(&s.w2t, (size_t)D * (KP + W2T_PAD) * 2));
+    VAEB_CUDA(cudaMalloc(&s.w1t, (size_t)(KB_MAX * 64) * 64 * 2));
+    VAEB_CUDA(cudaMemset(s.w1t, 0, (size_t)(KB_MAX * 64) * 64 * 2));
+    VAEB_TRY(vaeb_make_tmap_bf16((CUtensorMap*)s.map_w1, s.w1t, (uint64_t)(KB_MAX * 64), 64, 64, MINI_N));
     VAEB_CUDA(cudaFuncSetAttribute(is_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::TOTAL));
     VAEB_CUDA(cudaDeviceGetAttribute(&s.n_sm, cudaDevAttrMultiProcessorCount, h->cfg.device));
-    const int n_chunks = (D + NC - 1) / NC;
-    int tail = D - (n_chunks - 1) * NC;
-    tail = (tail + 15) & ~15;
-    s.n_chunks = n_chunks; s.tail_cols = tail;
-    VAEB_TRY(vaeb_make_tmap_bf16((CUtensorMap*)s.map_full, s.w2t, (uint64_t)D, (uint64_t)KP, (uint64_t)KP, NC));
-    VAEB_TRY(vaeb_make_tmap_bf16((CUtensorMap*)s.map_tail, s.w2t, (uint64_t)D, (uint64_t)KP, (uint64_t)KP,
-                                 (uint32_t)tail));
+    // output chunks: as few as fit 128 accumulator columns, equal width (a multiple of 16): 784 = 7 x 112
+    const int n_chunks = (D + NC_MAX - 1) / NC_MAX;
+    const int nc = (((D + n_chunks - 1) / n_chunks) + 15) & ~15;
+    s.n_chunks = n_chunks; s.tail_cols = nc;
+    VAEB_TRY(vaeb_make_tmap_bf16((CUtensorMap*)s.map_full, s.w2t, (uint64_t)D, (uint64_t)KP, (uint64_t)(KP + W2T_PAD),
+                                 (uint32_t)nc));
   }
   // the weights may have changed since the last call: refresh the bf16 transpose (0.8 MB)
   {
     const int64_t tot = (int64_t)D * KP;
     is_tc_prep_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->d_params + l.off[l.iW2], H, D, KP,
-                                                                    (__nv_bfloat16*)s.w2t);
+                                                                    KP + W2T_PAD, (__nv_bfloat16*)s.w2t);
+    ++h->launches;
+    VAEB_CUDA(cudaGetLastError());
+    is_tc_prep_w1_kernel<<<(KP * 64 + 255) / 256, 256, 0, st>>>(h->d_params + l.off[l.iW1], h->d_params + l.off[l.ib1], H,
+                                                                Z, KP, (__nv_bfloat16*)s.w1t);
     ++h->launches;
     VAEB_CUDA(cudaGetLastError());
   }
@@ -393,13 +498,14 @@ int is_tc_run(vaeb_handle* h, const float* d_x, const float* d_mu, const float* 
   }
   Params p{};
   p.n_points = n; p.L = L; p.D = D; p.H = H; p.Z = Z; p.KB = KB;
-  p.tiles_per_point = tpp; p.n_chunks = s.n_chunks; p.tail_cols = s.tail_cols;
+  p.tiles_per_point = tpp; p.n_chunks = s.n_chunks; p.NC = s.tail_cols; p.zk = (Z + 1 + 15) / 16;
   p.x = d_x; p.mu = d_mu; p.ls = d_ls;
-  p.W1 = h->d_params + l.off[l.iW1]; p.b1 = h->d_params + l.off[l.ib1]; p.b2 = h->d_params + l.off[l.ib2];
+  p.b2 = h->d_params + l.off[l.ib2];
   p.eps_inj = d_eps; p.seed = h->cfg.seed; p.row_offset = row_offset;
   p.partial = (float2*)s.partial; p.logw_out = d_logw;
-  const int grid = (int)std::min<int64_t>(n_tiles, s.n_sm);
-  is_tc_kernel<<<grid, THREADS, Smem::TOTAL, st>>>(*(const CUtensorMap*)s.map_full, *(const CUtensorMap*)s.map_tail, p);
+  int grid = (int)std::min<int64_t>(n_tiles, s.n_sm);
+  { const char* e = getenv("VAEB_IS_GRID"); if (e) grid = std::min(grid, atoi(e)); }
+  is_tc_kernel<<<grid, THREADS, Smem::TOTAL, st>>>(*(const CUtensorMap*)s.map_full, *(const CUtensorMap*)s.map_w1, p);
   ++h->launches;
   VAEB_CUDA(cudaGetLastError());
   is_tc_finish_kernel<<<(n + 127) / 128, 128, 0, st>>>((const float2*)s.partial, n, tpp, L, d_logp);
@@ -408,7 +514,3 @@ int is_tc_run(vaeb_handle* h, const float* d_x, const float* d_mu, const float* 
   return VAEB_OK;
 }
 
-extern "C" int vaeb_is_tc_debug(long long* d_buf) {
-  cudaMemcpyToSymbol(istc::g_is_dbg, &d_buf, sizeof(d_buf));
-  return 0;
-}

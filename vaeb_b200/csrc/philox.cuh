@@ -40,8 +40,8 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t stream, u
   const float rad0 = sqrtf(-2.0f * logf(u0));
   const float rad1 = sqrtf(-2.0f * logf(u2));
   float s0, c0, s1, c1;
-  sincosf(6.2831855f * u1, &s0, &c0);
-  sincosf(6.2831855f * u3, &s1, &c1);
+  sincospif(2.0f * u1, &s0, &c0);   // exact argument reduction: no slow path, small code
+  sincospif(2.0f * u3, &s1, &c1);
   n[0] = rad0 * c0; n[1] = rad0 * s0; n[2] = rad1 * c1; n[3] = rad1 * s1;
 }
 

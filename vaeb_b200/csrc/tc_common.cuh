@@ -35,6 +35,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
+#pragma unroll 1
   for (uint32_t it = 0; it < 400000000u; ++it) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -44,6 +45,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (ok) return;
+  }
+  __trap();
+}
+
+// Warp-collective wait: all 32 lanes (converged) poll, the loop exit is decided by a vote, so control
+// flow stays warp-uniform and the compiler keeps loop state on the uniform datapath (the issue loops of
+// the TMA / MMA warps must stay short: one warp issues every tcgen05.mma of the CTA).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+  for (uint32_t it = 0; it < 400000000u; ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (__all_sync(0xffffffffu, ok)) return;
   }
   __trap();
 }
