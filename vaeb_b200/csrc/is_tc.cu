@@ -45,7 +45,7 @@ struct Smem {                                   // offsets from a 1024-byte alig
   static constexpr int ZB = B + STAGES * B_STAGE;            // [z | 1] tile, [128 x 64] bf16, K-major SW128
   static constexpr int AUXP = ZB + BM * 128;                 // [128][ZG] partial prior/posterior terms
   static constexpr int AUX = AUXP + BM * ZG * 4;             // [3][128]
-  static constexpr int XB = AUX + 3 * BM * 4;                // [DMAX] float2 {b2[col], x[col]}; col >= D: {-1e30, 0}
+  static constexpr int XB = AUX + 3 * BM * 4;                // [DMAX] b2[col] then [DMAX] x[col] - 1/2; col >= D: (-30, -1/2)
   static constexpr int ROWSUM = XB + DMAX * 8;               // [2][128]
   static constexpr int RED = ROWSUM + 2 * BM * 4;            // [8]
   static constexpr int BARS = RED + 64;                      // mbarriers
@@ -70,21 +70,62 @@ __device__ __forceinline__ float tanh_approx(float v) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
   return r;
 }
-// 8 accumulator columns of one row: rs += x*a - softplus(a), a = acc + b2; {b2, x} pairs at shared address xb
-__device__ __forceinline__ void fold8(const float (&v)[8], uint32_t xb, float& rs0, float& rs1) {
+// ---- packed fp32 pairs (FADD2 / FMUL2 / FFMA2 of sm_100): the epilogue is issue- and MUFU-bound ----
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// Bernoulli log-likelihood of 8 accumulator columns of one row, two columns per instruction:
+//   x a - softplus(a) = a (x - 1/2) - |a|/2 - ln(1 + e^-|a|),   a = acc + b2
+// with m = -|a| log2(e), t = 2^m (one MUFU per element) and ln(1 + t) = t q(t) on the FMA pipe (q: degree-5
+// fit on [0,1], |error| <= 1.5e-6).  bx: shared address of {b2[8]} ; xh: shared address of {x - 1/2 [8]}.
+struct FoldConsts { uint64_t c0, c1, c2, c3, c4, c5, khalf; };
+__device__ __forceinline__ FoldConsts fold_consts() {
+  FoldConsts k;                                   // negated: the fold subtracts ln(1 + t)
+  k.c0 = pk2(-0.9999016523361206f, -0.9999016523361206f);
+  k.c1 = pk2(0.49787506461143494f, 0.49787506461143494f);
+  k.c2 = pk2(-0.3176489472389221f, -0.3176489472389221f);
+  k.c3 = pk2(0.19376075267791748f, 0.19376075267791748f);
+  k.c4 = pk2(-0.08556976169347763f, -0.08556976169347763f);
+  k.c5 = pk2(0.01833880878984928f, 0.01833880878984928f);
+  k.khalf = pk2(0.34657359027997264f, 0.34657359027997264f);   // ln(2)/2: m * khalf = -|a|/2
+  return k;
+}
+__device__ __forceinline__ void fold8(const float (&v)[8], uint32_t bx, uint32_t xh, const FoldConsts& k, uint64_t& acc) {
+  uint64_t b[4], x[4];
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b[0]), "=l"(b[1]) : "r"(bx));
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b[2]), "=l"(b[3]) : "r"(bx + 16u));
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(x[0]), "=l"(x[1]) : "r"(xh));
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(x[2]), "=l"(x[3]) : "r"(xh + 16u));
 #pragma unroll
-  for (int j = 0; j < 8; j += 2) {
-    float b0, x0, b1, x1;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(x0), "=f"(b1), "=f"(x1) : "r"(xb + 8u * j));
-    const float a0 = v[j] + b0, a1 = v[j + 1] + b1;
-    // softplus(a) = max(a,0) + ln2 * log2(1 + 2^(-|a| log2 e))
-    float t0, t1, l0, l1;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fabsf(a0) * -1.4426950408889634f));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fabsf(a1) * -1.4426950408889634f));
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(1.0f + t0));
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(1.0f + t1));
-    rs0 += fmaf(x0, a0, -fmaf(l0, 0.6931471805599453f, fmaxf(a0, 0.f)));
-    rs1 += fmaf(x1, a1, -fmaf(l1, 0.6931471805599453f, fmaxf(a1, 0.f)));
+  for (int j = 0; j < 4; ++j) {
+    const uint64_t a2 = add2(pk2(v[2 * j], v[2 * j + 1]), b[j]);
+    float a0, a1, t0, t1;
+    upk2(a2, a0, a1);
+    const float m0 = fabsf(a0) * -1.4426950408889634f, m1 = fabsf(a1) * -1.4426950408889634f;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(m0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(m1));
+    const uint64_t t2 = pk2(t0, t1);
+    uint64_t q = fma2(t2, k.c5, k.c4);
+    q = fma2(q, t2, k.c3);
+    q = fma2(q, t2, k.c2);
+    q = fma2(q, t2, k.c1);
+    q = fma2(q, t2, k.c0);
+    acc = fma2(a2, x[j], acc);
+    acc = fma2(pk2(m0, m1), k.khalf, acc);
+    acc = fma2(t2, q, acc);
   }
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -106,34 +147,169 @@ __device__ __forceinline__ bool elect_one() {
 
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// The order in which one CTA consumes ring stages, shared by the TMA and the MMA warp.  A "pass" is the
+// ---- lean single-thread primitives on raw 32-bit shared addresses (the TMA and MMA issue loops are each ONE
+// thread on the critical path of the whole CTA: every instruction in them costs ~8 cycles of latency) ----
+__device__ __forceinline__ void bar_wait(uint32_t addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_%=;\n\t}"
+      ::"r"(addr), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void commit_to(uint32_t addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ uint64_t mk64(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+
+// The order in which one CTA consumes ring stages, shared by the TMA and the MMA thread.  A "pass" is the
 // hidden-layer GEMM [z|1].W1^T for 64 hidden units of a tile (-> one k block of its A tile); a "w2" item is one
 // k block of one output chunk.  The passes of tile i+1 are interleaved with the LAST output chunk of tile i:
 // that chunk is the final reader of tile i's A blocks, so block kb can be rewritten as soon as its MMAs retire
 // (a_free[kb]) and the conversion of tile i+1 hides behind the rest of the sweep.  Pass j >= MINI_BUFS re-uses
 // the TMEM buffer of pass j-MINI_BUFS, whose conversion needs a_free[j-MINI_BUFS]: it is issued two k blocks later.
-template <class FPass, class FW2>
-__device__ __forceinline__ void walk_items(const Params& p, int n_tiles, FPass&& pass, FW2&& w2) {
+// FIRST / LAST are compile-time so the common (middle) chunk loop carries no per-item conditions.
+template <bool FIRST, bool LAST, class R>
+__device__ __forceinline__ void walk_chunk(const Params& p, uint32_t ti, int c, bool has_next, R& r) {
+  r.chunk_begin();
+  if (!LAST && r.template chunk_static<FIRST>(ti, c)) {
+    // whole chunk issued by the unrolled fast path
+  } else if (LAST && has_next) {
+#pragma unroll 1
+    for (int kb = 0; kb < p.KB; ++kb) {
+      if (kb == 0) {
+        for (int j = 0; j < MINI_BUFS && j < p.KB; ++j) r.pass(ti + 1, j);
+      } else if (kb >= 2 && kb + 2 < p.KB) {
+        r.pass(ti + 1, kb + 2);
+      }
+      r.template w2<FIRST, LAST>(ti, c, kb);
+    }
+  } else {
+#pragma unroll 1
+    for (int kb = 0; kb < p.KB; ++kb) r.template w2<FIRST, LAST>(ti, c, kb);
+  }
+  r.chunk_end();
+}
+template <class R>
+__device__ __forceinline__ void walk_items(const Params& p, int n_tiles, R& r) {
   if ((int)blockIdx.x >= n_tiles) return;
-  for (int j = 0; j < p.KB; ++j) pass(0u, j);
+  for (int j = 0; j < p.KB; ++j) r.pass(0u, j);
+  const int last_c = p.n_chunks - 1;
   uint32_t ti = 0;
   for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++ti) {
     const bool has_next = t + (int)gridDim.x < n_tiles;
-    for (int c = 0; c < p.n_chunks; ++c) {
-      const bool last = c == p.n_chunks - 1;
-      for (int kb = 0; kb < p.KB; ++kb) {
-        if (last && has_next) {
-          if (kb == 0) {
-            for (int j = 0; j < MINI_BUFS && j < p.KB; ++j) pass(ti + 1, j);
-          } else if (kb >= 2 && kb + 2 < p.KB) {
-            pass(ti + 1, kb + 2);
-          }
-        }
-        w2(ti, c, kb, last);
-      }
-    }
+    if (last_c == 0) { walk_chunk<true, true>(p, ti, 0, has_next, r); continue; }
+    walk_chunk<true, false>(p, ti, 0, false, r);
+#pragma unroll 1
+    for (int c = 1; c < last_c; ++c) walk_chunk<false, false>(p, ti, c, false, r);
+    walk_chunk<false, true>(p, ti, last_c, has_next, r);
   }
 }
+
+// barrier addresses (32-bit shared) used by the two issuing threads
+struct BarAddrs {
+  uint32_t b_full, b_empty, z_full, z_empty, mini_full, mini_empty, a_ready, a_free, acc_full, acc_empty;
+};
+
+struct TmaIssuer {
+  const CUtensorMap* map_w2; const CUtensorMap* map_w1;
+  BarAddrs bar;
+  uint32_t ring;                 // shared address of the ring
+  uint32_t w2_bytes; int NC;
+  uint32_t stage = 0, parity = 0;
+  __device__ __forceinline__ void load(const CUtensorMap* m, uint32_t bytes, int c0, int c1) {
+    const uint32_t full = bar.b_full + 8u * stage;
+    bar_wait(bar.b_empty + 8u * stage, parity ^ 1u);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(ring + stage * (uint32_t)B_STAGE), "l"(m), "r"(full), "r"(c0), "r"(c1)
+        : "memory");
+    if (++stage == STAGES) { stage = 0; parity ^= 1u; }
+  }
+  __device__ __forceinline__ void chunk_begin() {}
+  __device__ __forceinline__ void chunk_end() {}
+  template <bool FIRST>
+  __device__ __forceinline__ bool chunk_static(uint32_t, int) { return false; }
+  __device__ __forceinline__ void pass(uint32_t, int j) { load(map_w1, (uint32_t)MINI_N * 128u, 0, j * MINI_N); }
+  template <bool FIRST, bool LAST>
+  __device__ __forceinline__ void w2(uint32_t, int c, int kb) { load(map_w2, w2_bytes, kb * BK, c * NC); }
+};
+
+struct MmaIssuer {
+  BarAddrs bar;
+  uint32_t tmem_base, a_lo0, b_lo0, z_lo0, idesc, idesc_mini;
+  int KB, zk;
+  uint32_t stage = 0, parity = 0, acc_it = 0, mini_it = 0, d_acc = 0;
+  __device__ __forceinline__ void advance() { if (++stage == STAGES) { stage = 0; parity ^= 1u; } }
+  __device__ __forceinline__ void chunk_begin() {
+    const uint32_t buf = acc_it & 1u;
+    bar_wait(bar.acc_empty + 8u * buf, ((acc_it >> 1) & 1u) ^ 1u);
+    tc::tc_fence_after();
+    d_acc = tmem_base + buf * ACC_STRIDE;
+  }
+  __device__ __forceinline__ void chunk_end() {
+    commit_to(bar.acc_full + 8u * (acc_it & 1u));
+    ++acc_it;
+  }
+  __device__ __forceinline__ void pass(uint32_t tseq, int j) {
+    if (j == 0) bar_wait(bar.z_full, tseq & 1u);
+    const uint32_t mb = mini_it & (MINI_BUFS - 1);
+    bar_wait(bar.b_full + 8u * stage, parity);
+    bar_wait(bar.mini_empty + 8u * mb, ((mini_it / MINI_BUFS) & 1u) ^ 1u);
+    tc::tc_fence_after();
+    const uint32_t d = tmem_base + MINI_COL0 + mb * MINI_N;
+    const uint32_t b_lo = b_lo0 + stage * (uint32_t)(B_STAGE >> 4);
+    for (int k = 0; k < zk; ++k)
+      tc::umma_bf16(d, mk64(z_lo0 + 2u * k, DESC_HI), mk64(b_lo + 2u * k, DESC_HI), idesc_mini, k ? 1u : 0u);
+    commit_to(bar.b_empty + 8u * stage);
+    commit_to(bar.mini_full + 8u * mb);
+    if (j == KB - 1) commit_to(bar.z_empty);
+    advance();
+    ++mini_it;
+  }
+  // A whole chunk, fully unrolled, for the common case KB == 8 with the ring at stage 0 (8 items per chunk
+  // and 8 passes per tile keep it there): every descriptor / barrier address is base + constant.
+  template <bool FIRST>
+  __device__ __forceinline__ bool chunk_static(uint32_t tseq, int) {
+    if (KB != 8 || stage != 0) return false;
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+      constexpr int dummy = 0; (void)dummy;
+      const uint32_t st = (uint32_t)(kb & (STAGES - 1));
+      if (FIRST) bar_wait(bar.a_ready + 8u * kb, tseq & 1u);
+      bar_wait(bar.b_full + 8u * st, parity ^ (uint32_t)(kb / STAGES));
+      tc::tc_fence_after();
+      const uint32_t a_lo = a_lo0 + (uint32_t)kb * (uint32_t)(A_BLOCK >> 4);
+      const uint32_t b_lo = b_lo0 + st * (uint32_t)(B_STAGE >> 4);
+#pragma unroll
+      for (int k = 0; k < BK / 16; ++k)
+        tc::umma_bf16(d_acc, mk64(a_lo + 2u * k, DESC_HI), mk64(b_lo + 2u * k, DESC_HI), idesc, (kb | k) != 0 ? 1u : 0u);
+      commit_to(bar.b_empty + 8u * st);
+    }
+    return true;                                   // 8 items = two trips round the 4-stage ring: stage, parity unchanged
+  }
+  template <bool FIRST, bool LAST>
+  __device__ __forceinline__ void w2(uint32_t tseq, int, int kb) {
+    if (FIRST) bar_wait(bar.a_ready + 8u * kb, tseq & 1u);
+    bar_wait(bar.b_full + 8u * stage, parity);
+    tc::tc_fence_after();
+    const uint32_t a_lo = a_lo0 + (uint32_t)kb * (uint32_t)(A_BLOCK >> 4);
+    const uint32_t b_lo = b_lo0 + stage * (uint32_t)(B_STAGE >> 4);
+#pragma unroll
+    for (int k = 0; k < BK / 16; ++k)
+      tc::umma_bf16(d_acc, mk64(a_lo + 2u * k, DESC_HI), mk64(b_lo + 2u * k, DESC_HI), idesc, (kb | k) != 0 ? 1u : 0u);
+    commit_to(bar.b_empty + 8u * stage);
+    if (LAST) commit_to(bar.a_free + 8u * kb);
+    advance();
+  }
+};
 
 // Roles (640 threads): warp 0 TMA, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 producers
 // (z generation + TMEM -> tanh -> bf16 A tile conversion), warps 12-19 epilogue.
@@ -155,7 +331,8 @@ is_tc_kernel(const __grid_constant__ CUtensorMap map_w2, const __grid_constant__
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
   float* auxp = (float*)(smem + Smem::AUXP);
   float* aux_s = (float*)(smem + Smem::AUX);
-  float2* xb = (float2*)(smem + Smem::XB);
+  float* bb_s = (float*)(smem + Smem::XB);         // b2, padded with -30
+  float* xh_s = bb_s + DMAX;                       // x - 1/2 of the tile's test point, padded with -1/2
   float* rowsum_s = (float*)(smem + Smem::ROWSUM);
   float* red_s = (float*)(smem + Smem::RED);
 
@@ -174,8 +351,9 @@ is_tc_kernel(const __grid_constant__ CUtensorMap map_w2, const __grid_constant__
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc(tmem_slot, TMEM_COLS);
-  // columns past D: b2 = -1e30 and x = 0 make x*a - softplus(a) exactly 0 (no per-element bounds test)
-  for (int i = threadIdx.x; i < DMAX; i += THREADS) xb[i] = make_float2(i < p.D ? p.b2[i] : -1e30f, 0.f);
+  // columns past D: a = -30 (the W2^T rows are zero-filled), x - 1/2 = -1/2: a (x - 1/2) - |a|/2 = 15 - 15 and
+  // ln(1 + e^-30) ~ 1e-13, so padding contributes nothing (no per-element bounds test)
+  for (int i = threadIdx.x; i < DMAX; i += THREADS) { bb_s[i] = i < p.D ? p.b2[i] : -30.f; xh_s[i] = -0.5f; }
   for (int i = threadIdx.x; i < BM * 128 / 16; i += THREADS)          // [z|1] tile: k >= 24 stays zero
     reinterpret_cast<uint4*>(smem + Smem::ZB)[i] = make_uint4(0u, 0u, 0u, 0u);
   tc::fence_proxy_async();
@@ -184,74 +362,36 @@ is_tc_kernel(const __grid_constant__ CUtensorMap map_w2, const __grid_constant__
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  BarAddrs ba;
+  ba.b_full = tc::smem_u32(b_full); ba.b_empty = tc::smem_u32(b_empty);
+  ba.z_full = tc::smem_u32(z_full); ba.z_empty = tc::smem_u32(z_empty);
+  ba.mini_full = tc::smem_u32(mini_full); ba.mini_empty = tc::smem_u32(mini_empty);
+  ba.a_ready = tc::smem_u32(a_ready); ba.a_free = tc::smem_u32(a_free);
+  ba.acc_full = tc::smem_u32(acc_full); ba.acc_empty = tc::smem_u32(acc_empty);
+
   if (warp == 0) {
     // ===== TMA: W1^T boxes of the passes and W2^T boxes of the sweep, in walk_items order =====
     if (elect_one()) {
-      uint32_t it = 0;
-      const uint32_t w2_bytes = (uint32_t)p.NC * 128u;
-      auto acquire = [&]() -> int {
-        const int s = it % STAGES;
-        tc::mbar_wait(&b_empty[s], ((it / STAGES) & 1) ^ 1);
-        ++it;
-        return s;
-      };
-      walk_items(p, n_tiles,
-        [&](uint32_t, int j) {
-          const int s = acquire();
-          tc::mbar_expect_tx(&b_full[s], (uint32_t)MINI_N * 128u);
-          tc::tma_load_2d(smem + Smem::B + s * B_STAGE, &map_w1, &b_full[s], 0, j * MINI_N);
-        },
-        [&](uint32_t, int c, int kb, bool) {
-          const int s = acquire();
-          tc::mbar_expect_tx(&b_full[s], w2_bytes);
-          tc::tma_load_2d(smem + Smem::B + s * B_STAGE, &map_w2, &b_full[s], kb * BK, c * p.NC);
-        });
+      TmaIssuer r;
+      r.map_w2 = &map_w2; r.map_w1 = &map_w1; r.bar = ba;
+      r.ring = tc::smem_u32(smem + Smem::B);
+      r.w2_bytes = (uint32_t)p.NC * 128u; r.NC = p.NC;
+      walk_items(p, n_tiles, r);
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===== MMA issuer: ONE elected lane runs the whole loop (its state stays on the uniform datapath) =====
+    // ===== MMA issuer: ONE elected lane runs the whole loop =====
     if (elect_one()) {
-      uint32_t it = 0, acc_it = 0, mini_it = 0;
-      const uint64_t a_desc0 = tc::desc_kmajor(tc::smem_u32(smem + Smem::A), 0);
-      const uint64_t b_desc0 = tc::desc_kmajor(tc::smem_u32(smem + Smem::B), 0);
-      const uint64_t z_desc0 = tc::desc_kmajor(tc::smem_u32(smem + Smem::ZB), 0);
-      const uint32_t idesc_mini = tc::make_idesc_bf16(BM, MINI_N, 0, 0);
-      const uint32_t idesc = tc::make_idesc_bf16(BM, p.NC, 0, 0);
-      walk_items(p, n_tiles,
-        [&](uint32_t tseq, int j) {
-          if (j == 0) tc::mbar_wait(z_full, tseq & 1);
-          const int s = it % STAGES;
-          const uint32_t mb = mini_it % MINI_BUFS;
-          tc::mbar_wait(&b_full[s], (it / STAGES) & 1);
-          tc::mbar_wait(&mini_empty[mb], ((mini_it / MINI_BUFS) & 1) ^ 1);
-          tc::tc_fence_after();
-          const uint32_t d = tmem_base + MINI_COL0 + mb * MINI_N;
-          const uint64_t b = b_desc0 + (uint64_t)(s * (B_STAGE >> 4));
-          for (int k = 0; k < p.zk; ++k)
-            tc::umma_bf16(d, z_desc0 + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc_mini, k ? 1u : 0u);
-          tc::umma_commit(&b_empty[s]);
-          tc::umma_commit(&mini_full[mb]);
-          if (j == p.KB - 1) tc::umma_commit(z_empty);
-          ++it; ++mini_it;
-        },
-        [&](uint32_t tseq, int c, int kb, bool last) {
-          const uint32_t buf = acc_it & 1;
-          if (kb == 0) tc::mbar_wait(&acc_empty[buf], ((acc_it >> 1) & 1) ^ 1);
-          if (c == 0) tc::mbar_wait(&a_ready[kb], tseq & 1);
-          const int s = it % STAGES;
-          tc::mbar_wait(&b_full[s], (it / STAGES) & 1);
-          tc::tc_fence_after();
-          const uint32_t d = tmem_base + buf * ACC_STRIDE;
-          const uint64_t a = a_desc0 + (uint64_t)(kb * (A_BLOCK >> 4));
-          const uint64_t b = b_desc0 + (uint64_t)(s * (B_STAGE >> 4));
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            tc::umma_bf16(d, a + (uint64_t)(2 * k), b + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          tc::umma_commit(&b_empty[s]);
-          if (last) tc::umma_commit(&a_free[kb]);
-          if (kb == p.KB - 1) { tc::umma_commit(&acc_full[buf]); ++acc_it; }
-          ++it;
-        });
+      MmaIssuer r;
+      r.bar = ba;
+      r.tmem_base = tmem_base;
+      r.a_lo0 = (tc::smem_u32(smem + Smem::A) >> 4) | (1u << 16);       // LBO field = 1 (unused for SW128 K-major)
+      r.b_lo0 = (tc::smem_u32(smem + Smem::B) >> 4) | (1u << 16);
+      r.z_lo0 = (tc::smem_u32(smem + Smem::ZB) >> 4) | (1u << 16);
+      r.idesc = tc::make_idesc_bf16(BM, p.NC, 0, 0);
+      r.idesc_mini = tc::make_idesc_bf16(BM, MINI_N, 0, 0);
+      r.KB = p.KB; r.zk = p.zk;
+      walk_items(p, n_tiles, r);
     }
     __syncwarp();
   } else if (warp >= 4 && warp < 4 + PROD_WARPS) {
@@ -345,19 +485,21 @@ is_tc_kernel(const __grid_constant__ CUtensorMap map_w2, const __grid_constant__
     const int et = threadIdx.x - (4 + PROD_WARPS) * 32;                // [0, 256)
     const int row = q * 32 + lane;
     const int half = p.NC >> 1, n8 = half >> 3, c_lo = ch * half;      // NC is a multiple of 16
-    const uint32_t xb_addr = tc::smem_u32(xb);
+    const uint32_t bb_addr = tc::smem_u32(bb_s), xh_addr = tc::smem_u32(xh_s);
+    const FoldConsts fk = fold_consts();
     uint32_t acc_it = 0, tile_it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
       const int pi = t / p.tiles_per_point, l0 = (t - pi * p.tiles_per_point) * BM;
-      for (int i = et; i < p.D; i += EPI_WARPS * 32) xb[i].y = p.x[(size_t)pi * p.D + i];
+      for (int i = et; i < p.D; i += EPI_WARPS * 32) xh_s[i] = p.x[(size_t)pi * p.D + i] - 0.5f;
       named_bar(2, EPI_WARPS * 32);
-      float rs0 = 0.f, rs1 = 0.f;
+      uint64_t acc = 0ull;                                             // two fp32 partial sums (even / odd columns)
       for (int c = 0; c < p.n_chunks; ++c, ++acc_it) {
         const uint32_t buf = acc_it & 1;
         tc::mbar_wait(&acc_full[buf], (acc_it >> 1) & 1);
         tc::tc_fence_after();
         const uint32_t taddr = tmem_base + buf * ACC_STRIDE + (uint32_t)c_lo + ((uint32_t)(q * 32) << 16);
-        const uint32_t xa = xb_addr + (uint32_t)(c * p.NC + c_lo) * 8u;
+        const uint32_t col4 = (uint32_t)(c * p.NC + c_lo) * 4u;
+        const uint32_t ba = bb_addr + col4, xa = xh_addr + col4;
         // this warp's half of the chunk, 8 columns per TMEM load; the next load is in flight while the
         // current 8 columns are folded
         float va[8], vb[8];
@@ -365,17 +507,19 @@ is_tc_kernel(const __grid_constant__ CUtensorMap map_w2, const __grid_constant__
         for (int i = 0; i < n8; i += 2) {
           tc::tmem_ld_wait();
           if (i + 1 < n8) tmem_ld8(taddr + 8u * (i + 1), vb);
-          fold8(va, xa + 64u * i, rs0, rs1);
+          fold8(va, ba + 32u * i, xa + 32u * i, fk, acc);
           if (i + 1 < n8) {
             tc::tmem_ld_wait();
             if (i + 2 < n8) tmem_ld8(taddr + 8u * (i + 2), va);
-            fold8(vb, xa + 64u * (i + 1), rs0, rs1);
+            fold8(vb, ba + 32u * (i + 1), xa + 32u * (i + 1), fk, acc);
           }
         }
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
       }
+      float rs0, rs1;
+      upk2(acc, rs0, rs1);
       const float rs = rs0 + rs1;
       rowsum_s[ch * BM + row] = rs;
       named_bar(2, EPI_WARPS * 32);
