@@ -112,6 +112,18 @@ int vaeb_update(vaeb_handle* h, int64_t index, const float* eps, float* elbo_out
  * end-to-end path: H2D copy of the inputs + D2H of the result inside the call). */
 int vaeb_update_host(vaeb_handle* h, const float* x, int64_t rows, const float* eps, float* elbo_out);
 
+/* Streaming form of vaeb_update_host for a host-side data loader feeding train_model's loop
+ * (VAEB.py:577-579): enqueue one update on the minibatch x[rows,D] in PINNED host memory and return at
+ * once.  The H2D copy runs on a copy stream into a ring of staging buffers and overlaps the previous
+ * update's kernel; the update's bound is copied back D2H (4 bytes, asynchronously) as soon as its kernel
+ * ends.  The caller must not modify x until vaeb_collect returns.  Philox eps only. */
+int vaeb_update_host_async(vaeb_handle* h, const float* x, int64_t rows);
+
+/* Waits for every update enqueued by vaeb_update_host_async since the last collect and writes their
+ * SGVB/M values, in submission order, to elbo_out[0..n) where n = *n_inout on return
+ * (*n_inout on entry = capacity of elbo_out; VAEB_EARG if smaller than the number outstanding). */
+int vaeb_collect(vaeb_handle* h, int32_t* n_inout, float* elbo_out);
+
 /* The inner loop of train_model (VAEB.py:577-579) as ONE call: `n` updates in the order
  * `batch_order[0..n)` with no host synchronisation between them; elbo_out[n] receives each
  * step's SGVB/M.  Philox eps only. */

@@ -290,6 +290,36 @@ def test_update_host_equals_resident_update():
     m1.close(); m2.close()
 
 
+def test_update_host_async_stream_equals_synchronous_updates():
+    """vaeb_update_host_async + vaeb_collect: the pipelined host-input path (copy stream, staging ring,
+    deferred readback) must give exactly the bounds and parameters of the synchronous calls."""
+    x = O.synthetic_mnist(1100)
+    params = _rand_params(784, 500, 20, False, 3, 0.05)
+    m1 = _model(x[:100], False, 500, 20, 100, 1, "LB", params)
+    m2 = _model(x[:100], False, 500, 20, 100, 1, "LB", params)
+    order = [3, 1, 4, 0, 2, 9, 7, 8, 6, 5, 10]               # more steps than staging buffers
+    a = np.array([float(m1.update_host(x[100 * i:100 * i + 100])) for i in order], np.float32)
+    for i in order[:6]:
+        m2.update_host_async(x[100 * i:100 * i + 100])
+    b = list(m2.collect())
+    for i in order[6:]:
+        m2.update_host_async(x[100 * i:100 * i + 100])
+    b += list(m2.collect())
+    np.testing.assert_array_equal(a, np.array(b, np.float32))
+    assert len(m2.collect()) == 0
+    for p, q in zip(m1.get_params(), m2.get_params()):
+        np.testing.assert_array_equal(p, q)
+    # a non-fused configuration (L = 2) takes the per-layer path behind the same calls
+    m3 = _model(x[:100], False, 500, 20, 100, 2, "LB", params)
+    m4 = _model(x[:100], False, 500, 20, 100, 2, "LB", params)
+    c = np.array([float(m3.update_host(x[100 * i:100 * i + 100])) for i in order[:5]], np.float32)
+    for i in order[:5]:
+        m4.update_host_async(x[100 * i:100 * i + 100])
+    np.testing.assert_array_equal(c, m4.collect())
+    for m in (m1, m2, m3, m4):
+        m.close()
+
+
 # ---- importance-sampled log p(x) ------------------------------------------------------------
 def test_is_logpx_golden_and_oracle():
     g = load_golden("golden_frey_z2.npz")

@@ -41,6 +41,8 @@ EXPORTS = {
     "vaeb_update": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_float)]),
     "vaeb_update_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_float)]),
     "vaeb_update_many": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vaeb_update_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "vaeb_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "vaeb_validate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
     "vaeb_gradients": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                  C.POINTER(C.c_float), C.c_void_p]),

@@ -410,7 +410,7 @@ int read_scalars(vaeb_handle* h, int n, float* out) {
 
 // n updates through the fused single-launch kernel (fused_step.cu); scalars land in d_scalars[0..n)
 int fused_updates(vaeb_handle* h, const int32_t* batch_order, const float* d_xrows, int rows, int n,
-                  const float* d_eps) {
+                  const float* d_eps, int slot0 = 0) {
   VAEB_TRY(ensure_ws(h, rows, rows, true));
   const int* d_order = nullptr;
   if (batch_order) {
@@ -425,7 +425,7 @@ int fused_updates(vaeb_handle* h, const int32_t* batch_order, const float* d_xro
     VAEB_CUDA(cudaMemcpyAsync(f.d_order, batch_order, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     d_order = f.d_order;
   }
-  return fused_step_launch(h, d_order, d_xrows, rows, n, d_eps, 0, nullptr);
+  return fused_step_launch(h, d_order, d_xrows, rows, n, d_eps, slot0, nullptr);
 }
 
 float* flat_by_which(vaeb_handle* h, int which) {
@@ -544,6 +544,16 @@ int vaeb_destroy(vaeb_handle* h) {
   }
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->copy_stream) {
+    cudaStreamSynchronize(h->copy_stream);
+    for (int i = 0; i < vaeb_handle::ASYNC_BUFS; ++i) {
+      if (h->a_stage[i]) cudaFree(h->a_stage[i]);
+      cudaEventDestroy(h->a_copied[i]);
+      cudaEventDestroy(h->a_consumed[i]);
+    }
+    if (h->h_async) cudaFreeHost(h->h_async);
+    cudaStreamDestroy(h->copy_stream);
+  }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return VAEB_OK;
@@ -665,6 +675,66 @@ int vaeb_update_host(vaeb_handle* h, const float* x, int64_t rows, const float* 
   else
     VAEB_TRY(enqueue_update(h, h->d_stage, (int)rows, d_eps, nullptr, 0, true));
   return read_scalars(h, 1, elbo_out);
+}
+
+int vaeb_update_host_async(vaeb_handle* h, const float* x, int64_t rows) {
+  VAEB_REQUIRE(h && x && rows > 0, "null argument");
+  VAEB_REQUIRE(h->world == 1, "the streaming update is single-GPU (use vaeb_update for data-parallel steps)");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  constexpr int NB = vaeb_handle::ASYNC_BUFS;
+  constexpr int MAX_OUT = 8192;
+  const int64_t n = rows * h->D;
+  if (!h->copy_stream) {
+    VAEB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < NB; ++i) {
+      VAEB_CUDA(cudaEventCreateWithFlags(&h->a_copied[i], cudaEventDisableTiming));
+      VAEB_CUDA(cudaEventCreateWithFlags(&h->a_consumed[i], cudaEventDisableTiming));
+    }
+    VAEB_CUDA(cudaMallocHost((void**)&h->h_async, (size_t)MAX_OUT * sizeof(float)));
+    h->h_async_cap = MAX_OUT;
+  }
+  VAEB_REQUIRE(h->a_outstanding < h->h_async_cap, "too many uncollected updates: call vaeb_collect");
+  if (n > h->a_stage_cap) {
+    VAEB_CUDA(cudaStreamSynchronize(h->copy_stream));
+    VAEB_CUDA(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < NB; ++i) {
+      if (h->a_stage[i]) VAEB_CUDA(cudaFree(h->a_stage[i]));
+      h->a_stage[i] = nullptr;
+      VAEB_CUDA(cudaMalloc((void**)&h->a_stage[i], (size_t)n * sizeof(float)));
+      h->a_used[i] = false;
+    }
+    h->a_stage_cap = n;
+  }
+  VAEB_TRY(ensure_scalars(h, h->h_async_cap));
+  const int b = (int)(h->a_submitted % NB);
+  const int slot = h->a_outstanding;
+  // copy stream: wait until the kernel that last read this staging buffer is done, then H2D
+  if (h->a_used[b]) VAEB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->a_consumed[b], 0));
+  VAEB_CUDA(cudaMemcpyAsync(h->a_stage[b], x, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+  VAEB_CUDA(cudaEventRecord(h->a_copied[b], h->copy_stream));
+  // compute stream: the update, then the 4-byte readback of its bound
+  VAEB_CUDA(cudaStreamWaitEvent(h->stream, h->a_copied[b], 0));
+  if (fused_step_supported(h, (int)rows))
+    VAEB_TRY(fused_updates(h, nullptr, h->a_stage[b], (int)rows, 1, nullptr, slot));
+  else
+    VAEB_TRY(enqueue_update(h, h->a_stage[b], (int)rows, nullptr, nullptr, slot, true));
+  VAEB_CUDA(cudaEventRecord(h->a_consumed[b], h->stream));
+  VAEB_CUDA(cudaMemcpyAsync(h->h_async + slot, h->d_scalars + slot, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  h->a_used[b] = true;
+  ++h->a_submitted;
+  ++h->a_outstanding;
+  return VAEB_OK;
+}
+
+int vaeb_collect(vaeb_handle* h, int32_t* n_inout, float* elbo_out) {
+  VAEB_REQUIRE(h && n_inout && elbo_out, "null argument");
+  VAEB_REQUIRE(*n_inout >= h->a_outstanding, "elbo_out is smaller than the number of outstanding updates");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  VAEB_CUDA(cudaStreamSynchronize(h->stream));
+  std::memcpy(elbo_out, h->h_async, (size_t)h->a_outstanding * sizeof(float));
+  *n_inout = h->a_outstanding;
+  h->a_outstanding = 0;
+  return VAEB_OK;
 }
 
 int vaeb_update_many(vaeb_handle* h, const int32_t* batch_order, int32_t n, float* elbo_out) {

@@ -118,6 +118,14 @@ struct vaeb_handle {
   float* d_x = nullptr; int64_t n_data = 0;
   Workspace ws;
   float* d_stage = nullptr; int64_t stage_cap = 0;       // device staging for host inputs
+  // streaming host-input updates (vaeb_update_host_async): copy stream + ring of staging buffers
+  static constexpr int ASYNC_BUFS = 4;
+  cudaStream_t copy_stream = nullptr;
+  float* a_stage[ASYNC_BUFS] = {nullptr, nullptr, nullptr, nullptr}; int64_t a_stage_cap = 0;
+  cudaEvent_t a_copied[ASYNC_BUFS] = {}, a_consumed[ASYNC_BUFS] = {};
+  bool a_used[ASYNC_BUFS] = {false, false, false, false};
+  int64_t a_submitted = 0; int a_outstanding = 0;
+  float* h_async = nullptr; int h_async_cap = 0;          // pinned host landing zone of the bounds
   float* d_stage2 = nullptr; int64_t stage2_cap = 0;     // eps staging
   float* d_out = nullptr; int64_t out_cap = 0;           // device staging for outputs
   float* d_scalars = nullptr; float* h_scalars = nullptr; int scalars_cap = 0;

@@ -105,6 +105,7 @@ class VAEB(object):
         self._estimator = est
         self._fvb = est in (_lib.EST_FVB, _lib.EST_FVB_SAMPLED)
 
+        self._async_keep = []
         self.srng = RandomStreams(seed=10)              # VAEB.py:158
         self._eps_nodes = [self.srng.new_node() for _ in range(L)]
 
@@ -221,6 +222,26 @@ class VAEB(object):
         out = C.c_float()
         _lib.check(self._lib.vaeb_update_host(self._h, _ptr(xa), xa.shape[0], _ptr(ea), C.byref(out)))
         return np.asarray(out.value, dtype=np.float32)
+
+    def update_host_async(self, x_batch):
+        """Streaming form of update_host: enqueue one update on a minibatch in PINNED host memory and
+        return at once (its H2D copy overlaps the previous update's kernel).  Collect the bounds with
+        `collect()`; do not modify x_batch before that.  Philox noise only."""
+        if self.eps_mode == "theano":
+            raise ValueError("update_host_async draws its noise on the device (eps_mode='philox')")
+        xa = x_batch if (isinstance(x_batch, np.ndarray) and x_batch.dtype == np.float32 and
+                         x_batch.flags["C_CONTIGUOUS"]) else _f32(x_batch)
+        self._async_keep.append(xa)
+        _lib.check(self._lib.vaeb_update_host_async(self._h, xa.ctypes.data, xa.shape[0]))
+
+    def collect(self):
+        """Bounds (SGVB / batch_size, pre-update parameters) of every update enqueued by
+        update_host_async since the last collect, in submission order."""
+        n = C.c_int32(8192)
+        out = np.empty(8192, np.float32)
+        _lib.check(self._lib.vaeb_collect(self._h, C.byref(n), _ptr(out)))
+        self._async_keep = []
+        return out[:n.value].copy()
 
     def update_many(self, batch_order):
         """The inner loop of train_model (VAEB.py:577-579) in one call; Philox noise only."""
