@@ -78,6 +78,42 @@ def test_tc_step_large_batch_bf16x3():
     _check(x, 500, 20, 1152, 1, "LB", _rand_params(784, 500, 20, 4, 0.05), "bf16x3", 24, idx=1)
 
 
+@pytest.mark.parametrize("precision,est,Z,M", [("fp32", "LA", 10, 1100), ("fp32", "LB", 20, 1024), ("fp32", "LB", 3, 1030),
+                                              ("bf16x3", "LA", 20, 1280), ("bf16", "LB", 2, 1152)])
+def test_large_batch_latent_kernels(precision, est, Z, M):
+    """rows >= 1024 switches the latent layers (enc2 + reparam + dec1, their backward, the thin weight
+    gradients) to the 64-row tilings of kernels_latent.cu: ragged row counts, both estimators, Z in {2,3,10,20}."""
+    import vaeb_b200
+    x = O.synthetic_mnist(2 * M)
+    params = _rand_params(784, 500, Z, 5, 0.05)
+    rng = np.random.RandomState(31)
+    eps = rng.normal(size=(1, M, Z)).astype(np.float32)
+    m = vaeb_b200.VAEB(x, False, 500, Z, M, 1, 0.01, est == "LA", False, params, precision=precision)
+    o = O.OracleVAEB(x, False, 500, Z, M, L=1, estimator=est, params=params, dtype=np.float64)
+    sg_ref, rows_ref, g_ref = o.grads(x[M:2 * M], eps)
+    sg, rows, g = m.gradients(index=1, eps=eps)
+    tol, gtol, floor = (1e-2, 3e-2, 1.0) if precision == "bf16" else (1e-4, 1e-4, 0.1)
+    assert sg == pytest.approx(sg_ref, rel=tol)
+    np.testing.assert_allclose(rows, rows_ref, rtol=tol)
+    for a, b, n in zip(g, g_ref, O.param_names(False)):
+        assert_close_tensor(a, b, gtol, floor=floor, name="grad " + n)
+    m.close()
+
+
+def test_large_batch_philox_rows_match_small_batch_rows():
+    """Philox eps is keyed by the row: the first rows of a 1152-row minibatch (64-row tilings) get the same
+    noise, hence the same per-row bound, as the same rows in a 384-row minibatch (small-batch kernels)."""
+    import vaeb_b200
+    x = O.synthetic_mnist(1152)
+    params = _rand_params(784, 500, 20, 6, 0.05)
+    big = vaeb_b200.VAEB(x, False, 500, 20, 1152, 1, 0.01, False, False, params)
+    small = vaeb_b200.VAEB(x[:384], False, 500, 20, 384, 1, 0.01, False, False, params)
+    _, rows_b, _ = big.gradients(index=0)
+    _, rows_s, _ = small.gradients(index=0)
+    np.testing.assert_allclose(rows_b[:384], rows_s, rtol=2e-5)
+    big.close(); small.close()
+
+
 def test_tc_training_tracks_fp32_training():
     import vaeb_b200
     x = O.synthetic_mnist(1000)
