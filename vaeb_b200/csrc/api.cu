@@ -156,6 +156,7 @@ int tc_ensure(vaeb_handle* h, int64_t rows, int64_t R) {
     VAEB_TRY(grow_bytes(&b.w2h, (size_t)H * b.ldd * 2));
     VAEB_CUDA(cudaMemsetAsync(b.w3h, 0, (size_t)D * b.ldh * 2, h->stream));
     VAEB_CUDA(cudaMemsetAsync(b.w2h, 0, (size_t)H * b.ldd * 2, h->stream));
+    VAEB_TRY(grow_bytes((void**)&b.wg_scratch, tc_wgrad_scratch_elems(D, H) * sizeof(float)));
     if (lo) {
       VAEB_TRY(grow_bytes(&b.w3l, (size_t)D * b.ldh * 2));
       VAEB_TRY(grow_bytes(&b.w2l, (size_t)H * b.ldd * 2));
@@ -288,7 +289,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   // backward (T.grad, VAEB.py:397); formulas in SURVEY.md 8a
   if (tcp) {
     PH("wgrad W2,b2 [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dH + dR * dD) + 4 * dH * dD,
-       tc_wgrad2(st, lc, t.maps, t.ns, bn, R, H, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2)));
+       tc_wgrad2(st, lc, t.maps, t.ns, bn, R, H, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2), tb.wg_scratch));
     PH("dgrad h_d (.W2^T)*(1-h^2) [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dD + dH * dD) + 8 * dR * dH,
        tc_dgrad_hd(st, lc, t.maps, t.ns, bn, R, D, H, s.h_d, s.da1));
   } else {
@@ -314,7 +315,8 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
                         T_(h, grads, l.ib5), s.wg_scratch));
   if (tcp)
     PH("wgrad W3,b3 [tcgen05]", 2 * dr * dD * dH, 2.0 * t.ns * (dr * dD + dr * dH) + 4 * dD * dH,
-       tc_wgrad3(st, lc, t.maps, t.ns, bn, rows, D, H, x_row_off, T_(h, grads, l.iW3), T_(h, grads, l.ib3)));
+       tc_wgrad3(st, lc, t.maps, t.ns, bn, rows, D, H, x_row_off, T_(h, grads, l.iW3), T_(h, grads, l.ib3),
+                 tb.wg_scratch));
   else
     PH("wgrad W3,b3", 2 * dr * dD * dH, 4 * (dr * dD + dr * dH + dD * dH),
        launch_wgrad(st, lc, x, rows, D, s.da3, H, T_(h, grads, l.iW3), T_(h, grads, l.ib3)));
@@ -539,7 +541,7 @@ int vaeb_destroy(vaeb_handle* h) {
   }
   {
     TcBuffers& b = h->tc.data;
-    void* tb[] = {b.xh, b.xl, b.w3h, b.w3l, b.w2h, b.w2l, b.hdh, b.hdl, b.da2h, b.da2l, b.da3h, b.da3l, h->tc.xsh, h->tc.xsl};
+    void* tb[] = {b.xh, b.xl, b.w3h, b.w3l, b.w2h, b.w2l, b.hdh, b.hdl, b.da2h, b.da2l, b.da3h, b.da3l, h->tc.xsh, h->tc.xsl, b.wg_scratch};
     for (void* q : tb) if (q) cudaFree(q);
   }
   if (h->h_scalars) cudaFreeHost(h->h_scalars);

@@ -439,18 +439,28 @@ lb_latent_fwd_kernel(const float* __restrict__ h_e, int rows, int H, const float
 #pragma unroll
   for (int i = 0; i < 12; ++i) acc[i] = 0.f;
   for (int i = t; i < LB_ROWS * LB_ZP; i += LB_T) (&zs[0][0])[i] = 0.f;
-  for (int k0 = 0; k0 < H; k0 += LB_KC) {
+  // operand chunks go global -> registers -> shared; the loads of chunk k+1 are in flight while chunk k is contracted
+  float hreg[LB_ROWS * LB_KC / LB_T], wreg[LB_KC * LB_NC / LB_T];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < LB_ROWS * LB_KC / LB_T; ++i) {
       const int rr = (t >> 5) + 8 * i, kk = t & 31;
-      hs[rr][kk] = (m0 + rr < rows && k0 + kk < H) ? h_e[(size_t)(m0 + rr) * H + k0 + kk] : 0.f;
+      hreg[i] = (m0 + rr < rows && k0 + kk < H) ? h_e[(size_t)(m0 + rr) * H + k0 + kk] : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < LB_KC * LB_NC / LB_T; ++i) {
       const int e = t + LB_T * i, kk = e & 31, c = e >> 5;
-      ws[kk][c] = (c < Z2 && k0 + kk < H) ? w45t[(size_t)c * H + k0 + kk] : 0.f;
+      wreg[i] = (c < Z2 && k0 + kk < H) ? w45t[(size_t)c * H + k0 + kk] : 0.f;
     }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < H; k0 += LB_KC) {
+#pragma unroll
+    for (int i = 0; i < LB_ROWS * LB_KC / LB_T; ++i) hs[(t >> 5) + 8 * i][t & 31] = hreg[i];
+#pragma unroll
+    for (int i = 0; i < LB_KC * LB_NC / LB_T; ++i) { const int e = t + LB_T * i; ws[e & 31][e >> 5] = wreg[i]; }
     __syncthreads();
+    if (k0 + LB_KC < H) fetch(k0 + LB_KC);
 #pragma unroll 8
     for (int kk = 0; kk < LB_KC; ++kk) {
       const float hv = hs[r][kk];
@@ -508,9 +518,10 @@ lb_latent_fwd_kernel(const float* __restrict__ h_e, int rows, int H, const float
 #pragma unroll
     for (int j = 0; j < LB_ZP; ++j) w[j] = j < Z ? W1[(size_t)j * H + n] : 0.f;
     const float bn = b1[n];
-    for (int rr = 0; rr < LB_ROWS; ++rr) {
+    const int nrows = min(LB_ROWS, rows - m0);
+#pragma unroll 2
+    for (int rr = 0; rr < nrows; ++rr) {
       const int m = m0 + rr;
-      if (m >= rows) break;
       float a = bn;
 #pragma unroll
       for (int q = 0; q < LB_ZP / 4; ++q) {
@@ -548,18 +559,27 @@ lb_latent_bwd_kernel(const float* __restrict__ da1, const float* __restrict__ W1
 #pragma unroll
   for (int i = 0; i < 12; ++i) acc[i] = 0.f;
   for (int i = t; i < LB_ROWS * LB_NC; i += LB_T) (&dd[0][0])[i] = 0.f;
-  for (int n0 = 0; n0 < H; n0 += LB_KC) {
+  float dreg[LB_ROWS * LB_KC / LB_T], wreg[LB_KC * LB_ZP / LB_T];
+  auto fetch = [&](int n0) {
 #pragma unroll
     for (int i = 0; i < LB_ROWS * LB_KC / LB_T; ++i) {
       const int rr = (t >> 5) + 8 * i, kk = t & 31;
-      ds[rr][kk] = (m0 + rr < rows && n0 + kk < H) ? da1[(size_t)(m0 + rr) * H + n0 + kk] : 0.f;
+      dreg[i] = (m0 + rr < rows && n0 + kk < H) ? da1[(size_t)(m0 + rr) * H + n0 + kk] : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < LB_KC * LB_ZP / LB_T; ++i) {
       const int e = t + LB_T * i, kk = e & 31, j = e >> 5;
-      ws[kk][j] = (j < Z && n0 + kk < H) ? W1[(size_t)j * H + n0 + kk] : 0.f;
+      wreg[i] = (j < Z && n0 + kk < H) ? W1[(size_t)j * H + n0 + kk] : 0.f;
     }
+  };
+  fetch(0);
+  for (int n0 = 0; n0 < H; n0 += LB_KC) {
+#pragma unroll
+    for (int i = 0; i < LB_ROWS * LB_KC / LB_T; ++i) ds[(t >> 5) + 8 * i][t & 31] = dreg[i];
+#pragma unroll
+    for (int i = 0; i < LB_KC * LB_ZP / LB_T; ++i) { const int e = t + LB_T * i; ws[e & 31][e >> 5] = wreg[i]; }
     __syncthreads();
+    if (n0 + LB_KC < H) fetch(n0 + LB_KC);
 #pragma unroll 8
     for (int q = 0; q < LB_KC / 2; ++q) {
       const int kk = ks * (LB_KC / 2) + q;
@@ -598,9 +618,10 @@ lb_latent_bwd_kernel(const float* __restrict__ da1, const float* __restrict__ W1
     float wr[LB_NC];
 #pragma unroll
     for (int c = 0; c < LB_NC; ++c) wr[c] = c < 2 * Z ? w45t[(size_t)c * H + n] : 0.f;
-    for (int rr = 0; rr < LB_ROWS; ++rr) {
+    const int nrows = min(LB_ROWS, rows - m0);
+#pragma unroll 4
+    for (int rr = 0; rr < nrows; ++rr) {
       const int m = m0 + rr;
-      if (m >= rows) break;
       float a = 0.f;
 #pragma unroll
       for (int q = 0; q < LB_NC / 4; ++q) {
@@ -662,7 +683,7 @@ lb_wgrad45_kernel(const float* __restrict__ h_e, const float* __restrict__ dmu, 
     __syncthreads();
     if (k <= H) {
       const int nr = min(LB_WG_SUB, r_hi - r0);
-#pragma unroll 4
+#pragma unroll 8
       for (int rr = 0; rr < nr; ++rr) {
         const float hv = k < H ? h_e[(size_t)(r0 + rr) * H + k] : 1.0f;
 #pragma unroll
@@ -705,7 +726,7 @@ lb_wgrad1_kernel(const float* __restrict__ z, const float* __restrict__ da1, int
     __syncthreads();
     if (n < H) {
       const int nr = min(LB_WG_SUB, r_hi - r0);
-#pragma unroll 4
+#pragma unroll 8
       for (int rr = 0; rr < nr; ++rr) {
         const float dv = da1[(size_t)(r0 + rr) * H + n];
 #pragma unroll

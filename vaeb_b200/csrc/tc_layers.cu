@@ -31,14 +31,59 @@ __device__ __forceinline__ void put_split(__nv_bfloat16* hi, __nv_bfloat16* lo, 
 }
 
 // ---- epilogues: one thread owns one accumulator row, 16 columns per call --------------------
+// A thread's 16 columns are contiguous in every operand it touches, but neighbouring lanes are different
+// ROWS: scalar accesses would touch 32 cache lines per instruction, 4 (or 2) bytes each.  The fast paths move
+// 16 bytes per access (full 32-byte sectors per row), the scalar paths handle ragged edges.
+__device__ __forceinline__ bool vec_ok(const void* p, int col0, int N) {
+  return col0 + 16 <= N && (((uintptr_t)p) & 15u) == 0;
+}
+__device__ __forceinline__ void ld16f(const float* p, float* d) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
+    d[4 * q] = t.x; d[4 * q + 1] = t.y; d[4 * q + 2] = t.z; d[4 * q + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void st16f(float* p, const float* d) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
+}
+__device__ __forceinline__ void st16_split(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* d) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(d[2 * q]), h1 = __float2bfloat16_rn(d[2 * q + 1]);
+    h[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(d[2 * q] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(d[2 * q + 1] - __bfloat162float(h1));
+    l[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  reinterpret_cast<uint4*>(hi)[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  reinterpret_cast<uint4*>(hi)[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  if (lo) {
+    reinterpret_cast<uint4*>(lo)[0] = make_uint4(l[0], l[1], l[2], l[3]);
+    reinterpret_cast<uint4*>(lo)[1] = make_uint4(l[4], l[5], l[6], l[7]);
+  }
+}
+
 struct EpiTanh {            // out[row, col] = tanh(acc + bias[col])
   const float* bias; float* out; int ld;
   __device__ __forceinline__ void begin() {}
+  __device__ __forceinline__ void split(int) {}
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
     if (!ok) return;
+    float* o = out + (size_t)row * ld + col0;
+    if (vec_ok(o, col0, N) && vec_ok(bias + col0, col0, N)) {
+      float b[16], r[16];
+      ld16f(bias + col0, b);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = tanhf(v[j] + b[j]);
+      st16f(o, r);
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (col0 + j < N) out[(size_t)row * ld + col0 + j] = tanhf(v[j] + bias[col0 + j]);
+      if (col0 + j < N) o[j] = tanhf(v[j] + bias[col0 + j]);
   }
   __device__ __forceinline__ void end(int, bool, int, int) {}
 };
@@ -48,17 +93,34 @@ struct EpiBernoulliTc {     // VAEB.py:263,311: term = x*a - softplus(a); da = s
   __nv_bfloat16* da_hi; __nv_bfloat16* da_lo; int ldda; float* partial;
   float acc;
   __device__ __forceinline__ void begin() { acc = 0.f; }
+  __device__ __forceinline__ void split(int) {}
+  // one exponential serves both: t = e^-|a|; softplus = max(a,0) + log(1+t); sigmoid = {1, t}/(1+t)
+  __device__ __forceinline__ float one(float a, float xv) {
+    const float t = exp2f(-1.4426950408889634f * fabsf(a));
+    const float r = __fdividef(1.0f, 1.0f + t);
+    acc += xv * a - (fmaxf(a, 0.f) + __logf(1.0f + t));
+    return scale * (xv - (a >= 0.f ? r : t * r));
+  }
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
     if (!ok) return;
-    const float* xr = x + (size_t)((row / x_div) % x_mod) * ldx;
+    const float* xr = x + (size_t)((row / x_div) % x_mod) * ldx + col0;
+    __nv_bfloat16* dh = da_hi ? da_hi + (size_t)row * ldda + col0 : nullptr;
+    __nv_bfloat16* dl = da_lo ? da_lo + (size_t)row * ldda + col0 : nullptr;
+    if (vec_ok(xr, col0, N) && vec_ok(bias + col0, col0, N) && vec_ok(dh, col0, N) && vec_ok(dl, col0, N)) {
+      float b[16], xv[16], d[16];
+      ld16f(bias + col0, b);
+      ld16f(xr, xv);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) d[j] = one(v[j] + b[j], xv[j]);
+      if (dh) st16_split(dh, dl, d);
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int c = col0 + j;
       if (c < N) {
-        const float a = v[j] + bias[c];
-        const float xv = xr[c];
-        acc += xv * a - softplusf_(a);
-        if (da_hi) put_split(da_hi, da_lo, (size_t)row * ldda + c, scale * (xv - sigmoidf_(a)));
+        const float d = one(v[j] + bias[c], xr[j]);
+        if (dh) put_split(dh, dl, (size_t)j, d);
       }
     }
   }
@@ -69,13 +131,18 @@ struct EpiBernoulliTc {     // VAEB.py:263,311: term = x*a - softplus(a); da = s
 
 struct EpiWgradTc {         // rows < Hreal -> gW[Hreal, N]; row == Hreal (the ones column of A) -> gb
   float* gW; float* gb; int Hreal; int ld;
+  float* scratch; size_t split_stride;   // split-K: slice z writes [gW | gb] at scratch + z * split_stride
   __device__ __forceinline__ void begin() {}
+  __device__ __forceinline__ void split(int z) {
+    if (scratch) { gW = scratch + (size_t)z * split_stride; gb = gW + (size_t)Hreal * ld; }
+  }
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
     if (!ok) return;
-    float* dst = row < Hreal ? gW + (size_t)row * ld : gb;
+    float* dst = (row < Hreal ? gW + (size_t)row * ld : gb) + col0;
+    if (vec_ok(dst, col0, N)) { st16f(dst, v); return; }
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (col0 + j < N) dst[col0 + j] = v[j];
+      if (col0 + j < N) dst[j] = v[j];
   }
   __device__ __forceinline__ void end(int, bool, int, int) {}
 };
@@ -83,14 +150,22 @@ struct EpiWgradTc {         // rows < Hreal -> gW[Hreal, N]; row == Hreal (the o
 struct EpiDgradTanh {       // out = acc * (1 - h^2)
   const float* h; float* out; int ld;
   __device__ __forceinline__ void begin() {}
+  __device__ __forceinline__ void split(int) {}
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
     if (!ok) return;
+    const float* hp = h + (size_t)row * ld + col0;
+    float* o = out + (size_t)row * ld + col0;
+    if (vec_ok(hp, col0, N) && vec_ok(o, col0, N)) {
+      float hv[16], r[16];
+      ld16f(hp, hv);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = v[j] * (1.0f - hv[j] * hv[j]);
+      st16f(o, r);
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (col0 + j < N) {
-        const float hv = h[(size_t)row * ld + col0 + j];
-        out[(size_t)row * ld + col0 + j] = v[j] * (1.0f - hv * hv);
-      }
+      if (col0 + j < N) o[j] = v[j] * (1.0f - hp[j] * hp[j]);
   }
   __device__ __forceinline__ void end(int, bool, int, int) {}
 };
@@ -100,7 +175,10 @@ struct LayerSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = NS * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
+  // plain bf16 (NS = 1): 3-4 stages so that TWO CTAs share an SM and one tile's epilogue overlaps the other's
+  // loads and MMAs (the kernel is one tile per CTA); bf16x3 stages are twice as large: one CTA per SM
+  static constexpr int BUDGET = NS == 1 ? 104 * 1024 : 200 * 1024;
+  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
   static_assert(STAGES >= 2, "tile too large");
 };
@@ -110,7 +188,7 @@ struct LayerMaps {            // hi/lo tensor maps of both operands (lo unused w
 };
 
 template <int BN, bool A_MN, bool B_MN, int NS, class Epi>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, NS == 1 ? 2 : 1)
 tc_layer_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, int K, int a_row_off) {
   using S = LayerSmem<BN, NS>;
   extern __shared__ uint8_t smem_raw[];
@@ -122,7 +200,11 @@ tc_layer_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, i
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int nkb = (K + BK - 1) / BK;
+  const int nkb_all = (K + BK - 1) / BK;
+  // split-K (weight gradients at large batch: few output tiles, long contraction): slice z of gridDim.z
+  const int kb0 = (int)(((long long)nkb_all * blockIdx.z) / gridDim.z);
+  const int nkb = (int)(((long long)nkb_all * (blockIdx.z + 1)) / gridDim.z) - kb0;
+  epi.split(blockIdx.z);
   constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
 
   if (warp == 0 && lane == 0) {
@@ -153,14 +235,15 @@ tc_layer_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, i
         const CUtensorMap* ta = sp ? &maps.a_lo : &maps.a_hi;
         const CUtensorMap* tb = sp ? &maps.b_lo : &maps.b_hi;
         if (A_MN) {   // A stored [K rows, M contiguous]: the row offset applies to the K coordinate
-          for (int g = 0; g < BM / 64; ++g) tc::tma_load_2d(a + g * 8192, ta, &full[s], m0 + g * 64, a_row_off + kb * BK);
+          for (int g = 0; g < BM / 64; ++g)
+            tc::tma_load_2d(a + g * 8192, ta, &full[s], m0 + g * 64, a_row_off + (kb0 + kb) * BK);
         } else {      // A stored [M rows, K contiguous]
-          tc::tma_load_2d(a, ta, &full[s], kb * BK, a_row_off + m0);
+          tc::tma_load_2d(a, ta, &full[s], (kb0 + kb) * BK, a_row_off + m0);
         }
         if (B_MN) {
-          for (int g = 0; g < BN / 64; ++g) tc::tma_load_2d(b + g * 8192, tb, &full[s], n0 + g * 64, kb * BK);
+          for (int g = 0; g < BN / 64; ++g) tc::tma_load_2d(b + g * 8192, tb, &full[s], n0 + g * 64, (kb0 + kb) * BK);
         } else {
-          tc::tma_load_2d(b, tb, &full[s], kb * BK, n0);
+          tc::tma_load_2d(b, tb, &full[s], (kb0 + kb) * BK, n0);
         }
       }
     }
@@ -212,7 +295,8 @@ tc_layer_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, i
 }
 
 template <int BN, bool A_MN, bool B_MN, int NS, class Epi>
-cudaError_t launch_layer(cudaStream_t st, const LayerMaps& maps, const Epi& epi, int M, int N, int K, int a_row_off) {
+cudaError_t launch_layer(cudaStream_t st, const LayerMaps& maps, const Epi& epi, int M, int N, int K, int a_row_off,
+                         int splits = 1) {
   using S = LayerSmem<BN, NS>;
   auto kfn = tc_layer_kernel<BN, A_MN, B_MN, NS, Epi>;
   static bool attr_done = false;   // per instantiation
@@ -221,20 +305,54 @@ cudaError_t launch_layer(cudaStream_t st, const LayerMaps& maps, const Epi& epi,
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
   kfn<<<grid, TC_THREADS, S::TOTAL, st>>>(maps, epi, M, N, K, a_row_off);
   return cudaGetLastError();
 }
 
 template <bool A_MN, bool B_MN, class Epi>
 cudaError_t dispatch_layer(cudaStream_t st, int ns, int bn, const LayerMaps& maps, const Epi& epi, int M, int N, int K,
-                           int a_row_off) {
+                           int a_row_off, int splits = 1) {
   if (ns == 2) {
-    if (bn == 128) return launch_layer<128, A_MN, B_MN, 2, Epi>(st, maps, epi, M, N, K, a_row_off);
-    return launch_layer<64, A_MN, B_MN, 2, Epi>(st, maps, epi, M, N, K, a_row_off);
+    if (bn == 128) return launch_layer<128, A_MN, B_MN, 2, Epi>(st, maps, epi, M, N, K, a_row_off, splits);
+    return launch_layer<64, A_MN, B_MN, 2, Epi>(st, maps, epi, M, N, K, a_row_off, splits);
   }
-  if (bn == 128) return launch_layer<128, A_MN, B_MN, 1, Epi>(st, maps, epi, M, N, K, a_row_off);
-  return launch_layer<64, A_MN, B_MN, 1, Epi>(st, maps, epi, M, N, K, a_row_off);
+  if (bn == 128) return launch_layer<128, A_MN, B_MN, 1, Epi>(st, maps, epi, M, N, K, a_row_off, splits);
+  return launch_layer<64, A_MN, B_MN, 1, Epi>(st, maps, epi, M, N, K, a_row_off, splits);
+}
+
+// Split-K plan of a weight-gradient GEMM [Mo x No] over K: as many K slices as fill the SMs once, at least
+// 8 k blocks each.  The slices go to scratch and are summed in a fixed order (deterministic, unlike atomics).
+int tc_wgrad_splits(int Mo, int No, int K, int bn) {
+  const int tiles = ((No + bn - 1) / bn) * ((Mo + BM - 1) / BM);
+  const int nkb = (K + BK - 1) / BK;
+  int s = 148 / (tiles > 0 ? tiles : 1);
+  if (s > nkb / 8) s = nkb / 8;
+  return s < 1 ? 1 : s;
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_split_reduce_kernel(const float* __restrict__ scratch, int splits, size_t stride, int n_w, int n_b,
+                          float* __restrict__ gW, float* __restrict__ gb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_w + n_b) return;
+  float a = 0.f;
+  for (int z = 0; z < splits; ++z) a += scratch[(size_t)z * stride + i];
+  if (i < n_w) gW[i] = a; else gb[i - n_w] = a;
+}
+
+cudaError_t tc_wgrad_generic(cudaStream_t st, int64_t* launches, const LayerMaps& maps, int ns, int bn, int Kred,
+                             int Hreal, int N, int a_row_off, float* gW, float* gb, float* scratch) {
+  const int splits = scratch ? tc_wgrad_splits(Hreal + 1, N, Kred, bn) : 1;
+  const size_t stride = (size_t)(Hreal + 1) * N;
+  EpiWgradTc epi{gW, gb, Hreal, N, splits > 1 ? scratch : nullptr, stride};
+  ++*launches;
+  cudaError_t e = dispatch_layer<true, true>(st, ns, bn, maps, epi, Hreal + 1, N, Kred, a_row_off, splits);
+  if (e != cudaSuccess || splits == 1) return e;
+  const int tot = (int)stride;
+  wgrad_split_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(scratch, splits, stride, Hreal * N, N, gW, gb);
+  ++*launches;
+  return cudaGetLastError();
 }
 
 // fp32 [rows, cols] (leading dim ld_src) -> bf16 hi (/lo) mirrors [rows, ld_dst]; column `ones_col`
@@ -342,17 +460,19 @@ cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int
   return dispatch_layer<false, false>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.dgrad), epi, R, H, D, 0);
 }
 
+size_t tc_wgrad_scratch_elems(int D, int H) {
+  (void)D; (void)H;
+  return (size_t)148 * BM * 128;          // splits * Mo * No <= (148 / tiles) * tiles * 128 * 128
+}
+
 cudaError_t tc_wgrad2(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
-                      float* gW2, float* gb2) {
-  EpiWgradTc epi{gW2, gb2, H, D};
-  ++*launches;
-  return dispatch_layer<true, true>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.wgrad2), epi, H + 1, D, R, 0);
+                      float* gW2, float* gb2, float* scratch) {
+  return tc_wgrad_generic(st, launches, *reinterpret_cast<const LayerMaps*>(m.wgrad2), ns, bn, R, H, D, 0, gW2, gb2,
+                          scratch);
 }
 
 cudaError_t tc_wgrad3(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int D, int H,
-                      int x_row_off, float* gW3, float* gb3) {
-  EpiWgradTc epi{gW3, gb3, D, H};
-  ++*launches;
-  return dispatch_layer<true, true>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.wgrad3), epi, D + 1, H, rows,
-                                    x_row_off);
+                      int x_row_off, float* gW3, float* gb3, float* scratch) {
+  return tc_wgrad_generic(st, launches, *reinterpret_cast<const LayerMaps*>(m.wgrad3), ns, bn, rows, D, H, x_row_off, gW3,
+                          gb3, scratch);
 }

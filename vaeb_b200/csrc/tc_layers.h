@@ -13,6 +13,7 @@ struct TcBuffers {   // bf16 mirrors; *l == nullptr in plain-bf16 mode
   void *da2h = nullptr, *da2l = nullptr;   // d bound / d a      [R, ldd]
   void *da3h = nullptr, *da3l = nullptr;   // d bound / d a3     [rows, ldh]
   int ldx = 0, ldh = 0, ldd = 0;
+  float* wg_scratch = nullptr;             // split-K slices of the wide weight gradients
 };
 
 struct TcMaps {
@@ -36,7 +37,9 @@ cudaError_t tc_dec2_bernoulli(cudaStream_t st, int64_t* launches, const TcMaps& 
                               void* da_lo, int ldda, float* partial, int* n_tiles);
 cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int D, int H,
                         const float* h_d, float* da1);
+// scratch: device floats for the split-K slices of a weight gradient (tc_wgrad_scratch_elems), or nullptr
+size_t tc_wgrad_scratch_elems(int D, int H);
 cudaError_t tc_wgrad2(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
-                      float* gW2, float* gb2);
+                      float* gW2, float* gb2, float* scratch);
 cudaError_t tc_wgrad3(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int D, int H,
-                      int x_row_off, float* gW3, float* gb3);
+                      int x_row_off, float* gW3, float* gb3, float* scratch);
