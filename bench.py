@@ -299,21 +299,28 @@ def run_own(args):
                 "value": dps, "unit": "datapoints/s", "ms_per_step": ms3 / k3, "steps": k3, "precision": prec,
                 "algorithmic_tflops": tf, "frac_of_bf16_sustained_peak_per_gpu": tf / world / peaks_["bf16_tflops_sustained"]}
             m3.close()
-        # c5: importance-sampled log p(x), L = 5000 samples per point, points sharded over the ranks
-        n_pts, L5 = 2000, 5000
-        xt = synthetic_mnist(n_pts, seed=4242)
-        m5 = vaeb_b200.VAEB(xt[:100], False, H, Z, 100, 1, 0.01, False, False, device=local, seed=10)
-        m5.set_stream(stream.cuda_stream)
-        vd.sharded_log_px(m5, xt[:64 * world], L5, rank, world, gather=False)
-        res5 = {}
-        ms5 = timed(lambda: res5.update(lp=vd.sharded_log_px(m5, xt, L5, rank, world, gather=False)))
-        sps = n_pts * L5 / (ms5 * 1e-3)
-        also["c5_is_logpx"] = {
-            "workload": "c5: IS log p(x), %d MNIST-shape points x L=%d, D=784 H=500 Z=20, points sharded over GPUs, "
-                        "host x in / host log p out" % (n_pts, L5),
-            "value": sps, "unit": "samples/s", "ms": ms5, "precision": "fp32",
-            "algorithmic_tflops": sps * 804000 / 1e12, "mean_logpx_rank0": float(np.mean(res5["lp"]))}
-        m5.close()
+        # c5: importance-sampled log p(x), 10,000 test points x L = 5000 samples, points sharded over the ranks.
+        # Tensor-core estimator (is_tc.cu, bf16 operands, 1e-2 tier) on the full configuration; the fp32
+        # estimator (1e-4 tier) on a 1000-point sample.  Host x in, host log p out: the timed region holds the
+        # H2D copy, the fp32 encoder, the fused decoder/log-likelihood/logsumexp kernel and the D2H copy.
+        L5 = 5000
+        for prec, n_pts in (("bf16", 10000), ("fp32", 1000)):
+            xt = synthetic_mnist(n_pts, seed=4242)
+            m5 = vaeb_b200.VAEB(xt[:100], False, H, Z, 100, 1, 0.01, False, False, device=local, seed=10, precision=prec)
+            m5.set_stream(stream.cuda_stream)
+            vd.sharded_log_px(m5, xt, L5, rank, world, gather=False)          # warm-up at the timed size
+            res5 = {}
+            ms5 = timed(lambda: res5.update(lp=vd.sharded_log_px(m5, xt, L5, rank, world, gather=False)))
+            sps = n_pts * L5 / (ms5 * 1e-3)
+            tf5 = sps * 804000 / 1e12
+            also["c5_is_logpx_" + prec] = {
+                "workload": "c5: IS log p(x), %d MNIST-shape points x L=%d, D=784 H=500 Z=20, points sharded over GPUs, "
+                            "host x in / host log p out" % (n_pts, L5),
+                "value": sps, "unit": "samples/s", "ms": ms5, "precision": prec,
+                "algorithmic_tflops": tf5, "flops_per_sample": 804000,
+                "frac_of_bf16_sustained_peak_per_gpu": tf5 / world / peaks_["bf16_tflops_sustained"],
+                "mean_logpx_rank0": float(np.mean(res5["lp"]))}
+            m5.close()
         # c1: the reference's own CPU-runnable case on one GPU
         from vaeb_b200.data import synthetic_frey
         xf = synthetic_frey()[:1500]
