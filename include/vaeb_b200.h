@@ -73,6 +73,9 @@ typedef struct vaeb_config {
   uint64_t seed;          /* Philox key (reference: RandomStreams(seed=10), VAEB.py:158) */
 } vaeb_config;
 
+#define VAEB_OPT_ADAGRAD 0   /* getUpdates          VAEB.py:426-444 (the path the reference runs) */
+#define VAEB_OPT_ADADELTA 1  /* getAdaDeltaUpdates  VAEB.py:449-469 (the alternative commented out at :404) */
+
 const char* vaeb_last_error(void);
 int vaeb_version(void);
 
@@ -98,6 +101,12 @@ int vaeb_get_tensors(vaeb_handle* h, int32_t which, float* const* tensors);
 /* Device address of a flat buffer (`which` as above) for zero-copy plumbing (e.g. wrapping as
  * a tensor for torch.distributed). */
 int vaeb_device_buffer(vaeb_handle* h, int32_t which, void** d_ptr, int64_t* n_elements);
+
+/* Selects the update rule of the next vaeb_update* calls.  VAEB_OPT_ADADELTA restates
+ * getAdaDeltaUpdates (VAEB.py:449-469): g_ac = rho g_ac + (1-rho) g^2; dx = sqrt(dx_ac + eps) g / sqrt(g_ac + eps);
+ * p += dx; dx_ac = rho dx_ac + (1-rho) dx^2, with eps = adagrad_eps (VAEB.py:144) and rho = 0.95 (VAEB.py:145).
+ * Both accumulators restart at zero.  Not available for the full-VB estimators. */
+int vaeb_set_optimizer(vaeb_handle* h, int32_t optimizer, float rho);
 
 /* `x_train = th.shared(...)` (VAEB.py:184): copies x[N,D] to the device once. */
 int vaeb_upload_data(vaeb_handle* h, const float* x, int64_t n_rows);

@@ -336,6 +336,20 @@ def adagrad_update(params, ada, grads, lr, eps=1e-6, p2_coeff=0.0):
         q += upd
 
 
+def adadelta_update(params, g_ac, dx_ac, grads, rho=0.95, eps=1e-6):
+    """``getAdaDeltaUpdates`` VAEB.py:449-469 (the alternative to Adagrad that the reference keeps
+    commented out at VAEB.py:404): g_ac = rho*g_ac + (1-rho)*g^2; dx = sqrt(dx_ac+eps)*g/sqrt(g_ac+eps);
+    x += dx; dx_ac = rho*dx_ac + (1-rho)*dx^2.  In place."""
+    for q, a, d, g in zip(params, g_ac, dx_ac, grads):
+        dt = q.dtype.type
+        a *= dt(rho)
+        a += dt(1.0 - rho) * g * g
+        dx = np.sqrt(d + dt(eps)) * g / np.sqrt(a + dt(eps))
+        q += dx
+        d *= dt(rho)
+        d += dt(1.0 - rho) * dx * dx
+
+
 # --------------------------------------------------------------------------------------
 # model objects mirroring the compiled functions
 # --------------------------------------------------------------------------------------
@@ -348,12 +362,13 @@ class OracleVAEB:
     prior in the criterion, extra -lr*1e-6*p**2 in the update)."""
 
     def __init__(self, x_train, continuous, H, Z, batch_size, L=1, lr=0.01, estimator="LB",
-                 params=None, dtype=np.float64, variant="vaeb"):
+                 params=None, dtype=np.float64, variant="vaeb", optimizer="adagrad", rho=0.95):
         self.x = np.asarray(x_train, dtype=dtype)
         self.N, self.D = self.x.shape
         self.continuous, self.H, self.Z = continuous, H, Z
         self.M, self.L, self.lr = batch_size, L, lr
         self.estimator, self.variant, self.dtype = estimator, variant, dtype
+        self.optimizer, self.rho = optimizer, rho
         if params is None:
             params = init_params(self.D, H, Z, continuous, dtype=np.float32)
         self.params = [np.array(q, dtype=dtype, copy=True) for q in params]
@@ -363,6 +378,7 @@ class OracleVAEB:
         else:
             self.fvp = None
             self.ada = _zeros_like_list(self.params)               # VAEB.py:178-182
+            self.dx_ac = _zeros_like_list(self.params)             # VAEB.py:457 (AdaDelta only)
 
     # -- objective -------------------------------------------------------------------
     def _objective(self, x, eps, want_grads, zeta=None):
@@ -413,7 +429,10 @@ class OracleVAEB:
             adagrad_update(self.params, self.ada, grads, self.lr, 1e-6, p2_coeff=1e-6)
             return sgvb                                              # VAEBfullbayes.py:153
         target = self.fvp if self.fvp is not None else self.params
-        adagrad_update(target, self.ada, grads, self.lr, 1e-6)
+        if self.optimizer == "adadelta":
+            adadelta_update(target, self.ada, self.dx_ac, grads, self.rho, 1e-6)
+        else:
+            adagrad_update(target, self.ada, grads, self.lr, 1e-6)
         return sgvb / self.M
 
     def validate(self, x, eps, zeta=None):

@@ -188,6 +188,23 @@ def main():
             g["%s__%s" % (name, k)] = v
     np.savez_compressed(os.path.join(HERE, "ref_vaeb_small.npz"), **g)
 
+    # ---- AdaDelta: the reference keeps `updates = self.getAdaDeltaUpdates(gradients)` commented out at
+    # VAEB.py:404; swapping the method in is what un-commenting that line does -------------------------------
+    g = {}
+    keep = V.VAEB.getUpdates
+    V.VAEB.getUpdates = V.VAEB.getAdaDeltaUpdates
+    try:
+        for name in ("disc_LB_L1", "cont_LA_L1"):
+            c = cases[name]
+            r = run_vaeb_case(V, th, c["x"], c["continuous"], c["H"], c["Z"], c["M"], c["L"], 0.01, c["generic"],
+                              order=[0, 2, 1, 0, 1, 2], n_valid=2 * c["M"], scale=40.0)
+            for k, v in r.items():
+                if not k.startswith("ada_"):            # getAdaDeltaUpdates keeps its accumulators in local shared variables
+                    g["%s__%s" % (name, k)] = v
+    finally:
+        V.VAEB.getUpdates = keep
+    np.savez_compressed(os.path.join(HERE, "ref_adadelta_small.npz"), **g)
+
     # ---- the reference's initialisation at the real shapes (draw order, VAEB.py:50-125) -------
     g = {}
     for tag, (D, H, Z, cont) in {"mnist": (784, 500, 20, False), "frey": (560, 200, 2, True)}.items():

@@ -61,6 +61,23 @@ def test_cuda_matches_reference_vaeb_small(case):
     m.close()
 
 
+@pytest.mark.parametrize("case", ["disc_LB_L1", "cont_LA_L1"])
+def test_cuda_matches_reference_adadelta(case):
+    """getAdaDeltaUpdates (VAEB.py:449-469) on the device: six updates, then validate."""
+    c = _sub(load_golden("ref_adadelta_small.npz"), case)
+    names = NAMES_C if bool(c["continuous"]) else NAMES_D
+    m, rets, val = _replay(c, [c["init_" + n] for n in names], generic=bool(c["generic"]), optimizer="adadelta")
+    np.testing.assert_allclose(rets, c["update_returns"], rtol=1e-4)
+    assert val == pytest.approx(float(c["validate_return"]), rel=1e-4)
+    for n, p in zip(names, m.get_params()):
+        # an AdaDelta step is sqrt(dx_ac + 1e-6) * g / sqrt(g_ac + 1e-6) ~ 1e-3 * sign(g) at first: entries whose
+        # gradient is a sum of cancelling terms move by up to that much differently (cf. _check_state)
+        ref = np.asarray(c["final_" + n], np.float64)
+        err = np.abs(p.astype(np.float64) - ref)
+        assert np.all(err <= 1e-4 * np.maximum(np.abs(ref), 0.05 * np.abs(ref).max()) + 6e-6), (n, err.max())
+    m.close()
+
+
 @pytest.mark.parametrize("est", ["LB", "LA"])
 def test_cuda_matches_reference_frey_trained(est):
     """C1 shape (560-200-2, M=100) with the trained weights the reference ships."""

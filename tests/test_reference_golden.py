@@ -22,13 +22,13 @@ def _sub(g, prefix):
     return {k[len(prefix) + 2:]: v for k, v in g.items() if k.startswith(prefix + "__")}
 
 
-def _replay(c, params0, estimator, variant="vaeb"):
+def _replay(c, params0, estimator, variant="vaeb", optimizer="adagrad"):
     cont = bool(c["continuous"])
     names = O.param_names(cont)
     H, Z, M, L = int(c["H"]), int(c["Z"]), int(c["M"]), int(c.get("L", 1))
     x = c["x"].astype(np.float64)
     m = O.OracleVAEB(x, cont, H, Z, M, L=L, lr=float(c["lr"]), estimator=estimator, params=params0,
-                     dtype=np.float64, variant=variant)
+                     dtype=np.float64, variant=variant, optimizer=optimizer)
     rets = [m.update(int(i), c["eps_update_%d" % k]) for k, i in enumerate(c["order"])]
     nv = c["eps_validate"].shape[1]
     val = m.validate(x[:nv], c["eps_validate"])[0]
@@ -48,6 +48,20 @@ def test_oracle_matches_reference_vaeb_small(case):
     for n, p, a in zip(names, m.params, m.ada):
         np.testing.assert_allclose(p, c["final_" + n], rtol=1e-8, atol=1e-12, err_msg=n)
         np.testing.assert_allclose(a, c["ada_" + n], rtol=1e-8, atol=1e-14, err_msg="ada " + n)
+
+
+@pytest.mark.parametrize("case", ["disc_LB_L1", "cont_LA_L1"])
+def test_oracle_matches_reference_adadelta(case):
+    """getAdaDeltaUpdates (VAEB.py:449-469) swapped in for getUpdates, as un-commenting VAEB.py:404 does:
+    six updates (rho = 0.95, eps = 1e-6) and one validate."""
+    c = _sub(load_golden("ref_adadelta_small.npz"), case)
+    cont = bool(c["continuous"])
+    p0 = [c["init_" + n] for n in O.param_names(cont)]
+    m, names, rets, val = _replay(c, p0, "LA" if bool(c["generic"]) else "LB", optimizer="adadelta")
+    np.testing.assert_allclose(rets, c["update_returns"], rtol=RTOL)
+    assert val == pytest.approx(float(c["validate_return"]), rel=RTOL)
+    for n, p in zip(names, m.params):
+        np.testing.assert_allclose(p, c["final_" + n], rtol=1e-8, atol=1e-12, err_msg=n)
 
 
 def test_oracle_init_matches_reference_draw_order():

@@ -371,7 +371,12 @@ int enqueue_update(vaeb_handle* h, const float* d_xrows, int rows, const float* 
     VAEB_TRY(forward_backward(h, h->d_params, d_xrows, rows, L, true, w, src, h->d_grads, bo));
     VAEB_TRY(all_reduce_grads(h));
     const float prior = fb ? 0.f : h->cfg.prior_scale;
-    if (apply) {
+    if (apply && h->optimizer == VAEB_OPT_ADADELTA) {
+      PH("adadelta+prior (flat)", 0, 28.0 * (double)l.total,
+         launch_adadelta(st, lc, h->d_params, h->d_ada, h->d_ada2, h->d_grads, n4, h->rho, h->cfg.adagrad_eps, prior,
+                         base, 1.0f, Mg, dp ? h->d_scalars + slot : nullptr));
+      h->grads_have_prior = false;
+    } else if (apply) {
       PH("adagrad+prior (flat)", 0, 20.0 * (double)l.total,
          launch_adagrad(st, lc, h->d_params, h->d_ada, h->d_grads, n4, h->cfg.learning_rate, h->cfg.adagrad_eps,
                         prior, fb ? h->cfg.learning_rate * 1e-6f : 0.f, base, 1.0f, Mg,
@@ -441,6 +446,7 @@ float* flat_by_which(vaeb_handle* h, int which) {
     case 6: return h->d_ada_sig;
     case 7: return h->d_gmu;
     case 8: return h->d_gsig;
+    case 9: return h->d_ada2;
     default: return nullptr;
   }
 }
@@ -494,7 +500,7 @@ int vaeb_create(const vaeb_config* cfg, vaeb_handle** out) {
   h->D = cfg->input_dim; h->H = cfg->hidden_units; h->Z = cfg->latent_size; h->M = cfg->batch_size; h->L = cfg->L;
   h->cont = cfg->continuous != 0;
   build_layout(h->lay, h->D, h->H, h->Z, h->cont);
-  { const char* e = getenv("VAEB_B200_FUSED"); h->fused_off = e && e[0] == '0'; }
+  { const char* e = getenv("VAEB_B200_FUSED"); h->fused_off = e && e[0] == '0'; h->fused_off_user = h->fused_off; }
   h->tc.active = cfg->precision != VAEB_PREC_FP32;
   h->tc.ns = cfg->precision == VAEB_PREC_BF16X3 ? 2 : 1;
   VAEB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -530,7 +536,7 @@ int vaeb_destroy(vaeb_handle* h) {
   free_ws(h->ws);
   float* bufs[] = {h->d_params, h->d_ada, h->d_grads, h->d_vmu, h->d_vsig, h->d_ada_mu, h->d_ada_sig, h->d_gmu,
                    h->d_gsig, h->d_theta, h->d_zeta, h->d_tprior, h->d_x, h->d_stage, h->d_stage2, h->d_out,
-                   h->d_scalars};
+                   h->d_scalars, h->d_ada2};
   for (float* p : bufs) if (p) cudaFree(p);
   if (h->d_counter) cudaFree(h->d_counter);
   if (h->d_w45t) cudaFree(h->d_w45t);
@@ -677,6 +683,23 @@ int vaeb_update_host(vaeb_handle* h, const float* x, int64_t rows, const float* 
   else
     VAEB_TRY(enqueue_update(h, h->d_stage, (int)rows, d_eps, nullptr, 0, true));
   return read_scalars(h, 1, elbo_out);
+}
+
+int vaeb_set_optimizer(vaeb_handle* h, int32_t optimizer, float rho) {
+  VAEB_REQUIRE(h, "null handle");
+  VAEB_REQUIRE(optimizer == VAEB_OPT_ADAGRAD || optimizer == VAEB_OPT_ADADELTA, "unknown optimizer");
+  VAEB_REQUIRE(optimizer == VAEB_OPT_ADAGRAD || !is_fvb(h), "AdaDelta is not wired to the full-VB estimators");
+  VAEB_REQUIRE(optimizer == VAEB_OPT_ADAGRAD || (rho > 0.f && rho < 1.f), "rho must lie in (0, 1)");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  const size_t nb = (size_t)(h->lay.padded + 4) * sizeof(float);
+  VAEB_CUDA(cudaStreamSynchronize(h->stream));
+  if (optimizer == VAEB_OPT_ADADELTA && !h->d_ada2) VAEB_CUDA(cudaMalloc((void**)&h->d_ada2, nb));
+  if (h->d_ada2) VAEB_CUDA(cudaMemsetAsync(h->d_ada2, 0, nb, h->stream));
+  VAEB_CUDA(cudaMemsetAsync(h->d_ada, 0, nb, h->stream));
+  h->optimizer = optimizer;
+  h->rho = rho;
+  h->fused_off = optimizer != VAEB_OPT_ADAGRAD ? true : h->fused_off_user;
+  return VAEB_OK;
 }
 
 int vaeb_update_host_async(vaeb_handle* h, const float* x, int64_t rows) {

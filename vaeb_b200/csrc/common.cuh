@@ -117,6 +117,7 @@ struct vaeb_handle {
   float* d_w45t = nullptr;            // [2Z, H] transposed latent-head weights of the current theta
   float* d_x = nullptr; int64_t n_data = 0;
   Workspace ws;
+  int optimizer = 0; float rho = 0.95f; float* d_ada2 = nullptr;   // AdaDelta: d_ada = g_ac, d_ada2 = dx_ac
   float* d_stage = nullptr; int64_t stage_cap = 0;       // device staging for host inputs
   // streaming host-input updates (vaeb_update_host_async): copy stream + ring of staging buffers
   static constexpr int ASYNC_BUFS = 4;
@@ -136,6 +137,7 @@ struct vaeb_handle {
   FusedState fused;
   IsTcState istc;
   bool fused_off = false;             // VAEB_B200_FUSED=0: always use the per-layer kernels
+  bool fused_off_user = false;        // what the environment asked for (AdaDelta also turns the fused kernel off)
   // data parallel
   NcclApi nccl; void* comm = nullptr; int rank = 0, world = 1;
 };

@@ -253,6 +253,30 @@ adagrad_kernel(float4* __restrict__ p, float4* __restrict__ acc, const float4* _
   acc[i] = av;
 }
 
+// getAdaDeltaUpdates, VAEB.py:449-469 (g already carries the prior: VAEB.py:389-390), 28 B/parameter
+__device__ __forceinline__ void adadelta1(float& p, float& gac, float& dxac, float g, float rho, float eps, float prior) {
+  g -= prior * p;
+  gac = rho * gac + (1.0f - rho) * g * g;
+  const float dx = sqrtf(dxac + eps) * g / sqrtf(gac + eps);
+  p += dx;
+  dxac = rho * dxac + (1.0f - rho) * dx * dx;
+}
+__global__ void __launch_bounds__(256)
+adadelta_kernel(float4* __restrict__ p, float4* __restrict__ gac, float4* __restrict__ dxac, const float4* __restrict__ g,
+                int64_t n4, float rho, float eps, float prior, const float* __restrict__ base, float mult, float div,
+                float* __restrict__ scalar_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && scalar_out) *scalar_out = (mult * *base) / div;
+  if (i >= n4) return;
+  float4 pv = p[i], av = gac[i], dv = dxac[i];
+  const float4 gv = g[i];
+  adadelta1(pv.x, av.x, dv.x, gv.x, rho, eps, prior);
+  adadelta1(pv.y, av.y, dv.y, gv.y, rho, eps, prior);
+  adadelta1(pv.z, av.z, dv.z, gv.z, rho, eps, prior);
+  adadelta1(pv.w, av.w, dv.w, gv.w, rho, eps, prior);
+  p[i] = pv; gac[i] = av; dxac[i] = dv;
+}
+
 __global__ void __launch_bounds__(256)
 theta_prior_kernel(const float* __restrict__ vmu, const float* __restrict__ vsig, int64_t n,
                    float* __restrict__ partials) {
@@ -369,6 +393,14 @@ cudaError_t launch_add_prior(cudaStream_t st, int64_t* launches, float* g, const
                              const float* base, float mult, float div, float* scalar_out) {
   add_prior_kernel<<<blocks_for(n4, 256), 256, 0, st>>>((float4*)g, (const float4*)p, n4, prior, base, mult, div,
                                                         scalar_out);
+  return LAUNCHED();
+}
+
+cudaError_t launch_adadelta(cudaStream_t st, int64_t* launches, float* p, float* gac, float* dxac, const float* g,
+                            int64_t n4, float rho, float eps, float prior, const float* base, float mult, float div,
+                            float* scalar_out) {
+  adadelta_kernel<<<blocks_for(n4, 256), 256, 0, st>>>((float4*)p, (float4*)gac, (float4*)dxac, (const float4*)g, n4, rho,
+                                                       eps, prior, base, mult, div, scalar_out);
   return LAUNCHED();
 }
 

@@ -63,6 +63,9 @@ cudaError_t launch_add_prior(cudaStream_t st, int64_t* launches, float* g, const
                              const float* base, float mult, float div, float* scalar_out);
 // Adagrad (VAEB.py:426-444; VAEBfullbayes.py:183-184 with p2 = lr*1e-6) over the flat buffer.
 // If scalar_out != nullptr thread 0 also writes (mult*base + tprior)/div.
+cudaError_t launch_adadelta(cudaStream_t st, int64_t* launches, float* p, float* gac, float* dxac, const float* g,
+                            int64_t n4, float rho, float eps, float prior, const float* base, float mult, float div,
+                            float* scalar_out);
 cudaError_t launch_adagrad(cudaStream_t st, int64_t* launches, float* p, float* acc, const float* g, int64_t n4,
                            float lr, float eps, float prior, float p2, const float* base, float mult, float div,
                            float* scalar_out);

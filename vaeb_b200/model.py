@@ -70,9 +70,12 @@ class VAEB(object):
     #   eps_mode       'philox' on-device noise | 'theano' host RandomStreams emulation
     #   sample_weights full-VB with sample_variational_params live (VAEB.py:127-129)
     #   variant        'vaeb' | 'fullbayes' (VAEBfullbayes.py objective/update scalars)
+    #   optimizer      'adagrad' (getUpdates, VAEB.py:426-444) | 'adadelta' (getAdaDeltaUpdates, VAEB.py:449-469,
+    #                  the alternative the reference keeps commented out at VAEB.py:404; rho = self.rho = 0.95)
     def __init__(self, x_train, continuous, hidden_units, latent_size, batch_size,
                  L, learning_rate, genericEstimator, fullVariational, params=None, prng=None, sigmaInit=None,
-                 *, device=0, precision="fp32", eps_mode="philox", sample_weights=False, variant="vaeb", seed=10):
+                 *, device=0, precision="fp32", eps_mode="philox", sample_weights=False, variant="vaeb", seed=10,
+                 optimizer="adagrad"):
         x_train = np.asarray(x_train)
         [self.N, self.input_size] = x_train.shape       # VAEB.py:135
         self.n_hidden_units = hidden_units
@@ -149,6 +152,11 @@ class VAEB(object):
                 self.full_variational_params += [SharedParam(self, _lib.BUF_VMU, i, nm + "_mu_vb", s),
                                                  SharedParam(self, _lib.BUF_VSIG, i, nm + "_sigma_vb", s)]
 
+        if optimizer not in ("adagrad", "adadelta"):
+            raise ValueError("optimizer must be 'adagrad' or 'adadelta'")
+        self.optimizer = optimizer
+        if optimizer == "adadelta":
+            _lib.check(self._lib.vaeb_set_optimizer(self._h, _lib.OPT_ADADELTA, self.rho))
         _lib.check(self._lib.vaeb_upload_data(self._h, _ptr(_f32(x_train)), self.N))   # VAEB.py:184
 
     # ---- parameters -------------------------------------------------------------------
