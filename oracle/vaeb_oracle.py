@@ -5,13 +5,21 @@ checker for the CUDA path, never the product: only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / reference arm may
 import it.  Nothing under ``vaeb_b200/`` imports this module.
 
-PARITY UNPINNED: the reference ships no tests, golden input/output pairs or
-known-answer vectors for this path, and its arithmetic
-lives in Theano (third-party, not vendored, no version pin; the shipped pickles
-say Theano ~0.7-0.9 / Python 2.7), which cannot run in this image.  What pins
-this oracle instead:
+PINNED BY THE REFERENCE'S OWN SOURCE: the reference ships no tests, golden input/output
+pairs or known-answer vectors for this path and is Python 2 +
+Theano, which cannot run in this image -- so tests/golden/make_reference_golden.py
+executes the reference's files where they lie (VAEB.py, VAEBfullbayes.py,
+degenerate-vae/{logpdf,mlp,infalg}.py) on a lazy-graph Theano stand-in
+(tests/golden/theano_shim.py, torch CPU float64) and commits inputs, the noise each call
+drew and all outputs as tests/golden/ref_*.npz.  tests/test_reference_golden.py holds
+this oracle to those vectors (<= 1e-9 on every bound, parameter and accumulator: both
+decoders x both estimators x L in {1,2}, full-VB, the fullbayes variant, AdaDelta, the
+reference initialisation, the shipped trained Frey weights).  Unpinned remains only
+Theano's own arithmetic under the calls the stand-in substitutes, and the capabilities
+the reference does not have (IS estimator, sampled-weights full-VB: specified here).
+Further checks:
   * the one known-answer input in the reference, ``degenerate-vae/logpdf.py:119-123``
-    (value computed analytically: 6*ln(0.99+1e-7));
+    (6*ln(0.99+1e-7), now also produced by the reference's own ``bernoulli``);
   * an independent ``torch.autograd`` (CPU, fp64) re-derivation of every objective
     (tests/test_oracle.py) and central finite differences;
   * the trained fp32 Frey weights shipped in ``reconstruction_res/*.mdl`` as
