@@ -102,6 +102,22 @@ int vaeb_get_tensors(vaeb_handle* h, int32_t which, float* const* tensors);
  * a tensor for torch.distributed). */
 int vaeb_device_buffer(vaeb_handle* h, int32_t which, void** d_ptr, int64_t* n_elements);
 
+/* ---- AE baselines: ConstructAE of degenerate-vae/ae.py:41-117 and vanilla-ae/ae.py:45-104,
+ * one tanh hidden layer per side as LearnFreyFace / LearnMNIST build them.  They share the handle's parameter
+ * layout: W3 = Wenc, W4 = Wz, W1 = Wdec, W2 = Wout | Wmu, W6 = Wlogs2 (cfg.continuous = otype 'cont'); W5, b5 unused.
+ * cfg.prior_scale = 1/s2 (mlp.ConstructNormalPrior, mlp.py:87-91), cfg.learning_rate = eta of infalg.AdaGrad. */
+#define VAEB_AE_DEGENERATE 0  /* Z = Hz.Wz + bz, N(0,1) prior on Z, logpdf.bernoulli (+1e-7) | indep_normal */
+#define VAEB_AE_VANILLA 1     /* Z = tanh(Hz.Wz + bz), squared error of sigmoid outputs                      */
+
+/* `train(idx)` (ae.py:79-87): gathers rows idx[0..n) of the resident data (`givens = {X: Xtr[idx]}`), ascends
+ * logjoint with AdaGrad (infalg.py:148-164) and returns loglik / n (degenerate) or se / n (vanilla), computed with
+ * the pre-update parameters. */
+int vaeb_ae_train(vaeb_handle* h, int32_t kind, const int32_t* idx, int32_t n, float* out);
+
+/* `reconstruct(X)` (what = 0, ae.py:90-96), `encode(X)` (1, :99-105), `decode(Z)` (2, :108-114) on host arrays:
+ * in[rows, D | Dz] -> out[rows, D | Dz | D]. */
+int vaeb_ae_forward(vaeb_handle* h, int32_t kind, int32_t what, const float* in, int64_t rows, float* out);
+
 /* Selects the update rule of the next vaeb_update* calls.  VAEB_OPT_ADADELTA restates
  * getAdaDeltaUpdates (VAEB.py:449-469): g_ac = rho g_ac + (1-rho) g^2; dx = sqrt(dx_ac + eps) g / sqrt(g_ac + eps);
  * p += dx; dx_ac = rho dx_ac + (1-rho) dx^2, with eps = adagrad_eps (VAEB.py:144) and rho = 0.95 (VAEB.py:145).

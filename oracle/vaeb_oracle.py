@@ -536,6 +536,93 @@ def out_to_real(Hm, W, b):
 
 
 # --------------------------------------------------------------------------------------
+# AE baselines: degenerate-vae/ae.py:41-117 and vanilla-ae/ae.py:45-104, one hidden layer
+# per side as LearnFreyFace / LearnMNIST build them.  Parameters in the VAEB list order
+# [W3,W4,W5,W1,W2,(W6),b3,b4,b5,b1,b2,(b6)] with W3=Wenc0, W4=Wz, W1=Wdec0, W2=Wout|Wmu, W6=Wlogs2 (W5, b5 unused).
+# --------------------------------------------------------------------------------------
+def ae_objective_and_grads(params, x, continuous, kind, s2=1.0):
+    """Returns (reported value, gradient of logjoint w.r.t. params) for one minibatch x.
+    kind 'degenerate': Z = Hz.Wz+bz; loglik = logpdf.bernoulli (1e-7 inside both logs) | indep_normal;
+      logjoint = loglik + NormalPrior(theta, s2) + NormalPrior([Z], 1); reported loglik / M   (ae.py:46-87)
+    kind 'vanilla': Z = tanh(Hz.Wz+bz); se = sum((X - sigmoid(.))^2); logjoint = -se + NormalPrior(theta, s2);
+      reported se / M                                                                        (vanilla-ae/ae.py:50-83)"""
+    p = as_dict(params, continuous)
+    M = x.shape[0]
+    h_e = np.tanh(x @ p["W3"] + p["b3"])
+    pre = h_e @ p["W4"] + p["b4"]
+    z = np.tanh(pre) if kind == "vanilla" else pre
+    h_d = np.tanh(z @ p["W1"] + p["b1"])
+    a = h_d @ p["W2"] + p["b2"]
+    P = sigmoid(a)
+    Q = sigmoid(-a)                                     # 1 - P without cancellation
+    g = {n: np.zeros_like(q) for n, q in p.items()}
+    d_lv = None
+    if kind == "vanilla":
+        assert not continuous
+        value = ((x - P) ** 2).sum() / M
+        d_a = 2.0 * (x - P) * P * Q                     # d(-se)/da
+    elif continuous:
+        lv = h_d @ p["W6"] + p["b6"]
+        r = (x - P) * np.exp(-lv)
+        value = (-0.5 * (LOG2PI + lv + (x - P) * r)).sum() / M          # logpdf.py:112-114
+        d_a = r * P * Q
+        d_lv = -0.5 + 0.5 * (x - P) * r
+    else:
+        e = 1e-7
+        value = (x * np.log(P + e) + (1.0 - x) * np.log(Q + e)).sum() / M   # logpdf.py:85-86
+        d_a = (x / (P + e) - (1.0 - x) / (Q + e)) * P * Q
+    g["W2"] = h_d.T @ d_a
+    g["b2"] = d_a.sum(axis=0)
+    d_h = d_a @ p["W2"].T
+    if d_lv is not None:
+        g["W6"] = h_d.T @ d_lv
+        g["b6"] = d_lv.sum(axis=0)
+        d_h += d_lv @ p["W6"].T
+    d_a1 = d_h * (1.0 - h_d ** 2)
+    g["W1"] = z.T @ d_a1
+    g["b1"] = d_a1.sum(axis=0)
+    d_z = d_a1 @ p["W1"].T
+    d_pre = d_z * (1.0 - z ** 2) if kind == "vanilla" else d_z - z      # tanh'  |  NormalPrior([Z], 1.0)
+    g["W4"] = h_e.T @ d_pre
+    g["b4"] = d_pre.sum(axis=0)
+    d_a3 = (d_pre @ p["W4"].T) * (1.0 - h_e ** 2)
+    g["W3"] = x.T @ d_a3
+    g["b3"] = d_a3.sum(axis=0)
+    names = param_names(continuous)
+    grads = [g[n] - p[n] / s2 for n in names]           # mlp.py:87-91: -0.5*sum(p^2/s2 + log(2 pi s2))
+    for i, n in enumerate(names):
+        if n in ("W5", "b5"):
+            grads[i] = np.zeros_like(p[n])              # not part of theta in ae.py
+    return float(value), grads
+
+
+class OracleAE:
+    """`train(idx)` of ConstructAE with infalg.AdaGrad(eta) (infalg.py:148-164): gather rows, ascend logjoint."""
+
+    def __init__(self, x_train, continuous, params, kind="degenerate", s2=1.0, eta=0.01, dtype=np.float64):
+        self.x = np.asarray(x_train, dtype=dtype)
+        self.continuous, self.kind, self.s2, self.eta = continuous, kind, s2, eta
+        self.params = [np.array(q, dtype=dtype, copy=True) for q in params]
+        self.ada = _zeros_like_list(self.params)
+
+    def train(self, idx):
+        value, grads = ae_objective_and_grads(self.params, self.x[np.asarray(idx)], self.continuous, self.kind, self.s2)
+        adagrad_update(self.params, self.ada, grads, self.eta, 1e-6)
+        return value
+
+    def forward(self, x, what="reconstruct"):
+        p = as_dict(self.params, self.continuous)
+        if what == "decode":
+            z = np.asarray(x, self.x.dtype)
+        else:
+            pre = np.tanh(np.asarray(x, self.x.dtype) @ p["W3"] + p["b3"]) @ p["W4"] + p["b4"]
+            z = np.tanh(pre) if self.kind == "vanilla" else pre
+            if what == "encode":
+                return z
+        return sigmoid(np.tanh(z @ p["W1"] + p["b1"]) @ p["W2"] + p["b2"])
+
+
+# --------------------------------------------------------------------------------------
 # synthetic data of the reference's shapes (SURVEY 8d) -- shared by tests and bench
 # --------------------------------------------------------------------------------------
 def synthetic_mnist(n, seed=15485863, D=784):

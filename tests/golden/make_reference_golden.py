@@ -309,6 +309,43 @@ def main():
     g["ag_obj"] = np.array([float(step()), float(step())])
     g["ag_theta2_0"], g["ag_theta2_1"] = theta[0].get_value().copy(), theta[1].get_value().copy()
     np.savez_compressed(os.path.join(HERE, "ref_ae_primitives.npz"), **g)
+
+    # ---- AE baselines: ConstructAE of degenerate-vae/ae.py (binary + cont) and vanilla-ae/ae.py ------------------
+    # theta order of the reference: Wenc + benc + [Wz, bz] + Wdec + bdec + [Wout, bout] | [Wmu, Wlogs2, bmu, blogs2];
+    # stored under the VAEB names (W3=Wenc0, b3, W4=Wz, b4, W1=Wdec0, b1, W2=Wout|Wmu, b2, W6=Wlogs2, b6).
+    ae_deg = load_reference_module("degenerate-vae/ae.py", "ae_degenerate")
+    ae_van = load_reference_module("vanilla-ae/ae.py", "ae_vanilla")
+    g = {}
+    D, Hh, Dz, Ntr = 36, 20, 3, 40
+    for tag, mod, otype, xs in (("deg_binary", ae_deg, "binary", bern_x(Ntr, D)), ("deg_cont", ae_deg, "cont", cont_x(Ntr, D)),
+                                ("vanilla", ae_van, None, bern_x(Ntr, D))):
+        np.random.seed(1234)                              # mlp.WeightMatrix / BiasVector draw from the global numpy RNG
+        Xtr = th.shared(xs, "Xtr")
+        kw = dict(Denc=[Hh], Dz=Dz, Ddec=[Hh], inf=ia.AdaGrad(0.01))
+        if otype:
+            kw["otype"] = otype
+        train, reconstruct, encode, decode, theta = mod.ConstructAE(Xtr, **kw)
+        if otype == "cont":
+            names = ["W3", "b3", "W4", "b4", "W1", "b1", "W2", "W6", "b2", "b6"]
+        else:
+            names = ["W3", "b3", "W4", "b4", "W1", "b1", "W2", "b2"]
+        assert len(theta) == len(names)
+        for t_, n in zip(theta, names):
+            if n.startswith("W"):                         # 0.01-sigma initialisation keeps every tanh linear: scale up
+                t_.set_value(t_.get_value() * 40.0)
+            g["%s__init_%s" % (tag, n)] = t_.get_value().copy()
+        g["%s__x" % tag] = xs.astype(np.float32)
+        idx_rng = np.random.RandomState(77)
+        idxs = [idx_rng.permutation(Ntr)[:10].astype(np.int32) for _ in range(4)] + [np.arange(7, dtype=np.int32)]
+        g["%s__idx" % tag] = np.stack([np.pad(i, (0, 10 - len(i)), constant_values=-1) for i in idxs])
+        g["%s__train_returns" % tag] = np.array([float(train(i)) for i in idxs])
+        for t_, n in zip(theta, names):
+            g["%s__final_%s" % (tag, n)] = t_.get_value().copy()
+        g["%s__reconstruct" % tag] = reconstruct(xs[:6])
+        zz = encode(xs[:6])
+        g["%s__encode" % tag] = zz
+        g["%s__decode" % tag] = decode(zz)
+    np.savez_compressed(os.path.join(HERE, "ref_ae_baselines.npz"), **g)
     print("wrote", sorted(f for f in os.listdir(HERE) if f.startswith("ref_")))
 
 

@@ -83,7 +83,12 @@ class Var(object):
                 lo = None if idx.start is None else int(_ev(idx.start, env))
                 hi = None if idx.stop is None else int(_ev(idx.stop, env))
                 return v[lo:hi]
-            return v[int(_ev(idx, env))] if not isinstance(idx, tuple) else v[idx]
+            if isinstance(idx, tuple):
+                return v[idx]
+            i = _ev(idx, env)
+            if isinstance(i, torch.Tensor) and i.ndim >= 1:          # Xtr[idx] with an ivector: gather of rows
+                return v[i.long()]
+            return v[int(i)]
         return Var(fn)
 
     def sum(self, axis=None, keepdims=False):

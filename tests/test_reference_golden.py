@@ -162,3 +162,37 @@ def test_oracle_matches_reference_ae_primitives():
     np.testing.assert_allclose(objs, g["ag_obj"], rtol=1e-12)
     np.testing.assert_allclose(th[0], g["ag_theta2_0"], rtol=1e-12)
     np.testing.assert_allclose(th[1], g["ag_theta2_1"], rtol=1e-12)
+
+
+def ae_params_from_fixture(c, continuous, prefix):
+    """VAEB-ordered parameter list from a ref_ae_baselines fixture (W5, b5 are not part of an AE: zeros)."""
+    H, Z = c["init_W4"].shape
+    out = []
+    for n in O.param_names(continuous):
+        if n == "W5":
+            out.append(np.zeros((H, Z)))
+        elif n == "b5":
+            out.append(np.zeros(Z))
+        else:
+            out.append(np.array(c[prefix + n], dtype=np.float64))
+    return out
+
+
+@pytest.mark.parametrize("tag,kind,cont", [("deg_binary", "degenerate", False), ("deg_cont", "degenerate", True),
+                                           ("vanilla", "vanilla", False)])
+def test_oracle_matches_reference_ae_baselines(tag, kind, cont):
+    """ConstructAE of degenerate-vae/ae.py:41-117 (binary and cont outputs) and vanilla-ae/ae.py:45-104: five
+    `train(idx)` calls on gathered minibatches (the last one ragged), then reconstruct / encode / decode."""
+    c = _sub(load_golden("ref_ae_baselines.npz"), tag)
+    m = O.OracleAE(c["x"].astype(np.float64), cont, ae_params_from_fixture(c, cont, "init_"), kind=kind)
+    rets = [m.train(row[row >= 0]) for row in c["idx"]]
+    np.testing.assert_allclose(rets, c["train_returns"], rtol=RTOL)
+    for n, p in zip(O.param_names(cont), m.params):
+        if n in ("W5", "b5"):
+            assert not p.any()
+        else:
+            np.testing.assert_allclose(p, c["final_" + n], rtol=1e-8, atol=1e-12, err_msg=n)
+    x6 = c["x"][:6].astype(np.float64)
+    np.testing.assert_allclose(m.forward(x6, "reconstruct"), c["reconstruct"], rtol=1e-10)
+    np.testing.assert_allclose(m.forward(x6, "encode"), c["encode"], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(m.forward(c["encode"], "decode"), c["decode"], rtol=1e-10)

@@ -15,6 +15,7 @@ PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
 # buffers addressable through vaeb_{get,set}_tensors
 BUF_PARAMS, BUF_ADA, BUF_GRADS, BUF_VMU, BUF_VSIG, BUF_ADA_MU, BUF_ADA_SIG, BUF_GMU, BUF_GSIG, BUF_ADA2 = range(10)
 OPT_ADAGRAD, OPT_ADADELTA = 0, 1
+AE_DEGENERATE, AE_VANILLA = 0, 1
 
 
 class Config(C.Structure):
@@ -44,6 +45,8 @@ EXPORTS = {
     "vaeb_update_many": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "vaeb_update_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "vaeb_set_optimizer": (C.c_int, [C.c_void_p, C.c_int32, C.c_float]),
+    "vaeb_ae_train": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_float)]),
+    "vaeb_ae_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "vaeb_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "vaeb_validate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]),
     "vaeb_gradients": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,

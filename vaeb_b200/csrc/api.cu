@@ -685,6 +685,98 @@ int vaeb_update_host(vaeb_handle* h, const float* x, int64_t rows, const float* 
   return read_scalars(h, 1, elbo_out);
 }
 
+int vaeb_ae_train(vaeb_handle* h, int32_t kind, const int32_t* idx, int32_t n, float* out) {
+  VAEB_REQUIRE(h && idx && out && n > 0, "null argument");
+  VAEB_REQUIRE(kind == VAEB_AE_DEGENERATE || kind == VAEB_AE_VANILLA, "unknown AE kind");
+  VAEB_REQUIRE(!(kind == VAEB_AE_VANILLA && h->cont), "the vanilla AE has sigmoid outputs only (vanilla-ae/ae.py:62-67)");
+  VAEB_REQUIRE(h->L == 1 && !is_fvb(h) && h->world == 1, "AE baselines: L = 1, single GPU");
+  if (!h->d_x) { vaeb_set_error("vaeb_ae_train before vaeb_upload_data"); return VAEB_ESTATE; }
+  for (int i = 0; i < n; ++i) VAEB_REQUIRE(idx[i] >= 0 && idx[i] < h->n_data, "row index outside the resident data");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  const Layout& l = h->lay;
+  const int D = h->D, H = h->H, Z = h->Z, rows = n;
+  VAEB_TRY(ensure_ws(h, rows, rows, true));
+  VAEB_TRY(grow(&h->d_stage, &h->stage_cap, (int64_t)rows * D));
+  VAEB_TRY(grow(&h->d_stage2, &h->stage2_cap, (int64_t)rows));            // the row indices (as bits)
+  cudaStream_t st = h->stream;
+  int64_t* lc = &h->launches;
+  Workspace& s = h->ws;
+  float* th = h->d_params;
+  float* gr = h->d_grads;
+  VAEB_CUDA(cudaMemcpyAsync(h->d_stage2, idx, (size_t)rows * sizeof(int), cudaMemcpyHostToDevice, st));
+  VAEB_LAUNCH(launch_gather_rows(st, lc, h->d_x, (const int*)h->d_stage2, rows, D, h->d_stage));
+  const float* x = h->d_stage;
+  // forward (ae.py:48-58)
+  VAEB_LAUNCH(launch_dense_act(st, lc, x, rows, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, 1, s.h_e));
+  VAEB_LAUNCH(launch_dense_act(st, lc, s.h_e, rows, H, T_(h, th, l.iW4), T_(h, th, l.ib4), Z,
+                               kind == VAEB_AE_VANILLA ? 1 : 0, s.z));
+  VAEB_LAUNCH(launch_dense_act(st, lc, s.z, rows, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, 1, s.h_d));
+  int tiles = 0;
+  if (h->cont)     // otype 'cont': OutToProbs mean, OutToReal log-variance, indep_normal (ae.py:64-72) = the Gaussian head
+    VAEB_LAUNCH(launch_dec2_loglik(st, lc, true, s.h_d, rows, H, T_(h, th, l.iW2), T_(h, th, l.ib2), T_(h, th, l.iW6),
+                                   T_(h, th, l.ib6), D, x, 1, rows, 1.0f, s.da2, s.dlv, s.partial, &tiles));
+  else
+    VAEB_LAUNCH(launch_dec2_ae(st, lc, kind == VAEB_AE_VANILLA ? 1 : 0, s.h_d, rows, H, T_(h, th, l.iW2),
+                               T_(h, th, l.ib2), D, x, s.da2, s.partial, &tiles));
+  // backward of logjoint (T.grad inside AdaGrad.construct, infalg.py:156)
+  VAEB_CUDA(cudaMemsetAsync(gr, 0, (size_t)(l.padded + 4) * sizeof(float), st));     // W5, b5 are not part of theta
+  VAEB_LAUNCH(launch_wgrad(st, lc, s.h_d, rows, H, s.da2, D, T_(h, gr, l.iW2), T_(h, gr, l.ib2)));
+  if (h->cont) VAEB_LAUNCH(launch_wgrad(st, lc, s.h_d, rows, H, s.dlv, D, T_(h, gr, l.iW6), T_(h, gr, l.ib6)));
+  VAEB_LAUNCH(launch_dgrad_tanh(st, lc, s.da2, T_(h, th, l.iW2), h->cont ? s.dlv : nullptr,
+                                h->cont ? T_(h, th, l.iW6) : nullptr, rows, D, H, s.h_d, s.da1));
+  VAEB_LAUNCH(launch_wgrad(st, lc, s.z, rows, Z, s.da1, H, T_(h, gr, l.iW1), T_(h, gr, l.ib1)));
+  if (kind == VAEB_AE_VANILLA) {   // through Z = tanh(.)
+    VAEB_LAUNCH(launch_dgrad_tanh(st, lc, s.da1, T_(h, th, l.iW1), nullptr, nullptr, rows, H, Z, s.z, s.dmu));
+  } else {                         // + d/dZ of ConstructNormalPrior([Z], 1.0) = -Z   (ae.py:77)
+    VAEB_LAUNCH(launch_dgrad(st, lc, s.da1, T_(h, th, l.iW1), rows, H, Z, s.dmu));
+    VAEB_LAUNCH(launch_axpy(st, lc, s.dmu, s.z, -1.0f, (int64_t)rows * Z));
+  }
+  VAEB_LAUNCH(launch_wgrad(st, lc, s.h_e, rows, H, s.dmu, Z, T_(h, gr, l.iW4), T_(h, gr, l.ib4)));
+  VAEB_LAUNCH(launch_dgrad_tanh(st, lc, s.dmu, T_(h, th, l.iW4), nullptr, nullptr, rows, Z, H, s.h_e, s.da3));
+  VAEB_LAUNCH(launch_wgrad(st, lc, x, rows, D, s.da3, H, T_(h, gr, l.iW3), T_(h, gr, l.ib3)));
+  // reported value: loglik / n (ae.py:81) or se / n (vanilla-ae/ae.py:79); row_aux = 0: no latent term in it
+  VAEB_CUDA(cudaMemsetAsync(s.row_aux, 0, (size_t)rows * sizeof(float), st));
+  float* base = gr + l.padded;
+  VAEB_LAUNCH(launch_finalize(st, lc, s.partial, tiles, s.row_aux, rows, 1, s.per_row, base,
+                              kind == VAEB_AE_VANILLA ? -1.0f : 1.0f, nullptr, 0, (float)rows, h->d_scalars));
+  // AdaGrad ascent with the weight prior -p/s2 folded in (mlp.py:87-91; infalg.py:157-162)
+  VAEB_LAUNCH(launch_adagrad(st, lc, th, h->d_ada, gr, l.padded / 4, h->cfg.learning_rate, h->cfg.adagrad_eps,
+                             h->cfg.prior_scale, 0.f, base, 1.0f, 1.0f, nullptr));
+  h->grads_have_prior = false;
+  return read_scalars(h, 1, out);
+}
+
+int vaeb_ae_forward(vaeb_handle* h, int32_t kind, int32_t what, const float* in, int64_t rows, float* out) {
+  VAEB_REQUIRE(h && in && out && rows > 0, "null argument");
+  VAEB_REQUIRE(kind == VAEB_AE_DEGENERATE || kind == VAEB_AE_VANILLA, "unknown AE kind");
+  VAEB_REQUIRE(what >= 0 && what <= 2, "what: 0 reconstruct, 1 encode, 2 decode");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  const Layout& l = h->lay;
+  const int D = h->D, H = h->H, Z = h->Z, r = (int)rows;
+  VAEB_TRY(ensure_ws(h, rows, rows, false));
+  const int in_w = what == 2 ? Z : D, out_w = what == 1 ? Z : D;
+  VAEB_TRY(stage_in(h, &h->d_stage, &h->stage_cap, in, rows * in_w));
+  VAEB_TRY(grow(&h->d_out, &h->out_cap, rows * out_w));
+  cudaStream_t st = h->stream;
+  int64_t* lc = &h->launches;
+  Workspace& s = h->ws;
+  const float* th = h->d_params;
+  const float* z = h->d_stage;
+  if (what != 2) {
+    VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage, r, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, 1, s.h_e));
+    VAEB_LAUNCH(launch_dense_act(st, lc, s.h_e, r, H, T_(h, th, l.iW4), T_(h, th, l.ib4), Z,
+                                 kind == VAEB_AE_VANILLA ? 1 : 0, what == 1 ? h->d_out : s.z));
+    z = s.z;
+  }
+  if (what != 1) {
+    VAEB_LAUNCH(launch_dense_act(st, lc, z, r, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, 1, s.h_d));
+    VAEB_LAUNCH(launch_dense_act(st, lc, s.h_d, r, H, T_(h, th, l.iW2), T_(h, th, l.ib2), D, 2, h->d_out));   // OutToProbs
+  }
+  VAEB_CUDA(cudaMemcpyAsync(out, h->d_out, (size_t)rows * out_w * sizeof(float), cudaMemcpyDeviceToHost, st));
+  VAEB_CUDA(cudaStreamSynchronize(st));
+  return VAEB_OK;
+}
+
 int vaeb_set_optimizer(vaeb_handle* h, int32_t optimizer, float rho) {
   VAEB_REQUIRE(h, "null handle");
   VAEB_REQUIRE(optimizer == VAEB_OPT_ADAGRAD || optimizer == VAEB_OPT_ADADELTA, "unknown optimizer");

@@ -96,6 +96,32 @@ struct EpiGaussian {
   }
 };
 
+// AE baselines: logpdf.bernoulli with 1e-7 inside both logs (degenerate-vae/logpdf.py:85-86, ae.py:62):
+// term = x log(P+e) + (1-x) log(1-P+e), P = sigmoid(a); d_a = (x/(P+e) - (1-x)/(1-P+e)) P (1-P)
+struct EpiBernoulliClamp {
+  static constexpr bool kRowReduce = true;
+  const float* bias; const float* x; int ldx; float* da; int ldda;
+  __device__ __forceinline__ float operator()(int m, int n, float acc, float) const {
+    const float a = acc + bias[n];
+    const float xv = x[(size_t)m * ldx + n];
+    const float P = sigmoidf(a), Q = sigmoidf(-a);           // Q = 1 - P without cancellation
+    if (da) da[(size_t)m * ldda + n] = (xv / (P + 1e-7f) - (1.0f - xv) / (Q + 1e-7f)) * P * Q;
+    return xv * logf(P + 1e-7f) + (1.0f - xv) * logf(Q + 1e-7f);
+  }
+};
+// vanilla AE (vanilla-ae/ae.py:66-72): term = -(x - P)^2 (the row sums give -se); d_a = 2 (x - P) P (1-P)
+struct EpiSquaredError {
+  static constexpr bool kRowReduce = true;
+  const float* bias; const float* x; int ldx; float* da; int ldda;
+  __device__ __forceinline__ float operator()(int m, int n, float acc, float) const {
+    const float a = acc + bias[n];
+    const float xv = x[(size_t)m * ldx + n];
+    const float P = sigmoidf(a), d = xv - P;
+    if (da) da[(size_t)m * ldda + n] = 2.0f * d * P * sigmoidf(-a);
+    return -d * d;
+  }
+};
+
 // reconstruct (VAEB.py:282-292): y += sigmoid(a)/n, lv += lv/n
 struct EpiReconAccum {
   static constexpr bool kRowReduce = false;

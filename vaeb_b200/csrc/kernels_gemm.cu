@@ -54,6 +54,18 @@ cudaError_t launch_dec2_loglik(cudaStream_t st, int64_t* launches, bool continuo
   return run_gemm<false, false, false, false, false>(st, launches, g, epi, partial, n_col_tiles, fixed_tiles);
 }
 
+cudaError_t launch_dec2_ae(cudaStream_t st, int64_t* launches, int mode, const float* h_d, int rows, int H,
+                           const float* W2, const float* b2, int D, const float* x, float* da, float* partial,
+                           int* n_col_tiles) {
+  GemmOperands g{h_d, W2, nullptr, nullptr, H, D, rows, D, H};
+  if (mode == 1) {
+    EpiSquaredError epi{b2, x, D, da, D};
+    return run_gemm<false, false, false, false, false>(st, launches, g, epi, partial, n_col_tiles);
+  }
+  EpiBernoulliClamp epi{b2, x, D, da, D};
+  return run_gemm<false, false, false, false, false>(st, launches, g, epi, partial, n_col_tiles);
+}
+
 cudaError_t launch_dec2_recon(cudaStream_t st, int64_t* launches, bool continuous, const float* h_d, int rows,
                               int H, const float* W2, const float* b2, const float* W6, const float* b6, int D,
                               float* y, float* lv, float inv_n, int first) {

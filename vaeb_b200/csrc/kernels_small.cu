@@ -333,6 +333,20 @@ __global__ void philox_fill_kernel(uint64_t seed, uint32_t stream, uint32_t step
   out[i] = philox_normal1(seed, stream, step, sample, (uint64_t)(first + i));
 }
 
+// out[i, :] = src[idx[i], :]   (ae.py:83 `givens = { X : Xtr[idx] }`: minibatches are gathered, not sliced)
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, int n, int D, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n * D) return;
+  const int r = (int)(i / D), c = (int)(i - (int64_t)r * D);
+  out[i] = src[(size_t)idx[r] * D + c];
+}
+__global__ void __launch_bounds__(256)
+axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float a, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fmaf(a, x[i], y[i]);
+}
+
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace
@@ -393,6 +407,16 @@ cudaError_t launch_add_prior(cudaStream_t st, int64_t* launches, float* g, const
                              const float* base, float mult, float div, float* scalar_out) {
   add_prior_kernel<<<blocks_for(n4, 256), 256, 0, st>>>((float4*)g, (const float4*)p, n4, prior, base, mult, div,
                                                         scalar_out);
+  return LAUNCHED();
+}
+
+cudaError_t launch_gather_rows(cudaStream_t st, int64_t* launches, const float* src, const int* idx, int n, int D,
+                               float* out) {
+  gather_rows_kernel<<<blocks_for((int64_t)n * D, 256), 256, 0, st>>>(src, idx, n, D, out);
+  return LAUNCHED();
+}
+cudaError_t launch_axpy(cudaStream_t st, int64_t* launches, float* y, const float* x, float a, int64_t n) {
+  axpy_kernel<<<blocks_for(n, 256), 256, 0, st>>>(y, x, a, n);
   return LAUNCHED();
 }
 

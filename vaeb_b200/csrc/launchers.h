@@ -15,6 +15,11 @@ cudaError_t launch_dec2_loglik(cudaStream_t st, int64_t* launches, bool continuo
                                int H, const float* W2, const float* b2, const float* W6, const float* b6, int D,
                                const float* x, int x_div, int x_mod, float scale, float* da, float* dlv,
                                float* partial, int* n_col_tiles, bool fixed_tiles = false);
+// AE baselines: decoder output layer fused with logpdf.bernoulli (mode 0, 1e-7 clamp; logpdf.py:85-86) or the
+// squared error of vanilla-ae/ae.py:66 (mode 1, row sums = -se); da == nullptr: evaluation only
+cudaError_t launch_dec2_ae(cudaStream_t st, int64_t* launches, int mode, const float* h_d, int rows, int H,
+                           const float* W2, const float* b2, int D, const float* x, float* da, float* partial,
+                           int* n_col_tiles);
 // reconstruct accumulation (VAEB.py:282-292)
 cudaError_t launch_dec2_recon(cudaStream_t st, int64_t* launches, bool continuous, const float* h_d, int rows,
                               int H, const float* W2, const float* b2, const float* W6, const float* b6, int D,
@@ -58,6 +63,9 @@ cudaError_t launch_finalize(cudaStream_t st, int64_t* launches, const float* par
 // logw[r] = sum_t partial[r,t] + aux[r];  logp[i] = logsumexp_l logw[i*L+l] - log L
 cudaError_t launch_is_reduce(cudaStream_t st, int64_t* launches, const float* partial, int n_tiles,
                              const float* aux, int n, int L, float* logw, float* logp);
+cudaError_t launch_gather_rows(cudaStream_t st, int64_t* launches, const float* src, const int* idx, int n, int D,
+                               float* out);
+cudaError_t launch_axpy(cudaStream_t st, int64_t* launches, float* y, const float* x, float a, int64_t n);
 // g -= prior*p  (VAEB.py:389-390); thread 0 also writes (mult*base)/div to scalar_out if non-null
 cudaError_t launch_add_prior(cudaStream_t st, int64_t* launches, float* g, const float* p, int64_t n4, float prior,
                              const float* base, float mult, float div, float* scalar_out);
