@@ -211,9 +211,20 @@ def run_own(args):
     model.update_many(order(W))
     # GPU clocks ramp up lazily: keep the device busy for ~1 s before timing (measured: the first 3000
     # updates after a cold start run 10-70% slower than steady state on this pool's B200s)
+    # Warm-up continues until two consecutive 1000-update probes agree within 3 % (at least 1 s, at most 6 s).
     t_ramp = time.perf_counter()
-    while time.perf_counter() - t_ramp < 1.0:
+    probe, last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prev_ms = None
+    while True:
+        probe.record(stream)
         model.update_many(order(1000))
+        last.record(stream)
+        torch.cuda.synchronize()
+        cur_ms = probe.elapsed_time(last)
+        el = time.perf_counter() - t_ramp
+        if (el >= 1.0 and prev_ms is not None and abs(cur_ms - prev_ms) <= 0.03 * prev_ms) or el >= 6.0:
+            break
+        prev_ms = cur_ms
     barrier()
     l0 = model.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -471,6 +471,8 @@ int load_nccl(NcclApi& api, const char* path) {
 
 extern "C" {
 
+static int async_flush(vaeb_handle* h);   // launches streaming updates that were copied but not yet started
+
 const char* vaeb_last_error(void) { return g_last_error.c_str(); }
 int vaeb_version(void) { return 100; }
 
@@ -560,6 +562,7 @@ int vaeb_destroy(vaeb_handle* h) {
       cudaEventDestroy(h->a_consumed[i]);
     }
     if (h->h_async) cudaFreeHost(h->h_async);
+    if (h->d_iota) cudaFree(h->d_iota);
     cudaStreamDestroy(h->copy_stream);
   }
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -595,6 +598,7 @@ int vaeb_tensor_shape(vaeb_handle* h, int32_t i, int32_t* rows, int32_t* cols) {
 }
 
 int vaeb_set_tensors(vaeb_handle* h, int32_t which, const float* const* tensors) {
+  if (h && h->a_pending) VAEB_TRY(async_flush(h));
   VAEB_REQUIRE(h && tensors, "null argument");
   float* flat = flat_by_which(h, which);
   VAEB_REQUIRE(flat, "buffer not available for this estimator");
@@ -608,6 +612,7 @@ int vaeb_set_tensors(vaeb_handle* h, int32_t which, const float* const* tensors)
 }
 
 int vaeb_get_tensors(vaeb_handle* h, int32_t which, float* const* tensors) {
+  if (h && h->a_pending) VAEB_TRY(async_flush(h));
   VAEB_REQUIRE(h && tensors, "null argument");
   float* flat = flat_by_which(h, which);
   VAEB_REQUIRE(flat, "buffer not available for this estimator");
@@ -659,6 +664,7 @@ static int stage_eps_zeta(vaeb_handle* h, const float* eps, int64_t n_eps, const
 }
 
 int vaeb_update(vaeb_handle* h, int64_t index, const float* eps, float* elbo_out) {
+  if (h && h->a_pending) VAEB_TRY(async_flush(h));
   VAEB_REQUIRE(h && elbo_out, "null argument");
   if (!h->d_x) { vaeb_set_error("vaeb_update before vaeb_upload_data"); return VAEB_ESTATE; }
   VAEB_REQUIRE(index >= 0 && (index + 1) * (int64_t)h->M <= h->n_data, "batch index outside the resident data");
@@ -673,6 +679,7 @@ int vaeb_update(vaeb_handle* h, int64_t index, const float* eps, float* elbo_out
 }
 
 int vaeb_update_host(vaeb_handle* h, const float* x, int64_t rows, const float* eps, float* elbo_out) {
+  if (h && h->a_pending) VAEB_TRY(async_flush(h));
   VAEB_REQUIRE(h && x && elbo_out && rows > 0, "null argument");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
   VAEB_TRY(stage_in(h, &h->d_stage, &h->stage_cap, x, rows * h->D));
@@ -794,11 +801,36 @@ int vaeb_set_optimizer(vaeb_handle* h, int32_t optimizer, float rho) {
   return VAEB_OK;
 }
 
+// Launches the minibatches copied into the current group buffer: ONE fused-kernel launch for up to ASYNC_GROUP
+// updates (per-layer kernels otherwise), then the readback of their bounds.
+static int async_flush(vaeb_handle* h) {
+  if (h->a_pending == 0) return VAEB_OK;
+  const int g = h->a_group, n = h->a_pending;
+  const int rows = (int)h->a_rows;
+  const int slot0 = h->a_outstanding - n;
+  VAEB_CUDA(cudaEventRecord(h->a_copied[g], h->copy_stream));
+  VAEB_CUDA(cudaStreamWaitEvent(h->stream, h->a_copied[g], 0));
+  if (fused_step_supported(h, rows)) {
+    VAEB_TRY(ensure_ws(h, rows, rows, true));
+    VAEB_TRY(fused_step_launch(h, h->d_iota, h->a_stage[g], rows, n, nullptr, slot0, nullptr));
+  } else {
+    for (int i = 0; i < n; ++i)
+      VAEB_TRY(enqueue_update(h, h->a_stage[g] + (size_t)i * rows * h->D, rows, nullptr, nullptr, slot0 + i, true));
+  }
+  VAEB_CUDA(cudaEventRecord(h->a_consumed[g], h->stream));
+  VAEB_CUDA(cudaMemcpyAsync(h->h_async + slot0, h->d_scalars + slot0, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost,
+                            h->stream));
+  h->a_used[g] = true;
+  h->a_pending = 0;
+  h->a_group = (g + 1) % vaeb_handle::ASYNC_BUFS;
+  return VAEB_OK;
+}
+
 int vaeb_update_host_async(vaeb_handle* h, const float* x, int64_t rows) {
   VAEB_REQUIRE(h && x && rows > 0, "null argument");
   VAEB_REQUIRE(h->world == 1, "the streaming update is single-GPU (use vaeb_update for data-parallel steps)");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
-  constexpr int NB = vaeb_handle::ASYNC_BUFS;
+  constexpr int NB = vaeb_handle::ASYNC_BUFS, GROUP = vaeb_handle::ASYNC_GROUP;
   constexpr int MAX_OUT = 8192;
   const int64_t n = rows * h->D;
   if (!h->copy_stream) {
@@ -809,37 +841,35 @@ int vaeb_update_host_async(vaeb_handle* h, const float* x, int64_t rows) {
     }
     VAEB_CUDA(cudaMallocHost((void**)&h->h_async, (size_t)MAX_OUT * sizeof(float)));
     h->h_async_cap = MAX_OUT;
+    const int iota[GROUP] = {0, 1, 2, 3};
+    VAEB_CUDA(cudaMalloc((void**)&h->d_iota, sizeof(iota)));
+    VAEB_CUDA(cudaMemcpy(h->d_iota, iota, sizeof(iota), cudaMemcpyHostToDevice));
   }
   VAEB_REQUIRE(h->a_outstanding < h->h_async_cap, "too many uncollected updates: call vaeb_collect");
+  if (h->a_pending > 0 && rows != h->a_rows) VAEB_TRY(async_flush(h));     // a group holds minibatches of one size
   if (n > h->a_stage_cap) {
+    VAEB_TRY(async_flush(h));
     VAEB_CUDA(cudaStreamSynchronize(h->copy_stream));
     VAEB_CUDA(cudaStreamSynchronize(h->stream));
     for (int i = 0; i < NB; ++i) {
       if (h->a_stage[i]) VAEB_CUDA(cudaFree(h->a_stage[i]));
       h->a_stage[i] = nullptr;
-      VAEB_CUDA(cudaMalloc((void**)&h->a_stage[i], (size_t)n * sizeof(float)));
+      VAEB_CUDA(cudaMalloc((void**)&h->a_stage[i], (size_t)GROUP * n * sizeof(float)));
       h->a_used[i] = false;
     }
     h->a_stage_cap = n;
   }
   VAEB_TRY(ensure_scalars(h, h->h_async_cap));
-  const int b = (int)(h->a_submitted % NB);
-  const int slot = h->a_outstanding;
-  // copy stream: wait until the kernel that last read this staging buffer is done, then H2D
-  if (h->a_used[b]) VAEB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->a_consumed[b], 0));
-  VAEB_CUDA(cudaMemcpyAsync(h->a_stage[b], x, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
-  VAEB_CUDA(cudaEventRecord(h->a_copied[b], h->copy_stream));
-  // compute stream: the update, then the 4-byte readback of its bound
-  VAEB_CUDA(cudaStreamWaitEvent(h->stream, h->a_copied[b], 0));
-  if (fused_step_supported(h, (int)rows))
-    VAEB_TRY(fused_updates(h, nullptr, h->a_stage[b], (int)rows, 1, nullptr, slot));
-  else
-    VAEB_TRY(enqueue_update(h, h->a_stage[b], (int)rows, nullptr, nullptr, slot, true));
-  VAEB_CUDA(cudaEventRecord(h->a_consumed[b], h->stream));
-  VAEB_CUDA(cudaMemcpyAsync(h->h_async + slot, h->d_scalars + slot, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-  h->a_used[b] = true;
+  const int g = h->a_group;
+  // copy stream: before the first copy into a group buffer, wait for the kernel that last read it
+  if (h->a_pending == 0 && h->a_used[g]) VAEB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->a_consumed[g], 0));
+  VAEB_CUDA(cudaMemcpyAsync(h->a_stage[g] + (size_t)h->a_pending * n, x, (size_t)n * sizeof(float),
+                            cudaMemcpyHostToDevice, h->copy_stream));
+  h->a_rows = rows;
+  ++h->a_pending;
   ++h->a_submitted;
   ++h->a_outstanding;
+  if (h->a_pending == GROUP) VAEB_TRY(async_flush(h));
   return VAEB_OK;
 }
 
@@ -847,6 +877,7 @@ int vaeb_collect(vaeb_handle* h, int32_t* n_inout, float* elbo_out) {
   VAEB_REQUIRE(h && n_inout && elbo_out, "null argument");
   VAEB_REQUIRE(*n_inout >= h->a_outstanding, "elbo_out is smaller than the number of outstanding updates");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  VAEB_TRY(async_flush(h));
   VAEB_CUDA(cudaStreamSynchronize(h->stream));
   std::memcpy(elbo_out, h->h_async, (size_t)h->a_outstanding * sizeof(float));
   *n_inout = h->a_outstanding;
@@ -855,6 +886,7 @@ int vaeb_collect(vaeb_handle* h, int32_t* n_inout, float* elbo_out) {
 }
 
 int vaeb_update_many(vaeb_handle* h, const int32_t* batch_order, int32_t n, float* elbo_out) {
+  if (h && h->a_pending) VAEB_TRY(async_flush(h));
   VAEB_REQUIRE(h && batch_order && elbo_out && n > 0, "null argument");
   if (!h->d_x) { vaeb_set_error("vaeb_update_many before vaeb_upload_data"); return VAEB_ESTATE; }
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
@@ -876,6 +908,7 @@ int vaeb_update_many(vaeb_handle* h, const int32_t* batch_order, int32_t n, floa
 
 int vaeb_gradients(vaeb_handle* h, const float* x, int64_t rows, int64_t index, const float* eps, const float* zeta,
                    float* sgvb_out, float* per_row_out) {
+  if (h && h->a_pending) VAEB_TRY(async_flush(h));
   VAEB_REQUIRE(h && rows > 0, "null argument");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
   const float* d_x;
@@ -925,6 +958,7 @@ int vaeb_apply_update(vaeb_handle* h) {
 }
 
 int vaeb_validate(vaeb_handle* h, const float* x, int64_t n, const float* eps, float* sgvb_out, float* per_row_out) {
+  if (h && h->a_pending) VAEB_TRY(async_flush(h));
   VAEB_REQUIRE(h && x && sgvb_out && n > 0, "null argument");
   VAEB_REQUIRE(n * (int64_t)h->L < (int64_t)1 << 31, "too many rows for one validate call");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));

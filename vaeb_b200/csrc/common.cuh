@@ -125,6 +125,9 @@ struct vaeb_handle {
   float* a_stage[ASYNC_BUFS] = {nullptr, nullptr, nullptr, nullptr}; int64_t a_stage_cap = 0;
   cudaEvent_t a_copied[ASYNC_BUFS] = {}, a_consumed[ASYNC_BUFS] = {};
   bool a_used[ASYNC_BUFS] = {false, false, false, false};
+  static constexpr int ASYNC_GROUP = 4;                   // updates per launch of the fused kernel
+  int a_pending = 0, a_group = 0; int64_t a_rows = 0;     // minibatches copied but not yet launched; current group buffer
+  int* d_iota = nullptr;                                  // {0, 1, .., ASYNC_GROUP-1}: slot order inside a group buffer
   int64_t a_submitted = 0; int a_outstanding = 0;
   float* h_async = nullptr; int h_async_cap = 0;          // pinned host landing zone of the bounds
   float* d_stage2 = nullptr; int64_t stage2_cap = 0;     // eps staging

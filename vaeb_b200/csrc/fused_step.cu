@@ -823,7 +823,9 @@ int fused_step_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, 
   p.oW3 = l.off[l.iW3]; p.oW4 = l.off[l.iW4]; p.oW5 = l.off[l.iW5]; p.oW1 = l.off[l.iW1]; p.oW2 = l.off[l.iW2];
   p.ob3 = l.off[l.ib3]; p.ob4 = l.off[l.ib4]; p.ob5 = l.off[l.ib5]; p.ob1 = l.off[l.ib1]; p.ob2 = l.off[l.ib2];
   p.oW6 = h->cont ? l.off[l.iW6] : 0; p.ob6 = h->cont ? l.off[l.ib6] : 0;
-  p.x_base = h->d_x; p.batch_order = d_order; p.x_direct = d_xrows;
+  // rows of step s: batch_order[s] * M rows into the resident data -- or into d_xrows when both are given
+  // (the staging ring of the streaming host-input updates) -- else d_xrows itself for every step
+  p.x_base = (d_order && d_xrows) ? d_xrows : h->d_x; p.batch_order = d_order; p.x_direct = d_xrows;
   p.eps_inj = d_eps;
   p.seed = h->cfg.seed; p.step0 = h->step; p.row_offset = 0;
   p.h_e = s.h_e; p.mu = s.mu; p.ls = s.ls; p.eps = s.eps; p.z = s.z; p.h_d = s.h_d;
