@@ -176,6 +176,18 @@ int tc_ensure(vaeb_handle* h, int64_t rows, int64_t R) {
     VAEB_LAUNCH(tc_split_matrix(h->stream, &h->launches, nullptr, R, 0, 0, b.hdh, b.hdl, b.ldh, H));
     VAEB_CUDA(cudaMemsetAsync(b.da2h, 0, (size_t)R * b.ldd * 2, h->stream));
     if (lo) VAEB_CUDA(cudaMemsetAsync(b.da2l, 0, (size_t)R * b.ldd * 2, h->stream));
+    if (latent_large_batch((int)rows, H, h->Z, (int)(R / std::max<int64_t>(rows, 1)))) {
+      VAEB_TRY(grow_bytes(&b.d1h, (size_t)R * b.ldh * 2));
+      VAEB_TRY(grow_bytes(&b.zh, (size_t)R * b.ldz * 2));
+      VAEB_CUDA(cudaMemsetAsync(b.d1h, 0, (size_t)R * b.ldh * 2, h->stream));
+      if (lo) {
+        VAEB_TRY(grow_bytes(&b.d1l, (size_t)R * b.ldh * 2));
+        VAEB_TRY(grow_bytes(&b.zl, (size_t)R * b.ldz * 2));
+        VAEB_CUDA(cudaMemsetAsync(b.d1l, 0, (size_t)R * b.ldh * 2, h->stream));
+      }
+      // zero padding + the ones column at Z (bias row of the W1 weight-gradient GEMM)
+      VAEB_LAUNCH(tc_split_matrix(h->stream, &h->launches, nullptr, R, 0, 0, b.zh, b.zl, b.ldz, h->Z));
+    }
     t.cap_R = R;
     t.key_rows = -1;
   }
@@ -186,6 +198,18 @@ int tc_ensure(vaeb_handle* h, int64_t rows, int64_t R) {
     if (lo) {
       VAEB_TRY(grow_bytes(&b.da3l, (size_t)rows * b.ldh * 2));
       VAEB_CUDA(cudaMemsetAsync(b.da3l, 0, (size_t)rows * b.ldh * 2, h->stream));
+    }
+    if (latent_large_batch((int)rows, H, h->Z, 1)) {
+      VAEB_TRY(grow_bytes(&b.heh, (size_t)rows * b.ldh * 2));
+      VAEB_TRY(grow_bytes(&b.ddh, (size_t)rows * b.ldq * 2));
+      VAEB_CUDA(cudaMemsetAsync(b.ddh, 0, (size_t)rows * b.ldq * 2, h->stream));
+      if (lo) {
+        VAEB_TRY(grow_bytes(&b.hel, (size_t)rows * b.ldh * 2));
+        VAEB_TRY(grow_bytes(&b.ddl, (size_t)rows * b.ldq * 2));
+        VAEB_CUDA(cudaMemsetAsync(b.ddl, 0, (size_t)rows * b.ldq * 2, h->stream));
+      }
+      // zero padding + the ones column at H (bias row of the W4|W5 weight-gradient GEMM)
+      VAEB_LAUNCH(tc_split_matrix(h->stream, &h->launches, nullptr, rows, 0, 0, b.heh, b.hel, b.ldh, H));
     }
     t.cap_rows = rows;
     t.key_rows = -1;
@@ -242,7 +266,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
       rows_data = rows;
     }
     if (t.key_rows != rows || t.key_R != R || t.key_data != rows_data || t.key_bn != bn || t.key_x != b.xh) {
-      VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bn));
+      VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bn, Z));
       t.key_rows = rows; t.key_R = R; t.key_data = rows_data; t.key_bn = bn; t.key_x = b.xh;
     }
     PH("mirror W3,W2 -> bf16", 0, 12.0 * dD * dH,
@@ -250,10 +274,14 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
                          b.ldd));
   }
   const TcBuffers& tb = t.data;
+  // large-batch training on the tensor-core path: the thin weight gradients also run on tcgen05 (their operands'
+  // bf16 mirrors come from the kernels that produce h_e, z, da1 and [dmu|dls])
+  const bool tcl = tcp && want_grads && tb.heh && tb.zh && tb.d1h && tb.ddh && latent_large_batch(rows, H, Z, L);
   // encoder hidden layer, VAEB.py:246
   if (tcp)
     PH("enc1 x.W3+tanh [tcgen05]", 2 * dr * dD * dH, 2.0 * t.ns * (dr * dD + dD * dH) + 4 * dr * dH,
-       tc_enc1(st, lc, t.maps, t.ns, bn, rows, D, H, x_row_off, T_(h, theta, l.ib3), s.h_e));
+       tc_enc1(st, lc, t.maps, t.ns, bn, rows, D, H, x_row_off, T_(h, theta, l.ib3), s.h_e, tcl ? tb.heh : nullptr,
+               tcl ? tb.hel : nullptr, tb.ldh));
   else
     PH("enc1 x.W3+tanh", 2 * dr * dD * dH, 4 * (dr * dD + dD * dH + dr * dH),
        launch_dense_act(st, lc, x, rows, D, T_(h, theta, l.iW3), T_(h, theta, l.ib3), H, 1, s.h_e));
@@ -264,7 +292,8 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
      4 * (dr * dH + 3 * dH * dZ + 2 * dr * dZ + 2 * dR * dZ + dR * dH),
      launch_latent_fwd(st, lc, s.h_e, rows, H, h->d_w45t, T_(h, theta, l.ib4),
                        T_(h, theta, l.ib5), T_(h, theta, l.iW1), T_(h, theta, l.ib1), Z, L, la, src, s.mu, s.ls,
-                       s.eps, s.z, s.row_aux, s.h_d, tcp ? tb.hdh : nullptr, tcp ? tb.hdl : nullptr, tb.ldh));
+                       s.eps, s.z, s.row_aux, s.h_d, tcp ? tb.hdh : nullptr, tcp ? tb.hdl : nullptr, tb.ldh,
+                       tcl ? tb.zh : nullptr, tcl ? tb.zl : nullptr, tb.ldz));
   // decoder output layer + log-likelihood, VAEB.py:257-263,302-313
   const float scale = w / (float)L;
   const float* W6 = h->cont ? T_(h, theta, l.iW6) : nullptr;
@@ -291,7 +320,8 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
     PH("wgrad W2,b2 [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dH + dR * dD) + 4 * dH * dD,
        tc_wgrad2(st, lc, t.maps, t.ns, bn, R, H, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2), tb.wg_scratch));
     PH("dgrad h_d (.W2^T)*(1-h^2) [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dD + dH * dD) + 8 * dR * dH,
-       tc_dgrad_hd(st, lc, t.maps, t.ns, bn, R, D, H, s.h_d, s.da1));
+       tc_dgrad_hd(st, lc, t.maps, t.ns, bn, R, D, H, s.h_d, s.da1, tcl ? tb.d1h : nullptr, tcl ? tb.d1l : nullptr,
+                   tb.ldh));
   } else {
     PH("wgrad W2,b2", 2 * dR * dH * dD, 4 * (dR * dH + dR * dD + dH * dD),
        launch_wgrad(st, lc, s.h_d, R, H, s.da2, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2)));
@@ -307,7 +337,14 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
                        s.mu, s.ls, rows, H, Z, L, la, w, s.dmu, s.dls, s.da3, tcp ? tb.da3h : nullptr,
                        tcp ? tb.da3l : nullptr, tb.ldh, s.partial, tiles,
                        s.row_aux, s.per_row, h->d_counter, bo.base_out, bo.mult, bo.tprior, bo.n_tprior, bo.div,
-                       bo.scalar_out));
+                       bo.scalar_out, tcl ? tb.ddh : nullptr, tcl ? tb.ddl : nullptr, tb.ldq));
+  if (tcl) {
+    PH("wgrad W1,b1 [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * 32 + dR * dH) + 4 * dZ * dH,
+       tc_wgrad1(st, lc, t.maps, t.ns, bn, R, Z, H, T_(h, grads, l.iW1), T_(h, grads, l.ib1), tb.wg_scratch));
+    PH("wgrad W4,b4,W5,b5 [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * dH + dr * 64) + 8 * dZ * dH,
+       tc_wgrad45(st, lc, t.maps, t.ns, rows, H, Z, T_(h, grads, l.iW4), T_(h, grads, l.ib4), T_(h, grads, l.iW5),
+                  T_(h, grads, l.ib5), tb.wg_scratch));
+  } else
   PH("wgrad W1,b1,W4,b4,W5,b5", 2 * dR * dZ * dH + 4 * dr * dH * dZ,
      4 * (dR * dZ + dR * dH + dr * dH + 2 * dr * dZ + 3 * dH * dZ),
      launch_small_wgrad(st, lc, s.z, s.da1, R, s.h_e, s.dmu, s.dls, rows, H, Z, T_(h, grads, l.iW1),
@@ -549,7 +586,8 @@ int vaeb_destroy(vaeb_handle* h) {
   }
   {
     TcBuffers& b = h->tc.data;
-    void* tb[] = {b.xh, b.xl, b.w3h, b.w3l, b.w2h, b.w2l, b.hdh, b.hdl, b.da2h, b.da2l, b.da3h, b.da3l, h->tc.xsh, h->tc.xsl, b.wg_scratch};
+    void* tb[] = {b.xh, b.xl, b.w3h, b.w3l, b.w2h, b.w2l, b.hdh, b.hdl, b.da2h, b.da2l, b.da3h, b.da3l, h->tc.xsh, h->tc.xsl, b.wg_scratch,
+                  b.heh, b.hel, b.d1h, b.d1l, b.zh, b.zl, b.ddh, b.ddl};
     for (void* q : tb) if (q) cudaFree(q);
   }
   if (h->h_scalars) cudaFreeHost(h->h_scalars);

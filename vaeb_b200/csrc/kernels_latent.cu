@@ -427,7 +427,8 @@ lb_latent_fwd_kernel(const float* __restrict__ h_e, int rows, int H, const float
                      const float* __restrict__ b1, int Z, int la, EpsSource src, float* __restrict__ mu,
                      float* __restrict__ ls, float* __restrict__ eps, float* __restrict__ z,
                      float* __restrict__ row_aux, float* __restrict__ h_d, __nv_bfloat16* __restrict__ hd_hi,
-                     __nv_bfloat16* __restrict__ hd_lo, int ld_mirror) {
+                     __nv_bfloat16* __restrict__ hd_lo, int ld_mirror, __nv_bfloat16* __restrict__ z_hi,
+                     __nv_bfloat16* __restrict__ z_lo, int ldz) {
   __shared__ __align__(16) float hs[LB_ROWS][LB_KC + 1];
   __shared__ __align__(16) float ws[LB_KC][LB_WS];
   __shared__ __align__(16) float outs[LB_ROWS][LB_NC];
@@ -500,6 +501,7 @@ lb_latent_fwd_kernel(const float* __restrict__ h_e, int rows, int H, const float
           const float zv = am + expf(0.5f * al) * e;
           mu[o2] = am; ls[o2] = al; eps[o2] = e; z[o2] = zv;
           zs[rr][j] = zv;
+          if (z_hi) store_split(z_hi, z_lo, (size_t)m * ldz + j, zv);
           term += la ? (-0.5f * zv * zv + 0.5f * al + 0.5f * e * e) : 0.5f * (1.0f + al - am * am - expf(al));
         }
       }
@@ -546,7 +548,8 @@ lb_latent_bwd_kernel(const float* __restrict__ da1, const float* __restrict__ W1
                      const float* __restrict__ partial, int n_tiles, const float* __restrict__ row_aux,
                      float* __restrict__ per_row, unsigned int* __restrict__ counter, float* __restrict__ base_out,
                      float mult, const float* __restrict__ tprior, int n_tprior, float div,
-                     float* __restrict__ scalar_out) {
+                     float* __restrict__ scalar_out, __nv_bfloat16* __restrict__ dd_hi, __nv_bfloat16* __restrict__ dd_lo,
+                     int ldq) {
   __shared__ __align__(16) float ds[LB_ROWS][LB_KC + 1];
   __shared__ __align__(16) float ws[LB_KC][28];
   __shared__ __align__(16) float psum[2][LB_ROWS][LB_ZP];
@@ -611,6 +614,10 @@ lb_latent_bwd_kernel(const float* __restrict__ da1, const float* __restrict__ W1
       }
       dmu[o2] = a; dls[o2] = b;
       dd[rr][j] = a; dd[rr][Z + j] = b;
+      if (dd_hi) {
+        store_split(dd_hi, dd_lo, (size_t)m * ldq + j, a);
+        store_split(dd_hi, dd_lo, (size_t)m * ldq + Z + j, b);
+      }
     }
   }
   __syncthreads();
@@ -759,14 +766,15 @@ cudaError_t launch_transpose_heads(cudaStream_t st, int64_t* launches, const flo
 cudaError_t launch_latent_fwd(cudaStream_t st, int64_t* launches, const float* h_e, int rows, int H,
                               const float* w45t, const float* b4, const float* b5, const float* W1, const float* b1,
                               int Z, int L, int la, EpsSource src, float* mu, float* ls, float* eps, float* z,
-                              float* row_aux, float* h_d, void* hd_hi, void* hd_lo, int ld_mirror) {
+                              float* row_aux, float* h_d, void* hd_hi, void* hd_lo, int ld_mirror, void* z_hi,
+                              void* z_lo, int ldz) {
   const int nchunks = (2 * Z + 7) / 8;
   const int KS = max(1, NWARPS / nchunks);
   ++*launches;
   if (latent_lb_supported(rows, H, Z, L)) {
     lb_latent_fwd_kernel<<<(rows + LB_ROWS - 1) / LB_ROWS, LB_T, 0, st>>>(
         h_e, rows, H, w45t, b4, b5, W1, b1, Z, la, src, mu, ls, eps, z, row_aux, h_d, (__nv_bfloat16*)hd_hi,
-        (__nv_bfloat16*)hd_lo, ld_mirror);
+        (__nv_bfloat16*)hd_lo, ld_mirror, (__nv_bfloat16*)z_hi, (__nv_bfloat16*)z_lo, ldz);
   } else if (rows <= 512) {
     const size_t smem = (size_t)((KS + 1) * 2 * Z + 2 * Z) * sizeof(float);
     latent_fwd_kernel<1><<<rows, NTHREADS, smem, st>>>(h_e, rows, H, w45t, b4, b5, W1, b1, Z, L, la, src, mu, ls, eps,
@@ -788,7 +796,7 @@ cudaError_t launch_latent_bwd(cudaStream_t st, int64_t* launches, const float* d
                               float* da3, void* da3_hi, void* da3_lo, int ld_mirror, const float* partial,
                               int n_tiles, const float* row_aux, float* per_row, unsigned int* counter,
                               float* base_out, float mult, const float* tprior, int n_tprior, float div,
-                              float* scalar_out) {
+                              float* scalar_out, void* dd_hi, void* dd_lo, int ldq) {
   const int nchunks = (Z + 7) / 8;
   const int NSL = max(1, (NWARPS - 2) / nchunks);
   ++*launches;
@@ -796,7 +804,7 @@ cudaError_t launch_latent_bwd(cudaStream_t st, int64_t* launches, const float* d
     lb_latent_bwd_kernel<<<(rows + LB_ROWS - 1) / LB_ROWS, LB_T, 0, st>>>(
         da1, W1, w45t, h_e, z, eps, mu, ls, rows, H, Z, la, w, dmu, dls, da3, (__nv_bfloat16*)da3_hi,
         (__nv_bfloat16*)da3_lo, ld_mirror, partial, n_tiles, row_aux, per_row, counter, base_out, mult, tprior,
-        n_tprior, div, scalar_out);
+        n_tprior, div, scalar_out, (__nv_bfloat16*)dd_hi, (__nv_bfloat16*)dd_lo, ldq);
   } else if (rows <= 512) {
     const size_t smem = (size_t)(NSL + 2) * Z * sizeof(float);
     latent_bwd_kernel<1><<<rows, NTHREADS, smem, st>>>(
@@ -813,6 +821,8 @@ cudaError_t launch_latent_bwd(cudaStream_t st, int64_t* launches, const float* d
   }
   return cudaGetLastError();
 }
+
+bool latent_large_batch(int rows, int H, int Z, int L) { return latent_lb_supported(rows, H, Z, L); }
 
 int small_wgrad_chunks(int rows) { return rows <= 512 ? 1 : (rows + 255) / 256; }
 size_t small_wgrad_scratch_elems(int rows, int H, int Z) {

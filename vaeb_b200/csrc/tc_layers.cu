@@ -66,8 +66,9 @@ __device__ __forceinline__ void st16_split(__nv_bfloat16* hi, __nv_bfloat16* lo,
   }
 }
 
-struct EpiTanh {            // out[row, col] = tanh(acc + bias[col])
+struct EpiTanh {            // out[row, col] = tanh(acc + bias[col]) (+ optional bf16 hi/lo mirror of it)
   const float* bias; float* out; int ld;
+  __nv_bfloat16* mh; __nv_bfloat16* ml; int ldm;
   __device__ __forceinline__ void begin() {}
   __device__ __forceinline__ void split(int) {}
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
@@ -79,11 +80,16 @@ struct EpiTanh {            // out[row, col] = tanh(acc + bias[col])
 #pragma unroll
       for (int j = 0; j < 16; ++j) r[j] = tanhf(v[j] + b[j]);
       st16f(o, r);
+      if (mh) st16_split(mh + (size_t)row * ldm + col0, ml ? ml + (size_t)row * ldm + col0 : nullptr, r);
       return;
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (col0 + j < N) o[j] = tanhf(v[j] + bias[col0 + j]);
+      if (col0 + j < N) {
+        const float t = tanhf(v[j] + bias[col0 + j]);
+        o[j] = t;
+        if (mh) put_split(mh, ml, (size_t)row * ldm + col0 + j, t);
+      }
   }
   __device__ __forceinline__ void end(int, bool, int, int) {}
 };
@@ -147,8 +153,9 @@ struct EpiWgradTc {         // rows < Hreal -> gW[Hreal, N]; row == Hreal (the o
   __device__ __forceinline__ void end(int, bool, int, int) {}
 };
 
-struct EpiDgradTanh {       // out = acc * (1 - h^2)
+struct EpiDgradTanh {       // out = acc * (1 - h^2) (+ optional bf16 hi/lo mirror of it)
   const float* h; float* out; int ld;
+  __nv_bfloat16* mh; __nv_bfloat16* ml; int ldm;
   __device__ __forceinline__ void begin() {}
   __device__ __forceinline__ void split(int) {}
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
@@ -161,11 +168,16 @@ struct EpiDgradTanh {       // out = acc * (1 - h^2)
 #pragma unroll
       for (int j = 0; j < 16; ++j) r[j] = v[j] * (1.0f - hv[j] * hv[j]);
       st16f(o, r);
+      if (mh) st16_split(mh + (size_t)row * ldm + col0, ml ? ml + (size_t)row * ldm + col0 : nullptr, r);
       return;
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (col0 + j < N) o[j] = v[j] * (1.0f - hp[j] * hp[j]);
+      if (col0 + j < N) {
+        const float t = v[j] * (1.0f - hp[j] * hp[j]);
+        o[j] = t;
+        if (mh) put_split(mh, ml, (size_t)row * ldm + col0 + j, t);
+      }
   }
   __device__ __forceinline__ void end(int, bool, int, int) {}
 };
@@ -410,7 +422,7 @@ static int make_pair(CUtensorMap* hi, CUtensorMap* lo, const void* bh, const voi
   return VAEB_OK;
 }
 
-int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn) {
+int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z) {
   // enc1: A = x mirror [rows_data, D] K-major (the ones column at D stays out of the map), B = W3 [D, H] MN-major
   LayerMaps* e1 = reinterpret_cast<LayerMaps*>(m->enc1);
   VAEB_TRY(make_pair(&e1->a_hi, &e1->a_lo, b.xh, b.xl, rows_data, D, b.ldx, BM));
@@ -431,14 +443,24 @@ int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows,
   LayerMaps* w3 = reinterpret_cast<LayerMaps*>(m->wgrad3);
   VAEB_TRY(make_pair(&w3->a_hi, &w3->a_lo, b.xh, b.xl, rows_data, D + 1, b.ldx, 64));
   VAEB_TRY(make_pair(&w3->b_hi, &w3->b_lo, b.da3h, b.da3l, rows, H, b.ldh, 64));
+  if (b.heh) {
+    // wgrad W1: A = z mirror [R, Z+1] MN-major (ones column -> gb1), B = da1 mirror [R, H] MN-major
+    LayerMaps* w1 = reinterpret_cast<LayerMaps*>(m->wgrad1);
+    VAEB_TRY(make_pair(&w1->a_hi, &w1->a_lo, b.zh, b.zl, R, Z + 1, b.ldz, 64));
+    VAEB_TRY(make_pair(&w1->b_hi, &w1->b_lo, b.d1h, b.d1l, R, H, b.ldh, 64));
+    // wgrad W4|W5: A = h_e mirror [rows, H+1] MN-major (ones column -> gb4|gb5), B = [dmu|dls] mirror [rows, 2Z]
+    LayerMaps* w45 = reinterpret_cast<LayerMaps*>(m->wgrad45);
+    VAEB_TRY(make_pair(&w45->a_hi, &w45->a_lo, b.heh, b.hel, rows, H + 1, b.ldh, 64));
+    VAEB_TRY(make_pair(&w45->b_hi, &w45->b_lo, b.ddh, b.ddl, rows, 2 * Z, b.ldq, 64));
+  }
   return VAEB_OK;
 }
 
 static_assert(sizeof(LayerMaps) == TC_LAYER_MAPS_BYTES, "TcMaps storage size");
 
 cudaError_t tc_enc1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int D, int H,
-                    int x_row_off, const float* b3, float* h_e) {
-  EpiTanh epi{b3, h_e, H};
+                    int x_row_off, const float* b3, float* h_e, void* he_hi, void* he_lo, int ldm) {
+  EpiTanh epi{b3, h_e, H, (__nv_bfloat16*)he_hi, (__nv_bfloat16*)he_lo, ldm};
   ++*launches;
   return dispatch_layer<false, true>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.enc1), epi, rows, H, D,
                                      x_row_off);
@@ -454,10 +476,46 @@ cudaError_t tc_dec2_bernoulli(cudaStream_t st, int64_t* launches, const TcMaps& 
 }
 
 cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int D, int H,
-                        const float* h_d, float* da1) {
-  EpiDgradTanh epi{h_d, da1, H};
+                        const float* h_d, float* da1, void* d1_hi, void* d1_lo, int ldm) {
+  EpiDgradTanh epi{h_d, da1, H, (__nv_bfloat16*)d1_hi, (__nv_bfloat16*)d1_lo, ldm};
   ++*launches;
   return dispatch_layer<false, false>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.dgrad), epi, R, H, D, 0);
+}
+
+cudaError_t tc_wgrad1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int Z, int H,
+                      float* gW1, float* gb1, float* scratch) {
+  return tc_wgrad_generic(st, launches, *reinterpret_cast<const LayerMaps*>(m.wgrad1), ns, bn, R, Z, H, 0, gW1, gb1,
+                          scratch);
+}
+
+// scratch slices hold [(H+1) x 2Z]: column c < Z belongs to W4 / b4, c >= Z to W5 / b5
+__global__ void __launch_bounds__(256)
+wgrad45_reduce_kernel(const float* __restrict__ scratch, int splits, size_t stride, int H, int Z, float* __restrict__ gW4,
+                      float* __restrict__ gb4, float* __restrict__ gW5, float* __restrict__ gb5) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (H + 1) * 2 * Z) return;
+  float a = 0.f;
+  for (int z = 0; z < splits; ++z) a += scratch[(size_t)z * stride + i];
+  const int k = i / (2 * Z), c = i - k * 2 * Z;
+  float* gW = c < Z ? gW4 : gW5;
+  float* gb = c < Z ? gb4 : gb5;
+  const int j = c < Z ? c : c - Z;
+  if (k < H) gW[(size_t)k * Z + j] = a; else gb[j] = a;
+}
+
+cudaError_t tc_wgrad45(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int rows, int H, int Z, float* gW4,
+                       float* gb4, float* gW5, float* gb5, float* scratch) {
+  const int N = 2 * Z;
+  const int splits = tc_wgrad_splits(H + 1, N, rows, 64);
+  const size_t stride = (size_t)(H + 1) * N;
+  EpiWgradTc epi{nullptr, nullptr, H, N, scratch, stride};      // always through scratch: the reduce also de-interleaves
+  ++*launches;
+  cudaError_t e = dispatch_layer<true, true>(st, ns, 64, *reinterpret_cast<const LayerMaps*>(m.wgrad45), epi, H + 1, N, rows,
+                                             0, splits);
+  if (e != cudaSuccess) return e;
+  wgrad45_reduce_kernel<<<((H + 1) * N + 255) / 256, 256, 0, st>>>(scratch, splits, stride, H, Z, gW4, gb4, gW5, gb5);
+  ++*launches;
+  return cudaGetLastError();
 }
 
 size_t tc_wgrad_scratch_elems(int D, int H) {

@@ -12,6 +12,12 @@ struct TcBuffers {   // bf16 mirrors; *l == nullptr in plain-bf16 mode
   void *hdh = nullptr, *hdl = nullptr;     // h_d                [R, ldh], ones column at H
   void *da2h = nullptr, *da2l = nullptr;   // d bound / d a      [R, ldd]
   void *da3h = nullptr, *da3l = nullptr;   // d bound / d a3     [rows, ldh]
+  // large-batch latent layers (rows >= 1024, L = 1): operands of the thin weight-gradient GEMMs
+  void *heh = nullptr, *hel = nullptr;     // h_e                [rows, ldh], ones column at H
+  void *d1h = nullptr, *d1l = nullptr;     // d bound / d a1     [R, ldh]
+  void *zh = nullptr, *zl = nullptr;       // z                  [R, ldz], ones column at Z
+  void *ddh = nullptr, *ddl = nullptr;     // [dmu | dls]        [rows, ldq]
+  int ldz = 32, ldq = 64;
   int ldx = 0, ldh = 0, ldd = 0;
   float* wg_scratch = nullptr;             // split-K slices of the wide weight gradients
 };
@@ -22,21 +28,28 @@ struct TcMaps {
   alignas(64) unsigned char dgrad[TC_LAYER_MAPS_BYTES];
   alignas(64) unsigned char wgrad2[TC_LAYER_MAPS_BYTES];
   alignas(64) unsigned char wgrad3[TC_LAYER_MAPS_BYTES];
+  alignas(64) unsigned char wgrad1[TC_LAYER_MAPS_BYTES];    // gW1|gb1 = [z|1]^T . da1
+  alignas(64) unsigned char wgrad45[TC_LAYER_MAPS_BYTES];   // gW4|gW5 (+ bias row) = [h_e|1]^T . [dmu|dls]
 };
 
-int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn);
+int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z);
 
 cudaError_t tc_split_matrix(cudaStream_t st, int64_t* launches, const float* src, int64_t rows, int cols, int ld_src,
                             void* hi, void* lo, int ld_dst, int ones_col);
 cudaError_t tc_mirror_weights(cudaStream_t st, int64_t* launches, const float* w3, void* w3h, void* w3l, int D, int H,
                               int ldh, const float* w2, void* w2h, void* w2l, int ldd);
 cudaError_t tc_enc1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int D, int H,
-                    int x_row_off, const float* b3, float* h_e);
+                    int x_row_off, const float* b3, float* h_e, void* he_hi, void* he_lo, int ldm);
 cudaError_t tc_dec2_bernoulli(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
                               const float* b2, const float* x, int x_div, int x_mod, float scale, void* da_hi,
                               void* da_lo, int ldda, float* partial, int* n_tiles);
 cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int D, int H,
-                        const float* h_d, float* da1);
+                        const float* h_d, float* da1, void* d1_hi, void* d1_lo, int ldm);
+// thin weight gradients of the latent layers on tcgen05 (large batch): split-K over the rows, fixed-order reduction
+cudaError_t tc_wgrad1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int Z, int H,
+                      float* gW1, float* gb1, float* scratch);
+cudaError_t tc_wgrad45(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int rows, int H, int Z, float* gW4,
+                       float* gb4, float* gW5, float* gb5, float* scratch);
 // scratch: device floats for the split-K slices of a weight gradient (tc_wgrad_scratch_elems), or nullptr
 size_t tc_wgrad_scratch_elems(int D, int H);
 cudaError_t tc_wgrad2(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
