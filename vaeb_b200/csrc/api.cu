@@ -201,6 +201,10 @@ int tc_ensure(vaeb_handle* h, int64_t rows, int64_t R) {
     }
     if (latent_large_batch((int)rows, H, h->Z, 1)) {
       VAEB_TRY(grow_bytes(&b.heh, (size_t)rows * b.ldh * 2));
+      if (!b.w45h) {
+        VAEB_TRY(grow_bytes(&b.w45h, (size_t)2 * h->Z * b.ldh * 2));
+        if (lo) VAEB_TRY(grow_bytes(&b.w45l, (size_t)2 * h->Z * b.ldh * 2));
+      }
       VAEB_TRY(grow_bytes(&b.ddh, (size_t)rows * b.ldq * 2));
       VAEB_CUDA(cudaMemsetAsync(b.ddh, 0, (size_t)rows * b.ldq * 2, h->stream));
       if (lo) {
@@ -339,6 +343,10 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
                        s.row_aux, s.per_row, h->d_counter, bo.base_out, bo.mult, bo.tprior, bo.n_tprior, bo.div,
                        bo.scalar_out, tcl ? tb.ddh : nullptr, tcl ? tb.ddl : nullptr, tb.ldq));
   if (tcl) {
+    PH("mirror W4^T,W5^T -> bf16", 0, 12.0 * dZ * dH,
+       tc_split_matrix(st, lc, h->d_w45t, 2 * Z, H, H, tb.w45h, tb.w45l, tb.ldh, -1));
+    PH("dgrad h_e ([dmu|dls].W45^T)*(1-h^2) [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * 64 + 2 * dZ * dH) + 8 * dr * dH,
+       tc_dgrad_he(st, lc, t.maps, t.ns, bn, rows, Z, H, s.h_e, s.da3, tb.da3h, tb.da3l, tb.ldh));
     PH("wgrad W1,b1 [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * 32 + dR * dH) + 4 * dZ * dH,
        tc_wgrad1(st, lc, t.maps, t.ns, bn, R, Z, H, T_(h, grads, l.iW1), T_(h, grads, l.ib1), tb.wg_scratch));
     PH("wgrad W4,b4,W5,b5 [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * dH + dr * 64) + 8 * dZ * dH,
@@ -587,7 +595,7 @@ int vaeb_destroy(vaeb_handle* h) {
   {
     TcBuffers& b = h->tc.data;
     void* tb[] = {b.xh, b.xl, b.w3h, b.w3l, b.w2h, b.w2l, b.hdh, b.hdl, b.da2h, b.da2l, b.da3h, b.da3l, h->tc.xsh, h->tc.xsl, b.wg_scratch,
-                  b.heh, b.hel, b.d1h, b.d1l, b.zh, b.zl, b.ddh, b.ddl};
+                  b.heh, b.hel, b.d1h, b.d1l, b.zh, b.zl, b.ddh, b.ddl, b.w45h, b.w45l};
     for (void* q : tb) if (q) cudaFree(q);
   }
   if (h->h_scalars) cudaFreeHost(h->h_scalars);

@@ -621,7 +621,8 @@ lb_latent_bwd_kernel(const float* __restrict__ da1, const float* __restrict__ W1
     }
   }
   __syncthreads();
-  for (int n = t; n < H; n += LB_T) {
+  // da3: skipped when the [dmu|dls] mirrors feed a tcgen05 GEMM that computes it (tc_dgrad_he)
+  for (int n = t; n < (dd_hi ? 0 : H); n += LB_T) {
     float wr[LB_NC];
 #pragma unroll
     for (int c = 0; c < LB_NC; ++c) wr[c] = c < 2 * Z ? w45t[(size_t)c * H + n] : 0.f;

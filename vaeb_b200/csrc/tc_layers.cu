@@ -452,6 +452,10 @@ int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows,
     LayerMaps* w45 = reinterpret_cast<LayerMaps*>(m->wgrad45);
     VAEB_TRY(make_pair(&w45->a_hi, &w45->a_lo, b.heh, b.hel, rows, H + 1, b.ldh, 64));
     VAEB_TRY(make_pair(&w45->b_hi, &w45->b_lo, b.ddh, b.ddl, rows, 2 * Z, b.ldq, 64));
+    // dgrad h_e: A = [dmu|dls] mirror [rows, 2Z] K-major, B = [W4^T;W5^T] mirror [2Z, H] MN-major
+    LayerMaps* dh = reinterpret_cast<LayerMaps*>(m->dhe);
+    VAEB_TRY(make_pair(&dh->a_hi, &dh->a_lo, b.ddh, b.ddl, rows, 2 * Z, b.ldq, BM));
+    VAEB_TRY(make_pair(&dh->b_hi, &dh->b_lo, b.w45h, b.w45l, 2 * Z, H, b.ldh, 64));
   }
   return VAEB_OK;
 }
@@ -480,6 +484,13 @@ cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int
   EpiDgradTanh epi{h_d, da1, H, (__nv_bfloat16*)d1_hi, (__nv_bfloat16*)d1_lo, ldm};
   ++*launches;
   return dispatch_layer<false, false>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.dgrad), epi, R, H, D, 0);
+}
+
+cudaError_t tc_dgrad_he(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int Z, int H,
+                        const float* h_e, float* da3, void* da3_hi, void* da3_lo, int ldm) {
+  EpiDgradTanh epi{h_e, da3, H, (__nv_bfloat16*)da3_hi, (__nv_bfloat16*)da3_lo, ldm};
+  ++*launches;
+  return dispatch_layer<false, true>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.dhe), epi, rows, H, 2 * Z, 0);
 }
 
 cudaError_t tc_wgrad1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int Z, int H,

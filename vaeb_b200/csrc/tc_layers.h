@@ -17,6 +17,7 @@ struct TcBuffers {   // bf16 mirrors; *l == nullptr in plain-bf16 mode
   void *d1h = nullptr, *d1l = nullptr;     // d bound / d a1     [R, ldh]
   void *zh = nullptr, *zl = nullptr;       // z                  [R, ldz], ones column at Z
   void *ddh = nullptr, *ddl = nullptr;     // [dmu | dls]        [rows, ldq]
+  void *w45h = nullptr, *w45l = nullptr;   // [W4^T ; W5^T]      [2Z, ldh]
   int ldz = 32, ldq = 64;
   int ldx = 0, ldh = 0, ldd = 0;
   float* wg_scratch = nullptr;             // split-K slices of the wide weight gradients
@@ -30,6 +31,7 @@ struct TcMaps {
   alignas(64) unsigned char wgrad3[TC_LAYER_MAPS_BYTES];
   alignas(64) unsigned char wgrad1[TC_LAYER_MAPS_BYTES];    // gW1|gb1 = [z|1]^T . da1
   alignas(64) unsigned char wgrad45[TC_LAYER_MAPS_BYTES];   // gW4|gW5 (+ bias row) = [h_e|1]^T . [dmu|dls]
+  alignas(64) unsigned char dhe[TC_LAYER_MAPS_BYTES];       // da3 = ([dmu|dls] . [W4^T;W5^T]) * (1 - h_e^2)
 };
 
 int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z);
@@ -48,6 +50,8 @@ cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int
 // thin weight gradients of the latent layers on tcgen05 (large batch): split-K over the rows, fixed-order reduction
 cudaError_t tc_wgrad1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int Z, int H,
                       float* gW1, float* gb1, float* scratch);
+cudaError_t tc_dgrad_he(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int Z, int H,
+                        const float* h_e, float* da3, void* da3_hi, void* da3_lo, int ldm);
 cudaError_t tc_wgrad45(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int rows, int H, int Z, float* gW4,
                        float* gb4, float* gW5, float* gb5, float* scratch);
 // scratch: device floats for the split-K slices of a weight gradient (tc_wgrad_scratch_elems), or nullptr
