@@ -203,7 +203,11 @@ int tc_ensure(vaeb_handle* h, int64_t rows, int64_t R) {
       VAEB_TRY(grow_bytes(&b.heh, (size_t)rows * b.ldh * 2));
       if (!b.w45h) {
         VAEB_TRY(grow_bytes(&b.w45h, (size_t)2 * h->Z * b.ldh * 2));
-        if (lo) VAEB_TRY(grow_bytes(&b.w45l, (size_t)2 * h->Z * b.ldh * 2));
+        VAEB_TRY(grow_bytes(&b.w1h, (size_t)h->Z * b.ldh * 2));
+        if (lo) {
+          VAEB_TRY(grow_bytes(&b.w45l, (size_t)2 * h->Z * b.ldh * 2));
+          VAEB_TRY(grow_bytes(&b.w1l, (size_t)h->Z * b.ldh * 2));
+        }
       }
       VAEB_TRY(grow_bytes(&b.ddh, (size_t)rows * b.ldq * 2));
       VAEB_CUDA(cudaMemsetAsync(b.ddh, 0, (size_t)rows * b.ldq * 2, h->stream));
@@ -335,6 +339,15 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
     PH("dgrad h_d (.W2^T)*(1-h^2)", 2 * dR * dH * dD * c, 4 * (c * dR * dD + c * dH * dD + 2 * dR * dH),
        launch_dgrad_tanh(st, lc, s.da2, T_(h, theta, l.iW2), h->cont ? s.dlv : nullptr, W6, R, D, H, s.h_d, s.da1));
   }
+  if (tcl) {
+    PH("mirror W1 -> bf16", 0, 6.0 * dZ * dH,
+       tc_split_matrix(st, lc, T_(h, theta, l.iW1), Z, H, H, tb.w1h, tb.w1l, tb.ldh, -1));
+    PH("dz da1.W1^T + dmu,dls [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * dH + dZ * dH) + 28 * dR * dZ,
+       tc_dz_dprep(st, lc, t.maps, t.ns, R, H, Z, la, w, s.z, s.eps, s.mu, s.ls, s.dmu, s.dls, tb.ddh, tb.ddl, tb.ldq));
+    PH("bound (per row + total)", 0, 4 * (dR * tiles + 2 * dr),
+       launch_finalize(st, lc, s.partial, tiles, s.row_aux, rows, L, s.per_row, bo.base_out, bo.mult, bo.tprior,
+                       bo.n_tprior, bo.div, bo.scalar_out));
+  } else
   PH("latent bwd (dz,dmu,dls,da3,bound)", 2 * dR * dZ * dH + 4 * dr * dH * dZ,
      4 * (dR * dH + 3 * dZ * dH + 2 * dr * dH + 3 * dR * dZ + dR * tiles),
      launch_latent_bwd(st, lc, s.da1, T_(h, theta, l.iW1), h->d_w45t, s.h_e, s.z, s.eps,
@@ -595,7 +608,7 @@ int vaeb_destroy(vaeb_handle* h) {
   {
     TcBuffers& b = h->tc.data;
     void* tb[] = {b.xh, b.xl, b.w3h, b.w3l, b.w2h, b.w2l, b.hdh, b.hdl, b.da2h, b.da2l, b.da3h, b.da3l, h->tc.xsh, h->tc.xsl, b.wg_scratch,
-                  b.heh, b.hel, b.d1h, b.d1l, b.zh, b.zl, b.ddh, b.ddl, b.w45h, b.w45l};
+                  b.heh, b.hel, b.d1h, b.d1l, b.zh, b.zl, b.ddh, b.ddl, b.w45h, b.w45l, b.w1h, b.w1l};
     for (void* q : tb) if (q) cudaFree(q);
   }
   if (h->h_scalars) cudaFreeHost(h->h_scalars);

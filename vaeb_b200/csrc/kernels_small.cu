@@ -188,6 +188,40 @@ finalize_kernel(const float* __restrict__ partial, int n_tiles, const float* __r
   }
 }
 
+// large row counts: per-row bounds by all SMs, then one block totals them in a fixed order
+__global__ void __launch_bounds__(256)
+finalize_rows_kernel(const float* __restrict__ partial, int n_tiles, const float* __restrict__ row_aux, int rows, int L,
+                     float* __restrict__ per_row) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  float s = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const float* p = partial + ((size_t)l * rows + m) * n_tiles;
+    float t = 0.f;
+    for (int q = 0; q < n_tiles; ++q) t += p[q];
+    s += t;
+  }
+  per_row[m] = s * (1.0f / (float)L) + row_aux[m];
+}
+__global__ void __launch_bounds__(1024)
+finalize_total_kernel(const float* __restrict__ per_row, int rows, float* __restrict__ base_out, float mult,
+                      const float* __restrict__ tprior, int n_tprior, float div, float* __restrict__ scalar_out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int m = threadIdx.x; m < rows; m += blockDim.x) acc += per_row[m];
+  const float base = block_sum_1024(acc, red);
+  float tp = 0.f;
+  if (tprior) {
+    float t = 0.f;
+    for (int i = threadIdx.x; i < n_tprior; i += blockDim.x) t += tprior[i];
+    tp = block_sum_1024(t, red);
+  }
+  if (threadIdx.x == 0) {
+    *base_out = base;
+    if (scalar_out) *scalar_out = (mult * base + tp) / div;
+  }
+}
+
 __global__ void is_rowsum_kernel(const float* __restrict__ partial, int n_tiles, const float* __restrict__ aux,
                                  int64_t rows, float* __restrict__ logw) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -389,6 +423,12 @@ cudaError_t launch_dprep(cudaStream_t st, int64_t* launches, const float* dz, co
 cudaError_t launch_finalize(cudaStream_t st, int64_t* launches, const float* partial, int n_tiles,
                             const float* row_aux, int rows, int L, float* per_row, float* base_out, float mult,
                             const float* tprior, int n_tprior, float div, float* scalar_out) {
+  if (rows >= 2048) {
+    finalize_rows_kernel<<<blocks_for(rows, 256), 256, 0, st>>>(partial, n_tiles, row_aux, rows, L, per_row);
+    ++*launches;
+    finalize_total_kernel<<<1, 1024, 0, st>>>(per_row, rows, base_out, mult, tprior, n_tprior, div, scalar_out);
+    return LAUNCHED();
+  }
   finalize_kernel<<<1, 1024, 0, st>>>(partial, n_tiles, row_aux, rows, L, per_row, base_out, mult, tprior, n_tprior,
                                       div, scalar_out);
   return LAUNCHED();

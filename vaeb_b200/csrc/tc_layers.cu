@@ -182,6 +182,38 @@ struct EpiDgradTanh {       // out = acc * (1 - h^2) (+ optional bf16 hi/lo mirr
   __device__ __forceinline__ void end(int, bool, int, int) {}
 };
 
+// dz = da1.W1^T -> dmu, dls (L = 1; formulas of SURVEY.md 8a, as launch_dprep / lb_latent_bwd) + bf16 mirror [dmu|dls]
+struct EpiDzPrep {
+  const float* z; const float* eps; const float* mu; const float* ls; int Z; int la; float w;
+  float* dmu; float* dls; __nv_bfloat16* dd_hi; __nv_bfloat16* dd_lo; int ldq;
+  __device__ __forceinline__ void begin() {}
+  __device__ __forceinline__ void split(int) {}
+  __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
+    if (!ok) return;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = col0 + j;
+      if (c < N) {
+        const size_t o2 = (size_t)row * Z + c;
+        const float lsv = ls[o2];
+        float d = v[j];
+        if (la) d -= w * z[o2];
+        float a = d, b = d * (0.5f * expf(0.5f * lsv) * eps[o2]);
+        if (la) {
+          b += w * 0.5f;
+        } else {
+          a -= w * mu[o2];
+          b += w * 0.5f * (1.0f - expf(lsv));
+        }
+        dmu[o2] = a; dls[o2] = b;
+        put_split(dd_hi, dd_lo, (size_t)row * ldq + c, a);
+        put_split(dd_hi, dd_lo, (size_t)row * ldq + Z + c, b);
+      }
+    }
+  }
+  __device__ __forceinline__ void end(int, bool, int, int) {}
+};
+
 template <int BN, int NS>
 struct LayerSmem {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -452,6 +484,10 @@ int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows,
     LayerMaps* w45 = reinterpret_cast<LayerMaps*>(m->wgrad45);
     VAEB_TRY(make_pair(&w45->a_hi, &w45->a_lo, b.heh, b.hel, rows, H + 1, b.ldh, 64));
     VAEB_TRY(make_pair(&w45->b_hi, &w45->b_lo, b.ddh, b.ddl, rows, 2 * Z, b.ldq, 64));
+    // dz: A = da1 mirror [R, H] K-major, B = W1 mirror [Z, H] K-major (N = Z rows)
+    LayerMaps* dzm = reinterpret_cast<LayerMaps*>(m->dz);
+    VAEB_TRY(make_pair(&dzm->a_hi, &dzm->a_lo, b.d1h, b.d1l, R, H, b.ldh, BM));
+    VAEB_TRY(make_pair(&dzm->b_hi, &dzm->b_lo, b.w1h, b.w1l, Z, H, b.ldh, 64));
     // dgrad h_e: A = [dmu|dls] mirror [rows, 2Z] K-major, B = [W4^T;W5^T] mirror [2Z, H] MN-major
     LayerMaps* dh = reinterpret_cast<LayerMaps*>(m->dhe);
     VAEB_TRY(make_pair(&dh->a_hi, &dh->a_lo, b.ddh, b.ddl, rows, 2 * Z, b.ldq, BM));
@@ -484,6 +520,14 @@ cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int
   EpiDgradTanh epi{h_d, da1, H, (__nv_bfloat16*)d1_hi, (__nv_bfloat16*)d1_lo, ldm};
   ++*launches;
   return dispatch_layer<false, false>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.dgrad), epi, R, H, D, 0);
+}
+
+cudaError_t tc_dz_dprep(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int R, int H, int Z, int la, float w,
+                        const float* z, const float* eps, const float* mu, const float* ls, float* dmu, float* dls,
+                        void* dd_hi, void* dd_lo, int ldq) {
+  EpiDzPrep epi{z, eps, mu, ls, Z, la, w, dmu, dls, (__nv_bfloat16*)dd_hi, (__nv_bfloat16*)dd_lo, ldq};
+  ++*launches;
+  return dispatch_layer<false, false>(st, ns, 64, *reinterpret_cast<const LayerMaps*>(m.dz), epi, R, Z, H, 0);
 }
 
 cudaError_t tc_dgrad_he(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int Z, int H,

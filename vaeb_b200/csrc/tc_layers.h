@@ -18,6 +18,7 @@ struct TcBuffers {   // bf16 mirrors; *l == nullptr in plain-bf16 mode
   void *zh = nullptr, *zl = nullptr;       // z                  [R, ldz], ones column at Z
   void *ddh = nullptr, *ddl = nullptr;     // [dmu | dls]        [rows, ldq]
   void *w45h = nullptr, *w45l = nullptr;   // [W4^T ; W5^T]      [2Z, ldh]
+  void *w1h = nullptr, *w1l = nullptr;     // W1                 [Z, ldh]
   int ldz = 32, ldq = 64;
   int ldx = 0, ldh = 0, ldd = 0;
   float* wg_scratch = nullptr;             // split-K slices of the wide weight gradients
@@ -32,6 +33,7 @@ struct TcMaps {
   alignas(64) unsigned char wgrad1[TC_LAYER_MAPS_BYTES];    // gW1|gb1 = [z|1]^T . da1
   alignas(64) unsigned char wgrad45[TC_LAYER_MAPS_BYTES];   // gW4|gW5 (+ bias row) = [h_e|1]^T . [dmu|dls]
   alignas(64) unsigned char dhe[TC_LAYER_MAPS_BYTES];       // da3 = ([dmu|dls] . [W4^T;W5^T]) * (1 - h_e^2)
+  alignas(64) unsigned char dz[TC_LAYER_MAPS_BYTES];        // dz = da1 . W1^T (+ dmu, dls in the epilogue)
 };
 
 int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z);
@@ -50,6 +52,10 @@ cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int
 // thin weight gradients of the latent layers on tcgen05 (large batch): split-K over the rows, fixed-order reduction
 cudaError_t tc_wgrad1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int Z, int H,
                       float* gW1, float* gb1, float* scratch);
+// dz = da1.W1^T fused with the encoder-side gradient assembly (dmu, dls) and the [dmu|dls] mirror
+cudaError_t tc_dz_dprep(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int R, int H, int Z, int la, float w,
+                        const float* z, const float* eps, const float* mu, const float* ls, float* dmu, float* dls,
+                        void* dd_hi, void* dd_lo, int ldq);
 cudaError_t tc_dgrad_he(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int Z, int H,
                         const float* h_e, float* da3, void* da3_hi, void* da3_lo, int ldm);
 cudaError_t tc_wgrad45(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int rows, int H, int Z, float* gW4,
