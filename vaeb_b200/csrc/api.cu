@@ -204,6 +204,8 @@ int tc_ensure(vaeb_handle* h, int64_t rows, int64_t R) {
       if (!b.w45h) {
         VAEB_TRY(grow_bytes(&b.w45h, (size_t)2 * h->Z * b.ldh * 2));
         VAEB_TRY(grow_bytes(&b.w1h, (size_t)h->Z * b.ldh * 2));
+        VAEB_TRY(grow_bytes(&b.whh, (size_t)H * b.ldq * 2));
+        if (lo) VAEB_TRY(grow_bytes(&b.whl, (size_t)H * b.ldq * 2));
         if (lo) {
           VAEB_TRY(grow_bytes(&b.w45l, (size_t)2 * h->Z * b.ldh * 2));
           VAEB_TRY(grow_bytes(&b.w1l, (size_t)h->Z * b.ldh * 2));
@@ -296,6 +298,18 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   // latent heads + reparameterisation + row terms + decoder hidden layer, VAEB.py:248-254,41-47,343
   PH("transpose W4,W5", 0, 16 * dH * dZ,
      launch_transpose_heads(st, lc, T_(h, theta, l.iW4), T_(h, theta, l.iW5), H, Z, h->d_w45t));
+  if (tcl) {
+    int n_aux = 0;
+    PH("mirror heads, W1 -> bf16", 0, 18.0 * dZ * dH,
+       tc_mirror_heads(st, lc, T_(h, theta, l.iW4), T_(h, theta, l.iW5), H, Z, tb.whh, tb.whl, tb.ldq));
+    VAEB_LAUNCH(tc_split_matrix(st, lc, T_(h, theta, l.iW1), Z, H, H, tb.w1h, tb.w1l, tb.ldh, -1));
+    PH("enc2 h_e.[W4|W5] + reparam + KL [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * dH + 2 * dH * dZ) + 20 * dr * dZ,
+       tc_enc2_heads(st, lc, t.maps, t.ns, rows, H, Z, la, T_(h, theta, l.ib4), T_(h, theta, l.ib5), src, s.mu, s.ls,
+                     s.eps, s.z, tb.zh, tb.zl, tb.ldz, s.partial, &n_aux));
+    VAEB_LAUNCH(launch_row_partials_sum(st, lc, s.partial, n_aux, rows, s.row_aux));
+    PH("dec1 tanh(z.W1+b1) [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * 32 + dZ * dH) + 4 * dR * dH + 2.0 * t.ns * dR * dH,
+       tc_dec1(st, lc, t.maps, t.ns, bn, R, Z, H, T_(h, theta, l.ib1), s.h_d, tb.hdh, tb.hdl, tb.ldh));
+  } else
   PH("latent fwd (enc2,reparam,KL,dec1)", 4 * dr * dH * dZ + 2 * dR * dZ * dH,
      4 * (dr * dH + 3 * dH * dZ + 2 * dr * dZ + 2 * dR * dZ + dR * dH),
      launch_latent_fwd(st, lc, s.h_e, rows, H, h->d_w45t, T_(h, theta, l.ib4),
@@ -340,8 +354,6 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
        launch_dgrad_tanh(st, lc, s.da2, T_(h, theta, l.iW2), h->cont ? s.dlv : nullptr, W6, R, D, H, s.h_d, s.da1));
   }
   if (tcl) {
-    PH("mirror W1 -> bf16", 0, 6.0 * dZ * dH,
-       tc_split_matrix(st, lc, T_(h, theta, l.iW1), Z, H, H, tb.w1h, tb.w1l, tb.ldh, -1));
     PH("dz da1.W1^T + dmu,dls [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * dH + dZ * dH) + 28 * dR * dZ,
        tc_dz_dprep(st, lc, t.maps, t.ns, R, H, Z, la, w, s.z, s.eps, s.mu, s.ls, s.dmu, s.dls, tb.ddh, tb.ddl, tb.ldq));
     PH("bound (per row + total)", 0, 4 * (dR * tiles + 2 * dr),
@@ -608,7 +620,7 @@ int vaeb_destroy(vaeb_handle* h) {
   {
     TcBuffers& b = h->tc.data;
     void* tb[] = {b.xh, b.xl, b.w3h, b.w3l, b.w2h, b.w2l, b.hdh, b.hdl, b.da2h, b.da2l, b.da3h, b.da3l, h->tc.xsh, h->tc.xsl, b.wg_scratch,
-                  b.heh, b.hel, b.d1h, b.d1l, b.zh, b.zl, b.ddh, b.ddl, b.w45h, b.w45l, b.w1h, b.w1l};
+                  b.heh, b.hel, b.d1h, b.d1l, b.zh, b.zl, b.ddh, b.ddl, b.w45h, b.w45l, b.w1h, b.w1l, b.whh, b.whl};
     for (void* q : tb) if (q) cudaFree(q);
   }
   if (h->h_scalars) cudaFreeHost(h->h_scalars);

@@ -188,6 +188,15 @@ finalize_kernel(const float* __restrict__ partial, int n_tiles, const float* __r
   }
 }
 
+__global__ void __launch_bounds__(256)
+row_partials_sum_kernel(const float* __restrict__ part, int n_part, int rows, float* __restrict__ out) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  float t = 0.f;
+  for (int q = 0; q < n_part; ++q) t += part[(size_t)m * n_part + q];
+  out[m] = t;
+}
+
 // large row counts: per-row bounds by all SMs, then one block totals them in a fixed order
 __global__ void __launch_bounds__(256)
 finalize_rows_kernel(const float* __restrict__ partial, int n_tiles, const float* __restrict__ row_aux, int rows, int L,
@@ -447,6 +456,12 @@ cudaError_t launch_add_prior(cudaStream_t st, int64_t* launches, float* g, const
                              const float* base, float mult, float div, float* scalar_out) {
   add_prior_kernel<<<blocks_for(n4, 256), 256, 0, st>>>((float4*)g, (const float4*)p, n4, prior, base, mult, div,
                                                         scalar_out);
+  return LAUNCHED();
+}
+
+cudaError_t launch_row_partials_sum(cudaStream_t st, int64_t* launches, const float* part, int n_part, int rows,
+                                    float* out) {
+  row_partials_sum_kernel<<<blocks_for(rows, 256), 256, 0, st>>>(part, n_part, rows, out);
   return LAUNCHED();
 }
 

@@ -63,6 +63,9 @@ cudaError_t launch_finalize(cudaStream_t st, int64_t* launches, const float* par
 // logw[r] = sum_t partial[r,t] + aux[r];  logp[i] = logsumexp_l logw[i*L+l] - log L
 cudaError_t launch_is_reduce(cudaStream_t st, int64_t* launches, const float* partial, int n_tiles,
                              const float* aux, int n, int L, float* logw, float* logp);
+// out[m] = sum_q part[m, q]   (fixed order)
+cudaError_t launch_row_partials_sum(cudaStream_t st, int64_t* launches, const float* part, int n_part, int rows,
+                                    float* out);
 cudaError_t launch_gather_rows(cudaStream_t st, int64_t* launches, const float* src, const int* idx, int n, int D,
                                float* out);
 cudaError_t launch_axpy(cudaStream_t st, int64_t* launches, float* y, const float* x, float a, int64_t n);

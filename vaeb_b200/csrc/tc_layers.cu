@@ -16,6 +16,7 @@
 #include "launchers.h"
 #include "tc_common.cuh"
 #include "tc_layers.h"
+#include "philox.cuh"
 
 namespace {
 
@@ -180,6 +181,36 @@ struct EpiDgradTanh {       // out = acc * (1 - h^2) (+ optional bf16 hi/lo mirr
       }
   }
   __device__ __forceinline__ void end(int, bool, int, int) {}
+};
+
+// (mu_j, ls_j) = columns (2j, 2j+1) of h_e.[W4|W5]_interleaved + bias -> eps, z, row term, z mirror (L = 1)
+struct EpiHeads {
+  const float* b4; const float* b5; int Z; int la; EpsSource src;
+  float* mu; float* ls; float* eps; float* z; __nv_bfloat16* z_hi; __nv_bfloat16* z_lo; int ldz; float* aux_part;
+  float acc;
+  __device__ __forceinline__ void begin() { acc = 0.f; }
+  __device__ __forceinline__ void split(int) {}
+  __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
+    if (!ok) return;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j = (col0 >> 1) + jj;
+      if (j < Z) {
+        const float am = v[2 * jj] + b4[j], al = v[2 * jj + 1] + b5[j];
+        const size_t o2 = (size_t)row * Z + j;
+        const float e = src.injected ? src.injected[o2]
+                                     : philox_normal1(src.seed, src.stream, src.step, 0u,
+                                                      (uint64_t)((src.row_offset + row) * Z + j));
+        const float zv = am + expf(0.5f * al) * e;
+        mu[o2] = am; ls[o2] = al; eps[o2] = e; z[o2] = zv;
+        put_split(z_hi, z_lo, (size_t)row * ldz + j, zv);
+        acc += la ? (-0.5f * zv * zv + 0.5f * al + 0.5f * e * e) : 0.5f * (1.0f + al - am * am - expf(al));
+      }
+    }
+  }
+  __device__ __forceinline__ void end(int row, bool ok, int tile_n, int n_tiles) {
+    if (ok) aux_part[(size_t)row * n_tiles + tile_n] = acc;
+  }
 };
 
 // dz = da1.W1^T -> dmu, dls (L = 1; formulas of SURVEY.md 8a, as launch_dprep / lb_latent_bwd) + bf16 mirror [dmu|dls]
@@ -484,6 +515,14 @@ int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows,
     LayerMaps* w45 = reinterpret_cast<LayerMaps*>(m->wgrad45);
     VAEB_TRY(make_pair(&w45->a_hi, &w45->a_lo, b.heh, b.hel, rows, H + 1, b.ldh, 64));
     VAEB_TRY(make_pair(&w45->b_hi, &w45->b_lo, b.ddh, b.ddl, rows, 2 * Z, b.ldq, 64));
+    // enc2: A = h_e mirror [rows, H] K-major, B = interleaved heads mirror [H, 2Z] MN-major
+    LayerMaps* e2 = reinterpret_cast<LayerMaps*>(m->enc2);
+    VAEB_TRY(make_pair(&e2->a_hi, &e2->a_lo, b.heh, b.hel, rows, H, b.ldh, BM));
+    VAEB_TRY(make_pair(&e2->b_hi, &e2->b_lo, b.whh, b.whl, H, 2 * Z, b.ldq, 64));
+    // dec1: A = z mirror [R, Z] K-major (the ones column at Z stays out of the map), B = W1 mirror [Z, H] MN-major
+    LayerMaps* d1 = reinterpret_cast<LayerMaps*>(m->dec1);
+    VAEB_TRY(make_pair(&d1->a_hi, &d1->a_lo, b.zh, b.zl, R, Z, b.ldz, BM));
+    VAEB_TRY(make_pair(&d1->b_hi, &d1->b_lo, b.w1h, b.w1l, Z, H, b.ldh, 64));
     // dz: A = da1 mirror [R, H] K-major, B = W1 mirror [Z, H] K-major (N = Z rows)
     LayerMaps* dzm = reinterpret_cast<LayerMaps*>(m->dz);
     VAEB_TRY(make_pair(&dzm->a_hi, &dzm->a_lo, b.d1h, b.d1l, R, H, b.ldh, BM));
@@ -520,6 +559,40 @@ cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int
   EpiDgradTanh epi{h_d, da1, H, (__nv_bfloat16*)d1_hi, (__nv_bfloat16*)d1_lo, ldm};
   ++*launches;
   return dispatch_layer<false, false>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.dgrad), epi, R, H, D, 0);
+}
+
+__global__ void __launch_bounds__(256)
+mirror_heads_kernel(const float* __restrict__ W4, const float* __restrict__ W5, int H, int Z, __nv_bfloat16* __restrict__ hi,
+                    __nv_bfloat16* __restrict__ lo, int ldq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * ldq) return;
+  const int k = i / ldq, c = i - k * ldq, j = c >> 1;
+  float v = 0.f;
+  if (j < Z) v = (c & 1) ? W5[(size_t)k * Z + j] : W4[(size_t)k * Z + j];
+  put_split(hi, lo, (size_t)i, v);
+}
+
+cudaError_t tc_mirror_heads(cudaStream_t st, int64_t* launches, const float* W4, const float* W5, int H, int Z, void* hi,
+                            void* lo, int ldq) {
+  mirror_heads_kernel<<<(H * ldq + 255) / 256, 256, 0, st>>>(W4, W5, H, Z, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ldq);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+cudaError_t tc_enc2_heads(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int rows, int H, int Z, int la,
+                          const float* b4, const float* b5, const EpsSource& src, float* mu, float* ls, float* eps,
+                          float* z, void* z_hi, void* z_lo, int ldz, float* aux_part, int* n_aux) {
+  EpiHeads epi{b4, b5, Z, la, src, mu, ls, eps, z, (__nv_bfloat16*)z_hi, (__nv_bfloat16*)z_lo, ldz, aux_part, 0.f};
+  *n_aux = ((2 * Z + 63) / 64) * (EPI_WARPS / 4);
+  ++*launches;
+  return dispatch_layer<false, true>(st, ns, 64, *reinterpret_cast<const LayerMaps*>(m.enc2), epi, rows, 2 * Z, H, 0);
+}
+
+cudaError_t tc_dec1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int Z, int H,
+                    const float* b1, float* h_d, void* hd_hi, void* hd_lo, int ldm) {
+  EpiTanh epi{b1, h_d, H, (__nv_bfloat16*)hd_hi, (__nv_bfloat16*)hd_lo, ldm};
+  ++*launches;
+  return dispatch_layer<false, true>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.dec1), epi, R, H, Z, 0);
 }
 
 cudaError_t tc_dz_dprep(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int R, int H, int Z, int la, float w,

@@ -19,6 +19,7 @@ struct TcBuffers {   // bf16 mirrors; *l == nullptr in plain-bf16 mode
   void *ddh = nullptr, *ddl = nullptr;     // [dmu | dls]        [rows, ldq]
   void *w45h = nullptr, *w45l = nullptr;   // [W4^T ; W5^T]      [2Z, ldh]
   void *w1h = nullptr, *w1l = nullptr;     // W1                 [Z, ldh]
+  void *whh = nullptr, *whl = nullptr;     // heads, interleaved [H, ldq]: column 2j = W4[:,j], 2j+1 = W5[:,j]
   int ldz = 32, ldq = 64;
   int ldx = 0, ldh = 0, ldd = 0;
   float* wg_scratch = nullptr;             // split-K slices of the wide weight gradients
@@ -34,6 +35,8 @@ struct TcMaps {
   alignas(64) unsigned char wgrad45[TC_LAYER_MAPS_BYTES];   // gW4|gW5 (+ bias row) = [h_e|1]^T . [dmu|dls]
   alignas(64) unsigned char dhe[TC_LAYER_MAPS_BYTES];       // da3 = ([dmu|dls] . [W4^T;W5^T]) * (1 - h_e^2)
   alignas(64) unsigned char dz[TC_LAYER_MAPS_BYTES];        // dz = da1 . W1^T (+ dmu, dls in the epilogue)
+  alignas(64) unsigned char enc2[TC_LAYER_MAPS_BYTES];      // (mu, ls) = h_e . [W4|W5] (+ reparameterisation in the epilogue)
+  alignas(64) unsigned char dec1[TC_LAYER_MAPS_BYTES];      // h_d = tanh(z . W1 + b1)
 };
 
 int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z);
@@ -52,6 +55,18 @@ cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int
 // thin weight gradients of the latent layers on tcgen05 (large batch): split-K over the rows, fixed-order reduction
 cudaError_t tc_wgrad1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int Z, int H,
                       float* gW1, float* gb1, float* scratch);
+// interleaved bf16 mirror of the two head weight matrices (so that one epilogue thread holds mu_j and ls_j together)
+cudaError_t tc_mirror_heads(cudaStream_t st, int64_t* launches, const float* W4, const float* W5, int H, int Z, void* hi,
+                            void* lo, int ldq);
+// (mu, ls) = h_e.[W4|W5] + b fused with eps, z = mu + exp(.5 ls) eps, the KL / LA row terms (4 partials per row in
+// aux_part) and the z mirror (VAEB.py:248-249, 41-47, 343, 322-325)
+struct EpsSource;
+cudaError_t tc_enc2_heads(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int rows, int H, int Z, int la,
+                          const float* b4, const float* b5, const EpsSource& src, float* mu, float* ls, float* eps,
+                          float* z, void* z_hi, void* z_lo, int ldz, float* aux_part, int* n_aux);
+// h_d = tanh(z.W1 + b1) with its bf16 mirror (VAEB.py:254)
+cudaError_t tc_dec1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int Z, int H,
+                    const float* b1, float* h_d, void* hd_hi, void* hd_lo, int ldm);
 // dz = da1.W1^T fused with the encoder-side gradient assembly (dmu, dls) and the [dmu|dls] mirror
 cudaError_t tc_dz_dprep(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int R, int H, int Z, int la, float w,
                         const float* z, const float* eps, const float* mu, const float* ls, float* dmu, float* dls,
