@@ -204,11 +204,15 @@ int tc_ensure(vaeb_handle* h, int64_t rows, int64_t R) {
       if (!b.w45h) {
         VAEB_TRY(grow_bytes(&b.w45h, (size_t)2 * h->Z * b.ldh * 2));
         VAEB_TRY(grow_bytes(&b.w1h, (size_t)h->Z * b.ldh * 2));
+        VAEB_CUDA(cudaMemsetAsync(b.w45h, 0, (size_t)2 * h->Z * b.ldh * 2, h->stream));
+        VAEB_CUDA(cudaMemsetAsync(b.w1h, 0, (size_t)h->Z * b.ldh * 2, h->stream));
         VAEB_TRY(grow_bytes(&b.whh, (size_t)H * b.ldq * 2));
         if (lo) VAEB_TRY(grow_bytes(&b.whl, (size_t)H * b.ldq * 2));
         if (lo) {
           VAEB_TRY(grow_bytes(&b.w45l, (size_t)2 * h->Z * b.ldh * 2));
           VAEB_TRY(grow_bytes(&b.w1l, (size_t)h->Z * b.ldh * 2));
+          VAEB_CUDA(cudaMemsetAsync(b.w45l, 0, (size_t)2 * h->Z * b.ldh * 2, h->stream));
+          VAEB_CUDA(cudaMemsetAsync(b.w1l, 0, (size_t)h->Z * b.ldh * 2, h->stream));
         }
       }
       VAEB_TRY(grow_bytes(&b.ddh, (size_t)rows * b.ldq * 2));
@@ -279,9 +283,14 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
       VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bn, Z));
       t.key_rows = rows; t.key_R = R; t.key_data = rows_data; t.key_bn = bn; t.key_x = b.xh;
     }
-    PH("mirror W3,W2 -> bf16", 0, 12.0 * dD * dH,
-       tc_mirror_weights(st, lc, T_(h, theta, l.iW3), b.w3h, b.w3l, D, H, b.ldh, T_(h, theta, l.iW2), b.w2h, b.w2l,
-                         b.ldd));
+    if (want_grads && b.heh && b.zh && b.d1h && b.ddh && latent_large_batch(rows, H, Z, L))
+      PH("weight mirrors / transposes -> bf16 (one launch)", 0, 12.0 * dD * dH + 60.0 * dZ * dH,
+         tc_prepare_weights(st, lc, T_(h, theta, l.iW3), T_(h, theta, l.iW2), T_(h, theta, l.iW4), T_(h, theta, l.iW5),
+                            T_(h, theta, l.iW1), b, h->d_w45t, D, H, Z));
+    else
+      PH("mirror W3,W2 -> bf16", 0, 12.0 * dD * dH,
+         tc_mirror_weights(st, lc, T_(h, theta, l.iW3), b.w3h, b.w3l, D, H, b.ldh, T_(h, theta, l.iW2), b.w2h, b.w2l,
+                           b.ldd));
   }
   const TcBuffers& tb = t.data;
   // large-batch training on the tensor-core path: the thin weight gradients also run on tcgen05 (their operands'
@@ -296,13 +305,11 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
     PH("enc1 x.W3+tanh", 2 * dr * dD * dH, 4 * (dr * dD + dD * dH + dr * dH),
        launch_dense_act(st, lc, x, rows, D, T_(h, theta, l.iW3), T_(h, theta, l.ib3), H, 1, s.h_e));
   // latent heads + reparameterisation + row terms + decoder hidden layer, VAEB.py:248-254,41-47,343
-  PH("transpose W4,W5", 0, 16 * dH * dZ,
-     launch_transpose_heads(st, lc, T_(h, theta, l.iW4), T_(h, theta, l.iW5), H, Z, h->d_w45t));
+  if (!tcl)
+    PH("transpose W4,W5", 0, 16 * dH * dZ,
+       launch_transpose_heads(st, lc, T_(h, theta, l.iW4), T_(h, theta, l.iW5), H, Z, h->d_w45t));
   if (tcl) {
     int n_aux = 0;
-    PH("mirror heads, W1 -> bf16", 0, 18.0 * dZ * dH,
-       tc_mirror_heads(st, lc, T_(h, theta, l.iW4), T_(h, theta, l.iW5), H, Z, tb.whh, tb.whl, tb.ldq));
-    VAEB_LAUNCH(tc_split_matrix(st, lc, T_(h, theta, l.iW1), Z, H, H, tb.w1h, tb.w1l, tb.ldh, -1));
     PH("enc2 h_e.[W4|W5] + reparam + KL [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * dH + 2 * dH * dZ) + 20 * dr * dZ,
        tc_enc2_heads(st, lc, t.maps, t.ns, rows, H, Z, la, T_(h, theta, l.ib4), T_(h, theta, l.ib5), src, s.mu, s.ls,
                      s.eps, s.z, tb.zh, tb.zl, tb.ldz, s.partial, &n_aux));
@@ -368,8 +375,6 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
                        s.row_aux, s.per_row, h->d_counter, bo.base_out, bo.mult, bo.tprior, bo.n_tprior, bo.div,
                        bo.scalar_out, tcl ? tb.ddh : nullptr, tcl ? tb.ddl : nullptr, tb.ldq));
   if (tcl) {
-    PH("mirror W4^T,W5^T -> bf16", 0, 12.0 * dZ * dH,
-       tc_split_matrix(st, lc, h->d_w45t, 2 * Z, H, H, tb.w45h, tb.w45l, tb.ldh, -1));
     PH("dgrad h_e ([dmu|dls].W45^T)*(1-h^2) [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * 64 + 2 * dZ * dH) + 8 * dr * dH,
        tc_dgrad_he(st, lc, t.maps, t.ns, bn, rows, Z, H, s.h_e, s.da3, tb.da3h, tb.da3l, tb.ldh));
     PH("wgrad W1,b1 [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * 32 + dR * dH) + 4 * dZ * dH,

@@ -455,7 +455,60 @@ mirror_weights_kernel(MirrorSeg s0, MirrorSeg s1) {
   put_split(s.hi, s.lo, (size_t)r * s.ld + c, s.src[i]);
 }
 
+// Every per-step weight preparation of the large-batch path in ONE launch (blockIdx.y = task):
+//   0: W3 -> bf16 mirror   1: W2 -> mirror   2: [W4^T;W5^T] fp32 + mirror   3: interleaved heads mirror   4: W1 -> mirror
+struct PrepArgs {
+  const float *W3, *W2, *W4, *W5, *W1;
+  __nv_bfloat16 *w3h, *w3l, *w2h, *w2l, *w45h, *w45l, *whh, *whl, *w1h, *w1l;
+  float* w45t;
+  int D, H, Z, ldh, ldd, ldq;
+};
+__global__ void __launch_bounds__(256)
+prepare_weights_kernel(PrepArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int D = a.D, H = a.H, Z = a.Z;
+  switch (blockIdx.y) {
+    case 0:
+      if (i < (int64_t)D * H) put_split(a.w3h, a.w3l, (size_t)(i / H) * a.ldh + (i % H), a.W3[i]);
+      break;
+    case 1:
+      if (i < (int64_t)H * D) put_split(a.w2h, a.w2l, (size_t)(i / D) * a.ldd + (i % D), a.W2[i]);
+      break;
+    case 2:
+      if (i < (int64_t)2 * Z * H) {
+        const int o = (int)(i / H), k = (int)(i % H);
+        const float v = o < Z ? a.W4[(size_t)k * Z + o] : a.W5[(size_t)k * Z + (o - Z)];
+        a.w45t[i] = v;
+        put_split(a.w45h, a.w45l, (size_t)o * a.ldh + k, v);
+      }
+      break;
+    case 3:
+      if (i < (int64_t)H * a.ldq) {
+        const int k = (int)(i / a.ldq), c = (int)(i % a.ldq), j = c >> 1;
+        float v = 0.f;
+        if (j < Z) v = (c & 1) ? a.W5[(size_t)k * Z + j] : a.W4[(size_t)k * Z + j];
+        put_split(a.whh, a.whl, (size_t)i, v);
+      }
+      break;
+    default:
+      if (i < (int64_t)Z * H) put_split(a.w1h, a.w1l, (size_t)(i / H) * a.ldh + (i % H), a.W1[i]);
+      break;
+  }
+}
+
 }  // namespace
+
+cudaError_t tc_prepare_weights(cudaStream_t st, int64_t* launches, const float* W3, const float* W2, const float* W4,
+                               const float* W5, const float* W1, const TcBuffers& b, float* w45t, int D, int H, int Z) {
+  PrepArgs a{W3, W2, W4, W5, W1,
+             (__nv_bfloat16*)b.w3h, (__nv_bfloat16*)b.w3l, (__nv_bfloat16*)b.w2h, (__nv_bfloat16*)b.w2l,
+             (__nv_bfloat16*)b.w45h, (__nv_bfloat16*)b.w45l, (__nv_bfloat16*)b.whh, (__nv_bfloat16*)b.whl,
+             (__nv_bfloat16*)b.w1h, (__nv_bfloat16*)b.w1l, w45t, D, H, Z, b.ldh, b.ldd, b.ldq};
+  const int64_t n = (int64_t)D * H;
+  prepare_weights_kernel<<<dim3((unsigned)((n + 255) / 256), 5), 256, 0, st>>>(a);
+  ++*launches;
+  return cudaGetLastError();
+}
 
 // ---- host API (tc_layers.h) -------------------------------------------------------------------
 cudaError_t tc_split_matrix(cudaStream_t st, int64_t* launches, const float* src, int64_t rows, int cols, int ld_src,

@@ -55,6 +55,10 @@ cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int
 // thin weight gradients of the latent layers on tcgen05 (large batch): split-K over the rows, fixed-order reduction
 cudaError_t tc_wgrad1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int Z, int H,
                       float* gW1, float* gb1, float* scratch);
+// all per-step weight mirrors / transposes of the large-batch path in one launch (W3, W2, [W4^T;W5^T] incl. its fp32
+// copy w45t, the interleaved heads, W1)
+cudaError_t tc_prepare_weights(cudaStream_t st, int64_t* launches, const float* W3, const float* W2, const float* W4,
+                               const float* W5, const float* W1, const TcBuffers& b, float* w45t, int D, int H, int Z);
 // interleaved bf16 mirror of the two head weight matrices (so that one epilogue thread holds mu_j and ls_j together)
 cudaError_t tc_mirror_heads(cudaStream_t st, int64_t* launches, const float* W4, const float* W5, int H, int Z, void* hi,
                             void* lo, int ldq);
