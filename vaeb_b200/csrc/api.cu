@@ -259,6 +259,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   if (tcp) {
     VAEB_TRY(tc_ensure(h, rows, R));
     bn = R >= 1024 ? 128 : 64;
+    tc_set_pdl(R <= 4096);
     TcBuffers b = t.data;
     int64_t rows_data;
     const bool resident = h->d_x && x >= h->d_x && x < h->d_x + (size_t)h->n_data * D;

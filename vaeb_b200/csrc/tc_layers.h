@@ -39,6 +39,9 @@ struct TcMaps {
   alignas(64) unsigned char dec1[TC_LAYER_MAPS_BYTES];      // h_d = tanh(z . W1 + b1)
 };
 
+// programmatic dependent launch of the layer kernels (their prologues overlap the previous kernel's tail): for steps
+// whose kernels are all about one wave
+void tc_set_pdl(bool on);
 int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z);
 
 cudaError_t tc_split_matrix(cudaStream_t st, int64_t* launches, const float* src, int64_t rows, int cols, int ld_src,
