@@ -63,6 +63,11 @@ class ClockSampler(object):
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            # the first NVML queries of a process take tens of ms inside the driver and serialise with a kernel
+            # launch issued meanwhile (measured: +25..300 ms between the start event and the launch of the timed
+            # kernel): pay for them here, before the timed region, and let the thread sleep before its first sample
+            self._sample()
+            self.rows = []
             self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
         except Exception:
@@ -78,12 +83,11 @@ class ClockSampler(object):
         self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), int(reasons)))
 
     def _loop(self):
-        while not self.stop.is_set():
+        while not self.stop.wait(self.period if self.rows else 0.02):
             try:
                 self._sample()
             except Exception:
                 pass
-            self.stop.wait(self.period)
 
     def __exit__(self, *a):
         if self.t:
@@ -228,9 +232,11 @@ def run_own(args):
     barrier()
     l0 = model.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    order_k = order(K)
     with ClockSampler(local) as clocks:
+        barrier()
         e0.record(stream)
-        elbos = model.update_many(order(K))
+        elbos = model.update_many(order_k)
         e1.record(stream)
         barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -332,6 +338,24 @@ def run_own(args):
                 "frac_of_bf16_sustained_peak_per_gpu": tf5 / world / peaks_["bf16_tflops_sustained"],
                 "mean_logpx_rank0": float(np.mean(res5["lp"]))}
             m5.close()
+        # c4: full variational Bayes over the weights (VAEB.py --full_varational, getFVBL), discrete MNIST Nz = 2 / 10,
+        # M = 100: the reference-faithful mode (weights not sampled) and the sampled-weights mode of the
+        # north star (theta = mu + |sigma| zeta per minibatch).  Replica per GPU.
+        from oracle import vaeb_oracle as O_
+        for zz in (2, 10):
+            p0 = O_.init_params(D, H, zz, False)
+            for sampled in (False, True):
+                m4 = vaeb_b200.VAEB(x[:5000], False, H, zz, M, 1, 0.01, False, True, p0, device=local, seed=10,
+                                    sample_weights=sampled)
+                m4.set_stream(stream.cuda_stream)
+                m4.update_many(np.arange(50, dtype=np.int32) % 50)
+                k4 = 1000
+                ms4 = timed(lambda: m4.update_many(np.arange(k4, dtype=np.int32) % 50))
+                also["c4_fvb_z%d_%s" % (zz, "sampled" if sampled else "faithful")] = {
+                    "workload": "c4: full-VB Bernoulli MNIST 784-500-%d, M=100, L=1, %s" % (
+                        zz, "weights sampled per minibatch" if sampled else "reference-faithful (weights not sampled)"),
+                    "value": world * M * k4 / (ms4 * 1e-3), "unit": "datapoints/s", "ms_per_step": ms4 / k4}
+                m4.close()
         # c1: the reference's own CPU-runnable case on one GPU
         from vaeb_b200.data import synthetic_frey
         xf = synthetic_frey()[:1500]
