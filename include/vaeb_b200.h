@@ -211,6 +211,14 @@ int vaeb_comm_detach(vaeb_handle* h);
 int vaeb_profile_update(vaeb_handle* h, int64_t index, int32_t iters, int32_t max_phases, int32_t* n_phases,
                         float* ms, double* flops, double* bytes, char* names);
 
+/* Measurement aid for bench.py: the flat Adagrad pass of getUpdates (VAEB.py:426-444) over this handle's parameter,
+ * accumulator and gradient buffers, `iters` launches back to back between two CUDA events on the handle's stream.
+ * bytes_per_launch = 20 B x the number of parameters.  variant: 0 / 1 = the production kernel,
+ * 2 = with streaming cache hints, 4 = also two float4 per thread (measured alternatives).  A handle with a large hidden layer gives the stream-sized buffer the HBM roofline needs;
+ * parameters and accumulators are restored afterwards. */
+int vaeb_profile_optimizer(vaeb_handle* h, int32_t iters, int32_t variant, float* ms_per_launch,
+                           double* bytes_per_launch);
+
 /* Self-test of the tcgen05/TMA GEMM building block: C[M,N] = bf16(A[M,K]) . bf16(B[K,N]) with fp32
  * TMEM accumulation.  a_mn_major / b_mn_major choose the memory layout handed to TMA (0: the
  * contraction index is contiguous, 1: the M resp. N index is contiguous), block_n the UMMA N. */

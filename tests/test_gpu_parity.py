@@ -437,3 +437,31 @@ def test_theano_eps_mode_reproduces_reference_stream_order():
     assert float(m.update(1)) == pytest.approx(o.update(1, s.draw(100, 2)), rel=RTOL)
     assert float(m.validate(x[200:])) == pytest.approx(o.validate(x[200:], s.draw(100, 2))[0], rel=RTOL)
     m.close()
+
+
+def test_flat_adagrad_small_and_streaming_kernels_match_numpy():
+    """getUpdates (VAEB.py:426-444) + prior (VAEB.py:389-390) over the flat buffer: the one-float4-per-thread kernel
+    (P = 0.8 M, L2 resident) and the cp.async.bulk streaming kernel picked for buffers beyond L2 (P = 19 M here,
+    ragged last chunk) against the same arithmetic in numpy fp32."""
+    for Hh in (500, 12007):
+        D, Z = 784, 20
+        x = np.random.RandomState(3).uniform(size=(100, D)).astype(np.float32)
+        m = _model(x, False, Hh, Z, 100)
+        rng = np.random.RandomState(Hh)
+        shapes = O.param_shapes(D, Hh, Z, False)
+        p0 = [rng.normal(0, 0.1, s).astype(np.float32) for s in shapes]
+        a0 = [rng.uniform(0, 2, s).astype(np.float32) for s in shapes]
+        g0 = [rng.normal(0, 1, s).astype(np.float32) for s in shapes]
+        import vaeb_b200._lib as L_
+        for _ in range(2):            # twice: the accumulator written by the first pass feeds the second
+            m._set_buffer(L_.BUF_PARAMS, p0); m._set_buffer(L_.BUF_ADA, a0); m._set_buffer(L_.BUF_GRADS, g0)
+            m.apply_update()
+            p1, a1 = m._get_buffer(L_.BUF_PARAMS), m._get_buffer(L_.BUF_ADA)
+            for p, a, g, pn, an in zip(p0, a0, g0, p1, a1):
+                gg = g - np.float32(1.0) * p
+                ar = a + gg * gg
+                pr = p + np.float32(0.01) * gg / (np.sqrt(ar) + np.float32(1e-6))
+                np.testing.assert_allclose(an, ar, rtol=2e-6, atol=0)
+                np.testing.assert_allclose(pn, pr, rtol=2e-6, atol=1e-7)
+            p0, a0 = p1, a1
+        m.close()

@@ -1364,6 +1364,49 @@ int vaeb_profile_update(vaeb_handle* h, int64_t index, int32_t iters, int32_t ma
   return VAEB_OK;
 }
 
+int vaeb_profile_optimizer(vaeb_handle* h, int32_t iters, int32_t variant, float* ms_per_launch,
+                            double* bytes_per_launch) {
+  VAEB_REQUIRE(h && ms_per_launch && bytes_per_launch && iters > 0, "null argument");
+  VAEB_REQUIRE(!is_fvb(h), "vaeb_profile_optimizer covers the flat Adagrad pass of the LB/LA estimators");
+  VAEB_REQUIRE(variant == 0 || variant == 1 || variant == 2 || variant == 4, "variant must be 0, 1, 2 or 4");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  const size_t nb = (size_t)(h->lay.padded + 4) * sizeof(float);
+  float *bp = nullptr, *ba = nullptr;
+  VAEB_CUDA(cudaMalloc((void**)&bp, nb));
+  VAEB_CUDA(cudaMalloc((void**)&ba, nb));
+  VAEB_CUDA(cudaMemcpyAsync(bp, h->d_params, nb, cudaMemcpyDeviceToDevice, h->stream));
+  VAEB_CUDA(cudaMemcpyAsync(ba, h->d_ada, nb, cudaMemcpyDeviceToDevice, h->stream));
+  cudaEvent_t e0, e1;
+  VAEB_CUDA(cudaEventCreate(&e0));
+  VAEB_CUDA(cudaEventCreate(&e1));
+  const int64_t launches0 = h->launches;
+  const bool fb = h->cfg.variant == VAEB_VARIANT_FULLBAYES;
+  g_adagrad_unroll = variant;
+  cudaError_t ce = cudaSuccess;
+  for (int i = -2; i < iters && ce == cudaSuccess; ++i) {          // two untimed launches first
+    if (i == 0) ce = cudaEventRecord(e0, h->stream);
+    if (ce == cudaSuccess)
+      ce = launch_adagrad(h->stream, &h->launches, h->d_params, h->d_ada, h->d_grads, h->lay.padded / 4,
+                          h->cfg.learning_rate, h->cfg.adagrad_eps, fb ? 0.f : h->cfg.prior_scale,
+                          fb ? h->cfg.learning_rate * 1e-6f : 0.f, h->d_grads + h->lay.padded, 1.f, 1.f, nullptr);
+  }
+  g_adagrad_unroll = 0;
+  if (ce == cudaSuccess) ce = cudaEventRecord(e1, h->stream);
+  if (ce == cudaSuccess) ce = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  h->launches = launches0;
+  cudaMemcpyAsync(h->d_params, bp, nb, cudaMemcpyDeviceToDevice, h->stream);
+  cudaMemcpyAsync(h->d_ada, ba, nb, cudaMemcpyDeviceToDevice, h->stream);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(bp); cudaFree(ba);
+  VAEB_CUDA(ce);
+  *ms_per_launch = ms / (float)iters;
+  *bytes_per_launch = 20.0 * (double)h->lay.total;                 // read p, acc, g; write p, acc
+  return VAEB_OK;
+}
+
 int vaeb_launch_count(vaeb_handle* h, int64_t* n_launches) {
   VAEB_REQUIRE(h && n_launches, "null argument");
   *n_launches = h->launches;

@@ -345,6 +345,17 @@ class VAEB(object):
         return [(names.raw[48 * i:48 * i + 48].split(b"\0")[0].decode(), float(t[i]), float(fl[i]), float(by[i]))
                 for i in range(n.value)]
 
+    def apply_update(self):
+        """Adagrad step (VAEB.py:426-444) with the gradients left in the buffer by `gradients()` (or written
+        there by the caller): the second half of `update()` on its own."""
+        _lib.check(self._lib.vaeb_apply_update(self._h))
+
+    def profile_optimizer(self, iters=20, variant=0):
+        """(ms per launch, algorithmic bytes per launch) of the flat Adagrad pass over this model's buffers."""
+        ms, by = C.c_float(), C.c_double()
+        _lib.check(self._lib.vaeb_profile_optimizer(self._h, int(iters), int(variant), C.byref(ms), C.byref(by)))
+        return ms.value, by.value
+
     def launch_count(self):
         n = C.c_int64()
         _lib.check(self._lib.vaeb_launch_count(self._h, C.byref(n)))
