@@ -439,10 +439,9 @@ def test_theano_eps_mode_reproduces_reference_stream_order():
     m.close()
 
 
-def test_flat_adagrad_small_and_streaming_kernels_match_numpy():
-    """getUpdates (VAEB.py:426-444) + prior (VAEB.py:389-390) over the flat buffer: the one-float4-per-thread kernel
-    (P = 0.8 M, L2 resident) and the cp.async.bulk streaming kernel picked for buffers beyond L2 (P = 19 M here,
-    ragged last chunk) against the same arithmetic in numpy fp32."""
+def test_flat_adagrad_kernel_matches_numpy():
+    """getUpdates (VAEB.py:426-444) + prior (VAEB.py:389-390) over the flat buffer, at the C2 size (P = 0.8 M, L2
+    resident) and at a stream size beyond L2 (P = 19 M, ragged tail), against the same arithmetic in numpy fp32."""
     for Hh in (500, 12007):
         D, Z = 784, 20
         x = np.random.RandomState(3).uniform(size=(100, D)).astype(np.float32)
@@ -465,3 +464,32 @@ def test_flat_adagrad_small_and_streaming_kernels_match_numpy():
                 np.testing.assert_allclose(pn, pr, rtol=2e-6, atol=1e-7)
             p0, a0 = p1, a1
         m.close()
+
+
+@pytest.mark.parametrize("continuous", [False, True])
+def test_sampled_full_vb_update_fused_kernel_matches_oracle(continuous):
+    """update() of the full-VB estimator with sampled weights (theta = mu + |sigma| zeta, VAEB.py:127-129 live in
+    getFVBL :349-367) runs in the fused step kernel: phase 0 draws zeta (Philox stream 3, keyed by step and flat
+    parameter index), every layer reads theta, the update epilogues apply Adagrad to mu and sigma.  The oracle is fed
+    the same zeta / eps draws; three consecutive updates, then every variational parameter."""
+    D, H, Z, M = 52, 36, 3, 24
+    x = np.random.RandomState(1).uniform(size=(3 * M, D)).astype(np.float32)
+    params = _rand_params(D, H, Z, continuous, 2, 0.2)
+    m = _model(x, continuous, H, Z, M, 1, "FVB_SAMPLED", params, seed=10)
+    o = O.OracleVAEB(x, continuous, H, Z, M, params=params, estimator="FVB_SAMPLED")
+    total = sum(p.size for p in params)
+    l0 = m.launch_count()
+    for step, idx in enumerate([1, 0, 2]):
+        flat = O.philox_normal(10, 3, step, total)
+        zeta, k = [], 0
+        for p in params:
+            zeta.append(flat[k:k + p.size].reshape(p.shape)); k += p.size
+        eps = np.random.RandomState(20 + step).normal(size=(1, M, Z)).astype(np.float32)
+        got = float(m.update(idx, eps=eps))
+        ref = o.update(idx, eps, zeta)
+        assert got == pytest.approx(ref, rel=RTOL), step
+    assert m.launch_count() - l0 == 3          # one fused launch per update
+    fv = [p.get_value() for p in m.full_variational_params]
+    for i, (a, b) in enumerate(zip(fv, o.fvp)):
+        assert_close_tensor(a, b, RTOL, name="fvp %d" % i)
+    m.close()

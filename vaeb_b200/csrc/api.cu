@@ -620,7 +620,7 @@ int vaeb_destroy(vaeb_handle* h) {
   if (h->d_w45t) cudaFree(h->d_w45t);
   {
     FusedState& f = h->fused;
-    void* fb[] = {f.bar, f.params_alt, f.partial, f.aux_part, f.d_order, f.d_timing};
+    void* fb[] = {f.bar, f.params_alt, f.partial, f.aux_part, f.tprior_part, f.d_order, f.d_timing};
     for (void* q : fb) if (q) cudaFree(q);
   }
   {

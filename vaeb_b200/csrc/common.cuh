@@ -85,6 +85,7 @@ struct FusedState {
   unsigned long long bar_count = 0;        // arrivals so far = the next launch's base
   float* params_alt = nullptr;             // the other half of the parameter double buffer
   float* partial = nullptr; float* aux_part = nullptr;
+  float* tprior_part = nullptr;            // per-CTA thetaPrior partial sums (sampled full VB)
   int* d_order = nullptr; int order_cap = 0;
   long long* d_timing = nullptr; int timing_cap = 0;
   int rows = -1;

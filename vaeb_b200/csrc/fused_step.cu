@@ -261,6 +261,13 @@ __device__ __forceinline__ void fma_quad(const float* sA, const float* sB, int k
   }
 }
 
+// elements an epilogue keeps in flight per thread (the sampled full-VB update holds 5 operands per element)
+template <class Epi> struct EpiInflight { static constexpr int value = 2; };
+template <bool FVB> struct EpiAdagrad;
+template <bool FVB> struct EpiAdagrad2;
+template <> struct EpiInflight<EpiAdagrad<true>> { static constexpr int value = 1; };
+template <> struct EpiInflight<EpiAdagrad2<true>> { static constexpr int value = 1; };
+
 // ---------------------------------------------------------------------------------------------
 // one CTA item of a job.  tm_fixed >= 0: the item covers tiles (tm_fixed, item*tpi + tl) -- the
 // row-block chains, where one CTA runs two dependent layers for its own rows.
@@ -355,7 +362,7 @@ __device__ __forceinline__ void run_item(const Gemm& g, int item, const Epi& epi
   const int gidx = ksi * 32 + lane, gsize = ks * 32;
   float* gbuf = smem + (tl * ks) * WBUF;
   if (active) {
-    constexpr int U = 2;                   // elements in flight per thread: their global operands are
+    constexpr int U = EpiInflight<Epi>::value;   // elements in flight per thread: their global operands are
 #pragma unroll 1                           // requested before the partial tiles are summed
     for (int e0 = gidx; e0 < TM * TNE; e0 += gsize * U) {
       typename Epi::Pre pre[U];
@@ -522,37 +529,77 @@ __device__ __forceinline__ void adagrad_apply(float p, float a0, float* Pn, floa
   ada[o] = a;
 }
 
+// Full VB with sampled weights: theta = mu + |sigma| zeta, so dL/dmu = g and dL/dsigma = g zeta sign(sigma); the
+// prior terms are d/dmu [thetaPrior - .5 prior mu^2] = -mu - prior mu and d/dsigma = 1/s - s - prior s
+// (VAEB.py:359-363,391-393); Adagrad (VAEB.py:426-444) on both.
+struct Fvb { float* vsig; float* ada_sig; const float* zeta; };
+
+__device__ __forceinline__ void fvb_apply(float m, float am0, float s, float as0, float zt, float* vmu, float* ada_mu,
+                                          const Fvb& f, size_t o, float g, const Hyper& hy) {
+  const float sg = (s > 0.f) ? 1.f : ((s < 0.f) ? -1.f : 0.f);
+  const float gm = g - m - hy.prior * m;
+  const float gs = 1.0f / s - s - hy.prior * s + g * zt * sg;
+  const float am = am0 + gm * gm, as = as0 + gs * gs;
+  ada_mu[o] = am;
+  f.ada_sig[o] = as;
+  vmu[o] = m + hy.lr * gm / (sqrtf(am) + hy.eps);
+  f.vsig[o] = s + hy.lr * gs / (sqrtf(as) + hy.eps);
+}
+
+template <bool FVB> struct PreAda { float p, a; };
+template <> struct PreAda<true> { float p, a, s, as, zt; };
+template <bool FVB> struct PreAda2 { float pa, aa, pb, ab; };
+template <> struct PreAda2<true> { float pa, aa, pb, ab, sa, asa, za, sb, asb, zb; };
+
+template <bool FVB>
 struct EpiAdagrad {                   // rows < nW: weight [nW, ld]; row == nW: the bias (ones row of A)
   static constexpr bool ROWSUM = false;
-  struct Pre { float p, a; };
-  const float* P; float* Pn; float* ada; int64_t oW, ob; int nW, ld; Hyper hy;
+  using Pre = PreAda<FVB>;
+  const float* P; float* Pn; float* ada; int64_t oW, ob; int nW, ld; Hyper hy; Fvb f;
   __device__ __forceinline__ size_t off(int m, int n) const {
     return m < nW ? (size_t)oW + (size_t)m * ld + n : (size_t)ob + n;
   }
   __device__ __forceinline__ Pre pre(int m, int n) const {
     const size_t o = off(m, n);
-    return Pre{__ldcg(P + o), __ldcg(ada + o)};
+    Pre q;
+    q.p = __ldcg(P + o); q.a = __ldcg(ada + o);
+    if constexpr (FVB) { q.s = __ldcg(f.vsig + o); q.as = __ldcg(f.ada_sig + o); q.zt = __ldcg(f.zeta + o); }
+    return q;
   }
   __device__ __forceinline__ float elem(int m, int n, float v, float, const Pre& q) const {
-    adagrad_apply(q.p, q.a, Pn, ada, off(m, n), v, hy);
+    if constexpr (FVB) fvb_apply(q.p, q.a, q.s, q.as, q.zt, Pn, ada, f, off(m, n), v, hy);
+    else adagrad_apply(q.p, q.a, Pn, ada, off(m, n), v, hy);
     return 0.f;
   }
   __device__ __forceinline__ void rowsum(int, int, float) const {}
 };
 
+template <bool FVB>
 struct EpiAdagrad2 {                  // two heads at once (W4|W5, b4|b5)
   static constexpr bool ROWSUM = false;
-  struct Pre { float pa, aa, pb, ab; };
-  const float* P; float* Pn; float* ada; int64_t oWa, oba, oWb, obb; int nW, ld; Hyper hy;
+  using Pre = PreAda2<FVB>;
+  const float* P; float* Pn; float* ada; int64_t oWa, oba, oWb, obb; int nW, ld; Hyper hy; Fvb f;
   __device__ __forceinline__ Pre pre(int m, int n) const {
     const size_t off = m < nW ? (size_t)m * ld + n : (size_t)n;
     const size_t oa = (size_t)(m < nW ? oWa : oba) + off, ob_ = (size_t)(m < nW ? oWb : obb) + off;
-    return Pre{__ldcg(P + oa), __ldcg(ada + oa), __ldcg(P + ob_), __ldcg(ada + ob_)};
+    Pre q;
+    q.pa = __ldcg(P + oa); q.aa = __ldcg(ada + oa); q.pb = __ldcg(P + ob_); q.ab = __ldcg(ada + ob_);
+    if constexpr (FVB) {
+      q.sa = __ldcg(f.vsig + oa); q.asa = __ldcg(f.ada_sig + oa); q.za = __ldcg(f.zeta + oa);
+      q.sb = __ldcg(f.vsig + ob_); q.asb = __ldcg(f.ada_sig + ob_); q.zb = __ldcg(f.zeta + ob_);
+    }
+    return q;
   }
   __device__ __forceinline__ float elem(int m, int n, float v0, float v1, const Pre& q) const {
     const size_t off = m < nW ? (size_t)m * ld + n : (size_t)n;
-    adagrad_apply(q.pa, q.aa, Pn, ada, (size_t)(m < nW ? oWa : oba) + off, v0, hy);
-    adagrad_apply(q.pb, q.ab, Pn, ada, (size_t)(m < nW ? oWb : obb) + off, v1, hy);
+    const size_t oa = (size_t)(m < nW ? oWa : oba) + off, ob_ = (size_t)(m < nW ? oWb : obb) + off;
+    if constexpr (FVB) {
+      fvb_apply(q.pa, q.aa, q.sa, q.asa, q.za, Pn, ada, f, oa, v0, hy);
+      fvb_apply(q.pb, q.ab, q.sb, q.asb, q.zb, Pn, ada, f, ob_, v1, hy);
+    } else {
+      adagrad_apply(q.pa, q.aa, Pn, ada, oa, v0, hy);
+      adagrad_apply(q.pb, q.ab, Pn, ada, ob_, v1, hy);
+    }
     return 0.f;
   }
   __device__ __forceinline__ void rowsum(int, int, float) const {}
@@ -586,6 +633,86 @@ __device__ __forceinline__ long long gtime() {
 
 #define FS_JOB(J) job_tmt(J), job_tnt(J)
 
+// phases 6-8 of one update (the weight-gradient phases), templated on the update rule of their epilogues
+template <bool FVB>
+__device__ __forceinline__ void update_phases(const StepParams& p, float* smem, int s, const float* x, const float* P,
+                                              const float* Pu, float* Pn, const Fvb& fv, const Hyper& hy,
+                                              unsigned long long& target, long long* tm) {
+  const int D = p.D, H = p.H, Z = p.Z, M = p.M;
+  const int G = gridDim.x, cta = blockIdx.x;
+    // ---- phase 6: W2 (W6) update | dz -> dmu, dls | W1 update | the bound ---------------------
+    {
+      const Gemm g2 = make_gemm(p.h_d, nullptr, H, p.da2, nullptr, D, H + 1, D, M, 0, H, p.job[J_WG2]);
+      const EpiAdagrad<FVB> e2{Pu, Pn, p.ada, p.oW2, p.ob2, H, D, hy, fv};
+      const Gemm g6 = make_gemm(p.h_d, nullptr, H, p.dlv, nullptr, D, H + 1, D, M, 0, H, p.job[J_WG6]);
+      const EpiAdagrad<FVB> e6{Pu, Pn, p.ada, p.oW6, p.ob6, H, D, hy, fv};
+      const Gemm gz = make_gemm(p.da1, nullptr, H, P + p.oW1, nullptr, H, M, Z, H, 0, -1, p.job[J_DZ]);
+      const EpiDz ez{p.z, p.eps, p.mu, p.ls, Z, p.la, p.w, p.dmu, p.dls};
+      const Gemm g1 = make_gemm(p.z, nullptr, Z, p.da1, nullptr, H, Z + 1, H, M, 0, Z, p.job[J_WG1]);
+      const EpiAdagrad<FVB> e1{Pu, Pn, p.ada, p.oW1, p.ob1, Z, H, hy, fv};
+      const int n2 = g2.c.n_items, n6 = p.cont ? g6.c.n_items : 0, nz = gz.c.n_items, n1 = g1.c.n_items;
+      const int total = n2 + n6 + nz + n1 + 1;
+      for (int it = cta; it < total; it += G) {
+        int i = it;
+        if (i < n2) { run_item<FS_JOB(J_WG2), A_KM, B_KN, PLAIN>(g2, i, e2, smem); continue; }
+        i -= n2;
+        if (i < n6) { run_item<FS_JOB(J_WG6), A_KM, B_KN, PLAIN>(g6, i, e6, smem); continue; }
+        i -= n6;
+        if (i < nz) { run_item<FS_JOB(J_DZ), A_MK, B_NK, PLAIN>(gz, i, ez, smem); continue; }
+        i -= nz;
+        if (i < n1) { run_item<FS_JOB(J_WG1), A_KM, B_KN, PLAIN>(g1, i, e1, smem); continue; }
+        // the bound of this step: fixed-order sum of the row partials (VAEB.py:340-344), / Mg
+        const int tc = p.job[J_DEC2].tiles_n, ta = p.job[J_ENC2].tiles_n;
+        float t = 0.f;
+        for (int r = threadIdx.x; r < M; r += NT) {
+          float rsum = 0.f;
+          for (int q = 0; q < tc; ++q) rsum += __ldcg(p.partial + (size_t)r * tc + q);
+          for (int q = 0; q < ta; ++q) rsum += __ldcg(p.aux_part + (size_t)r * ta + q);
+          t += rsum;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = t;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          float b = 0.f;
+          for (int wq = 0; wq < NW; ++wq) b += smem[wq];
+          float tp = 0.f;                                        // thetaPrior (full VB), fixed order
+          if constexpr (FVB)
+            for (int c = 0; c < G; ++c) tp += __ldcg(p.tprior_part + c);
+          p.scalars[s] = (p.bmult * b + tp) / p.Mg;
+        }
+        __syncthreads();
+      }
+    }
+    grid_barrier(p.bar, target += G);
+    if (tm) tm[6] = gtime();
+
+    // ---- phase 7: back through the latent heads | W4, W5 update ---------------------------------
+    {
+      const Gemm gh = make_gemm(p.dmu, p.dls, Z, P + p.oW4, P + p.oW5, Z, M, H, Z, Z, -1, p.job[J_DHE]);
+      const EpiTanhBack eh{p.h_e, p.da3, H};
+      const Gemm g45 = make_gemm(p.h_e, nullptr, H, p.dmu, p.dls, Z, H + 1, Z, M, 0, H, p.job[J_WG45]);
+      const EpiAdagrad2<FVB> e45{Pu, Pn, p.ada, p.oW4, p.ob4, p.oW5, p.ob5, H, Z, hy, fv};
+      const int nh = gh.c.n_items, total = nh + g45.c.n_items;
+      for (int it = cta; it < total; it += G) {
+        if (it < nh) run_item<FS_JOB(J_DHE), A_MK, B_NK, DUALK>(gh, it, eh, smem);
+        else run_item<FS_JOB(J_WG45), A_KM, B_KN, DUALN>(g45, it - nh, e45, smem);
+      }
+    }
+    grid_barrier(p.bar, target += G);
+    if (tm) tm[7] = gtime();
+
+    // ---- phase 8: W3 update -------------------------------------------------------------------
+    {
+      const Gemm g = make_gemm(x, nullptr, D, p.da3, nullptr, H, D + 1, H, M, 0, D, p.job[J_WG3]);
+      const EpiAdagrad<FVB> epi{Pu, Pn, p.ada, p.oW3, p.ob3, D, H, hy, fv};
+      for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_WG3), A_KM, B_KN, PLAIN>(g, it, epi, smem);
+    }
+}
+
+template <bool FVB>
 __global__ void __launch_bounds__(NT, 1) fused_step_kernel(const StepParams p) {
   extern __shared__ __align__(16) float smem[];
   const int D = p.D, H = p.H, Z = p.Z, M = p.M;
@@ -596,11 +723,44 @@ __global__ void __launch_bounds__(NT, 1) fused_step_kernel(const StepParams p) {
 
   for (int s = 0; s < p.n_steps; ++s) {
     const int cur = (p.parity0 + s) & 1;
-    const float* P = p.params[cur];
-    float* Pn = p.params[cur ^ 1];
+    const float* P = FVB ? p.theta : p.params[cur];          // what the layers read
+    const float* Pu = FVB ? p.vmu : p.params[cur];           // what the update epilogues read / write
+    float* Pn = FVB ? p.vmu : p.params[cur ^ 1];
+    const Fvb fv{p.vsig, p.ada_sig, p.zeta};
     const float* x = p.batch_order ? p.x_base + (size_t)__ldg(p.batch_order + s) * M * D : p.x_direct;
     long long* tm = rec ? p.timing + (size_t)s * (N_PHASES + 1) : nullptr;
     if (tm) tm[0] = gtime();
+
+    // ---- phase 0 (sampled full VB): theta = mu + |sigma| zeta, VAEB.py:127-129; thetaPrior, :359-363 -----
+    if constexpr (FVB) {
+      float tp = 0.f;
+      // one Philox group = four consecutive flat elements (the buffers are 16-byte aligned and padded to 4)
+      for (int64_t g4 = (int64_t)cta * NT + threadIdx.x; 4 * g4 < p.total; g4 += (int64_t)G * NT) {
+        const float4 m4 = __ldcg(reinterpret_cast<const float4*>(p.vmu) + g4);
+        const float4 s4 = __ldcg(reinterpret_cast<const float4*>(p.vsig) + g4);
+        float zt[4];
+        philox_normal4(p.seed, VAEB_STREAM_ZETA, p.step0 + (uint32_t)s, 0u, (uint64_t)g4, zt);
+        const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+        float th[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          th[j] = mm[j] + fabsf(ss[j]) * zt[j];
+          if (4 * g4 + j < p.total) tp += 0.5f * (1.0f + logf(ss[j] * ss[j]) - mm[j] * mm[j] - ss[j] * ss[j]);
+        }
+        reinterpret_cast<float4*>(p.zeta)[g4] = make_float4(zt[0], zt[1], zt[2], zt[3]);
+        reinterpret_cast<float4*>(p.theta)[g4] = make_float4(th[0], th[1], th[2], th[3]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) tp += __shfl_xor_sync(0xffffffffu, tp, o);
+      if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = tp;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float b = 0.f;
+        for (int wq = 0; wq < NW; ++wq) b += smem[wq];
+        p.tprior_part[cta] = b;
+      }
+      grid_barrier(p.bar, target += G);
+    }
 
     // ---- phase 1: encoder hidden layer ------------------------------------------------------
     {
@@ -657,73 +817,7 @@ __global__ void __launch_bounds__(NT, 1) fused_step_kernel(const StepParams p) {
     grid_barrier(p.bar, target += G);
     if (tm) tm[5] = gtime();
 
-    // ---- phase 6: W2 (W6) update | dz -> dmu, dls | W1 update | the bound ---------------------
-    {
-      const Gemm g2 = make_gemm(p.h_d, nullptr, H, p.da2, nullptr, D, H + 1, D, M, 0, H, p.job[J_WG2]);
-      const EpiAdagrad e2{P, Pn, p.ada, p.oW2, p.ob2, H, D, hy};
-      const Gemm g6 = make_gemm(p.h_d, nullptr, H, p.dlv, nullptr, D, H + 1, D, M, 0, H, p.job[J_WG6]);
-      const EpiAdagrad e6{P, Pn, p.ada, p.oW6, p.ob6, H, D, hy};
-      const Gemm gz = make_gemm(p.da1, nullptr, H, P + p.oW1, nullptr, H, M, Z, H, 0, -1, p.job[J_DZ]);
-      const EpiDz ez{p.z, p.eps, p.mu, p.ls, Z, p.la, p.w, p.dmu, p.dls};
-      const Gemm g1 = make_gemm(p.z, nullptr, Z, p.da1, nullptr, H, Z + 1, H, M, 0, Z, p.job[J_WG1]);
-      const EpiAdagrad e1{P, Pn, p.ada, p.oW1, p.ob1, Z, H, hy};
-      const int n2 = g2.c.n_items, n6 = p.cont ? g6.c.n_items : 0, nz = gz.c.n_items, n1 = g1.c.n_items;
-      const int total = n2 + n6 + nz + n1 + 1;
-      for (int it = cta; it < total; it += G) {
-        int i = it;
-        if (i < n2) { run_item<FS_JOB(J_WG2), A_KM, B_KN, PLAIN>(g2, i, e2, smem); continue; }
-        i -= n2;
-        if (i < n6) { run_item<FS_JOB(J_WG6), A_KM, B_KN, PLAIN>(g6, i, e6, smem); continue; }
-        i -= n6;
-        if (i < nz) { run_item<FS_JOB(J_DZ), A_MK, B_NK, PLAIN>(gz, i, ez, smem); continue; }
-        i -= nz;
-        if (i < n1) { run_item<FS_JOB(J_WG1), A_KM, B_KN, PLAIN>(g1, i, e1, smem); continue; }
-        // the bound of this step: fixed-order sum of the row partials (VAEB.py:340-344), / Mg
-        const int tc = p.job[J_DEC2].tiles_n, ta = p.job[J_ENC2].tiles_n;
-        float t = 0.f;
-        for (int r = threadIdx.x; r < M; r += NT) {
-          float rsum = 0.f;
-          for (int q = 0; q < tc; ++q) rsum += __ldcg(p.partial + (size_t)r * tc + q);
-          for (int q = 0; q < ta; ++q) rsum += __ldcg(p.aux_part + (size_t)r * ta + q);
-          t += rsum;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = t;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          float b = 0.f;
-          for (int wq = 0; wq < NW; ++wq) b += smem[wq];
-          p.scalars[s] = b / p.Mg;
-        }
-        __syncthreads();
-      }
-    }
-    grid_barrier(p.bar, target += G);
-    if (tm) tm[6] = gtime();
-
-    // ---- phase 7: back through the latent heads | W4, W5 update ---------------------------------
-    {
-      const Gemm gh = make_gemm(p.dmu, p.dls, Z, P + p.oW4, P + p.oW5, Z, M, H, Z, Z, -1, p.job[J_DHE]);
-      const EpiTanhBack eh{p.h_e, p.da3, H};
-      const Gemm g45 = make_gemm(p.h_e, nullptr, H, p.dmu, p.dls, Z, H + 1, Z, M, 0, H, p.job[J_WG45]);
-      const EpiAdagrad2 e45{P, Pn, p.ada, p.oW4, p.ob4, p.oW5, p.ob5, H, Z, hy};
-      const int nh = gh.c.n_items, total = nh + g45.c.n_items;
-      for (int it = cta; it < total; it += G) {
-        if (it < nh) run_item<FS_JOB(J_DHE), A_MK, B_NK, DUALK>(gh, it, eh, smem);
-        else run_item<FS_JOB(J_WG45), A_KM, B_KN, DUALN>(g45, it - nh, e45, smem);
-      }
-    }
-    grid_barrier(p.bar, target += G);
-    if (tm) tm[7] = gtime();
-
-    // ---- phase 8: W3 update -------------------------------------------------------------------
-    {
-      const Gemm g = make_gemm(x, nullptr, D, p.da3, nullptr, H, D + 1, H, M, 0, D, p.job[J_WG3]);
-      const EpiAdagrad epi{P, Pn, p.ada, p.oW3, p.ob3, D, H, hy};
-      for (int it = cta; it < g.c.n_items; it += G) run_item<FS_JOB(J_WG3), A_KM, B_KN, PLAIN>(g, it, epi, smem);
-    }
+    update_phases<FVB>(p, smem, s, x, P, Pu, Pn, fv, hy, target, tm);
     grid_barrier(p.bar, target += G);
     if (tm) tm[8] = gtime();
   }
@@ -760,7 +854,7 @@ static JobCfg plan_job(int job, int M, int N, int K, int n_cta, bool dual_n) {
 
 bool fused_step_supported(const vaeb_handle* h, int rows) {
   const int e = h->cfg.estimator;
-  return (e == VAEB_EST_LB || e == VAEB_EST_LA) && h->L == 1 && h->world == 1 &&
+  return (e == VAEB_EST_LB || e == VAEB_EST_LA || e == VAEB_EST_FVB_SAMPLED) && h->L == 1 && h->world == 1 &&
          h->cfg.precision == VAEB_PREC_FP32 && rows >= 1 && rows <= 4096 && !h->fused_off;
 }
 
@@ -775,10 +869,12 @@ int fused_step_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, 
     VAEB_CUDA(cudaDeviceGetAttribute(&f.n_sm, cudaDevAttrMultiProcessorCount, dev));
     VAEB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     VAEB_REQUIRE(coop != 0, "device lacks cooperative launch");
-    VAEB_CUDA(cudaFuncSetAttribute(fused_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    int occ = 0;
-    VAEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_step_kernel, NT, SMEM_BYTES));
-    VAEB_REQUIRE(occ >= 1, "fused step kernel does not fit on an SM");
+    VAEB_CUDA(cudaFuncSetAttribute(fused_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    VAEB_CUDA(cudaFuncSetAttribute(fused_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    int occ = 0, occ_f = 0;
+    VAEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_step_kernel<false>, NT, SMEM_BYTES));
+    VAEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, fused_step_kernel<true>, NT, SMEM_BYTES));
+    VAEB_REQUIRE(occ >= 1 && occ_f >= 1, "fused step kernel does not fit on an SM");
     VAEB_CUDA(cudaMalloc((void**)&f.bar, sizeof(unsigned long long)));
     VAEB_CUDA(cudaMemset(f.bar, 0, sizeof(unsigned long long)));
     const size_t nb = (size_t)(l.padded + 4) * sizeof(float);
@@ -831,18 +927,29 @@ int fused_step_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, 
   p.h_e = s.h_e; p.mu = s.mu; p.ls = s.ls; p.eps = s.eps; p.z = s.z; p.h_d = s.h_d;
   p.da2 = s.da2; p.dlv = s.dlv; p.da1 = s.da1; p.dmu = s.dmu; p.dls = s.dls; p.da3 = s.da3;
   p.partial = f.partial; p.aux_part = f.aux_part;
-  p.scalars = h->d_scalars + slot0; p.Mg = (float)rows;
+  p.scalars = h->d_scalars + slot0; p.Mg = (float)rows; p.bmult = 1.0f;
+  const bool fvb = h->cfg.estimator == VAEB_EST_FVB_SAMPLED;
+  p.fvb = fvb ? 1 : 0;
+  if (fvb) {
+    // SGVB = x.shape[0]*(sum logp + sum KL) + thetaPrior, update returns SGVB/M (VAEB.py:364,412); the data term of
+    // the gradient carries the same factor M; the prior terms live in the update epilogue
+    if (!f.tprior_part) VAEB_CUDA(cudaMalloc((void**)&f.tprior_part, (size_t)f.n_sm * sizeof(float)));
+    p.w = (float)rows; p.bmult = (float)rows;
+    p.prior = h->cfg.prior_scale; p.p2 = 0.f;
+    p.vmu = h->d_vmu; p.vsig = h->d_vsig; p.ada = h->d_ada_mu; p.ada_sig = h->d_ada_sig;
+    p.theta = h->d_theta; p.zeta = h->d_zeta; p.tprior_part = f.tprior_part; p.total = l.total;
+  }
   p.n_steps = n_steps; p.parity0 = 0;
   p.bar = f.bar; p.bar_base = f.bar_count;
   p.timing = d_timing;
   for (int j = 0; j < J_COUNT; ++j) p.job[j] = f.job[j];
   void* args[] = {&p};
-  VAEB_CUDA(cudaLaunchCooperativeKernel((const void*)fused_step_kernel, dim3(f.n_sm), dim3(NT), args, SMEM_BYTES,
-                                        h->stream));
-  f.bar_count += (unsigned long long)f.n_sm * (unsigned long long)N_PHASES * (unsigned long long)n_steps;
+  const void* kfn = fvb ? (const void*)fused_step_kernel<true> : (const void*)fused_step_kernel<false>;
+  VAEB_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(f.n_sm), dim3(NT), args, SMEM_BYTES, h->stream));
+  f.bar_count += (unsigned long long)f.n_sm * (unsigned long long)(N_PHASES + (fvb ? 1 : 0)) * (unsigned long long)n_steps;
   ++h->launches;
   h->step += (uint32_t)n_steps;
-  if (n_steps & 1) std::swap(h->d_params, f.params_alt);   // theta now lives in the other buffer
+  if ((n_steps & 1) && !fvb) std::swap(h->d_params, f.params_alt);   // theta now lives in the other buffer
   h->grads_have_prior = false;
   return VAEB_OK;
 }

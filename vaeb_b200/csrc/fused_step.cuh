@@ -15,7 +15,7 @@ constexpr int NT = NW * 32;       // threads per CTA
 constexpr int KC = 16;            // contraction chunk staged per warp
 constexpr int NSTAGE = 2;          // cp.async stages per warp
 constexpr int WBUF = 960 * NSTAGE; // floats of shared memory per warp (operand stages, then the tile)
-constexpr int N_PHASES = 8;       // grid barriers per update
+constexpr int N_PHASES = 8;       // grid barriers per update (+1 with sampled full-VB weights)
 constexpr size_t SMEM_BYTES = (size_t)NW * WBUF * sizeof(float) + 64;
 
 // tile jobs of one update, in phase order
@@ -66,7 +66,16 @@ struct StepParams {
   float *h_e, *mu, *ls, *eps, *z, *h_d, *da2, *dlv, *da1, *dmu, *dls, *da3;
   float* partial;                 // [M, tiles_n(J_DEC2)] log-likelihood row partials
   float* aux_part;                // [M, tiles_n(J_ENC2)] KL / LA row partials
-  float* scalars; float Mg;       // scalars[s] = bound of step s / Mg
+  float* scalars; float Mg;       // scalars[s] = (bmult * bound of step s + thetaPrior) / Mg
+  float bmult;
+  // full variational Bayes with sampled weights (VAEB.py:127-129 live, getFVBL :349-367): phase 0 draws
+  // theta = mu + |sigma| zeta for the whole flat buffer, every layer reads theta, the weight-gradient epilogues
+  // update (mu, sigma) and their accumulators
+  int fvb;
+  float *vmu, *vsig, *ada_sig;    // `ada` holds the accumulators of mu
+  float *theta, *zeta;            // this step's weights and their noise (flat, parameter layout)
+  float* tprior_part;             // [gridDim.x] partial sums of thetaPrior (VAEB.py:359-363)
+  int64_t total;                  // parameters in the flat buffer
   int n_steps, parity0;
   unsigned long long* bar; unsigned long long bar_base;
   long long* timing;              // nullptr or [n_steps*(N_PHASES+1)] globaltimer stamps of CTA 0
