@@ -181,6 +181,11 @@ int vaeb_is_logpx(vaeb_handle* h, const float* x, int64_t n, int32_t L, const fl
 int vaeb_reconstruct(vaeb_handle* h, const float* x, int64_t n, int32_t n_samples,
                      const float* eps, float* y_out, float* lv_out);
 
+/* The decoder alone on caller-supplied latent points z[n,Z] (VAEB.py:253-265; the compiled `freyFace(z)` function
+ * of freyFace.py:237-244 that the manifold renderer :350-369 calls): y_out[n,D] = sigmoid(tanh(z.W1+b1).W2+b2),
+ * and for the Gaussian decoder lv_out[n,D] = tanh(z.W1+b1).W6+b6 (else may be NULL). */
+int vaeb_decode(vaeb_handle* h, const float* z, int64_t n, float* y_out, float* lv_out);
+
 /* Dense tanh layers of the AE-side builders (degenerate-vae/mlp.py:66-74 ConstructMLP):
  * out = f(...f(x.W0+b0)...Wk+bk), f = tanh on every layer (act=1) or identity on the last
  * (act_last=0: logpdf.py:72-73 OutToReal; 2: sigmoid, logpdf.py:46-47 OutToProbs). */

@@ -493,3 +493,33 @@ def test_sampled_full_vb_update_fused_kernel_matches_oracle(continuous):
     for i, (a, b) in enumerate(zip(fv, o.fvp)):
         assert_close_tensor(a, b, RTOL, name="fvp %d" % i)
     m.close()
+
+
+@pytest.mark.parametrize("continuous", [False, True])
+def test_decode_and_manifold_grid_match_oracle_decoder(continuous):
+    """vaeb_decode = the decoder alone (VAEB.py:253-265 / the compiled freyFace(z) of freyFace.py:237-244) on the
+    10 x 10 quantile grid of the manifold renderer (freyFace.py:350-352), trained Frey weights for the Gaussian
+    decoder."""
+    from vaeb_b200 import manifold
+    if continuous:
+        D, H, Z = 560, 200, 2
+        params = frey_trained_params()
+    else:
+        D, H, Z = 784, 500, 2
+        params = _rand_params(D, H, Z, False, 5, 0.05)
+    x = np.zeros((4, D), np.float32)
+    m = _model(x, continuous, H, Z, 4, params=params)
+    z = manifold.grid_points()
+    p = O.as_dict([np.asarray(t, np.float64) for t in params], continuous)
+    _, a, lv = O.decoder(p, z.astype(np.float64), continuous)
+    y_ref = 1.0 / (1.0 + np.exp(-a))
+    out = m.decode(z)
+    if continuous:
+        assert_close_tensor(out[0], y_ref, RTOL, name="mu_x")
+        assert_close_tensor(out[1], lv, RTOL, name="log_sigma")
+        assert m.freyFace(z[:1])[0].shape == (1, D)
+    else:
+        assert_close_tensor(out, y_ref, RTOL, name="y")
+    faces, tiled = manifold.render(m)
+    assert faces.shape == (100, D) and tiled.shape[0] == 280
+    m.close()

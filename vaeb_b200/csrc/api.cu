@@ -255,10 +255,11 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   // ---- tensor-core path: mirrors, descriptors -------------------------------------------------
   const bool tcp = h->tc.active;
   TcState& t = h->tc;
-  int x_row_off = 0, bn = 64;
+  int x_row_off = 0, bn = 64, bna = 64;   // UMMA N of the weight-gradient / of the activation layers
   if (tcp) {
     VAEB_TRY(tc_ensure(h, rows, R));
     bn = R >= 1024 ? 128 : 64;
+    bna = tc_act_bn(rows, std::min(H, D));
     tc_set_pdl(R <= 4096);
     TcBuffers b = t.data;
     int64_t rows_data;
@@ -280,9 +281,9 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
       b.xh = t.xsh; b.xl = t.xsl;
       rows_data = rows;
     }
-    if (t.key_rows != rows || t.key_R != R || t.key_data != rows_data || t.key_bn != bn || t.key_x != b.xh) {
-      VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bn, Z));
-      t.key_rows = rows; t.key_R = R; t.key_data = rows_data; t.key_bn = bn; t.key_x = b.xh;
+    if (t.key_rows != rows || t.key_R != R || t.key_data != rows_data || t.key_bn != bna || t.key_x != b.xh) {
+      VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bna, Z));
+      t.key_rows = rows; t.key_R = R; t.key_data = rows_data; t.key_bn = bna; t.key_x = b.xh;
     }
     if (want_grads && b.heh && b.zh && b.d1h && b.ddh && latent_large_batch(rows, H, Z, L))
       PH("weight mirrors / transposes -> bf16 (one launch)", 0, 12.0 * dD * dH + 60.0 * dZ * dH,
@@ -300,8 +301,8 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   // encoder hidden layer, VAEB.py:246
   if (tcp)
     PH("enc1 x.W3+tanh [tcgen05]", 2 * dr * dD * dH, 2.0 * t.ns * (dr * dD + dD * dH) + 4 * dr * dH,
-       tc_enc1(st, lc, t.maps, t.ns, bn, rows, D, H, x_row_off, T_(h, theta, l.ib3), s.h_e, tcl ? tb.heh : nullptr,
-               tcl ? tb.hel : nullptr, tb.ldh));
+       tc_enc1(st, lc, t.maps, t.ns, bna, rows, D, H, x_row_off, T_(h, theta, l.ib3), tcl ? nullptr : s.h_e,
+               tcl ? tb.heh : nullptr, tcl ? tb.hel : nullptr, tb.ldh));   // tcl: every consumer of h_e reads its mirror
   else
     PH("enc1 x.W3+tanh", 2 * dr * dD * dH, 4 * (dr * dD + dD * dH + dr * dH),
        launch_dense_act(st, lc, x, rows, D, T_(h, theta, l.iW3), T_(h, theta, l.ib3), H, 1, s.h_e));
@@ -316,7 +317,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
                      s.eps, s.z, tb.zh, tb.zl, tb.ldz, s.partial, &n_aux));
     VAEB_LAUNCH(launch_row_partials_sum(st, lc, s.partial, n_aux, rows, s.row_aux));
     PH("dec1 tanh(z.W1+b1) [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * 32 + dZ * dH) + 4 * dR * dH + 2.0 * t.ns * dR * dH,
-       tc_dec1(st, lc, t.maps, t.ns, bn, R, Z, H, T_(h, theta, l.ib1), s.h_d, tb.hdh, tb.hdl, tb.ldh));
+       tc_dec1(st, lc, t.maps, t.ns, bna, R, Z, H, T_(h, theta, l.ib1), nullptr, tb.hdh, tb.hdl, tb.ldh));
   } else
   PH("latent fwd (enc2,reparam,KL,dec1)", 4 * dr * dH * dZ + 2 * dR * dZ * dH,
      4 * (dr * dH + 3 * dH * dZ + 2 * dr * dZ + 2 * dR * dZ + dR * dH),
@@ -331,7 +332,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   if (tcp)
     PH("dec2 h.W2+loglik [tcgen05]", 2 * dR * dH * dD,
        2.0 * t.ns * (dR * dH + dH * dD) + 4 * dr * dD + (want_grads ? 2.0 * t.ns * dR * dD : 0.0),
-       tc_dec2_bernoulli(st, lc, t.maps, t.ns, bn, R, H, D, T_(h, theta, l.ib2), x, 1, rows, scale,
+       tc_dec2_bernoulli(st, lc, t.maps, t.ns, bna, R, H, D, T_(h, theta, l.ib2), x, 1, rows, scale,
                          want_grads ? tb.da2h : nullptr, want_grads ? tb.da2l : nullptr, tb.ldd, s.partial, &tiles));
   else
     PH("dec2 h.W2+loglik", 2 * dR * dH * dD * c,
@@ -350,8 +351,8 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
     PH("wgrad W2,b2 [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dH + dR * dD) + 4 * dH * dD,
        tc_wgrad2(st, lc, t.maps, t.ns, bn, R, H, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2), tb.wg_scratch));
     PH("dgrad h_d (.W2^T)*(1-h^2) [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dD + dH * dD) + 8 * dR * dH,
-       tc_dgrad_hd(st, lc, t.maps, t.ns, bn, R, D, H, s.h_d, s.da1, tcl ? tb.d1h : nullptr, tcl ? tb.d1l : nullptr,
-                   tb.ldh));
+       tc_dgrad_hd(st, lc, t.maps, t.ns, bna, R, D, H, tcl ? nullptr : s.h_d, tcl ? nullptr : s.da1,
+                   tcl ? tb.d1h : nullptr, tcl ? tb.d1l : nullptr, tb.ldh, tb.hdh, tb.hdl));
   } else {
     PH("wgrad W2,b2", 2 * dR * dH * dD, 4 * (dR * dH + dR * dD + dH * dD),
        launch_wgrad(st, lc, s.h_d, R, H, s.da2, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2)));
@@ -377,7 +378,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
                        bo.scalar_out, tcl ? tb.ddh : nullptr, tcl ? tb.ddl : nullptr, tb.ldq));
   if (tcl) {
     PH("dgrad h_e ([dmu|dls].W45^T)*(1-h^2) [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * 64 + 2 * dZ * dH) + 8 * dr * dH,
-       tc_dgrad_he(st, lc, t.maps, t.ns, bn, rows, Z, H, s.h_e, s.da3, tb.da3h, tb.da3l, tb.ldh));
+       tc_dgrad_he(st, lc, t.maps, t.ns, bna, rows, Z, H, nullptr, nullptr, tb.da3h, tb.da3l, tb.ldh, tb.heh, tb.hel));
     PH("wgrad W1,b1 [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * 32 + dR * dH) + 4 * dZ * dH,
        tc_wgrad1(st, lc, t.maps, t.ns, bn, R, Z, H, T_(h, grads, l.iW1), T_(h, grads, l.ib1), tb.wg_scratch));
     PH("wgrad W4,b4,W5,b5 [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * dH + dr * 64) + 8 * dZ * dH,
@@ -1161,6 +1162,34 @@ int vaeb_reconstruct(vaeb_handle* h, const float* x, int64_t n, int32_t n_sample
                                   d_y, d_lv, 1.0f / (float)passes, sidx == 0));
   }
   ++h->step;
+  VAEB_CUDA(cudaMemcpyAsync(y_out, d_y, (size_t)n * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (h->cont)
+    VAEB_CUDA(cudaMemcpyAsync(lv_out, d_lv, (size_t)n * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+  VAEB_CUDA(cudaStreamSynchronize(st));
+  return VAEB_OK;
+}
+
+int vaeb_decode(vaeb_handle* h, const float* z, int64_t n, float* y_out, float* lv_out) {
+  if (h && h->a_pending) VAEB_TRY(async_flush(h));
+  VAEB_REQUIRE(h && z && y_out && n > 0, "null argument");
+  VAEB_REQUIRE(!h->cont || lv_out, "the Gaussian decoder needs lv_out");
+  VAEB_REQUIRE(n < (int64_t)1 << 24, "too many latent points for one decode call");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  const Layout& l = h->lay;
+  const int D = h->D, H = h->H, Z = h->Z;
+  VAEB_TRY(ensure_ws(h, n, n, false));
+  VAEB_TRY(stage_in(h, &h->d_stage2, &h->stage2_cap, z, n * Z));
+  VAEB_TRY(grow(&h->d_out, &h->out_cap, 2 * n * D));
+  float* d_y = h->d_out;
+  float* d_lv = h->d_out + n * D;
+  cudaStream_t st = h->stream;
+  int64_t* lc = &h->launches;
+  const float* th = h->d_params;
+  Workspace& s = h->ws;
+  VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage2, (int)n, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, 1, s.h_d));
+  VAEB_LAUNCH(launch_dec2_recon(st, lc, h->cont, s.h_d, (int)n, H, T_(h, th, l.iW2), T_(h, th, l.ib2),
+                                h->cont ? T_(h, th, l.iW6) : nullptr, h->cont ? T_(h, th, l.ib6) : nullptr, D, d_y, d_lv,
+                                1.0f, true));
   VAEB_CUDA(cudaMemcpyAsync(y_out, d_y, (size_t)n * D * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (h->cont)
     VAEB_CUDA(cudaMemcpyAsync(lv_out, d_lv, (size_t)n * D * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -68,6 +68,7 @@ __device__ __forceinline__ void st16_split(__nv_bfloat16* hi, __nv_bfloat16* lo,
   }
 }
 
+// out == nullptr: only the mirror is written (large-batch path: every consumer reads the bf16 mirrors)
 struct EpiTanh {            // out[row, col] = tanh(acc + bias[col]) (+ optional bf16 hi/lo mirror of it)
   const float* bias; float* out; int ld;
   __nv_bfloat16* mh; __nv_bfloat16* ml; int ldm;
@@ -75,13 +76,13 @@ struct EpiTanh {            // out[row, col] = tanh(acc + bias[col]) (+ optional
   __device__ __forceinline__ void split(int) {}
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
     if (!ok) return;
-    float* o = out + (size_t)row * ld + col0;
-    if (vec_ok(o, col0, N) && vec_ok(bias + col0, col0, N)) {
+    float* o = out ? out + (size_t)row * ld + col0 : nullptr;
+    if (vec_ok(o, col0, N) && vec_ok(bias + col0, col0, N) && vec_ok(mh ? mh + (size_t)row * ldm + col0 : nullptr, col0, N)) {
       float b[16], r[16];
       ld16f(bias + col0, b);
 #pragma unroll
       for (int j = 0; j < 16; ++j) r[j] = tanhf(v[j] + b[j]);
-      st16f(o, r);
+      if (out) st16f(o, r);
       if (mh) st16_split(mh + (size_t)row * ldm + col0, ml ? ml + (size_t)row * ldm + col0 : nullptr, r);
       return;
     }
@@ -89,7 +90,7 @@ struct EpiTanh {            // out[row, col] = tanh(acc + bias[col]) (+ optional
     for (int j = 0; j < 16; ++j)
       if (col0 + j < N) {
         const float t = tanhf(v[j] + bias[col0 + j]);
-        o[j] = t;
+        if (out) o[j] = t;
         if (mh) put_split(mh, ml, (size_t)row * ldm + col0 + j, t);
       }
   }
@@ -155,30 +156,61 @@ struct EpiWgradTc {         // rows < Hreal -> gW[Hreal, N]; row == Hreal (the o
   __device__ __forceinline__ void end(int, bool, int, int) {}
 };
 
+// h comes in fp32 (h != nullptr) or as its bf16 mirror hh (+ hl: hi + lo carries 16 mantissa bits); out == nullptr:
+// only the mirror of the result is written (large-batch path)
+__device__ __forceinline__ void ld16bf(const __nv_bfloat16* p, float* d) {
+  const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    d[2 * q] = __uint_as_float(w[q] << 16);
+    d[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+  }
+}
 struct EpiDgradTanh {       // out = acc * (1 - h^2) (+ optional bf16 hi/lo mirror of it)
   const float* h; float* out; int ld;
   __nv_bfloat16* mh; __nv_bfloat16* ml; int ldm;
+  const __nv_bfloat16* hh; const __nv_bfloat16* hl;      // mirror of h, leading dimension ldm
   __device__ __forceinline__ void begin() {}
   __device__ __forceinline__ void split(int) {}
+  __device__ __forceinline__ float hval(int row, int c) const {
+    if (h) return h[(size_t)row * ld + c];
+    float t = __bfloat162float(hh[(size_t)row * ldm + c]);
+    if (hl) t += __bfloat162float(hl[(size_t)row * ldm + c]);
+    return t;
+  }
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
     if (!ok) return;
-    const float* hp = h + (size_t)row * ld + col0;
-    float* o = out + (size_t)row * ld + col0;
-    if (vec_ok(hp, col0, N) && vec_ok(o, col0, N)) {
+    const float* hp = h ? h + (size_t)row * ld + col0 : nullptr;
+    float* o = out ? out + (size_t)row * ld + col0 : nullptr;
+    const size_t om = (size_t)row * ldm + col0;
+    if (vec_ok(hp, col0, N) && vec_ok(o, col0, N) && vec_ok(mh ? mh + om : nullptr, col0, N) &&
+        vec_ok(hh ? hh + om : nullptr, col0, N)) {
       float hv[16], r[16];
-      ld16f(hp, hv);
+      if (h) {
+        ld16f(hp, hv);
+      } else {
+        ld16bf(hh + om, hv);
+        if (hl) {
+          float lo[16];
+          ld16bf(hl + om, lo);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) hv[j] += lo[j];
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) r[j] = v[j] * (1.0f - hv[j] * hv[j]);
-      st16f(o, r);
-      if (mh) st16_split(mh + (size_t)row * ldm + col0, ml ? ml + (size_t)row * ldm + col0 : nullptr, r);
+      if (out) st16f(o, r);
+      if (mh) st16_split(mh + om, ml ? ml + om : nullptr, r);
       return;
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j)
       if (col0 + j < N) {
-        const float t = v[j] * (1.0f - hp[j] * hp[j]);
-        o[j] = t;
-        if (mh) put_split(mh, ml, (size_t)row * ldm + col0 + j, t);
+        const float hvj = hval(row, col0 + j);
+        const float t = v[j] * (1.0f - hvj * hvj);
+        if (out) o[j] = t;
+        if (mh) put_split(mh, ml, om + j, t);
       }
   }
   __device__ __forceinline__ void end(int, bool, int, int) {}
@@ -375,6 +407,180 @@ tc_layer_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, i
   if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---- persistent form for large batches (A K-major: the activation layers) ---------------------------------
+// One CTA per SM walks the tile list (tile = blockIdx.x + i * gridDim.x; tiles of one row block are neighbours, so
+// the A rows are fetched from HBM once and shared through L2).  Two TMEM accumulators: the epilogue of tile i
+// (16 warps) overlaps the loads and MMAs of tile i+1; the operand ring keeps its phase across tiles, so the TMA
+// producer runs ahead into the next tile while the last k blocks of this one are still being contracted.  BN up to
+// 256 (2 x 256 TMEM columns): a 128 x 256 tile re-reads A half as often as two 128 x 128 tiles -- these layers are
+// bound by L2 -> shared-memory operand traffic (K <= 784: 64 flop per operand byte at 128 x 128).
+template <int BN, int NS>
+struct PersistSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = NS * (A_BYTES + B_BYTES);
+  static constexpr int BUDGET = 208 * 1024;
+  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+  static_assert(STAGES >= 2, "tile too large");
+};
+
+template <int BN, bool B_MN, int NS, class Epi>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, int K, int a_row_off) {
+  using S = PersistSmem<BN, NS>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + S::STAGES * S::STAGE_BYTES);
+  uint64_t* empty = full + S::STAGES;
+  uint64_t* tmem_full = empty + S::STAGES;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (K + BK - 1) / BK;
+  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BM - 1) / BM;
+  const int n_tiles = tiles_m * tiles_n;
+  constexpr uint32_t ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&maps.a_hi);
+    tc::tma_prefetch_desc(&maps.b_hi);
+    if (NS == 2) { tc::tma_prefetch_desc(&maps.a_lo); tc::tma_prefetch_desc(&maps.b_lo); }
+    for (int s = 0; s < S::STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(&tmem_full[b], 1); tc::mbar_init(&tmem_empty[b], EPI_WARPS); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, TMEM_COLS);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    uint32_t it = 0;                                   // k blocks issued so far (ring position across tiles)
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % S::STAGES;
+        tc::mbar_wait(&empty[s], ((it / S::STAGES) & 1) ^ 1);
+        uint8_t* base = smem + s * S::STAGE_BYTES;
+        tc::mbar_expect_tx(&full[s], S::STAGE_BYTES);
+#pragma unroll
+        for (int sp = 0; sp < NS; ++sp) {
+          uint8_t* a = base + sp * S::A_BYTES;
+          uint8_t* b = base + NS * S::A_BYTES + sp * S::B_BYTES;
+          const CUtensorMap* ta = sp ? &maps.a_lo : &maps.a_hi;
+          const CUtensorMap* tb = sp ? &maps.b_lo : &maps.b_hi;
+          tc::tma_load_2d(a, ta, &full[s], kb * BK, a_row_off + m0);
+          if (B_MN) {
+            for (int g = 0; g < BN / 64; ++g) tc::tma_load_2d(b + g * 8192, tb, &full[s], n0 + g * 64, kb * BK);
+          } else {
+            tc::tma_load_2d(b, tb, &full[s], kb * BK, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN, 0, B_MN ? 1 : 0);
+    uint32_t it = 0, lt = 0;                           // ring position; tiles done by this CTA
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t buf = lt & 1;
+      tc::mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1) ^ 1);     // the epilogue drained this accumulator
+      tc::tc_fence_after();
+      const uint32_t acc = tmem_base + buf * ACC_COLS;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % S::STAGES;
+        tc::mbar_wait(&full[s], (it / S::STAGES) & 1);
+        tc::tc_fence_after();
+        const uint32_t a = tc::smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t b = a + NS * S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          const uint64_t dah = tc::desc_kmajor(a, k);
+          const uint64_t dbh = B_MN ? tc::desc_mnmajor(b, k, 8192u) : tc::desc_kmajor(b, k);
+          tc::umma_bf16(acc, dah, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (NS == 2) {
+            const uint64_t dal = tc::desc_kmajor(a + S::A_BYTES, k);
+            const uint64_t dbl = B_MN ? tc::desc_mnmajor(b + S::B_BYTES, k, 8192u) : tc::desc_kmajor(b + S::B_BYTES, k);
+            tc::umma_bf16(acc, dah, dbl, idesc, 1u);
+            tc::umma_bf16(acc, dal, dbh, idesc, 1u);
+          }
+        }
+        tc::umma_commit(&empty[s]);
+      }
+      tc::umma_commit(&tmem_full[buf]);
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: warp e = warp-4 reads lane quarter e%4, column slice e/4 of the tile =====
+    const int q = warp & 3, cs = (warp - 4) >> 2;
+    constexpr int SLICE = BN / (EPI_WARPS / 4);
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const int tm = tile / tiles_n, tn = tile % tiles_n;
+      const int m0 = tm * BM, n0 = tn * BN;
+      const uint32_t buf = lt & 1;
+      const int row = m0 + q * 32 + lane;
+      const bool ok = row < M;
+      epi.begin();
+      tc::mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
+      tc::tc_fence_after();
+      const uint32_t acc = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = cs * SLICE; c < (cs + 1) * SLICE; c += 16) {
+        float v[16];
+        tc::tmem_ld16(acc + (uint32_t)c, v);
+        tc::tmem_ld_wait();
+        if (c + 16 >= (cs + 1) * SLICE) {               // last read of this warp: hand the accumulator back early
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
+        }
+        if (n0 + c < N) epi.chunk(row, ok, n0 + c, N, v);
+      }
+      epi.end(row, ok, tn * (EPI_WARPS / 4) + cs, tiles_n * (EPI_WARPS / 4));
+    }
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+int g_persist = -1;     // -1: by size; 0 / 1: forced (VAEB_TC_PERSIST, measurement switch)
+
+template <int BN, bool B_MN, int NS, class Epi>
+cudaError_t launch_layer_persistent(cudaStream_t st, const LayerMaps& maps, const Epi& epi, int M, int N, int K,
+                                    int a_row_off) {
+  using S = PersistSmem<BN, NS>;
+  auto kfn = tc_layer_persistent_kernel<BN, B_MN, NS, Epi>;
+  static bool attr_done = false;   // per instantiation
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles < 148 ? tiles : 148);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = st;
+  cfg.numAttrs = 0;
+  return cudaLaunchKernelEx(&cfg, kfn, maps, epi, M, N, K, a_row_off);
+}
+
+// the persistent form pays off from about two tiles per SM
+inline bool use_persistent(int M, int N, int bn) {
+  if (g_persist == -1) { const char* e = getenv("VAEB_TC_PERSIST"); g_persist = e ? (e[0] != '0' ? 1 : 0) : 2; }
+  if (g_persist != 2) return g_persist == 1;
+  return ((N + bn - 1) / bn) * ((M + BM - 1) / BM) >= 148 + 74;
+}
+
 bool g_pdl = false;
 
 template <int BN, bool A_MN, bool B_MN, int NS, class Epi>
@@ -408,6 +614,12 @@ cudaError_t launch_layer(cudaStream_t st, const LayerMaps& maps, const Epi& epi,
 template <bool A_MN, bool B_MN, class Epi>
 cudaError_t dispatch_layer(cudaStream_t st, int ns, int bn, const LayerMaps& maps, const Epi& epi, int M, int N, int K,
                            int a_row_off, int splits = 1) {
+  if constexpr (!A_MN) {
+    if (bn == 256) {                   // tc_act_bn chose the persistent form
+      if (ns == 2) return launch_layer_persistent<256, B_MN, 2, Epi>(st, maps, epi, M, N, K, a_row_off);
+      return launch_layer_persistent<256, B_MN, 1, Epi>(st, maps, epi, M, N, K, a_row_off);
+    }
+  }
   if (ns == 2) {
     if (bn == 128) return launch_layer<128, A_MN, B_MN, 2, Epi>(st, maps, epi, M, N, K, a_row_off, splits);
     return launch_layer<64, A_MN, B_MN, 2, Epi>(st, maps, epi, M, N, K, a_row_off, splits);
@@ -533,6 +745,11 @@ cudaError_t tc_prepare_weights(cudaStream_t st, int64_t* launches, const float* 
 // ---- host API (tc_layers.h) -------------------------------------------------------------------
 void tc_set_pdl(bool on) { g_pdl = on; }
 
+int tc_act_bn(int rows, int n_min) {
+  if (use_persistent(rows, n_min, 256)) return 256;
+  return rows >= 1024 ? 128 : 64;
+}
+
 cudaError_t tc_split_matrix(cudaStream_t st, int64_t* launches, const float* src, int64_t rows, int cols, int ld_src,
                             void* hi, void* lo, int ld_dst, int ones_col) {
   const int64_t n = rows * ld_dst;
@@ -630,8 +847,10 @@ cudaError_t tc_dec2_bernoulli(cudaStream_t st, int64_t* launches, const TcMaps& 
 }
 
 cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int D, int H,
-                        const float* h_d, float* da1, void* d1_hi, void* d1_lo, int ldm) {
-  EpiDgradTanh epi{h_d, da1, H, (__nv_bfloat16*)d1_hi, (__nv_bfloat16*)d1_lo, ldm};
+                        const float* h_d, float* da1, void* d1_hi, void* d1_lo, int ldm, const void* h_hi,
+                        const void* h_lo) {
+  EpiDgradTanh epi{h_d, da1, H, (__nv_bfloat16*)d1_hi, (__nv_bfloat16*)d1_lo, ldm,
+                   (const __nv_bfloat16*)h_hi, (const __nv_bfloat16*)h_lo};
   ++*launches;
   return dispatch_layer<false, false>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.dgrad), epi, R, H, D, 0);
 }
@@ -679,8 +898,10 @@ cudaError_t tc_dz_dprep(cudaStream_t st, int64_t* launches, const TcMaps& m, int
 }
 
 cudaError_t tc_dgrad_he(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int Z, int H,
-                        const float* h_e, float* da3, void* da3_hi, void* da3_lo, int ldm) {
-  EpiDgradTanh epi{h_e, da3, H, (__nv_bfloat16*)da3_hi, (__nv_bfloat16*)da3_lo, ldm};
+                        const float* h_e, float* da3, void* da3_hi, void* da3_lo, int ldm, const void* h_hi,
+                        const void* h_lo) {
+  EpiDgradTanh epi{h_e, da3, H, (__nv_bfloat16*)da3_hi, (__nv_bfloat16*)da3_lo, ldm,
+                   (const __nv_bfloat16*)h_hi, (const __nv_bfloat16*)h_lo};
   ++*launches;
   return dispatch_layer<false, true>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.dhe), epi, rows, H, 2 * Z, 0);
 }

@@ -42,6 +42,9 @@ struct TcMaps {
 // programmatic dependent launch of the layer kernels (their prologues overlap the previous kernel's tail): for steps
 // whose kernels are all about one wave
 void tc_set_pdl(bool on);
+// UMMA N of the activation layers (A K-major) for `rows` rows and outputs at least n_min wide: 256 selects the
+// persistent kernel (large batches), else 128 / 64 with one tile per CTA
+int tc_act_bn(int rows, int n_min);
 int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z);
 
 cudaError_t tc_split_matrix(cudaStream_t st, int64_t* launches, const float* src, int64_t rows, int cols, int ld_src,
@@ -54,7 +57,8 @@ cudaError_t tc_dec2_bernoulli(cudaStream_t st, int64_t* launches, const TcMaps& 
                               const float* b2, const float* x, int x_div, int x_mod, float scale, void* da_hi,
                               void* da_lo, int ldda, float* partial, int* n_tiles);
 cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int D, int H,
-                        const float* h_d, float* da1, void* d1_hi, void* d1_lo, int ldm);
+                        const float* h_d, float* da1, void* d1_hi, void* d1_lo, int ldm, const void* h_hi = nullptr,
+                        const void* h_lo = nullptr);   // h_d == nullptr: h is read from its mirror; da1 == nullptr: mirror only
 // thin weight gradients of the latent layers on tcgen05 (large batch): split-K over the rows, fixed-order reduction
 cudaError_t tc_wgrad1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int Z, int H,
                       float* gW1, float* gb1, float* scratch);
@@ -79,7 +83,8 @@ cudaError_t tc_dz_dprep(cudaStream_t st, int64_t* launches, const TcMaps& m, int
                         const float* z, const float* eps, const float* mu, const float* ls, float* dmu, float* dls,
                         void* dd_hi, void* dd_lo, int ldq);
 cudaError_t tc_dgrad_he(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int Z, int H,
-                        const float* h_e, float* da3, void* da3_hi, void* da3_lo, int ldm);
+                        const float* h_e, float* da3, void* da3_hi, void* da3_lo, int ldm, const void* h_hi = nullptr,
+                        const void* h_lo = nullptr);
 cudaError_t tc_wgrad45(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int rows, int H, int Z, float* gW4,
                        float* gb4, float* gW5, float* gb5, float* scratch);
 // scratch: device floats for the split-K slices of a weight gradient (tc_wgrad_scratch_elems), or nullptr

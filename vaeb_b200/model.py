@@ -303,6 +303,17 @@ class VAEB(object):
             y = y + np.exp(lv) * np.random.standard_normal(y.shape).astype(np.float32)
         return y[0] if single else y
 
+    def decode(self, z):
+        """The decoder alone (VAEB.py:253-265) on latent points z[n, Z]: y for the Bernoulli decoder,
+        (mu, log_sigma) for the Gaussian one -- what the compiled `freyFace(z)` of freyFace.py:237-244 returns."""
+        za = _f32(z).reshape(-1, self.n_latent)
+        y = np.empty((za.shape[0], self.input_size), np.float32)
+        lv = np.empty_like(y) if self.continuous else None
+        _lib.check(self._lib.vaeb_decode(self._h, _ptr(za), za.shape[0], _ptr(y), _ptr(lv)))
+        return (y, lv) if self.continuous else y
+
+    freyFace = decode       # freyFace.py:137 names the compiled decoder function after its first use
+
     # ---- persistence ---------------------------------------------------------------------
     def save(self, file_name):
         """VAEB.py:189-203 (plus the `genericEstimator` entry `load` expects, VAEB.py:218)."""
