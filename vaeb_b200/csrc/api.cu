@@ -256,11 +256,14 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   const bool tcp = h->tc.active;
   TcState& t = h->tc;
   int x_row_off = 0, bn = 64, bna = 64;   // UMMA N of the weight-gradient / of the activation layers
+  const void *x_mirror_hi = nullptr, *x_mirror_lo = nullptr;
   if (tcp) {
     VAEB_TRY(tc_ensure(h, rows, R));
     bn = R >= 1024 ? 128 : 64;
     bna = tc_act_bn(rows, std::min(H, D));
-    tc_set_pdl(R <= 4096);
+    // bf16x3 kernels are one CTA per SM: an early dependent grid never takes slots from the running one (16384 rows:
+    // 523 -> 499 us per update); in plain bf16 (two CTAs per SM) it does beyond about one wave (331 -> 355 us)
+    tc_set_pdl(R <= 4096 || t.ns == 2);
     TcBuffers b = t.data;
     int64_t rows_data;
     const bool resident = h->d_x && x >= h->d_x && x < h->d_x + (size_t)h->n_data * D;
@@ -281,6 +284,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
       b.xh = t.xsh; b.xl = t.xsl;
       rows_data = rows;
     }
+    x_mirror_hi = b.xh; x_mirror_lo = t.ns == 2 ? b.xl : nullptr;
     if (t.key_rows != rows || t.key_R != R || t.key_data != rows_data || t.key_bn != bna || t.key_x != b.xh) {
       VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bna, Z));
       t.key_rows = rows; t.key_R = R; t.key_data = rows_data; t.key_bn = bna; t.key_x = b.xh;
@@ -332,8 +336,9 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   if (tcp)
     PH("dec2 h.W2+loglik [tcgen05]", 2 * dR * dH * dD,
        2.0 * t.ns * (dR * dH + dH * dD) + 4 * dr * dD + (want_grads ? 2.0 * t.ns * dR * dD : 0.0),
-       tc_dec2_bernoulli(st, lc, t.maps, t.ns, bna, R, H, D, T_(h, theta, l.ib2), x, 1, rows, scale,
-                         want_grads ? tb.da2h : nullptr, want_grads ? tb.da2l : nullptr, tb.ldd, s.partial, &tiles));
+       tc_dec2_bernoulli(st, lc, t.maps, t.ns, bna, R, H, D, T_(h, theta, l.ib2), tcl ? nullptr : x, 1, rows, scale,
+                         want_grads ? tb.da2h : nullptr, want_grads ? tb.da2l : nullptr, tb.ldd, s.partial, &tiles,
+                         x_mirror_hi, x_mirror_lo, tb.ldx, x_row_off));   // tcl: x from the mirror enc1 reads
   else
     PH("dec2 h.W2+loglik", 2 * dR * dH * dD * c,
        4 * (dR * dH + c * dH * dD + dr * dD + (want_grads ? c * dR * dD : 0.0)),

@@ -46,6 +46,15 @@ __device__ __forceinline__ void ld16f(const float* p, float* d) {
     d[4 * q] = t.x; d[4 * q + 1] = t.y; d[4 * q + 2] = t.z; d[4 * q + 3] = t.w;
   }
 }
+__device__ __forceinline__ void ld16bf(const __nv_bfloat16* p, float* d) {
+  const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    d[2 * q] = __uint_as_float(w[q] << 16);
+    d[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+  }
+}
 __device__ __forceinline__ void st16f(float* p, const float* d) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
@@ -100,6 +109,8 @@ struct EpiTanh {            // out[row, col] = tanh(acc + bias[col]) (+ optional
 struct EpiBernoulliTc {     // VAEB.py:263,311: term = x*a - softplus(a); da = scale*(x - sigmoid(a))
   const float* bias; const float* x; int ldx; int x_div; int x_mod; float scale;
   __nv_bfloat16* da_hi; __nv_bfloat16* da_lo; int ldda; float* partial;
+  // x == nullptr: x is read from its bf16 mirror (hi + lo when present), row offset xm_off, leading dimension ldxm
+  const __nv_bfloat16* xm_hi; const __nv_bfloat16* xm_lo; int ldxm; int xm_off;
   float acc;
   __device__ __forceinline__ void begin() { acc = 0.f; }
   __device__ __forceinline__ void split(int) {}
@@ -112,13 +123,26 @@ struct EpiBernoulliTc {     // VAEB.py:263,311: term = x*a - softplus(a); da = s
   }
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
     if (!ok) return;
-    const float* xr = x + (size_t)((row / x_div) % x_mod) * ldx + col0;
+    const int xrow = (row / x_div) % x_mod;
+    const float* xr = x ? x + (size_t)xrow * ldx + col0 : nullptr;
+    const size_t oxm = (size_t)(xm_off + xrow) * ldxm + col0;
     __nv_bfloat16* dh = da_hi ? da_hi + (size_t)row * ldda + col0 : nullptr;
     __nv_bfloat16* dl = da_lo ? da_lo + (size_t)row * ldda + col0 : nullptr;
-    if (vec_ok(xr, col0, N) && vec_ok(bias + col0, col0, N) && vec_ok(dh, col0, N) && vec_ok(dl, col0, N)) {
+    if (vec_ok(xr, col0, N) && vec_ok(bias + col0, col0, N) && vec_ok(dh, col0, N) && vec_ok(dl, col0, N) &&
+        vec_ok(x ? nullptr : xm_hi + oxm, col0, N)) {
       float b[16], xv[16], d[16];
       ld16f(bias + col0, b);
-      ld16f(xr, xv);
+      if (x) {
+        ld16f(xr, xv);
+      } else {
+        ld16bf(xm_hi + oxm, xv);
+        if (xm_lo) {
+          float lo[16];
+          ld16bf(xm_lo + oxm, lo);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) xv[j] += lo[j];
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) d[j] = one(v[j] + b[j], xv[j]);
       if (dh) st16_split(dh, dl, d);
@@ -128,7 +152,10 @@ struct EpiBernoulliTc {     // VAEB.py:263,311: term = x*a - softplus(a); da = s
     for (int j = 0; j < 16; ++j) {
       const int c = col0 + j;
       if (c < N) {
-        const float d = one(v[j] + bias[c], xr[j]);
+        float xj;
+        if (x) xj = xr[j];
+        else xj = __bfloat162float(xm_hi[oxm + j]) + (xm_lo ? __bfloat162float(xm_lo[oxm + j]) : 0.f);
+        const float d = one(v[j] + bias[c], xj);
         if (dh) put_split(dh, dl, (size_t)j, d);
       }
     }
@@ -158,15 +185,6 @@ struct EpiWgradTc {         // rows < Hreal -> gW[Hreal, N]; row == Hreal (the o
 
 // h comes in fp32 (h != nullptr) or as its bf16 mirror hh (+ hl: hi + lo carries 16 mantissa bits); out == nullptr:
 // only the mirror of the result is written (large-batch path)
-__device__ __forceinline__ void ld16bf(const __nv_bfloat16* p, float* d) {
-  const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
-  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    d[2 * q] = __uint_as_float(w[q] << 16);
-    d[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
-  }
-}
 struct EpiDgradTanh {       // out = acc * (1 - h^2) (+ optional bf16 hi/lo mirror of it)
   const float* h; float* out; int ld;
   __nv_bfloat16* mh; __nv_bfloat16* ml; int ldm;
@@ -407,6 +425,8 @@ tc_layer_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, i
   if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+bool g_pdl = false;
+
 // ---- persistent form for large batches (A K-major: the activation layers) ---------------------------------
 // One CTA per SM walks the tile list (tile = blockIdx.x + i * gridDim.x; tiles of one row block are neighbours, so
 // the A rows are fetched from HBM once and shared through L2).  Two TMEM accumulators: the epilogue of tile i
@@ -570,7 +590,11 @@ cudaError_t launch_layer_persistent(cudaStream_t st, const LayerMaps& maps, cons
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = st;
-  cfg.numAttrs = 0;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kfn, maps, epi, M, N, K, a_row_off);
 }
 
@@ -581,7 +605,6 @@ inline bool use_persistent(int M, int N, int bn) {
   return ((N + bn - 1) / bn) * ((M + BM - 1) / BM) >= 148 + 74;
 }
 
-bool g_pdl = false;
 
 template <int BN, bool A_MN, bool B_MN, int NS, class Epi>
 cudaError_t launch_layer(cudaStream_t st, const LayerMaps& maps, const Epi& epi, int M, int N, int K, int a_row_off,
@@ -839,8 +862,10 @@ cudaError_t tc_enc1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns,
 
 cudaError_t tc_dec2_bernoulli(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
                               const float* b2, const float* x, int x_div, int x_mod, float scale, void* da_hi,
-                              void* da_lo, int ldda, float* partial, int* n_tiles) {
-  EpiBernoulliTc epi{b2, x, D, x_div, x_mod, scale, (__nv_bfloat16*)da_hi, (__nv_bfloat16*)da_lo, ldda, partial, 0.f};
+                              void* da_lo, int ldda, float* partial, int* n_tiles, const void* xm_hi, const void* xm_lo,
+                              int ldxm, int xm_off) {
+  EpiBernoulliTc epi{b2, x, D, x_div, x_mod, scale, (__nv_bfloat16*)da_hi, (__nv_bfloat16*)da_lo, ldda, partial,
+                     (const __nv_bfloat16*)xm_hi, (const __nv_bfloat16*)xm_lo, ldxm, xm_off, 0.f};
   *n_tiles = ((D + bn - 1) / bn) * (EPI_WARPS / 4);
   ++*launches;
   return dispatch_layer<false, true>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.dec2), epi, R, D, H, 0);

@@ -55,7 +55,8 @@ cudaError_t tc_enc1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns,
                     int x_row_off, const float* b3, float* h_e, void* he_hi, void* he_lo, int ldm);
 cudaError_t tc_dec2_bernoulli(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
                               const float* b2, const float* x, int x_div, int x_mod, float scale, void* da_hi,
-                              void* da_lo, int ldda, float* partial, int* n_tiles);
+                              void* da_lo, int ldda, float* partial, int* n_tiles, const void* xm_hi = nullptr,
+                              const void* xm_lo = nullptr, int ldxm = 0, int xm_off = 0);   // x == nullptr: x from its mirror
 cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int D, int H,
                         const float* h_d, float* da1, void* d1_hi, void* d1_lo, int ldm, const void* h_hi = nullptr,
                         const void* h_lo = nullptr);   // h_d == nullptr: h is read from its mirror; da1 == nullptr: mirror only
