@@ -156,7 +156,7 @@ int tc_ensure(vaeb_handle* h, int64_t rows, int64_t R) {
     VAEB_TRY(grow_bytes(&b.w2h, (size_t)H * b.ldd * 2));
     VAEB_CUDA(cudaMemsetAsync(b.w3h, 0, (size_t)D * b.ldh * 2, h->stream));
     VAEB_CUDA(cudaMemsetAsync(b.w2h, 0, (size_t)H * b.ldd * 2, h->stream));
-    VAEB_TRY(grow_bytes((void**)&b.wg_scratch, tc_wgrad_scratch_elems(D, H) * sizeof(float)));
+    VAEB_TRY(grow_bytes((void**)&b.wg_scratch, 4 * tc_wgrad_scratch_elems(D, H) * sizeof(float)));   // a region per weight gradient
     if (lo) {
       VAEB_TRY(grow_bytes(&b.w3l, (size_t)D * b.ldh * 2));
       VAEB_TRY(grow_bytes(&b.w2l, (size_t)H * b.ldd * 2));
@@ -302,6 +302,11 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   // large-batch training on the tensor-core path: the thin weight gradients also run on tcgen05 (their operands'
   // bf16 mirrors come from the kernels that produce h_e, z, da1 and [dmu|dls])
   const bool tcl = tcp && want_grads && tb.heh && tb.zh && tb.d1h && tb.ddh && latent_large_batch(rows, H, Z, L);
+  // large batch: the split-K slices of the four weight-gradient GEMMs stay in their scratch regions and ONE launch
+  // after the last GEMM sums them all (4 launches less per update)
+  TcReduceJobs reduce_jobs;
+  TcReduceJobs* defer = tcl ? &reduce_jobs : nullptr;
+  const size_t wg_region = tcp ? tc_wgrad_scratch_elems(D, H) : 0;
   // encoder hidden layer, VAEB.py:246
   if (tcp)
     PH("enc1 x.W3+tanh [tcgen05]", 2 * dr * dD * dH, 2.0 * t.ns * (dr * dD + dD * dH) + 4 * dr * dH,
@@ -354,7 +359,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   // backward (T.grad, VAEB.py:397); formulas in SURVEY.md 8a
   if (tcp) {
     PH("wgrad W2,b2 [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dH + dR * dD) + 4 * dH * dD,
-       tc_wgrad2(st, lc, t.maps, t.ns, bn, R, H, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2), tb.wg_scratch));
+       tc_wgrad2(st, lc, t.maps, t.ns, bn, R, H, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2), tb.wg_scratch, defer));
     PH("dgrad h_d (.W2^T)*(1-h^2) [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dD + dH * dD) + 8 * dR * dH,
        tc_dgrad_hd(st, lc, t.maps, t.ns, bna, R, D, H, tcl ? nullptr : s.h_d, tcl ? nullptr : s.da1,
                    tcl ? tb.d1h : nullptr, tcl ? tb.d1l : nullptr, tb.ldh, tb.hdh, tb.hdl));
@@ -372,7 +377,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
        tc_dz_dprep(st, lc, t.maps, t.ns, R, H, Z, la, w, s.z, s.eps, s.mu, s.ls, s.dmu, s.dls, tb.ddh, tb.ddl, tb.ldq));
     PH("bound (per row + total)", 0, 4 * (dR * tiles + 2 * dr),
        launch_finalize(st, lc, s.partial, tiles, s.row_aux, rows, L, s.per_row, bo.base_out, bo.mult, bo.tprior,
-                       bo.n_tprior, bo.div, bo.scalar_out));
+                       bo.n_tprior, bo.div, bo.scalar_out, h->d_counter));
   } else
   PH("latent bwd (dz,dmu,dls,da3,bound)", 2 * dR * dZ * dH + 4 * dr * dH * dZ,
      4 * (dR * dH + 3 * dZ * dH + 2 * dr * dH + 3 * dR * dZ + dR * tiles),
@@ -385,10 +390,11 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
     PH("dgrad h_e ([dmu|dls].W45^T)*(1-h^2) [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * 64 + 2 * dZ * dH) + 8 * dr * dH,
        tc_dgrad_he(st, lc, t.maps, t.ns, bna, rows, Z, H, nullptr, nullptr, tb.da3h, tb.da3l, tb.ldh, tb.heh, tb.hel));
     PH("wgrad W1,b1 [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * 32 + dR * dH) + 4 * dZ * dH,
-       tc_wgrad1(st, lc, t.maps, t.ns, bn, R, Z, H, T_(h, grads, l.iW1), T_(h, grads, l.ib1), tb.wg_scratch));
+       tc_wgrad1(st, lc, t.maps, t.ns, bn, R, Z, H, T_(h, grads, l.iW1), T_(h, grads, l.ib1), tb.wg_scratch + wg_region,
+                 defer));
     PH("wgrad W4,b4,W5,b5 [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * dH + dr * 64) + 8 * dZ * dH,
        tc_wgrad45(st, lc, t.maps, t.ns, rows, H, Z, T_(h, grads, l.iW4), T_(h, grads, l.ib4), T_(h, grads, l.iW5),
-                  T_(h, grads, l.ib5), tb.wg_scratch));
+                  T_(h, grads, l.ib5), tb.wg_scratch + 2 * wg_region, defer));
   } else
   PH("wgrad W1,b1,W4,b4,W5,b5", 2 * dR * dZ * dH + 4 * dr * dH * dZ,
      4 * (dR * dZ + dR * dH + dr * dH + 2 * dr * dZ + 3 * dH * dZ),
@@ -398,10 +404,12 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   if (tcp)
     PH("wgrad W3,b3 [tcgen05]", 2 * dr * dD * dH, 2.0 * t.ns * (dr * dD + dr * dH) + 4 * dD * dH,
        tc_wgrad3(st, lc, t.maps, t.ns, bn, rows, D, H, x_row_off, T_(h, grads, l.iW3), T_(h, grads, l.ib3),
-                 tb.wg_scratch));
+                 tcl ? tb.wg_scratch + 3 * wg_region : tb.wg_scratch, defer));
   else
     PH("wgrad W3,b3", 2 * dr * dD * dH, 4 * (dr * dD + dr * dH + dD * dH),
        launch_wgrad(st, lc, x, rows, D, s.da3, H, T_(h, grads, l.iW3), T_(h, grads, l.ib3)));
+  if (reduce_jobs.n > 0)
+    PH("sum of the split-K weight-gradient slices (one launch)", 0, 0, tc_wgrad_reduce_all(st, lc, reduce_jobs));
   return VAEB_OK;
 }
 

@@ -77,10 +77,31 @@ __device__ __forceinline__ void st16_split(__nv_bfloat16* hi, __nv_bfloat16* lo,
   }
 }
 
+// tanh on the epilogue's critical path: 16 warps finish a 128 x 256 tile = 32768 activations, and libdevice's tanhf
+// (~40 instructions, a divergent branch) alone costs ~5 us per tile.  fast = 1 (plain bf16 tier, the result is
+// rounded to bf16 anyway): MUFU tanh.approx (|err| <= 2^-10.99).  fast = 0 (bf16x3, fp32 tier): branch-free --
+// 1 - 2/(e^{2|x|}+1) from ex2.approx / rcp.approx (|err| < 4e-7) for |x| >= 0.1, the odd Taylor polynomial through
+// x^9 below (truncation < 1e-13 at 0.1); relative error < 5e-6 everywhere.
+__device__ __forceinline__ float tanh_tc(float x, int fast) {
+  if (fast) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+  }
+  const float ax = fabsf(x), x2 = x * x;
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.8853900817779268f));   // e^{2|x|}
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  const float big = copysignf(fmaf(-2.0f, r, 1.0f), x);
+  const float poly = fmaf(x * x2, fmaf(x2, fmaf(x2, fmaf(x2, 0.021869488536155203f, -0.053968253968253971f),
+                                                0.13333333333333333f), -0.33333333333333331f), x);
+  return ax < 0.1f ? poly : big;
+}
+
 // out == nullptr: only the mirror is written (large-batch path: every consumer reads the bf16 mirrors)
 struct EpiTanh {            // out[row, col] = tanh(acc + bias[col]) (+ optional bf16 hi/lo mirror of it)
   const float* bias; float* out; int ld;
-  __nv_bfloat16* mh; __nv_bfloat16* ml; int ldm;
+  __nv_bfloat16* mh; __nv_bfloat16* ml; int ldm; int fast;
   __device__ __forceinline__ void begin() {}
   __device__ __forceinline__ void split(int) {}
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
@@ -90,7 +111,7 @@ struct EpiTanh {            // out[row, col] = tanh(acc + bias[col]) (+ optional
       float b[16], r[16];
       ld16f(bias + col0, b);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) r[j] = tanhf(v[j] + b[j]);
+      for (int j = 0; j < 16; ++j) r[j] = tanh_tc(v[j] + b[j], fast);
       if (out) st16f(o, r);
       if (mh) st16_split(mh + (size_t)row * ldm + col0, ml ? ml + (size_t)row * ldm + col0 : nullptr, r);
       return;
@@ -98,7 +119,7 @@ struct EpiTanh {            // out[row, col] = tanh(acc + bias[col]) (+ optional
 #pragma unroll
     for (int j = 0; j < 16; ++j)
       if (col0 + j < N) {
-        const float t = tanhf(v[j] + bias[col0 + j]);
+        const float t = tanh_tc(v[j] + bias[col0 + j], fast);
         if (out) o[j] = t;
         if (mh) put_split(mh, ml, (size_t)row * ldm + col0 + j, t);
       }
@@ -243,15 +264,30 @@ struct EpiHeads {
   __device__ __forceinline__ void split(int) {}
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
     if (!ok) return;
+    // one Philox counter yields four draws: elements (row, 4g..4g+3) share one when Z is a multiple of 4
+    float e8[8];
+    const int j0 = col0 >> 1;
+    if (!src.injected && (Z & 3) == 0) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        if (j0 + 4 * g < Z)
+          philox_normal4(src.seed, src.stream, src.step, 0u,
+                         (uint64_t)(((src.row_offset + row) * Z + j0 + 4 * g) >> 2), e8 + 4 * g);
+    } else {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+        if (j0 + jj < Z)
+          e8[jj] = src.injected ? src.injected[(size_t)row * Z + j0 + jj]
+                                : philox_normal1(src.seed, src.stream, src.step, 0u,
+                                                 (uint64_t)((src.row_offset + row) * Z + j0 + jj));
+    }
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
-      const int j = (col0 >> 1) + jj;
+      const int j = j0 + jj;
       if (j < Z) {
         const float am = v[2 * jj] + b4[j], al = v[2 * jj + 1] + b5[j];
         const size_t o2 = (size_t)row * Z + j;
-        const float e = src.injected ? src.injected[o2]
-                                     : philox_normal1(src.seed, src.stream, src.step, 0u,
-                                                      (uint64_t)((src.row_offset + row) * Z + j));
+        const float e = e8[jj];
         const float zv = am + expf(0.5f * al) * e;
         mu[o2] = am; ls[o2] = al; eps[o2] = e; z[o2] = zv;
         put_split(z_hi, z_lo, (size_t)row * ldz + j, zv);
@@ -671,14 +707,49 @@ wgrad_split_reduce_kernel(const float* __restrict__ scratch, int splits, size_t 
   if (i < n_w) gW[i] = a; else gb[i - n_w] = a;
 }
 
+// One launch sums the split-K slices of every weight gradient of the step (blockIdx.y = job) in a fixed order.
+// kind 0: scratch slice [n_w | n_b] -> gW, gb.  kind 1 (heads): slice [(H+1) x 2Z], column c < Z -> W4 / b4, else W5 / b5.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_all_kernel(TcReduceJobs jobs) {
+  const TcReduceJob& j = jobs.job[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.n_w + j.n_b) return;
+  float a = 0.f;
+  for (int z = 0; z < j.splits; ++z) a += j.scratch[(size_t)z * j.stride + i];
+  if (j.kind == 0) {
+    if (i < j.n_w) j.gW[i] = a; else j.gb[i - j.n_w] = a;
+  } else {
+    const int Z = j.Z, H = j.H;
+    const int k = i / (2 * Z), c = i - k * 2 * Z;
+    float* gW = c < Z ? j.gW : j.gW2;
+    float* gb = c < Z ? j.gb : j.gb2;
+    const int jj = c < Z ? c : c - Z;
+    if (k < H) gW[(size_t)k * Z + jj] = a; else gb[jj] = a;
+  }
+}
+
+cudaError_t reduce_all_impl(cudaStream_t st, int64_t* launches, const TcReduceJobs& jobs) {
+  if (jobs.n == 0) return cudaSuccess;
+  int most = 0;
+  for (int q = 0; q < jobs.n; ++q) most = jobs.job[q].n_w + jobs.job[q].n_b > most ? jobs.job[q].n_w + jobs.job[q].n_b : most;
+  wgrad_reduce_all_kernel<<<dim3((most + 255) / 256, jobs.n), 256, 0, st>>>(jobs);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+// `defer` != nullptr: the slices stay in `scratch` (a region of its own) and their reduction is appended to the list
 cudaError_t tc_wgrad_generic(cudaStream_t st, int64_t* launches, const LayerMaps& maps, int ns, int bn, int Kred,
-                             int Hreal, int N, int a_row_off, float* gW, float* gb, float* scratch) {
+                             int Hreal, int N, int a_row_off, float* gW, float* gb, float* scratch, TcReduceJobs* defer) {
   const int splits = scratch ? tc_wgrad_splits(Hreal + 1, N, Kred, bn) : 1;
   const size_t stride = (size_t)(Hreal + 1) * N;
   EpiWgradTc epi{gW, gb, Hreal, N, splits > 1 ? scratch : nullptr, stride};
   ++*launches;
   cudaError_t e = dispatch_layer<true, true>(st, ns, bn, maps, epi, Hreal + 1, N, Kred, a_row_off, splits);
   if (e != cudaSuccess || splits == 1) return e;
+  if (defer && defer->n < TC_MAX_REDUCE_JOBS) {
+    defer->job[defer->n++] = TcReduceJob{scratch, splits, stride, Hreal * N, N, gW, gb, nullptr, nullptr, 0, 0, 0};
+    return cudaSuccess;
+  }
   const int tot = (int)stride;
   wgrad_split_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(scratch, splits, stride, Hreal * N, N, gW, gb);
   ++*launches;
@@ -766,6 +837,9 @@ cudaError_t tc_prepare_weights(cudaStream_t st, int64_t* launches, const float* 
 }
 
 // ---- host API (tc_layers.h) -------------------------------------------------------------------
+cudaError_t tc_wgrad_reduce_all(cudaStream_t st, int64_t* launches, const TcReduceJobs& jobs) {
+  return reduce_all_impl(st, launches, jobs);
+}
 void tc_set_pdl(bool on) { g_pdl = on; }
 
 int tc_act_bn(int rows, int n_min) {
@@ -854,7 +928,7 @@ static_assert(sizeof(LayerMaps) == TC_LAYER_MAPS_BYTES, "TcMaps storage size");
 
 cudaError_t tc_enc1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int D, int H,
                     int x_row_off, const float* b3, float* h_e, void* he_hi, void* he_lo, int ldm) {
-  EpiTanh epi{b3, h_e, H, (__nv_bfloat16*)he_hi, (__nv_bfloat16*)he_lo, ldm};
+  EpiTanh epi{b3, h_e, H, (__nv_bfloat16*)he_hi, (__nv_bfloat16*)he_lo, ldm, (ns == 1 && h_e == nullptr) ? 1 : 0};
   ++*launches;
   return dispatch_layer<false, true>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.enc1), epi, rows, H, D,
                                      x_row_off);
@@ -909,7 +983,7 @@ cudaError_t tc_enc2_heads(cudaStream_t st, int64_t* launches, const TcMaps& m, i
 
 cudaError_t tc_dec1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int Z, int H,
                     const float* b1, float* h_d, void* hd_hi, void* hd_lo, int ldm) {
-  EpiTanh epi{b1, h_d, H, (__nv_bfloat16*)hd_hi, (__nv_bfloat16*)hd_lo, ldm};
+  EpiTanh epi{b1, h_d, H, (__nv_bfloat16*)hd_hi, (__nv_bfloat16*)hd_lo, ldm, (ns == 1 && h_d == nullptr) ? 1 : 0};
   ++*launches;
   return dispatch_layer<false, true>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.dec1), epi, R, H, Z, 0);
 }
@@ -932,9 +1006,9 @@ cudaError_t tc_dgrad_he(cudaStream_t st, int64_t* launches, const TcMaps& m, int
 }
 
 cudaError_t tc_wgrad1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int Z, int H,
-                      float* gW1, float* gb1, float* scratch) {
+                      float* gW1, float* gb1, float* scratch, TcReduceJobs* defer) {
   return tc_wgrad_generic(st, launches, *reinterpret_cast<const LayerMaps*>(m.wgrad1), ns, bn, R, Z, H, 0, gW1, gb1,
-                          scratch);
+                          scratch, defer);
 }
 
 // scratch slices hold [(H+1) x 2Z]: column c < Z belongs to W4 / b4, c >= Z to W5 / b5
@@ -953,7 +1027,7 @@ wgrad45_reduce_kernel(const float* __restrict__ scratch, int splits, size_t stri
 }
 
 cudaError_t tc_wgrad45(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int rows, int H, int Z, float* gW4,
-                       float* gb4, float* gW5, float* gb5, float* scratch) {
+                       float* gb4, float* gW5, float* gb5, float* scratch, TcReduceJobs* defer) {
   const int N = 2 * Z;
   const int splits = tc_wgrad_splits(H + 1, N, rows, 64);
   const size_t stride = (size_t)(H + 1) * N;
@@ -962,6 +1036,10 @@ cudaError_t tc_wgrad45(cudaStream_t st, int64_t* launches, const TcMaps& m, int 
   cudaError_t e = dispatch_layer<true, true>(st, ns, 64, *reinterpret_cast<const LayerMaps*>(m.wgrad45), epi, H + 1, N, rows,
                                              0, splits);
   if (e != cudaSuccess) return e;
+  if (defer && defer->n < TC_MAX_REDUCE_JOBS) {
+    defer->job[defer->n++] = TcReduceJob{scratch, splits, stride, (H + 1) * N, 0, gW4, gb4, gW5, gb5, 1, H, Z};
+    return cudaSuccess;
+  }
   wgrad45_reduce_kernel<<<((H + 1) * N + 255) / 256, 256, 0, st>>>(scratch, splits, stride, H, Z, gW4, gb4, gW5, gb5);
   ++*launches;
   return cudaGetLastError();
@@ -973,13 +1051,13 @@ size_t tc_wgrad_scratch_elems(int D, int H) {
 }
 
 cudaError_t tc_wgrad2(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
-                      float* gW2, float* gb2, float* scratch) {
+                      float* gW2, float* gb2, float* scratch, TcReduceJobs* defer) {
   return tc_wgrad_generic(st, launches, *reinterpret_cast<const LayerMaps*>(m.wgrad2), ns, bn, R, H, D, 0, gW2, gb2,
-                          scratch);
+                          scratch, defer);
 }
 
 cudaError_t tc_wgrad3(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int D, int H,
-                      int x_row_off, float* gW3, float* gb3, float* scratch) {
+                      int x_row_off, float* gW3, float* gb3, float* scratch, TcReduceJobs* defer) {
   return tc_wgrad_generic(st, launches, *reinterpret_cast<const LayerMaps*>(m.wgrad3), ns, bn, rows, D, H, x_row_off, gW3,
-                          gb3, scratch);
+                          gb3, scratch, defer);
 }

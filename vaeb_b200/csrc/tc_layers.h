@@ -61,8 +61,16 @@ cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int
                         const float* h_d, float* da1, void* d1_hi, void* d1_lo, int ldm, const void* h_hi = nullptr,
                         const void* h_lo = nullptr);   // h_d == nullptr: h is read from its mirror; da1 == nullptr: mirror only
 // thin weight gradients of the latent layers on tcgen05 (large batch): split-K over the rows, fixed-order reduction
+// Deferred reduction of split-K slices: the weight-gradient GEMMs of a step append their job, one launch sums all
+constexpr int TC_MAX_REDUCE_JOBS = 4;
+struct TcReduceJob {
+  const float* scratch; int splits; size_t stride; int n_w, n_b;
+  float *gW, *gb, *gW2, *gb2; int kind, H, Z;       // kind 1: the interleaved heads slice -> (W4, b4, W5, b5)
+};
+struct TcReduceJobs { TcReduceJob job[TC_MAX_REDUCE_JOBS]; int n = 0; };
+cudaError_t tc_wgrad_reduce_all(cudaStream_t st, int64_t* launches, const TcReduceJobs& jobs);
 cudaError_t tc_wgrad1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int Z, int H,
-                      float* gW1, float* gb1, float* scratch);
+                      float* gW1, float* gb1, float* scratch, TcReduceJobs* defer = nullptr);
 // all per-step weight mirrors / transposes of the large-batch path in one launch (W3, W2, [W4^T;W5^T] incl. its fp32
 // copy w45t, the interleaved heads, W1)
 cudaError_t tc_prepare_weights(cudaStream_t st, int64_t* launches, const float* W3, const float* W2, const float* W4,
@@ -87,10 +95,10 @@ cudaError_t tc_dgrad_he(cudaStream_t st, int64_t* launches, const TcMaps& m, int
                         const float* h_e, float* da3, void* da3_hi, void* da3_lo, int ldm, const void* h_hi = nullptr,
                         const void* h_lo = nullptr);
 cudaError_t tc_wgrad45(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int rows, int H, int Z, float* gW4,
-                       float* gb4, float* gW5, float* gb5, float* scratch);
+                       float* gb4, float* gW5, float* gb5, float* scratch, TcReduceJobs* defer = nullptr);
 // scratch: device floats for the split-K slices of a weight gradient (tc_wgrad_scratch_elems), or nullptr
 size_t tc_wgrad_scratch_elems(int D, int H);
 cudaError_t tc_wgrad2(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
-                      float* gW2, float* gb2, float* scratch);
+                      float* gW2, float* gb2, float* scratch, TcReduceJobs* defer = nullptr);
 cudaError_t tc_wgrad3(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int D, int H,
-                      int x_row_off, float* gW3, float* gb3, float* scratch);
+                      int x_row_off, float* gW3, float* gb3, float* scratch, TcReduceJobs* defer = nullptr);
