@@ -377,7 +377,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
        tc_dz_dprep(st, lc, t.maps, t.ns, R, H, Z, la, w, s.z, s.eps, s.mu, s.ls, s.dmu, s.dls, tb.ddh, tb.ddl, tb.ldq));
     PH("bound (per row + total)", 0, 4 * (dR * tiles + 2 * dr),
        launch_finalize(st, lc, s.partial, tiles, s.row_aux, rows, L, s.per_row, bo.base_out, bo.mult, bo.tprior,
-                       bo.n_tprior, bo.div, bo.scalar_out, h->d_counter));
+                       bo.n_tprior, bo.div, bo.scalar_out, h->d_counter, s.dec_aux));   // dec_aux: idle outside the IS path
   } else
   PH("latent bwd (dz,dmu,dls,da3,bound)", 2 * dR * dZ * dH + 4 * dr * dH * dZ,
      4 * (dR * dH + 3 * dZ * dH + 2 * dr * dH + 3 * dR * dZ + dR * tiles),

@@ -197,14 +197,15 @@ row_partials_sum_kernel(const float* __restrict__ part, int n_part, int rows, fl
   out[m] = t;
 }
 
-// large row counts: per-row bounds by all SMs, then one block totals them in a fixed order -- the LAST block to
-// finish when a ticket counter is given (one launch), else finalize_total_kernel
+// large row counts: per-row bounds by all SMs, then one block totals them in a fixed order -- with a ticket counter
+// and a buffer for the per-block sums the LAST block to finish does it (one launch), else finalize_total_kernel
 __global__ void __launch_bounds__(256)
 finalize_rows_kernel(const float* __restrict__ partial, int n_tiles, const float* __restrict__ row_aux, int rows, int L,
-                     float* __restrict__ per_row, unsigned int* __restrict__ counter, float* __restrict__ base_out,
-                     float mult, const float* __restrict__ tprior, int n_tprior, float div,
+                     float* __restrict__ per_row, unsigned int* __restrict__ counter, float* __restrict__ block_part,
+                     float* __restrict__ base_out, float mult, const float* __restrict__ tprior, int n_tprior, float div,
                      float* __restrict__ scalar_out) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  float v = 0.f;
   if (m < rows) {
     float s = 0.f;
     for (int l = 0; l < L; ++l) {
@@ -213,19 +214,23 @@ finalize_rows_kernel(const float* __restrict__ partial, int n_tiles, const float
       for (int q = 0; q < n_tiles; ++q) t += p[q];
       s += t;
     }
-    per_row[m] = s * (1.0f / (float)L) + row_aux[m];
+    v = s * (1.0f / (float)L) + row_aux[m];
+    per_row[m] = v;
   }
   if (!counter) return;
   __shared__ unsigned int is_last;
   __shared__ float red[32];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  const float bsum = block_sum_1024(v, red);
+  if (threadIdx.x == 0) {
+    block_part[blockIdx.x] = bsum;
+    __threadfence();
+    is_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
   float acc = 0.f;
-  for (int r = threadIdx.x; r < rows; r += blockDim.x) acc += __ldcg(per_row + r);
+  for (int r = threadIdx.x; r < (int)gridDim.x; r += blockDim.x) acc += __ldcg(block_part + r);
   const float base = block_sum_1024(acc, red);
   float tp = 0.f;
   if (tprior) {
@@ -476,10 +481,13 @@ cudaError_t launch_dprep(cudaStream_t st, int64_t* launches, const float* dz, co
 
 cudaError_t launch_finalize(cudaStream_t st, int64_t* launches, const float* partial, int n_tiles,
                             const float* row_aux, int rows, int L, float* per_row, float* base_out, float mult,
-                            const float* tprior, int n_tprior, float div, float* scalar_out, unsigned int* counter) {
+                            const float* tprior, int n_tprior, float div, float* scalar_out, unsigned int* counter,
+                            float* block_part) {
   if (rows >= 2048) {
+    if (!block_part) counter = nullptr;
     finalize_rows_kernel<<<blocks_for(rows, 256), 256, 0, st>>>(partial, n_tiles, row_aux, rows, L, per_row, counter,
-                                                                base_out, mult, tprior, n_tprior, div, scalar_out);
+                                                                block_part, base_out, mult, tprior, n_tprior, div,
+                                                                scalar_out);
     if (counter) return LAUNCHED();
     ++*launches;
     finalize_total_kernel<<<1, 1024, 0, st>>>(per_row, rows, base_out, mult, tprior, n_tprior, div, scalar_out);

@@ -60,7 +60,8 @@ cudaError_t launch_dprep(cudaStream_t st, int64_t* launches, const float* dz, co
 cudaError_t launch_finalize(cudaStream_t st, int64_t* launches, const float* partial, int n_tiles,
                             const float* row_aux, int rows, int L, float* per_row, float* base_out,
                             float mult, const float* tprior, int n_tprior, float div, float* scalar_out,
-                            unsigned int* counter = nullptr);   // rows >= 2048 with a ticket counter: one launch
+                            unsigned int* counter = nullptr,   // rows >= 2048 with a ticket counter and room for
+                            float* block_part = nullptr);      // rows/256 block sums: one launch
 // logw[r] = sum_t partial[r,t] + aux[r];  logp[i] = logsumexp_l logw[i*L+l] - log L
 cudaError_t launch_is_reduce(cudaStream_t st, int64_t* launches, const float* partial, int n_tiles,
                              const float* aux, int n, int L, float* logw, float* logp);

@@ -281,18 +281,60 @@ struct EpiHeads {
                                 : philox_normal1(src.seed, src.stream, src.step, 0u,
                                                  (uint64_t)((src.row_offset + row) * Z + j0 + jj));
     }
+    float am8[8], al8[8], z8[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
       const int j = j0 + jj;
+      am8[jj] = al8[jj] = z8[jj] = 0.f;
       if (j < Z) {
         const float am = v[2 * jj] + b4[j], al = v[2 * jj + 1] + b5[j];
-        const size_t o2 = (size_t)row * Z + j;
         const float e = e8[jj];
         const float zv = am + expf(0.5f * al) * e;
-        mu[o2] = am; ls[o2] = al; eps[o2] = e; z[o2] = zv;
-        put_split(z_hi, z_lo, (size_t)row * ldz + j, zv);
+        am8[jj] = am; al8[jj] = al; z8[jj] = zv;
         acc += la ? (-0.5f * zv * zv + 0.5f * al + 0.5f * e * e) : 0.5f * (1.0f + al - am * am - expf(al));
+      } else {
+        e8[jj] = 0.f;
       }
+    }
+    // a thread's eight latent units are contiguous in every output: 16-byte stores where a whole quad is valid
+    const size_t o2 = (size_t)row * Z + j0;
+    const bool al16 = ((Z & 3) == 0) && ((((uintptr_t)mu | (uintptr_t)ls | (uintptr_t)eps | (uintptr_t)z) & 15u) == 0);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int jq = j0 + 4 * g;
+      if (al16 && jq + 4 <= Z) {
+        *reinterpret_cast<float4*>(mu + o2 + 4 * g) = make_float4(am8[4 * g], am8[4 * g + 1], am8[4 * g + 2], am8[4 * g + 3]);
+        *reinterpret_cast<float4*>(ls + o2 + 4 * g) = make_float4(al8[4 * g], al8[4 * g + 1], al8[4 * g + 2], al8[4 * g + 3]);
+        *reinterpret_cast<float4*>(eps + o2 + 4 * g) = make_float4(e8[4 * g], e8[4 * g + 1], e8[4 * g + 2], e8[4 * g + 3]);
+        *reinterpret_cast<float4*>(z + o2 + 4 * g) = make_float4(z8[4 * g], z8[4 * g + 1], z8[4 * g + 2], z8[4 * g + 3]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (jq + q < Z) {
+            mu[o2 + 4 * g + q] = am8[4 * g + q]; ls[o2 + 4 * g + q] = al8[4 * g + q];
+            eps[o2 + 4 * g + q] = e8[4 * g + q]; z[o2 + 4 * g + q] = z8[4 * g + q];
+          }
+      }
+    }
+    // z mirror: the row is ldz wide (a multiple of 8: 16-byte aligned octets), columns >= Z stay as initialised
+    __nv_bfloat16* zh = z_hi + (size_t)row * ldz + j0;
+    __nv_bfloat16* zl = z_lo ? z_lo + (size_t)row * ldz + j0 : nullptr;
+    if (j0 + 8 <= Z && (((uintptr_t)zh) & 15u) == 0 && (!zl || (((uintptr_t)zl) & 15u) == 0)) {
+      uint32_t hq[4], lq[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(z8[2 * q]), h1 = __float2bfloat16_rn(z8[2 * q + 1]);
+        hq[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(z8[2 * q] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(z8[2 * q + 1] - __bfloat162float(h1));
+        lq[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      }
+      *reinterpret_cast<uint4*>(zh) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+      if (zl) *reinterpret_cast<uint4*>(zl) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+    } else {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+        if (j0 + jj < Z) put_split(z_hi, z_lo, (size_t)row * ldz + j0 + jj, z8[jj]);
     }
   }
   __device__ __forceinline__ void end(int row, bool ok, int tile_n, int n_tiles) {
@@ -308,25 +350,54 @@ struct EpiDzPrep {
   __device__ __forceinline__ void split(int) {}
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
     if (!ok) return;
+    const size_t o0 = (size_t)row * Z + col0;
+    const bool al16 = ((Z & 3) == 0) &&
+                      ((((uintptr_t)z | (uintptr_t)eps | (uintptr_t)mu | (uintptr_t)ls | (uintptr_t)dmu | (uintptr_t)dls) & 15u) == 0);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int c = col0 + j;
-      if (c < N) {
-        const size_t o2 = (size_t)row * Z + c;
-        const float lsv = ls[o2];
-        float d = v[j];
-        if (la) d -= w * z[o2];
-        float a = d, b = d * (0.5f * expf(0.5f * lsv) * eps[o2]);
-        if (la) {
-          b += w * 0.5f;
-        } else {
-          a -= w * mu[o2];
-          b += w * 0.5f * (1.0f - expf(lsv));
+    for (int g = 0; g < 4; ++g) {
+      const int c = col0 + 4 * g;
+      if (c >= N) break;
+      float lsv[4], zv[4], ev[4], mv[4], a[4], b[4];
+      const bool vec = al16 && c + 4 <= N;
+      if (vec) {
+        const float4 t0 = *reinterpret_cast<const float4*>(ls + o0 + 4 * g), t1 = *reinterpret_cast<const float4*>(eps + o0 + 4 * g);
+        lsv[0] = t0.x; lsv[1] = t0.y; lsv[2] = t0.z; lsv[3] = t0.w;
+        ev[0] = t1.x; ev[1] = t1.y; ev[2] = t1.z; ev[3] = t1.w;
+        const float4 t2 = *reinterpret_cast<const float4*>((la ? z : mu) + o0 + 4 * g);
+        zv[0] = mv[0] = t2.x; zv[1] = mv[1] = t2.y; zv[2] = mv[2] = t2.z; zv[3] = mv[3] = t2.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          lsv[q] = ev[q] = zv[q] = mv[q] = 0.f;
+          if (c + q < N) {
+            lsv[q] = ls[o0 + 4 * g + q]; ev[q] = eps[o0 + 4 * g + q];
+            zv[q] = mv[q] = (la ? z : mu)[o0 + 4 * g + q];
+          }
         }
-        dmu[o2] = a; dls[o2] = b;
-        put_split(dd_hi, dd_lo, (size_t)row * ldq + c, a);
-        put_split(dd_hi, dd_lo, (size_t)row * ldq + Z + c, b);
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float d = v[4 * g + q];
+        if (la) d -= w * zv[q];
+        a[q] = d; b[q] = d * (0.5f * expf(0.5f * lsv[q]) * ev[q]);
+        if (la) {
+          b[q] += w * 0.5f;
+        } else {
+          a[q] -= w * mv[q];
+          b[q] += w * 0.5f * (1.0f - expf(lsv[q]));
+        }
+      }
+      if (vec) {
+        *reinterpret_cast<float4*>(dmu + o0 + 4 * g) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(dls + o0 + 4 * g) = make_float4(b[0], b[1], b[2], b[3]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (c + q < N) {
+          if (!vec) { dmu[o0 + 4 * g + q] = a[q]; dls[o0 + 4 * g + q] = b[q]; }
+          put_split(dd_hi, dd_lo, (size_t)row * ldq + c + q, a[q]);
+          put_split(dd_hi, dd_lo, (size_t)row * ldq + Z + c + q, b[q]);
+        }
     }
   }
   __device__ __forceinline__ void end(int, bool, int, int) {}
