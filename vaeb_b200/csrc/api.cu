@@ -151,7 +151,8 @@ int tc_ensure(vaeb_handle* h, int64_t rows, int64_t R) {
   const int D = h->D, H = h->H;
   const bool lo = t.ns == 2;
   if (b.ldh == 0) {
-    b.ldh = round8(H + 1); b.ldd = round8(D + 1); b.ldx = b.ldd;
+    // rows of the mirrors start on 32-byte sectors: a thread of a tcgen05 epilogue writes 16 bf16 = one whole sector
+    b.ldh = (H + 1 + 15) / 16 * 16; b.ldd = (D + 1 + 15) / 16 * 16; b.ldx = b.ldd;
     VAEB_TRY(grow_bytes(&b.w3h, (size_t)D * b.ldh * 2));
     VAEB_TRY(grow_bytes(&b.w2h, (size_t)H * b.ldd * 2));
     VAEB_CUDA(cudaMemsetAsync(b.w3h, 0, (size_t)D * b.ldh * 2, h->stream));

@@ -391,13 +391,38 @@ struct EpiDzPrep {
         *reinterpret_cast<float4*>(dmu + o0 + 4 * g) = make_float4(a[0], a[1], a[2], a[3]);
         *reinterpret_cast<float4*>(dls + o0 + 4 * g) = make_float4(b[0], b[1], b[2], b[3]);
       }
+      // [dmu | dls] mirror row: quads are 8-byte aligned when Z and ldq are multiples of 4
+      const size_t oa = (size_t)row * ldq + c, ob = oa + Z;
+      if (vec && (ldq & 3) == 0 && (((uintptr_t)dd_hi | (uintptr_t)dd_lo) & 7u) == 0) {
+        uint32_t ha[2], la_[2], hb[2], lb[2];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (c + q < N) {
-          if (!vec) { dmu[o0 + 4 * g + q] = a[q]; dls[o0 + 4 * g + q] = b[q]; }
-          put_split(dd_hi, dd_lo, (size_t)row * ldq + c + q, a[q]);
-          put_split(dd_hi, dd_lo, (size_t)row * ldq + Z + c + q, b[q]);
+        for (int q = 0; q < 2; ++q) {
+          const __nv_bfloat16 a0 = __float2bfloat16_rn(a[2 * q]), a1 = __float2bfloat16_rn(a[2 * q + 1]);
+          const __nv_bfloat16 b0 = __float2bfloat16_rn(b[2 * q]), b1 = __float2bfloat16_rn(b[2 * q + 1]);
+          ha[q] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(a1) << 16);
+          hb[q] = (uint32_t)__bfloat16_as_ushort(b0) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+          const __nv_bfloat16 a0l = __float2bfloat16_rn(a[2 * q] - __bfloat162float(a0));
+          const __nv_bfloat16 a1l = __float2bfloat16_rn(a[2 * q + 1] - __bfloat162float(a1));
+          const __nv_bfloat16 b0l = __float2bfloat16_rn(b[2 * q] - __bfloat162float(b0));
+          const __nv_bfloat16 b1l = __float2bfloat16_rn(b[2 * q + 1] - __bfloat162float(b1));
+          la_[q] = (uint32_t)__bfloat16_as_ushort(a0l) | ((uint32_t)__bfloat16_as_ushort(a1l) << 16);
+          lb[q] = (uint32_t)__bfloat16_as_ushort(b0l) | ((uint32_t)__bfloat16_as_ushort(b1l) << 16);
         }
+        *reinterpret_cast<uint2*>(dd_hi + oa) = make_uint2(ha[0], ha[1]);
+        *reinterpret_cast<uint2*>(dd_hi + ob) = make_uint2(hb[0], hb[1]);
+        if (dd_lo) {
+          *reinterpret_cast<uint2*>(dd_lo + oa) = make_uint2(la_[0], la_[1]);
+          *reinterpret_cast<uint2*>(dd_lo + ob) = make_uint2(lb[0], lb[1]);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (c + q < N) {
+            if (!vec) { dmu[o0 + 4 * g + q] = a[q]; dls[o0 + 4 * g + q] = b[q]; }
+            put_split(dd_hi, dd_lo, oa + q, a[q]);
+            put_split(dd_hi, dd_lo, ob + q, b[q]);
+          }
+      }
     }
   }
   __device__ __forceinline__ void end(int, bool, int, int) {}
