@@ -39,6 +39,17 @@ __device__ __forceinline__ void put_split(__nv_bfloat16* hi, __nv_bfloat16* lo, 
 __device__ __forceinline__ bool vec_ok(const void* p, int col0, int N) {
   return col0 + 16 <= N && (((uintptr_t)p) & 15u) == 0;
 }
+// 32-byte (whole-sector) accesses, sm_100: one request per sector instead of two half-sector ones
+__device__ __forceinline__ void st32B(void* p, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld32B(const void* p, uint32_t* w) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
 __device__ __forceinline__ void ld16f(const float* p, float* d) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -47,8 +58,13 @@ __device__ __forceinline__ void ld16f(const float* p, float* d) {
   }
 }
 __device__ __forceinline__ void ld16bf(const __nv_bfloat16* p, float* d) {
-  const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
-  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t w[8];
+  if ((((uintptr_t)p) & 31u) == 0) {
+    ld32B(p, w);
+  } else {
+    const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  }
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     d[2 * q] = __uint_as_float(w[q] << 16);
@@ -68,6 +84,11 @@ __device__ __forceinline__ void st16_split(__nv_bfloat16* hi, __nv_bfloat16* lo,
     const __nv_bfloat16 l0 = __float2bfloat16_rn(d[2 * q] - __bfloat162float(h0));
     const __nv_bfloat16 l1 = __float2bfloat16_rn(d[2 * q + 1] - __bfloat162float(h1));
     l[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  if ((((uintptr_t)hi | (uintptr_t)lo) & 31u) == 0) {
+    st32B(hi, h);
+    if (lo) st32B(lo, l);
+    return;
   }
   reinterpret_cast<uint4*>(hi)[0] = make_uint4(h[0], h[1], h[2], h[3]);
   reinterpret_cast<uint4*>(hi)[1] = make_uint4(h[4], h[5], h[6], h[7]);
