@@ -51,6 +51,11 @@ __device__ __forceinline__ void ld32B(const void* p, uint32_t* w) {
                : "l"(p));
 }
 __device__ __forceinline__ void ld16f(const float* p, float* d) {
+  if ((((uintptr_t)p) & 31u) == 0) {
+    ld32B(p, reinterpret_cast<uint32_t*>(d));
+    ld32B(p + 8, reinterpret_cast<uint32_t*>(d) + 8);
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 t = *reinterpret_cast<const float4*>(p + 4 * q);
@@ -72,6 +77,11 @@ __device__ __forceinline__ void ld16bf(const __nv_bfloat16* p, float* d) {
   }
 }
 __device__ __forceinline__ void st16f(float* p, const float* d) {
+  if ((((uintptr_t)p) & 31u) == 0) {
+    st32B(p, reinterpret_cast<const uint32_t*>(d));
+    st32B(p + 8, reinterpret_cast<const uint32_t*>(d) + 8);
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
 }
