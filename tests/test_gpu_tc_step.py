@@ -132,3 +132,30 @@ def test_tc_rejects_gaussian_decoder():
     import vaeb_b200
     with pytest.raises(ValueError, match="Bernoulli"):
         vaeb_b200.VAEB(np.zeros((8, 6), np.float32), True, 4, 2, 4, 1, 0.01, False, False, precision="bf16")
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_c3_full_size_persistent_kernels_match_oracle(precision):
+    """BASELINE config C3 at its full per-GPU size (M = 16384 rows, 784-500-20): at this size the activation layers
+    run in the persistent tcgen05 kernel (128 x 256 tiles, two TMEM accumulators) and no fp32 activations are kept.
+    Bound, per-row bounds and every gradient tensor against the fp64 oracle; the bound is also the sum of its rows
+    (size-independent property)."""
+    import vaeb_b200
+    M, Z = 16384, 20
+    x = O.synthetic_mnist(M)
+    params = _rand_params(784, 500, Z, 7, 0.05)
+    eps = np.random.RandomState(41).normal(size=(1, M, Z)).astype(np.float32)
+    m = vaeb_b200.VAEB(x, False, 500, Z, M, 1, 0.01, False, False, params, precision=precision)
+    o = O.OracleVAEB(x, False, 500, Z, M, L=1, estimator="LB", params=params, dtype=np.float64)
+    sg_ref, rows_ref, g_ref = o.grads(x, eps)
+    sg, rows, g = m.gradients(index=0, eps=eps)
+    tol, gtol, floor = (1e-2, 3e-2, 1.0) if precision == "bf16" else (1e-4, 1e-4, 0.1)
+    assert sg == pytest.approx(sg_ref, rel=tol)
+    assert float(np.sum(rows, dtype=np.float64)) == pytest.approx(sg, rel=1e-5)
+    np.testing.assert_allclose(rows, rows_ref, rtol=tol)
+    for a, b, n in zip(g, g_ref, O.param_names(False)):
+        assert_close_tensor(a, b, gtol, floor=floor, name="grad " + n)
+    # one update through the same kernels moves the parameters like the oracle's Adagrad step
+    before = float(m.update(0, eps=eps))
+    assert before == pytest.approx(o.update(0, eps), rel=tol)
+    m.close()
