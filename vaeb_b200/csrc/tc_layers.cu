@@ -864,6 +864,15 @@ cudaError_t reduce_all_impl(cudaStream_t st, int64_t* launches, const TcReduceJo
   return cudaGetLastError();
 }
 
+// a scratch region has one job (a GEMM launched again -- the per-phase profiler repeats launches -- replaces it)
+bool add_reduce_job(TcReduceJobs* jobs, const TcReduceJob& j) {
+  for (int q = 0; q < jobs->n; ++q)
+    if (jobs->job[q].scratch == j.scratch) { jobs->job[q] = j; return true; }
+  if (jobs->n >= TC_MAX_REDUCE_JOBS) return false;
+  jobs->job[jobs->n++] = j;
+  return true;
+}
+
 // `defer` != nullptr: the slices stay in `scratch` (a region of its own) and their reduction is appended to the list
 cudaError_t tc_wgrad_generic(cudaStream_t st, int64_t* launches, const LayerMaps& maps, int ns, int bn, int Kred,
                              int Hreal, int N, int a_row_off, float* gW, float* gb, float* scratch, TcReduceJobs* defer) {
@@ -873,10 +882,8 @@ cudaError_t tc_wgrad_generic(cudaStream_t st, int64_t* launches, const LayerMaps
   ++*launches;
   cudaError_t e = dispatch_layer<true, true>(st, ns, bn, maps, epi, Hreal + 1, N, Kred, a_row_off, splits);
   if (e != cudaSuccess || splits == 1) return e;
-  if (defer && defer->n < TC_MAX_REDUCE_JOBS) {
-    defer->job[defer->n++] = TcReduceJob{scratch, splits, stride, Hreal * N, N, gW, gb, nullptr, nullptr, 0, 0, 0};
+  if (defer && add_reduce_job(defer, TcReduceJob{scratch, splits, stride, Hreal * N, N, gW, gb, nullptr, nullptr, 0, 0, 0}))
     return cudaSuccess;
-  }
   const int tot = (int)stride;
   wgrad_split_reduce_kernel<<<(tot + 255) / 256, 256, 0, st>>>(scratch, splits, stride, Hreal * N, N, gW, gb);
   ++*launches;
@@ -1163,10 +1170,8 @@ cudaError_t tc_wgrad45(cudaStream_t st, int64_t* launches, const TcMaps& m, int 
   cudaError_t e = dispatch_layer<true, true>(st, ns, 64, *reinterpret_cast<const LayerMaps*>(m.wgrad45), epi, H + 1, N, rows,
                                              0, splits);
   if (e != cudaSuccess) return e;
-  if (defer && defer->n < TC_MAX_REDUCE_JOBS) {
-    defer->job[defer->n++] = TcReduceJob{scratch, splits, stride, (H + 1) * N, 0, gW4, gb4, gW5, gb5, 1, H, Z};
+  if (defer && add_reduce_job(defer, TcReduceJob{scratch, splits, stride, (H + 1) * N, 0, gW4, gb4, gW5, gb5, 1, H, Z}))
     return cudaSuccess;
-  }
   wgrad45_reduce_kernel<<<((H + 1) * N + 255) / 256, 256, 0, st>>>(scratch, splits, stride, H, Z, gW4, gb4, gW5, gb5);
   ++*launches;
   return cudaGetLastError();
