@@ -597,9 +597,10 @@ bool g_pdl = false;
 // producer runs ahead into the next tile while the last k blocks of this one are still being contracted.  BN up to
 // 256 (2 x 256 TMEM columns): a 128 x 256 tile re-reads A half as often as two 128 x 128 tiles -- these layers are
 // bound by L2 -> shared-memory operand traffic (K <= 784: 64 flop per operand byte at 128 x 128).
-template <int BN, int NS>
+template <int BN, int NS, int MT>
 struct PersistSmem {
-  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int A1_BYTES = BM * BK * 2;              // one 128-row block of A
+  static constexpr int A_BYTES = MT * A1_BYTES;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = NS * (A_BYTES + B_BYTES);
   static constexpr int BUDGET = 208 * 1024;
@@ -608,10 +609,15 @@ struct PersistSmem {
   static_assert(STAGES >= 2, "tile too large");
 };
 
-template <int BN, bool B_MN, int NS, class Epi>
+// MT = 2: a CTA tile is 256 x BN -- two 128-row blocks of A share every B stage (two MMAs per k step into two
+// accumulators that fill TMEM, so the epilogue of a tile overlaps only the operand loads of the next one).  ncu on
+// the MT = 1 kernels: tensor pipe 25 % active, L2 slices 25 %, 6.8 TB/s of L2 -> shared-memory fill (46 GB/s per SM,
+// the same rate the IS kernel streams W2^T at): the fill rate bounds these layers, and MT = 2 moves 36 % fewer bytes
+// per flop -- yet it measured slower (see dispatch_layer).
+template <int BN, bool B_MN, int NS, class Epi, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, int K, int a_row_off) {
-  using S = PersistSmem<BN, NS>;
+  using S = PersistSmem<BN, NS, MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + S::STAGES * S::STAGE_BYTES);
@@ -622,10 +628,13 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (K + BK - 1) / BK;
-  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BM - 1) / BM;
+  constexpr int TILE_M = MT * BM;
+  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + TILE_M - 1) / TILE_M;
   const int n_tiles = tiles_m * tiles_n;
   constexpr uint32_t ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+  constexpr uint32_t NBUF = (512u / (MT * ACC_COLS)) >= 2u ? 2u : 1u;      // accumulator sets in TMEM
+  constexpr uint32_t TMEM_COLS = NBUF * MT * ACC_COLS;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocation");
 
   if (warp == 0 && lane == 0) {
     tc::tma_prefetch_desc(&maps.a_hi);
@@ -646,7 +655,7 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
     // ===== TMA producer =====
     uint32_t it = 0;                                   // k blocks issued so far (ring position across tiles)
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int m0 = (tile / tiles_n) * TILE_M, n0 = (tile % tiles_n) * BN;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % S::STAGES;
         tc::mbar_wait(&empty[s], ((it / S::STAGES) & 1) ^ 1);
@@ -658,7 +667,9 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
           uint8_t* b = base + NS * S::A_BYTES + sp * S::B_BYTES;
           const CUtensorMap* ta = sp ? &maps.a_lo : &maps.a_hi;
           const CUtensorMap* tb = sp ? &maps.b_lo : &maps.b_hi;
-          tc::tma_load_2d(a, ta, &full[s], kb * BK, a_row_off + m0);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            tc::tma_load_2d(a + mt * S::A1_BYTES, ta, &full[s], kb * BK, a_row_off + m0 + mt * BM);
           if (B_MN) {
             for (int g = 0; g < BN / 64; ++g) tc::tma_load_2d(b + g * 8192, tb, &full[s], n0 + g * 64, kb * BK);
           } else {
@@ -672,10 +683,10 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
     constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN, 0, B_MN ? 1 : 0);
     uint32_t it = 0, lt = 0;                           // ring position; tiles done by this CTA
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
-      const uint32_t buf = lt & 1;
-      tc::mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1) ^ 1);     // the epilogue drained this accumulator
+      const uint32_t buf = lt % NBUF, use = lt / NBUF;
+      tc::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);           // the epilogue drained this accumulator set
       tc::tc_fence_after();
-      const uint32_t acc = tmem_base + buf * ACC_COLS;
+      const uint32_t acc = tmem_base + buf * (MT * ACC_COLS);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % S::STAGES;
         tc::mbar_wait(&full[s], (it / S::STAGES) & 1);
@@ -684,14 +695,17 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
         const uint32_t b = a + NS * S::A_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t dah = tc::desc_kmajor(a, k);
           const uint64_t dbh = B_MN ? tc::desc_mnmajor(b, k, 8192u) : tc::desc_kmajor(b, k);
-          tc::umma_bf16(acc, dah, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
-          if (NS == 2) {
-            const uint64_t dal = tc::desc_kmajor(a + S::A_BYTES, k);
-            const uint64_t dbl = B_MN ? tc::desc_mnmajor(b + S::B_BYTES, k, 8192u) : tc::desc_kmajor(b + S::B_BYTES, k);
-            tc::umma_bf16(acc, dah, dbl, idesc, 1u);
-            tc::umma_bf16(acc, dal, dbh, idesc, 1u);
+          const uint64_t dbl = NS == 2 ? (B_MN ? tc::desc_mnmajor(b + S::B_BYTES, k, 8192u) : tc::desc_kmajor(b + S::B_BYTES, k)) : 0;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t dah = tc::desc_kmajor(a + mt * S::A1_BYTES, k);
+            tc::umma_bf16(acc + mt * ACC_COLS, dah, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (NS == 2) {
+              const uint64_t dal = tc::desc_kmajor(a + S::A_BYTES + mt * S::A1_BYTES, k);
+              tc::umma_bf16(acc + mt * ACC_COLS, dah, dbl, idesc, 1u);
+              tc::umma_bf16(acc + mt * ACC_COLS, dal, dbh, idesc, 1u);
+            }
           }
         }
         tc::umma_commit(&empty[s]);
@@ -705,27 +719,30 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
       const int tm = tile / tiles_n, tn = tile % tiles_n;
-      const int m0 = tm * BM, n0 = tn * BN;
-      const uint32_t buf = lt & 1;
-      const int row = m0 + q * 32 + lane;
-      const bool ok = row < M;
-      epi.begin();
-      tc::mbar_wait(&tmem_full[buf], (lt >> 1) & 1);
+      const int n0 = tn * BN;
+      const uint32_t buf = lt % NBUF, use = lt / NBUF;
+      tc::mbar_wait(&tmem_full[buf], use & 1);
       tc::tc_fence_after();
-      const uint32_t acc = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c = cs * SLICE; c < (cs + 1) * SLICE; c += 16) {
-        float v[16];
-        tc::tmem_ld16(acc + (uint32_t)c, v);
-        tc::tmem_ld_wait();
-        if (c + 16 >= (cs + 1) * SLICE) {               // last read of this warp: hand the accumulator back early
-          tc::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
+      for (int mt = 0; mt < MT; ++mt) {
+        const int row = tm * TILE_M + mt * BM + q * 32 + lane;
+        const bool ok = row < M;
+        epi.begin();
+        const uint32_t acc = tmem_base + buf * (MT * ACC_COLS) + mt * ACC_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int c = cs * SLICE; c < (cs + 1) * SLICE; c += 16) {
+          float v[16];
+          tc::tmem_ld16(acc + (uint32_t)c, v);
+          tc::tmem_ld_wait();
+          if (mt == MT - 1 && c + 16 >= (cs + 1) * SLICE) {   // last read of this warp: hand the accumulators back early
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
+          }
+          if (n0 + c < N) epi.chunk(row, ok, n0 + c, N, v);
         }
-        if (n0 + c < N) epi.chunk(row, ok, n0 + c, N, v);
+        epi.end(row, ok, tn * (EPI_WARPS / 4) + cs, tiles_n * (EPI_WARPS / 4));
       }
-      epi.end(row, ok, tn * (EPI_WARPS / 4) + cs, tiles_n * (EPI_WARPS / 4));
     }
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -736,18 +753,20 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
 
 int g_persist = -1;     // -1: by size; 0 / 1: forced (VAEB_TC_PERSIST, measurement switch)
 
-template <int BN, bool B_MN, int NS, class Epi>
+int g_persist_mt = -1;  // -1: by size; 1 / 2: forced (VAEB_TC_MT, measurement switch)
+
+template <int BN, bool B_MN, int NS, class Epi, int MT>
 cudaError_t launch_layer_persistent(cudaStream_t st, const LayerMaps& maps, const Epi& epi, int M, int N, int K,
                                     int a_row_off) {
-  using S = PersistSmem<BN, NS>;
-  auto kfn = tc_layer_persistent_kernel<BN, B_MN, NS, Epi>;
+  using S = PersistSmem<BN, NS, MT>;
+  auto kfn = tc_layer_persistent_kernel<BN, B_MN, NS, Epi, MT>;
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+  const int tiles = ((N + BN - 1) / BN) * ((M + MT * BM - 1) / (MT * BM));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(tiles < 148 ? tiles : 148);
   cfg.blockDim = dim3(TC_THREADS);
@@ -802,8 +821,13 @@ cudaError_t dispatch_layer(cudaStream_t st, int ns, int bn, const LayerMaps& map
                            int a_row_off, int splits = 1) {
   if constexpr (!A_MN) {
     if (bn == 256) {                   // tc_act_bn chose the persistent form
-      if (ns == 2) return launch_layer_persistent<256, B_MN, 2, Epi>(st, maps, epi, M, N, K, a_row_off);
-      return launch_layer_persistent<256, B_MN, 1, Epi>(st, maps, epi, M, N, K, a_row_off);
+      if (ns == 2) return launch_layer_persistent<256, B_MN, 2, Epi, 1>(st, maps, epi, M, N, K, a_row_off);
+      // 256 x 256 tiles (VAEB_TC_MT=2): measured SLOWER at 16384 rows (275 vs 263 us per update; enc1 25.2 vs 23.2,
+      // dec2 44.1 vs 38.1 us) -- one wave of 128 tiles with the epilogue of both accumulators serialised behind the
+      // MMAs loses more than the halved operand traffic gains.  Kept as a measurement switch.
+      if (g_persist_mt == -1) { const char* e = getenv("VAEB_TC_MT"); g_persist_mt = e ? atoi(e) : 0; }
+      if (g_persist_mt == 2) return launch_layer_persistent<256, B_MN, 1, Epi, 2>(st, maps, epi, M, N, K, a_row_off);
+      return launch_layer_persistent<256, B_MN, 1, Epi, 1>(st, maps, epi, M, N, K, a_row_off);
     }
   }
   if (ns == 2) {
