@@ -85,15 +85,17 @@ __device__ __forceinline__ void st16f(float* p, const float* d) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(p + 4 * q) = make_float4(d[4 * q], d[4 * q + 1], d[4 * q + 2], d[4 * q + 3]);
 }
+// packed conversions (F2FP.BF16.PACK_AB, full rate) instead of one quarter-rate F2F per element
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
 __device__ __forceinline__ void st16_split(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* d) {
   uint32_t h[8], l[8];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(d[2 * q]), h1 = __float2bfloat16_rn(d[2 * q + 1]);
-    h[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(d[2 * q] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(d[2 * q + 1] - __bfloat162float(h1));
-    l[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    h[q] = pack_bf16x2(d[2 * q], d[2 * q + 1]);
+    if (lo) l[q] = pack_bf16x2(d[2 * q] - __uint_as_float(h[q] << 16), d[2 * q + 1] - __uint_as_float(h[q] & 0xffff0000u));
   }
   if ((((uintptr_t)hi | (uintptr_t)lo) & 31u) == 0) {
     st32B(hi, h);
@@ -354,11 +356,8 @@ struct EpiHeads {
       uint32_t hq[4], lq[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(z8[2 * q]), h1 = __float2bfloat16_rn(z8[2 * q + 1]);
-        hq[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(z8[2 * q] - __bfloat162float(h0));
-        const __nv_bfloat16 l1 = __float2bfloat16_rn(z8[2 * q + 1] - __bfloat162float(h1));
-        lq[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        hq[q] = pack_bf16x2(z8[2 * q], z8[2 * q + 1]);
+        lq[q] = pack_bf16x2(z8[2 * q] - __uint_as_float(hq[q] << 16), z8[2 * q + 1] - __uint_as_float(hq[q] & 0xffff0000u));
       }
       *reinterpret_cast<uint4*>(zh) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
       if (zl) *reinterpret_cast<uint4*>(zl) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
@@ -428,16 +427,10 @@ struct EpiDzPrep {
         uint32_t ha[2], la_[2], hb[2], lb[2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const __nv_bfloat16 a0 = __float2bfloat16_rn(a[2 * q]), a1 = __float2bfloat16_rn(a[2 * q + 1]);
-          const __nv_bfloat16 b0 = __float2bfloat16_rn(b[2 * q]), b1 = __float2bfloat16_rn(b[2 * q + 1]);
-          ha[q] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(a1) << 16);
-          hb[q] = (uint32_t)__bfloat16_as_ushort(b0) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
-          const __nv_bfloat16 a0l = __float2bfloat16_rn(a[2 * q] - __bfloat162float(a0));
-          const __nv_bfloat16 a1l = __float2bfloat16_rn(a[2 * q + 1] - __bfloat162float(a1));
-          const __nv_bfloat16 b0l = __float2bfloat16_rn(b[2 * q] - __bfloat162float(b0));
-          const __nv_bfloat16 b1l = __float2bfloat16_rn(b[2 * q + 1] - __bfloat162float(b1));
-          la_[q] = (uint32_t)__bfloat16_as_ushort(a0l) | ((uint32_t)__bfloat16_as_ushort(a1l) << 16);
-          lb[q] = (uint32_t)__bfloat16_as_ushort(b0l) | ((uint32_t)__bfloat16_as_ushort(b1l) << 16);
+          ha[q] = pack_bf16x2(a[2 * q], a[2 * q + 1]);
+          hb[q] = pack_bf16x2(b[2 * q], b[2 * q + 1]);
+          la_[q] = pack_bf16x2(a[2 * q] - __uint_as_float(ha[q] << 16), a[2 * q + 1] - __uint_as_float(ha[q] & 0xffff0000u));
+          lb[q] = pack_bf16x2(b[2 * q] - __uint_as_float(hb[q] << 16), b[2 * q + 1] - __uint_as_float(hb[q] & 0xffff0000u));
         }
         *reinterpret_cast<uint2*>(dd_hi + oa) = make_uint2(ha[0], ha[1]);
         *reinterpret_cast<uint2*>(dd_hi + ob) = make_uint2(hb[0], hb[1]);
