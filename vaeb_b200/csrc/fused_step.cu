@@ -633,6 +633,50 @@ __device__ __forceinline__ long long gtime() {
 
 #define FS_JOB(J) job_tmt(J), job_tnt(J)
 
+// the bound of step s: fixed-order sum of the row partials (VAEB.py:340-344) (+ thetaPrior, :364), / Mg -- one CTA
+template <bool TPRIOR>
+__device__ __forceinline__ void bound_item(const StepParams& p, float* smem, int s) {
+  const int M = p.M, G = gridDim.x;
+  const int tc = p.job[J_DEC2].tiles_n, ta = p.job[J_ENC2].tiles_n;
+  float t = 0.f;
+  for (int r = threadIdx.x; r < M; r += NT) {
+    float rsum = 0.f;
+    for (int q = 0; q < tc; ++q) rsum += __ldcg(p.partial + (size_t)r * tc + q);
+    for (int q = 0; q < ta; ++q) rsum += __ldcg(p.aux_part + (size_t)r * ta + q);
+    t += rsum;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = 0.f;
+    for (int wq = 0; wq < NW; ++wq) b += smem[wq];
+    float tp = 0.f;                                        // thetaPrior (full VB), fixed order
+    if constexpr (TPRIOR) {
+      const float* part = p.tprior_part + (size_t)(s & 1) * G;   // double buffered by step parity
+      for (int c = 0; c < G; ++c) tp += __ldcg(part + c);
+    }
+    p.scalars[s] = (p.bmult * b + tp) / p.Mg;
+  }
+  __syncthreads();
+}
+
+// per-CTA partial sum of thetaPrior into the step's half of tprior_part
+__device__ __forceinline__ void store_tprior(const StepParams& p, float* smem, int s, float tp) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tp += __shfl_xor_sync(0xffffffffu, tp, o);
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = tp;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = 0.f;
+    for (int wq = 0; wq < NW; ++wq) b += smem[wq];
+    p.tprior_part[(size_t)(s & 1) * gridDim.x + blockIdx.x] = b;
+  }
+  __syncthreads();
+}
+
 // phases 6-8 of one update (the weight-gradient phases), templated on the update rule of their epilogues
 template <bool FVB>
 __device__ __forceinline__ void update_phases(const StepParams& p, float* smem, int s, const float* x, const float* P,
@@ -661,29 +705,7 @@ __device__ __forceinline__ void update_phases(const StepParams& p, float* smem, 
         if (i < nz) { run_item<FS_JOB(J_DZ), A_MK, B_NK, PLAIN>(gz, i, ez, smem); continue; }
         i -= nz;
         if (i < n1) { run_item<FS_JOB(J_WG1), A_KM, B_KN, PLAIN>(g1, i, e1, smem); continue; }
-        // the bound of this step: fixed-order sum of the row partials (VAEB.py:340-344), / Mg
-        const int tc = p.job[J_DEC2].tiles_n, ta = p.job[J_ENC2].tiles_n;
-        float t = 0.f;
-        for (int r = threadIdx.x; r < M; r += NT) {
-          float rsum = 0.f;
-          for (int q = 0; q < tc; ++q) rsum += __ldcg(p.partial + (size_t)r * tc + q);
-          for (int q = 0; q < ta; ++q) rsum += __ldcg(p.aux_part + (size_t)r * ta + q);
-          t += rsum;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = t;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          float b = 0.f;
-          for (int wq = 0; wq < NW; ++wq) b += smem[wq];
-          float tp = 0.f;                                        // thetaPrior (full VB), fixed order
-          if constexpr (FVB)
-            for (int c = 0; c < G; ++c) tp += __ldcg(p.tprior_part + c);
-          p.scalars[s] = (p.bmult * b + tp) / p.Mg;
-        }
-        __syncthreads();
+        bound_item<FVB>(p, smem, s);
       }
     }
     grid_barrier(p.bar, target += G);
@@ -712,8 +734,12 @@ __device__ __forceinline__ void update_phases(const StepParams& p, float* smem, 
     }
 }
 
-template <bool FVB>
+// MODE 0: L^B / L^A on plain parameters.  1: full VB with sampled weights.  2: full VB as the reference runs it
+// (VAEB.py:349-367 with :127-129 dead): the layers read the frozen MAP parameters, only the bound is
+// needed from them (no backward), and (mu, sigma) follow the prior terms alone -- four phases per update.
+template <int MODE>
 __global__ void __launch_bounds__(NT, 1) fused_step_kernel(const StepParams p) {
+  constexpr bool FVB = MODE == 1;
   extern __shared__ __align__(16) float smem[];
   const int D = p.D, H = p.H, Z = p.Z, M = p.M;
   const int G = gridDim.x, cta = blockIdx.x;
@@ -750,16 +776,37 @@ __global__ void __launch_bounds__(NT, 1) fused_step_kernel(const StepParams p) {
         reinterpret_cast<float4*>(p.zeta)[g4] = make_float4(zt[0], zt[1], zt[2], zt[3]);
         reinterpret_cast<float4*>(p.theta)[g4] = make_float4(th[0], th[1], th[2], th[3]);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) tp += __shfl_xor_sync(0xffffffffu, tp, o);
-      if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = tp;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        float b = 0.f;
-        for (int wq = 0; wq < NW; ++wq) b += smem[wq];
-        p.tprior_part[cta] = b;
-      }
+      store_tprior(p, smem, s, tp);
       grid_barrier(p.bar, target += G);
+    }
+    if constexpr (MODE == 2) {
+      // reference-faithful full VB: thetaPrior and the whole (mu, sigma) update in one pass -- d/dmu = -mu - prior mu,
+      // d/dsigma = 1/s - s - prior s (VAEB.py:359-363,391-393), Adagrad :426-444.  Nothing downstream reads them:
+      // no barrier before the layers.
+      float tp = 0.f;
+      for (int64_t g4 = (int64_t)cta * NT + threadIdx.x; 4 * g4 < p.total; g4 += (int64_t)G * NT) {
+        float4 m4 = __ldcg(reinterpret_cast<const float4*>(p.vmu) + g4);
+        float4 s4 = __ldcg(reinterpret_cast<const float4*>(p.vsig) + g4);
+        float4 am4 = __ldcg(reinterpret_cast<const float4*>(p.ada) + g4);
+        float4 as4 = __ldcg(reinterpret_cast<const float4*>(p.ada_sig) + g4);
+        float* mm = &m4.x; float* ss = &s4.x; float* am = &am4.x; float* as = &as4.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (4 * g4 + j < p.total) {
+            const float m = mm[j], sg = ss[j];
+            tp += 0.5f * (1.0f + logf(sg * sg) - m * m - sg * sg);
+            const float gm = -m - hy.prior * m, gs = 1.0f / sg - sg - hy.prior * sg;
+            am[j] += gm * gm; as[j] += gs * gs;
+            mm[j] = m + hy.lr * gm / (sqrtf(am[j]) + hy.eps);
+            ss[j] = sg + hy.lr * gs / (sqrtf(as[j]) + hy.eps);
+          }
+        }
+        reinterpret_cast<float4*>(p.vmu)[g4] = m4;
+        reinterpret_cast<float4*>(p.vsig)[g4] = s4;
+        reinterpret_cast<float4*>(p.ada)[g4] = am4;
+        reinterpret_cast<float4*>(p.ada_sig)[g4] = as4;
+      }
+      store_tprior(p, smem, s, tp);
     }
 
     // ---- phase 1: encoder hidden layer ------------------------------------------------------
@@ -802,6 +849,13 @@ __global__ void __launch_bounds__(NT, 1) fused_step_kernel(const StepParams p) {
     }
     grid_barrier(p.bar, target += G);
     if (tm) tm[4] = gtime();
+
+    if constexpr (MODE == 2) {
+      // the bound needs every CTA's row partials and thetaPrior sums (all written before the barrier above); the next
+      // update overwrites them only after its own barriers, which wait for this CTA
+      if (cta == (s % G)) bound_item<true>(p, smem, s);
+      continue;
+    }
 
     // ---- phase 5: back through the decoder output layer -------------------------------------
     {
@@ -854,7 +908,8 @@ static JobCfg plan_job(int job, int M, int N, int K, int n_cta, bool dual_n) {
 
 bool fused_step_supported(const vaeb_handle* h, int rows) {
   const int e = h->cfg.estimator;
-  return (e == VAEB_EST_LB || e == VAEB_EST_LA || e == VAEB_EST_FVB_SAMPLED) && h->L == 1 && h->world == 1 &&
+  return (e == VAEB_EST_LB || e == VAEB_EST_LA || e == VAEB_EST_FVB_SAMPLED || e == VAEB_EST_FVB) && h->L == 1 &&
+         h->world == 1 &&
          h->cfg.precision == VAEB_PREC_FP32 && rows >= 1 && rows <= 4096 && !h->fused_off;
 }
 
@@ -869,12 +924,14 @@ int fused_step_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, 
     VAEB_CUDA(cudaDeviceGetAttribute(&f.n_sm, cudaDevAttrMultiProcessorCount, dev));
     VAEB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     VAEB_REQUIRE(coop != 0, "device lacks cooperative launch");
-    VAEB_CUDA(cudaFuncSetAttribute(fused_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    VAEB_CUDA(cudaFuncSetAttribute(fused_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    int occ = 0, occ_f = 0;
-    VAEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_step_kernel<false>, NT, SMEM_BYTES));
-    VAEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, fused_step_kernel<true>, NT, SMEM_BYTES));
-    VAEB_REQUIRE(occ >= 1 && occ_f >= 1, "fused step kernel does not fit on an SM");
+    const void* kfns[3] = {(const void*)fused_step_kernel<0>, (const void*)fused_step_kernel<1>,
+                           (const void*)fused_step_kernel<2>};
+    for (const void* k : kfns) {
+      VAEB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+      int occ = 0;
+      VAEB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, NT, SMEM_BYTES));
+      VAEB_REQUIRE(occ >= 1, "fused step kernel does not fit on an SM");
+    }
     VAEB_CUDA(cudaMalloc((void**)&f.bar, sizeof(unsigned long long)));
     VAEB_CUDA(cudaMemset(f.bar, 0, sizeof(unsigned long long)));
     const size_t nb = (size_t)(l.padded + 4) * sizeof(float);
@@ -929,27 +986,31 @@ int fused_step_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, 
   p.partial = f.partial; p.aux_part = f.aux_part;
   p.scalars = h->d_scalars + slot0; p.Mg = (float)rows; p.bmult = 1.0f;
   const bool fvb = h->cfg.estimator == VAEB_EST_FVB_SAMPLED;
-  p.fvb = fvb ? 1 : 0;
-  if (fvb) {
+  const bool faithful = h->cfg.estimator == VAEB_EST_FVB;
+  p.fvb = fvb ? 1 : (faithful ? 2 : 0);
+  if (fvb || faithful) {
     // SGVB = x.shape[0]*(sum logp + sum KL) + thetaPrior, update returns SGVB/M (VAEB.py:364,412); the data term of
     // the gradient carries the same factor M; the prior terms live in the update epilogue
-    if (!f.tprior_part) VAEB_CUDA(cudaMalloc((void**)&f.tprior_part, (size_t)f.n_sm * sizeof(float)));
+    if (!f.tprior_part) VAEB_CUDA(cudaMalloc((void**)&f.tprior_part, (size_t)2 * f.n_sm * sizeof(float)));
     p.w = (float)rows; p.bmult = (float)rows;
     p.prior = h->cfg.prior_scale; p.p2 = 0.f;
     p.vmu = h->d_vmu; p.vsig = h->d_vsig; p.ada = h->d_ada_mu; p.ada_sig = h->d_ada_sig;
     p.theta = h->d_theta; p.zeta = h->d_zeta; p.tprior_part = f.tprior_part; p.total = l.total;
+    if (faithful) p.params[1] = p.params[0];     // the MAP parameters are frozen (VAEB.py:119,352): no ping-pong
   }
   p.n_steps = n_steps; p.parity0 = 0;
   p.bar = f.bar; p.bar_base = f.bar_count;
   p.timing = d_timing;
   for (int j = 0; j < J_COUNT; ++j) p.job[j] = f.job[j];
   void* args[] = {&p};
-  const void* kfn = fvb ? (const void*)fused_step_kernel<true> : (const void*)fused_step_kernel<false>;
+  const void* kfn = fvb ? (const void*)fused_step_kernel<1>
+                        : (faithful ? (const void*)fused_step_kernel<2> : (const void*)fused_step_kernel<0>);
   VAEB_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(f.n_sm), dim3(NT), args, SMEM_BYTES, h->stream));
-  f.bar_count += (unsigned long long)f.n_sm * (unsigned long long)(N_PHASES + (fvb ? 1 : 0)) * (unsigned long long)n_steps;
+  const int phases = faithful ? 4 : N_PHASES + (fvb ? 1 : 0);           // grid barriers per update
+  f.bar_count += (unsigned long long)f.n_sm * (unsigned long long)phases * (unsigned long long)n_steps;
   ++h->launches;
   h->step += (uint32_t)n_steps;
-  if ((n_steps & 1) && !fvb) std::swap(h->d_params, f.params_alt);   // theta now lives in the other buffer
+  if ((n_steps & 1) && !fvb && !faithful) std::swap(h->d_params, f.params_alt);   // theta now lives in the other buffer
   h->grads_have_prior = false;
   return VAEB_OK;
 }
