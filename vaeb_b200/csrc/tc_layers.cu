@@ -62,6 +62,13 @@ __device__ __forceinline__ void ld16f(const float* p, float* d) {
     d[4 * q] = t.x; d[4 * q + 1] = t.y; d[4 * q + 2] = t.z; d[4 * q + 3] = t.w;
   }
 }
+__device__ __forceinline__ void unpack16bf(const uint32_t* w, float* d) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    d[2 * q] = __uint_as_float(w[q] << 16);
+    d[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+  }
+}
 __device__ __forceinline__ void ld16bf(const __nv_bfloat16* p, float* d) {
   uint32_t w[8];
   if ((((uintptr_t)p) & 31u) == 0) {
@@ -133,11 +140,13 @@ __device__ __forceinline__ float tanh_tc(float x, int fast) {
 
 // out == nullptr: only the mirror is written (large-batch path: every consumer reads the bf16 mirrors)
 struct EpiTanh {            // out[row, col] = tanh(acc + bias[col]) (+ optional bf16 hi/lo mirror of it)
+  static constexpr bool PREFETCH = true;   // persistent kernel: unrolled epilogue with the next chunk's operand in flight
   const float* bias; float* out; int ld;
   __nv_bfloat16* mh; __nv_bfloat16* ml; int ldm; int fast;
   __device__ __forceinline__ void begin() {}
   __device__ __forceinline__ void split(int) {}
-  __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
+  __device__ __forceinline__ bool preload(int, bool, int, int, uint32_t*) const { return false; }
+  __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v, const uint32_t* = nullptr) {
     if (!ok) return;
     float* o = out ? out + (size_t)row * ld + col0 : nullptr;
     if (vec_ok(o, col0, N) && vec_ok(bias + col0, col0, N) && vec_ok(mh ? mh + (size_t)row * ldm + col0 : nullptr, col0, N)) {
@@ -161,6 +170,7 @@ struct EpiTanh {            // out[row, col] = tanh(acc + bias[col]) (+ optional
 };
 
 struct EpiBernoulliTc {     // VAEB.py:263,311: term = x*a - softplus(a); da = scale*(x - sigmoid(a))
+  static constexpr bool PREFETCH = false;   // persistent kernel: unrolled epilogue with the next chunk's operand in flight
   const float* bias; const float* x; int ldx; int x_div; int x_mod; float scale;
   __nv_bfloat16* da_hi; __nv_bfloat16* da_lo; int ldda; float* partial;
   // x == nullptr: x is read from its bf16 mirror (hi + lo when present), row offset xm_off, leading dimension ldxm
@@ -175,7 +185,15 @@ struct EpiBernoulliTc {     // VAEB.py:263,311: term = x*a - softplus(a); da = s
     acc += xv * a - (fmaxf(a, 0.f) + __logf(1.0f + t));
     return scale * (xv - (a >= 0.f ? r : t * r));
   }
-  __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
+  // the persistent kernel requests the next chunk's x (hi mirror, one sector) before it finishes the current one
+  __device__ __forceinline__ bool preload(int row, bool ok, int col0, int N, uint32_t* w) const {
+    if (!ok || x || col0 + 16 > N) return false;
+    const __nv_bfloat16* p = xm_hi + (size_t)(xm_off + (row / x_div) % x_mod) * ldxm + col0;
+    if (((uintptr_t)p) & 31u) return false;
+    ld32B(p, w);
+    return true;
+  }
+  __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v, const uint32_t* pre = nullptr) {
     if (!ok) return;
     const int xrow = (row / x_div) % x_mod;
     const float* xr = x ? x + (size_t)xrow * ldx + col0 : nullptr;
@@ -189,7 +207,7 @@ struct EpiBernoulliTc {     // VAEB.py:263,311: term = x*a - softplus(a); da = s
       if (x) {
         ld16f(xr, xv);
       } else {
-        ld16bf(xm_hi + oxm, xv);
+        if (pre) unpack16bf(pre, xv); else ld16bf(xm_hi + oxm, xv);
         if (xm_lo) {
           float lo[16];
           ld16bf(xm_lo + oxm, lo);
@@ -220,13 +238,15 @@ struct EpiBernoulliTc {     // VAEB.py:263,311: term = x*a - softplus(a); da = s
 };
 
 struct EpiWgradTc {         // rows < Hreal -> gW[Hreal, N]; row == Hreal (the ones column of A) -> gb
+  static constexpr bool PREFETCH = false;   // persistent kernel: unrolled epilogue with the next chunk's operand in flight
   float* gW; float* gb; int Hreal; int ld;
   float* scratch; size_t split_stride;   // split-K: slice z writes [gW | gb] at scratch + z * split_stride
   __device__ __forceinline__ void begin() {}
   __device__ __forceinline__ void split(int z) {
     if (scratch) { gW = scratch + (size_t)z * split_stride; gb = gW + (size_t)Hreal * ld; }
   }
-  __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
+  __device__ __forceinline__ bool preload(int, bool, int, int, uint32_t*) const { return false; }
+  __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v, const uint32_t* = nullptr) {
     if (!ok) return;
     float* dst = (row < Hreal ? gW + (size_t)row * ld : gb) + col0;
     if (vec_ok(dst, col0, N)) { st16f(dst, v); return; }
@@ -240,6 +260,7 @@ struct EpiWgradTc {         // rows < Hreal -> gW[Hreal, N]; row == Hreal (the o
 // h comes in fp32 (h != nullptr) or as its bf16 mirror hh (+ hl: hi + lo carries 16 mantissa bits); out == nullptr:
 // only the mirror of the result is written (large-batch path)
 struct EpiDgradTanh {       // out = acc * (1 - h^2) (+ optional bf16 hi/lo mirror of it)
+  static constexpr bool PREFETCH = true;   // persistent kernel: unrolled epilogue with the next chunk's operand in flight
   const float* h; float* out; int ld;
   __nv_bfloat16* mh; __nv_bfloat16* ml; int ldm;
   const __nv_bfloat16* hh; const __nv_bfloat16* hl;      // mirror of h, leading dimension ldm
@@ -251,7 +272,14 @@ struct EpiDgradTanh {       // out = acc * (1 - h^2) (+ optional bf16 hi/lo mirr
     if (hl) t += __bfloat162float(hl[(size_t)row * ldm + c]);
     return t;
   }
-  __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
+  __device__ __forceinline__ bool preload(int row, bool ok, int col0, int N, uint32_t* w) const {
+    if (!ok || h || col0 + 16 > N) return false;
+    const __nv_bfloat16* p = hh + (size_t)row * ldm + col0;
+    if (((uintptr_t)p) & 31u) return false;
+    ld32B(p, w);
+    return true;
+  }
+  __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v, const uint32_t* pre = nullptr) {
     if (!ok) return;
     const float* hp = h ? h + (size_t)row * ld + col0 : nullptr;
     float* o = out ? out + (size_t)row * ld + col0 : nullptr;
@@ -262,7 +290,7 @@ struct EpiDgradTanh {       // out = acc * (1 - h^2) (+ optional bf16 hi/lo mirr
       if (h) {
         ld16f(hp, hv);
       } else {
-        ld16bf(hh + om, hv);
+        if (pre) unpack16bf(pre, hv); else ld16bf(hh + om, hv);
         if (hl) {
           float lo[16];
           ld16bf(hl + om, lo);
@@ -290,12 +318,14 @@ struct EpiDgradTanh {       // out = acc * (1 - h^2) (+ optional bf16 hi/lo mirr
 
 // (mu_j, ls_j) = columns (2j, 2j+1) of h_e.[W4|W5]_interleaved + bias -> eps, z, row term, z mirror (L = 1)
 struct EpiHeads {
+  static constexpr bool PREFETCH = false;   // persistent kernel: unrolled epilogue with the next chunk's operand in flight
   const float* b4; const float* b5; int Z; int la; EpsSource src;
   float* mu; float* ls; float* eps; float* z; __nv_bfloat16* z_hi; __nv_bfloat16* z_lo; int ldz; float* aux_part;
   float acc;
   __device__ __forceinline__ void begin() { acc = 0.f; }
   __device__ __forceinline__ void split(int) {}
-  __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
+  __device__ __forceinline__ bool preload(int, bool, int, int, uint32_t*) const { return false; }
+  __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v, const uint32_t* = nullptr) {
     if (!ok) return;
     // one Philox counter yields four draws: elements (row, 4g..4g+3) share one when Z is a multiple of 4
     float e8[8];
@@ -374,11 +404,13 @@ struct EpiHeads {
 
 // dz = da1.W1^T -> dmu, dls (L = 1; formulas of SURVEY.md 8a, as launch_dprep / lb_latent_bwd) + bf16 mirror [dmu|dls]
 struct EpiDzPrep {
+  static constexpr bool PREFETCH = false;   // persistent kernel: unrolled epilogue with the next chunk's operand in flight
   const float* z; const float* eps; const float* mu; const float* ls; int Z; int la; float w;
   float* dmu; float* dls; __nv_bfloat16* dd_hi; __nv_bfloat16* dd_lo; int ldq;
   __device__ __forceinline__ void begin() {}
   __device__ __forceinline__ void split(int) {}
-  __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v) {
+  __device__ __forceinline__ bool preload(int, bool, int, int, uint32_t*) const { return false; }
+  __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v, const uint32_t* = nullptr) {
     if (!ok) return;
     const size_t o0 = (size_t)row * Z + col0;
     const bool al16 = ((Z & 3) == 0) &&
@@ -714,25 +746,56 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
       const int tm = tile / tiles_n, tn = tile % tiles_n;
       const int n0 = tn * BN;
       const uint32_t buf = lt % NBUF, use = lt / NBUF;
-      tc::mbar_wait(&tmem_full[buf], use & 1);
-      tc::tc_fence_after();
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const int row = tm * TILE_M + mt * BM + q * 32 + lane;
         const bool ok = row < M;
         epi.begin();
         const uint32_t acc = tmem_base + buf * (MT * ACC_COLS) + mt * ACC_COLS + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-        for (int c = cs * SLICE; c < (cs + 1) * SLICE; c += 16) {
-          float v[16];
-          tc::tmem_ld16(acc + (uint32_t)c, v);
-          tc::tmem_ld_wait();
-          if (mt == MT - 1 && c + 16 >= (cs + 1) * SLICE) {   // last read of this warp: hand the accumulators back early
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
+        // the global operand of chunk i+1 (one 32-byte sector of a bf16 mirror) is requested before chunk i is finished:
+        // 4 warps per scheduler, each a serial chain TMEM read -> global operand -> math -> store, cannot hide that
+        // latency otherwise (ncu: 22 % of the samples on the first use of the load)
+        constexpr int NCH = SLICE / 16;
+        if constexpr (Epi::PREFETCH) {
+          uint32_t pw[2][8];
+          bool ph[2];
+          ph[0] = (n0 + cs * SLICE < N) && epi.preload(row, ok, n0 + cs * SLICE, N, pw[0]);
+          if (mt == 0) {                                      // the first request overlaps the wait for the accumulator
+            tc::mbar_wait(&tmem_full[buf], use & 1);
+            tc::tc_fence_after();
           }
-          if (n0 + c < N) epi.chunk(row, ok, n0 + c, N, v);
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) {
+            const int c = cs * SLICE + 16 * i;
+            if (i + 1 < NCH) ph[(i + 1) & 1] = (n0 + c + 16 < N) && epi.preload(row, ok, n0 + c + 16, N, pw[(i + 1) & 1]);
+            float v[16];
+            tc::tmem_ld16(acc + (uint32_t)c, v);
+            tc::tmem_ld_wait();
+            if (mt == MT - 1 && i == NCH - 1) {               // last read of this warp: hand the accumulators back early
+              tc::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
+            }
+            if (n0 + c < N) epi.chunk(row, ok, n0 + c, N, v, ph[i & 1] ? pw[i & 1] : nullptr);
+          }
+        } else {
+          if (mt == 0) {
+            tc::mbar_wait(&tmem_full[buf], use & 1);
+            tc::tc_fence_after();
+          }
+#pragma unroll 1
+          for (int i = 0; i < NCH; ++i) {
+            const int c = cs * SLICE + 16 * i;
+            float v[16];
+            tc::tmem_ld16(acc + (uint32_t)c, v);
+            tc::tmem_ld_wait();
+            if (mt == MT - 1 && i == NCH - 1) {
+              tc::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
+            }
+            if (n0 + c < N) epi.chunk(row, ok, n0 + c, N, v);
+          }
         }
         epi.end(row, ok, tn * (EPI_WARPS / 4) + cs, tiles_n * (EPI_WARPS / 4));
       }
