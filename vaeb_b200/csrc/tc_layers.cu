@@ -1003,16 +1003,37 @@ struct PrepArgs {
   float* w45t;
   int D, H, Z, ldh, ldd, ldq;
 };
+// row-major fp32 [rows, cols] -> bf16 hi (/lo) mirror [rows, ld]: four elements per thread when cols % 4 == 0
+// (16-byte loads, 8-byte stores), else one
+__device__ __forceinline__ void mirror_quad(const float* __restrict__ src, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                                            int64_t q, int rows, int cols, int ld) {
+  if ((cols & 3) == 0 && (ld & 3) == 0 && (((uintptr_t)src) & 15u) == 0 && ((((uintptr_t)hi) | ((uintptr_t)lo)) & 7u) == 0) {
+    const int64_t i = 4 * q;
+    if (i >= (int64_t)rows * cols) return;
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    const size_t o = (size_t)(i / cols) * ld + (i % cols);
+    const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(hi + o) = make_uint2(h0, h1);
+    if (lo)
+      *reinterpret_cast<uint2*>(lo + o) =
+          make_uint2(pack_bf16x2(v.x - __uint_as_float(h0 << 16), v.y - __uint_as_float(h0 & 0xffff0000u)),
+                     pack_bf16x2(v.z - __uint_as_float(h1 << 16), v.w - __uint_as_float(h1 & 0xffff0000u)));
+    return;
+  }
+  for (int64_t i = 4 * q; i < 4 * q + 4 && i < (int64_t)rows * cols; ++i)
+    put_split(hi, lo, (size_t)(i / cols) * ld + (i % cols), src[i]);
+}
+
 __global__ void __launch_bounds__(256)
 prepare_weights_kernel(PrepArgs a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int D = a.D, H = a.H, Z = a.Z;
   switch (blockIdx.y) {
     case 0:
-      if (i < (int64_t)D * H) put_split(a.w3h, a.w3l, (size_t)(i / H) * a.ldh + (i % H), a.W3[i]);
+      mirror_quad(a.W3, a.w3h, a.w3l, i, D, H, a.ldh);
       break;
     case 1:
-      if (i < (int64_t)H * D) put_split(a.w2h, a.w2l, (size_t)(i / D) * a.ldd + (i % D), a.W2[i]);
+      mirror_quad(a.W2, a.w2h, a.w2l, i, H, D, a.ldd);
       break;
     case 2:
       if (i < (int64_t)2 * Z * H) {
@@ -1031,7 +1052,7 @@ prepare_weights_kernel(PrepArgs a) {
       }
       break;
     default:
-      if (i < (int64_t)Z * H) put_split(a.w1h, a.w1l, (size_t)(i / H) * a.ldh + (i % H), a.W1[i]);
+      mirror_quad(a.W1, a.w1h, a.w1l, i, Z, H, a.ldh);
       break;
   }
 }
@@ -1044,7 +1065,10 @@ cudaError_t tc_prepare_weights(cudaStream_t st, int64_t* launches, const float* 
              (__nv_bfloat16*)b.w3h, (__nv_bfloat16*)b.w3l, (__nv_bfloat16*)b.w2h, (__nv_bfloat16*)b.w2l,
              (__nv_bfloat16*)b.w45h, (__nv_bfloat16*)b.w45l, (__nv_bfloat16*)b.whh, (__nv_bfloat16*)b.whl,
              (__nv_bfloat16*)b.w1h, (__nv_bfloat16*)b.w1l, w45t, D, H, Z, b.ldh, b.ldd, b.ldq};
-  const int64_t n = (int64_t)D * H;
+  // x-extent: a quad per thread for the three mirrors, an element per thread for the (small) transposed head copies
+  int64_t n = ((int64_t)D * H + 3) / 4;
+  if (n < (int64_t)2 * Z * H) n = (int64_t)2 * Z * H;
+  if (n < (int64_t)H * b.ldq) n = (int64_t)H * b.ldq;
   prepare_weights_kernel<<<dim3((unsigned)((n + 255) / 256), 5), 256, 0, st>>>(a);
   ++*launches;
   return cudaGetLastError();
