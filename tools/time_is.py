@@ -7,7 +7,7 @@ n, L = int(sys.argv[1]), int(sys.argv[2])
 x = synthetic_mnist(n, seed=4242)
 for prec in sys.argv[3].split(","):
     m = vaeb_b200.VAEB(x[:100], False, 500, 20, 100, 1, 0.01, False, False, precision=prec)
-    m.log_px(x[:64], L=L)
+    m.log_px(x, L=min(L, 256))       # warm-up at the timed number of points (buffers sized, kernels loaded)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     lp = m.log_px(x, L=L)

@@ -644,6 +644,17 @@ int vaeb_destroy(vaeb_handle* h) {
                   b.heh, b.hel, b.d1h, b.d1l, b.zh, b.zl, b.ddh, b.ddl, b.w45h, b.w45l, b.w1h, b.w1l, b.whh, b.whl};
     for (void* q : tb) if (q) cudaFree(q);
   }
+  {
+    IsTcState& q = h->istc;
+    if (q.copy) {
+      cudaStreamSynchronize(q.copy);
+      for (int i = 0; i < 2; ++i) { cudaEventDestroy(q.copied[i]); cudaEventDestroy(q.consumed[i]); if (q.xbuf[i]) cudaFree(q.xbuf[i]); }
+      cudaStreamDestroy(q.copy);
+    }
+    if (q.w2t) cudaFree(q.w2t);
+    if (q.w1t) cudaFree(q.w1t);
+    if (q.partial) cudaFree(q.partial);
+  }
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->copy_stream) {
@@ -1103,6 +1114,65 @@ int vaeb_is_logpx(vaeb_handle* h, const float* x, int64_t n, int32_t L, const fl
   cudaStream_t st = h->stream;
   int64_t* lc = &h->launches;
   const float* th = h->d_params;
+  if (tcp && !logw_out && !eps) {
+    // Tensor-core estimator with Philox noise: host x in, host log p out, pipelined.  The points go through two
+    // staging buffers: chunk i+1 is copied on a second stream while chunk i is encoded and sampled, so only the first
+    // copy is exposed (31 MB of x for 10k points is ~3 ms of a 49 ms call; per GPU of an 8-way shard 14 % of the call).
+    IsTcState& q = h->istc;
+    if (!q.copy) {
+      VAEB_CUDA(cudaStreamCreateWithFlags(&q.copy, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        VAEB_CUDA(cudaEventCreateWithFlags(&q.copied[i], cudaEventDisableTiming));
+        VAEB_CUDA(cudaEventCreateWithFlags(&q.consumed[i], cudaEventDisableTiming));
+      }
+    }
+    // about four chunks per call, 512..8192 points each (a chunk of 512 points x 5000 samples is 20480 tiles: 138 per SM)
+    int64_t pcp = ((n + 3) / 4 + 255) / 256 * 256;
+    pcp = std::max<int64_t>(512, std::min<int64_t>(pcp, 8192));
+    pcp = std::min<int64_t>(pcp, n);
+    VAEB_REQUIRE(pcp * L < (int64_t)1 << 31, "L too large");
+    VAEB_TRY(ensure_ws(h, pcp, pcp, false));
+    VAEB_TRY(grow(&h->d_out, &h->out_cap, pcp));
+    if (pcp * D > q.xbuf_cap) {
+      VAEB_CUDA(cudaStreamSynchronize(st));
+      VAEB_CUDA(cudaStreamSynchronize(q.copy));
+      for (int i = 0; i < 2; ++i) {
+        if (q.xbuf[i]) VAEB_CUDA(cudaFree(q.xbuf[i]));
+        q.xbuf[i] = nullptr;
+        VAEB_CUDA(cudaMalloc((void**)&q.xbuf[i], (size_t)pcp * D * sizeof(float)));
+      }
+      q.xbuf_cap = pcp * D;
+    }
+    const int64_t n_chunks = (n + pcp - 1) / pcp;
+    auto copy_in = [&](int64_t k) -> int {
+      const int64_t i0 = k * pcp, c = std::min<int64_t>(pcp, n - i0);
+      if (k >= 2) VAEB_CUDA(cudaStreamWaitEvent(q.copy, q.consumed[k & 1], 0));     // the buffer's previous chunk was read
+      VAEB_CUDA(cudaMemcpyAsync(q.xbuf[k & 1], x + i0 * D, (size_t)c * D * sizeof(float), cudaMemcpyHostToDevice, q.copy));
+      VAEB_CUDA(cudaEventRecord(q.copied[k & 1], q.copy));
+      return VAEB_OK;
+    };
+    // work queued on the handle's stream before this call may still read nothing of ours; order the copy stream after
+    // nothing: the staging buffers belong to this path alone (their last readers were synchronised at the end of the
+    // previous call)
+    VAEB_TRY(copy_in(0));
+    for (int64_t k = 0; k < n_chunks; ++k) {
+      const int64_t i0 = k * pcp;
+      const int c = (int)std::min<int64_t>(pcp, n - i0);
+      const float* dx = q.xbuf[k & 1];
+      VAEB_CUDA(cudaStreamWaitEvent(st, q.copied[k & 1], 0));
+      EpsSource src{nullptr, h->cfg.seed, VAEB_STREAM_IS, 0u, row_offset + i0};
+      Workspace& s = h->ws;
+      VAEB_LAUNCH(launch_dense_act(st, lc, dx, c, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, 1, s.h_e));
+      VAEB_LAUNCH(launch_enc2(st, lc, s.h_e, c, H, T_(h, th, l.iW4), T_(h, th, l.ib4), T_(h, th, l.iW5),
+                              T_(h, th, l.ib5), Z, 0, 0, src, s.mu, s.ls, s.eps, s.z, s.row_aux));
+      VAEB_TRY(is_tc_run(h, dx, s.mu, s.ls, c, L, nullptr, row_offset + i0, h->d_out, nullptr));
+      VAEB_CUDA(cudaEventRecord(q.consumed[k & 1], st));
+      if (k + 1 < n_chunks) VAEB_TRY(copy_in(k + 1));       // the host stages the next chunk while this one runs
+      VAEB_CUDA(cudaMemcpyAsync(logpx_out + i0, h->d_out, (size_t)c * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    VAEB_CUDA(cudaStreamSynchronize(st));
+    return VAEB_OK;
+  }
   std::vector<float> tmp;
   for (int64_t i0 = 0; i0 < n; i0 += pc) {
     const int c = (int)std::min<int64_t>(pc, n - i0);

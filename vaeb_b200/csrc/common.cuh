@@ -100,6 +100,10 @@ struct IsTcState {
   alignas(64) unsigned char map_full[128];           // CUtensorMap over w2t, boxes of `tail_cols` rows (one output chunk)
   int n_sm = 0, n_chunks = 0, tail_cols = 0;         // tail_cols = chunk width NC (multiple of 16)
   void* partial = nullptr; int64_t partial_cap = 0;  // per-tile (max, sum exp)
+  // pipelined host input of vaeb_is_logpx: the next chunk of points is copied on `copy` while this one is sampled
+  cudaStream_t copy = nullptr;
+  cudaEvent_t copied[2] = {}, consumed[2] = {};
+  float* xbuf[2] = {nullptr, nullptr}; int64_t xbuf_cap = 0;
 };
 
 struct vaeb_handle {
