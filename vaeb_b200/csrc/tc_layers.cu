@@ -837,7 +837,11 @@ cudaError_t launch_layer_persistent(cudaStream_t st, const LayerMaps& maps, cons
   attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr.val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = &attr;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  // always a programmatic dependent launch: one CTA per SM with ~200 KB of shared memory never shares an SM with the
+  // kernel before it, so its prologue (barriers, TMEM, descriptors) simply hides behind that kernel's tail
+  // (16384 rows, bf16: 250 -> 239 us per update; VAEB_NO_PDL=1 switches it off)
+  static const bool no_pdl = getenv("VAEB_NO_PDL") != nullptr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
   return cudaLaunchKernelEx(&cfg, kfn, maps, epi, M, N, K, a_row_off);
 }
 
