@@ -262,9 +262,11 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
     VAEB_TRY(tc_ensure(h, rows, R));
     bn = R >= 1024 ? 128 : 64;
     bna = tc_act_bn(rows, std::min(H, D));
-    // bf16x3 kernels are one CTA per SM: an early dependent grid never takes slots from the running one (16384 rows:
-    // 523 -> 499 us per update); in plain bf16 (two CTAs per SM) it does beyond about one wave (331 -> 355 us)
-    tc_set_pdl(R <= 4096 || t.ns == 2);
+    // Programmatic dependent launch for the one-tile-per-CTA kernels: bf16x3 (one CTA per SM: an early dependent grid
+    // never takes slots from the running one; 16384 rows: 523 -> 499 us per update) and, in plain bf16, whenever the
+    // activation layers are NOT in the persistent form (8192 rows: 215 -> 196 us); next to the persistent kernels the
+    // early two-per-SM grids cost more than they hide (16384 rows: 241 -> 247 us).  Persistent launches always use it.
+    tc_set_pdl(bna != 256 || t.ns == 2);
     TcBuffers b = t.data;
     int64_t rows_data;
     const bool resident = h->d_x && x >= h->d_x && x < h->d_x + (size_t)h->n_data * D;

@@ -845,11 +845,11 @@ cudaError_t launch_layer_persistent(cudaStream_t st, const LayerMaps& maps, cons
   return cudaLaunchKernelEx(&cfg, kfn, maps, epi, M, N, K, a_row_off);
 }
 
-// the persistent form pays off from about two tiles per SM
+// the persistent form pays off from about one 128 x 256 tile per SM (4096 rows: 145 vs 142 us, bf16x3 190 vs 169 us)
 inline bool use_persistent(int M, int N, int bn) {
   if (g_persist == -1) { const char* e = getenv("VAEB_TC_PERSIST"); g_persist = e ? (e[0] != '0' ? 1 : 0) : 2; }
   if (g_persist != 2) return g_persist == 1;
-  return ((N + bn - 1) / bn) * ((M + BM - 1) / BM) >= 148 + 74;
+  return ((N + bn - 1) / bn) * ((M + BM - 1) / BM) >= 120;   // 8192 rows x 500: 128 tiles (measured: 196 -> 170 us per update)
 }
 
 
