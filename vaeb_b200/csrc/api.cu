@@ -152,7 +152,8 @@ int tc_ensure(vaeb_handle* h, int64_t rows, int64_t R) {
   const bool lo = t.ns == 2;
   if (b.ldh == 0) {
     // rows of the mirrors start on 32-byte sectors: a thread of a tcgen05 epilogue writes 16 bf16 = one whole sector
-    b.ldh = (H + 1 + 15) / 16 * 16; b.ldd = (D + 1 + 15) / 16 * 16; b.ldx = b.ldd;
+    // (and on whole 64-element column groups: the MN-major operands are loaded with one 3-D TMA box per tile)
+    b.ldh = (H + 1 + 63) / 64 * 64; b.ldd = (D + 1 + 63) / 64 * 64; b.ldx = b.ldd;
     VAEB_TRY(grow_bytes(&b.w3h, (size_t)D * b.ldh * 2));
     VAEB_TRY(grow_bytes(&b.w2h, (size_t)H * b.ldd * 2));
     VAEB_CUDA(cudaMemsetAsync(b.w3h, 0, (size_t)D * b.ldh * 2, h->stream));
@@ -288,9 +289,9 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
       rows_data = rows;
     }
     x_mirror_hi = b.xh; x_mirror_lo = t.ns == 2 ? b.xl : nullptr;
-    if (t.key_rows != rows || t.key_R != R || t.key_data != rows_data || t.key_bn != bna || t.key_x != b.xh) {
-      VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bna, Z));
-      t.key_rows = rows; t.key_R = R; t.key_data = rows_data; t.key_bn = bna; t.key_x = b.xh;
+    if (t.key_rows != rows || t.key_R != R || t.key_data != rows_data || t.key_bn != bna * 1024 + bn || t.key_x != b.xh) {
+      VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bna, Z, bn));
+      t.key_rows = rows; t.key_R = R; t.key_data = rows_data; t.key_bn = bna * 1024 + bn; t.key_x = b.xh;
     }
     if (want_grads && b.heh && b.zh && b.d1h && b.ddh && latent_large_batch(rows, H, Z, L))
       PH("weight mirrors / transposes -> bf16 (one launch)", 0, 12.0 * dD * dH + 60.0 * dZ * dH,

@@ -81,6 +81,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 3-D tile load (MN-major operands: c0 = element inside a 64-wide column group, c1 = contraction row, c2 = column group).
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ---- tcgen05 ------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {   // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
@@ -175,5 +183,11 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
 
 // ---- host: tensor maps -------------------------------------------------------------------
 // 2-D bf16 row-major matrix [rows, cols] (cols contiguous) -> boxes of [box_rows x 64 cols], 128B swizzle.
+// MN-major operand [k_rows, cols] (cols contiguous, row stride a multiple of 64 elements) seen as
+// [cols/64 groups][k_rows][64]: ONE box of `groups` column groups x 64 contraction rows per tile and k block lands in
+// shared memory as `groups` consecutive [64 x 128 B] SWIZZLE_128B blocks -- a TMA box costs ~120 ns of issue time
+// whatever its size (tools/tma_fill_probe.py), so one 32 KB box instead of four 8 KB ones.
+int vaeb_make_tmap_bf16_mn(CUtensorMap* out, const void* base, uint64_t k_rows, uint64_t cols, uint64_t row_stride_elems,
+                           uint32_t groups);
 int vaeb_make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                         uint32_t box_rows);

@@ -184,6 +184,30 @@ int vaeb_make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint6
   return VAEB_OK;
 }
 
+int vaeb_make_tmap_bf16_mn(CUtensorMap* out, const void* base, uint64_t k_rows, uint64_t cols, uint64_t row_stride_elems,
+                           uint32_t groups) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { vaeb_set_error("cuTensorMapEncodeTiled not available from the driver"); return VAEB_ECUDA; }
+  const uint64_t n_groups = (cols + 63) / 64;
+  if (row_stride_elems % 64 != 0 || n_groups * 64 > row_stride_elems || ((uintptr_t)base & 127) != 0 || groups < 1 ||
+      groups > 4) {
+    vaeb_set_error("MN-major tensor map: the row stride must be a multiple of 64 elements covering every column group");
+    return VAEB_EINVAL;
+  }
+  cuuint64_t gdim[3] = {64, k_rows, n_groups};
+  cuuint64_t gstr[2] = {row_stride_elems * 2, 128};
+  cuuint32_t box[3] = {64, 64, groups};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    vaeb_set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult " + std::to_string((int)r));
+    return VAEB_ECUDA;
+  }
+  return VAEB_OK;
+}
+
 extern "C" int vaeb_tc_gemm_test(int32_t device, int32_t M, int32_t N, int32_t K, int32_t a_mn_major,
                                  int32_t b_mn_major, int32_t block_n, const float* A, const float* B, float* C) {
   // A is the logical [M,K] matrix, B the logical [K,N] matrix (row-major fp32 on the host); they
@@ -278,4 +302,84 @@ extern "C" int vaeb_tc_gemm_probe(int32_t device, int32_t M, int32_t N, int32_t 
   VAEB_CUDA(cudaMemcpy(stamps, dD, 40 * 8, cudaMemcpyDeviceToHost));
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dD);
   return VAEB_OK;
+}
+
+
+// ---- L2 -> shared-memory fill-rate probe ------------------------------------------------------------------
+// Every CTA (one per SM, or `ctas` of them) streams the SAME [rows x 64] bf16 matrix (rows*128 bytes, L2 resident
+// after the first pass) through a ring of `stages` stages with TMA boxes of `box_rows` rows, `batch` boxes per stage
+// (one mbarrier wait + one expect_tx per stage, like a GEMM producer loop), `passes` times, and does nothing else:
+// the rate at which ONE issuing thread can fill shared memory from L2 when all SMs read one hot weight matrix -- the
+// access pattern of the persistent layers and of the IS kernel.  Returns GB/s over all CTAs.
+namespace {
+__global__ void __launch_bounds__(128, 1)
+tma_fill_kernel(const __grid_constant__ CUtensorMap map, int rows, int box_rows, int batch, int stages, int passes,
+                unsigned long long* sink) {
+  extern __shared__ uint8_t fill_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)fill_smem_raw + 1023) & ~(uintptr_t)1023);
+  const int box_bytes = box_rows * 128, stage_bytes = batch * box_bytes;
+  uint64_t* full = (uint64_t*)(smem + (size_t)stages * stage_bytes);
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&map);
+    for (int s = 0; s < stages; ++s) tc::mbar_init(&full[s], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int boxes = rows / box_rows;
+    const long long total = (long long)(boxes / batch) * passes;       // stages issued in all
+    long long issued = 0, done = 0;
+    const int start = (int)((blockIdx.x * 7) % boxes);                 // CTAs start at different rows
+    auto issue = [&](long long it) {
+      const int s = (int)(it % stages);
+      tc::mbar_expect_tx(&full[s], stage_bytes);
+      for (int b = 0; b < batch; ++b)
+        tc::tma_load_2d(smem + (size_t)s * stage_bytes + (size_t)b * box_bytes, &map, &full[s], 0,
+                        (int)((start + it * batch + b) % boxes) * box_rows);
+    };
+    for (; issued < total && issued < stages; ++issued) issue(issued);
+    for (; done < total; ++done) {
+      const int s = (int)(done % stages);
+      tc::mbar_wait(&full[s], (uint32_t)((done / stages) & 1));
+      if (issued < total) { issue(issued); ++issued; }
+    }
+    if (sink) atomicAdd(sink, (unsigned long long)done);
+  }
+}
+}  // namespace
+
+extern "C" int vaeb_tma_fill_probe(int32_t device, int32_t rows, int32_t box_rows, int32_t batch, int32_t stages,
+                                   int32_t passes, int32_t ctas, float* gbytes_per_s) {
+  VAEB_REQUIRE(gbytes_per_s && rows > 0 && box_rows >= 8 && box_rows <= 256 && batch >= 1 &&
+               rows % (box_rows * batch) == 0 && stages >= 1 && passes >= 1 && ctas >= 1, "bad argument");
+  const size_t smem = (size_t)stages * batch * box_rows * 128 + stages * 8 + 1024 + 64;
+  VAEB_REQUIRE(smem <= 227 * 1024, "ring does not fit in shared memory");
+  VAEB_CUDA(cudaSetDevice(device));
+  void* d = nullptr;
+  unsigned long long* sink = nullptr;
+  VAEB_CUDA(cudaMalloc(&d, (size_t)rows * 128));
+  VAEB_CUDA(cudaMemset(d, 0, (size_t)rows * 128));
+  VAEB_CUDA(cudaMalloc((void**)&sink, 8));
+  VAEB_CUDA(cudaMemset(sink, 0, 8));
+  CUtensorMap tm;
+  int rc = vaeb_make_tmap_bf16(&tm, d, (uint64_t)rows, 64, 64, (uint32_t)box_rows);
+  if (rc == VAEB_OK) {
+    cudaError_t e = cudaFuncSetAttribute(tma_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    if (e == cudaSuccess) {
+      tma_fill_kernel<<<ctas, 128, smem>>>(tm, rows, box_rows, batch, stages, 1, sink);      // warm-up: into L2
+      cudaEventRecord(e0);
+      tma_fill_kernel<<<ctas, 128, smem>>>(tm, rows, box_rows, batch, stages, passes, sink);
+      cudaEventRecord(e1);
+      e = cudaEventSynchronize(e1);
+    }
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) { vaeb_set_error(std::string("tma fill probe: ") + cudaGetErrorString(e)); rc = VAEB_ECUDA; }
+    else *gbytes_per_s = (float)((double)rows * 128.0 * passes * ctas / (ms * 1e-3) / 1e9);
+  }
+  cudaFree(d); cudaFree(sink);
+  return rc;
 }

@@ -558,14 +558,15 @@ tc_layer_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, i
         uint8_t* b = base + NS * S::A_BYTES + sp * S::B_BYTES;
         const CUtensorMap* ta = sp ? &maps.a_lo : &maps.a_hi;
         const CUtensorMap* tb = sp ? &maps.b_lo : &maps.b_hi;
+        // MN-major operands: ONE 3-D box per tile and k block (its BM/64 resp. BN/64 column groups land as consecutive
+        // 8 KB blocks) -- the producer is bound by the number of boxes it issues, not by their bytes
         if (A_MN) {   // A stored [K rows, M contiguous]: the row offset applies to the K coordinate
-          for (int g = 0; g < BM / 64; ++g)
-            tc::tma_load_2d(a + g * 8192, ta, &full[s], m0 + g * 64, a_row_off + (kb0 + kb) * BK);
+          tc::tma_load_3d(a, ta, &full[s], 0, a_row_off + (kb0 + kb) * BK, m0 / 64);
         } else {      // A stored [M rows, K contiguous]
           tc::tma_load_2d(a, ta, &full[s], (kb0 + kb) * BK, a_row_off + m0);
         }
         if (B_MN) {
-          for (int g = 0; g < BN / 64; ++g) tc::tma_load_2d(b + g * 8192, tb, &full[s], n0 + g * 64, (kb0 + kb) * BK);
+          tc::tma_load_3d(b, tb, &full[s], 0, (kb0 + kb) * BK, n0 / 64);
         } else {
           tc::tma_load_2d(b, tb, &full[s], (kb0 + kb) * BK, n0);
         }
@@ -701,7 +702,7 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
           for (int mt = 0; mt < MT; ++mt)
             tc::tma_load_2d(a + mt * S::A1_BYTES, ta, &full[s], kb * BK, a_row_off + m0 + mt * BM);
           if (B_MN) {
-            for (int g = 0; g < BN / 64; ++g) tc::tma_load_2d(b + g * 8192, tb, &full[s], n0 + g * 64, kb * BK);
+            tc::tma_load_3d(b, tb, &full[s], 0, kb * BK, n0 / 64);      // one box: BN/64 column groups
           } else {
             tc::tma_load_2d(b, tb, &full[s], kb * BK, n0);
           }
@@ -1121,44 +1122,55 @@ static int make_pair(CUtensorMap* hi, CUtensorMap* lo, const void* bh, const voi
   return VAEB_OK;
 }
 
-int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z) {
+// MN-major operand [k_rows, cols]: 3-D map with `groups` 64-wide column groups per box
+static int make_pair_mn(CUtensorMap* hi, CUtensorMap* lo, const void* bh, const void* bl, uint64_t k_rows, uint64_t cols,
+                        uint64_t stride, uint32_t groups) {
+  VAEB_TRY(vaeb_make_tmap_bf16_mn(hi, bh, k_rows, cols, stride, groups));
+  if (bl) VAEB_TRY(vaeb_make_tmap_bf16_mn(lo, bl, k_rows, cols, stride, groups));
+  else *lo = *hi;
+  return VAEB_OK;
+}
+
+// bn: UMMA N of the activation layers (tc_act_bn); bn_w: of the weight-gradient GEMMs
+int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z, int bn_w) {
+  const uint32_t ga = BM / 64, gb = (uint32_t)bn / 64, gw = (uint32_t)bn_w / 64;
   // enc1: A = x mirror [rows_data, D] K-major (the ones column at D stays out of the map), B = W3 [D, H] MN-major
   LayerMaps* e1 = reinterpret_cast<LayerMaps*>(m->enc1);
   VAEB_TRY(make_pair(&e1->a_hi, &e1->a_lo, b.xh, b.xl, rows_data, D, b.ldx, BM));
-  VAEB_TRY(make_pair(&e1->b_hi, &e1->b_lo, b.w3h, b.w3l, D, H, b.ldh, 64));
+  VAEB_TRY(make_pair_mn(&e1->b_hi, &e1->b_lo, b.w3h, b.w3l, D, H, b.ldh, gb));
   // dec2: A = h_d mirror [R, H] K-major, B = W2 [H, D] MN-major
   LayerMaps* d2 = reinterpret_cast<LayerMaps*>(m->dec2);
   VAEB_TRY(make_pair(&d2->a_hi, &d2->a_lo, b.hdh, b.hdl, R, H, b.ldh, BM));
-  VAEB_TRY(make_pair(&d2->b_hi, &d2->b_lo, b.w2h, b.w2l, H, D, b.ldd, 64));
+  VAEB_TRY(make_pair_mn(&d2->b_hi, &d2->b_lo, b.w2h, b.w2l, H, D, b.ldd, gb));
   // dgrad h_d: A = da2 mirror [R, D] K-major, B = W2 [H, D] K-major (N = H rows)
   LayerMaps* dg = reinterpret_cast<LayerMaps*>(m->dgrad);
   VAEB_TRY(make_pair(&dg->a_hi, &dg->a_lo, b.da2h, b.da2l, R, D, b.ldd, BM));
   VAEB_TRY(make_pair(&dg->b_hi, &dg->b_lo, b.w2h, b.w2l, H, D, b.ldd, (uint32_t)bn));
   // wgrad W2: A = h_d mirror [R, H+1] MN-major (ones column -> bias row), B = da2 mirror [R, D] MN-major
   LayerMaps* w2 = reinterpret_cast<LayerMaps*>(m->wgrad2);
-  VAEB_TRY(make_pair(&w2->a_hi, &w2->a_lo, b.hdh, b.hdl, R, H + 1, b.ldh, 64));
-  VAEB_TRY(make_pair(&w2->b_hi, &w2->b_lo, b.da2h, b.da2l, R, D, b.ldd, 64));
+  VAEB_TRY(make_pair_mn(&w2->a_hi, &w2->a_lo, b.hdh, b.hdl, R, H + 1, b.ldh, ga));
+  VAEB_TRY(make_pair_mn(&w2->b_hi, &w2->b_lo, b.da2h, b.da2l, R, D, b.ldd, gw));
   // wgrad W3: A = x mirror [rows_data, D+1] MN-major, B = da3 mirror [rows, H] MN-major
   LayerMaps* w3 = reinterpret_cast<LayerMaps*>(m->wgrad3);
-  VAEB_TRY(make_pair(&w3->a_hi, &w3->a_lo, b.xh, b.xl, rows_data, D + 1, b.ldx, 64));
-  VAEB_TRY(make_pair(&w3->b_hi, &w3->b_lo, b.da3h, b.da3l, rows, H, b.ldh, 64));
+  VAEB_TRY(make_pair_mn(&w3->a_hi, &w3->a_lo, b.xh, b.xl, rows_data, D + 1, b.ldx, ga));
+  VAEB_TRY(make_pair_mn(&w3->b_hi, &w3->b_lo, b.da3h, b.da3l, rows, H, b.ldh, gw));
   if (b.heh) {
     // wgrad W1: A = z mirror [R, Z+1] MN-major (ones column -> gb1), B = da1 mirror [R, H] MN-major
     LayerMaps* w1 = reinterpret_cast<LayerMaps*>(m->wgrad1);
-    VAEB_TRY(make_pair(&w1->a_hi, &w1->a_lo, b.zh, b.zl, R, Z + 1, b.ldz, 64));
-    VAEB_TRY(make_pair(&w1->b_hi, &w1->b_lo, b.d1h, b.d1l, R, H, b.ldh, 64));
+    VAEB_TRY(make_pair_mn(&w1->a_hi, &w1->a_lo, b.zh, b.zl, R, Z + 1, b.ldz, ga));
+    VAEB_TRY(make_pair_mn(&w1->b_hi, &w1->b_lo, b.d1h, b.d1l, R, H, b.ldh, gw));
     // wgrad W4|W5: A = h_e mirror [rows, H+1] MN-major (ones column -> gb4|gb5), B = [dmu|dls] mirror [rows, 2Z]
     LayerMaps* w45 = reinterpret_cast<LayerMaps*>(m->wgrad45);
-    VAEB_TRY(make_pair(&w45->a_hi, &w45->a_lo, b.heh, b.hel, rows, H + 1, b.ldh, 64));
-    VAEB_TRY(make_pair(&w45->b_hi, &w45->b_lo, b.ddh, b.ddl, rows, 2 * Z, b.ldq, 64));
+    VAEB_TRY(make_pair_mn(&w45->a_hi, &w45->a_lo, b.heh, b.hel, rows, H + 1, b.ldh, ga));
+    VAEB_TRY(make_pair_mn(&w45->b_hi, &w45->b_lo, b.ddh, b.ddl, rows, 2 * Z, b.ldq, 1));
     // enc2: A = h_e mirror [rows, H] K-major, B = interleaved heads mirror [H, 2Z] MN-major
     LayerMaps* e2 = reinterpret_cast<LayerMaps*>(m->enc2);
     VAEB_TRY(make_pair(&e2->a_hi, &e2->a_lo, b.heh, b.hel, rows, H, b.ldh, BM));
-    VAEB_TRY(make_pair(&e2->b_hi, &e2->b_lo, b.whh, b.whl, H, 2 * Z, b.ldq, 64));
+    VAEB_TRY(make_pair_mn(&e2->b_hi, &e2->b_lo, b.whh, b.whl, H, 2 * Z, b.ldq, 1));
     // dec1: A = z mirror [R, Z] K-major (the ones column at Z stays out of the map), B = W1 mirror [Z, H] MN-major
     LayerMaps* d1 = reinterpret_cast<LayerMaps*>(m->dec1);
     VAEB_TRY(make_pair(&d1->a_hi, &d1->a_lo, b.zh, b.zl, R, Z, b.ldz, BM));
-    VAEB_TRY(make_pair(&d1->b_hi, &d1->b_lo, b.w1h, b.w1l, Z, H, b.ldh, 64));
+    VAEB_TRY(make_pair_mn(&d1->b_hi, &d1->b_lo, b.w1h, b.w1l, Z, H, b.ldh, gb));
     // dz: A = da1 mirror [R, H] K-major, B = W1 mirror [Z, H] K-major (N = Z rows)
     LayerMaps* dzm = reinterpret_cast<LayerMaps*>(m->dz);
     VAEB_TRY(make_pair(&dzm->a_hi, &dzm->a_lo, b.d1h, b.d1l, R, H, b.ldh, BM));
@@ -1166,7 +1178,7 @@ int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows,
     // dgrad h_e: A = [dmu|dls] mirror [rows, 2Z] K-major, B = [W4^T;W5^T] mirror [2Z, H] MN-major
     LayerMaps* dh = reinterpret_cast<LayerMaps*>(m->dhe);
     VAEB_TRY(make_pair(&dh->a_hi, &dh->a_lo, b.ddh, b.ddl, rows, 2 * Z, b.ldq, BM));
-    VAEB_TRY(make_pair(&dh->b_hi, &dh->b_lo, b.w45h, b.w45l, 2 * Z, H, b.ldh, 64));
+    VAEB_TRY(make_pair_mn(&dh->b_hi, &dh->b_lo, b.w45h, b.w45l, 2 * Z, H, b.ldh, gb));
   }
   return VAEB_OK;
 }

@@ -20,7 +20,7 @@ struct TcBuffers {   // bf16 mirrors; *l == nullptr in plain-bf16 mode
   void *w45h = nullptr, *w45l = nullptr;   // [W4^T ; W5^T]      [2Z, ldh]
   void *w1h = nullptr, *w1l = nullptr;     // W1                 [Z, ldh]
   void *whh = nullptr, *whl = nullptr;     // heads, interleaved [H, ldq]: column 2j = W4[:,j], 2j+1 = W5[:,j]
-  int ldz = 32, ldq = 64;
+  int ldz = 64, ldq = 64;                   // MN-major operands: row strides are multiples of 64 elements (3-D TMA boxes)
   int ldx = 0, ldh = 0, ldd = 0;
   float* wg_scratch = nullptr;             // split-K slices of the wide weight gradients
 };
@@ -45,7 +45,7 @@ void tc_set_pdl(bool on);
 // UMMA N of the activation layers (A K-major) for `rows` rows and outputs at least n_min wide: 256 selects the
 // persistent kernel (large batches), else 128 / 64 with one tile per CTA
 int tc_act_bn(int rows, int n_min);
-int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z);
+int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z, int bn_w);
 
 cudaError_t tc_split_matrix(cudaStream_t st, int64_t* launches, const float* src, int64_t rows, int cols, int ld_src,
                             void* hi, void* lo, int ld_dst, int ones_col);
