@@ -188,6 +188,6 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int c) {
 // shared memory as `groups` consecutive [64 x 128 B] SWIZZLE_128B blocks -- a TMA box costs ~120 ns of issue time
 // whatever its size (tools/tma_fill_probe.py), so one 32 KB box instead of four 8 KB ones.
 int vaeb_make_tmap_bf16_mn(CUtensorMap* out, const void* base, uint64_t k_rows, uint64_t cols, uint64_t row_stride_elems,
-                           uint32_t groups);
+                           uint32_t groups, uint32_t k_box = 64);
 int vaeb_make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                         uint32_t box_rows);

@@ -185,7 +185,7 @@ int vaeb_make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint6
 }
 
 int vaeb_make_tmap_bf16_mn(CUtensorMap* out, const void* base, uint64_t k_rows, uint64_t cols, uint64_t row_stride_elems,
-                           uint32_t groups) {
+                           uint32_t groups, uint32_t k_box) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { vaeb_set_error("cuTensorMapEncodeTiled not available from the driver"); return VAEB_ECUDA; }
   const uint64_t n_groups = (cols + 63) / 64;
@@ -196,7 +196,7 @@ int vaeb_make_tmap_bf16_mn(CUtensorMap* out, const void* base, uint64_t k_rows, 
   }
   cuuint64_t gdim[3] = {64, k_rows, n_groups};
   cuuint64_t gstr[2] = {row_stride_elems * 2, 128};
-  cuuint32_t box[3] = {64, 64, groups};
+  cuuint32_t box[3] = {64, k_box, groups};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -489,14 +489,23 @@ struct EpiDzPrep {
   __device__ __forceinline__ void end(int, bool, int, int) {}
 };
 
-template <int BN, int NS>
+// contraction extent of one ring stage: the weight gradients in plain bf16 (both operands MN-major, one 3-D box each)
+// take 128 rows per stage -- two 32 KB boxes per mbarrier round trip instead of two 16 KB ones: their producer is bound
+// by issues (wait + expect_tx + ~120 ns per box, tools/tma_fill_probe.py), not by bytes
+template <bool A_MN, bool B_MN, int NS>
+constexpr int stage_k() { return (A_MN && B_MN && NS == 1) ? 2 * BK : BK; }
+
+template <int BN, int NS, bool A_MN, int SK = BK>
 struct LayerSmem {
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int A_BYTES = BM * SK * 2;
+  static constexpr int B_BYTES = BN * SK * 2;
   static constexpr int STAGE_BYTES = NS * (A_BYTES + B_BYTES);
-  // plain bf16 (NS = 1): 3-4 stages so that TWO CTAs share an SM and one tile's epilogue overlaps the other's
-  // loads and MMAs (the kernel is one tile per CTA); bf16x3 stages are twice as large: one CTA per SM
-  static constexpr int BUDGET = NS == 1 ? 104 * 1024 : 200 * 1024;
+  // activation layers in plain bf16 (NS = 1): 3-4 stages so that TWO CTAs share an SM and one tile's epilogue
+  // overlaps the other's loads and MMAs (the kernel is one tile per CTA); bf16x3 stages are twice as large: one CTA
+  // per SM.  Weight gradients (A MN-major: split-K, at most one CTA per SM, a long contraction): the whole shared
+  // memory as ring -- their operand stream is bound by bytes in flight / L2 latency.
+  static constexpr bool TWO_PER_SM = NS == 1 && !A_MN;
+  static constexpr int BUDGET = TWO_PER_SM ? 104 * 1024 : 200 * 1024;
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
   static_assert(STAGES >= 2, "tile too large");
@@ -507,9 +516,10 @@ struct LayerMaps {            // hi/lo tensor maps of both operands (lo unused w
 };
 
 template <int BN, bool A_MN, bool B_MN, int NS, class Epi>
-__global__ void __launch_bounds__(TC_THREADS, NS == 1 ? 2 : 1)
+__global__ void __launch_bounds__(TC_THREADS, (NS == 1 && !A_MN) ? 2 : 1)
 tc_layer_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, int K, int a_row_off) {
-  using S = LayerSmem<BN, NS>;
+  constexpr int SK = stage_k<A_MN, B_MN, NS>();
+  using S = LayerSmem<BN, NS, A_MN, SK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(smem + S::STAGES * S::STAGE_BYTES);
@@ -519,7 +529,7 @@ tc_layer_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, i
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int nkb_all = (K + BK - 1) / BK;
+  const int nkb_all = (K + SK - 1) / SK;       // ring stages over the whole contraction
   // split-K (weight gradients at large batch: few output tiles, long contraction): slice z of gridDim.z
   const int kb0 = (int)(((long long)nkb_all * blockIdx.z) / gridDim.z);
   const int nkb = (int)(((long long)nkb_all * (blockIdx.z + 1)) / gridDim.z) - kb0;
@@ -561,14 +571,14 @@ tc_layer_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, i
         // MN-major operands: ONE 3-D box per tile and k block (its BM/64 resp. BN/64 column groups land as consecutive
         // 8 KB blocks) -- the producer is bound by the number of boxes it issues, not by their bytes
         if (A_MN) {   // A stored [K rows, M contiguous]: the row offset applies to the K coordinate
-          tc::tma_load_3d(a, ta, &full[s], 0, a_row_off + (kb0 + kb) * BK, m0 / 64);
+          tc::tma_load_3d(a, ta, &full[s], 0, a_row_off + (kb0 + kb) * SK, m0 / 64);
         } else {      // A stored [M rows, K contiguous]
-          tc::tma_load_2d(a, ta, &full[s], (kb0 + kb) * BK, a_row_off + m0);
+          tc::tma_load_2d(a, ta, &full[s], (kb0 + kb) * SK, a_row_off + m0);
         }
         if (B_MN) {
-          tc::tma_load_3d(b, tb, &full[s], 0, (kb0 + kb) * BK, n0 / 64);
+          tc::tma_load_3d(b, tb, &full[s], 0, (kb0 + kb) * SK, n0 / 64);
         } else {
-          tc::tma_load_2d(b, tb, &full[s], (kb0 + kb) * BK, n0);
+          tc::tma_load_2d(b, tb, &full[s], (kb0 + kb) * SK, n0);
         }
       }
     }
@@ -581,14 +591,15 @@ tc_layer_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, i
       tc::tc_fence_after();
       const uint32_t a = tc::smem_u32(smem + s * S::STAGE_BYTES);
       const uint32_t b = a + NS * S::A_BYTES;
+      constexpr uint32_t GRP = 128u * SK;      // bytes of one 64-wide column group of an MN-major stage
 #pragma unroll
-      for (int k = 0; k < BK / 16; ++k) {
-        const uint64_t dah = A_MN ? tc::desc_mnmajor(a, k, 8192u) : tc::desc_kmajor(a, k);
-        const uint64_t dbh = B_MN ? tc::desc_mnmajor(b, k, 8192u) : tc::desc_kmajor(b, k);
+      for (int k = 0; k < SK / 16; ++k) {
+        const uint64_t dah = A_MN ? tc::desc_mnmajor(a, k, GRP) : tc::desc_kmajor(a, k);
+        const uint64_t dbh = B_MN ? tc::desc_mnmajor(b, k, GRP) : tc::desc_kmajor(b, k);
         tc::umma_bf16(tmem_base, dah, dbh, idesc, (kb | k) != 0 ? 1u : 0u);
         if (NS == 2) {
-          const uint64_t dal = A_MN ? tc::desc_mnmajor(a + S::A_BYTES, k, 8192u) : tc::desc_kmajor(a + S::A_BYTES, k);
-          const uint64_t dbl = B_MN ? tc::desc_mnmajor(b + S::B_BYTES, k, 8192u) : tc::desc_kmajor(b + S::B_BYTES, k);
+          const uint64_t dal = A_MN ? tc::desc_mnmajor(a + S::A_BYTES, k, GRP) : tc::desc_kmajor(a + S::A_BYTES, k);
+          const uint64_t dbl = B_MN ? tc::desc_mnmajor(b + S::B_BYTES, k, GRP) : tc::desc_kmajor(b + S::B_BYTES, k);
           tc::umma_bf16(tmem_base, dah, dbl, idesc, 1u);
           tc::umma_bf16(tmem_base, dal, dbh, idesc, 1u);
         }
@@ -857,7 +868,7 @@ inline bool use_persistent(int M, int N, int bn) {
 template <int BN, bool A_MN, bool B_MN, int NS, class Epi>
 cudaError_t launch_layer(cudaStream_t st, const LayerMaps& maps, const Epi& epi, int M, int N, int K, int a_row_off,
                          int splits = 1) {
-  using S = LayerSmem<BN, NS>;
+  using S = LayerSmem<BN, NS, A_MN, stage_k<A_MN, B_MN, NS>()>;
   auto kfn = tc_layer_kernel<BN, A_MN, B_MN, NS, Epi>;
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
@@ -906,11 +917,13 @@ cudaError_t dispatch_layer(cudaStream_t st, int ns, int bn, const LayerMaps& map
 
 // Split-K plan of a weight-gradient GEMM [Mo x No] over K: as many K slices as fill the SMs once, at least
 // 8 k blocks each.  The slices go to scratch and are summed in a fixed order (deterministic, unlike atomics).
-int tc_wgrad_splits(int Mo, int No, int K, int bn) {
+int tc_wgrad_splits(int Mo, int No, int K, int bn, int ns) {
   const int tiles = ((No + bn - 1) / bn) * ((Mo + BM - 1) / BM);
-  const int nkb = (K + BK - 1) / BK;
+  const int sk = ns == 1 ? 2 * BK : BK;           // stage_k of the weight-gradient kernel
+  const int nst = (K + sk - 1) / sk;              // ring stages over the contraction
   int s = 148 / (tiles > 0 ? tiles : 1);
-  if (s > nkb / 8) s = nkb / 8;
+  if (s > nst * sk / (8 * BK)) s = nst * sk / (8 * BK);
+  if (s > nst) s = nst;
   return s < 1 ? 1 : s;
 }
 
@@ -966,7 +979,7 @@ bool add_reduce_job(TcReduceJobs* jobs, const TcReduceJob& j) {
 // `defer` != nullptr: the slices stay in `scratch` (a region of its own) and their reduction is appended to the list
 cudaError_t tc_wgrad_generic(cudaStream_t st, int64_t* launches, const LayerMaps& maps, int ns, int bn, int Kred,
                              int Hreal, int N, int a_row_off, float* gW, float* gb, float* scratch, TcReduceJobs* defer) {
-  const int splits = scratch ? tc_wgrad_splits(Hreal + 1, N, Kred, bn) : 1;
+  const int splits = scratch ? tc_wgrad_splits(Hreal + 1, N, Kred, bn, ns) : 1;
   const size_t stride = (size_t)(Hreal + 1) * N;
   EpiWgradTc epi{gW, gb, Hreal, N, splits > 1 ? scratch : nullptr, stride};
   ++*launches;
@@ -1124,9 +1137,9 @@ static int make_pair(CUtensorMap* hi, CUtensorMap* lo, const void* bh, const voi
 
 // MN-major operand [k_rows, cols]: 3-D map with `groups` 64-wide column groups per box
 static int make_pair_mn(CUtensorMap* hi, CUtensorMap* lo, const void* bh, const void* bl, uint64_t k_rows, uint64_t cols,
-                        uint64_t stride, uint32_t groups) {
-  VAEB_TRY(vaeb_make_tmap_bf16_mn(hi, bh, k_rows, cols, stride, groups));
-  if (bl) VAEB_TRY(vaeb_make_tmap_bf16_mn(lo, bl, k_rows, cols, stride, groups));
+                        uint64_t stride, uint32_t groups, uint32_t k_box = 64) {
+  VAEB_TRY(vaeb_make_tmap_bf16_mn(hi, bh, k_rows, cols, stride, groups, k_box));
+  if (bl) VAEB_TRY(vaeb_make_tmap_bf16_mn(lo, bl, k_rows, cols, stride, groups, k_box));
   else *lo = *hi;
   return VAEB_OK;
 }
@@ -1134,6 +1147,7 @@ static int make_pair_mn(CUtensorMap* hi, CUtensorMap* lo, const void* bh, const 
 // bn: UMMA N of the activation layers (tc_act_bn); bn_w: of the weight-gradient GEMMs
 int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z, int bn_w) {
   const uint32_t ga = BM / 64, gb = (uint32_t)bn / 64, gw = (uint32_t)bn_w / 64;
+  const uint32_t kw = b.w3l ? BK : 2 * BK;      // contraction rows per box of the weight-gradient operands (stage_k)
   // enc1: A = x mirror [rows_data, D] K-major (the ones column at D stays out of the map), B = W3 [D, H] MN-major
   LayerMaps* e1 = reinterpret_cast<LayerMaps*>(m->enc1);
   VAEB_TRY(make_pair(&e1->a_hi, &e1->a_lo, b.xh, b.xl, rows_data, D, b.ldx, BM));
@@ -1148,21 +1162,21 @@ int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows,
   VAEB_TRY(make_pair(&dg->b_hi, &dg->b_lo, b.w2h, b.w2l, H, D, b.ldd, (uint32_t)bn));
   // wgrad W2: A = h_d mirror [R, H+1] MN-major (ones column -> bias row), B = da2 mirror [R, D] MN-major
   LayerMaps* w2 = reinterpret_cast<LayerMaps*>(m->wgrad2);
-  VAEB_TRY(make_pair_mn(&w2->a_hi, &w2->a_lo, b.hdh, b.hdl, R, H + 1, b.ldh, ga));
-  VAEB_TRY(make_pair_mn(&w2->b_hi, &w2->b_lo, b.da2h, b.da2l, R, D, b.ldd, gw));
+  VAEB_TRY(make_pair_mn(&w2->a_hi, &w2->a_lo, b.hdh, b.hdl, R, H + 1, b.ldh, ga, kw));
+  VAEB_TRY(make_pair_mn(&w2->b_hi, &w2->b_lo, b.da2h, b.da2l, R, D, b.ldd, gw, kw));
   // wgrad W3: A = x mirror [rows_data, D+1] MN-major, B = da3 mirror [rows, H] MN-major
   LayerMaps* w3 = reinterpret_cast<LayerMaps*>(m->wgrad3);
-  VAEB_TRY(make_pair_mn(&w3->a_hi, &w3->a_lo, b.xh, b.xl, rows_data, D + 1, b.ldx, ga));
-  VAEB_TRY(make_pair_mn(&w3->b_hi, &w3->b_lo, b.da3h, b.da3l, rows, H, b.ldh, gw));
+  VAEB_TRY(make_pair_mn(&w3->a_hi, &w3->a_lo, b.xh, b.xl, rows_data, D + 1, b.ldx, ga, kw));
+  VAEB_TRY(make_pair_mn(&w3->b_hi, &w3->b_lo, b.da3h, b.da3l, rows, H, b.ldh, gw, kw));
   if (b.heh) {
     // wgrad W1: A = z mirror [R, Z+1] MN-major (ones column -> gb1), B = da1 mirror [R, H] MN-major
     LayerMaps* w1 = reinterpret_cast<LayerMaps*>(m->wgrad1);
-    VAEB_TRY(make_pair_mn(&w1->a_hi, &w1->a_lo, b.zh, b.zl, R, Z + 1, b.ldz, ga));
-    VAEB_TRY(make_pair_mn(&w1->b_hi, &w1->b_lo, b.d1h, b.d1l, R, H, b.ldh, gw));
+    VAEB_TRY(make_pair_mn(&w1->a_hi, &w1->a_lo, b.zh, b.zl, R, Z + 1, b.ldz, ga, kw));
+    VAEB_TRY(make_pair_mn(&w1->b_hi, &w1->b_lo, b.d1h, b.d1l, R, H, b.ldh, gw, kw));
     // wgrad W4|W5: A = h_e mirror [rows, H+1] MN-major (ones column -> gb4|gb5), B = [dmu|dls] mirror [rows, 2Z]
     LayerMaps* w45 = reinterpret_cast<LayerMaps*>(m->wgrad45);
-    VAEB_TRY(make_pair_mn(&w45->a_hi, &w45->a_lo, b.heh, b.hel, rows, H + 1, b.ldh, ga));
-    VAEB_TRY(make_pair_mn(&w45->b_hi, &w45->b_lo, b.ddh, b.ddl, rows, 2 * Z, b.ldq, 1));
+    VAEB_TRY(make_pair_mn(&w45->a_hi, &w45->a_lo, b.heh, b.hel, rows, H + 1, b.ldh, ga, kw));
+    VAEB_TRY(make_pair_mn(&w45->b_hi, &w45->b_lo, b.ddh, b.ddl, rows, 2 * Z, b.ldq, 1, kw));
     // enc2: A = h_e mirror [rows, H] K-major, B = interleaved heads mirror [H, 2Z] MN-major
     LayerMaps* e2 = reinterpret_cast<LayerMaps*>(m->enc2);
     VAEB_TRY(make_pair(&e2->a_hi, &e2->a_lo, b.heh, b.hel, rows, H, b.ldh, BM));
@@ -1288,7 +1302,7 @@ wgrad45_reduce_kernel(const float* __restrict__ scratch, int splits, size_t stri
 cudaError_t tc_wgrad45(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int rows, int H, int Z, float* gW4,
                        float* gb4, float* gW5, float* gb5, float* scratch, TcReduceJobs* defer) {
   const int N = 2 * Z;
-  const int splits = tc_wgrad_splits(H + 1, N, rows, 64);
+  const int splits = tc_wgrad_splits(H + 1, N, rows, 64, ns);
   const size_t stride = (size_t)(H + 1) * N;
   EpiWgradTc epi{nullptr, nullptr, H, N, scratch, stride};      // always through scratch: the reduce also de-interleaves
   ++*launches;
