@@ -314,22 +314,27 @@ extern "C" int vaeb_tc_gemm_probe(int32_t device, int32_t M, int32_t N, int32_t 
 namespace {
 __global__ void __launch_bounds__(128, 1)
 tma_fill_kernel(const __grid_constant__ CUtensorMap map, int rows, int box_rows, int batch, int stages, int passes,
-                unsigned long long* sink) {
+                int producers, unsigned long long* sink) {
   extern __shared__ uint8_t fill_smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)fill_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem0 = (uint8_t*)(((uintptr_t)fill_smem_raw + 1023) & ~(uintptr_t)1023);
   const int box_bytes = box_rows * 128, stage_bytes = batch * box_bytes;
+  // `producers` issuing threads (lane 0 of warps 0..producers-1), each with its own ring and barriers
+  const int w = threadIdx.x >> 5;
+  const size_t ring_bytes = ((size_t)stages * stage_bytes + stages * 8 + 1023) & ~(size_t)1023;
+  uint8_t* smem = smem0 + (size_t)w * ring_bytes;
   uint64_t* full = (uint64_t*)(smem + (size_t)stages * stage_bytes);
-  if (threadIdx.x == 0) {
+  const bool issuer = (threadIdx.x & 31) == 0 && w < producers;
+  if (issuer) {
     tc::tma_prefetch_desc(&map);
     for (int s = 0; s < stages; ++s) tc::mbar_init(&full[s], 1);
     tc::fence_barrier_init();
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (issuer) {
     const int boxes = rows / box_rows;
-    const long long total = (long long)(boxes / batch) * passes;       // stages issued in all
+    const long long total = (long long)(boxes / batch) * passes / producers;       // stages issued by this thread
     long long issued = 0, done = 0;
-    const int start = (int)((blockIdx.x * 7) % boxes);                 // CTAs start at different rows
+    const int start = (int)((blockIdx.x * 7 + w * 13) % boxes);                     // start at different rows
     auto issue = [&](long long it) {
       const int s = (int)(it % stages);
       tc::mbar_expect_tx(&full[s], stage_bytes);
@@ -349,10 +354,12 @@ tma_fill_kernel(const __grid_constant__ CUtensorMap map, int rows, int box_rows,
 }  // namespace
 
 extern "C" int vaeb_tma_fill_probe(int32_t device, int32_t rows, int32_t box_rows, int32_t batch, int32_t stages,
-                                   int32_t passes, int32_t ctas, float* gbytes_per_s) {
+                                   int32_t passes, int32_t ctas, int32_t producers, float* gbytes_per_s) {
   VAEB_REQUIRE(gbytes_per_s && rows > 0 && box_rows >= 8 && box_rows <= 256 && batch >= 1 &&
-               rows % (box_rows * batch) == 0 && stages >= 1 && passes >= 1 && ctas >= 1, "bad argument");
-  const size_t smem = (size_t)stages * batch * box_rows * 128 + stages * 8 + 1024 + 64;
+               rows % (box_rows * batch) == 0 && stages >= 1 && passes >= 1 && ctas >= 1 && producers >= 1 && producers <= 4,
+               "bad argument");
+  passes = (passes + producers - 1) / producers * producers;
+  const size_t smem = (((size_t)stages * batch * box_rows * 128 + stages * 8 + 1023) & ~(size_t)1023) * producers + 2048;
   VAEB_REQUIRE(smem <= 227 * 1024, "ring does not fit in shared memory");
   VAEB_CUDA(cudaSetDevice(device));
   void* d = nullptr;
@@ -368,9 +375,9 @@ extern "C" int vaeb_tma_fill_probe(int32_t device, int32_t rows, int32_t box_row
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     if (e == cudaSuccess) {
-      tma_fill_kernel<<<ctas, 128, smem>>>(tm, rows, box_rows, batch, stages, 1, sink);      // warm-up: into L2
+      tma_fill_kernel<<<ctas, 128, smem>>>(tm, rows, box_rows, batch, stages, producers, producers, sink);   // warm-up: into L2
       cudaEventRecord(e0);
-      tma_fill_kernel<<<ctas, 128, smem>>>(tm, rows, box_rows, batch, stages, passes, sink);
+      tma_fill_kernel<<<ctas, 128, smem>>>(tm, rows, box_rows, batch, stages, passes, producers, sink);
       cudaEventRecord(e1);
       e = cudaEventSynchronize(e1);
     }
