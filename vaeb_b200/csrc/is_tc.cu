@@ -25,7 +25,7 @@
 
 namespace istc {
 
-constexpr int BM = 128, BK = 64, NC_MAX = 128, STAGES = 4;
+constexpr int BM = 128, BK = 64, NC_MAX = 160, STAGES = 3;
 constexpr int KB_MAX = 8;                       // hidden units padded to <= 512
 constexpr int ZMAX = 20;                        // latent size; the bias rides along as contraction index Z
 constexpr int ZG = 6;                           // groups of four contraction indices written per z row (24 >= Z + 1)
@@ -36,8 +36,9 @@ constexpr int A_BLOCK = BM * 128;               // bytes of one 64-wide k block 
 constexpr int B_STAGE = NC_MAX * 128;           // one ring stage: up to [128 rows x 64 k] bf16 (W2^T or W1^T box)
 constexpr int TMEM_COLS = 512;
 constexpr int W2T_PAD = 64;                     // W2^T row stride = KP + 64 elements: rows do not alias in L2
-constexpr int ACC_STRIDE = 128;                 // two accumulators of the output sweep: columns [0,128), [128,256)
-constexpr int MINI_COL0 = 256, MINI_BUFS = 4, MINI_N = 64;   // four 64-column accumulators of the hidden-layer GEMM
+constexpr int ACC_STRIDE = 160;                 // two accumulators of the output sweep: columns [0,160), [160,320)
+constexpr int MINI_COL0 = 320, MINI_BUFS = 2, MINI_N = 64;   // two 64-column accumulators of the hidden-layer GEMM
+static_assert(MINI_COL0 + MINI_BUFS * MINI_N <= TMEM_COLS && 2 * ACC_STRIDE <= MINI_COL0 && NC_MAX <= ACC_STRIDE, "TMEM map");
 
 struct Smem {                                   // offsets from a 1024-byte aligned base
   static constexpr int A = 0;                                // h tile, 8 k blocks, UMMA K-major SW128
@@ -185,8 +186,8 @@ __device__ __forceinline__ void walk_chunk(const Params& p, uint32_t ti, int c, 
     for (int kb = 0; kb < p.KB; ++kb) {
       if (kb == 0) {
         for (int j = 0; j < MINI_BUFS && j < p.KB; ++j) r.pass(ti + 1, j);
-      } else if (kb >= 2 && kb + 2 < p.KB) {
-        r.pass(ti + 1, kb + 2);
+      } else if (kb >= 2 && kb + MINI_BUFS - 2 < p.KB) {
+        r.pass(ti + 1, kb + MINI_BUFS - 2);      // its TMEM buffer was read (a_free of pass - MINI_BUFS) two k blocks ago
       }
       r.template w2<FIRST, LAST>(ti, c, kb);
     }
@@ -278,7 +279,7 @@ struct MmaIssuer {
   // and 8 passes per tile keep it there): every descriptor / barrier address is base + constant.
   template <bool FIRST>
   __device__ __forceinline__ bool chunk_static(uint32_t tseq, int) {
-    if (KB != 8 || stage != 0) return false;
+    if (STAGES != 4 || KB != 8 || stage != 0) return false;
 #pragma unroll
     for (int kb = 0; kb < 8; ++kb) {
       constexpr int dummy = 0; (void)dummy;
