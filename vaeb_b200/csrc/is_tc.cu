@@ -275,17 +275,16 @@ struct MmaIssuer {
     advance();
     ++mini_it;
   }
-  // A whole chunk, fully unrolled, for the common case KB == 8 with the ring at stage 0 (8 items per chunk
-  // and 8 passes per tile keep it there): every descriptor / barrier address is base + constant.
-  template <bool FIRST>
-  __device__ __forceinline__ bool chunk_static(uint32_t tseq, int) {
-    if (STAGES != 4 || KB != 8 || stage != 0) return false;
+  // A whole chunk, fully unrolled, for the common case KB == 8: one instantiation per ring position the chunk can
+  // start at, so that every descriptor / barrier address is base + constant.
+  template <bool FIRST, int S0>
+  __device__ __forceinline__ void chunk_unrolled(uint32_t tseq) {
 #pragma unroll
     for (int kb = 0; kb < 8; ++kb) {
       constexpr int dummy = 0; (void)dummy;
-      const uint32_t st = (uint32_t)(kb & (STAGES - 1));
+      const uint32_t st = (uint32_t)((S0 + kb) % STAGES), wrap = (uint32_t)(((S0 + kb) / STAGES) & 1);
       if (FIRST) bar_wait(bar.a_ready + 8u * kb, tseq & 1u);
-      bar_wait(bar.b_full + 8u * st, parity ^ (uint32_t)(kb / STAGES));
+      bar_wait(bar.b_full + 8u * st, parity ^ wrap);
       tc::tc_fence_after();
       const uint32_t a_lo = a_lo0 + (uint32_t)kb * (uint32_t)(A_BLOCK >> 4);
       const uint32_t b_lo = b_lo0 + st * (uint32_t)(B_STAGE >> 4);
@@ -294,7 +293,20 @@ struct MmaIssuer {
         tc::umma_bf16(d_acc, mk64(a_lo + 2u * k, DESC_HI), mk64(b_lo + 2u * k, DESC_HI), idesc, (kb | k) != 0 ? 1u : 0u);
       commit_to(bar.b_empty + 8u * st);
     }
-    return true;                                   // 8 items = two trips round the 4-stage ring: stage, parity unchanged
+    stage = (uint32_t)((S0 + 8) % STAGES);
+    parity ^= (uint32_t)(((S0 + 8) / STAGES) & 1);
+  }
+  template <bool FIRST>
+  __device__ __forceinline__ bool chunk_static(uint32_t tseq, int) {
+    if (KB != 8) return false;
+    static_assert(STAGES >= 2 && STAGES <= 4, "one unrolled chunk per starting stage");
+    switch (stage) {
+      case 0: chunk_unrolled<FIRST, 0>(tseq); break;
+      case 1: chunk_unrolled<FIRST, 1>(tseq); break;
+      case 2: chunk_unrolled<FIRST, 2 % STAGES>(tseq); break;
+      default: chunk_unrolled<FIRST, 3 % STAGES>(tseq); break;
+    }
+    return true;
   }
   template <bool FIRST, bool LAST>
   __device__ __forceinline__ void w2(uint32_t tseq, int, int kb) {
