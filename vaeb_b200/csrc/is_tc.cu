@@ -8,7 +8,7 @@
 //   h = tanh(pre) -> bf16 -> k block of the A tile in shared memory: the decoder hidden layer never
 //       exists in HBM                                                              -- producer warps
 //   a = h.W2 : tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM), W2^T streamed through a TMA
-//       ring of [NC n x 64 k] boxes, output swept in equal chunks of NC <= 128 columns (784 = 7 x 112),
+//       ring of [NC n x 64 k] boxes, output swept in equal chunks of NC <= 160 columns (784 -> 5 x 160),
 //       two TMEM accumulators so the epilogue of chunk c overlaps the MMAs of chunk c+1
 //   log w = sum_d x_d a_d - softplus(a_d) + log p(z) - log q(z|x), per sample; then the tile's
 //       (max, sum exp) pair -> partial[tile]                                       -- epilogue warps
@@ -30,7 +30,7 @@ constexpr int KB_MAX = 8;                       // hidden units padded to <= 512
 constexpr int ZMAX = 20;                        // latent size; the bias rides along as contraction index Z
 constexpr int ZG = 6;                           // groups of four contraction indices written per z row (24 >= Z + 1)
 constexpr int DMAX = 1024;
-constexpr int PROD_WARPS = 8, EPI_WARPS = 8;
+constexpr int PROD_WARPS = 8, EPI_WARPS = 16;     // epilogue: 4 TMEM lane quarters x (EPI_WARPS / 4) column slices
 constexpr int THREADS = (4 + PROD_WARPS + EPI_WARPS) * 32;
 constexpr int A_BLOCK = BM * 128;               // bytes of one 64-wide k block of the A tile
 constexpr int B_STAGE = NC_MAX * 128;           // one ring stage: up to [128 rows x 64 k] bf16 (W2^T or W1^T box)
@@ -47,8 +47,8 @@ struct Smem {                                   // offsets from a 1024-byte alig
   static constexpr int AUXP = ZB + BM * 128;                 // [128][ZG] partial prior/posterior terms
   static constexpr int AUX = AUXP + BM * ZG * 4;             // [3][128]
   static constexpr int XB = AUX + 3 * BM * 4;                // [DMAX] b2[col] then [DMAX] x[col] - 1/2; col >= D: (-30, -1/2)
-  static constexpr int ROWSUM = XB + DMAX * 8;               // [2][128]
-  static constexpr int RED = ROWSUM + 2 * BM * 4;            // [8]
+  static constexpr int ROWSUM = XB + DMAX * 8;               // [EPI_WARPS / 4][128]
+  static constexpr int RED = ROWSUM + (EPI_WARPS / 4) * BM * 4;   // [8]
   static constexpr int BARS = RED + 64;                      // mbarriers
   static constexpr int TOTAL = BARS + 512 + 1024;
 };
@@ -497,7 +497,8 @@ is_tc_kernel(const __grid_constant__ CUtensorMap map_w2, const __grid_constant__
     const int e = warp - 4 - PROD_WARPS, q = warp & 3, ch = e >> 2;   // TMEM lane quarter = warp % 4
     const int et = threadIdx.x - (4 + PROD_WARPS) * 32;                // [0, 256)
     const int row = q * 32 + lane;
-    const int half = p.NC >> 1, n8 = half >> 3, c_lo = ch * half;      // NC is a multiple of 16
+    constexpr int SL = EPI_WARPS / 4;                                  // column slices of a chunk
+    const int half = p.NC / SL, n8 = half >> 3, c_lo = ch * half;      // host: NC is a multiple of 8 * SL
     const uint32_t bb_addr = tc::smem_u32(bb_s), xh_addr = tc::smem_u32(xh_s);
     const FoldConsts fk = fold_consts();
     uint32_t acc_it = 0, tile_it = 0;
@@ -539,7 +540,9 @@ is_tc_kernel(const __grid_constant__ CUtensorMap map_w2, const __grid_constant__
       if (ch == 0) {
         const int l = l0 + row;
         const bool valid = l < p.L;
-        const float lw = rowsum_s[row] + rowsum_s[BM + row] + aux_s[(tile_it % 3) * BM + row];
+        float lw = aux_s[(tile_it % 3) * BM + row];
+#pragma unroll
+        for (int sl = 0; sl < SL; ++sl) lw += rowsum_s[sl * BM + row];
         if (valid && p.logw_out) p.logw_out[(size_t)pi * p.L + l] = lw;
         float m = valid ? lw : -INFINITY;
 #pragma unroll
@@ -624,9 +627,9 @@ int is_tc_run(vaeb_handle* h, const float* d_x, const float* d_mu, const float* 
     VAEB_TRY(vaeb_make_tmap_bf16((CUtensorMap*)s.map_w1, s.w1t, (uint64_t)(KB_MAX * 64), 64, 64, MINI_N));
     VAEB_CUDA(cudaFuncSetAttribute(is_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::TOTAL));
     VAEB_CUDA(cudaDeviceGetAttribute(&s.n_sm, cudaDevAttrMultiProcessorCount, h->cfg.device));
-    // output chunks: as few as fit 128 accumulator columns, equal width (a multiple of 16): 784 = 7 x 112
+    // output chunks: as few as fit NC_MAX accumulator columns, equal width (a multiple of 32): 784 -> 5 x 160
     const int n_chunks = (D + NC_MAX - 1) / NC_MAX;
-    const int nc = (((D + n_chunks - 1) / n_chunks) + 15) & ~15;
+    const int nc = (((D + n_chunks - 1) / n_chunks) + 31) & ~31;      // 8 columns per fold x EPI_WARPS / 4 slices
     s.n_chunks = n_chunks; s.tail_cols = nc;
     VAEB_TRY(vaeb_make_tmap_bf16((CUtensorMap*)s.map_full, s.w2t, (uint64_t)D, (uint64_t)KP, (uint64_t)(KP + W2T_PAD),
                                  (uint32_t)nc));
