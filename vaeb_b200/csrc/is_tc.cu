@@ -224,14 +224,21 @@ struct TmaIssuer {
   uint32_t ring;                 // shared address of the ring
   uint32_t w2_bytes; int NC;
   uint32_t stage = 0, parity = 0;
+  // TWO issuing threads (lane 0 of warps 0 and 3) walk the same item sequence and issue alternate items: an item costs
+  // its thread an mbarrier round trip (~0.3 us) whatever the bytes, and the fill rate scales with the number of
+  // issuing threads (tools/tma_fill_probe.py: 30 / 59 / 118 GB/s per SM for 1 / 2 / 4 threads).
+  uint32_t me = 0, turn = 0;
   __device__ __forceinline__ void load(const CUtensorMap* m, uint32_t bytes, int c0, int c1) {
-    const uint32_t full = bar.b_full + 8u * stage;
-    bar_wait(bar.b_empty + 8u * stage, parity ^ 1u);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(ring + stage * (uint32_t)B_STAGE), "l"(m), "r"(full), "r"(c0), "r"(c1)
-        : "memory");
+    if (turn == me) {
+      const uint32_t full = bar.b_full + 8u * stage;
+      bar_wait(bar.b_empty + 8u * stage, parity ^ 1u);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+          ::"r"(ring + stage * (uint32_t)B_STAGE), "l"(m), "r"(full), "r"(c0), "r"(c1)
+          : "memory");
+    }
+    turn ^= 1u;
     if (++stage == STAGES) { stage = 0; parity ^= 1u; }
   }
   __device__ __forceinline__ void chunk_begin() {}
@@ -382,10 +389,11 @@ is_tc_kernel(const __grid_constant__ CUtensorMap map_w2, const __grid_constant__
   ba.a_ready = tc::smem_u32(a_ready); ba.a_free = tc::smem_u32(a_free);
   ba.acc_full = tc::smem_u32(acc_full); ba.acc_empty = tc::smem_u32(acc_empty);
 
-  if (warp == 0) {
-    // ===== TMA: W1^T boxes of the passes and W2^T boxes of the sweep, in walk_items order =====
+  if (warp == 0 || warp == 3) {
+    // ===== TMA: W1^T boxes of the passes and W2^T boxes of the sweep, in walk_items order (alternate items) =====
     if (elect_one()) {
       TmaIssuer r;
+      r.me = warp == 0 ? 0u : 1u;
       r.map_w2 = &map_w2; r.map_w1 = &map_w1; r.bar = ba;
       r.ring = tc::smem_u32(smem + Smem::B);
       r.w2_bytes = (uint32_t)p.NC * 128u; r.NC = p.NC;
