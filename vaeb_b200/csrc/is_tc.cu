@@ -37,7 +37,7 @@ constexpr int B_STAGE = NC_MAX * 128;           // one ring stage: up to [128 ro
 constexpr int TMEM_COLS = 512;
 constexpr int W2T_PAD = 64;                     // W2^T row stride = KP + 64 elements: rows do not alias in L2
 constexpr int ACC_STRIDE = 160;                 // two accumulators of the output sweep: columns [0,160), [160,320)
-constexpr int MINI_COL0 = 320, MINI_BUFS = 2, MINI_N = 64;   // two 64-column accumulators of the hidden-layer GEMM
+constexpr int MINI_COL0 = 320, MINI_BUFS = 3, MINI_N = 64;   // three 64-column accumulators of the hidden-layer GEMM
 static_assert(MINI_COL0 + MINI_BUFS * MINI_N <= TMEM_COLS && 2 * ACC_STRIDE <= MINI_COL0 && NC_MAX <= ACC_STRIDE, "TMEM map");
 
 struct Smem {                                   // offsets from a 1024-byte aligned base
@@ -268,7 +268,7 @@ struct MmaIssuer {
   }
   __device__ __forceinline__ void pass(uint32_t tseq, int j) {
     if (j == 0) bar_wait(bar.z_full, tseq & 1u);
-    const uint32_t mb = mini_it & (MINI_BUFS - 1);
+    const uint32_t mb = mini_it % MINI_BUFS;
     bar_wait(bar.b_full + 8u * stage, parity);
     bar_wait(bar.mini_empty + 8u * mb, ((mini_it / MINI_BUFS) & 1u) ^ 1u);
     tc::tc_fence_after();
