@@ -142,8 +142,6 @@ int grow_bytes(void** p, size_t bytes) {
   return VAEB_OK;
 }
 
-inline int round8(int v) { return (v + 7) / 8 * 8; }
-
 // Allocate / grow the bf16 mirrors for `R` decoder rows and `rows` encoder rows.
 int tc_ensure(vaeb_handle* h, int64_t rows, int64_t R) {
   TcState& t = h->tc;

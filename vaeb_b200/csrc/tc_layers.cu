@@ -24,8 +24,6 @@ namespace {
 constexpr int BM = 128, BK = 64;
 constexpr int EPI_WARPS = 16, TC_THREADS = 128 + EPI_WARPS * 32;
 
-__device__ __forceinline__ float softplusf_(float a) { return fmaxf(a, 0.f) + log1pf(expf(-fabsf(a))); }
-__device__ __forceinline__ float sigmoidf_(float a) { return 1.0f / (1.0f + expf(-a)); }
 __device__ __forceinline__ void put_split(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t o, float v) {
   const __nv_bfloat16 h = __float2bfloat16_rn(v);
   hi[o] = h;
@@ -145,7 +143,7 @@ struct EpiTanh {            // out[row, col] = tanh(acc + bias[col]) (+ optional
   __nv_bfloat16* mh; __nv_bfloat16* ml; int ldm; int fast;
   __device__ __forceinline__ void begin() {}
   __device__ __forceinline__ void split(int) {}
-  __device__ __forceinline__ bool preload(int, bool, int, int, uint32_t*) const { return false; }
+  __device__ __forceinline__ bool preload(int, bool, int, int, uint32_t*) const { return false; }   // bias only: L1 hits
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v, const uint32_t* = nullptr) {
     if (!ok) return;
     float* o = out ? out + (size_t)row * ld + col0 : nullptr;
@@ -189,14 +187,6 @@ struct EpiBernoulliTc {     // VAEB.py:263,311: term = x*a - softplus(a); da = s
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
     acc += fmaf(xv, a, -fmaf(lg, 0.6931471805599453f, fmaxf(a, 0.f)));
     return scale * (xv - (a >= 0.f ? r : t * r));
-  }
-  // the persistent kernel requests the next chunk's x (hi mirror, one sector) before it finishes the current one
-  __device__ __forceinline__ bool preload(int row, bool ok, int col0, int N, uint32_t* w) const {
-    if (!ok || x || col0 + 16 > N) return false;
-    const __nv_bfloat16* p = xm_hi + (size_t)(xm_off + (row / x_div) % x_mod) * ldxm + col0;
-    if (((uintptr_t)p) & 31u) return false;
-    ld32B(p, w);
-    return true;
   }
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v, const uint32_t* pre = nullptr) {
     if (!ok) return;
@@ -243,14 +233,12 @@ struct EpiBernoulliTc {     // VAEB.py:263,311: term = x*a - softplus(a); da = s
 };
 
 struct EpiWgradTc {         // rows < Hreal -> gW[Hreal, N]; row == Hreal (the ones column of A) -> gb
-  static constexpr bool PREFETCH = false;   // persistent kernel: unrolled epilogue with the next chunk's operand in flight
   float* gW; float* gb; int Hreal; int ld;
   float* scratch; size_t split_stride;   // split-K: slice z writes [gW | gb] at scratch + z * split_stride
   __device__ __forceinline__ void begin() {}
   __device__ __forceinline__ void split(int z) {
     if (scratch) { gW = scratch + (size_t)z * split_stride; gb = gW + (size_t)Hreal * ld; }
   }
-  __device__ __forceinline__ bool preload(int, bool, int, int, uint32_t*) const { return false; }
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v, const uint32_t* = nullptr) {
     if (!ok) return;
     float* dst = (row < Hreal ? gW + (size_t)row * ld : gb) + col0;
@@ -329,7 +317,6 @@ struct EpiHeads {
   float acc;
   __device__ __forceinline__ void begin() { acc = 0.f; }
   __device__ __forceinline__ void split(int) {}
-  __device__ __forceinline__ bool preload(int, bool, int, int, uint32_t*) const { return false; }
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v, const uint32_t* = nullptr) {
     if (!ok) return;
     // one Philox counter yields four draws: elements (row, 4g..4g+3) share one when Z is a multiple of 4
@@ -414,7 +401,6 @@ struct EpiDzPrep {
   float* dmu; float* dls; __nv_bfloat16* dd_hi; __nv_bfloat16* dd_lo; int ldq;
   __device__ __forceinline__ void begin() {}
   __device__ __forceinline__ void split(int) {}
-  __device__ __forceinline__ bool preload(int, bool, int, int, uint32_t*) const { return false; }
   __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v, const uint32_t* = nullptr) {
     if (!ok) return;
     const size_t o0 = (size_t)row * Z + col0;
