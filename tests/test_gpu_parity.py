@@ -402,9 +402,11 @@ def test_train_model_end_to_end(tmp_path, capsys):
     import vaeb_b200
     from vaeb_b200 import io
     trc, mdl = str(tmp_path / "t.trc"), str(tmp_path / "m.mdl")
+    pgm = str(tmp_path / "manifold.pgm")
     args = vaeb_b200.parse_args(["--continuous", "--n_latent", "2", "--n_epochs", "3", "--trace_file", trc,
-                                 "--save_file", mdl, "--synthetic"])
+                                 "--save_file", mdl, "--synthetic", "--manifold_file", pgm])
     model, data = vaeb_b200.train_model(args)
+    assert open(pgm, "rb").read().startswith(b"P5 200 280 255\n")     # 10 x 10 Frey tiles of 20 x 28 (freyFace.py:346-369)
     lines = open(trc).read().splitlines()
     assert lines[0] == "num_samples,L,Lvalid" and len(lines) == 1 + 2 * 3
     assert lines[1] == lines[2] and lines[1].startswith("1500,") and lines[5].startswith("4500,")

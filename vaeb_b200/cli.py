@@ -29,7 +29,8 @@ command_line_args = {'seed': (15485863, int),
                      # --- extensions (defaults keep the reference behaviour) ---
                      'device': (0, int),
                      'precision': ('fp32', str),      # fp32 | bf16
-                     'eps_mode': ('philox', str)}     # philox | theano
+                     'eps_mode': ('philox', str),     # philox | theano
+                     'manifold_file': ('', str)}      # PGM of the learned 2-d manifold (freyFace.py:346-369)
 command_line_flags = ['continuous', 'generic_estimator', 'full_varational',
                       # --- extensions ---
                       'synthetic',        # synthetic data of the dataset's shape if the files are absent
@@ -142,6 +143,13 @@ def train_model(args, data=None):
 
     if len(save_file) > 0:
         model.save(save_file)
+
+    # freyFace.py:346-369 renders the learned manifold after training: the decoder on a 10 x 10 grid of Gaussian
+    # quantiles, tiled into one image (VAEBImage.multipleImages)
+    if len(args.get('manifold_file', '')) > 0:
+        from . import manifold
+        _, tiled = manifold.render(model)
+        manifold.save_pgm(tiled, args['manifold_file'])
 
     return model, data
 
