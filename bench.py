@@ -1,20 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- ELBO-gradient datapoints/s of the AEVB step on synthetic MNIST-shaped data.
 
-Contract (driver): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line from
-rank 0.  Workload at every N is BASELINE.json configs[1] ("c2": VAEB.py discrete MNIST 784-d
-Bernoulli, Nz=20, 500 tanh hidden, M=100, L=1, Adagrad).  A step = one `update()` = forward +
-bound + backward + prior + Adagrad on one minibatch of 100 rows.  M=100 training does not shard
-("replicas only"), so N>1 runs N independent replicas (weak scaling, no data-path
-collective); the data-parallel config (c3, NCCL all-reduce) and the importance-sampling
-estimator (c5) are measured in the same run and reported under "also".
+Contract (driver): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line from rank 0.
 
-  value  device-resident: x_train already in HBM, K updates enqueued through
-         vaeb_update_many (one call, no host sync inside), CUDA events on the launch stream.
-  e2e    the reference-facing call with HOST inputs: every step copies its minibatch from
-         pinned host memory (H2D), runs the update and reads the bound back (D2H), synchronously.
-  --impl reference  the reference's CPU path: it cannot run here (Python 2 + Theano), so this is
-         the numpy restatement in oracle/ (kind "port"), fp32, all BLAS threads of the host.
+HEADLINE (every N; changed in round 2 as VERDICT r1 item 3 asks -- round 1's headline was c2, which is now the
+last entry of "also"): BASELINE.json configs[2] = "c3": MNIST Bernoulli 784-500-20, ONE global minibatch of
+M = 16384 rows per step, split over the N ranks (16384/N rows each), bf16x3 tensor-core precision (bf16 hi+lo
+operands, fp32 accumulation: the fp32 parity tier, 1e-4), NCCL sum all-reduce of the 3.26 MB gradient when N > 1,
+prior once after it, replicated Adagrad.  Total work per step is fixed => "scaling": "strong".
+
+  value  device-resident: the rank's rows already in HBM (several minibatches, > L2 in total, visited in turn),
+         K updates enqueued back to back, CUDA events on the launch stream, max over ranks.
+  e2e    the reference-facing call with HOST inputs: every step copies ITS minibatch share from pinned host memory
+         (H2D) and reads ITS bound back (D2H); streaming form (vaeb_update_host_async + vaeb_collect).
+  roofline  tensor pipe: whole-step algorithmic flops (4,100,000 per datapoint) and the dominant kernel's
+         own flops / its CUDA-event time (vaeb_profile_update), against the measured sustained bf16 peak.
+  --impl reference  the reference's CPU path: it cannot run here (Python 2 + Theano), so this is the numpy fp32
+         restatement in oracle/ (kind "port") on all BLAS threads of the host, same step (M = 16384 rows).
+  also   c3 in plain bf16, c4 (full VB), c1 (Frey), the flat Adagrad pass vs HBM, then c5 (IS log p(x), sharded over
+         the ranks) and c2 (M = 100, the reference's own hot loop; replicas when N > 1) LAST and compact.
 """
 from __future__ import annotations
 
@@ -32,9 +36,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 D, H, Z, M, L = 784, 500, 20, 100, 1
-N_TRAIN = 50000                      # rows resident in HBM: 157 MB > the 126 MB L2
+N_TRAIN = 50000                      # c2: rows resident in HBM: 157 MB > the 126 MB L2
 FLOPS_PER_DATAPOINT = 4100000        # SURVEY.md 8d (fwd 1,628,000 + bwd 2,472,000)
-METRIC = "ELBO-gradient datapoints/sec (AEVB update, MNIST 784-500-20 Bernoulli, M=100, L=1)"
+METRIC = "ELBO-gradient datapoints/sec (AEVB update, MNIST 784-500-20 Bernoulli, global M=16384, L=1)"
 UNIT = "datapoints/s"
 
 
@@ -110,6 +114,13 @@ class ClockSampler(object):
                 "samples": len(sm)}
 
 
+MG = 16384                           # c3: rows of the ONE global minibatch of a step
+C3_PREC = "bf16x3"
+C3_FLOPS_PER_STEP = MG * FLOPS_PER_DATAPOINT            # 67.17 GFLOP
+WORKLOAD = ("c3: MNIST-shape Bernoulli VAE D=784 H=500 Z=20, global minibatch M=16384 rows per step split over the "
+            "ranks, L=1, Adagrad, %s; one step = one update()" % C3_PREC)
+
+
 def make_problem(seed=15485863):
     from vaeb_b200.data import synthetic_mnist
     return synthetic_mnist(N_TRAIN, seed=seed)
@@ -118,22 +129,21 @@ def make_problem(seed=15485863):
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------
-def cpu_step_loop(x, steps, warmup, budget_s=None):
-    """fp32 numpy restatement (oracle/vaeb_oracle.py) of the same update on the same shapes."""
+def cpu_step_loop(x, rows, steps, warmup, budget_s=None, min_steps=2):
+    """fp32 numpy restatement (oracle/vaeb_oracle.py) of the same update() on minibatches of `rows` rows."""
     from oracle import vaeb_oracle as O
-    m = O.OracleVAEB(x, False, H, Z, M, L=L, params=O.init_params(D, H, Z, False), dtype=np.float32)
+    m = O.OracleVAEB(x, False, H, Z, rows, L=L, params=O.init_params(D, H, Z, False), dtype=np.float32)
     rng = np.random.RandomState(10)
-    nb = x.shape[0] // M
-    order = np.random.RandomState(1).permutation(nb)
+    nb = x.shape[0] // rows
     for i in range(warmup):
-        m.update(int(order[i % nb]), rng.normal(size=(L, M, Z)).astype(np.float32))
+        m.update(i % nb, rng.normal(size=(L, rows, Z)).astype(np.float32))
     t0 = time.perf_counter()
     done = 0
     for i in range(steps):
         # eps is drawn on the host inside the step, as the reference does (VAEB.py:42)
-        m.update(int(order[(warmup + i) % nb]), rng.normal(size=(L, M, Z)).astype(np.float32))
+        m.update((warmup + i) % nb, rng.normal(size=(L, rows, Z)).astype(np.float32))
         done += 1
-        if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 20:
+        if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= min_steps:
             break
     dt = time.perf_counter() - t0
     return done, dt
@@ -152,18 +162,27 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    x = make_problem()[:5000]          # the CPU arm cycles through 50 minibatches of the same data
-    done, dt = cpu_step_loop(x, args.steps, args.warmup)
-    val = done * M / dt
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is ONE process that may use every core
+    # of the host whatever N is (the N >= 2 reference numbers ran single-threaded)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+    from vaeb_b200.data import synthetic_mnist
+    x = synthetic_mnist(2 * MG, seed=777)            # two global minibatches, visited in turn
+    # a step of the reference arm is one whole update() on 16384 rows (~0.3-1 s of CPU work); cap the run at ~2 min
+    done, dt = cpu_step_loop(x, MG, args.steps, min(args.warmup, 2), budget_s=120.0)
+    val = done * MG / dt
     cores = blas_threads()
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "c2: MNIST-shape Bernoulli VAE D=784 H=500 Z=20, M=100, L=1, Adagrad; one step = "
-                                   "one update() on 100 rows", "host_cpus": os.cpu_count()},
+            "steps": done, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * dt / done, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "host_cpus": os.cpu_count()},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d update() steps of the numpy fp32 restatement (oracle/vaeb_oracle.py); the "
-                                       "reference itself needs Python 2 + Theano and cannot run here" % done},
+                             "sample": "%d update() steps on 16384 rows each of the numpy fp32 restatement "
+                                       "(oracle/vaeb_oracle.py); the reference itself needs Python 2 + Theano and "
+                                       "cannot run here" % done},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -187,19 +206,10 @@ def run_own(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     import vaeb_b200
-    x = make_problem()
-    model = vaeb_b200.VAEB(x, False, H, Z, M, L, 0.01, False, False, device=local, seed=10 + rank,
-                           precision=args.precision)
+    from vaeb_b200.data import synthetic_mnist, synthetic_frey
+    from vaeb_b200 import distributed as vd
     stream = torch.cuda.current_stream()
-    model.set_stream(stream.cuda_stream)
-    nb = N_TRAIN // M
-    rng = np.random.RandomState(15485863 + rank)
-
-    def order(n):
-        out = []
-        while len(out) < n:
-            out += list(rng.permutation(nb))       # np.random.shuffle(batch_order) per epoch (VAEB.py:574)
-        return np.asarray(out[:n], dtype=np.int32)
+    peaks = measured_peaks()
 
     def barrier():
         torch.cuda.synchronize()
@@ -214,96 +224,6 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    K, W = args.steps, max(args.warmup, 3)
-    # ---- value: device-resident, no host sync inside the timed region -------------------
-    # the first call also sizes the per-launch buffers (batch order, bounds, pinned readback) for K updates: growing
-    # them inside the timed region (cudaFree / cudaMallocHost between the start event and the launch) cost 25-300 ms
-    # in some runs -- the spread of `value` seen earlier in the round
-    model.update_many(order(max(W, K)))
-    # GPU clocks ramp up lazily: keep the device busy for ~1 s before timing (measured: the first 3000
-    # updates after a cold start run 10-70% slower than steady state on this pool's B200s)
-    # Warm-up continues until two consecutive 1000-update probes agree within 3 % (at least 1 s, at most 6 s).
-    # The NVML sampler runs from BEFORE the warm-up to after the timed region and only its samples inside the region
-    # are reported, so that none of its start-up work (nvmlInit, first queries) falls into the region.
-    clocks = ClockSampler(local)
-    clocks.__enter__()
-    t_ramp = time.perf_counter()
-    probe, last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    prev_ms = None
-    while True:
-        probe.record(stream)
-        model.update_many(order(1000))
-        last.record(stream)
-        torch.cuda.synchronize()
-        cur_ms = probe.elapsed_time(last)
-        el = time.perf_counter() - t_ramp
-        if (el >= 1.0 and prev_ms is not None and abs(cur_ms - prev_ms) <= 0.03 * prev_ms) or el >= 6.0:
-            break
-        prev_ms = cur_ms
-    probe_ms_per_step = cur_ms / 1000.0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-    def timed_region():
-        order_k = order(K)
-        barrier()
-        l0 = model.launch_count()
-        t0 = time.perf_counter()
-        e0.record(stream)
-        out = model.update_many(order_k)
-        e1.record(stream)
-        barrier()
-        return max_over_ranks(e0.elapsed_time(e1)), model.launch_count() - l0, out, (t0, time.perf_counter())
-
-    ms, launches, elbos, window = timed_region()
-    remeasured = None
-    if ms / K > 1.3 * probe_ms_per_step:
-        # a one-off stall between the start event and the launch: the K steps are timed once more and BOTH results are
-        # reported -- `value` is the second one
-        remeasured = {"first_ms_per_step": ms / K, "warmup_probe_ms_per_step": probe_ms_per_step}
-        ms, launches, elbos, window = timed_region()
-    clocks.__exit__(None, None, None)
-    clocks_summary = clocks.summary(*window)
-    value = world * K * M / (ms * 1e-3)
-
-    # ---- e2e: host minibatch in, bound out, every step --------------------------------
-    pinned = torch.empty((N_TRAIN, D), dtype=torch.float32, pin_memory=True)
-    pinned.copy_(torch.from_numpy(x))
-    xp = pinned.numpy()
-    Ke = min(K, 2000)
-    oe = order(W + Ke)
-    for b in oe[:W]:
-        model.update_host(xp[b * M:(b + 1) * M])
-    barrier()
-    e0.record(stream)
-    for b in oe[W:]:
-        model.update_host(xp[b * M:(b + 1) * M])
-    e1.record(stream)
-    barrier()
-    ms_e2e_sync = max_over_ranks(e0.elapsed_time(e1))
-    e2e_sync = world * Ke * M / (ms_e2e_sync * 1e-3)
-    # streaming form (the call a host-side data loader makes): every step still copies ITS minibatch
-    # H2D from pinned memory and reads ITS bound back D2H, but the copy of step i+1 overlaps the
-    # kernel of step i and the host only waits in collect()
-    Ka = K
-    oa = order(W + Ka)
-    for b in oa[:W]:
-        model.update_host_async(xp[b * M:(b + 1) * M])
-    model.collect()
-    barrier()
-    e0.record(stream)
-    got = 0
-    for i, b in enumerate(oa[W:]):
-        model.update_host_async(xp[b * M:(b + 1) * M])
-        if (i + 1) % 4096 == 0:
-            got += len(model.collect())
-    got += len(model.collect())
-    e1.record(stream)
-    barrier()
-    assert got == Ka
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    e2e = world * Ka * M / (ms_e2e * 1e-3)
-
-    # ---- also: the two configurations that shard, measured in the same run -------------
     def timed(fn):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -313,59 +233,141 @@ def run_own(args):
         barrier()
         return max_over_ranks(a.elapsed_time(b))
 
+    K, W = args.steps, max(args.warmup, 3)
+    # ================= headline: c3, global M = 16384 split over the ranks ==========================================
+    per = MG // world
+    # resident rows: whole minibatches, > 160 MB in total per rank (the 126 MB L2 cannot hold them), visited in turn
+    nb3 = max(3, -(-160 * 1024 * 1024 // (per * D * 4)))
+    xs = synthetic_mnist(per * nb3, seed=777 + rank)
+    m3 = vaeb_b200.VAEB(xs, False, H, Z, per, 1, 0.01, False, False, device=local, precision=args.precision, seed=10)
+    m3.set_stream(stream.cuda_stream)
+    if world > 1:
+        vd.attach_data_parallel(m3)
+
+    def order3(n, start=0):
+        return (np.arange(start, start + n) % nb3).astype(np.int32)
+
+    m3.update_many(order3(max(W, 3)))                   # also sizes every per-launch buffer
+    # clocks ramp up lazily: keep the device busy until two consecutive probes agree within 3 % (1..6 s)
+    clocks = ClockSampler(local)
+    clocks.__enter__()
+    t_ramp = time.perf_counter()
+    probe, last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prev_ms, n_probe = None, 40
+    while True:
+        probe.record(stream)
+        m3.update_many(order3(n_probe))
+        last.record(stream)
+        torch.cuda.synchronize()
+        cur_ms = probe.elapsed_time(last)
+        el = time.perf_counter() - t_ramp
+        stop = (el >= 1.0 and prev_ms is not None and abs(cur_ms - prev_ms) <= 0.03 * prev_ms) or el >= 6.0
+        if world > 1:                                   # every rank must leave the loop in the same iteration
+            t = torch.tensor([1.0 if stop else 0.0], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            stop = bool(t.item() > 0.5) or el >= 12.0
+        if stop:
+            break
+        prev_ms = cur_ms
+    probe_ms_per_step = cur_ms / n_probe
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    order_k = order3(K, 1)
+    barrier()
+    l0 = m3.launch_count()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    elbos = m3.update_many(order_k)
+    e1.record(stream)
+    barrier()
+    window = (t0, time.perf_counter())
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = m3.launch_count() - l0
+    clocks.__exit__(None, None, None)
+    clocks_summary = clocks.summary(*window)
+    value = K * MG / (ms * 1e-3)
+
+    # ---- e2e: every step copies its minibatch share H2D from pinned host memory and reads its bound back D2H ----
+    pinned = torch.empty((per * nb3, D), dtype=torch.float32, pin_memory=True)
+    pinned.copy_(torch.from_numpy(xs))
+    xp = pinned.numpy()
+    Ke = min(K, 200)
+    for b in order3(W):
+        m3.update_host_async(xp[b * per:(b + 1) * per])
+    m3.collect()
+    barrier()
+    e0.record(stream)
+    got = 0
+    for i, b in enumerate(order3(Ke, 1)):
+        m3.update_host_async(xp[b * per:(b + 1) * per])
+        if (i + 1) % 64 == 0:
+            got += len(m3.collect())
+    got += len(m3.collect())
+    e1.record(stream)
+    barrier()
+    assert got == Ke
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e = Ke * MG / (ms_e2e * 1e-3)
+    # the synchronous call (H2D, update, D2H, host sync every step)
+    Ks = min(K, 50)
+    for b in order3(2):
+        m3.update_host(xp[b * per:(b + 1) * per])
+    barrier()
+    e0.record(stream)
+    for b in order3(Ks, 1):
+        m3.update_host(xp[b * per:(b + 1) * per])
+    e1.record(stream)
+    barrier()
+    ms_sync = max_over_ranks(e0.elapsed_time(e1))
+    e2e_sync = Ks * MG / (ms_sync * 1e-3)
+
+    # ---- roofline: whole step and the dominant kernel (per-kernel CUDA-event times, single GPU only) --------------
+    tf_step = C3_FLOPS_PER_STEP / world / (ms / K * 1e-3) / 1e12          # per GPU
+    peak_tf = peaks["bf16_tflops_sustained"]
+    roofline = {"kernel": "whole c3 step (%d launches per update)" % round(launches / K), "bound": "tensor",
+                "achieved": tf_step, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf_step / peak_tf,
+                "traffic": None, "traffic_note": "per-kernel dram bytes: profiles/r2_c3_ncu_*.txt (ncu --set full)",
+                "peak_source": peaks["source"] + " (sustained cuBLAS bf16, MEASURED_PEAKS.json: kernels timed inside a long step)",
+                "flops_per_step": C3_FLOPS_PER_STEP, "flops_per_datapoint": FLOPS_PER_DATAPOINT,
+                "note": "algorithmic flops (SURVEY 8d); bf16x3 issues three bf16 MMAs per algorithmic product"}
+    if world == 1:
+        try:
+            phases = m3.profile_update(index=1, iters=20)
+            tot = sum(p[1] for p in phases)
+            gemm = [p for p in phases if p[2] > 0]
+            dom = max(gemm, key=lambda p: p[1])
+            dom_tf = dom[2] / (dom[1] * 1e-3) / 1e12
+            roofline.update({"kernel": dom[0] + " (dominant kernel of the step)", "achieved": dom_tf, "frac": dom_tf / peak_tf,
+                             "ms_per_launch": dom[1], "flops_per_launch": dom[2], "share_of_step": dom[1] / tot,
+                             "whole_step": {"achieved": tf_step, "frac": tf_step / peak_tf, "ms": ms / K},
+                             "phases": [{"name": p[0][:40], "us": round(1e3 * p[1], 1), "share": round(p[1] / tot, 3),
+                                         "tflops": round(p[2] / (p[1] * 1e-3) / 1e12, 1) if p[2] else None}
+                                        for p in phases]})
+        except Exception as ex:                          # profiling is evidence, never a reason to lose the line
+            roofline["phases_error"] = str(ex)[:200]
+    m3.close()
+    del pinned, xp, xs
+
+    # ================= also: the other configurations, c5 and c2 last ==============================================
     also = {}
     if not args.no_also:
-        from vaeb_b200.data import synthetic_mnist
-        from vaeb_b200 import distributed as vd
-        peaks_ = measured_peaks()
-        # c3: large-batch data-parallel training, global M = 16384 rows, NCCL sum all-reduce of the gradients
-        MG = 16384
-        per = MG // world
-        for prec in ("bf16x3", "bf16"):
-            xs = synthetic_mnist(per * 3, seed=777 + rank)
-            m3 = vaeb_b200.VAEB(xs, False, H, Z, per, 1, 0.01, False, False, device=local, precision=prec, seed=10)
-            m3.set_stream(stream.cuda_stream)
-            if world > 1:
-                vd.attach_data_parallel(m3)
-            m3.update_many(np.arange(3, dtype=np.int32) % 3)
-            k3 = 30
-            ms3 = timed(lambda: m3.update_many(np.arange(k3, dtype=np.int32) % 3))
-            dps = MG * k3 / (ms3 * 1e-3)
-            tf = dps * FLOPS_PER_DATAPOINT / 1e12
-            also["c3_dp_" + prec] = {
-                "workload": "c3: MNIST Bernoulli 784-500-20, global M=16384 (%d rows/GPU), L=1, Adagrad, NCCL all-reduce "
-                            "of the 3.26 MB gradient" % per,
-                "value": dps, "unit": "datapoints/s", "ms_per_step": ms3 / k3, "steps": k3, "precision": prec,
-                "algorithmic_tflops": tf, "frac_of_bf16_sustained_peak_per_gpu": tf / world / peaks_["bf16_tflops_sustained"]}
-            m3.close()
-        # c5: importance-sampled log p(x), 10,000 test points x L = 5000 samples, points sharded over the ranks.
-        # Tensor-core estimator (is_tc.cu, bf16 operands, 1e-2 tier) on the full configuration; the fp32
-        # estimator (1e-4 tier) on a 1000-point sample.  Host x in, host log p out: the timed region holds the
-        # H2D copy, the fp32 encoder, the fused decoder/log-likelihood/logsumexp kernel and the D2H copy.
-        L5 = 5000
-        for prec, n_pts in (("bf16", 10000), ("fp32", 1000)):
-            xt = synthetic_mnist(n_pts, seed=4242)
-            m5 = vaeb_b200.VAEB(xt[:100], False, H, Z, 100, 1, 0.01, False, False, device=local, seed=10, precision=prec)
-            m5.set_stream(stream.cuda_stream)
-            vd.sharded_log_px(m5, xt, L5, rank, world, gather=False)          # warm-up at the timed size
-            res5 = {}
-            ms5 = timed(lambda: res5.update(lp=vd.sharded_log_px(m5, xt, L5, rank, world, gather=False)))
-            sps = n_pts * L5 / (ms5 * 1e-3)
-            tf5 = sps * 804000 / 1e12
-            also["c5_is_logpx_" + prec] = {
-                "workload": "c5: IS log p(x), %d MNIST-shape points x L=%d, D=784 H=500 Z=20, points sharded over GPUs, "
-                            "host x in / host log p out" % (n_pts, L5),
-                "value": sps, "unit": "samples/s", "ms": ms5, "precision": prec,
-                "algorithmic_tflops": tf5, "flops_per_sample": 804000,
-                "frac_of_bf16_sustained_peak_per_gpu": tf5 / world / peaks_["bf16_tflops_sustained"],
-                "mean_logpx_rank0": float(np.mean(res5["lp"]))}
-            m5.close()
-        # c4: full variational Bayes over the weights (VAEB.py --full_varational, getFVBL), discrete MNIST Nz = 2 / 10,
-        # M = 100: the reference-faithful mode (weights not sampled) and the sampled-weights mode of the
-        # north star (theta = mu + |sigma| zeta per minibatch).  Replica per GPU.
+        # c3 in plain bf16 (1e-2 tier)
+        xs = synthetic_mnist(per * 3, seed=777 + rank)
+        mb = vaeb_b200.VAEB(xs, False, H, Z, per, 1, 0.01, False, False, device=local, precision="bf16", seed=10)
+        mb.set_stream(stream.cuda_stream)
+        if world > 1:
+            vd.attach_data_parallel(mb)
+        mb.update_many(np.arange(6, dtype=np.int32) % 3)
+        kb = 30
+        msb = timed(lambda: mb.update_many(np.arange(kb, dtype=np.int32) % 3))
+        tfb = MG * kb / (msb * 1e-3) * FLOPS_PER_DATAPOINT / 1e12
+        also["c3_bf16"] = {"value": MG * kb / (msb * 1e-3), "unit": UNIT, "ms_per_step": msb / kb,
+                           "frac_bf16_sustained_per_gpu": tfb / world / peak_tf}
+        mb.close()
+        x = make_problem()
+        # c4: full VB (VAEB.py --full_varational, getFVBL), MNIST Nz = 2 / 10, M = 100; replicas when N > 1
         for zz in (2, 10):
             m0 = vaeb_b200.VAEB(x[:200], False, H, zz, M, 1, 0.01, False, False, device=local, seed=10)
-            p0 = m0.get_params()          # the reference initialisation (VAEB.py:50-115) as the MAP start of :117-125
+            p0 = m0.get_params()
             m0.close()
             for sampled in (False, True):
                 m4 = vaeb_b200.VAEB(x[:5000], False, H, zz, M, 1, 0.01, False, True, p0, device=local, seed=10,
@@ -374,90 +376,98 @@ def run_own(args):
                 m4.update_many(np.arange(50, dtype=np.int32) % 50)
                 k4 = 1000
                 ms4 = timed(lambda: m4.update_many(np.arange(k4, dtype=np.int32) % 50))
-                also["c4_fvb_z%d_%s" % (zz, "sampled" if sampled else "faithful")] = {
-                    "workload": "c4: full-VB Bernoulli MNIST 784-500-%d, M=100, L=1, %s" % (
-                        zz, "weights sampled per minibatch" if sampled else "reference-faithful (weights not sampled)"),
-                    "value": world * M * k4 / (ms4 * 1e-3), "unit": "datapoints/s", "ms_per_step": ms4 / k4}
+                also["c4_z%d_%s" % (zz, "sampled" if sampled else "faithful")] = {
+                    "value": world * M * k4 / (ms4 * 1e-3), "unit": UNIT, "us_per_step": 1e3 * ms4 / k4}
                 m4.close()
-        # flat Adagrad pass against the HBM roofline (on a buffer far larger than L2 -- at the real parameter
-        # counts the 3.3 MB buffers never leave L2): a handle with a 40000-unit hidden layer, 65 M parameters, 1.3 GB
-        mo = vaeb_b200.VAEB(x[:200], False, 40000, Z, M, 1, 0.01, False, False, device=local, seed=10)
-        mo.set_stream(stream.cuda_stream)
-        ms_o, by_o = mo.profile_optimizer(iters=50)
-        also["adagrad_flat_stream"] = {
-            "workload": "flat Adagrad + prior over 65.2 M parameters (20 B/parameter, 1.30 GB per launch)",
-            "value": by_o / (ms_o * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_o,
-            "frac_of_measured_hbm_peak": by_o / (ms_o * 1e-3) / 1e9 / peaks_["hbm_gbs"]}
-        mo.close()
-        # c1: the reference's own CPU-runnable case on one GPU
-        from vaeb_b200.data import synthetic_frey
+        # c1: Frey-shape Gaussian decoder 560-200-2, M = 100 (the reference's own CPU-runnable case)
         xf = synthetic_frey()[:1500]
         m1 = vaeb_b200.VAEB(xf, True, 200, 2, 100, 1, 0.01, False, False, device=local, seed=10)
         m1.set_stream(stream.cuda_stream)
         m1.update_many(np.arange(30, dtype=np.int32) % 15)
         k1 = 3000
         ms1 = timed(lambda: m1.update_many(np.arange(k1, dtype=np.int32) % 15))
-        also["c1_frey"] = {"workload": "c1: Frey-shape Gaussian decoder 560-200-2, M=100, L=1 (replica per GPU)",
-                           "value": world * 100 * k1 / (ms1 * 1e-3), "unit": "datapoints/s", "ms_per_step": ms1 / k1}
+        also["c1_frey"] = {"value": world * 100 * k1 / (ms1 * 1e-3), "unit": UNIT, "us_per_step": 1e3 * ms1 / k1}
         m1.close()
+        # flat Adagrad pass against the HBM roofline on a stream-sized buffer (65 M parameters, 1.3 GB per launch)
+        mo = vaeb_b200.VAEB(x[:200], False, 40000, Z, M, 1, 0.01, False, False, device=local, seed=10)
+        mo.set_stream(stream.cuda_stream)
+        ms_o, by_o = mo.profile_optimizer(iters=50)
+        also["adagrad_flat"] = {"value": by_o / (ms_o * 1e-3) / 1e9, "unit": "GB/s",
+                                "frac_hbm": by_o / (ms_o * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        mo.close()
+        # c5: importance-sampled log p(x), 10,000 points x L = 5000, points sharded over the ranks; host x in, host
+        # log p out.  Tensor-core estimator (bf16, 1e-2 tier) at full size; fp32 estimator (1e-4 tier) on 1000 points
+        L5 = 5000
+        for prec, n_pts in (("fp32", 1000), ("bf16", 10000)):
+            xt = synthetic_mnist(n_pts, seed=4242)
+            m5 = vaeb_b200.VAEB(xt[:100], False, H, Z, 100, 1, 0.01, False, False, device=local, seed=10, precision=prec)
+            m5.set_stream(stream.cuda_stream)
+            vd.sharded_log_px(m5, xt, L5, rank, world, gather=False)          # warm-up at the timed size
+            res5 = {}
+            ms5 = timed(lambda: res5.update(lp=vd.sharded_log_px(m5, xt, L5, rank, world, gather=False)))
+            sps = n_pts * L5 / (ms5 * 1e-3)
+            also["c5_is_" + prec] = {"value": sps, "unit": "samples/s", "ms": ms5, "points": n_pts, "L": L5,
+                                     "frac_bf16_sustained_per_gpu": sps * 804000 / 1e12 / world / peak_tf,
+                                     "mean_logpx_rank0": float(np.mean(res5["lp"]))}
+            m5.close()
+        # c2: the reference's own hot loop (BASELINE configs[1]): M = 100, single-launch step kernel; replicas if N > 1
+        m2 = vaeb_b200.VAEB(x, False, H, Z, M, L, 0.01, False, False, device=local, seed=10 + rank)
+        m2.set_stream(stream.cuda_stream)
+        nb = N_TRAIN // M
+        rng = np.random.RandomState(15485863 + rank)
+        k2 = 2000
+        m2.update_many(rng.permutation(nb)[:k2].astype(np.int32))
+        t_r = time.perf_counter()
+        while time.perf_counter() - t_r < 1.0:
+            m2.update_many(rng.permutation(nb).astype(np.int32))
+        o2 = rng.permutation(nb)[:k2].astype(np.int32)
+        ms2 = timed(lambda: m2.update_many(o2))
+        pin2 = torch.empty((N_TRAIN, D), dtype=torch.float32, pin_memory=True)
+        pin2.copy_(torch.from_numpy(x))
+        xp2 = pin2.numpy()
+        for b in o2[:8]:
+            m2.update_host_async(xp2[b * M:(b + 1) * M])
+        m2.collect()
+
+        def stream2():
+            for b in o2:
+                m2.update_host_async(xp2[b * M:(b + 1) * M])
+            m2.collect()
+        ms2e = timed(stream2)
+        n_params = sum(int(np.prod(sh)) for sh in m2._shapes)
+        by2 = 20.0 * n_params + 4.0 * M * D
+        also["c2_m100"] = {"value": world * k2 * M / (ms2 * 1e-3), "unit": UNIT, "us_per_step": 1e3 * ms2 / k2,
+                           "e2e": world * k2 * M / (ms2e * 1e-3), "e2e_us_per_step": 1e3 * ms2e / k2,
+                           "hbm_frac": by2 * k2 / (ms2 * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                           "kernel": m2.step_kernel_name() if hasattr(m2, "step_kernel_name") else "fused_step_kernel"}
+        m2.close()
 
     line = None
     if rank == 0:
-        peaks = measured_peaks()
-        # ---- the dominant kernel: the fused step kernel IS the timed region (one launch = K updates),
-        # so its duration is the CUDA-event time above.  Algorithmic bytes per update:
-        # Adagrad 20 B/parameter + the minibatch 4*M*D.  Per-phase times come from %globaltimer stamps
-        # taken inside the kernel at every grid barrier (CTA 0), averaged over 50 updates.
-        n_params = sum(int(np.prod(sh)) for sh in model._shapes)
-        bytes_per_update = 20.0 * n_params + 4.0 * M * D
-        ach = bytes_per_update * K / (ms * 1e-3) / 1e9
-        phases = model.profile_update(index=3, iters=50)
-        tot = sum(p[1] for p in phases)
-        roofline = {"kernel": "fs::fused_step_kernel (persistent cooperative kernel; one launch = %d updates)" % K,
-                    "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"],
-                    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
-                    # (profiles/r1_fused_step_ncu_full.txt: 24.91 MB for a 50-update launch), scaled to K updates
-                    "traffic": 24.906496e6 / 50.0 * K,
-                    "peak_source": peaks["source"] + " (copy bandwidth, MEASURED_PEAKS.json)",
-                    "ms_per_launch": ms, "bytes_per_launch": bytes_per_update * K,
-                    "bytes_per_update": bytes_per_update, "updates_per_launch": K,
-                    "tflops_whole_step": value / world * FLOPS_PER_DATAPOINT / 1e12,
-                    "note": "M=100 is latency bound, not roofline bound: 8 grid barriers + 0.41 GFLOP of fp32 FFMA "
-                            "per update; parameters/ADA (13 MB) stay L2 resident, so DRAM traffic is far below the "
-                            "algorithmic bytes.  See DESIGN.md and profiles/",
-                    "phases": [{"name": p[0], "us": round(1e3 * p[1], 2), "share": round(p[1] / tot, 3),
-                                "tflops": round(p[2] / (p[1] * 1e-3) / 1e12, 3) if p[2] else None,
-                                "l2_gbs": round(p[3] / (p[1] * 1e-3) / 1e9, 1)} for p in phases]}
-        # ---- CPU baseline on the host cores (bounded sample) -------------------------------
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            done, dt = cpu_step_loop(x[:5000], 100000, 5, budget_s=12.0)
-            cpu = {"value": done * M / dt, "unit": UNIT, "cores": blas_threads(), "kind": "port",
-                   "sample": "%d update() steps (%.1f s) of the numpy fp32 restatement in oracle/" % (done, dt)}
+            xc = synthetic_mnist(2 * MG, seed=777)
+            done, dt = cpu_step_loop(xc, MG, 1000, 1, budget_s=15.0)
+            cpu = {"value": done * MG / dt, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+                   "sample": "%d update() steps on 16384 rows (%.1f s) of the numpy fp32 restatement in oracle/" % (done, dt)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (hi+lo operands, fp32 accumulate)", "bf16": "bf16"}[args.precision],
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (bf16 hi+lo operands, fp32 accumulate: the fp32 parity tier)",
+                          "bf16": "bf16"}[args.precision],
                 "data": "synthetic",
-                "config": {"workload": "c2: MNIST-shape Bernoulli VAE D=784 H=500 Z=20, M=100, L=1, Adagrad; one step "
-                                       "= one update() on 100 rows; N>1 = independent replicas (M=100 does not shard)",
-                           "rows_resident": N_TRAIN,
-                           "l2": "x_train (157 MB) exceeds the 126 MB L2 and minibatches are visited in shuffled "
-                                 "order; the 3.3 MB parameter/ADA/gradient buffers stay L2-resident as in real training",
-                           "eps": "Philox4x32-10 on device", "precision": args.precision},
-                "clocks": clocks_summary,
-                "warmup_probe_ms_per_step": probe_ms_per_step, "remeasured": remeasured,
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": M * D * 4, "d2h_bytes_per_step": 4,
-                        "steps": Ka, "ms_per_step": ms_e2e / Ka,
-                        "api": "VAEB.update_host_async + collect -> vaeb_update_host_async / vaeb_collect (pinned host minibatch "
-                               "per step, H2D on a copy stream overlapping the previous step's kernel, 4-byte D2H of every bound)",
-                        "sync_call": {"value": e2e_sync, "ms_per_step": ms_e2e_sync / Ke, "steps": Ke,
-                                      "api": "VAEB.update_host -> vaeb_update_host (H2D, update, D2H, host sync every step)"}},
+                "config": {"workload": WORKLOAD, "rows_per_gpu": per, "rows_resident_per_gpu": per * nb3,
+                           "l2": "inputs larger than L2: %d minibatches (%.0f MB) resident per GPU, visited in turn"
+                                 % (nb3, per * nb3 * D * 4 / 1e6),
+                           "eps": "Philox4x32-10 on device", "precision": args.precision,
+                           "collective": "ncclAllReduce(sum) of the flat gradient + bound" if world > 1 else "none (1 GPU)"},
+                "clocks": clocks_summary, "warmup_probe_ms_per_step": probe_ms_per_step,
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": per * D * 4 * world, "d2h_bytes_per_step": 4 * world,
+                        "steps": Ke, "ms_per_step": ms_e2e / Ke,
+                        "api": "VAEB.update_host_async + collect (pinned host minibatch per step, H2D on a copy stream "
+                               "overlapping the previous step, 4-byte D2H of every bound)",
+                        "sync_call": {"value": e2e_sync, "ms_per_step": ms_sync / Ks, "steps": Ks}},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "final_bound_per_datapoint": float(np.mean(elbos[-50:])),
-                "flops_per_datapoint": FLOPS_PER_DATAPOINT,
-                "achieved_tflops_whole_step": value / world * FLOPS_PER_DATAPOINT / 1e12, "also": also}
-    model.close()
+                "final_bound_per_datapoint": float(np.mean(elbos[-5:])), "also": also}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -468,12 +478,12 @@ def run_own(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-also", action="store_true", help="skip the c1/c3/c5 side measurements")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--no-also", action="store_true", help="skip the side measurements (c1, c2, c4, c5, Adagrad)")
+    ap.add_argument("--precision", default=C3_PREC, choices=["fp32", "bf16x3", "bf16"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -99,7 +99,11 @@ int vaeb_tensor_shape(vaeb_handle* h, int32_t i, int32_t* rows, int32_t* cols);
 int vaeb_set_tensors(vaeb_handle* h, int32_t which, const float* const* tensors);
 int vaeb_get_tensors(vaeb_handle* h, int32_t which, float* const* tensors);
 /* Device address of a flat buffer (`which` as above) for zero-copy plumbing (e.g. wrapping as
- * a tensor for torch.distributed). */
+ * a tensor for torch.distributed).  LIFETIME: the PARAMETER buffer (which = 0) is double-buffered by the
+ * single-launch step kernels (they read theta_t from one copy while writing theta_{t+1} into the other), so its
+ * address is valid only until the next vaeb_update* / vaeb_collect call on the handle: RE-QUERY it after every
+ * update and never cache it across updates (tests/test_gpu_parity.py::test_device_buffer_tracks_updates).  The
+ * accumulator and gradient buffers keep their addresses for the life of the handle. */
 int vaeb_device_buffer(vaeb_handle* h, int32_t which, void** d_ptr, int64_t* n_elements);
 
 /* ---- AE baselines: ConstructAE of degenerate-vae/ae.py:41-117 and vanilla-ae/ae.py:45-104,
@@ -144,9 +148,15 @@ int vaeb_update_host(vaeb_handle* h, const float* x, int64_t rows, const float* 
  * ends.  The caller must not modify x until vaeb_collect returns.  Philox eps only. */
 int vaeb_update_host_async(vaeb_handle* h, const float* x, int64_t rows);
 
+/* Page-locked host memory for vaeb_update_host_async (plain cudaMallocHost / cudaFreeHost, so that a host
+ * without torch can feed the streaming path).  vaeb_update_host_async returns VAEB_EINVAL for pageable memory:
+ * such a copy would be staged synchronously by the driver and the overlap would be lost without any sign. */
+int vaeb_host_alloc(int64_t bytes, void** out);
+int vaeb_host_free(void* p);
+
 /* Waits for every update enqueued by vaeb_update_host_async since the last collect and writes their
  * SGVB/M values, in submission order, to elbo_out[0..n) where n = *n_inout on return
- * (*n_inout on entry = capacity of elbo_out; VAEB_EARG if smaller than the number outstanding). */
+ * (*n_inout on entry = capacity of elbo_out; VAEB_EINVAL if smaller than the number outstanding). */
 int vaeb_collect(vaeb_handle* h, int32_t* n_inout, float* elbo_out);
 
 /* The inner loop of train_model (VAEB.py:577-579) as ONE call: `n` updates in the order

@@ -40,3 +40,40 @@ def test_render_needs_two_latent_dimensions(tmp_path):
     manifold.save_pgm(tiled, str(tmp_path / "m.pgm"))
     raw = open(tmp_path / "m.pgm", "rb").read()
     assert raw.startswith(b"P5 56 56 255\n") and len(raw) == len(b"P5 56 56 255\n") + 56 * 56
+
+
+def test_save_image_orientation_and_inversion(tmp_path):
+    """VAEBImage.save_image (VAEBImage.py:13-21): (1 - x)*255, MNIST rows in C order, Frey rows in F order rotated
+    by -90 degrees; PGM without PIL, JPG through PIL like the reference."""
+    import numpy as np
+    from vaeb_b200 import manifold
+    x = np.zeros(784, np.float32); x[3] = 1.0                  # pixel (row 0, col 3)
+    a = manifold.save_image(x, str(tmp_path / "m.pgm"))
+    assert a.shape == (28, 28) and a[0, 3] == 0 and a[0, 0] == 255
+    raw = open(tmp_path / "m.pgm", "rb").read()
+    assert raw.startswith(b"P5 28 28 255\n") and len(raw) == len(b"P5 28 28 255\n") + 784
+    f = np.zeros(560, np.float32); f[1] = 1.0                  # F order: (row 1, col 0) of the 20 x 28 array
+    b = manifold.save_image(f, str(tmp_path / "f.pgm"))
+    assert b.shape == (28, 20) and (b == 0).sum() == 1
+    try:
+        import PIL  # noqa: F401
+    except ImportError:
+        return
+    manifold.save_image(x, str(tmp_path / "m.jpg"))
+    from PIL import Image
+    assert Image.open(tmp_path / "m.jpg").size == (28, 28)
+
+
+def test_reconstruction_mse_host_logic():
+    """reconstruction.MSE = mean_i ||reconstruct(x_i) - x_i||^2 (reconstruction.py:9-18) -- host arithmetic only."""
+    import numpy as np
+    from vaeb_b200 import reconstruction as R
+
+    class Fake(object):
+        input_size, n_latent, continuous = 6, 2, False
+
+        def reconstruct(self, x, n, eps=None):
+            return x + 0.5
+
+    x = np.arange(18, dtype=np.float32).reshape(3, 6)
+    assert R.MSE(Fake(), x, 0) == 6 * 0.25

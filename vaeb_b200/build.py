@@ -21,43 +21,50 @@ def _sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _stamp():
+def _header_hash():
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(HERE, "..", "include")):
         for f in sorted(os.listdir(root)):
             p = os.path.join(root, f)
-            if os.path.isfile(p) and f.endswith((".cu", ".cuh", ".h")):
+            if os.path.isfile(p) and f.endswith((".cuh", ".h")):
                 h.update(f.encode())
                 h.update(open(p, "rb").read())
     h.update(" ".join(FLAGS).encode())
     return h.hexdigest()
 
 
-def _compile(src):
+def _src_stamp(src, hh):
+    return hashlib.sha256(open(src, "rb").read() + hh.encode()).hexdigest()
+
+
+def _compile(job):
+    src, hh, force = job
     obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+    stamp = _src_stamp(src, hh)
+    if not force and os.path.exists(obj) and os.path.exists(obj + ".stamp") and open(obj + ".stamp").read() == stamp:
+        return obj, False                      # this translation unit and every header are unchanged
     r = subprocess.run([NVCC, *FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(obj + ".log", "w") as f:
         f.write(log)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s" % (src, log))
-    return obj
+    with open(obj + ".stamp", "w") as f:
+        f.write(stamp)
+    return obj, True
 
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    stamp_file = os.path.join(OBJ, "stamp")
-    stamp = _stamp()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
-        return LIB
     srcs = _sources()
+    hh = _header_hash()
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        objs = list(ex.map(_compile, srcs))
-    r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-ldl"], capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
-    with open(stamp_file, "w") as f:
-        f.write(stamp)
+        res = list(ex.map(_compile, [(s, hh, force) for s in srcs]))
+    objs = [o for o, _ in res]
+    if any(c for _, c in res) or not os.path.exists(LIB):
+        r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-ldl"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     if verbose:
         for o in objs:
             sys.stdout.write(open(o + ".log").read())

@@ -3,7 +3,6 @@
 `full_varational` spelling), defaults, printed blocks, `.trc` layout and `.mdl` layout."""
 from __future__ import annotations
 
-import copy
 import sys
 import time
 
@@ -13,8 +12,7 @@ from . import io
 from .data import load_frey, load_mnist
 from .model import VAEB
 
-#   to add another command line argument, add its name as a key and a tuple of its default
-#   value and type (VAEB.py:22-36)
+# name -> (default, type): the dictionary-driven CLI of VAEB.py:22-38; a new option is one more entry here
 command_line_args = {'seed': (15485863, int),
                      'n_latent': (10, int),
                      'n_epochs': (2000, int),
@@ -37,109 +35,101 @@ command_line_flags = ['continuous', 'generic_estimator', 'full_varational',
                       'sample_weights']   # full-VB with sampled weights (VAEB.py:127-129 live)
 
 
+def _pop_option(tokens, name, n_values):
+    """Removes the first `--name` from `tokens` together with its `n_values` values; returns the values (a list)
+    or None when the option is absent.  The reference's parser (VAEB.py:471-489) behaves the same way: first
+    occurrence wins, later duplicates stay behind and end up in the 'unused' report."""
+    key = "--" + name
+    try:
+        at = tokens.index(key)
+    except ValueError:
+        return None
+    values = tokens[at + 1:at + 1 + n_values]
+    if len(values) < n_values:                       # `--key` as the last token: the reference raises IndexError here
+        raise IndexError("missing value for %s" % key)
+    tokens[at:at + 1 + n_values] = []
+    return values
+
+
 def get_arg(arg, args, default, type_):
-    arg = '--' + arg
-    if arg in args:
-        index = args.index(arg)
-        value = args[args.index(arg) + 1]
-        del args[index]     # remove arg-name
-        del args[index]     # remove value
-        return type_(value)
-    else:
-        return default
+    """`--arg value` cast with the dictionary's type, else the default (VAEB.py:471-480)."""
+    found = _pop_option(args, arg, 1)
+    return default if found is None else type_(found[0])
 
 
 def get_flag(flag, args):
-    flag = '--' + flag
-    have_flag = flag in args
-    if have_flag:
-        args.remove(flag)
-    return have_flag
+    """True iff `--flag` was given (VAEB.py:483-489)."""
+    return _pop_option(args, flag, 0) is not None
 
 
 def parse_args(argv=None):
-    args = copy.deepcopy(sys.argv[1:] if argv is None else list(argv))
-    arg_dict = {}
-    for (arg_name, arg_args) in command_line_args.items():
-        (arg_default_val, arg_type) = arg_args
-        arg_dict[arg_name] = get_arg(arg_name, args, arg_default_val, arg_type)
-    for flag_name in command_line_flags:
-        arg_dict[flag_name] = get_flag(flag_name, args)
-    if len(args) > 0:
-        print('Have unused args: {0}'.format(args))
-    return arg_dict
+    """VAEB.py:491-504: every key of the two dictionaries ends up in the result; what is left over is reported."""
+    tokens = list(sys.argv[1:] if argv is None else argv)
+    parsed = {name: get_arg(name, tokens, default, cast) for name, (default, cast) in command_line_args.items()}
+    parsed.update((name, get_flag(name, tokens)) for name in command_line_flags)
+    if tokens:
+        print('Have unused args: {0}'.format(tokens))
+    return parsed
 
 
 def print_args(args):
-    print('Parameters used:')
-    print('--------------------------------------')
-    for (k, v) in args.items():
-        print('\t{0}: {1}'.format(k, v))
-    print('--------------------------------------')
+    """VAEB.py:507-512."""
+    rule = '-' * 38
+    body = ['\t{0}: {1}'.format(key, args[key]) for key in args]
+    print('\n'.join(['Parameters used:', rule] + body + [rule]))
+
+
+def _default_hidden(continuous, hidden_unit):
+    # VAEB.py:542-543,551-552: 200 units for Frey Face, 500 for MNIST unless --hidden_unit says otherwise
+    return hidden_unit if hidden_unit >= 0 else (200 if continuous else 500)
 
 
 def train_model(args, data=None):
-    """VAEB.py:524-598."""
+    """The training driver of VAEB.py:524-598: seed numpy's global RNG (it only drives the shuffle), load the
+    dataset of the chosen mode, build the model (on top of --vb_param_file for full VB), then per epoch: shuffle
+    the minibatch order, update on every minibatch, validate, write the trace line (twice, as the reference does)
+    and print the two progress lines; finally save."""
     np.random.seed(args['seed'])
-    n_latent = args['n_latent']
-    n_epochs = args['n_epochs']
     continuous = args['continuous']
-    batch_size = args['batch_size']
-    L = args['L']
-    hidden_unit = args['hidden_unit']
-    learning_rate = args['learning_rate']
-    trace_file = args['trace_file']
-    generic_estimator = args['generic_estimator']
-    full_varational = args['full_varational']
-    save_file = args['save_file']
-    vb_param_file = args['vb_param_file']
+    synthetic = args.get('synthetic', False)
     ext = dict(device=args.get('device', 0), precision=args.get('precision', 'fp32'),
                eps_mode=args.get('eps_mode', 'philox'))
+    trace_file, save_file = args['trace_file'], args['save_file']
 
     print("loading data")
-    if continuous:
-        if hidden_unit < 0:
-            hidden_unit = 200
-        if data is None:
-            data = load_frey(synthetic=args.get('synthetic', False))
-    else:
-        if hidden_unit < 0:
-            hidden_unit = 500
-        if data is None:
-            data = load_mnist(synthetic=args.get('synthetic', False))
+    if data is None:
+        data = load_frey(synthetic=synthetic) if continuous else load_mnist(synthetic=synthetic)
     x_train, x_valid = data[0], data[1]
 
     print("creating the model")
-    if full_varational:
-        model, tmp = VAEB.load(vb_param_file, data=data, **ext)
-        params = model.get_params()
-        model.close()
-    else:
-        params = None
-
-    model = VAEB(x_train, continuous, hidden_unit, n_latent, batch_size, L, learning_rate, generic_estimator,
-                 full_varational, params, sample_weights=args.get('sample_weights', False), **ext)
+    params = None
+    if args['full_varational']:                        # VAEB.py:559-561: the MAP solution seeds the variational means
+        seed_model, _ = VAEB.load(args['vb_param_file'], data=data, **ext)
+        params = seed_model.get_params()
+        seed_model.close()
+    model = VAEB(x_train, continuous, _default_hidden(continuous, args['hidden_unit']), args['n_latent'],
+                 args['batch_size'], args['L'], args['learning_rate'], args['generic_estimator'],
+                 args['full_varational'], params, sample_weights=args.get('sample_weights', False), **ext)
 
     print("learning")
-    if len(trace_file) > 0:
+    tracing = len(trace_file) > 0
+    if tracing:
         io.trace_header(trace_file)
-    batch_order = np.arange(int(model.N / model.batch_size))  # ordering of the batches
-    for epoch in range(n_epochs):
-        start = time.time()
+    batch_order = np.arange(model.N // model.batch_size)           # the remainder rows are never visited (:571)
+    for epoch in range(args['n_epochs']):
+        t_epoch = time.time()
         np.random.shuffle(batch_order)
-        # the reference loops `LB += model.update(batch)` (VAEB.py:577-579); update_many runs
-        # the same updates in the same order without a host round-trip per minibatch
-        LB = float(np.sum(model.update_many(batch_order), dtype=np.float64))
-        LB /= len(batch_order)
+        # the reference accumulates `model.update(batch)` over the order (VAEB.py:577-579); update_many performs
+        # the same updates in the same order without a host round trip per minibatch
+        LB = float(np.sum(model.update_many(batch_order), dtype=np.float64)) / len(batch_order)
         LBvalidation = float(model.validate(x_valid)) / x_valid.shape[0]
-        if len(trace_file) > 0:
-            io.trace_line(trace_file, model.N * (epoch + 1), LB, LBvalidation)
-
-        print("Epoch %s : [Lower bound: %s, time: %s]" % (epoch, io.py2_float(LB), time.time() - start))
+        seen = model.N * (epoch + 1)
+        if tracing:
+            io.trace_line(trace_file, seen, LB, LBvalidation)
+        print("Epoch %s : [Lower bound: %s, time: %s]" % (epoch, io.py2_float(LB), time.time() - t_epoch))
         print("          [Lower bound on validation set: %s]" % io.py2_float(LBvalidation))
-
-        if len(trace_file) > 0:   # the reference writes every line twice (VAEB.py:591-593)
-            io.trace_line(trace_file, model.N * (epoch + 1), LB, LBvalidation)
+        if tracing:                                                # every line appears twice (VAEB.py:591-593)
+            io.trace_line(trace_file, seen, LB, LBvalidation)
 
     if len(save_file) > 0:
         model.save(save_file)

@@ -563,6 +563,30 @@ int load_nccl(NcclApi& api, const char* path) {
 
 extern "C" {
 
+// Backup of params + accumulators around the profiling entry points: restored and freed on EVERY exit path
+struct StateBackup {
+  vaeb_handle* h; size_t nb; float* bp = nullptr; float* ba = nullptr; uint32_t step0; int64_t launches0;
+  StateBackup(vaeb_handle* hh, size_t n) : h(hh), nb(n), step0(hh->step), launches0(hh->launches) {}
+  cudaError_t take() {
+    cudaError_t e = cudaMalloc((void**)&bp, nb);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ba, nb);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bp, h->d_params, nb, cudaMemcpyDeviceToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ba, h->d_ada, nb, cudaMemcpyDeviceToDevice, h->stream);
+    return e;
+  }
+  ~StateBackup() {
+    h->step = step0;
+    h->launches = launches0;
+    if (bp && ba) {
+      cudaMemcpyAsync(h->d_params, bp, nb, cudaMemcpyDeviceToDevice, h->stream);
+      cudaMemcpyAsync(h->d_ada, ba, nb, cudaMemcpyDeviceToDevice, h->stream);
+      cudaStreamSynchronize(h->stream);
+    }
+    if (bp) cudaFree(bp);
+    if (ba) cudaFree(ba);
+  }
+};
+
 static int async_flush(vaeb_handle* h);   // launches streaming updates that were copied but not yet started
 
 const char* vaeb_last_error(void) { return g_last_error.c_str(); }
@@ -797,6 +821,7 @@ int vaeb_update_host(vaeb_handle* h, const float* x, int64_t rows, const float* 
 }
 
 int vaeb_ae_train(vaeb_handle* h, int32_t kind, const int32_t* idx, int32_t n, float* out) {
+  if (h && h->a_pending) VAEB_TRY(async_flush(h));
   VAEB_REQUIRE(h && idx && out && n > 0, "null argument");
   VAEB_REQUIRE(kind == VAEB_AE_DEGENERATE || kind == VAEB_AE_VANILLA, "unknown AE kind");
   VAEB_REQUIRE(!(kind == VAEB_AE_VANILLA && h->cont), "the vanilla AE has sigmoid outputs only (vanilla-ae/ae.py:62-67)");
@@ -858,6 +883,7 @@ int vaeb_ae_train(vaeb_handle* h, int32_t kind, const int32_t* idx, int32_t n, f
 }
 
 int vaeb_ae_forward(vaeb_handle* h, int32_t kind, int32_t what, const float* in, int64_t rows, float* out) {
+  if (h && h->a_pending) VAEB_TRY(async_flush(h));
   VAEB_REQUIRE(h && in && out && rows > 0, "null argument");
   VAEB_REQUIRE(kind == VAEB_AE_DEGENERATE || kind == VAEB_AE_VANILLA, "unknown AE kind");
   VAEB_REQUIRE(what >= 0 && what <= 2, "what: 0 reconstruct, 1 encode, 2 decode");
@@ -889,6 +915,7 @@ int vaeb_ae_forward(vaeb_handle* h, int32_t kind, int32_t what, const float* in,
 }
 
 int vaeb_set_optimizer(vaeb_handle* h, int32_t optimizer, float rho) {
+  if (h && h->a_pending) VAEB_TRY(async_flush(h));
   VAEB_REQUIRE(h, "null handle");
   VAEB_REQUIRE(optimizer == VAEB_OPT_ADAGRAD || optimizer == VAEB_OPT_ADADELTA, "unknown optimizer");
   VAEB_REQUIRE(optimizer == VAEB_OPT_ADAGRAD || !is_fvb(h), "AdaDelta is not wired to the full-VB estimators");
@@ -932,8 +959,16 @@ static int async_flush(vaeb_handle* h) {
 
 int vaeb_update_host_async(vaeb_handle* h, const float* x, int64_t rows) {
   VAEB_REQUIRE(h && x && rows > 0, "null argument");
-  VAEB_REQUIRE(h->world == 1, "the streaming update is single-GPU (use vaeb_update for data-parallel steps)");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  {
+    // pageable memory would turn the copy into a staged, synchronous one and serialise the pipeline silently
+    cudaPointerAttributes pa{};
+    const cudaError_t pe = cudaPointerGetAttributes(&pa, x);
+    if (pe != cudaSuccess) (void)cudaGetLastError();
+    VAEB_REQUIRE(pe == cudaSuccess && (pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged),
+                 "vaeb_update_host_async needs PINNED host memory (cudaHostAlloc / cudaHostRegister / "
+                 "torch pin_memory); use vaeb_update_host for pageable buffers");
+  }
   constexpr int NB = vaeb_handle::ASYNC_BUFS, GROUP = vaeb_handle::ASYNC_GROUP;
   constexpr int MAX_OUT = 8192;
   const int64_t n = rows * h->D;
@@ -1049,6 +1084,7 @@ int vaeb_gradients(vaeb_handle* h, const float* x, int64_t rows, int64_t index, 
 }
 
 int vaeb_apply_update(vaeb_handle* h) {
+  if (h && h->a_pending) VAEB_TRY(async_flush(h));
   VAEB_REQUIRE(h, "null handle");
   VAEB_REQUIRE(!is_fvb(h), "vaeb_apply_update: use vaeb_update for the full-VB estimators");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
@@ -1100,6 +1136,7 @@ int vaeb_validate(vaeb_handle* h, const float* x, int64_t n, const float* eps, f
 
 int vaeb_is_logpx(vaeb_handle* h, const float* x, int64_t n, int32_t L, const float* eps, int64_t row_offset,
                   float* logpx_out, float* logw_out) {
+  if (h && h->a_pending) VAEB_TRY(async_flush(h));
   VAEB_REQUIRE(h && x && logpx_out && n > 0 && L > 0, "null argument");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
   const Layout& l = h->lay;
@@ -1212,6 +1249,7 @@ int vaeb_is_logpx(vaeb_handle* h, const float* x, int64_t n, int32_t L, const fl
 
 int vaeb_reconstruct(vaeb_handle* h, const float* x, int64_t n, int32_t n_samples, const float* eps, float* y_out,
                      float* lv_out) {
+  if (h && h->a_pending) VAEB_TRY(async_flush(h));
   VAEB_REQUIRE(h && x && y_out && n > 0, "null argument");
   VAEB_REQUIRE(!h->cont || lv_out, "the Gaussian decoder also returns its log-variance output");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
@@ -1386,13 +1424,8 @@ int vaeb_profile_update(vaeb_handle* h, int64_t index, int32_t iters, int32_t ma
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
   // the repeated Adagrad launches must not disturb the model: back params/ADA up
   const size_t nb = (size_t)(h->lay.padded + 4) * sizeof(float);
-  float *bp = nullptr, *ba = nullptr;
-  VAEB_CUDA(cudaMalloc((void**)&bp, nb));
-  VAEB_CUDA(cudaMalloc((void**)&ba, nb));
-  VAEB_CUDA(cudaMemcpyAsync(bp, h->d_params, nb, cudaMemcpyDeviceToDevice, h->stream));
-  VAEB_CUDA(cudaMemcpyAsync(ba, h->d_ada, nb, cudaMemcpyDeviceToDevice, h->stream));
-  const uint32_t step0 = h->step;
-  const int64_t launches0 = h->launches;
+  StateBackup backup(h, nb);              // restores params / ADA / step / launch count on every exit path
+  VAEB_CUDA(backup.take());
   int rc = VAEB_OK;
   int n = 0;
   if (fused_step_supported(h, h->M)) {
@@ -1467,12 +1500,6 @@ int vaeb_profile_update(vaeb_handle* h, int64_t index, int32_t iters, int32_t ma
       names[48 * i + 47] = 0;
     }
   }
-  h->step = step0;
-  h->launches = launches0;
-  cudaMemcpyAsync(h->d_params, bp, nb, cudaMemcpyDeviceToDevice, h->stream);
-  cudaMemcpyAsync(h->d_ada, ba, nb, cudaMemcpyDeviceToDevice, h->stream);
-  cudaStreamSynchronize(h->stream);
-  cudaFree(bp); cudaFree(ba);
   if (rc != VAEB_OK) return rc;
   *n_phases = n;
   return VAEB_OK;
@@ -1485,17 +1512,13 @@ int vaeb_profile_optimizer(vaeb_handle* h, int32_t iters, int32_t variant, float
   VAEB_REQUIRE(variant == 0 || variant == 1 || variant == 2 || variant == 4, "variant must be 0, 1, 2 or 4");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
   const size_t nb = (size_t)(h->lay.padded + 4) * sizeof(float);
-  float *bp = nullptr, *ba = nullptr;
-  VAEB_CUDA(cudaMalloc((void**)&bp, nb));
-  VAEB_CUDA(cudaMalloc((void**)&ba, nb));
-  VAEB_CUDA(cudaMemcpyAsync(bp, h->d_params, nb, cudaMemcpyDeviceToDevice, h->stream));
-  VAEB_CUDA(cudaMemcpyAsync(ba, h->d_ada, nb, cudaMemcpyDeviceToDevice, h->stream));
-  cudaEvent_t e0, e1;
+  StateBackup backup(h, nb);
+  VAEB_CUDA(backup.take());
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
   VAEB_CUDA(cudaEventCreate(&e0));
-  VAEB_CUDA(cudaEventCreate(&e1));
-  const int64_t launches0 = h->launches;
+  if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); VAEB_CUDA(cudaErrorUnknown); }
   const bool fb = h->cfg.variant == VAEB_VARIANT_FULLBAYES;
-  g_adagrad_unroll = variant;
+  g_adagrad_unroll = variant;          // thread_local: the switch belongs to this call
   cudaError_t ce = cudaSuccess;
   for (int i = -2; i < iters && ce == cudaSuccess; ++i) {          // two untimed launches first
     if (i == 0) ce = cudaEventRecord(e0, h->stream);
@@ -1510,14 +1533,20 @@ int vaeb_profile_optimizer(vaeb_handle* h, int32_t iters, int32_t variant, float
   float ms = 0.f;
   if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  h->launches = launches0;
-  cudaMemcpyAsync(h->d_params, bp, nb, cudaMemcpyDeviceToDevice, h->stream);
-  cudaMemcpyAsync(h->d_ada, ba, nb, cudaMemcpyDeviceToDevice, h->stream);
-  cudaStreamSynchronize(h->stream);
-  cudaFree(bp); cudaFree(ba);
   VAEB_CUDA(ce);
   *ms_per_launch = ms / (float)iters;
   *bytes_per_launch = 20.0 * (double)h->lay.total;                 // read p, acc, g; write p, acc
+  return VAEB_OK;
+}
+
+int vaeb_host_alloc(int64_t bytes, void** out) {
+  VAEB_REQUIRE(out && bytes > 0, "null argument");
+  VAEB_CUDA(cudaMallocHost(out, (size_t)bytes));
+  return VAEB_OK;
+}
+
+int vaeb_host_free(void* p) {
+  if (p) VAEB_CUDA(cudaFreeHost(p));
   return VAEB_OK;
 }
 

@@ -538,7 +538,7 @@ cudaError_t launch_adadelta(cudaStream_t st, int64_t* launches, float* p, float*
   return LAUNCHED();
 }
 
-int g_adagrad_unroll = 0;   // measurement switch (vaeb_profile_optimizer): 0/1 production, 2 = streaming cache hints, 4 = + two float4 per thread
+thread_local int g_adagrad_unroll = 0;   // measurement switch (vaeb_profile_optimizer): 0/1 production, 2 = streaming cache hints, 4 = + two float4 per thread
 
 cudaError_t launch_adagrad(cudaStream_t st, int64_t* launches, float* p, float* acc, const float* g, int64_t n4,
                            float lr, float eps, float prior, float p2, const float* base, float mult, float div,

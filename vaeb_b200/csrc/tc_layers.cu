@@ -616,7 +616,7 @@ tc_layer_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int M, int N, i
   if (warp == 2) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-bool g_pdl = false;
+thread_local bool g_pdl = false;   // set and read within one forward_backward call of one thread
 
 // ---- persistent form for large batches (A K-major: the activation layers) ---------------------------------
 // One CTA per SM walks the tile list (tile = blockIdx.x + i * gridDim.x; tiles of one row block are neighbours, so

@@ -22,27 +22,22 @@ class VAE(VAEB):
 
 
 def main(n_epochs=2000, continuous=True, n_latent=10, synthetic=False, **ext):
-    """VAEBfullbayes.py:203-244."""
+    """The script body of VAEBfullbayes.py:203-244: Frey Face (200 hidden units) or MNIST (500), a fixed seed of
+    10, one printed pair of lines per epoch; `validate` already returns a mean here (:243)."""
     np.random.seed(10)
     print("loading data")
-    if continuous:
-        hu_N = 200
-        x_train, x_valid = load_frey(synthetic=synthetic)
-    else:
-        hu_N = 500
-        x_train, x_valid = load_mnist(synthetic=synthetic)
+    loader, hidden = (load_frey, 200) if continuous else (load_mnist, 500)
+    x_train, x_valid = loader(synthetic=synthetic)
     print("creating the model")
-    model = VAE(x_train, continuous, hu_N, n_latent, **ext)
+    model = VAE(x_train, continuous, hidden, n_latent, **ext)
     print("learning")
-    batch_order = np.arange(int(model.N / model.batch_size))
-    epoch = 0
+    batch_order = np.arange(model.N // model.batch_size)
     LB = LBvalidation = float("nan")
-    while epoch < n_epochs:
-        epoch += 1
-        start = time.time()
+    for epoch in range(1, n_epochs + 1):
+        t_epoch = time.time()
         np.random.shuffle(batch_order)
         LB = float(np.sum(model.update_many(batch_order), dtype=np.float64)) / len(batch_order)
-        print("Epoch %s : [Lower bound: %s, time: %s]" % (epoch, LB, time.time() - start))
-        LBvalidation = float(model.validate(x_valid))      # already a mean (VAEBfullbayes.py:243)
+        print("Epoch %s : [Lower bound: %s, time: %s]" % (epoch, LB, time.time() - t_epoch))
+        LBvalidation = float(model.validate(x_valid))
         print("          [Lower bound on validation set: %s]" % LBvalidation)
     return model, LB, LBvalidation

@@ -36,7 +36,10 @@ def _stub_factory(*args, **kwargs):
 class _RestrictedUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module in ("numpy.core.multiarray", "numpy._core.multiarray") and name in ("_reconstruct", "scalar"):
-            import numpy._core.multiarray as m
+            try:                                   # numpy >= 2
+                import numpy._core.multiarray as m
+            except ImportError:                    # numpy 1.x
+                import numpy.core.multiarray as m
             return getattr(m, name)
         if module == "numpy" and name in ("ndarray", "dtype"):
             return getattr(np, name)

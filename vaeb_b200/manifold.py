@@ -53,3 +53,23 @@ def save_pgm(img, path):
     with open(path, "wb") as f:
         f.write(b"P5 %d %d 255\n" % (a.shape[1], a.shape[0]))
         f.write(a.tobytes())
+
+
+def save_image(x, filename):
+    """VAEBImage.save_image (VAEBImage.py:13-21): one data row -> image file with the (1 - x)*255 inversion, in the
+    dataset's orientation.  `.jpg` / `.png` go through PIL when it is installed (as in the reference); `.pgm` needs
+    no imaging library.  Returns the 2-D uint8 array that was written."""
+    x = np.asarray(x, np.float32).ravel()
+    if x.size not in DIMENSIONS:
+        raise ValueError("save_image knows MNIST (784) and Frey Face (560) rows, got %d values" % x.size)
+    img = to_image(x)
+    a = np.clip((1.0 - np.asarray(img, np.float64)) * 255.0, 0, 255).astype(np.uint8)
+    if filename.lower().endswith(".pgm"):
+        save_pgm(img, filename)
+        return a
+    try:
+        from PIL import Image
+    except ImportError as ex:                             # pragma: no cover
+        raise RuntimeError("writing %s needs PIL; use a .pgm file name instead" % filename) from ex
+    Image.fromarray(a).convert("RGB").save(filename)
+    return a

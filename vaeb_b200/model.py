@@ -134,9 +134,10 @@ class VAEB(object):
         if params is None:
             values = self.initialize_params(None)
         else:
+            params = list(params)
+            if len(params) != len(self._shapes):      # VAEB.py:165-167 unpacks into a fixed-length list and fails loudly
+                raise ValueError("expected %d parameter tensors, got %d" % (len(self._shapes), len(params)))
             values = [_as_array(p).reshape(s) for p, s in zip(params, self._shapes)]
-            if len(values) != len(self._shapes):
-                raise ValueError("expected %d parameter tensors" % len(self._shapes))
         self._set_buffer(_lib.BUF_PARAMS, values)
         self.params = [SharedParam(self, _lib.BUF_PARAMS, i, nm, s)
                        for i, (nm, s) in enumerate(zip(self._names, self._shapes))]
@@ -387,6 +388,33 @@ class VAEB(object):
             self.close()
         except Exception:
             pass
+
+
+class _PinnedBlock(object):
+    """Owner of one cudaMallocHost block; freed when the last array viewing it goes away."""
+
+    def __init__(self, nbytes):
+        self._lib = _lib.load()
+        self.ptr = C.c_void_p()
+        _lib.check(self._lib.vaeb_host_alloc(int(nbytes), C.byref(self.ptr)))
+        self.buf = (C.c_uint8 * int(nbytes)).from_address(self.ptr.value)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self._lib.vaeb_host_free(self.ptr)
+                self.ptr = C.c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """numpy array in page-locked host memory (what `update_host_async` requires)."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    blk = _PinnedBlock(max(n, 1))
+    arr = np.frombuffer(blk.buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    return arr            # arr.base chain keeps blk.buf (and with it blk) alive
 
 
 def comm_unique_id(nccl_library=None):
