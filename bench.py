@@ -56,7 +56,7 @@ class ClockSampler(object):
     """SM clock and throttle reasons sampled through NVML DURING the timed region (a thread in
     this process: spawning nvidia-smi in a loop contends with kernel launches for the driver)."""
 
-    def __init__(self, index, period_s=0.05):
+    def __init__(self, index, period_s=0.01):
         self.index, self.period, self.rows, self.stop = index, period_s, [], threading.Event()
         self.max_mhz, self.t = None, None
 
@@ -416,11 +416,15 @@ def run_own(args):
         nb = N_TRAIN // M
         rng = np.random.RandomState(15485863 + rank)
         k2 = 2000
-        m2.update_many(rng.permutation(nb)[:k2].astype(np.int32))
+
+        def order2(n):                                  # np.random.shuffle(batch_order) per epoch (VAEB.py:574)
+            return np.concatenate([rng.permutation(nb) for _ in range(-(-n // nb))])[:n].astype(np.int32)
+        m2.update_many(order2(k2))
         t_r = time.perf_counter()
         while time.perf_counter() - t_r < 1.0:
-            m2.update_many(rng.permutation(nb).astype(np.int32))
-        o2 = rng.permutation(nb)[:k2].astype(np.int32)
+            m2.update_many(order2(1000))
+        o2 = order2(k2)
+        assert len(o2) == k2
         ms2 = timed(lambda: m2.update_many(o2))
         pin2 = torch.empty((N_TRAIN, D), dtype=torch.float32, pin_memory=True)
         pin2.copy_(torch.from_numpy(x))

@@ -293,7 +293,10 @@ def test_update_host_equals_resident_update():
 def test_update_host_async_stream_equals_synchronous_updates():
     """vaeb_update_host_async + vaeb_collect: the pipelined host-input path (copy stream, staging ring,
     deferred readback) must give exactly the bounds and parameters of the synchronous calls."""
-    x = O.synthetic_mnist(1100)
+    import vaeb_b200
+    xs = O.synthetic_mnist(1100)
+    x = vaeb_b200.pinned_empty(xs.shape)                     # the streaming path needs page-locked host memory
+    x[:] = xs
     params = _rand_params(784, 500, 20, False, 3, 0.05)
     m1 = _model(x[:100], False, 500, 20, 100, 1, "LB", params)
     m2 = _model(x[:100], False, 500, 20, 100, 1, "LB", params)

@@ -446,6 +446,7 @@ int all_reduce_grads(vaeb_handle* h) {
 // One update on device-resident rows; the scalar lands in d_scalars[slot].
 int enqueue_update(vaeb_handle* h, const float* d_xrows, int rows, const float* d_eps, const float* d_zeta,
                    int slot, bool apply) {
+  if (apply) h->steptc.mirrors_valid = false;       // the parameters change behind the step kernel's bf16 mirrors
   const Layout& l = h->lay;
   const int L = h->L;
   VAEB_TRY(ensure_ws(h, rows, (int64_t)rows * L, true));
@@ -524,7 +525,13 @@ int fused_updates(vaeb_handle* h, const int32_t* batch_order, const float* d_xro
     VAEB_CUDA(cudaMemcpyAsync(f.d_order, batch_order, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     d_order = f.d_order;
   }
+  if (step_tc_supported(h, rows)) return step_tc_launch(h, d_order, d_xrows, rows, n, d_eps, slot0, nullptr);
   return fused_step_launch(h, d_order, d_xrows, rows, n, d_eps, slot0, nullptr);
+}
+
+// an update of `rows` rows is ONE launch: the tensor-core step kernel (step_tc.cu) or the FFMA one (fused_step.cu)
+inline bool single_launch_supported(const vaeb_handle* h, int rows) {
+  return step_tc_supported(h, rows) || fused_step_supported(h, rows);
 }
 
 float* flat_by_which(vaeb_handle* h, int which) {
@@ -575,6 +582,7 @@ struct StateBackup {
     return e;
   }
   ~StateBackup() {
+    h->steptc.mirrors_valid = false;
     h->step = step0;
     h->launches = launches0;
     if (bp && ba) {
@@ -619,6 +627,7 @@ int vaeb_create(const vaeb_config* cfg, vaeb_handle** out) {
   h->cont = cfg->continuous != 0;
   build_layout(h->lay, h->D, h->H, h->Z, h->cont);
   { const char* e = getenv("VAEB_B200_FUSED"); h->fused_off = e && e[0] == '0'; h->fused_off_user = h->fused_off; }
+  { const char* e = getenv("VAEB_B200_STEP_TC"); h->steptc_off = e && e[0] == '0'; }
   h->tc.active = cfg->precision != VAEB_PREC_FP32;
   h->tc.ns = cfg->precision == VAEB_PREC_BF16X3 ? 2 : 1;
   VAEB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -658,6 +667,7 @@ int vaeb_destroy(vaeb_handle* h) {
   for (float* p : bufs) if (p) cudaFree(p);
   if (h->d_counter) cudaFree(h->d_counter);
   if (h->d_w45t) cudaFree(h->d_w45t);
+  step_tc_free(h->steptc);
   {
     FusedState& f = h->fused;
     void* fb[] = {f.bar, f.params_alt, f.partial, f.aux_part, f.tprior_part, f.d_order, f.d_timing};
@@ -731,6 +741,7 @@ int vaeb_set_tensors(vaeb_handle* h, int32_t which, const float* const* tensors)
   float* flat = flat_by_which(h, which);
   VAEB_REQUIRE(flat, "buffer not available for this estimator");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  h->steptc.mirrors_valid = false;
   for (int t = 0; t < h->lay.n; ++t) {
     const size_t n = (size_t)h->lay.rows[t] * h->lay.cols[t];
     VAEB_CUDA(cudaMemcpyAsync(flat + h->lay.off[t], tensors[t], n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
@@ -799,7 +810,7 @@ int vaeb_update(vaeb_handle* h, int64_t index, const float* eps, float* elbo_out
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
   const float* d_eps;
   VAEB_TRY(stage_eps_zeta(h, eps, (int64_t)h->L * h->M * h->Z, &d_eps));
-  if (fused_step_supported(h, h->M))
+  if (single_launch_supported(h, h->M))
     VAEB_TRY(fused_updates(h, nullptr, h->d_x + (size_t)index * h->M * h->D, h->M, 1, d_eps));
   else
     VAEB_TRY(enqueue_update(h, h->d_x + (size_t)index * h->M * h->D, h->M, d_eps, nullptr, 0, true));
@@ -813,7 +824,7 @@ int vaeb_update_host(vaeb_handle* h, const float* x, int64_t rows, const float* 
   VAEB_TRY(stage_in(h, &h->d_stage, &h->stage_cap, x, rows * h->D));
   const float* d_eps;
   VAEB_TRY(stage_eps_zeta(h, eps, (int64_t)h->L * rows * h->Z, &d_eps));
-  if (fused_step_supported(h, (int)rows))
+  if (single_launch_supported(h, (int)rows))
     VAEB_TRY(fused_updates(h, nullptr, h->d_stage, (int)rows, 1, d_eps));
   else
     VAEB_TRY(enqueue_update(h, h->d_stage, (int)rows, d_eps, nullptr, 0, true));
@@ -827,6 +838,7 @@ int vaeb_ae_train(vaeb_handle* h, int32_t kind, const int32_t* idx, int32_t n, f
   VAEB_REQUIRE(!(kind == VAEB_AE_VANILLA && h->cont), "the vanilla AE has sigmoid outputs only (vanilla-ae/ae.py:62-67)");
   VAEB_REQUIRE(h->L == 1 && !is_fvb(h) && h->world == 1, "AE baselines: L = 1, single GPU");
   if (!h->d_x) { vaeb_set_error("vaeb_ae_train before vaeb_upload_data"); return VAEB_ESTATE; }
+  h->steptc.mirrors_valid = false;
   for (int i = 0; i < n; ++i) VAEB_REQUIRE(idx[i] >= 0 && idx[i] < h->n_data, "row index outside the resident data");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
   const Layout& l = h->lay;
@@ -941,7 +953,9 @@ static int async_flush(vaeb_handle* h) {
   const int slot0 = h->a_outstanding - n;
   VAEB_CUDA(cudaEventRecord(h->a_copied[g], h->copy_stream));
   VAEB_CUDA(cudaStreamWaitEvent(h->stream, h->a_copied[g], 0));
-  if (fused_step_supported(h, rows)) {
+  if (step_tc_supported(h, rows)) {
+    VAEB_TRY(step_tc_launch(h, h->d_iota, h->a_stage[g], rows, n, nullptr, slot0, nullptr));
+  } else if (fused_step_supported(h, rows)) {
     VAEB_TRY(ensure_ws(h, rows, rows, true));
     VAEB_TRY(fused_step_launch(h, h->d_iota, h->a_stage[g], rows, n, nullptr, slot0, nullptr));
   } else {
@@ -1034,7 +1048,7 @@ int vaeb_update_many(vaeb_handle* h, const int32_t* batch_order, int32_t n, floa
     const int64_t index = batch_order[i];
     VAEB_REQUIRE(index >= 0 && (index + 1) * (int64_t)h->M <= h->n_data, "batch index outside the resident data");
   }
-  if (fused_step_supported(h, h->M)) {
+  if (single_launch_supported(h, h->M)) {
     VAEB_TRY(fused_updates(h, batch_order, nullptr, h->M, n, nullptr));
     return read_scalars(h, n, elbo_out);
   }
@@ -1090,6 +1104,7 @@ int vaeb_apply_update(vaeb_handle* h) {
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
   const bool fb = h->cfg.variant == VAEB_VARIANT_FULLBAYES;
   const float prior = (fb || h->grads_have_prior) ? 0.f : h->cfg.prior_scale;
+  h->steptc.mirrors_valid = false;
   VAEB_LAUNCH(launch_adagrad(h->stream, &h->launches, h->d_params, h->d_ada, h->d_grads, h->lay.padded / 4,
                              h->cfg.learning_rate, h->cfg.adagrad_eps, prior,
                              fb ? h->cfg.learning_rate * 1e-6f : 0.f, h->d_grads + h->lay.padded, 1.f, 1.f, nullptr));
@@ -1428,7 +1443,59 @@ int vaeb_profile_update(vaeb_handle* h, int64_t index, int32_t iters, int32_t ma
   VAEB_CUDA(backup.take());
   int rc = VAEB_OK;
   int n = 0;
-  if (fused_step_supported(h, h->M)) {
+  if (step_tc_supported(h, h->M)) {
+    // the tensor-core step kernel stamps %globaltimer after every grid barrier (CTA 0): ns per phase, averaged over
+    // `iters` consecutive updates of one launch (the first two are warm-up)
+    constexpr int NP = st2::N_PHASES;
+    static const char* const kNames[NP] = {
+        "P1 enc1 x.W3+tanh | W4,W5 update", "P2 heads+reparam+KL", "P3 dec1+dec2 h.W2+loglik+delta",
+        "P4 dgrad (da.W2^T)*(1-h^2)", "P5 dz | W2 update | bound", "P6 W3 update | W1 update"};
+    const int steps = iters + 2;
+    StepTcState& f = h->steptc;
+    if (steps * (NP + 1) > f.timing_cap) {
+      if (f.d_timing) cudaFree(f.d_timing);
+      f.d_timing = nullptr;
+      VAEB_CUDA(cudaMalloc((void**)&f.d_timing, ((size_t)steps * (NP + 1) + 128) * sizeof(long long)));   // + sub-phase trace
+      f.timing_cap = steps * (NP + 1);
+    }
+    VAEB_CUDA(cudaMemsetAsync(f.d_timing, 0, ((size_t)steps * (NP + 1) + 128) * sizeof(long long), h->stream));
+    if (steps > f.order_cap) {
+      if (f.d_order) cudaFree(f.d_order);
+      f.d_order = nullptr;
+      VAEB_CUDA(cudaMalloc((void**)&f.d_order, (size_t)steps * sizeof(int)));
+      f.order_cap = steps;
+    }
+    std::vector<int32_t> order((size_t)steps, (int32_t)index);
+    VAEB_CUDA(cudaMemcpyAsync(f.d_order, order.data(), (size_t)steps * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    VAEB_CUDA(cudaStreamSynchronize(h->stream));
+    VAEB_TRY(ensure_scalars(h, steps));
+    rc = step_tc_launch(h, f.d_order, nullptr, h->M, steps, nullptr, 0, f.d_timing);
+    std::vector<long long> tm((size_t)steps * (NP + 1) + 128);
+    if (rc == VAEB_OK) {
+      VAEB_CUDA(cudaMemcpyAsync(tm.data(), f.d_timing, tm.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+      VAEB_CUDA(cudaStreamSynchronize(h->stream));
+      if (getenv("VAEB_STEPTC_TRACE")) {               // sub-phase stamps of CTA 0 in the last step (ns since the first)
+        const long long* tr = tm.data() + (size_t)steps * (NP + 1);
+        for (int q = 0; q < 60 && tr[2 * q] != 0; ++q)
+          fprintf(stderr, "st2 trace %3lld  +%8.3f us\n", tr[2 * q], 1e-3 * (double)(tr[2 * q + 1] - tr[1]));
+      }
+      const double dM = h->M, dD = h->D, dH = h->H, dZ = h->Z;
+      const double fl[NP] = {2 * dM * dD * dH + 4 * dM * dH * dZ, 4 * dM * dH * dZ, 2 * dM * dZ * dH + 2 * dM * dH * dD,
+                             2 * dM * dH * dD, 2 * dM * dZ * dH + 2 * dM * dH * dD, 2 * dM * dD * dH + 4 * dM * dH * dZ + 2 * dM * dZ * dH};
+      const double by[NP] = {4 * (dM * dD + dD * dH + dM * dH) + 40 * dH * dZ, 4 * (dM * dH + 2 * dH * dZ + 4 * dM * dZ),
+                             4 * (dM * dZ + dZ * dH + dH * dD + 2 * dM * dD), 4 * (dM * dD + dH * dD + 2 * dM * dH),
+                             4 * (dM * dH + dM * dD) + 24 * dH * dD, 4 * (dM * dD + dM * dH) + 20 * dD * dH + 20 * dZ * dH};
+      n = std::min(NP, (int)max_phases);
+      for (int i = 0; i < n; ++i) {
+        double acc = 0;
+        for (int q = 2; q < steps; ++q) acc += (double)(tm[(size_t)q * (NP + 1) + i + 1] - tm[(size_t)q * (NP + 1) + i]);
+        ms[i] = (float)(acc / iters * 1e-6);
+        flops[i] = fl[i]; bytes[i] = by[i];
+        std::strncpy(names + 48 * i, kNames[i], 47);
+        names[48 * i + 47] = 0;
+      }
+    }
+  } else if (fused_step_supported(h, h->M)) {
     // the fused kernel stamps %globaltimer at every phase boundary (CTA 0): ns per phase, averaged
     // over `iters` consecutive updates of one launch (the first two are warm-up)
     constexpr int NP = fs::N_PHASES;

@@ -8,6 +8,7 @@
 #include "../../include/vaeb_b200.h"
 #include "tc_layers.h"
 #include "fused_step.cuh"
+#include "step_tc.cuh"
 
 void vaeb_set_error(const std::string& msg);
 
@@ -144,6 +145,8 @@ struct vaeb_handle {
   bool grads_have_prior = false;
   FusedState fused;
   IsTcState istc;
+  StepTcState steptc;                 // tensor-core single-launch step (step_tc.cu)
+  bool steptc_off = false;            // VAEB_B200_STEP_TC=0: the FFMA kernel of fused_step.cu serves M <= 128 too
   bool fused_off = false;             // VAEB_B200_FUSED=0: always use the per-layer kernels
   bool fused_off_user = false;        // what the environment asked for (AdaDelta also turns the fused kernel off)
   // data parallel

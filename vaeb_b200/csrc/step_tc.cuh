@@ -1,0 +1,69 @@
+// Shared declarations of the tensor-core single-launch AEVB step (step_tc.cu <-> api.cu).
+//
+// The M = 100 update of the reference (VAEB.py:408-415 -- forward, bound, backward, prior, Adagrad; configs C2 and
+// the Bernoulli runs of scripts/pg_7_graphs.sh) as ONE persistent kernel of thread-block clusters: every contraction
+// runs on tcgen05 (bf16 hi+lo operands, three MMAs per k step, fp32 accumulation in TMEM: the fp32 parity tier), the
+// split of a contraction over the four CTAs of a cluster is reduced through distributed shared memory, weights are
+// read from bf16 mirrors kept in the UMMA shared-memory image (pre-swizzled, K-major) and rewritten by the Adagrad
+// epilogues of the weight-gradient GEMMs.  Six grid barriers per update (the FFMA kernel of fused_step.cu needs
+// eight), no parameter double buffer.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace st2 {
+
+constexpr int NT = 512;                 // threads per CTA (16 warps)
+constexpr int CL = 4;                   // CTAs per cluster = ways a contraction is split
+constexpr int MP = 128;                 // rows of a minibatch tile (UMMA M); minibatches of up to 128 rows
+constexpr int N_PHASES = 6;             // grid barriers per update
+
+// tile rows (UMMA N) of the mirrored weight operands
+constexpr int TR_ENC1 = 16, TR_DEC2 = 32, TR_DGRAD = 16;
+
+struct Params {
+  int D, H, Z, M;
+  int HP;                               // H rounded up to 64 (leading dimension of the hidden activations)
+  int KD, KH;                           // 64-wide k chunks over D and over H
+  int NH;                               // 2Z rounded up to 16: UMMA N of the latent heads
+  int NZ;                               // Z + 1 rounded up to 16: UMMA N of dz and of the W1 weight gradient
+  int la;
+  float w, lr, ada_eps, prior, p2;
+  float* P;                             // flat fp32 parameters (reference tensor order), updated in place
+  float* ada;
+  int64_t oW3, oW4, oW5, oW1, oW2, ob3, ob4, ob5, ob1, ob2;
+  // bf16 hi/lo mirrors, [n tile][k chunk][hi, lo][rows x 128 B] in the K-major SWIZZLE_128B image
+  uint8_t *m_enc1, *m_heads, *m_dec2, *m_dgrad, *m_dz;
+  const float* x_base; const int* batch_order; const float* x_direct;
+  const float* eps_inj;
+  uint64_t seed; uint32_t step0; int64_t row_offset;
+  float *he, *hd, *da2, *da1, *dd, *mu, *ls, *eps, *z;     // fp32 activations: [MP, HP] / [MP, D] / [MP, 2Z] / [MP, Z]
+  float *partial, *aux;                 // [MP, tiles of dec2] log-likelihood row partials; [MP] KL / LA row terms
+  int n_tiles3;                         // n tiles of dec2 (partial's leading dimension)
+  float* scalars; float Mg; float bmult;
+  int n_steps;
+  unsigned long long* bar; unsigned long long bar_base;
+  long long* timing;                    // nullptr or [n_steps * (N_PHASES + 1)] globaltimer stamps of CTA 0
+};
+
+}  // namespace st2
+
+struct vaeb_handle;
+struct StepTcState {
+  bool ready = false, unavailable = false;
+  int n_cta = 0;
+  unsigned long long* bar = nullptr; unsigned long long bar_count = 0;
+  uint8_t *m_enc1 = nullptr, *m_heads = nullptr, *m_dec2 = nullptr, *m_dgrad = nullptr, *m_dz = nullptr;
+  bool mirrors_valid = false;
+  float *he = nullptr, *hd = nullptr, *da2 = nullptr, *da1 = nullptr, *dd = nullptr, *mu = nullptr, *ls = nullptr,
+        *eps = nullptr, *z = nullptr, *partial = nullptr, *aux = nullptr;
+  int* d_order = nullptr; int order_cap = 0;
+  long long* d_timing = nullptr; int timing_cap = 0;
+};
+
+// true if this configuration / minibatch is served by the tensor-core step kernel
+bool step_tc_supported(const vaeb_handle* h, int rows);
+// n_steps updates in one launch (same contract as fused_step_launch)
+int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int rows, int n_steps, const float* d_eps,
+                   int slot0, long long* d_timing);
+void step_tc_free(StepTcState& s);
