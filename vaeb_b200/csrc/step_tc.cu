@@ -8,11 +8,15 @@
 //   * CTA items -- the weight-gradient GEMMs gW[128 features x N] = act^T . delta (K = the minibatch, zero padded to
 //     128): one output tile per CTA, Adagrad with the prior (VAEB.py:389-390,426-444) in the epilogue, which also
 //     rewrites the bf16 mirrors of the weights it just updated.
-// Operands.  The A side of every GEMM is produced in software: fp32 activations are read from L2 (ld.global.cg),
-// split into bf16 hi + lo and stored into shared memory in the UMMA K-major SWIZZLE_128B image (the decoder hidden
-// layer and the encoder's dh_e are not even read -- they are recomputed there from z resp. [dmu|dls] with FFMA, K = Z).
-// The B side of the activation GEMMs is a straight 16-byte copy of a pre-swizzled mirror blob.  One thread issues
-// hi*hi + hi*lo + lo*hi per k step (bf16x3: the fp32 parity tier), commits to an mbarrier; 16 warps read TMEM.
+// Operands.  Every operand is a bf16 hi + lo pair of tiles in the UMMA K-major SWIZZLE_128B image.  Weights AND
+// activations are kept in that image in global memory (L2): an epilogue thread stores the value it produced straight
+// into the mirrors its consumers will load (row-major for the next layer, transposed for the weight gradients), so
+// staging an operand is ONE cp.async.bulk issued by one thread and completed on an mbarrier.  Two operands are produced
+// in software instead: the minibatch x (fp32 from the caller; staged while the CTA would otherwise wait at the
+// preceding grid barrier) and the two thin layers around the latent code, recomputed with FFMA where they are consumed
+// (h_d = tanh(z.W1 + b1) into the A tile of dec2, da3 = ([dmu|dls].W45^T)(1 - h_e^2) into the B tile of the W3 gradient).
+// One thread issues hi*hi + hi*lo + lo*hi per k step (bf16x3: the fp32 parity tier) and commits to an mbarrier; all 16
+// warps read TMEM.
 // Phases of one update (a grid barrier after each):
 //   P1 enc1 (+ the W4/W5 update of the previous step on the spare cluster)   P2 heads + reparam + KL
 //   P3 dec1 (recomputed) + dec2 + log-lik + da2                              P4 dgrad -> da1
@@ -28,7 +32,7 @@
 
 namespace st2 {
 
-constexpr int TBA = MP * 128;                      // bytes of one 64-wide k chunk of an A tile (hi or lo half)
+constexpr int TBA = MP * 128;                      // bytes of one 64-wide k chunk of a 128-row tile (hi or lo half)
 constexpr int A_MAXCH = 4;
 constexpr int SM_A = 0;                            // A_MAXCH chunks x (hi, lo) x 16 KB = 128 KB
 constexpr int SM_B = A_MAXCH * 2 * TBA;            // B tiles: up to 32 KB (48 KB for the heads), scratch above
@@ -36,17 +40,25 @@ constexpr int SM_B_BYTES = 57344;
 constexpr int SM_SCR = SM_B + 32768;               // 24 KB of producer scratch inside the B region
 constexpr int SM_RECV = SM_B + SM_B_BYTES;         // [CL][32 rows][<= 48 cols] fp32 partials from the cluster
 constexpr int SM_RECV_BYTES = CL * 32 * 48 * 4;
-constexpr int SM_MISC = SM_RECV + SM_RECV_BYTES;   // mbarrier, TMEM slot, small reductions
+constexpr int SM_MISC = SM_RECV + SM_RECV_BYTES;   // mbarriers, TMEM slot, small reductions
 constexpr int SMEM_BYTES = SM_MISC + 1024 + 1024;  // + slack for the 1024-byte alignment of the base
 constexpr uint32_t TMEM_COLS = 64;
+
+// Base of the (1024-byte aligned) dynamic shared memory, derived from the symbol itself: the compiler then knows every
+// pointer built from it is a shared-memory pointer and emits LDS / STS instead of generic loads and stores.
+extern __shared__ uint8_t st2_smem_raw[];
+__device__ __forceinline__ uint8_t* smem_base() {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(st2_smem_raw);
+  return st2_smem_raw + ((1024u - (a & 1023u)) & 1023u);
+}
 
 struct Ctx {
   uint8_t* sm;
   uint32_t tmem;
-  uint64_t* mma_bar;
-  uint32_t mma_phase;
+  uint64_t *mma_bar, *op_bar;
+  uint32_t mma_phase, op_phase;
   int rank, cid, ncl, warp, lane;
-  long long* trace; int tn;            // optional sub-phase stamps (cluster 0, rank 0, thread 0 of the last step)
+  long long* trace; int tn;            // optional sub-phase stamps (CTA 0, thread 0, last step of a profiling launch)
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------------
@@ -71,12 +83,26 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
                : "r"(taddr)
                : "memory");
 }
+// one bulk copy global -> this CTA's shared memory, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ long long gtime() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define ST2_TRACE(c, id) do { if ((c).trace && threadIdx.x == 0 && (c).tn < 60) { (c).trace[(c).tn * 2] = (id); (c).trace[(c).tn * 2 + 1] = gtime(); ++(c).tn; } } while (0)
+#define ST2_TRACE(c, id)                                               \
+  do {                                                                 \
+    if ((c).trace && threadIdx.x == 0 && (c).tn < 62) {                \
+      (c).trace[(c).tn * 2] = (id);                                    \
+      (c).trace[(c).tn * 2 + 1] = gtime();                             \
+      ++(c).tn;                                                        \
+    }                                                                  \
+  } while (0)
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&t);
@@ -92,8 +118,19 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-// branch-free tanh, relative error < 5e-6 (as the bf16x3 layer kernels, tc_layers.cu): 1 - 2/(e^{2|x|}+1) from
-// ex2.approx / rcp.approx for |x| >= 0.1, the odd Taylor polynomial through x^9 below
+__device__ __forceinline__ void put_unit(uint8_t* d, int half_bytes, const float* v) {
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  *reinterpret_cast<uint4*>(d) = hi;
+  *reinterpret_cast<uint4*>(d + half_bytes) = lo;
+}
+// one element (hi at d, lo half_bytes later)
+__device__ __forceinline__ void put_bf(uint8_t* d, int half_bytes, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  *reinterpret_cast<__nv_bfloat16*>(d) = h;
+  *reinterpret_cast<__nv_bfloat16*>(d + half_bytes) = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+// branch-free tanh, relative error < 5e-6 (as the bf16x3 layer kernels, tc_layers.cu)
 __device__ __forceinline__ float tanh_fast(float x) {
   const float ax = fabsf(x), x2 = x * x;
   float e, r;
@@ -109,158 +146,118 @@ __device__ __forceinline__ float sigmoidf_(float a) { return 1.0f / (1.0f + expf
 
 // byte offset of the 16-byte unit (row r, k octet cu) inside one K-major SWIZZLE_128B chunk tile
 __device__ __forceinline__ uint32_t unit_off(int r, int cu) { return (uint32_t)r * 128u + (((uint32_t)cu ^ ((uint32_t)r & 7u)) << 4); }
-
-// ---- operand producers -------------------------------------------------------------------------------------------
-// Every producer is two-phase: ALL global loads of a batch are issued before the first shared-memory store, so a
-// thread pays one L2 round trip per batch instead of one per 32 bytes (stores through generic pointers would otherwise
-// order the loads behind them).  A unit = eight consecutive k of one tile row = one 16-byte piece of the hi and of
-// the lo half of the tile.
-__device__ __forceinline__ void put_unit(uint8_t* d, int half_bytes, const float* v) {
-  uint4 hi, lo;
-  split8(v, hi, lo);
-  *reinterpret_cast<uint4*>(d) = hi;
-  *reinterpret_cast<uint4*>(d + half_bytes) = lo;
+// address of element (batch row r, column k) in a row-major activation mirror [k chunk][hi, lo][128 x 128 B]
+__device__ __forceinline__ uint8_t* km_addr(uint8_t* base, int r, int k) {
+  return base + (size_t)(k >> 6) * 2 * TBA + tc::sw128_offset(r, k & 63);
+}
+// address of element (row of feature tile `tile`, batch row b) in a transposed mirror
+// [feature tile][batch chunk (2)][hi, lo][tile rows x 128 B]; half = tile rows * 128
+__device__ __forceinline__ uint8_t* t_addr(uint8_t* base, int tile, int half, int row, int b) {
+  return base + ((size_t)tile * 2 + (b >> 6)) * 2 * half + tc::sw128_offset(row, b & 63);
 }
 
-// K-major tile whose rows are the SOURCE rows (activation GEMMs): src[rows][ld] fp32, k in [k0, k0 + 64 nch) clipped to
-// kmax (a multiple of 8), rows >= rows_valid and k >= kmax zero filled.  Chunk ci: hi at base + ci*2*TBA, lo TBA later.
-struct RowsSrc {
-  const float* src; int ld, rows_valid, k0, kmax, per_row;
-  __device__ __forceinline__ void load(int u, float* v) const {
-    const int r = u / per_row, ku = u - r * per_row;
-    const int k = k0 + (ku >> 3) * 64 + (ku & 7) * 8;
-    if (r < rows_valid && k < kmax) {
-      const float* s = src + (size_t)r * ld + k;
-      const float4 a = __ldcg(reinterpret_cast<const float4*>(s)), b = __ldcg(reinterpret_cast<const float4*>(s + 4));
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
+// ---- software producers for the minibatch x ------------------------------------------------------------------------
+// Two-phase: every global load of a batch is issued before the first shared-memory store (one L2 round trip per batch).
+// A tile of enc1: rows = batch rows, k in [64 c0, 64 (c0 + nch)), zero beyond D and beyond M rows.
+__device__ __forceinline__ void stage_x_rows(uint8_t* sm, const float* __restrict__ x, int D, int M, int c0, int nch) {
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    float v[4][8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    for (int b = 0; b < 4; ++b) {
+      const int u = threadIdx.x + (half * 4 + b) * NT;          // 128 rows x 32 slots (4 chunks x 8 octets)
+      const int r = u >> 5, ku = u & 31;
+      const int k = (c0 + (ku >> 3)) * 64 + (ku & 7) * 8;
+      if (ku < nch * 8 && r < M && k < D) {
+        const float* s = x + (size_t)r * D + k;
+        const float4 a0 = __ldcg(reinterpret_cast<const float4*>(s)), a1 = __ldcg(reinterpret_cast<const float4*>(s + 4));
+        v[b][0] = a0.x; v[b][1] = a0.y; v[b][2] = a0.z; v[b][3] = a0.w;
+        v[b][4] = a1.x; v[b][5] = a1.y; v[b][6] = a1.z; v[b][7] = a1.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[b][e] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int u = threadIdx.x + (half * 4 + b) * NT;
+      const int r = u >> 5, ku = u & 31;
+      if (ku < nch * 8) put_unit(sm + SM_A + (size_t)(ku >> 3) * 2 * TBA + unit_off(r, ku & 7), TBA, v[b]);
     }
   }
-  __device__ __forceinline__ uint8_t* dst(uint8_t* base, int u) const {
-    const int r = u / per_row, ku = u - r * per_row;
-    return base + (size_t)(ku >> 3) * 2 * TBA + unit_off(r, ku & 7);
-  }
-};
-
-// K-major tile whose rows are FEATURES and whose contraction index is the minibatch (weight gradients): element
-// (feature f0 + i, batch b) = src[b][f0 + i]; feature == ones_f reads as 1 (bias gradient), features >= fmax and
-// batch rows >= M are zero.  Two k chunks (128 batch rows).  TR rows per tile, TR * 128 bytes per chunk half.
-struct TSrc {
-  const float* src; int TR, ld, M, f0, fmax, ones_f;
-  __device__ __forceinline__ void load(int u, float* v) const {
-    const int bo = u / TR, f = f0 + (u - bo * TR);
+}
+// A tile of the W3 gradient: rows = pixels f0 .. f0+127 (pixel == D reads as 1: the bias row), k = batch rows
+__device__ __forceinline__ void stage_x_T(uint8_t* sm, const float* __restrict__ x, int D, int M, int f0) {
+  float v[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int u = threadIdx.x + i * NT;                          // 16 batch octets x 128 features
+    const int bo = u >> 7, f = f0 + (u & 127);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int b = bo * 8 + e;
       float t = 0.f;
       if (b < M) {
-        if (f == ones_f) t = 1.0f;
-        else if (f < fmax) t = __ldcg(src + (size_t)b * ld + f);
+        if (f == D) t = 1.0f;
+        else if (f < D) t = __ldcg(x + (size_t)b * D + f);
       }
-      v[e] = t;
+      v[i][e] = t;
     }
   }
-  __device__ __forceinline__ uint8_t* dst(uint8_t* base, int u) const {
-    const int bo = u / TR, i = u - bo * TR;
-    return base + (size_t)(bo >> 3) * 2 * (TR * 128) + unit_off(i, bo & 7);
-  }
-};
-
-// A tile from RowsSrc (2 nch units per thread) + the pre-swizzled B blob of a mirror (16-byte pieces)
-__device__ __forceinline__ void stage_rows_blob(uint8_t* sm, const RowsSrc& a, int nch, const uint8_t* __restrict__ blob,
-                                                int blob_bytes) {
-  uint8_t* bd = sm + SM_B;
-  uint4 bl[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int o = (threadIdx.x + i * NT) * 16;
-    bl[i] = o < blob_bytes ? __ldcg(reinterpret_cast<const uint4*>(blob + o)) : make_uint4(0, 0, 0, 0);
+    const int u = threadIdx.x + i * NT;
+    const int bo = u >> 7;
+    put_unit(sm + SM_A + (size_t)(bo >> 3) * 2 * TBA + unit_off(u & 127, bo & 7), TBA, v[i]);
   }
-  const int n_units = MP * nch * 8;
-  bool blob_stored = false;
-  for (int u0 = threadIdx.x; u0 < n_units; u0 += 4 * NT) {
-    float v[4][8];
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-      if (u0 + b * NT < n_units) a.load(u0 + b * NT, v[b]);
-    if (!blob_stored) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int o = (threadIdx.x + i * NT) * 16;
-        if (o < blob_bytes) *reinterpret_cast<uint4*>(bd + o) = bl[i];
-      }
-      blob_stored = true;
-    }
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-      if (u0 + b * NT < n_units) put_unit(a.dst(sm + SM_A, u0 + b * NT), TBA, v[b]);
-  }
-  if (!blob_stored) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int o = (threadIdx.x + i * NT) * 16;
-      if (o < blob_bytes) *reinterpret_cast<uint4*>(bd + o) = bl[i];
-    }
-  }
-  for (int o = (threadIdx.x + 4 * NT) * 16; o < blob_bytes; o += NT * 16)
-    *reinterpret_cast<uint4*>(bd + o) = __ldcg(reinterpret_cast<const uint4*>(blob + o));
-}
-
-// transposed tiles of a weight-gradient GEMM: A (128 features: 4 units per thread) and optionally B (<= 48 features)
-__device__ __forceinline__ void stage_T(uint8_t* sm, const TSrc& a, const TSrc* b) {
-  float va[4][8], vb[2][8];
-  const int nb = b ? b->TR * 16 : 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) a.load(threadIdx.x + i * NT, va[i]);
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-    if ((int)threadIdx.x + i * NT < nb) b->load(threadIdx.x + i * NT, vb[i]);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) put_unit(a.dst(sm + SM_A, threadIdx.x + i * NT), TBA, va[i]);
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-    if ((int)threadIdx.x + i * NT < nb) put_unit(b->dst(sm + SM_B, threadIdx.x + i * NT), b->TR * 128, vb[i]);
-}
-
-__device__ __forceinline__ void copy_blob(uint8_t* dst, const uint8_t* __restrict__ src, int bytes) {
-  for (int o = threadIdx.x * 16; o < bytes; o += NT * 16)
-    *reinterpret_cast<uint4*>(dst + o) = __ldcg(reinterpret_cast<const uint4*>(src + o));
 }
 
 // ---- MMA ---------------------------------------------------------------------------------------------------------
-// acc[128 x N] = sum over nch chunks / k16_total k steps of A.B^T in bf16x3.  Called by every thread of the CTA after
-// the producers; returns when the accumulator is complete (nch == 0: nothing is issued).
-__device__ __forceinline__ void mma_run(Ctx& c, int nch, int k16_total, int TBB, int N) {
+// thread 0: announce `bytes` of operand traffic on the operand barrier (the bulk copies follow)
+// (the generic-proxy writes the copies read were fenced towards the async proxy by their WRITERS, before the grid
+// barrier that ordered them before this thread: grid_barrier)
+__device__ __forceinline__ void ops_begin(Ctx& c, uint32_t bytes) { tc::mbar_expect_tx(c.op_bar, bytes); }
+// acc[128 x N] = sum over nch chunks / k16_total k steps of A.B^T in bf16x3.  Called by EVERY thread; `wait_ops`: the
+// issuing thread first waits for the bulk copies announced by ops_begin.  Returns when the accumulator is complete.
+__device__ __forceinline__ void mma_run(Ctx& c, int nch, int k16_total, int TBB, int N, bool wait_ops) {
   tc::fence_proxy_async();            // this thread's shared-memory stores -> visible to the tensor core (async proxy)
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  if (nch <= 0) return;
   if (threadIdx.x == 0) {
-    const uint32_t idesc = tc::make_idesc_bf16(MP, N, 0, 0);
-    const uint32_t a0 = tc::smem_u32(c.sm + SM_A), b0 = tc::smem_u32(c.sm + SM_B);
-    uint32_t acc = 0;
-    int k16 = 0;
-    for (int ci = 0; ci < nch; ++ci) {
-      const uint32_t a = a0 + (uint32_t)ci * 2u * TBA, b = b0 + (uint32_t)ci * 2u * (uint32_t)TBB;
-#pragma unroll
-      for (int k = 0; k < 4; ++k, ++k16) {
-        if (k16 >= k16_total) break;
-        const uint64_t ah = tc::desc_kmajor(a, k), al = tc::desc_kmajor(a + TBA, k);
-        const uint64_t bh = tc::desc_kmajor(b, k), bl = tc::desc_kmajor(b + (uint32_t)TBB, k);
-        tc::umma_bf16(c.tmem, ah, bh, idesc, acc);
-        tc::umma_bf16(c.tmem, ah, bl, idesc, 1u);
-        tc::umma_bf16(c.tmem, al, bh, idesc, 1u);
-        acc = 1u;
-      }
+    if (wait_ops) {
+      tc::mbar_wait(c.op_bar, c.op_phase);
+      c.op_phase ^= 1u;
+      tc::tc_fence_after();
     }
-    tc::umma_commit(c.mma_bar);
+    if (nch > 0) {
+      const uint32_t idesc = tc::make_idesc_bf16(MP, N, 0, 0);
+      // descriptor = constant fields | (address >> 4); the address field (14 bits) never overflows: smem < 256 KB
+      const uint64_t d0 = tc::make_smem_desc(0u, 16u, 1024u);
+      const uint64_t a0 = d0 | (uint64_t)(tc::smem_u32(c.sm + SM_A) >> 4), b0 = d0 | (uint64_t)(tc::smem_u32(c.sm + SM_B) >> 4);
+      const uint32_t a_lo = TBA >> 4, b_lo = (uint32_t)TBB >> 4;
+      uint32_t acc = 0;
+      int k16 = 0;
+#pragma unroll 1
+      for (int ci = 0; ci < nch; ++ci) {
+        const uint64_t a = a0 + (uint64_t)((uint32_t)ci * 2u * a_lo), b = b0 + (uint64_t)((uint32_t)ci * 2u * b_lo);
+#pragma unroll
+        for (int k = 0; k < 4; ++k, ++k16) {
+          if (k16 >= k16_total) break;
+          tc::umma_bf16(c.tmem, a + 2 * k, b + 2 * k, idesc, acc);
+          tc::umma_bf16(c.tmem, a + 2 * k, b + b_lo + 2 * k, idesc, 1u);
+          tc::umma_bf16(c.tmem, a + a_lo + 2 * k, b + 2 * k, idesc, 1u);
+          acc = 1u;
+        }
+      }
+      tc::umma_commit(c.mma_bar);
+    }
   }
-  tc::mbar_wait(c.mma_bar, c.mma_phase);
-  c.mma_phase ^= 1u;
-  tc::tc_fence_after();
+  if (nch > 0) {
+    tc::mbar_wait(c.mma_bar, c.mma_phase);
+    c.mma_phase ^= 1u;
+    tc::tc_fence_after();
+  }
 }
 
 // Partial accumulator [128 x N] -> the four CTAs of the cluster by row quarter: rows 32q..32q+31 go to CTA q, slot
@@ -290,16 +287,6 @@ __device__ __forceinline__ float recv_sum(const float* recv, int N, int row, int
 }
 
 struct Hyper { float lr, eps, prior, p2; };
-__device__ __forceinline__ float adagrad_step(float* P, float* ada, size_t o, float g, const Hyper& hy) {
-  const float p = __ldcg(P + o), a0 = __ldcg(ada + o);
-  g -= hy.prior * p;                                    // VAEB.py:389-390
-  const float a = a0 + g * g;                           // VAEB.py:439
-  float np_ = p + hy.lr * g / (sqrtf(a) + hy.eps);      // VAEB.py:441
-  if (hy.p2 != 0.f) np_ -= hy.p2 * p * p;               // VAEBfullbayes.py:183-184
-  P[o] = np_;
-  ada[o] = a;
-  return np_;
-}
 // Adagrad on the (up to) eight parameters one epilogue thread owns: every load is issued before the first store
 // (one L2 round trip per unit), 16-byte accesses when the eight are contiguous and aligned.  nv = the new values.
 __device__ __forceinline__ void adagrad8(float* P, float* ada, const size_t* off, const bool* ok, const float* g,
@@ -339,18 +326,15 @@ __device__ __forceinline__ void adagrad8(float* P, float* ada, const size_t* off
       if (ok[e]) { P[off[e]] = nv[e]; ada[off[e]] = a[e]; }
   }
 }
-// one element of a mirror: tile of TR rows, KC chunks per tile; (n, k) -> hi and lo halves
-__device__ __forceinline__ void mirror_put(uint8_t* m, int TR, int KC, int n, int k, float v) {
+// one element of a weight mirror: tiles of TR rows (tile index nt, row r inside it), KC chunks per tile
+__device__ __forceinline__ void mirror_put(uint8_t* m, int TR, int KC, int nt, int r, int k, float v) {
   const int TB = TR * 128;
-  const int r = n % TR;
-  uint8_t* d = m + ((size_t)(n / TR) * KC + (k >> 6)) * 2 * TB + tc::sw128_offset(r, k & 63);
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  *reinterpret_cast<__nv_bfloat16*>(d) = h;
-  *reinterpret_cast<__nv_bfloat16*>(d + TB) = __float2bfloat16_rn(v - __bfloat162float(h));
+  put_bf(m + ((size_t)nt * KC + (k >> 6)) * 2 * TB + tc::sw128_offset(r, k & 63), TB, v);
 }
 
 // ---- grid barrier (monotonic counter, release / acquire at gpu scope) --------------------------------------------
 __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long target) {
+  fence_proxy_async_all();            // this thread's global stores -> ordered before later async-proxy (bulk copy) reads
   __syncthreads();
   if (threadIdx.x == 0) {
     asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(bar) : "memory");
@@ -369,50 +353,84 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned l
 // cluster items
 // =================================================================================================================
 // P1: h_e[:, 16t .. 16t+15] = tanh(x.W3 + b3)                                               VAEB.py:246
-__device__ __noinline__ void item_enc1(Ctx& c, const Params& p, const float* x, float* he, int t) {
+__device__ __forceinline__ void item_enc1(Ctx& c, const Params& p, const float* x, float* he, uint8_t* he_t, int t, bool a_staged, bool more) {
+  ST2_TRACE(c, 10);
   const int c0 = c.rank * p.KD / CL, c1 = (c.rank + 1) * p.KD / CL, nch = c1 - c0;
   constexpr int TB = TR_ENC1 * 128;
-  stage_rows_blob(c.sm, RowsSrc{x, p.D, p.M, c0 * 64, p.D, nch * 8}, nch,
-                  p.m_enc1 + ((size_t)t * p.KD + c0) * 2 * TB, nch * 2 * TB);
-  mma_run(c, nch, min(nch * 4, (p.D - c0 * 64 + 15) / 16), TB, TR_ENC1);
-  reduce_scatter(c, TR_ENC1, nch > 0);
-  const float* recv = reinterpret_cast<const float*>(c.sm + SM_RECV);
-  {
-    const int row = threadIdx.x >> 4, col = threadIdx.x & 15;
-    const int gr = c.rank * 32 + row, j = t * 16 + col;
-    if (gr < p.M) {
-      const float v = recv_sum(recv, TR_ENC1, row, col);
-      he[(size_t)gr * p.HP + j] = j < p.H ? tanhf(v + __ldcg(p.P + p.ob3 + j)) : 0.f;
-    }
+  if (threadIdx.x == 0 && nch > 0) {
+    ops_begin(c, (uint32_t)(nch * 2 * TB));
+    bulk_g2s(c.sm + SM_B, p.m_enc1 + ((size_t)t * p.KD + c0) * 2 * TB, (uint32_t)(nch * 2 * TB), c.op_bar);
   }
-  cluster_sync();
+  if (!a_staged) stage_x_rows(c.sm, x, p.D, p.M, c0, nch);
+  const int row = threadIdx.x >> 4, col = threadIdx.x & 15;
+  const int gr = c.rank * 32 + row, j = t * 16 + col;
+  const float bias = j < p.H ? __ldcg(p.P + p.ob3 + j) : 0.f;
+  ST2_TRACE(c, 11);
+  mma_run(c, nch, min(nch * 4, (p.D - c0 * 64 + 15) / 16), TB, TR_ENC1, nch > 0);
+  ST2_TRACE(c, 12);
+  reduce_scatter(c, TR_ENC1, nch > 0);
+  ST2_TRACE(c, 13);
+  const float* recv = reinterpret_cast<const float*>(c.sm + SM_RECV);
+  if (gr < p.M) {
+    const float v = j < p.H ? tanh_fast(recv_sum(recv, TR_ENC1, row, col) + bias) : 0.f;
+    he[(size_t)gr * p.HP + j] = v;
+    put_bf(km_addr(p.he_km, gr, j), TBA, v);
+    if (j < p.H) put_bf(t_addr(he_t, j >> 7, TBA, j & 127, gr), TBA, v);
+  }
+  ST2_TRACE(c, 14);
+  if (more) cluster_sync();          // the receive buffer is reused by this cluster's next item of the phase
+  else __syncthreads();
+  ST2_TRACE(c, 15);
 }
 
 // P2: (mu, ls) = h_e.[W4|W5] + b, eps, z = mu + exp(ls/2) eps, the KL / L^A row term        VAEB.py:248-249,41-47,343,322-325
-__device__ __noinline__ void item_heads(Ctx& c, const Params& p, const float* he, uint32_t step) {
+__device__ __forceinline__ void item_heads(Ctx& c, const Params& p, uint32_t step, bool more) {
   ST2_TRACE(c, 20);
   const int c0 = c.rank * p.KH / CL, c1 = (c.rank + 1) * p.KH / CL, nch = c1 - c0;
   const int TB = p.NH * 128, Z = p.Z, N = p.NH;
-  stage_rows_blob(c.sm, RowsSrc{he, p.HP, p.M, c0 * 64, p.HP, nch * 8}, nch, p.m_heads + (size_t)c0 * 2 * TB, nch * 2 * TB);
+  if (threadIdx.x == 0 && nch > 0) {
+    ops_begin(c, (uint32_t)(nch * 2 * (TBA + TB)));
+    bulk_g2s(c.sm + SM_A, p.he_km + (size_t)c0 * 2 * TBA, (uint32_t)(nch * 2 * TBA), c.op_bar);
+    bulk_g2s(c.sm + SM_B, p.m_heads + (size_t)c0 * 2 * TB, (uint32_t)(nch * 2 * TB), c.op_bar);
+  }
+  // while the operands are in flight: this thread's noise and biases (two (row, j) items per thread at most)
+  float e_[2], b4_[2], b5_[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int it = threadIdx.x + i * NT;
+    const int row = it / Z, j = it - row * Z;
+    const int gr = c.rank * 32 + row;
+    e_[i] = b4_[i] = b5_[i] = 0.f;
+    if (it < 32 * Z && gr < p.M) {
+      const size_t o = (size_t)gr * Z + j;
+      e_[i] = p.eps_inj ? __ldcg(p.eps_inj + o)
+                        : philox_normal1(p.seed, VAEB_STREAM_TRAIN, step, 0u, (uint64_t)((p.row_offset + gr) * Z + j));
+      b4_[i] = __ldcg(p.P + p.ob4 + j); b5_[i] = __ldcg(p.P + p.ob5 + j);
+    }
+  }
   ST2_TRACE(c, 21);
-  mma_run(c, nch, nch * 4, TB, N);
+  mma_run(c, nch, nch * 4, TB, N, nch > 0);
   ST2_TRACE(c, 22);
   reduce_scatter(c, N, nch > 0);
   ST2_TRACE(c, 23);
   const float* recv = reinterpret_cast<const float*>(c.sm + SM_RECV);
   float* term = reinterpret_cast<float*>(c.sm + SM_B);          // [32][Z] (the B tiles are dead)
-  for (int it = threadIdx.x; it < 32 * Z; it += NT) {
+  const int zt_half = p.NZ * 128;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int it = threadIdx.x + i * NT;
+    if (it >= 32 * Z) break;
     const int row = it / Z, j = it - row * Z;
     const int gr = c.rank * 32 + row;
     float tv = 0.f;
     if (gr < p.M) {
-      const float am = recv_sum(recv, N, row, j) + __ldcg(p.P + p.ob4 + j);
-      const float al = recv_sum(recv, N, row, Z + j) + __ldcg(p.P + p.ob5 + j);
+      const float am = recv_sum(recv, N, row, j) + b4_[i];
+      const float al = recv_sum(recv, N, row, Z + j) + b5_[i];
       const size_t o = (size_t)gr * Z + j;
-      const float e = p.eps_inj ? __ldcg(p.eps_inj + o)
-                                : philox_normal1(p.seed, VAEB_STREAM_TRAIN, step, 0u, (uint64_t)((p.row_offset + gr) * Z + j));
+      const float e = e_[i];
       const float zv = am + expf(0.5f * al) * e;
       p.mu[o] = am; p.ls[o] = al; p.eps[o] = e; p.z[o] = zv;
+      put_bf(t_addr(p.z_t, 0, zt_half, j, gr), zt_half, zv);
       tv = p.la ? (-0.5f * zv * zv + 0.5f * al + 0.5f * e * e) : 0.5f * (1.0f + al - am * am - expf(al));
     }
     term[it] = tv;
@@ -427,46 +445,51 @@ __device__ __noinline__ void item_heads(Ctx& c, const Params& p, const float* he
     }
   }
   ST2_TRACE(c, 24);
-  cluster_sync();
+  if (more) cluster_sync();          // the receive buffer is reused by this cluster's next item of the phase
+  else __syncthreads();
   ST2_TRACE(c, 25);
 }
 
 // P3: h_d = tanh(z.W1 + b1) recomputed into the A tile, a = h_d.W2 + b2, x a - softplus(a), da2 = w (x - sigmoid a)
 //                                                                                           VAEB.py:254,263,311
-__device__ __noinline__ void item_dec2(Ctx& c, const Params& p, const float* x, int t) {
+__device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* x, int t, bool more) {
+  ST2_TRACE(c, 30);
   const int c0 = c.rank * p.KH / CL, c1 = (c.rank + 1) * p.KH / CL, nch = c1 - c0;
   constexpr int TB = TR_DEC2 * 128;
   const int Z = p.Z, H = p.H, M = p.M;
   float* zs = reinterpret_cast<float*>(c.sm + SM_SCR);          // [MP][Z]
   float* ws = zs + MP * Z;                                      // [Z][64]
   float* bs = ws + Z * 64;                                      // [64]
+  if (threadIdx.x == 0 && nch > 0) {
+    ops_begin(c, (uint32_t)(nch * 2 * TB));
+    bulk_g2s(c.sm + SM_B, p.m_dec2 + ((size_t)t * p.KH + c0) * 2 * TB, (uint32_t)(nch * 2 * TB), c.op_bar);
+  }
   {
-    // z and the mirror blob: all loads first (one L2 round trip), then the shared-memory stores
-    float zr[6]; uint4 bl[4];
-    const uint8_t* blob = p.m_dec2 + ((size_t)t * p.KH + c0) * 2 * TB;
-    const int bbytes = nch * 2 * TB;
+    float zr[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const int e = threadIdx.x + i * NT;
       zr[i] = e < M * Z ? __ldcg(p.z + e) : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int o = (threadIdx.x + i * NT) * 16;
-      bl[i] = o < bbytes ? __ldcg(reinterpret_cast<const uint4*>(blob + o)) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
     for (int i = 0; i < 6; ++i)
       if ((int)threadIdx.x + i * NT < MP * Z) zs[threadIdx.x + i * NT] = zr[i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int o = (threadIdx.x + i * NT) * 16;
-      if (o < bbytes) *reinterpret_cast<uint4*>(c.sm + SM_B + o) = bl[i];
-    }
   }
+  // this thread's two elements of the final stage: x and the output bias (in flight during the producer and the MMAs)
+  float xv_[2], b2_[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int it = threadIdx.x + i * NT;
+    const int gr = c.rank * 32 + (it >> 5), n = t * TR_DEC2 + (it & 31);
+    const bool ok = gr < M && n < p.D;
+    xv_[i] = ok ? __ldcg(x + (size_t)gr * p.D + n) : 0.f;
+    b2_[i] = ok ? __ldcg(p.P + p.ob2 + n) : 0.f;
+  }
+  ST2_TRACE(c, 36);
   for (int ci = 0; ci < nch; ++ci) {
     const int k0 = (c0 + ci) * 64;
     __syncthreads();
+    ST2_TRACE(c, 37);
     {
       float wr[3]; float br = 0.f;
 #pragma unroll
@@ -482,50 +505,56 @@ __device__ __noinline__ void item_dec2(Ctx& c, const Params& p, const float* x, 
       if (threadIdx.x < 64) bs[threadIdx.x] = br;
     }
     __syncthreads();
-    for (int u = threadIdx.x; u < M * 8; u += NT) {
+    ST2_TRACE(c, 38);
+    for (int u = threadIdx.x; u < MP * 8; u += NT) {
       const int r = u >> 3, cu = u & 7;
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = bs[cu * 8 + e];
-      for (int q = 0; q < Z; ++q) {
-        const float zq = zs[r * Z + q];
-        const float4 w0 = *reinterpret_cast<const float4*>(ws + q * 64 + cu * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(ws + q * 64 + cu * 8 + 4);
-        v[0] = fmaf(zq, w0.x, v[0]); v[1] = fmaf(zq, w0.y, v[1]); v[2] = fmaf(zq, w0.z, v[2]); v[3] = fmaf(zq, w0.w, v[3]);
-        v[4] = fmaf(zq, w1.x, v[4]); v[5] = fmaf(zq, w1.y, v[5]); v[6] = fmaf(zq, w1.z, v[6]); v[7] = fmaf(zq, w1.w, v[7]);
+      if (r < M) {
+        for (int q = 0; q < Z; ++q) {
+          const float zq = zs[r * Z + q];
+          const float4 w0 = *reinterpret_cast<const float4*>(ws + q * 64 + cu * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(ws + q * 64 + cu * 8 + 4);
+          v[0] = fmaf(zq, w0.x, v[0]); v[1] = fmaf(zq, w0.y, v[1]); v[2] = fmaf(zq, w0.z, v[2]); v[3] = fmaf(zq, w0.w, v[3]);
+          v[4] = fmaf(zq, w1.x, v[4]); v[5] = fmaf(zq, w1.y, v[5]); v[6] = fmaf(zq, w1.z, v[6]); v[7] = fmaf(zq, w1.w, v[7]);
+        }
       }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = (k0 + cu * 8 + e < H) ? tanh_fast(v[e]) : 0.f;
-      if (t == 0) {                                              // the cluster of tile 0 publishes h_d for P4 / P5
+      for (int e = 0; e < 8; ++e) v[e] = (r < M && k0 + cu * 8 + e < H) ? tanh_fast(v[e]) : 0.f;
+      if (r < M && r % p.n_tiles3 == t) {                        // every cluster publishes a few rows of h_d for P4 / P5
         float* o = p.hd + (size_t)r * p.HP + k0 + cu * 8;
         *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = k0 + cu * 8 + e;
+          if (k < H) put_bf(t_addr(p.hd_t, k >> 7, TBA, k & 127, r), TBA, v[e]);
+        }
       }
-      uint4 hi, lo;
-      split8(v, hi, lo);
-      uint8_t* d = c.sm + SM_A + (size_t)ci * 2 * TBA + unit_off(r, cu);
-      *reinterpret_cast<uint4*>(d) = hi;
-      *reinterpret_cast<uint4*>(d + TBA) = lo;
+      put_unit(c.sm + SM_A + (size_t)ci * 2 * TBA + unit_off(r, cu), TBA, v);
     }
+    ST2_TRACE(c, 39);
   }
-  for (int u = M * 8 * nch + threadIdx.x; u < MP * 8 * nch; u += NT) {      // rows >= M of the A tile: zeros
-    const int r = M + (u - M * 8 * nch) / (8 * nch), ku = (u - M * 8 * nch) % (8 * nch);
-    uint8_t* d = c.sm + SM_A + (size_t)(ku >> 3) * 2 * TBA + unit_off(r, ku & 7);
-    *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(d + TBA) = make_uint4(0, 0, 0, 0);
-  }
-  mma_run(c, nch, nch * 4, TB, TR_DEC2);
+  ST2_TRACE(c, 31);
+  mma_run(c, nch, nch * 4, TB, TR_DEC2, nch > 0);
+  ST2_TRACE(c, 32);
   reduce_scatter(c, TR_DEC2, nch > 0);
+  ST2_TRACE(c, 33);
   const float* recv = reinterpret_cast<const float*>(c.sm + SM_RECV);
   float* term = reinterpret_cast<float*>(c.sm + SM_B);          // [32][32]
-  for (int it = threadIdx.x; it < 32 * TR_DEC2; it += NT) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int it = threadIdx.x + i * NT;
     const int row = it >> 5, col = it & 31;
     const int gr = c.rank * 32 + row, n = t * TR_DEC2 + col;
     float tv = 0.f;
     if (gr < M && n < p.D) {
-      const float a = recv_sum(recv, TR_DEC2, row, col) + __ldcg(p.P + p.ob2 + n);
-      const float xv = __ldcg(x + (size_t)gr * p.D + n);
-      p.da2[(size_t)gr * p.D + n] = p.w * (xv - sigmoidf_(a));
+      const float a = recv_sum(recv, TR_DEC2, row, col) + b2_[i];
+      const float xv = xv_[i];
+      const float d = p.w * (xv - sigmoidf_(a));
+      put_bf(km_addr(p.da2_km, gr, n), TBA, d);
+      put_bf(t_addr(p.da2_t, t, TB, col, gr), TB, d);
       tv = xv * a - softplusf_(a);
     }
     term[it] = tv;
@@ -539,64 +568,98 @@ __device__ __noinline__ void item_dec2(Ctx& c, const Params& p, const float* x, 
       p.partial[(size_t)gr * p.n_tiles3 + t] = s;
     }
   }
-  cluster_sync();
+  ST2_TRACE(c, 34);
+  if (more) cluster_sync();          // the receive buffer is reused by this cluster's next item of the phase
+  else __syncthreads();
+  ST2_TRACE(c, 35);
 }
 
 // P4: da1[:, 16t..] = (da2.W2^T) * (1 - h_d^2)                                              T.grad, VAEB.py:397
-__device__ __noinline__ void item_dgrad(Ctx& c, const Params& p, int t) {
+__device__ __forceinline__ void item_dgrad(Ctx& c, const Params& p, int t, bool more) {
   ST2_TRACE(c, 40);
   const int c0 = c.rank * p.KD / CL, c1 = (c.rank + 1) * p.KD / CL, nch = c1 - c0;
   constexpr int TB = TR_DGRAD * 128;
-  stage_rows_blob(c.sm, RowsSrc{p.da2, p.D, p.M, c0 * 64, p.D, nch * 8}, nch,
-                  p.m_dgrad + ((size_t)t * p.KD + c0) * 2 * TB, nch * 2 * TB);
+  if (threadIdx.x == 0 && nch > 0) {
+    ops_begin(c, (uint32_t)(nch * 2 * (TBA + TB)));
+    bulk_g2s(c.sm + SM_A, p.da2_km + (size_t)c0 * 2 * TBA, (uint32_t)(nch * 2 * TBA), c.op_bar);
+    bulk_g2s(c.sm + SM_B, p.m_dgrad + ((size_t)t * p.KD + c0) * 2 * TB, (uint32_t)(nch * 2 * TB), c.op_bar);
+  }
+  const int row = threadIdx.x >> 4, col = threadIdx.x & 15;
+  const int gr = c.rank * 32 + row, j = t * 16 + col;
+  const float hv = gr < p.M ? __ldcg(p.hd + (size_t)gr * p.HP + j) : 0.f;
   ST2_TRACE(c, 41);
-  mma_run(c, nch, min(nch * 4, (p.D - c0 * 64 + 15) / 16), TB, TR_DGRAD);
+  mma_run(c, nch, min(nch * 4, (p.D - c0 * 64 + 15) / 16), TB, TR_DGRAD, nch > 0);
   ST2_TRACE(c, 42);
   reduce_scatter(c, TR_DGRAD, nch > 0);
   ST2_TRACE(c, 43);
   const float* recv = reinterpret_cast<const float*>(c.sm + SM_RECV);
-  {
-    const int row = threadIdx.x >> 4, col = threadIdx.x & 15;
-    const int gr = c.rank * 32 + row, j = t * 16 + col;
-    if (gr < p.M) {
-      const size_t o = (size_t)gr * p.HP + j;
-      const float hv = __ldcg(p.hd + o);
-      p.da1[o] = recv_sum(recv, TR_DGRAD, row, col) * (1.0f - hv * hv);
-    }
+  if (gr < p.M) {
+    const float d = recv_sum(recv, TR_DGRAD, row, col) * (1.0f - hv * hv);
+    put_bf(km_addr(p.da1_km, gr, j), TBA, d);
+    if (j < p.H) put_bf(t_addr(p.da1_t, j >> 7, TBA, j & 127, gr), TBA, d);
   }
   ST2_TRACE(c, 44);
-  cluster_sync();
+  if (more) cluster_sync();          // the receive buffer is reused by this cluster's next item of the phase
+  else __syncthreads();
   ST2_TRACE(c, 45);
 }
 
 // P5: dz = da1.W1^T -> dmu, dls (SURVEY.md 8a backward formulas)
-__device__ __noinline__ void item_dz(Ctx& c, const Params& p) {
+__device__ __forceinline__ void item_dz(Ctx& c, const Params& p, bool more) {
+  ST2_TRACE(c, 50);
   const int c0 = c.rank * p.KH / CL, c1 = (c.rank + 1) * p.KH / CL, nch = c1 - c0;
   const int TB = p.NZ * 128, Z = p.Z, N = p.NZ;
-  stage_rows_blob(c.sm, RowsSrc{p.da1, p.HP, p.M, c0 * 64, p.HP, nch * 8}, nch, p.m_dz + (size_t)c0 * 2 * TB, nch * 2 * TB);
-  mma_run(c, nch, nch * 4, TB, N);
+  if (threadIdx.x == 0 && nch > 0) {
+    ops_begin(c, (uint32_t)(nch * 2 * (TBA + TB)));
+    bulk_g2s(c.sm + SM_A, p.da1_km + (size_t)c0 * 2 * TBA, (uint32_t)(nch * 2 * TBA), c.op_bar);
+    bulk_g2s(c.sm + SM_B, p.m_dz + (size_t)c0 * 2 * TB, (uint32_t)(nch * 2 * TB), c.op_bar);
+  }
+  float ls_[2], ev_[2], zm_[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int it = threadIdx.x + i * NT;
+    const int row = it / Z, j = it - row * Z;
+    const int gr = c.rank * 32 + row;
+    ls_[i] = ev_[i] = zm_[i] = 0.f;
+    if (it < 32 * Z && gr < p.M) {
+      const size_t o = (size_t)gr * Z + j;
+      ls_[i] = __ldcg(p.ls + o); ev_[i] = __ldcg(p.eps + o);
+      zm_[i] = p.la ? __ldcg(p.z + o) : __ldcg(p.mu + o);
+    }
+  }
+  ST2_TRACE(c, 51);
+  mma_run(c, nch, nch * 4, TB, N, nch > 0);
+  ST2_TRACE(c, 52);
   reduce_scatter(c, N, nch > 0);
+  ST2_TRACE(c, 53);
   const float* recv = reinterpret_cast<const float*>(c.sm + SM_RECV);
-  for (int it = threadIdx.x; it < 32 * Z; it += NT) {
+  const int ddt_half = p.NH * 128;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int it = threadIdx.x + i * NT;
+    if (it >= 32 * Z) break;
     const int row = it / Z, j = it - row * Z;
     const int gr = c.rank * 32 + row;
     if (gr < p.M) {
-      const size_t o = (size_t)gr * Z + j;
-      const float lsv = __ldcg(p.ls + o), ev = __ldcg(p.eps + o);
       float d = recv_sum(recv, N, row, j);
-      if (p.la) d -= p.w * __ldcg(p.z + o);
-      float a = d, b = d * (0.5f * expf(0.5f * lsv) * ev);
+      if (p.la) d -= p.w * zm_[i];
+      float a = d, b = d * (0.5f * expf(0.5f * ls_[i]) * ev_[i]);
       if (p.la) {
         b += p.w * 0.5f;
       } else {
-        a -= p.w * __ldcg(p.mu + o);
-        b += p.w * 0.5f * (1.0f - expf(lsv));
+        a -= p.w * zm_[i];
+        b += p.w * 0.5f * (1.0f - expf(ls_[i]));
       }
       p.dd[(size_t)gr * 2 * Z + j] = a;
       p.dd[(size_t)gr * 2 * Z + Z + j] = b;
+      put_bf(t_addr(p.dd_t, 0, ddt_half, j, gr), ddt_half, a);
+      put_bf(t_addr(p.dd_t, 0, ddt_half, Z + j, gr), ddt_half, b);
     }
   }
-  cluster_sync();
+  ST2_TRACE(c, 54);
+  if (more) cluster_sync();          // the receive buffer is reused by this cluster's next item of the phase
+  else __syncthreads();
+  ST2_TRACE(c, 55);
 }
 
 // =================================================================================================================
@@ -613,15 +676,20 @@ __device__ __forceinline__ void wgrad_epilogue(Ctx& c, int N, F fn) {
     fn(q * 32 + c.lane, u * 8, v);
   }
   tc::tc_fence_before();
+  __syncthreads();
 }
 
 // W2, b2 <- Adagrad([h_d | 1]^T . da2); tile = 128 hidden units x 32 pixels
-__device__ __noinline__ void item_wg2(Ctx& c, const Params& p, const Hyper& hy, int mt, int nt) {
-  {
-    const TSrc b{p.da2, TR_DEC2, p.D, p.M, nt * TR_DEC2, p.D, -1};
-    stage_T(c.sm, TSrc{p.hd, MP, p.HP, p.M, mt * MP, p.H, p.H}, &b);
+__device__ __forceinline__ void item_wg2(Ctx& c, const Params& p, const Hyper& hy, int mt, int nt) {
+  ST2_TRACE(c, 60);
+  constexpr int TB = TR_DEC2 * 128;
+  if (threadIdx.x == 0) {
+    ops_begin(c, (uint32_t)(4 * TBA + 4 * TB));
+    bulk_g2s(c.sm + SM_A, p.hd_t + (size_t)mt * 4 * TBA, (uint32_t)(4 * TBA), c.op_bar);
+    bulk_g2s(c.sm + SM_B, p.da2_t + (size_t)nt * 4 * TB, (uint32_t)(4 * TB), c.op_bar);
   }
-  mma_run(c, 2, (p.M + 15) / 16, TR_DEC2 * 128, TR_DEC2);
+  mma_run(c, 2, (p.M + 15) / 16, TB, TR_DEC2, true);
+  ST2_TRACE(c, 61);
   const int H = p.H, D = p.D;
   wgrad_epilogue(c, TR_DEC2, [&](int row, int col0, const float* v) {
     const int i = mt * MP + row, n0 = nt * TR_DEC2 + col0;
@@ -636,35 +704,61 @@ __device__ __noinline__ void item_wg2(Ctx& c, const Params& p, const Hyper& hy, 
     if (i < H) {
 #pragma unroll
       for (int e = 0; e < 8; ++e)
-        if (ok[e]) mirror_put(p.m_dec2, TR_DEC2, p.KH, n0 + e, i, nv[e]);
+        if (ok[e]) mirror_put(p.m_dec2, TR_DEC2, p.KH, nt, col0 + e, i, nv[e]);
         else nv[e] = 0.f;
       // dgrad mirror: row = hidden unit i, k = pixel: eight consecutive k = one 16-byte unit (n0 is a multiple of 8)
-      constexpr int TB = TR_DGRAD * 128;
-      put_unit(p.m_dgrad + ((size_t)(i / TR_DGRAD) * p.KD + (n0 >> 6)) * 2 * TB + unit_off(i % TR_DGRAD, (n0 & 63) >> 3), TB, nv);
+      constexpr int TG = TR_DGRAD * 128;
+      put_unit(p.m_dgrad + ((size_t)(i >> 4) * p.KD + (n0 >> 6)) * 2 * TG + unit_off(i & 15, (n0 & 63) >> 3), TG, nv);
     }
   });
+  ST2_TRACE(c, 62);
 }
 
 // W3, b3 <- Adagrad([x | 1]^T . da3), da3 = ([dmu|dls].[W4|W5]^T) * (1 - h_e^2) recomputed into the B tile;
 // tile = 128 pixels x 32 hidden units
-__device__ __noinline__ void item_wg3(Ctx& c, const Params& p, const Hyper& hy, const float* x, const float* he, int mt, int nt) {
+__device__ __forceinline__ void item_wg3(Ctx& c, const Params& p, const Hyper& hy, const float* x, const float* he, int mt, int nt,
+                                      bool a_staged) {
+  ST2_TRACE(c, 70);
   const int Z = p.Z, Z2 = 2 * p.Z, H = p.H, M = p.M, D = p.D;
-  stage_T(c.sm, TSrc{x, MP, D, M, mt * MP, D, D}, nullptr);
   float* dds = reinterpret_cast<float*>(c.sm + SM_SCR);         // [M][2Z]  (scratch region + receive buffer: 48 KB)
   float* w45 = dds + MP * Z2;                                   // [32][2Z + 1]
-  for (int i = threadIdx.x; i < M * Z2; i += NT) dds[i] = __ldcg(p.dd + i);
-  for (int i = threadIdx.x; i < 32 * Z2; i += NT) {
-    const int jj = i / Z2, q = i - jj * Z2;
-    const int j = nt * 32 + jj;
-    float t = 0.f;
-    if (j < H) t = q < Z ? __ldcg(p.P + p.oW4 + (size_t)j * Z + q) : __ldcg(p.P + p.oW5 + (size_t)j * Z + q - Z);
-    w45[jj * (Z2 + 1) + q] = t;
+  {
+    // [dmu|dls] and the 32 rows of [W4|W5] this tile needs: loads first, stores second
+    float dr[12], wr[3];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const int e = threadIdx.x + i * NT;
+      dr[i] = e < M * Z2 ? __ldcg(p.dd + e) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int e = threadIdx.x + i * NT;
+      const int jj = e / Z2, q = e - jj * Z2;
+      const int j = nt * 32 + jj;
+      wr[i] = 0.f;
+      if (e < 32 * Z2 && j < H) wr[i] = q < Z ? __ldcg(p.P + p.oW4 + (size_t)j * Z + q) : __ldcg(p.P + p.oW5 + (size_t)j * Z + q - Z);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i)
+      if ((int)threadIdx.x + i * NT < M * Z2) dds[threadIdx.x + i * NT] = dr[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int e = threadIdx.x + i * NT;
+      if (e < 32 * Z2) w45[(e / Z2) * (Z2 + 1) + (e % Z2)] = wr[i];
+    }
+  }
+  if (!a_staged) stage_x_T(c.sm, x, D, M, mt * MP);
+  const int jj = threadIdx.x & 31, bo = threadIdx.x >> 5;        // 32 hidden units x 16 batch octets
+  const int j = nt * 32 + jj;
+  float hv[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int b = bo * 8 + e;
+    hv[e] = (b < M && j < H) ? __ldcg(he + (size_t)b * p.HP + j) : 0.f;
   }
   __syncthreads();
   {
     constexpr int TB = 32 * 128;
-    const int jj = threadIdx.x & 31, bo = threadIdx.x >> 5;      // 32 hidden units x 16 batch octets
-    const int j = nt * 32 + jj;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -673,18 +767,15 @@ __device__ __noinline__ void item_wg3(Ctx& c, const Params& p, const Hyper& hy, 
       if (b < M && j < H) {
         float s = 0.f;
         for (int q = 0; q < Z2; ++q) s = fmaf(dds[b * Z2 + q], w45[jj * (Z2 + 1) + q], s);
-        const float hv = __ldcg(he + (size_t)b * p.HP + j);
-        t = s * (1.0f - hv * hv);
+        t = s * (1.0f - hv[e] * hv[e]);
       }
       v[e] = t;
     }
-    uint4 hi, lo;
-    split8(v, hi, lo);
-    uint8_t* d = c.sm + SM_B + (size_t)(bo >> 3) * 2 * TB + unit_off(jj, bo & 7);
-    *reinterpret_cast<uint4*>(d) = hi;
-    *reinterpret_cast<uint4*>(d + TB) = lo;
+    put_unit(c.sm + SM_B + (size_t)(bo >> 3) * 2 * TB + unit_off(jj, bo & 7), TB, v);
   }
-  mma_run(c, 2, (M + 15) / 16, 32 * 128, 32);
+  ST2_TRACE(c, 71);
+  mma_run(c, 2, (M + 15) / 16, 32 * 128, 32, false);
+  ST2_TRACE(c, 72);
   wgrad_epilogue(c, 32, [&](int row, int col0, const float* v) {
     const int i = mt * MP + row, j0 = nt * 32 + col0;
     if (i > D || j0 >= H) return;
@@ -698,19 +789,22 @@ __device__ __noinline__ void item_wg3(Ctx& c, const Params& p, const Hyper& hy, 
     if (i < D) {
 #pragma unroll
       for (int e = 0; e < 8; ++e)
-        if (ok[e]) mirror_put(p.m_enc1, TR_ENC1, p.KD, j0 + e, i, nv[e]);
+        if (ok[e]) mirror_put(p.m_enc1, TR_ENC1, p.KD, (j0 + e) >> 4, (j0 + e) & 15, i, nv[e]);
     }
   });
+  ST2_TRACE(c, 73);
 }
 
 // W1, b1 <- Adagrad([z | 1]^T . da1), computed transposed: tile = 128 hidden units x (Z + 1) latent columns
-__device__ __noinline__ void item_wg1(Ctx& c, const Params& p, const Hyper& hy, int mt) {
+__device__ __forceinline__ void item_wg1(Ctx& c, const Params& p, const Hyper& hy, int mt) {
   const int Z = p.Z, H = p.H, N = p.NZ;
-  {
-    const TSrc b{p.z, N, Z, p.M, 0, Z, Z};
-    stage_T(c.sm, TSrc{p.da1, MP, p.HP, p.M, mt * MP, H, -1}, &b);
+  const int TB = N * 128;
+  if (threadIdx.x == 0) {
+    ops_begin(c, (uint32_t)(4 * TBA + 4 * TB));
+    bulk_g2s(c.sm + SM_A, p.da1_t + (size_t)mt * 4 * TBA, (uint32_t)(4 * TBA), c.op_bar);
+    bulk_g2s(c.sm + SM_B, p.z_t, (uint32_t)(4 * TB), c.op_bar);
   }
-  mma_run(c, 2, (p.M + 15) / 16, N * 128, N);
+  mma_run(c, 2, (p.M + 15) / 16, TB, N, true);
   wgrad_epilogue(c, N, [&](int row, int col0, const float* v) {
     const int i = mt * MP + row;
     if (i >= H || col0 > Z) return;
@@ -724,18 +818,20 @@ __device__ __noinline__ void item_wg1(Ctx& c, const Params& p, const Hyper& hy, 
     adagrad8(p.P, p.ada, off, ok, v, hy, nv);
 #pragma unroll
     for (int e = 0; e < 8; ++e)
-      if (col0 + e < Z) mirror_put(p.m_dz, N, p.KH, col0 + e, i, nv[e]);
+      if (col0 + e < Z) mirror_put(p.m_dz, N, p.KH, 0, col0 + e, i, nv[e]);
   });
 }
 
 // W4, b4, W5, b5 <- Adagrad([h_e | 1]^T . [dmu | dls]); tile = 128 hidden units x 2Z
-__device__ __noinline__ void item_wg45(Ctx& c, const Params& p, const Hyper& hy, const float* he, int mt) {
+__device__ __forceinline__ void item_wg45(Ctx& c, const Params& p, const Hyper& hy, const uint8_t* he_t, int mt) {
   const int Z = p.Z, H = p.H, N = p.NH;
-  {
-    const TSrc b{p.dd, N, 2 * Z, p.M, 0, 2 * Z, -1};
-    stage_T(c.sm, TSrc{he, MP, p.HP, p.M, mt * MP, H, H}, &b);
+  const int TB = N * 128;
+  if (threadIdx.x == 0) {
+    ops_begin(c, (uint32_t)(4 * TBA + 4 * TB));
+    bulk_g2s(c.sm + SM_A, he_t + (size_t)mt * 4 * TBA, (uint32_t)(4 * TBA), c.op_bar);
+    bulk_g2s(c.sm + SM_B, p.dd_t, (uint32_t)(4 * TB), c.op_bar);
   }
-  mma_run(c, 2, (p.M + 15) / 16, N * 128, N);
+  mma_run(c, 2, (p.M + 15) / 16, TB, N, true);
   wgrad_epilogue(c, N, [&](int row, int col0, const float* v) {
     const int i = mt * MP + row;
     if (i > H || col0 >= 2 * Z) return;
@@ -752,13 +848,13 @@ __device__ __noinline__ void item_wg45(Ctx& c, const Params& p, const Hyper& hy,
     if (i < H) {
 #pragma unroll
       for (int e = 0; e < 8; ++e)
-        if (ok[e]) mirror_put(p.m_heads, N, p.KH, col0 + e, i, nv[e]);
+        if (ok[e]) mirror_put(p.m_heads, N, p.KH, 0, col0 + e, i, nv[e]);
     }
   });
 }
 
 // the bound of step s: fixed-order sum of the row partials (VAEB.py:340-344) / Mg
-__device__ __noinline__ void item_bound(Ctx& c, const Params& p, int s) {
+__device__ __forceinline__ void item_bound(Ctx& c, const Params& p, int s) {
   float* red = reinterpret_cast<float*>(c.sm + SM_MISC + 256);
   float t = 0.f;
   for (int r = threadIdx.x; r < p.M; r += NT) {
@@ -781,17 +877,18 @@ __device__ __noinline__ void item_bound(Ctx& c, const Params& p, int s) {
 
 // =================================================================================================================
 __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ Params p) {
-  extern __shared__ uint8_t smem_raw[];
   Ctx c;
-  c.sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  c.sm = smem_base();
   c.mma_bar = reinterpret_cast<uint64_t*>(c.sm + SM_MISC);
+  c.op_bar = c.mma_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.sm + SM_MISC + 16);
-  c.mma_phase = 0;
+  c.mma_phase = 0; c.op_phase = 0;
   c.rank = (int)cluster_ctarank(); c.cid = (int)cluster_idx(); c.ncl = (int)cluster_count();
   c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
   c.trace = nullptr; c.tn = 0;
   if (threadIdx.x == 0) {
     tc::mbar_init(c.mma_bar, 1);
+    tc::mbar_init(c.op_bar, 1);
     tc::fence_barrier_init();
   }
   if (c.warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -811,13 +908,22 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
   const int m_h = (p.H + MP - 1) / MP;
   const int m_d1 = (p.D + 1 + MP - 1) / MP;
   const int n_h32 = p.HP / 32;
+  const int n3w = m_d1 * n_h32;                     // W3 gradient tiles
+  const size_t he_t_bytes = (size_t)m_h1 * 4 * TBA;
   // a phase's item list: cluster items first, then CTA items in groups of four (one per rank of a cluster)
   auto n_groups = [](int n_cta_items) { return (n_cta_items + CL - 1) / CL; };
+  auto x_of = [&](int s) { return p.batch_order ? p.x_base + (size_t)__ldg(p.batch_order + s) * p.M * p.D : p.x_direct; };
+  const int kd0 = c.rank * p.KD / CL, kdn = (c.rank + 1) * p.KD / CL - kd0;
+
+  // the A tile of this CTA's first enc1 item is staged ahead of the barrier that opens P1 (x depends on nothing)
+  bool p1_staged = false;
+  if (c.cid < n1) { stage_x_rows(c.sm, x_of(0), p.D, p.M, kd0, kdn); p1_staged = true; }
 
   for (int s = 0; s < p.n_steps; ++s) {
-    const float* x = p.batch_order ? p.x_base + (size_t)__ldg(p.batch_order + s) * p.M * p.D : p.x_direct;
+    const float* x = x_of(s);
     float* he = p.he + (size_t)(s & 1) * MP * p.HP;              // double buffered: the W4/W5 update of step s runs in P1 of s+1
-    const float* he_prev = p.he + (size_t)((s & 1) ^ 1) * MP * p.HP;
+    uint8_t* he_t = p.he_t + (size_t)(s & 1) * he_t_bytes;
+    const uint8_t* he_t_prev = p.he_t + (size_t)((s & 1) ^ 1) * he_t_bytes;
     long long* tm = rec ? p.timing + (size_t)s * (N_PHASES + 1) : nullptr;
     if (tm) tm[0] = gtime();
     if (p.timing && blockIdx.x == 0 && s == p.n_steps - 1) c.trace = p.timing + (size_t)p.n_steps * (N_PHASES + 1);
@@ -826,29 +932,30 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     {
       const int n45 = s > 0 ? m_h1 : 0;
       for (int it = c.cid; it < n1 + n_groups(n45); it += c.ncl) {
-        if (it < n1) { item_enc1(c, p, x, he, it); continue; }
+        if (it < n1) { item_enc1(c, p, x, he, he_t, it, p1_staged && it == c.cid, it + c.ncl < n1); continue; }
         const int i = (it - n1) * CL + c.rank;
-        if (i < n45) item_wg45(c, p, hy, he_prev, i);
+        if (i < n45) item_wg45(c, p, hy, he_t_prev, i);
       }
+      p1_staged = false;
     }
     ST2_TRACE(c, 81);
     grid_barrier(p.bar, target += G);
     if (tm) tm[1] = gtime();
     ST2_TRACE(c, 91);
     // ---- P2: latent heads ------------------------------------------------------------------------------------
-    if (c.cid == 0) item_heads(c, p, he, p.step0 + (uint32_t)s);
+    if (c.cid == 0) item_heads(c, p, p.step0 + (uint32_t)s, false);
     ST2_TRACE(c, 82);
     grid_barrier(p.bar, target += G);
     if (tm) tm[2] = gtime();
     ST2_TRACE(c, 92);
     // ---- P3: decoder + log-likelihood ------------------------------------------------------------------------
-    for (int it = c.cid; it < n3; it += c.ncl) item_dec2(c, p, x, it);
+    for (int it = c.cid; it < n3; it += c.ncl) item_dec2(c, p, x, it, it + c.ncl < n3);
     ST2_TRACE(c, 83);
     grid_barrier(p.bar, target += G);
     if (tm) tm[3] = gtime();
     ST2_TRACE(c, 93);
     // ---- P4: back through the decoder output layer ---------------------------------------------------------------
-    for (int it = c.cid; it < n1; it += c.ncl) item_dgrad(c, p, it);
+    for (int it = c.cid; it < n1; it += c.ncl) item_dgrad(c, p, it, it + c.ncl < n1);
     ST2_TRACE(c, 84);
     grid_barrier(p.bar, target += G);
     if (tm) tm[4] = gtime();
@@ -857,25 +964,29 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     {
       const int n2 = m_h1 * n3;
       for (int it = c.cid; it < 1 + n_groups(n2 + 1); it += c.ncl) {
-        if (it == 0) { item_dz(c, p); continue; }
+        if (it == 0) { item_dz(c, p, false); continue; }
         const int i = (it - 1) * CL + c.rank;
         if (i < n2) item_wg2(c, p, hy, i / n3, i % n3);
         else if (i == n2) item_bound(c, p, s);
       }
     }
+    // the A tile (x^T) of this CTA's first W3-gradient item, staged ahead of the barrier that opens P6
+    const int i6 = c.cid * CL + c.rank;
+    const bool p6_staged = i6 < n3w;
+    if (p6_staged) stage_x_T(c.sm, x, p.D, p.M, (i6 / n_h32) * MP);
     ST2_TRACE(c, 85);
     grid_barrier(p.bar, target += G);
     if (tm) tm[5] = gtime();
     ST2_TRACE(c, 95);
     // ---- P6: W3 update | W1 update ---------------------------------------------------------------------------------
     {
-      const int n3w = m_d1 * n_h32;
       for (int it = c.cid; it < n_groups(n3w + m_h); it += c.ncl) {
         const int i = it * CL + c.rank;
-        if (i < n3w) item_wg3(c, p, hy, x, he, i / n_h32, i % n_h32);
+        if (i < n3w) item_wg3(c, p, hy, x, he, i / n_h32, i % n_h32, p6_staged && it == c.cid);
         else if (i < n3w + m_h) item_wg1(c, p, hy, i - n3w);
       }
     }
+    if (s + 1 < p.n_steps && c.cid < n1) { stage_x_rows(c.sm, x_of(s + 1), p.D, p.M, kd0, kdn); p1_staged = true; }
     ST2_TRACE(c, 86);
     grid_barrier(p.bar, target += G);
     if (tm) tm[6] = gtime();
@@ -883,10 +994,10 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
   }
   // ---- tail: the W4, W5 update of the last step (nothing else runs: no barrier needed after it) ---------------------
   {
-    const float* he_last = p.he + (size_t)((p.n_steps - 1) & 1) * MP * p.HP;
+    const uint8_t* he_t_last = p.he_t + (size_t)((p.n_steps - 1) & 1) * he_t_bytes;
     for (int it = c.cid; it < n_groups(m_h1); it += c.ncl) {
       const int i = it * CL + c.rank;
-      if (i < m_h1) item_wg45(c, p, hy, he_last, i);
+      if (i < m_h1) item_wg45(c, p, hy, he_t_last, i);
     }
   }
   tc::tc_fence_before();
@@ -909,7 +1020,7 @@ __global__ void __launch_bounds__(256) build_mirrors_kernel(MirrorArgs a) {
       const int K = a.KD * 64;
       if (i >= (int64_t)a.HP * K) return;
       const int n = (int)(i / K), k = (int)(i % K);
-      mirror_put(a.m_enc1, TR_ENC1, a.KD, n, k, (n < H && k < D) ? a.P[a.oW3 + (size_t)k * H + n] : 0.f);
+      mirror_put(a.m_enc1, TR_ENC1, a.KD, n / TR_ENC1, n % TR_ENC1, k, (n < H && k < D) ? a.P[a.oW3 + (size_t)k * H + n] : 0.f);
       break;
     }
     case 1: {   // heads: n = [W4 cols | W5 cols] (NH rows), k = hidden
@@ -918,31 +1029,43 @@ __global__ void __launch_bounds__(256) build_mirrors_kernel(MirrorArgs a) {
       const int n = (int)(i / K), k = (int)(i % K);
       float v = 0.f;
       if (k < H && n < 2 * Z) v = n < Z ? a.P[a.oW4 + (size_t)k * Z + n] : a.P[a.oW5 + (size_t)k * Z + n - Z];
-      mirror_put(a.m_heads, a.NH, a.KH, n, k, v);
+      mirror_put(a.m_heads, a.NH, a.KH, 0, n, k, v);
       break;
     }
     case 2: {   // dec2: n = pixel (tiles of 32), k = hidden
       const int K = a.KH * 64, NR = (D + TR_DEC2 - 1) / TR_DEC2 * TR_DEC2;
       if (i >= (int64_t)NR * K) return;
       const int n = (int)(i / K), k = (int)(i % K);
-      mirror_put(a.m_dec2, TR_DEC2, a.KH, n, k, (n < D && k < H) ? a.P[a.oW2 + (size_t)k * D + n] : 0.f);
+      mirror_put(a.m_dec2, TR_DEC2, a.KH, n / TR_DEC2, n % TR_DEC2, k, (n < D && k < H) ? a.P[a.oW2 + (size_t)k * D + n] : 0.f);
       break;
     }
     case 3: {   // dgrad: n = hidden (HP rows), k = pixel
       const int K = a.KD * 64;
       if (i >= (int64_t)a.HP * K) return;
       const int n = (int)(i / K), k = (int)(i % K);
-      mirror_put(a.m_dgrad, TR_DGRAD, a.KD, n, k, (n < H && k < D) ? a.P[a.oW2 + (size_t)n * D + k] : 0.f);
+      mirror_put(a.m_dgrad, TR_DGRAD, a.KD, n / TR_DGRAD, n % TR_DGRAD, k, (n < H && k < D) ? a.P[a.oW2 + (size_t)n * D + k] : 0.f);
       break;
     }
     default: {  // dz: n = latent (NZ rows), k = hidden
       const int K = a.KH * 64;
       if (i >= (int64_t)a.NZ * K) return;
       const int n = (int)(i / K), k = (int)(i % K);
-      mirror_put(a.m_dz, a.NZ, a.KH, n, k, (n < Z && k < H) ? a.P[a.oW1 + (size_t)n * H + k] : 0.f);
+      mirror_put(a.m_dz, a.NZ, a.KH, 0, n, k, (n < Z && k < H) ? a.P[a.oW1 + (size_t)n * H + k] : 0.f);
       break;
     }
   }
+}
+
+// constant rows of the transposed activation mirrors: the "ones" feature that turns a weight-gradient GEMM's extra row /
+// column into the bias gradient (h_e and h_d: feature H; z: feature Z).  Everything else starts as zero.
+struct OnesArgs { uint8_t *he_t0, *he_t1, *hd_t, *z_t; int H, Z, NZ; };
+__global__ void __launch_bounds__(128) init_ones_kernel(OnesArgs a) {
+  const int b = threadIdx.x;                       // batch column 0..127
+  const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
+  uint8_t* m[3] = {a.he_t0, a.he_t1, a.hd_t};
+  for (int q = 0; q < 3; ++q)
+    *reinterpret_cast<__nv_bfloat16*>(t_addr(m[q], a.H >> 7, TBA, a.H & 127, b)) = one;
+  *reinterpret_cast<__nv_bfloat16*>(t_addr(a.z_t, 0, a.NZ * 128, a.Z, b)) = one;
 }
 
 }  // namespace st2
@@ -960,7 +1083,7 @@ bool step_tc_supported(const vaeb_handle* h, int rows) {
 }
 
 void step_tc_free(StepTcState& s) {
-  void* ptrs[] = {s.bar, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz, s.he, s.hd, s.da2, s.da1, s.dd, s.mu, s.ls,
+  void* ptrs[] = {s.bar, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz, s.act, s.he, s.hd, s.dd, s.mu, s.ls,
                   s.eps, s.z, s.partial, s.aux, s.d_order, s.d_timing};
   for (void* q : ptrs)
     if (q) cudaFree(q);
@@ -974,6 +1097,7 @@ static int step_tc_init(vaeb_handle* h) {
   const int HP = (H + 63) / 64 * 64, KD = (D + 63) / 64, KH = HP / 64;
   const int NH = (2 * Z + 15) / 16 * 16, NZ = (Z + 1 + 15) / 16 * 16;
   const int n3 = (D + TR_DEC2 - 1) / TR_DEC2;
+  const int m_h1 = (H + 1 + MP - 1) / MP;
   VAEB_CUDA(cudaFuncSetAttribute(step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   // how many clusters of four fit at once: the grid must be co-resident (grid barriers)
   cudaLaunchConfig_t cfg{};
@@ -996,10 +1120,23 @@ static int step_tc_init(vaeb_handle* h) {
   VAEB_CUDA(alloc((void**)&s.m_heads, (size_t)NH * KH * 64 * 4));
   VAEB_CUDA(alloc((void**)&s.m_dec2, (size_t)n3 * TR_DEC2 * KH * 64 * 4));
   VAEB_CUDA(alloc((void**)&s.m_dz, (size_t)NZ * KH * 64 * 4));
+  // activation mirrors in one allocation (cleared together when the minibatch size changes)
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t at_ = o; o += (bytes + 1023) / 1024 * 1024; return at_; };
+  s.he_t_bytes = (size_t)m_h1 * 4 * TBA;
+  s.o_he_km = take((size_t)KH * 2 * TBA);
+  s.o_he_t = take(2 * s.he_t_bytes);
+  s.o_hd_t = take((size_t)m_h1 * 4 * TBA);
+  s.o_da2_km = take((size_t)KD * 2 * TBA);
+  s.o_da2_t = take((size_t)n3 * 4 * TR_DEC2 * 128);
+  s.o_da1_km = take((size_t)KH * 2 * TBA);
+  s.o_da1_t = take((size_t)m_h1 * 4 * TBA);
+  s.o_dd_t = take((size_t)4 * NH * 128);
+  s.o_z_t = take((size_t)4 * NZ * 128);
+  s.act_bytes = o;
+  VAEB_CUDA(alloc((void**)&s.act, s.act_bytes));
   VAEB_CUDA(alloc((void**)&s.he, (size_t)2 * MP * HP * 4));
   VAEB_CUDA(alloc((void**)&s.hd, (size_t)MP * HP * 4));
-  VAEB_CUDA(alloc((void**)&s.da1, (size_t)MP * HP * 4));
-  VAEB_CUDA(alloc((void**)&s.da2, (size_t)MP * D * 4));
   VAEB_CUDA(alloc((void**)&s.dd, (size_t)MP * 2 * Z * 4));
   VAEB_CUDA(alloc((void**)&s.mu, (size_t)MP * Z * 4));
   VAEB_CUDA(alloc((void**)&s.ls, (size_t)MP * Z * 4));
@@ -1036,15 +1173,28 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
   p.oW3 = l.off[l.iW3]; p.oW4 = l.off[l.iW4]; p.oW5 = l.off[l.iW5]; p.oW1 = l.off[l.iW1]; p.oW2 = l.off[l.iW2];
   p.ob3 = l.off[l.ib3]; p.ob4 = l.off[l.ib4]; p.ob5 = l.off[l.ib5]; p.ob1 = l.off[l.ib1]; p.ob2 = l.off[l.ib2];
   p.m_enc1 = s.m_enc1; p.m_heads = s.m_heads; p.m_dec2 = s.m_dec2; p.m_dgrad = s.m_dgrad; p.m_dz = s.m_dz;
+  p.he_km = s.act + s.o_he_km; p.he_t = s.act + s.o_he_t; p.hd_t = s.act + s.o_hd_t;
+  p.da2_km = s.act + s.o_da2_km; p.da2_t = s.act + s.o_da2_t; p.da1_km = s.act + s.o_da1_km; p.da1_t = s.act + s.o_da1_t;
+  p.dd_t = s.act + s.o_dd_t; p.z_t = s.act + s.o_z_t;
   p.x_base = (d_order && d_xrows) ? d_xrows : h->d_x; p.batch_order = d_order; p.x_direct = d_xrows;
   p.eps_inj = d_eps;
   p.seed = h->cfg.seed; p.step0 = h->step; p.row_offset = 0;
-  p.he = s.he; p.hd = s.hd; p.da2 = s.da2; p.da1 = s.da1; p.dd = s.dd; p.mu = s.mu; p.ls = s.ls; p.eps = s.eps; p.z = s.z;
+  p.he = s.he; p.hd = s.hd; p.dd = s.dd; p.mu = s.mu; p.ls = s.ls; p.eps = s.eps; p.z = s.z;
   p.partial = s.partial; p.aux = s.aux;
   p.scalars = h->d_scalars + slot0; p.Mg = (float)rows; p.bmult = 1.0f;
   p.n_steps = n_steps;
   p.bar = s.bar; p.bar_base = s.bar_count;
   p.timing = d_timing;
+  if (rows != s.rows_init) {
+    // batch columns >= rows of every activation mirror must read as zero (they are contraction rows of the weight
+    // gradients): clear everything when the minibatch size changes, then restore the constant "ones" features
+    VAEB_CUDA(cudaMemsetAsync(s.act, 0, s.act_bytes, h->stream));
+    OnesArgs oa{p.he_t, p.he_t + s.he_t_bytes, p.hd_t, p.z_t, H, Z, p.NZ};
+    init_ones_kernel<<<1, 128, 0, h->stream>>>(oa);
+    VAEB_CUDA(cudaGetLastError());
+    ++h->launches;
+    s.rows_init = rows;
+  }
   if (!s.mirrors_valid) {
     MirrorArgs a{h->d_params, p.oW3, p.oW4, p.oW5, p.oW1, p.oW2, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz,
                  D, H, Z, p.HP, p.KD, p.KH, p.NH, p.NZ};

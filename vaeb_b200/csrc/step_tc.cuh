@@ -3,10 +3,11 @@
 // The M = 100 update of the reference (VAEB.py:408-415 -- forward, bound, backward, prior, Adagrad; configs C2 and
 // the Bernoulli runs of scripts/pg_7_graphs.sh) as ONE persistent kernel of thread-block clusters: every contraction
 // runs on tcgen05 (bf16 hi+lo operands, three MMAs per k step, fp32 accumulation in TMEM: the fp32 parity tier), the
-// split of a contraction over the four CTAs of a cluster is reduced through distributed shared memory, weights are
-// read from bf16 mirrors kept in the UMMA shared-memory image (pre-swizzled, K-major) and rewritten by the Adagrad
-// epilogues of the weight-gradient GEMMs.  Six grid barriers per update (the FFMA kernel of fused_step.cu needs
-// eight), no parameter double buffer.
+// split of a contraction over the four CTAs of a cluster is reduced through distributed shared memory, and EVERY
+// operand lives in global memory (L2) as a bf16 hi/lo mirror in the UMMA shared-memory image (pre-swizzled, K-major):
+// weights are rewritten by the Adagrad epilogues of the weight-gradient GEMMs, activations by the epilogue that
+// produces them -- so staging an operand is one cp.async.bulk.  Six grid barriers per update (the FFMA kernel of
+// fused_step.cu needs eight), no parameter double buffer.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -32,18 +33,21 @@ struct Params {
   float* P;                             // flat fp32 parameters (reference tensor order), updated in place
   float* ada;
   int64_t oW3, oW4, oW5, oW1, oW2, ob3, ob4, ob5, ob1, ob2;
-  // bf16 hi/lo mirrors, [n tile][k chunk][hi, lo][rows x 128 B] in the K-major SWIZZLE_128B image
+  // weight mirrors: [n tile][k chunk][hi, lo][rows x 128 B], K-major SWIZZLE_128B
   uint8_t *m_enc1, *m_heads, *m_dec2, *m_dgrad, *m_dz;
+  // activation mirrors.  *_km: [k chunk][hi, lo][128 batch rows x 128 B] (A operand of the next layer);
+  // *_t: [feature tile][batch chunk (2)][hi, lo][tile rows x 128 B] (operands of the weight gradients)
+  uint8_t *he_km, *he_t, *hd_t, *da2_km, *da2_t, *da1_km, *da1_t, *dd_t, *z_t;
   const float* x_base; const int* batch_order; const float* x_direct;
   const float* eps_inj;
   uint64_t seed; uint32_t step0; int64_t row_offset;
-  float *he, *hd, *da2, *da1, *dd, *mu, *ls, *eps, *z;     // fp32 activations: [MP, HP] / [MP, D] / [MP, 2Z] / [MP, Z]
+  float *he, *hd, *dd, *mu, *ls, *eps, *z;     // fp32 copies the epilogues read: [2][MP, HP], [MP, HP], [MP, 2Z], [MP, Z]
   float *partial, *aux;                 // [MP, tiles of dec2] log-likelihood row partials; [MP] KL / LA row terms
   int n_tiles3;                         // n tiles of dec2 (partial's leading dimension)
   float* scalars; float Mg; float bmult;
   int n_steps;
   unsigned long long* bar; unsigned long long bar_base;
-  long long* timing;                    // nullptr or [n_steps * (N_PHASES + 1)] globaltimer stamps of CTA 0
+  long long* timing;                    // nullptr or [n_steps * (N_PHASES + 1) + 128] globaltimer stamps of CTA 0
 };
 
 }  // namespace st2
@@ -52,11 +56,15 @@ struct vaeb_handle;
 struct StepTcState {
   bool ready = false, unavailable = false;
   int n_cta = 0;
+  int rows_init = -1;                   // minibatch rows the activation mirrors were cleared for
   unsigned long long* bar = nullptr; unsigned long long bar_count = 0;
   uint8_t *m_enc1 = nullptr, *m_heads = nullptr, *m_dec2 = nullptr, *m_dgrad = nullptr, *m_dz = nullptr;
+  uint8_t* act = nullptr; size_t act_bytes = 0;      // one allocation for every activation mirror
+  size_t o_he_km = 0, o_he_t = 0, o_hd_t = 0, o_da2_km = 0, o_da2_t = 0, o_da1_km = 0, o_da1_t = 0, o_dd_t = 0, o_z_t = 0;
+  size_t he_t_bytes = 0;
   bool mirrors_valid = false;
-  float *he = nullptr, *hd = nullptr, *da2 = nullptr, *da1 = nullptr, *dd = nullptr, *mu = nullptr, *ls = nullptr,
-        *eps = nullptr, *z = nullptr, *partial = nullptr, *aux = nullptr;
+  float *he = nullptr, *hd = nullptr, *dd = nullptr, *mu = nullptr, *ls = nullptr, *eps = nullptr, *z = nullptr,
+        *partial = nullptr, *aux = nullptr;
   int* d_order = nullptr; int order_cap = 0;
   long long* d_timing = nullptr; int timing_cap = 0;
 };
