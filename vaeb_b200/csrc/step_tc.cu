@@ -141,8 +141,17 @@ __device__ __forceinline__ float tanh_fast(float x) {
                                                 0.13333333333333333f), -0.33333333333333331f), x);
   return ax < 0.1f ? poly : big;
 }
-__device__ __forceinline__ float softplusf_(float a) { return fmaxf(a, 0.f) + log1pf(expf(-fabsf(a))); }
-__device__ __forceinline__ float sigmoidf_(float a) { return 1.0f / (1.0f + expf(-a)); }
+// one exponential serves both: t = e^-|a|; softplus = max(a,0) + log(1+t); sigmoid = {1, t}/(1+t)  (MUFU ex2 / rcp /
+// lg2 with ~1e-7 relative error each: the log-likelihood terms are O(1) and are summed over 784 pixels)
+__device__ __forceinline__ void softplus_sigmoid(float a, float& sp, float& sg) {
+  float t, r, lg;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-1.4426950408889634f * fabsf(a)));
+  const float u = 1.0f + t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(u));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
+  sp = fmaf(lg, 0.6931471805599453f, fmaxf(a, 0.f));
+  sg = a >= 0.f ? r : t * r;
+}
 
 // byte offset of the 16-byte unit (row r, k octet cu) inside one K-major SWIZZLE_128B chunk tile
 __device__ __forceinline__ uint32_t unit_off(int r, int cu) { return (uint32_t)r * 128u + (((uint32_t)cu ^ ((uint32_t)r & 7u)) << 4); }
@@ -393,7 +402,8 @@ __device__ __forceinline__ void item_heads(Ctx& c, const Params& p, uint32_t ste
     bulk_g2s(c.sm + SM_A, p.he_km + (size_t)c0 * 2 * TBA, (uint32_t)(nch * 2 * TBA), c.op_bar);
     bulk_g2s(c.sm + SM_B, p.m_heads + (size_t)c0 * 2 * TB, (uint32_t)(nch * 2 * TB), c.op_bar);
   }
-  // while the operands are in flight: this thread's noise and biases (two (row, j) items per thread at most)
+  // while the operands are in flight: this thread's noise (drawn in P1 by the spare cluster, or injected) and biases
+  const float* eps_src = p.eps_inj ? p.eps_inj : p.eps;
   float e_[2], b4_[2], b5_[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -402,9 +412,7 @@ __device__ __forceinline__ void item_heads(Ctx& c, const Params& p, uint32_t ste
     const int gr = c.rank * 32 + row;
     e_[i] = b4_[i] = b5_[i] = 0.f;
     if (it < 32 * Z && gr < p.M) {
-      const size_t o = (size_t)gr * Z + j;
-      e_[i] = p.eps_inj ? __ldcg(p.eps_inj + o)
-                        : philox_normal1(p.seed, VAEB_STREAM_TRAIN, step, 0u, (uint64_t)((p.row_offset + gr) * Z + j));
+      e_[i] = __ldcg(eps_src + (size_t)gr * Z + j);
       b4_[i] = __ldcg(p.P + p.ob4 + j); b5_[i] = __ldcg(p.P + p.ob5 + j);
     }
   }
@@ -429,7 +437,8 @@ __device__ __forceinline__ void item_heads(Ctx& c, const Params& p, uint32_t ste
       const size_t o = (size_t)gr * Z + j;
       const float e = e_[i];
       const float zv = am + expf(0.5f * al) * e;
-      p.mu[o] = am; p.ls[o] = al; p.eps[o] = e; p.z[o] = zv;
+      p.mu[o] = am; p.ls[o] = al; p.z[o] = zv; p.zT[(size_t)j * MP + gr] = zv;
+      if (p.eps_inj) p.eps[o] = e;
       put_bf(t_addr(p.z_t, 0, zt_half, j, gr), zt_half, zv);
       tv = p.la ? (-0.5f * zv * zv + 0.5f * al + 0.5f * e * e) : 0.5f * (1.0f + al - am * am - expf(al));
     }
@@ -457,9 +466,12 @@ __device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* 
   const int c0 = c.rank * p.KH / CL, c1 = (c.rank + 1) * p.KH / CL, nch = c1 - c0;
   constexpr int TB = TR_DEC2 * 128;
   const int Z = p.Z, H = p.H, M = p.M;
-  float* zs = reinterpret_cast<float*>(c.sm + SM_SCR);          // [MP][Z]
-  float* ws = zs + MP * Z;                                      // [Z][64]
-  float* bs = ws + Z * 64;                                      // [64]
+  // producer scratch: z^T [Z][128] and, per k chunk, W1[:, chunk] as [Z][low / high half of an octet][8 octets][4]
+  // (the eight 16-byte loads of a quarter warp are then 128 contiguous bytes: no bank conflicts) + b1[chunk]
+  constexpr int WP = 64;                                        // floats per q row of a staged W1 chunk
+  float* zsT = reinterpret_cast<float*>(c.sm + SM_SCR);         // [Z][MP]
+  float* ws = zsT + Z * MP;                                     // [2][Z][WP]
+  float* bs = ws + 2 * Z * WP;                                  // [2][64]
   if (threadIdx.x == 0 && nch > 0) {
     ops_begin(c, (uint32_t)(nch * 2 * TB));
     bulk_g2s(c.sm + SM_B, p.m_dec2 + ((size_t)t * p.KH + c0) * 2 * TB, (uint32_t)(nch * 2 * TB), c.op_bar);
@@ -469,11 +481,11 @@ __device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* 
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const int e = threadIdx.x + i * NT;
-      zr[i] = e < M * Z ? __ldcg(p.z + e) : 0.f;
+      zr[i] = e < Z * MP ? __ldcg(p.zT + e) : 0.f;              // rows >= M of z^T stay zero (never written)
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i)
-      if ((int)threadIdx.x + i * NT < MP * Z) zs[threadIdx.x + i * NT] = zr[i];
+      if ((int)threadIdx.x + i * NT < Z * MP) zsT[threadIdx.x + i * NT] = zr[i];
   }
   // this thread's two elements of the final stage: x and the output bias (in flight during the producer and the MMAs)
   float xv_[2], b2_[2];
@@ -486,53 +498,79 @@ __device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* 
     b2_[i] = ok ? __ldcg(p.P + p.ob2 + n) : 0.f;
   }
   ST2_TRACE(c, 36);
-  for (int ci = 0; ci < nch; ++ci) {
-    const int k0 = (c0 + ci) * 64;
+  for (int cp = 0; cp < nch; cp += 2) {                          // two k chunks per pass: 2 x 32 row groups x 8 octets = 512 threads
     __syncthreads();
-    ST2_TRACE(c, 37);
     {
-      float wr[3]; float br = 0.f;
+      float wr[5]; float br = 0.f;
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int e = threadIdx.x + i * NT;
-        const int q = e >> 6, kk = e & 63;
-        wr[i] = (e < Z * 64 && k0 + kk < H) ? __ldcg(p.P + p.oW1 + (size_t)q * H + k0 + kk) : 0.f;
+      for (int i = 0; i < 5; ++i) {
+        const int e = threadIdx.x + i * NT;                      // (chunk half, q, kk): 2 x Z x 64
+        const int hc = e / (Z * 64), r2 = e - hc * Z * 64;
+        const int q = r2 >> 6, kk = r2 & 63;
+        const int k = (c0 + cp + hc) * 64 + kk;
+        wr[i] = (e < 2 * Z * 64 && cp + hc < nch && k < H) ? __ldcg(p.P + p.oW1 + (size_t)q * H + k) : 0.f;
       }
-      if (threadIdx.x < 64 && k0 + threadIdx.x < H) br = __ldcg(p.P + p.ob1 + k0 + threadIdx.x);
+      if (threadIdx.x < 128) {
+        const int k = (c0 + cp + (threadIdx.x >> 6)) * 64 + (threadIdx.x & 63);
+        if (cp + (int)(threadIdx.x >> 6) < nch && k < H) br = __ldcg(p.P + p.ob1 + k);
+      }
 #pragma unroll
-      for (int i = 0; i < 3; ++i)
-        if ((int)threadIdx.x + i * NT < Z * 64) ws[threadIdx.x + i * NT] = wr[i];
-      if (threadIdx.x < 64) bs[threadIdx.x] = br;
+      for (int i = 0; i < 5; ++i) {
+        const int e = threadIdx.x + i * NT;
+        if (e < 2 * Z * 64) {
+          const int hc = e / (Z * 64), r2 = e - hc * Z * 64;
+          const int q = r2 >> 6, kk = r2 & 63;
+          ws[(hc * Z + q) * WP + ((kk >> 2) & 1) * 32 + (kk >> 3) * 4 + (kk & 3)] = wr[i];
+        }
+      }
+      if (threadIdx.x < 128) bs[threadIdx.x] = br;
     }
     __syncthreads();
     ST2_TRACE(c, 38);
-    for (int u = threadIdx.x; u < MP * 8; u += NT) {
-      const int r = u >> 3, cu = u & 7;
-      float v[8];
+    const int hc = threadIdx.x >> 8, rg = (threadIdx.x >> 3) & 31, cu = threadIdx.x & 7;
+    const int ci = cp + hc;
+    if (ci < nch) {
+      const int k0 = (c0 + ci) * 64;
+      float v[4][8];
+      if (rg * 4 < M) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = bs[cu * 8 + e];
-      if (r < M) {
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[i][e] = bs[hc * 64 + cu * 8 + e];
+        const float* wq = ws + hc * Z * WP + cu * 4;
+        const float* zq = zsT + rg * 4;
+#pragma unroll 4
         for (int q = 0; q < Z; ++q) {
-          const float zq = zs[r * Z + q];
-          const float4 w0 = *reinterpret_cast<const float4*>(ws + q * 64 + cu * 8);
-          const float4 w1 = *reinterpret_cast<const float4*>(ws + q * 64 + cu * 8 + 4);
-          v[0] = fmaf(zq, w0.x, v[0]); v[1] = fmaf(zq, w0.y, v[1]); v[2] = fmaf(zq, w0.z, v[2]); v[3] = fmaf(zq, w0.w, v[3]);
-          v[4] = fmaf(zq, w1.x, v[4]); v[5] = fmaf(zq, w1.y, v[5]); v[6] = fmaf(zq, w1.z, v[6]); v[7] = fmaf(zq, w1.w, v[7]);
+          const float4 w0 = *reinterpret_cast<const float4*>(wq + q * WP);
+          const float4 w1 = *reinterpret_cast<const float4*>(wq + q * WP + 32);
+          const float4 z4 = *reinterpret_cast<const float4*>(zq + q * MP);
+          const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[i][0] = fmaf(zz[i], w0.x, v[i][0]); v[i][1] = fmaf(zz[i], w0.y, v[i][1]);
+            v[i][2] = fmaf(zz[i], w0.z, v[i][2]); v[i][3] = fmaf(zz[i], w0.w, v[i][3]);
+            v[i][4] = fmaf(zz[i], w1.x, v[i][4]); v[i][5] = fmaf(zz[i], w1.y, v[i][5]);
+            v[i][6] = fmaf(zz[i], w1.z, v[i][6]); v[i][7] = fmaf(zz[i], w1.w, v[i][7]);
+          }
         }
       }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = (r < M && k0 + cu * 8 + e < H) ? tanh_fast(v[e]) : 0.f;
-      if (r < M && r % p.n_tiles3 == t) {                        // every cluster publishes a few rows of h_d for P4 / P5
-        float* o = p.hd + (size_t)r * p.HP + k0 + cu * 8;
-        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      for (int i = 0; i < 4; ++i) {
+        const int r = rg * 4 + i;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int k = k0 + cu * 8 + e;
-          if (k < H) put_bf(t_addr(p.hd_t, k >> 7, TBA, k & 127, r), TBA, v[e]);
+        for (int e = 0; e < 8; ++e) v[i][e] = (r < M && k0 + cu * 8 + e < H) ? tanh_fast(v[i][e]) : 0.f;
+        if (r < M && r % p.n_tiles3 == t) {                      // every cluster publishes a few rows of h_d for P4 / P5
+          float* o = p.hd + (size_t)r * p.HP + k0 + cu * 8;
+          *reinterpret_cast<float4*>(o) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int k = k0 + cu * 8 + e;
+            if (k < H) put_bf(t_addr(p.hd_t, k >> 7, TBA, k & 127, r), TBA, v[i][e]);
+          }
         }
+        put_unit(c.sm + SM_A + (size_t)ci * 2 * TBA + unit_off(r, cu), TBA, v[i]);
       }
-      put_unit(c.sm + SM_A + (size_t)ci * 2 * TBA + unit_off(r, cu), TBA, v);
     }
     ST2_TRACE(c, 39);
   }
@@ -552,10 +590,12 @@ __device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* 
     if (gr < M && n < p.D) {
       const float a = recv_sum(recv, TR_DEC2, row, col) + b2_[i];
       const float xv = xv_[i];
-      const float d = p.w * (xv - sigmoidf_(a));
+      float sp, sg;
+      softplus_sigmoid(a, sp, sg);
+      const float d = p.w * (xv - sg);
       put_bf(km_addr(p.da2_km, gr, n), TBA, d);
       put_bf(t_addr(p.da2_t, t, TB, col, gr), TB, d);
-      tv = xv * a - softplusf_(a);
+      tv = xv * a - sp;
     }
     term[it] = tv;
   }
@@ -633,7 +673,6 @@ __device__ __forceinline__ void item_dz(Ctx& c, const Params& p, bool more) {
   reduce_scatter(c, N, nch > 0);
   ST2_TRACE(c, 53);
   const float* recv = reinterpret_cast<const float*>(c.sm + SM_RECV);
-  const int ddt_half = p.NH * 128;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int it = threadIdx.x + i * NT;
@@ -650,10 +689,10 @@ __device__ __forceinline__ void item_dz(Ctx& c, const Params& p, bool more) {
         a -= p.w * zm_[i];
         b += p.w * 0.5f * (1.0f - expf(ls_[i]));
       }
-      p.dd[(size_t)gr * 2 * Z + j] = a;
-      p.dd[(size_t)gr * 2 * Z + Z + j] = b;
-      put_bf(t_addr(p.dd_t, 0, ddt_half, j, gr), ddt_half, a);
-      put_bf(t_addr(p.dd_t, 0, ddt_half, Z + j, gr), ddt_half, b);
+      p.ddT[(size_t)j * MP + gr] = a;
+      p.ddT[(size_t)(Z + j) * MP + gr] = b;
+      put_bf(t_addr(p.dd_t, j >> 4, 2048, j & 15, gr), 2048, a);                 // [dmu|dls]^T in tiles of 16 columns
+      put_bf(t_addr(p.dd_t, (Z + j) >> 4, 2048, (Z + j) & 15, gr), 2048, b);
     }
   }
   ST2_TRACE(c, 54);
@@ -679,6 +718,70 @@ __device__ __forceinline__ void wgrad_epilogue(Ctx& c, int N, F fn) {
   __syncthreads();
 }
 
+// Coalesced form.  The accumulator tile [128 x N] (N = 16 or 32) goes through shared memory twice:
+//   A  thread = accumulator row (TMEM lane): the sums are parked in a [128][33] fp32 tile;
+//   B  lane = column: a warp instruction reads / writes ONE contiguous row segment of the parameters and of the
+//      accumulators (the uncoalesced form touches 32 lines per instruction and is bound by L1 request processing:
+//      3.6 us per tile measured), Adagrad, the new values go back into the tile;
+//   C  thread = row again: `mir(row, col0, nv[8])` writes the bf16 mirrors (their k index runs along the rows).
+// off(row, col) = flat offset of the parameter behind accumulator element (row, col), or -1.
+template <int N>
+struct WgPre {                                                     // parameters / accumulators of phase B, loaded early
+  static constexpr int RPP = 32 / N, NP = 8 / RPP;                 // rows per warp pass; passes (a warp owns 8 rows)
+  long long o[NP]; float pv[NP], av[NP];
+};
+// issue the phase-B loads (they do not depend on the GEMM): called BEFORE waiting for the operands and the MMAs
+template <int N, class OffF>
+__device__ __forceinline__ void wgrad_prefetch(Ctx& c, const Params& p, OffF off, WgPre<N>& w) {
+  const int col = c.lane % N, rsub = c.lane / N;
+#pragma unroll
+  for (int r = 0; r < WgPre<N>::NP; ++r) {
+    const int row = c.warp * 8 + r * WgPre<N>::RPP + rsub;
+    w.o[r] = off(row, col);
+    w.pv[r] = w.o[r] >= 0 ? __ldcg(p.P + w.o[r]) : 0.f;
+    w.av[r] = w.o[r] >= 0 ? __ldcg(p.ada + w.o[r]) : 0.f;
+  }
+}
+template <int N, class MirF>
+__device__ __forceinline__ void wgrad_epilogue_coalesced(Ctx& c, const Params& p, const Hyper& hy, const WgPre<N>& w, MirF mir) {
+  constexpr int GP = 33;
+  float* gt = reinterpret_cast<float*>(c.sm + SM_RECV);            // 128 x 33 floats = 16.5 KB (no cluster item is active)
+  const int q = c.warp & 3;
+  for (int u = c.warp >> 2; u < N / 8; u += 4) {
+    float v[8];
+    tmem_ld8(c.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * 8), v);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gt[(q * 32 + c.lane) * GP + u * 8 + e] = v[e];
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  {
+    const int col = c.lane % N, rsub = c.lane / N;
+#pragma unroll
+    for (int r = 0; r < WgPre<N>::NP; ++r) {
+      const int row = c.warp * 8 + r * WgPre<N>::RPP + rsub;
+      if (w.o[r] >= 0) {
+        const float gg = gt[row * GP + col] - hy.prior * w.pv[r];  // VAEB.py:389-390
+        const float a = w.av[r] + gg * gg;                         // VAEB.py:439
+        float nv = w.pv[r] + hy.lr * gg / (sqrtf(a) + hy.eps);     // VAEB.py:441
+        if (hy.p2 != 0.f) nv -= hy.p2 * w.pv[r] * w.pv[r];         // VAEBfullbayes.py:183-184
+        p.P[w.o[r]] = nv;
+        p.ada[w.o[r]] = a;
+        gt[row * GP + col] = nv;
+      }
+    }
+  }
+  __syncthreads();
+  for (int u = c.warp >> 2; u < N / 8; u += 4) {
+    float nv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) nv[e] = gt[(q * 32 + c.lane) * GP + u * 8 + e];
+    mir(q * 32 + c.lane, u * 8, nv);
+  }
+  __syncthreads();
+}
+
 // W2, b2 <- Adagrad([h_d | 1]^T . da2); tile = 128 hidden units x 32 pixels
 __device__ __forceinline__ void item_wg2(Ctx& c, const Params& p, const Hyper& hy, int mt, int nt) {
   ST2_TRACE(c, 60);
@@ -688,29 +791,28 @@ __device__ __forceinline__ void item_wg2(Ctx& c, const Params& p, const Hyper& h
     bulk_g2s(c.sm + SM_A, p.hd_t + (size_t)mt * 4 * TBA, (uint32_t)(4 * TBA), c.op_bar);
     bulk_g2s(c.sm + SM_B, p.da2_t + (size_t)nt * 4 * TB, (uint32_t)(4 * TB), c.op_bar);
   }
+  const int H = p.H, D = p.D;
+  WgPre<TR_DEC2> pre;
+  wgrad_prefetch<TR_DEC2>(c, p, [&](int row, int col) -> long long {
+    const int i = mt * MP + row, n = nt * TR_DEC2 + col;
+    if (i > H || n >= D) return -1;
+    return i < H ? p.oW2 + (long long)i * D + n : p.ob2 + n;
+  }, pre);
   mma_run(c, 2, (p.M + 15) / 16, TB, TR_DEC2, true);
   ST2_TRACE(c, 61);
-  const int H = p.H, D = p.D;
-  wgrad_epilogue(c, TR_DEC2, [&](int row, int col0, const float* v) {
-    const int i = mt * MP + row, n0 = nt * TR_DEC2 + col0;
-    if (i > H || n0 >= D) return;
-    size_t off[8]; bool ok[8]; float nv[8];
+  wgrad_epilogue_coalesced<TR_DEC2>(
+      c, p, hy, pre,
+      [&](int row, int col0, float* nv) {
+        const int i = mt * MP + row, n0 = nt * TR_DEC2 + col0;
+        if (i >= H || n0 >= D) return;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      ok[e] = n0 + e < D;
-      off[e] = (i < H ? (size_t)p.oW2 + (size_t)i * D : (size_t)p.ob2) + n0 + e;
-    }
-    adagrad8(p.P, p.ada, off, ok, v, hy, nv);
-    if (i < H) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (ok[e]) mirror_put(p.m_dec2, TR_DEC2, p.KH, nt, col0 + e, i, nv[e]);
-        else nv[e] = 0.f;
-      // dgrad mirror: row = hidden unit i, k = pixel: eight consecutive k = one 16-byte unit (n0 is a multiple of 8)
-      constexpr int TG = TR_DGRAD * 128;
-      put_unit(p.m_dgrad + ((size_t)(i >> 4) * p.KD + (n0 >> 6)) * 2 * TG + unit_off(i & 15, (n0 & 63) >> 3), TG, nv);
-    }
-  });
+        for (int e = 0; e < 8; ++e)
+          if (n0 + e < D) mirror_put(p.m_dec2, TR_DEC2, p.KH, nt, col0 + e, i, nv[e]);
+          else nv[e] = 0.f;
+        // dgrad mirror: row = hidden unit i, k = pixel: eight consecutive k = one 16-byte unit (n0 is a multiple of 8)
+        constexpr int TG = TR_DGRAD * 128;
+        put_unit(p.m_dgrad + ((size_t)(i >> 4) * p.KD + (n0 >> 6)) * 2 * TG + unit_off(i & 15, (n0 & 63) >> 3), TG, nv);
+      });
   ST2_TRACE(c, 62);
 }
 
@@ -720,78 +822,73 @@ __device__ __forceinline__ void item_wg3(Ctx& c, const Params& p, const Hyper& h
                                       bool a_staged) {
   ST2_TRACE(c, 70);
   const int Z = p.Z, Z2 = 2 * p.Z, H = p.H, M = p.M, D = p.D;
-  float* dds = reinterpret_cast<float*>(c.sm + SM_SCR);         // [M][2Z]  (scratch region + receive buffer: 48 KB)
-  float* w45 = dds + MP * Z2;                                   // [32][2Z + 1]
+  float* ddsT = reinterpret_cast<float*>(c.sm + SM_SCR);        // [2Z][128]  (scratch region + receive buffer: 48 KB)
+  float* w45 = ddsT + Z2 * MP;                                  // [2Z][32]
+  const int jj = threadIdx.x & 31, bo = threadIdx.x >> 5;        // 32 hidden units x 16 batch octets
+  const int j = nt * 32 + jj;
+  float hv[8];
   {
-    // [dmu|dls] and the 32 rows of [W4|W5] this tile needs: loads first, stores second
+    // [dmu|dls]^T and the 32 columns of the [W4|W5]^T snapshot this tile needs: loads first, stores second
     float dr[12], wr[3];
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
       const int e = threadIdx.x + i * NT;
-      dr[i] = e < M * Z2 ? __ldcg(p.dd + e) : 0.f;
+      dr[i] = e < Z2 * MP ? __ldcg(p.ddT + e) : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const int e = threadIdx.x + i * NT;
-      const int jj = e / Z2, q = e - jj * Z2;
-      const int j = nt * 32 + jj;
-      wr[i] = 0.f;
-      if (e < 32 * Z2 && j < H) wr[i] = q < Z ? __ldcg(p.P + p.oW4 + (size_t)j * Z + q) : __ldcg(p.P + p.oW5 + (size_t)j * Z + q - Z);
+      const int e = threadIdx.x + i * NT;                        // (q, jj): 2Z x 32
+      wr[i] = e < Z2 * 32 ? __ldcg(p.w45s + (size_t)(e >> 5) * p.HP + nt * 32 + (e & 31)) : 0.f;
     }
-#pragma unroll
-    for (int i = 0; i < 12; ++i)
-      if ((int)threadIdx.x + i * NT < M * Z2) dds[threadIdx.x + i * NT] = dr[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int e = threadIdx.x + i * NT;
-      if (e < 32 * Z2) w45[(e / Z2) * (Z2 + 1) + (e % Z2)] = wr[i];
-    }
-  }
-  if (!a_staged) stage_x_T(c.sm, x, D, M, mt * MP);
-  const int jj = threadIdx.x & 31, bo = threadIdx.x >> 5;        // 32 hidden units x 16 batch octets
-  const int j = nt * 32 + jj;
-  float hv[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int b = bo * 8 + e;
-    hv[e] = (b < M && j < H) ? __ldcg(he + (size_t)b * p.HP + j) : 0.f;
-  }
-  __syncthreads();
-  {
-    constexpr int TB = 32 * 128;
-    float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int b = bo * 8 + e;
-      float t = 0.f;
-      if (b < M && j < H) {
-        float s = 0.f;
-        for (int q = 0; q < Z2; ++q) s = fmaf(dds[b * Z2 + q], w45[jj * (Z2 + 1) + q], s);
-        t = s * (1.0f - hv[e] * hv[e]);
-      }
-      v[e] = t;
+      hv[e] = (b < M && j < H) ? __ldcg(he + (size_t)b * p.HP + j) : 0.f;
     }
+#pragma unroll
+    for (int i = 0; i < 12; ++i)
+      if ((int)threadIdx.x + i * NT < Z2 * MP) ddsT[threadIdx.x + i * NT] = dr[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      if ((int)threadIdx.x + i * NT < Z2 * 32) w45[threadIdx.x + i * NT] = wr[i];
+  }
+  if (!a_staged) stage_x_T(c.sm, x, D, M, mt * MP);
+  __syncthreads();
+  {
+    constexpr int TB = 32 * 128;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (bo * 8 < M) {
+#pragma unroll 4
+      for (int q = 0; q < Z2; ++q) {
+        const float wv = w45[q * 32 + jj];
+        const float4 d0 = *reinterpret_cast<const float4*>(ddsT + q * MP + bo * 8);
+        const float4 d1 = *reinterpret_cast<const float4*>(ddsT + q * MP + bo * 8 + 4);
+        v[0] = fmaf(d0.x, wv, v[0]); v[1] = fmaf(d0.y, wv, v[1]); v[2] = fmaf(d0.z, wv, v[2]); v[3] = fmaf(d0.w, wv, v[3]);
+        v[4] = fmaf(d1.x, wv, v[4]); v[5] = fmaf(d1.y, wv, v[5]); v[6] = fmaf(d1.z, wv, v[6]); v[7] = fmaf(d1.w, wv, v[7]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (bo * 8 + e < M && j < H) ? v[e] * (1.0f - hv[e] * hv[e]) : 0.f;
     put_unit(c.sm + SM_B + (size_t)(bo >> 3) * 2 * TB + unit_off(jj, bo & 7), TB, v);
   }
+  WgPre<32> pre;
+  wgrad_prefetch<32>(c, p, [&](int row, int col) -> long long {
+    const int i = mt * MP + row, jc = nt * 32 + col;
+    if (i > D || jc >= H) return -1;
+    return i < D ? p.oW3 + (long long)i * H + jc : p.ob3 + jc;
+  }, pre);
   ST2_TRACE(c, 71);
   mma_run(c, 2, (M + 15) / 16, 32 * 128, 32, false);
   ST2_TRACE(c, 72);
-  wgrad_epilogue(c, 32, [&](int row, int col0, const float* v) {
-    const int i = mt * MP + row, j0 = nt * 32 + col0;
-    if (i > D || j0 >= H) return;
-    size_t off[8]; bool ok[8]; float nv[8];
+  wgrad_epilogue_coalesced<32>(
+      c, p, hy, pre,
+      [&](int row, int col0, float* nv) {
+        const int i = mt * MP + row, j0 = nt * 32 + col0;
+        if (i >= D) return;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      ok[e] = j0 + e < H;
-      off[e] = (i < D ? (size_t)p.oW3 + (size_t)i * H : (size_t)p.ob3) + j0 + e;
-    }
-    adagrad8(p.P, p.ada, off, ok, v, hy, nv);
-    if (i < D) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (ok[e]) mirror_put(p.m_enc1, TR_ENC1, p.KD, (j0 + e) >> 4, (j0 + e) & 15, i, nv[e]);
-    }
-  });
+        for (int e = 0; e < 8; ++e)
+          if (j0 + e < H) mirror_put(p.m_enc1, TR_ENC1, p.KD, (j0 + e) >> 4, (j0 + e) & 15, i, nv[e]);
+      });
   ST2_TRACE(c, 73);
 }
 
@@ -822,35 +919,58 @@ __device__ __forceinline__ void item_wg1(Ctx& c, const Params& p, const Hyper& h
   });
 }
 
-// W4, b4, W5, b5 <- Adagrad([h_e | 1]^T . [dmu | dls]); tile = 128 hidden units x 2Z
-__device__ __forceinline__ void item_wg45(Ctx& c, const Params& p, const Hyper& hy, const uint8_t* he_t, int mt) {
-  const int Z = p.Z, H = p.H, N = p.NH;
-  const int TB = N * 128;
+// W4, b4, W5, b5 <- Adagrad([h_e | 1]^T . [dmu | dls]); tile = 128 hidden units x 16 columns of [dmu | dls]
+__device__ __forceinline__ void item_wg45(Ctx& c, const Params& p, const Hyper& hy, int mt, int nt) {
+  const int Z = p.Z, H = p.H;
+  constexpr int N = 16, TB = N * 128;
   if (threadIdx.x == 0) {
     ops_begin(c, (uint32_t)(4 * TBA + 4 * TB));
-    bulk_g2s(c.sm + SM_A, he_t + (size_t)mt * 4 * TBA, (uint32_t)(4 * TBA), c.op_bar);
-    bulk_g2s(c.sm + SM_B, p.dd_t, (uint32_t)(4 * TB), c.op_bar);
+    bulk_g2s(c.sm + SM_A, p.he_t + (size_t)mt * 4 * TBA, (uint32_t)(4 * TBA), c.op_bar);
+    bulk_g2s(c.sm + SM_B, p.dd_t + (size_t)nt * 4 * TB, (uint32_t)(4 * TB), c.op_bar);
   }
+  WgPre<N> pre;
+  wgrad_prefetch<N>(c, p, [&](int row, int col) -> long long {
+    const int i = mt * MP + row, cc = nt * N + col;
+    if (i > H || cc >= 2 * Z) return -1;
+    const int jc = cc < Z ? cc : cc - Z;
+    if (i < H) return (cc < Z ? p.oW4 : p.oW5) + (long long)i * Z + jc;
+    return (cc < Z ? p.ob4 : p.ob5) + jc;
+  }, pre);
   mma_run(c, 2, (p.M + 15) / 16, TB, N, true);
-  wgrad_epilogue(c, N, [&](int row, int col0, const float* v) {
-    const int i = mt * MP + row;
-    if (i > H || col0 >= 2 * Z) return;
-    size_t off[8]; bool ok[8]; float nv[8];
+  wgrad_epilogue_coalesced<N>(
+      c, p, hy, pre,
+      [&](int row, int col0, float* nv) {
+        const int i = mt * MP + row, cc0 = nt * N + col0;
+        if (i >= H) return;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int cc = col0 + e;
-      ok[e] = cc < 2 * Z;
-      const int j = cc < Z ? cc : cc - Z;
-      if (i < H) off[e] = (size_t)(cc < Z ? p.oW4 : p.oW5) + (size_t)i * Z + j;
-      else off[e] = (size_t)(cc < Z ? p.ob4 : p.ob5) + j;
+        for (int e = 0; e < 8; ++e)
+          if (cc0 + e < 2 * Z) mirror_put(p.m_heads, p.NH, p.KH, 0, cc0 + e, i, nv[e]);
+      });
+}
+
+// noise of the step: eps[M, Z] ~ N(0, 1) from Philox (VAEB.py:42's srng.normal, on the device); one CTA per quarter
+__device__ __forceinline__ void item_eps(const Params& p, uint32_t step, int part) {
+  const int e = part * NT + threadIdx.x;
+  if (e < p.M * p.Z)
+    p.eps[e] = philox_normal1(p.seed, VAEB_STREAM_TRAIN, step, 0u, (uint64_t)(p.row_offset * p.Z + e));
+  if (part == 0)
+    for (int e2 = CL * NT + threadIdx.x; e2 < p.M * p.Z; e2 += NT)
+      p.eps[e2] = philox_normal1(p.seed, VAEB_STREAM_TRAIN, step, 0u, (uint64_t)(p.row_offset * p.Z + e2));
+}
+
+// snapshot of [W4|W5]^T for the W3-gradient producers of P6: w45s[q][j], one CTA per quarter of the hidden units
+__device__ __forceinline__ void item_snap45(const Params& p, int part) {
+  const int Z = p.Z, Z2 = 2 * p.Z, H = p.H;
+  const int per = (p.HP + CL - 1) / CL;
+  for (int e = threadIdx.x; e < per * Z2; e += NT) {
+    const int jl = e / Z2, q = e - jl * Z2;
+    const int j = part * per + jl;
+    if (j < p.HP) {
+      float v = 0.f;
+      if (j < H) v = q < Z ? __ldcg(p.P + p.oW4 + (size_t)j * Z + q) : __ldcg(p.P + p.oW5 + (size_t)j * Z + q - Z);
+      p.w45s[(size_t)q * p.HP + j] = v;
     }
-    adagrad8(p.P, p.ada, off, ok, v, hy, nv);
-    if (i < H) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (ok[e]) mirror_put(p.m_heads, N, p.KH, 0, col0 + e, i, nv[e]);
-    }
-  });
+  }
 }
 
 // the bound of step s: fixed-order sum of the row partials (VAEB.py:340-344) / Mg
@@ -909,7 +1029,7 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
   const int m_d1 = (p.D + 1 + MP - 1) / MP;
   const int n_h32 = p.HP / 32;
   const int n3w = m_d1 * n_h32;                     // W3 gradient tiles
-  const size_t he_t_bytes = (size_t)m_h1 * 4 * TBA;
+  const int n45t = p.NH / 16;                       // 16-column tiles of [dmu|dls] in the W4/W5 gradient
   // a phase's item list: cluster items first, then CTA items in groups of four (one per rank of a cluster)
   auto n_groups = [](int n_cta_items) { return (n_cta_items + CL - 1) / CL; };
   auto x_of = [&](int s) { return p.batch_order ? p.x_base + (size_t)__ldg(p.batch_order + s) * p.M * p.D : p.x_direct; };
@@ -921,20 +1041,16 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
 
   for (int s = 0; s < p.n_steps; ++s) {
     const float* x = x_of(s);
-    float* he = p.he + (size_t)(s & 1) * MP * p.HP;              // double buffered: the W4/W5 update of step s runs in P1 of s+1
-    uint8_t* he_t = p.he_t + (size_t)(s & 1) * he_t_bytes;
-    const uint8_t* he_t_prev = p.he_t + (size_t)((s & 1) ^ 1) * he_t_bytes;
     long long* tm = rec ? p.timing + (size_t)s * (N_PHASES + 1) : nullptr;
     if (tm) tm[0] = gtime();
     if (p.timing && blockIdx.x == 0 && s == p.n_steps - 1) c.trace = p.timing + (size_t)p.n_steps * (N_PHASES + 1);
 
-    // ---- P1: encoder hidden layer | W4, W5 update of the previous step ---------------------------------------
+    // ---- P1: encoder hidden layer | this step's noise ----------------------------------------------------------
     {
-      const int n45 = s > 0 ? m_h1 : 0;
-      for (int it = c.cid; it < n1 + n_groups(n45); it += c.ncl) {
-        if (it < n1) { item_enc1(c, p, x, he, he_t, it, p1_staged && it == c.cid, it + c.ncl < n1); continue; }
-        const int i = (it - n1) * CL + c.rank;
-        if (i < n45) item_wg45(c, p, hy, he_t_prev, i);
+      const int n_e = p.eps_inj ? 0 : CL;
+      for (int it = c.cid; it < n1 + n_groups(n_e); it += c.ncl) {
+        if (it < n1) { item_enc1(c, p, x, p.he, p.he_t, it, p1_staged && it == c.cid, it + c.ncl < n1); continue; }
+        item_eps(p, p.step0 + (uint32_t)s, c.rank);
       }
       p1_staged = false;
     }
@@ -960,11 +1076,13 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     grid_barrier(p.bar, target += G);
     if (tm) tm[4] = gtime();
     ST2_TRACE(c, 94);
-    // ---- P5: dz | W2 update | the bound ----------------------------------------------------------------------------
+    // ---- P5: dz | W2 update | the bound | snapshot of [W4|W5]^T --------------------------------------------------
     {
       const int n2 = m_h1 * n3;
-      for (int it = c.cid; it < 1 + n_groups(n2 + 1); it += c.ncl) {
+      const int g2 = n_groups(n2 + 1);
+      for (int it = c.cid; it < 1 + g2 + 1; it += c.ncl) {
         if (it == 0) { item_dz(c, p, false); continue; }
+        if (it == 1 + g2) { item_snap45(p, c.rank); continue; }
         const int i = (it - 1) * CL + c.rank;
         if (i < n2) item_wg2(c, p, hy, i / n3, i % n3);
         else if (i == n2) item_bound(c, p, s);
@@ -978,12 +1096,14 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     grid_barrier(p.bar, target += G);
     if (tm) tm[5] = gtime();
     ST2_TRACE(c, 95);
-    // ---- P6: W3 update | W1 update ---------------------------------------------------------------------------------
+    // ---- P6: W3 update | W1 update | W4, W5 update -----------------------------------------------------------------
     {
-      for (int it = c.cid; it < n_groups(n3w + m_h); it += c.ncl) {
+      const int n45 = m_h1 * n45t;
+      for (int it = c.cid; it < n_groups(n3w + m_h + n45); it += c.ncl) {
         const int i = it * CL + c.rank;
-        if (i < n3w) item_wg3(c, p, hy, x, he, i / n_h32, i % n_h32, p6_staged && it == c.cid);
+        if (i < n3w) item_wg3(c, p, hy, x, p.he, i / n_h32, i % n_h32, p6_staged && it == c.cid);
         else if (i < n3w + m_h) item_wg1(c, p, hy, i - n3w);
+        else if (i < n3w + m_h + n45) item_wg45(c, p, hy, (i - n3w - m_h) / n45t, (i - n3w - m_h) % n45t);
       }
     }
     if (s + 1 < p.n_steps && c.cid < n1) { stage_x_rows(c.sm, x_of(s + 1), p.D, p.M, kd0, kdn); p1_staged = true; }
@@ -991,14 +1111,6 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     grid_barrier(p.bar, target += G);
     if (tm) tm[6] = gtime();
     ST2_TRACE(c, 96);
-  }
-  // ---- tail: the W4, W5 update of the last step (nothing else runs: no barrier needed after it) ---------------------
-  {
-    const uint8_t* he_t_last = p.he_t + (size_t)((p.n_steps - 1) & 1) * he_t_bytes;
-    for (int it = c.cid; it < n_groups(m_h1); it += c.ncl) {
-      const int i = it * CL + c.rank;
-      if (i < m_h1) item_wg45(c, p, hy, he_t_last, i);
-    }
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -1058,12 +1170,12 @@ __global__ void __launch_bounds__(256) build_mirrors_kernel(MirrorArgs a) {
 
 // constant rows of the transposed activation mirrors: the "ones" feature that turns a weight-gradient GEMM's extra row /
 // column into the bias gradient (h_e and h_d: feature H; z: feature Z).  Everything else starts as zero.
-struct OnesArgs { uint8_t *he_t0, *he_t1, *hd_t, *z_t; int H, Z, NZ; };
+struct OnesArgs { uint8_t *he_t, *hd_t, *z_t; int H, Z, NZ; };
 __global__ void __launch_bounds__(128) init_ones_kernel(OnesArgs a) {
   const int b = threadIdx.x;                       // batch column 0..127
   const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
-  uint8_t* m[3] = {a.he_t0, a.he_t1, a.hd_t};
-  for (int q = 0; q < 3; ++q)
+  uint8_t* m[2] = {a.he_t, a.hd_t};
+  for (int q = 0; q < 2; ++q)
     *reinterpret_cast<__nv_bfloat16*>(t_addr(m[q], a.H >> 7, TBA, a.H & 127, b)) = one;
   *reinterpret_cast<__nv_bfloat16*>(t_addr(a.z_t, 0, a.NZ * 128, a.Z, b)) = one;
 }
@@ -1079,12 +1191,12 @@ bool step_tc_supported(const vaeb_handle* h, int rows) {
   return (e == VAEB_EST_LB || e == VAEB_EST_LA) && !h->cont && h->L == 1 && h->world == 1 &&
          h->cfg.precision != VAEB_PREC_BF16 && h->optimizer == VAEB_OPT_ADAGRAD && rows >= 1 && rows <= st2::MP &&
          (h->D % 8) == 0 && (h->H % 4) == 0 && h->D >= 64 && h->H >= 64 && h->D <= 1024 && h->H <= 1024 && h->Z >= 1 &&
-         h->Z <= 24;
+         h->Z <= 20;
 }
 
 void step_tc_free(StepTcState& s) {
-  void* ptrs[] = {s.bar, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz, s.act, s.he, s.hd, s.dd, s.mu, s.ls,
-                  s.eps, s.z, s.partial, s.aux, s.d_order, s.d_timing};
+  void* ptrs[] = {s.bar, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz, s.act, s.he, s.hd, s.mu, s.ls,
+                  s.eps, s.z, s.zT, s.ddT, s.w45s, s.partial, s.aux, s.d_order, s.d_timing};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   s = StepTcState();
@@ -1123,9 +1235,8 @@ static int step_tc_init(vaeb_handle* h) {
   // activation mirrors in one allocation (cleared together when the minibatch size changes)
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t at_ = o; o += (bytes + 1023) / 1024 * 1024; return at_; };
-  s.he_t_bytes = (size_t)m_h1 * 4 * TBA;
   s.o_he_km = take((size_t)KH * 2 * TBA);
-  s.o_he_t = take(2 * s.he_t_bytes);
+  s.o_he_t = take((size_t)m_h1 * 4 * TBA);
   s.o_hd_t = take((size_t)m_h1 * 4 * TBA);
   s.o_da2_km = take((size_t)KD * 2 * TBA);
   s.o_da2_t = take((size_t)n3 * 4 * TR_DEC2 * 128);
@@ -1135,9 +1246,11 @@ static int step_tc_init(vaeb_handle* h) {
   s.o_z_t = take((size_t)4 * NZ * 128);
   s.act_bytes = o;
   VAEB_CUDA(alloc((void**)&s.act, s.act_bytes));
-  VAEB_CUDA(alloc((void**)&s.he, (size_t)2 * MP * HP * 4));
+  VAEB_CUDA(alloc((void**)&s.he, (size_t)MP * HP * 4));
   VAEB_CUDA(alloc((void**)&s.hd, (size_t)MP * HP * 4));
-  VAEB_CUDA(alloc((void**)&s.dd, (size_t)MP * 2 * Z * 4));
+  VAEB_CUDA(alloc((void**)&s.zT, (size_t)Z * MP * 4));
+  VAEB_CUDA(alloc((void**)&s.ddT, (size_t)2 * Z * MP * 4));
+  VAEB_CUDA(alloc((void**)&s.w45s, (size_t)2 * Z * HP * 4));
   VAEB_CUDA(alloc((void**)&s.mu, (size_t)MP * Z * 4));
   VAEB_CUDA(alloc((void**)&s.ls, (size_t)MP * Z * 4));
   VAEB_CUDA(alloc((void**)&s.eps, (size_t)MP * Z * 4));
@@ -1179,7 +1292,8 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
   p.x_base = (d_order && d_xrows) ? d_xrows : h->d_x; p.batch_order = d_order; p.x_direct = d_xrows;
   p.eps_inj = d_eps;
   p.seed = h->cfg.seed; p.step0 = h->step; p.row_offset = 0;
-  p.he = s.he; p.hd = s.hd; p.dd = s.dd; p.mu = s.mu; p.ls = s.ls; p.eps = s.eps; p.z = s.z;
+  p.he = s.he; p.hd = s.hd; p.mu = s.mu; p.ls = s.ls; p.eps = s.eps; p.z = s.z;
+  p.zT = s.zT; p.ddT = s.ddT; p.w45s = s.w45s;
   p.partial = s.partial; p.aux = s.aux;
   p.scalars = h->d_scalars + slot0; p.Mg = (float)rows; p.bmult = 1.0f;
   p.n_steps = n_steps;
@@ -1189,7 +1303,9 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
     // batch columns >= rows of every activation mirror must read as zero (they are contraction rows of the weight
     // gradients): clear everything when the minibatch size changes, then restore the constant "ones" features
     VAEB_CUDA(cudaMemsetAsync(s.act, 0, s.act_bytes, h->stream));
-    OnesArgs oa{p.he_t, p.he_t + s.he_t_bytes, p.hd_t, p.z_t, H, Z, p.NZ};
+    OnesArgs oa{p.he_t, p.hd_t, p.z_t, H, Z, p.NZ};
+    VAEB_CUDA(cudaMemsetAsync(s.zT, 0, (size_t)Z * MP * 4, h->stream));
+    VAEB_CUDA(cudaMemsetAsync(s.ddT, 0, (size_t)2 * Z * MP * 4, h->stream));
     init_ones_kernel<<<1, 128, 0, h->stream>>>(oa);
     VAEB_CUDA(cudaGetLastError());
     ++h->launches;

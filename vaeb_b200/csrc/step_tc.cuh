@@ -41,7 +41,10 @@ struct Params {
   const float* x_base; const int* batch_order; const float* x_direct;
   const float* eps_inj;
   uint64_t seed; uint32_t step0; int64_t row_offset;
-  float *he, *hd, *dd, *mu, *ls, *eps, *z;     // fp32 copies the epilogues read: [2][MP, HP], [MP, HP], [MP, 2Z], [MP, Z]
+  float *he, *hd, *mu, *ls, *eps, *z;   // fp32 copies the epilogues read: [MP, HP], [MP, HP], [MP, Z] x 4
+  float *zT, *ddT;                      // z and [dmu|dls] transposed, fp32: [Z][MP], [2Z][MP] (software producers)
+  float* w45s;                          // snapshot of [W4|W5]^T taken in P5: [2Z][HP] (the W3-gradient producer reads it
+                                        // while the W4/W5 update of the same phase rewrites the parameters)
   float *partial, *aux;                 // [MP, tiles of dec2] log-likelihood row partials; [MP] KL / LA row terms
   int n_tiles3;                         // n tiles of dec2 (partial's leading dimension)
   float* scalars; float Mg; float bmult;
@@ -61,10 +64,9 @@ struct StepTcState {
   uint8_t *m_enc1 = nullptr, *m_heads = nullptr, *m_dec2 = nullptr, *m_dgrad = nullptr, *m_dz = nullptr;
   uint8_t* act = nullptr; size_t act_bytes = 0;      // one allocation for every activation mirror
   size_t o_he_km = 0, o_he_t = 0, o_hd_t = 0, o_da2_km = 0, o_da2_t = 0, o_da1_km = 0, o_da1_t = 0, o_dd_t = 0, o_z_t = 0;
-  size_t he_t_bytes = 0;
   bool mirrors_valid = false;
-  float *he = nullptr, *hd = nullptr, *dd = nullptr, *mu = nullptr, *ls = nullptr, *eps = nullptr, *z = nullptr,
-        *partial = nullptr, *aux = nullptr;
+  float *he = nullptr, *hd = nullptr, *mu = nullptr, *ls = nullptr, *eps = nullptr, *z = nullptr, *zT = nullptr,
+        *ddT = nullptr, *w45s = nullptr, *partial = nullptr, *aux = nullptr;
   int* d_order = nullptr; int order_cap = 0;
   long long* d_timing = nullptr; int timing_cap = 0;
 };
