@@ -7,21 +7,21 @@
 //     the layer's fused epilogue (tanh / reparameterisation + KL / Bernoulli log-likelihood + delta / tanh' / dz);
 //   * CTA items -- the weight-gradient GEMMs gW[128 features x N] = act^T . delta (K = the minibatch, zero padded to
 //     128): one output tile per CTA, Adagrad with the prior (VAEB.py:389-390,426-444) in the epilogue, which also
-//     rewrites the bf16 mirrors of the weights it just updated.
-// Operands.  Every operand is a bf16 hi + lo pair of tiles in the UMMA K-major SWIZZLE_128B image.  Weights AND
+//     rewrites the fp16 mirrors of the weights it just updated.
+// Operands.  Every operand is a fp16 hi + lo pair of tiles in the UMMA K-major SWIZZLE_128B image.  Weights AND
 // activations are kept in that image in global memory (L2): an epilogue thread stores the value it produced straight
 // into the mirrors its consumers will load (row-major for the next layer, transposed for the weight gradients), so
 // staging an operand is ONE cp.async.bulk issued by one thread and completed on an mbarrier.  Two operands are produced
 // in software instead: the minibatch x (fp32 from the caller; staged while the CTA would otherwise wait at the
 // preceding grid barrier) and the two thin layers around the latent code, recomputed with FFMA where they are consumed
 // (h_d = tanh(z.W1 + b1) into the A tile of dec2, da3 = ([dmu|dls].W45^T)(1 - h_e^2) into the B tile of the W3 gradient).
-// One thread issues hi*hi + hi*lo + lo*hi per k step (bf16x3: the fp32 parity tier) and commits to an mbarrier; all 16
+// One thread issues hi*hi + hi*lo + lo*hi per k step (fp16 pairs, 22 mantissa bits: the fp32 parity tier) and commits to an mbarrier; all 16
 // warps read TMEM.
 // Phases of one update (a grid barrier after each):
 //   P1 enc1 (+ the W4/W5 update of the previous step on the spare cluster)   P2 heads + reparam + KL
 //   P3 dec1 (recomputed) + dec2 + log-lik + da2                              P4 dgrad -> da1
 //   P5 dz -> dmu, dls | W2,b2 update | the bound                             P6 W3,b3 update (dh_e recomputed) | W1,b1 update
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 
@@ -42,7 +42,7 @@ constexpr int SM_RECV = SM_B + SM_B_BYTES;         // [CL][32 rows][<= 48 cols] 
 constexpr int SM_RECV_BYTES = CL * 32 * 48 * 4;
 constexpr int SM_MISC = SM_RECV + SM_RECV_BYTES;   // mbarriers, TMEM slot, small reductions
 constexpr int SMEM_BYTES = SM_MISC + 1024 + 1024;  // + slack for the 1024-byte alignment of the base
-constexpr uint32_t TMEM_COLS = 64;
+constexpr uint32_t TMEM_COLS = 256;                // columns 0..63: a layer's accumulator; 64..191: the decoder hidden layer
 
 // Base of the (1024-byte aligned) dynamic shared memory, derived from the symbol itself: the compiler then knows every
 // pointer built from it is a shared-memory pointer and emits LDS / STS instead of generic loads and stores.
@@ -103,32 +103,45 @@ __device__ __forceinline__ long long gtime() {
       ++(c).tn;                                                        \
     }                                                                  \
   } while (0)
+// Operand format: every fp32 value v is carried as an fp16 pair hi = rn(v), lo = rn(v - hi): 22 mantissa bits
+// (|error| <= max(2^-23 |v|, 2^-25): the residual of a small value is an fp16 subnormal with absolute spacing 2^-24),
+// so hi*hi + hi*lo + lo*hi reproduces the fp32 product to ~2^-21 -- the fp32 parity tier.  Weights (|w| ~ 1e-2 at
+// initialisation, VAEB.py:54) are mirrored times WSCALE = 2^8 so that their residuals stay normal numbers; the
+// epilogue of a GEMM whose B operand is a weight mirror multiplies the sum by 2^-8 (exact).  Values are clamped to the
+// fp16 range (a weight beyond +-255 or a delta beyond +-65504 is saturated instead of becoming inf - inf = NaN).
+constexpr float WSCALE = 256.0f, WUNSCALE = 1.0f / 256.0f, H_MAX = 65504.0f;
+__device__ __forceinline__ float clamp_h(float v) { return fminf(fmaxf(v, -H_MAX), H_MAX); }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
-  const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  const __half2 t = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&t);
 }
-// eight fp32 -> eight bf16 hi + eight bf16 lo (lo = the rounding residual: hi + lo carries 16 mantissa bits)
+// eight fp32 -> eight fp16 hi + eight fp16 lo
+template <bool CLAMP = false>
 __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    h[q] = pack2(v[2 * q], v[2 * q + 1]);
-    l[q] = pack2(v[2 * q] - __uint_as_float(h[q] << 16), v[2 * q + 1] - __uint_as_float(h[q] & 0xffff0000u));
+    const float a = CLAMP ? clamp_h(v[2 * q]) : v[2 * q], b = CLAMP ? clamp_h(v[2 * q + 1]) : v[2 * q + 1];
+    h[q] = pack2(a, b);
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[q]));
+    l[q] = pack2(a - f.x, b - f.y);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
+template <bool CLAMP = false>
 __device__ __forceinline__ void put_unit(uint8_t* d, int half_bytes, const float* v) {
   uint4 hi, lo;
-  split8(v, hi, lo);
+  split8<CLAMP>(v, hi, lo);
   *reinterpret_cast<uint4*>(d) = hi;
   *reinterpret_cast<uint4*>(d + half_bytes) = lo;
 }
 // one element (hi at d, lo half_bytes later)
-__device__ __forceinline__ void put_bf(uint8_t* d, int half_bytes, float v) {
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  *reinterpret_cast<__nv_bfloat16*>(d) = h;
-  *reinterpret_cast<__nv_bfloat16*>(d + half_bytes) = __float2bfloat16_rn(v - __bfloat162float(h));
+__device__ __forceinline__ void put_hl(uint8_t* d, int half_bytes, float v) {
+  v = clamp_h(v);
+  const __half h = __float2half_rn(v);
+  *reinterpret_cast<__half*>(d) = h;
+  *reinterpret_cast<__half*>(d + half_bytes) = __float2half_rn(v - __half2float(h));
 }
 // branch-free tanh, relative error < 5e-6 (as the bf16x3 layer kernels, tc_layers.cu)
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -226,7 +239,7 @@ __device__ __forceinline__ void stage_x_T(uint8_t* sm, const float* __restrict__
 // (the generic-proxy writes the copies read were fenced towards the async proxy by their WRITERS, before the grid
 // barrier that ordered them before this thread: grid_barrier)
 __device__ __forceinline__ void ops_begin(Ctx& c, uint32_t bytes) { tc::mbar_expect_tx(c.op_bar, bytes); }
-// acc[128 x N] = sum over nch chunks / k16_total k steps of A.B^T in bf16x3.  Called by EVERY thread; `wait_ops`: the
+// acc[128 x N] = sum over nch chunks / k16_total k steps of A.B^T (three MMAs per k step).  Called by EVERY thread; `wait_ops`: the
 // issuing thread first waits for the bulk copies announced by ops_begin.  Returns when the accumulator is complete.
 __device__ __forceinline__ void mma_run(Ctx& c, int nch, int k16_total, int TBB, int N, bool wait_ops) {
   tc::fence_proxy_async();            // this thread's shared-memory stores -> visible to the tensor core (async proxy)
@@ -240,7 +253,7 @@ __device__ __forceinline__ void mma_run(Ctx& c, int nch, int k16_total, int TBB,
       tc::tc_fence_after();
     }
     if (nch > 0) {
-      const uint32_t idesc = tc::make_idesc_bf16(MP, N, 0, 0);
+      const uint32_t idesc = tc::make_idesc_f16(MP, N, 0, 0);
       // descriptor = constant fields | (address >> 4); the address field (14 bits) never overflows: smem < 256 KB
       const uint64_t d0 = tc::make_smem_desc(0u, 16u, 1024u);
       const uint64_t a0 = d0 | (uint64_t)(tc::smem_u32(c.sm + SM_A) >> 4), b0 = d0 | (uint64_t)(tc::smem_u32(c.sm + SM_B) >> 4);
@@ -295,7 +308,7 @@ __device__ __forceinline__ float recv_sum(const float* recv, int N, int row, int
   return s;
 }
 
-struct Hyper { float lr, eps, prior, p2; };
+struct Hyper { float lr, eps, prior, p2, w; };   // w: the factor of the data term (1, or 1/M for the mean objective)
 // Adagrad on the (up to) eight parameters one epilogue thread owns: every load is issued before the first store
 // (one L2 round trip per unit), 16-byte accesses when the eight are contiguous and aligned.  nv = the new values.
 __device__ __forceinline__ void adagrad8(float* P, float* ada, const size_t* off, const bool* ok, const float* g,
@@ -318,7 +331,7 @@ __device__ __forceinline__ void adagrad8(float* P, float* ada, const size_t* off
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const float gg = g[e] - hy.prior * p[e];             // VAEB.py:389-390
+    const float gg = fmaf(g[e], hy.w, -hy.prior * p[e]);     // VAEB.py:389-390
     a[e] += gg * gg;                                      // VAEB.py:439
     float q = p[e] + hy.lr * gg / (sqrtf(a[e]) + hy.eps); // VAEB.py:441
     if (hy.p2 != 0.f) q -= hy.p2 * p[e] * p[e];           // VAEBfullbayes.py:183-184
@@ -338,7 +351,7 @@ __device__ __forceinline__ void adagrad8(float* P, float* ada, const size_t* off
 // one element of a weight mirror: tiles of TR rows (tile index nt, row r inside it), KC chunks per tile
 __device__ __forceinline__ void mirror_put(uint8_t* m, int TR, int KC, int nt, int r, int k, float v) {
   const int TB = TR * 128;
-  put_bf(m + ((size_t)nt * KC + (k >> 6)) * 2 * TB + tc::sw128_offset(r, k & 63), TB, v);
+  put_hl(m + ((size_t)nt * KC + (k >> 6)) * 2 * TB + tc::sw128_offset(r, k & 63), TB, v * WSCALE);
 }
 
 // ---- grid barrier (monotonic counter, release / acquire at gpu scope) --------------------------------------------
@@ -381,10 +394,10 @@ __device__ __forceinline__ void item_enc1(Ctx& c, const Params& p, const float* 
   ST2_TRACE(c, 13);
   const float* recv = reinterpret_cast<const float*>(c.sm + SM_RECV);
   if (gr < p.M) {
-    const float v = j < p.H ? tanh_fast(recv_sum(recv, TR_ENC1, row, col) + bias) : 0.f;
+    const float v = j < p.H ? tanh_fast(fmaf(recv_sum(recv, TR_ENC1, row, col), WUNSCALE, bias)) : 0.f;
     he[(size_t)gr * p.HP + j] = v;
-    put_bf(km_addr(p.he_km, gr, j), TBA, v);
-    if (j < p.H) put_bf(t_addr(he_t, j >> 7, TBA, j & 127, gr), TBA, v);
+    put_hl(km_addr(p.he_km, gr, j), TBA, v);
+    if (j < p.H) put_hl(t_addr(he_t, j >> 7, TBA, j & 127, gr), TBA, v);
   }
   ST2_TRACE(c, 14);
   if (more) cluster_sync();          // the receive buffer is reused by this cluster's next item of the phase
@@ -432,14 +445,15 @@ __device__ __forceinline__ void item_heads(Ctx& c, const Params& p, uint32_t ste
     const int gr = c.rank * 32 + row;
     float tv = 0.f;
     if (gr < p.M) {
-      const float am = recv_sum(recv, N, row, j) + b4_[i];
-      const float al = recv_sum(recv, N, row, Z + j) + b5_[i];
+      const float am = fmaf(recv_sum(recv, N, row, j), WUNSCALE, b4_[i]);
+      const float al = fmaf(recv_sum(recv, N, row, Z + j), WUNSCALE, b5_[i]);
       const size_t o = (size_t)gr * Z + j;
       const float e = e_[i];
       const float zv = am + expf(0.5f * al) * e;
-      p.mu[o] = am; p.ls[o] = al; p.z[o] = zv; p.zT[(size_t)j * MP + gr] = zv;
+      p.mu[o] = am; p.ls[o] = al; p.z[o] = zv;
+      put_hl(km_addr(p.z_km, gr, j), TBA, zv);
       if (p.eps_inj) p.eps[o] = e;
-      put_bf(t_addr(p.z_t, 0, zt_half, j, gr), zt_half, zv);
+      put_hl(t_addr(p.z_t, 0, zt_half, j, gr), zt_half, zv);
       tv = p.la ? (-0.5f * zv * zv + 0.5f * al + 0.5f * e * e) : 0.5f * (1.0f + al - am * am - expf(al));
     }
     term[it] = tv;
@@ -466,28 +480,18 @@ __device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* 
   const int c0 = c.rank * p.KH / CL, c1 = (c.rank + 1) * p.KH / CL, nch = c1 - c0;
   constexpr int TB = TR_DEC2 * 128;
   const int Z = p.Z, H = p.H, M = p.M;
-  // producer scratch: z^T [Z][128] and, per k chunk, W1[:, chunk] as [Z][low / high half of an octet][8 octets][4]
-  // (the eight 16-byte loads of a quarter warp are then 128 contiguous bytes: no bank conflicts) + b1[chunk]
-  constexpr int WP = 64;                                        // floats per q row of a staged W1 chunk
-  float* zsT = reinterpret_cast<float*>(c.sm + SM_SCR);         // [Z][MP]
-  float* ws = zsT + Z * MP;                                     // [2][Z][WP]
-  float* bs = ws + 2 * Z * WP;                                  // [2][64]
+  // Operands of BOTH GEMMs of the item in one transaction: [z|1] (A of the hidden layer) into the last chunk of the A
+  // region, this rank's 64-unit tiles of [W1^T|b1] behind the W2 blob in the B region.
+  constexpr int T1 = 64 * 128;                                  // one half (hi or lo) of a [W1^T|b1] tile
+  uint8_t* z_sm = c.sm + SM_A + 3 * 2 * TBA;
+  uint8_t* w1_sm = c.sm + SM_B + 16384;
   if (threadIdx.x == 0 && nch > 0) {
-    ops_begin(c, (uint32_t)(nch * 2 * TB));
+    ops_begin(c, (uint32_t)(nch * 2 * TB + 2 * TBA + nch * 2 * T1));
+    bulk_g2s(z_sm, p.z_km, (uint32_t)(2 * TBA), c.op_bar);
+    bulk_g2s(w1_sm, p.m_dec1 + (size_t)c0 * 2 * T1, (uint32_t)(nch * 2 * T1), c.op_bar);
     bulk_g2s(c.sm + SM_B, p.m_dec2 + ((size_t)t * p.KH + c0) * 2 * TB, (uint32_t)(nch * 2 * TB), c.op_bar);
   }
-  {
-    float zr[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int e = threadIdx.x + i * NT;
-      zr[i] = e < Z * MP ? __ldcg(p.zT + e) : 0.f;              // rows >= M of z^T stay zero (never written)
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-      if ((int)threadIdx.x + i * NT < Z * MP) zsT[threadIdx.x + i * NT] = zr[i];
-  }
-  // this thread's two elements of the final stage: x and the output bias (in flight during the producer and the MMAs)
+  // this thread's two elements of the final stage: x and the output bias (in flight during both GEMMs)
   float xv_[2], b2_[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -498,108 +502,100 @@ __device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* 
     b2_[i] = ok ? __ldcg(p.P + p.ob2 + n) : 0.f;
   }
   ST2_TRACE(c, 36);
-  for (int cp = 0; cp < nch; cp += 2) {                          // two k chunks per pass: 2 x 32 row groups x 8 octets = 512 threads
-    __syncthreads();
-    {
-      float wr[5]; float br = 0.f;
+  // ---- hidden layer on the tensor cores: D1[128 x 64 nch] = [z|1] . [W1^T|b1]^T (K = 32: latent code + bias) --------
+  tc::tc_fence_before();
+  __syncthreads();                                              // the previous item's TMEM reads are complete
+  tc::tc_fence_after();
+  if (threadIdx.x == 0 && nch > 0) {
+    tc::mbar_wait(c.op_bar, c.op_phase);
+    c.op_phase ^= 1u;
+    tc::tc_fence_after();
+    const uint32_t idesc = tc::make_idesc_f16(MP, 64, 0, 0);
+    const uint64_t d0 = tc::make_smem_desc(0u, 16u, 1024u);
+    const uint64_t a = d0 | (uint64_t)(tc::smem_u32(z_sm) >> 4);
+    const uint32_t a_lo = TBA >> 4, b_lo = T1 >> 4;
+    for (int ci = 0; ci < nch; ++ci) {
+      const uint64_t b = d0 | (uint64_t)((tc::smem_u32(w1_sm) + (uint32_t)ci * 2u * T1) >> 4);
+      const uint32_t dcol = c.tmem + 64u + (uint32_t)ci * 64u;
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const int e = threadIdx.x + i * NT;                      // (chunk half, q, kk): 2 x Z x 64
-        const int hc = e / (Z * 64), r2 = e - hc * Z * 64;
-        const int q = r2 >> 6, kk = r2 & 63;
-        const int k = (c0 + cp + hc) * 64 + kk;
-        wr[i] = (e < 2 * Z * 64 && cp + hc < nch && k < H) ? __ldcg(p.P + p.oW1 + (size_t)q * H + k) : 0.f;
-      }
-      if (threadIdx.x < 128) {
-        const int k = (c0 + cp + (threadIdx.x >> 6)) * 64 + (threadIdx.x & 63);
-        if (cp + (int)(threadIdx.x >> 6) < nch && k < H) br = __ldcg(p.P + p.ob1 + k);
-      }
-#pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const int e = threadIdx.x + i * NT;
-        if (e < 2 * Z * 64) {
-          const int hc = e / (Z * 64), r2 = e - hc * Z * 64;
-          const int q = r2 >> 6, kk = r2 & 63;
-          ws[(hc * Z + q) * WP + ((kk >> 2) & 1) * 32 + (kk >> 3) * 4 + (kk & 3)] = wr[i];
-        }
-      }
-      if (threadIdx.x < 128) bs[threadIdx.x] = br;
-    }
-    __syncthreads();
-    ST2_TRACE(c, 38);
-    const int hc = threadIdx.x >> 8, rg = (threadIdx.x >> 3) & 31, cu = threadIdx.x & 7;
-    const int ci = cp + hc;
-    if (ci < nch) {
-      const int k0 = (c0 + ci) * 64;
-      float v[4][8];
-      if (rg * 4 < M) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[i][e] = bs[hc * 64 + cu * 8 + e];
-        const float* wq = ws + hc * Z * WP + cu * 4;
-        const float* zq = zsT + rg * 4;
-#pragma unroll 4
-        for (int q = 0; q < Z; ++q) {
-          const float4 w0 = *reinterpret_cast<const float4*>(wq + q * WP);
-          const float4 w1 = *reinterpret_cast<const float4*>(wq + q * WP + 32);
-          const float4 z4 = *reinterpret_cast<const float4*>(zq + q * MP);
-          const float zz[4] = {z4.x, z4.y, z4.z, z4.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            v[i][0] = fmaf(zz[i], w0.x, v[i][0]); v[i][1] = fmaf(zz[i], w0.y, v[i][1]);
-            v[i][2] = fmaf(zz[i], w0.z, v[i][2]); v[i][3] = fmaf(zz[i], w0.w, v[i][3]);
-            v[i][4] = fmaf(zz[i], w1.x, v[i][4]); v[i][5] = fmaf(zz[i], w1.y, v[i][5]);
-            v[i][6] = fmaf(zz[i], w1.z, v[i][6]); v[i][7] = fmaf(zz[i], w1.w, v[i][7]);
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = rg * 4 + i;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[i][e] = (r < M && k0 + cu * 8 + e < H) ? tanh_fast(v[i][e]) : 0.f;
-        if (r < M && r % p.n_tiles3 == t) {                      // every cluster publishes a few rows of h_d for P4 / P5
-          float* o = p.hd + (size_t)r * p.HP + k0 + cu * 8;
-          *reinterpret_cast<float4*>(o) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
-          *reinterpret_cast<float4*>(o + 4) = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int k = k0 + cu * 8 + e;
-            if (k < H) put_bf(t_addr(p.hd_t, k >> 7, TBA, k & 127, r), TBA, v[i][e]);
-          }
-        }
-        put_unit(c.sm + SM_A + (size_t)ci * 2 * TBA + unit_off(r, cu), TBA, v[i]);
+      for (int k = 0; k < 2; ++k) {
+        tc::umma_bf16(dcol, a + 2 * k, b + 2 * k, idesc, k ? 1u : 0u);
+        tc::umma_bf16(dcol, a + 2 * k, b + b_lo + 2 * k, idesc, 1u);
+        tc::umma_bf16(dcol, a + a_lo + 2 * k, b + 2 * k, idesc, 1u);
       }
     }
-    ST2_TRACE(c, 39);
+    tc::umma_commit(c.mma_bar);
   }
+  if (nch > 0) {
+    tc::mbar_wait(c.mma_bar, c.mma_phase);
+    c.mma_phase ^= 1u;
+    tc::tc_fence_after();
+  }
+  ST2_TRACE(c, 38);
+  {
+    // h_d = tanh(D1) (the bias rode along as latent column Z) -> the A tile of the output layer; thread = batch row,
+    // eight consecutive hidden units per TMEM read = one 16-byte unit of the tile
+    const int q = c.warp & 3, cg = c.warp >> 2;                 // lane quarter; 32-column group of the (up to) 128 columns
+    const int r = q * 32 + c.lane;
+    if (cg * 32 < nch * 64) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+        tmem_ld8(c.tmem + ((uint32_t)(q * 32) << 16) + 64u + (uint32_t)(cg * 32 + u * 8), v);
+        tc::tmem_ld_wait();
+        const int kl = cg * 32 + u * 8;                          // column inside this rank's slice
+        const int k0 = c0 * 64 + kl;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (r < M && k0 + e < H) ? tanh_fast(v[e] * WUNSCALE) : 0.f;
+        if (r < M && r % p.n_tiles3 == t) {                      // every cluster publishes a few rows of h_d for P4 / P5
+          float* o = p.hd + (size_t)r * p.HP + k0;
+          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (k0 + e < H) put_hl(t_addr(p.hd_t, (k0 + e) >> 7, TBA, (k0 + e) & 127, r), TBA, v[e]);
+        }
+        put_unit(c.sm + SM_A + (size_t)(kl >> 6) * 2 * TBA + unit_off(r, (kl & 63) >> 3), TBA, v);
+      }
+    }
+  }
+  ST2_TRACE(c, 39);
   ST2_TRACE(c, 31);
-  mma_run(c, nch, nch * 4, TB, TR_DEC2, nch > 0);
+  mma_run(c, nch, nch * 4, TB, TR_DEC2, false);
   ST2_TRACE(c, 32);
   reduce_scatter(c, TR_DEC2, nch > 0);
   ST2_TRACE(c, 33);
   const float* recv = reinterpret_cast<const float*>(c.sm + SM_RECV);
   float* term = reinterpret_cast<float*>(c.sm + SM_B);          // [32][32]
+  float* dtile = term + 32 * 32;                                // [32][33]
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int it = threadIdx.x + i * NT;
     const int row = it >> 5, col = it & 31;
     const int gr = c.rank * 32 + row, n = t * TR_DEC2 + col;
-    float tv = 0.f;
+    float tv = 0.f, dval = 0.f;
     if (gr < M && n < p.D) {
-      const float a = recv_sum(recv, TR_DEC2, row, col) + b2_[i];
+      const float a = fmaf(recv_sum(recv, TR_DEC2, row, col), WUNSCALE, b2_[i]);
       const float xv = xv_[i];
       float sp, sg;
       softplus_sigmoid(a, sp, sg);
-      const float d = p.w * (xv - sg);
-      put_bf(km_addr(p.da2_km, gr, n), TBA, d);
-      put_bf(t_addr(p.da2_t, t, TB, col, gr), TB, d);
+      const float d = xv - sg;                                 // deltas are carried without the factor w (applied with the weight gradients)
+      put_hl(km_addr(p.da2_km, gr, n), TBA, d);
+      dval = d;
       tv = xv * a - sp;
     }
     term[it] = tv;
+    dtile[row * 33 + col] = dval;
   }
   __syncthreads();
+  // the transposed mirror (operand of the W2 gradient) with the lanes along the batch rows: 64 contiguous bytes per store
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int it = threadIdx.x + i * NT;
+    const int col = it >> 5, row = it & 31;
+    const int gr = c.rank * 32 + row, n = t * TR_DEC2 + col;
+    if (gr < M && n < p.D) put_hl(t_addr(p.da2_t, t, TB, col, gr), TB, dtile[row * 33 + col]);
+  }
   if (threadIdx.x < 32) {
     const int gr = c.rank * 32 + threadIdx.x;
     if (gr < M) {
@@ -634,9 +630,9 @@ __device__ __forceinline__ void item_dgrad(Ctx& c, const Params& p, int t, bool 
   ST2_TRACE(c, 43);
   const float* recv = reinterpret_cast<const float*>(c.sm + SM_RECV);
   if (gr < p.M) {
-    const float d = recv_sum(recv, TR_DGRAD, row, col) * (1.0f - hv * hv);
-    put_bf(km_addr(p.da1_km, gr, j), TBA, d);
-    if (j < p.H) put_bf(t_addr(p.da1_t, j >> 7, TBA, j & 127, gr), TBA, d);
+    const float d = recv_sum(recv, TR_DGRAD, row, col) * WUNSCALE * (1.0f - hv * hv);
+    put_hl(km_addr(p.da1_km, gr, j), TBA, d);
+    if (j < p.H) put_hl(t_addr(p.da1_t, j >> 7, TBA, j & 127, gr), TBA, d);
   }
   ST2_TRACE(c, 44);
   if (more) cluster_sync();          // the receive buffer is reused by this cluster's next item of the phase
@@ -680,19 +676,19 @@ __device__ __forceinline__ void item_dz(Ctx& c, const Params& p, bool more) {
     const int row = it / Z, j = it - row * Z;
     const int gr = c.rank * 32 + row;
     if (gr < p.M) {
-      float d = recv_sum(recv, N, row, j);
-      if (p.la) d -= p.w * zm_[i];
+      float d = recv_sum(recv, N, row, j) * WUNSCALE;
+      if (p.la) d -= zm_[i];
       float a = d, b = d * (0.5f * expf(0.5f * ls_[i]) * ev_[i]);
       if (p.la) {
-        b += p.w * 0.5f;
+        b += 0.5f;
       } else {
-        a -= p.w * zm_[i];
-        b += p.w * 0.5f * (1.0f - expf(ls_[i]));
+        a -= zm_[i];
+        b += 0.5f * (1.0f - expf(ls_[i]));
       }
       p.ddT[(size_t)j * MP + gr] = a;
       p.ddT[(size_t)(Z + j) * MP + gr] = b;
-      put_bf(t_addr(p.dd_t, j >> 4, 2048, j & 15, gr), 2048, a);                 // [dmu|dls]^T in tiles of 16 columns
-      put_bf(t_addr(p.dd_t, (Z + j) >> 4, 2048, (Z + j) & 15, gr), 2048, b);
+      put_hl(t_addr(p.dd_t, j >> 4, 2048, j & 15, gr), 2048, a);                 // [dmu|dls]^T in tiles of 16 columns
+      put_hl(t_addr(p.dd_t, (Z + j) >> 4, 2048, (Z + j) & 15, gr), 2048, b);
     }
   }
   ST2_TRACE(c, 54);
@@ -723,7 +719,7 @@ __device__ __forceinline__ void wgrad_epilogue(Ctx& c, int N, F fn) {
 //   B  lane = column: a warp instruction reads / writes ONE contiguous row segment of the parameters and of the
 //      accumulators (the uncoalesced form touches 32 lines per instruction and is bound by L1 request processing:
 //      3.6 us per tile measured), Adagrad, the new values go back into the tile;
-//   C  thread = row again: `mir(row, col0, nv[8])` writes the bf16 mirrors (their k index runs along the rows).
+//   C  thread = row again: `mir(row, col0, nv[8])` writes the fp16 mirrors (their k index runs along the rows).
 // off(row, col) = flat offset of the parameter behind accumulator element (row, col), or -1.
 template <int N>
 struct WgPre {                                                     // parameters / accumulators of phase B, loaded early
@@ -762,7 +758,7 @@ __device__ __forceinline__ void wgrad_epilogue_coalesced(Ctx& c, const Params& p
     for (int r = 0; r < WgPre<N>::NP; ++r) {
       const int row = c.warp * 8 + r * WgPre<N>::RPP + rsub;
       if (w.o[r] >= 0) {
-        const float gg = gt[row * GP + col] - hy.prior * w.pv[r];  // VAEB.py:389-390
+        const float gg = fmaf(gt[row * GP + col], hy.w, -hy.prior * w.pv[r]);  // VAEB.py:389-390
         const float a = w.av[r] + gg * gg;                         // VAEB.py:439
         float nv = w.pv[r] + hy.lr * gg / (sqrtf(a) + hy.eps);     // VAEB.py:441
         if (hy.p2 != 0.f) nv -= hy.p2 * w.pv[r] * w.pv[r];         // VAEBfullbayes.py:183-184
@@ -809,9 +805,11 @@ __device__ __forceinline__ void item_wg2(Ctx& c, const Params& p, const Hyper& h
         for (int e = 0; e < 8; ++e)
           if (n0 + e < D) mirror_put(p.m_dec2, TR_DEC2, p.KH, nt, col0 + e, i, nv[e]);
           else nv[e] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) nv[e] *= WSCALE;
         // dgrad mirror: row = hidden unit i, k = pixel: eight consecutive k = one 16-byte unit (n0 is a multiple of 8)
         constexpr int TG = TR_DGRAD * 128;
-        put_unit(p.m_dgrad + ((size_t)(i >> 4) * p.KD + (n0 >> 6)) * 2 * TG + unit_off(i & 15, (n0 & 63) >> 3), TG, nv);
+        put_unit<true>(p.m_dgrad + ((size_t)(i >> 4) * p.KD + (n0 >> 6)) * 2 * TG + unit_off(i & 15, (n0 & 63) >> 3), TG, nv);
       });
   ST2_TRACE(c, 62);
 }
@@ -914,8 +912,10 @@ __device__ __forceinline__ void item_wg1(Ctx& c, const Params& p, const Hyper& h
     }
     adagrad8(p.P, p.ada, off, ok, v, hy, nv);
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
+    for (int e = 0; e < 8; ++e) {
       if (col0 + e < Z) mirror_put(p.m_dz, N, p.KH, 0, col0 + e, i, nv[e]);
+      if (col0 + e <= Z) mirror_put(p.m_dec1, 64, 1, i >> 6, i & 63, col0 + e, nv[e]);      // [W1^T | b1] of the hidden layer
+    }
   });
 }
 
@@ -1020,7 +1020,7 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
 
   const int G = gridDim.x;
   unsigned long long target = p.bar_base;
-  const Hyper hy{p.lr, p.ada_eps, p.prior, p.p2};
+  const Hyper hy{p.lr, p.ada_eps, p.prior, p.p2, p.w};
   const bool rec = p.timing != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   const int n1 = p.HP / 16;                         // enc1 / dgrad tiles
   const int n3 = p.n_tiles3;                        // dec2 tiles
@@ -1120,8 +1120,8 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
 
 // ---- mirrors from the fp32 master parameters (after set_tensors / load / an update by another path) ----------------
 struct MirrorArgs {
-  const float* P; int64_t oW3, oW4, oW5, oW1, oW2;
-  uint8_t *m_enc1, *m_heads, *m_dec2, *m_dgrad, *m_dz;
+  const float* P; int64_t oW3, oW4, oW5, oW1, oW2, ob1;
+  uint8_t *m_enc1, *m_heads, *m_dec2, *m_dgrad, *m_dz, *m_dec1;
   int D, H, Z, HP, KD, KH, NH, NZ;
 };
 __global__ void __launch_bounds__(256) build_mirrors_kernel(MirrorArgs a) {
@@ -1158,6 +1158,14 @@ __global__ void __launch_bounds__(256) build_mirrors_kernel(MirrorArgs a) {
       mirror_put(a.m_dgrad, TR_DGRAD, a.KD, n / TR_DGRAD, n % TR_DGRAD, k, (n < H && k < D) ? a.P[a.oW2 + (size_t)n * D + k] : 0.f);
       break;
     }
+    case 5: {   // dec1: n = hidden (tiles of 64), k = latent index, k = Z: the bias
+      if (i >= (int64_t)a.HP * 64) return;
+      const int n = (int)(i / 64), k = (int)(i % 64);
+      float v = 0.f;
+      if (n < H) v = k < Z ? a.P[a.oW1 + (size_t)k * H + n] : (k == Z ? a.P[a.ob1 + n] : 0.f);
+      mirror_put(a.m_dec1, 64, 1, n >> 6, n & 63, k, v);
+      break;
+    }
     default: {  // dz: n = latent (NZ rows), k = hidden
       const int K = a.KH * 64;
       if (i >= (int64_t)a.NZ * K) return;
@@ -1170,14 +1178,15 @@ __global__ void __launch_bounds__(256) build_mirrors_kernel(MirrorArgs a) {
 
 // constant rows of the transposed activation mirrors: the "ones" feature that turns a weight-gradient GEMM's extra row /
 // column into the bias gradient (h_e and h_d: feature H; z: feature Z).  Everything else starts as zero.
-struct OnesArgs { uint8_t *he_t, *hd_t, *z_t; int H, Z, NZ; };
+struct OnesArgs { uint8_t *he_t, *hd_t, *z_t, *z_km; int H, Z, NZ; };
 __global__ void __launch_bounds__(128) init_ones_kernel(OnesArgs a) {
   const int b = threadIdx.x;                       // batch column 0..127
-  const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
+  const __half one = __float2half_rn(1.0f);
   uint8_t* m[2] = {a.he_t, a.hd_t};
   for (int q = 0; q < 2; ++q)
-    *reinterpret_cast<__nv_bfloat16*>(t_addr(m[q], a.H >> 7, TBA, a.H & 127, b)) = one;
-  *reinterpret_cast<__nv_bfloat16*>(t_addr(a.z_t, 0, a.NZ * 128, a.Z, b)) = one;
+    *reinterpret_cast<__half*>(t_addr(m[q], a.H >> 7, TBA, a.H & 127, b)) = one;
+  *reinterpret_cast<__half*>(t_addr(a.z_t, 0, a.NZ * 128, a.Z, b)) = one;
+  *reinterpret_cast<__half*>(km_addr(a.z_km, b, a.Z)) = one;      // [z | 1]: batch row b, column Z
 }
 
 }  // namespace st2
@@ -1190,13 +1199,13 @@ bool step_tc_supported(const vaeb_handle* h, int rows) {
   if (h->steptc.unavailable || h->steptc_off) return false;
   return (e == VAEB_EST_LB || e == VAEB_EST_LA) && !h->cont && h->L == 1 && h->world == 1 &&
          h->cfg.precision != VAEB_PREC_BF16 && h->optimizer == VAEB_OPT_ADAGRAD && rows >= 1 && rows <= st2::MP &&
-         (h->D % 8) == 0 && (h->H % 4) == 0 && h->D >= 64 && h->H >= 64 && h->D <= 1024 && h->H <= 1024 && h->Z >= 1 &&
+         (h->D % 8) == 0 && (h->H % 4) == 0 && h->D >= 64 && h->H >= 64 && h->D <= 1024 && h->H <= 512 && h->Z >= 1 &&
          h->Z <= 20;
 }
 
 void step_tc_free(StepTcState& s) {
-  void* ptrs[] = {s.bar, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz, s.act, s.he, s.hd, s.mu, s.ls,
-                  s.eps, s.z, s.zT, s.ddT, s.w45s, s.partial, s.aux, s.d_order, s.d_timing};
+  void* ptrs[] = {s.bar, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz, s.m_dec1, s.act, s.he, s.hd, s.mu, s.ls,
+                  s.eps, s.z, s.ddT, s.w45s, s.partial, s.aux, s.d_order, s.d_timing};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   s = StepTcState();
@@ -1232,6 +1241,7 @@ static int step_tc_init(vaeb_handle* h) {
   VAEB_CUDA(alloc((void**)&s.m_heads, (size_t)NH * KH * 64 * 4));
   VAEB_CUDA(alloc((void**)&s.m_dec2, (size_t)n3 * TR_DEC2 * KH * 64 * 4));
   VAEB_CUDA(alloc((void**)&s.m_dz, (size_t)NZ * KH * 64 * 4));
+  VAEB_CUDA(alloc((void**)&s.m_dec1, (size_t)HP * 64 * 4));
   // activation mirrors in one allocation (cleared together when the minibatch size changes)
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t at_ = o; o += (bytes + 1023) / 1024 * 1024; return at_; };
@@ -1244,11 +1254,11 @@ static int step_tc_init(vaeb_handle* h) {
   s.o_da1_t = take((size_t)m_h1 * 4 * TBA);
   s.o_dd_t = take((size_t)4 * NH * 128);
   s.o_z_t = take((size_t)4 * NZ * 128);
+  s.o_z_km = take((size_t)2 * TBA);
   s.act_bytes = o;
   VAEB_CUDA(alloc((void**)&s.act, s.act_bytes));
   VAEB_CUDA(alloc((void**)&s.he, (size_t)MP * HP * 4));
   VAEB_CUDA(alloc((void**)&s.hd, (size_t)MP * HP * 4));
-  VAEB_CUDA(alloc((void**)&s.zT, (size_t)Z * MP * 4));
   VAEB_CUDA(alloc((void**)&s.ddT, (size_t)2 * Z * MP * 4));
   VAEB_CUDA(alloc((void**)&s.w45s, (size_t)2 * Z * HP * 4));
   VAEB_CUDA(alloc((void**)&s.mu, (size_t)MP * Z * 4));
@@ -1286,14 +1296,15 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
   p.oW3 = l.off[l.iW3]; p.oW4 = l.off[l.iW4]; p.oW5 = l.off[l.iW5]; p.oW1 = l.off[l.iW1]; p.oW2 = l.off[l.iW2];
   p.ob3 = l.off[l.ib3]; p.ob4 = l.off[l.ib4]; p.ob5 = l.off[l.ib5]; p.ob1 = l.off[l.ib1]; p.ob2 = l.off[l.ib2];
   p.m_enc1 = s.m_enc1; p.m_heads = s.m_heads; p.m_dec2 = s.m_dec2; p.m_dgrad = s.m_dgrad; p.m_dz = s.m_dz;
+  p.m_dec1 = s.m_dec1;
   p.he_km = s.act + s.o_he_km; p.he_t = s.act + s.o_he_t; p.hd_t = s.act + s.o_hd_t;
   p.da2_km = s.act + s.o_da2_km; p.da2_t = s.act + s.o_da2_t; p.da1_km = s.act + s.o_da1_km; p.da1_t = s.act + s.o_da1_t;
-  p.dd_t = s.act + s.o_dd_t; p.z_t = s.act + s.o_z_t;
+  p.dd_t = s.act + s.o_dd_t; p.z_t = s.act + s.o_z_t; p.z_km = s.act + s.o_z_km;
   p.x_base = (d_order && d_xrows) ? d_xrows : h->d_x; p.batch_order = d_order; p.x_direct = d_xrows;
   p.eps_inj = d_eps;
   p.seed = h->cfg.seed; p.step0 = h->step; p.row_offset = 0;
   p.he = s.he; p.hd = s.hd; p.mu = s.mu; p.ls = s.ls; p.eps = s.eps; p.z = s.z;
-  p.zT = s.zT; p.ddT = s.ddT; p.w45s = s.w45s;
+  p.ddT = s.ddT; p.w45s = s.w45s;
   p.partial = s.partial; p.aux = s.aux;
   p.scalars = h->d_scalars + slot0; p.Mg = (float)rows; p.bmult = 1.0f;
   p.n_steps = n_steps;
@@ -1303,8 +1314,7 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
     // batch columns >= rows of every activation mirror must read as zero (they are contraction rows of the weight
     // gradients): clear everything when the minibatch size changes, then restore the constant "ones" features
     VAEB_CUDA(cudaMemsetAsync(s.act, 0, s.act_bytes, h->stream));
-    OnesArgs oa{p.he_t, p.hd_t, p.z_t, H, Z, p.NZ};
-    VAEB_CUDA(cudaMemsetAsync(s.zT, 0, (size_t)Z * MP * 4, h->stream));
+    OnesArgs oa{p.he_t, p.hd_t, p.z_t, p.z_km, H, Z, p.NZ};
     VAEB_CUDA(cudaMemsetAsync(s.ddT, 0, (size_t)2 * Z * MP * 4, h->stream));
     init_ones_kernel<<<1, 128, 0, h->stream>>>(oa);
     VAEB_CUDA(cudaGetLastError());
@@ -1312,12 +1322,12 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
     s.rows_init = rows;
   }
   if (!s.mirrors_valid) {
-    MirrorArgs a{h->d_params, p.oW3, p.oW4, p.oW5, p.oW1, p.oW2, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz,
-                 D, H, Z, p.HP, p.KD, p.KH, p.NH, p.NZ};
+    MirrorArgs a{h->d_params, p.oW3, p.oW4, p.oW5, p.oW1, p.oW2, p.ob1, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz,
+                 s.m_dec1, D, H, Z, p.HP, p.KD, p.KH, p.NH, p.NZ};
     int64_t most = (int64_t)p.HP * p.KD * 64;
     most = std::max<int64_t>(most, (int64_t)p.n_tiles3 * TR_DEC2 * p.KH * 64);
     most = std::max<int64_t>(most, (int64_t)p.NH * p.KH * 64);
-    build_mirrors_kernel<<<dim3((unsigned)((most + 255) / 256), 5), 256, 0, h->stream>>>(a);
+    build_mirrors_kernel<<<dim3((unsigned)((most + 255) / 256), 6), 256, 0, h->stream>>>(a);
     VAEB_CUDA(cudaGetLastError());
     ++h->launches;
     s.mirrors_valid = true;

@@ -35,14 +35,16 @@ struct Params {
   int64_t oW3, oW4, oW5, oW1, oW2, ob3, ob4, ob5, ob1, ob2;
   // weight mirrors: [n tile][k chunk][hi, lo][rows x 128 B], K-major SWIZZLE_128B
   uint8_t *m_enc1, *m_heads, *m_dec2, *m_dgrad, *m_dz;
+  uint8_t* m_dec1;                      // [W1^T | b1]: tiles of 64 hidden units x one k chunk (k = latent index, k = Z: the bias)
   // activation mirrors.  *_km: [k chunk][hi, lo][128 batch rows x 128 B] (A operand of the next layer);
   // *_t: [feature tile][batch chunk (2)][hi, lo][tile rows x 128 B] (operands of the weight gradients)
   uint8_t *he_km, *he_t, *hd_t, *da2_km, *da2_t, *da1_km, *da1_t, *dd_t, *z_t;
+  uint8_t* z_km;                        // [z | 1]: one k chunk (column Z reads as 1: the bias of the decoder hidden layer)
   const float* x_base; const int* batch_order; const float* x_direct;
   const float* eps_inj;
   uint64_t seed; uint32_t step0; int64_t row_offset;
   float *he, *hd, *mu, *ls, *eps, *z;   // fp32 copies the epilogues read: [MP, HP], [MP, HP], [MP, Z] x 4
-  float *zT, *ddT;                      // z and [dmu|dls] transposed, fp32: [Z][MP], [2Z][MP] (software producers)
+  float* ddT;                           // [dmu|dls] transposed, fp32: [2Z][MP] (producer of the W3 gradient's B tile)
   float* w45s;                          // snapshot of [W4|W5]^T taken in P5: [2Z][HP] (the W3-gradient producer reads it
                                         // while the W4/W5 update of the same phase rewrites the parameters)
   float *partial, *aux;                 // [MP, tiles of dec2] log-likelihood row partials; [MP] KL / LA row terms
@@ -61,11 +63,11 @@ struct StepTcState {
   int n_cta = 0;
   int rows_init = -1;                   // minibatch rows the activation mirrors were cleared for
   unsigned long long* bar = nullptr; unsigned long long bar_count = 0;
-  uint8_t *m_enc1 = nullptr, *m_heads = nullptr, *m_dec2 = nullptr, *m_dgrad = nullptr, *m_dz = nullptr;
+  uint8_t *m_enc1 = nullptr, *m_heads = nullptr, *m_dec2 = nullptr, *m_dgrad = nullptr, *m_dz = nullptr, *m_dec1 = nullptr;
   uint8_t* act = nullptr; size_t act_bytes = 0;      // one allocation for every activation mirror
-  size_t o_he_km = 0, o_he_t = 0, o_hd_t = 0, o_da2_km = 0, o_da2_t = 0, o_da1_km = 0, o_da1_t = 0, o_dd_t = 0, o_z_t = 0;
+  size_t o_he_km = 0, o_he_t = 0, o_hd_t = 0, o_da2_km = 0, o_da2_t = 0, o_da1_km = 0, o_da1_t = 0, o_dd_t = 0, o_z_t = 0, o_z_km = 0;
   bool mirrors_valid = false;
-  float *he = nullptr, *hd = nullptr, *mu = nullptr, *ls = nullptr, *eps = nullptr, *z = nullptr, *zT = nullptr,
+  float *he = nullptr, *hd = nullptr, *mu = nullptr, *ls = nullptr, *eps = nullptr, *z = nullptr,
         *ddT = nullptr, *w45s = nullptr, *partial = nullptr, *aux = nullptr;
   int* d_order = nullptr; int order_cap = 0;
   long long* d_timing = nullptr; int timing_cap = 0;

@@ -413,8 +413,10 @@ def pinned_empty(shape, dtype=np.float32):
     dt = np.dtype(dtype)
     n = int(np.prod(shape)) * dt.itemsize
     blk = _PinnedBlock(max(n, 1))
-    arr = np.frombuffer(blk.buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
-    return arr            # arr.base chain keeps blk.buf (and with it blk) alive
+    buf = blk.buf
+    blk.buf = None
+    buf._owner = blk      # arr.base chain -> buf -> blk: the block is freed when the last view of it goes away
+    return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
 
 
 def comm_unique_id(nccl_library=None):
