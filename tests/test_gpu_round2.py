@@ -117,7 +117,8 @@ def test_c3_parameters_after_tensor_core_updates(precision):
     # after two steps p = p0 + lr*g1/|g1| + lr*g2/sqrt(g1^2+g2^2): the second term carries the gradient magnitudes
     for a, b, p0, w, n in zip(m.get_params(), o.params, params, well, O.param_names(False)):
         assert w.sum() >= 8, (n, w.sum())
-        np.testing.assert_allclose((a - p0)[w], (b - p0)[w], rtol=2e-3 if precision == "bf16x3" else 5e-2, atol=1e-7,
+        # atol: the two Adagrad terms cancel where g1 and g2 have opposite signs (0.2 % of the learning rate)
+        np.testing.assert_allclose((a - p0)[w], (b - p0)[w], rtol=2e-3 if precision == "bf16x3" else 5e-2, atol=2e-5,
                                    err_msg="params after 2 updates: " + n)
     ada = m._get_buffer(1)
     for a, b, w, n in zip(ada, o.ada, well, O.param_names(False)):

@@ -1455,10 +1455,10 @@ int vaeb_profile_update(vaeb_handle* h, int64_t index, int32_t iters, int32_t ma
     if (steps * (NP + 1) > f.timing_cap) {
       if (f.d_timing) cudaFree(f.d_timing);
       f.d_timing = nullptr;
-      VAEB_CUDA(cudaMalloc((void**)&f.d_timing, ((size_t)steps * (NP + 1) + 128) * sizeof(long long)));   // + sub-phase trace
+      VAEB_CUDA(cudaMalloc((void**)&f.d_timing, ((size_t)steps * (NP + 1) + 128 + 256 * NP) * sizeof(long long)));   // + sub-phase trace + per-CTA arrivals
       f.timing_cap = steps * (NP + 1);
     }
-    VAEB_CUDA(cudaMemsetAsync(f.d_timing, 0, ((size_t)steps * (NP + 1) + 128) * sizeof(long long), h->stream));
+    VAEB_CUDA(cudaMemsetAsync(f.d_timing, 0, ((size_t)steps * (NP + 1) + 128 + 256 * NP) * sizeof(long long), h->stream));
     if (steps > f.order_cap) {
       if (f.d_order) cudaFree(f.d_order);
       f.d_order = nullptr;
@@ -1470,7 +1470,7 @@ int vaeb_profile_update(vaeb_handle* h, int64_t index, int32_t iters, int32_t ma
     VAEB_CUDA(cudaStreamSynchronize(h->stream));
     VAEB_TRY(ensure_scalars(h, steps));
     rc = step_tc_launch(h, f.d_order, nullptr, h->M, steps, nullptr, 0, f.d_timing);
-    std::vector<long long> tm((size_t)steps * (NP + 1) + 128);
+    std::vector<long long> tm((size_t)steps * (NP + 1) + 128 + 256 * NP);
     if (rc == VAEB_OK) {
       VAEB_CUDA(cudaMemcpyAsync(tm.data(), f.d_timing, tm.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
       VAEB_CUDA(cudaStreamSynchronize(h->stream));
@@ -1478,6 +1478,14 @@ int vaeb_profile_update(vaeb_handle* h, int64_t index, int32_t iters, int32_t ma
         const long long* tr = tm.data() + (size_t)steps * (NP + 1);
         for (int q = 0; q < 60 && tr[2 * q] != 0; ++q)
           fprintf(stderr, "st2 trace %3lld  +%8.3f us\n", tr[2 * q], 1e-3 * (double)(tr[2 * q + 1] - tr[1]));
+        // arrival of every CTA at the barrier that ends each phase of the last step (us after the phase opened for CTA 0)
+        const long long* ar = tr + 128;
+        const long long* last = tm.data() + (size_t)(steps - 1) * (NP + 1);
+        for (int ph = 0; ph < NP; ++ph) {
+          fprintf(stderr, "st2 arrive P%d:", ph + 1);
+          for (int b = 0; b < f.n_cta && b < 256; ++b) fprintf(stderr, " %.1f", 1e-3 * (double)(ar[(size_t)b * NP + ph] - last[ph]));
+          fprintf(stderr, "\n");
+        }
       }
       const double dM = h->M, dD = h->D, dH = h->H, dZ = h->Z;
       const double fl[NP] = {2 * dM * dD * dH + 4 * dM * dH * dZ, 4 * dM * dH * dZ, 2 * dM * dZ * dH + 2 * dM * dH * dD,

@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "philox.cuh"
@@ -55,8 +56,8 @@ __device__ __forceinline__ uint8_t* smem_base() {
 struct Ctx {
   uint8_t* sm;
   uint32_t tmem;
-  uint64_t *mma_bar, *op_bar;
-  uint32_t mma_phase, op_phase;
+  uint64_t *mma_bar, *op_bar, *x_bar;
+  uint32_t mma_phase, op_phase, x_phase;
   int rank, cid, ncl, warp, lane;
   long long* trace; int tn;            // optional sub-phase stamps (CTA 0, thread 0, last step of a profiling launch)
 };
@@ -208,29 +209,32 @@ __device__ __forceinline__ void stage_x_rows(uint8_t* sm, const float* __restric
     }
   }
 }
-// A tile of the W3 gradient: rows = pixels f0 .. f0+127 (pixel == D reads as 1: the bias row), k = batch rows
-__device__ __forceinline__ void stage_x_T(uint8_t* sm, const float* __restrict__ x, int D, int M, int f0) {
-  float v[4][8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int u = threadIdx.x + i * NT;                          // 16 batch octets x 128 features
-    const int bo = u >> 7, f = f0 + (u & 127);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int b = bo * 8 + e;
-      float t = 0.f;
-      if (b < M) {
-        if (f == D) t = 1.0f;
-        else if (f < D) t = __ldcg(x + (size_t)b * D + f);
-      }
-      v[i][e] = t;
+// The minibatch as tensor-core operands, written to global memory (P2, by the clusters without a latent-head item):
+// x_km of the NEXT step (rows = batch rows, k = pixel: the A operand of enc1) and x_t of THIS step (rows = pixels, k =
+// batch rows: the A operand of the W3 gradient; the row of pixel D is the constant 1 that yields the bias gradient).
+// part / nparts: this CTA's share.  Rows >= M and pixels >= D are never written (zero since the mirrors were cleared).
+__device__ __forceinline__ void item_xmirrors(const Params& p, const float* __restrict__ x_next, const float* __restrict__ x_cur,
+                                              int part, int nparts) {
+  const int D = p.D, M = p.M, D8 = D >> 3;
+  if (x_next) {
+    const int nu = M * D8;                                       // (batch row, pixel octet): lanes along the pixels
+    for (int u = part * NT + threadIdx.x; u < nu; u += nparts * NT) {
+      const int r = u / D8, ku = u - r * D8;
+      const float* s = x_next + (size_t)r * D + ku * 8;
+      const float4 a0 = __ldcg(reinterpret_cast<const float4*>(s)), a1 = __ldcg(reinterpret_cast<const float4*>(s + 4));
+      const float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      put_unit(p.x_km + (size_t)(ku >> 3) * 2 * TBA + unit_off(r, ku & 7), TBA, v);
     }
   }
+  {
+    const int nbo = (M + 7) >> 3, nu = nbo * D;                  // (batch octet, pixel): lanes along the pixels
+    for (int u = part * NT + threadIdx.x; u < nu; u += nparts * NT) {
+      const int bo = u / D, f = u - bo * D;
+      float v[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int u = threadIdx.x + i * NT;
-    const int bo = u >> 7;
-    put_unit(sm + SM_A + (size_t)(bo >> 3) * 2 * TBA + unit_off(u & 127, bo & 7), TBA, v[i]);
+      for (int e = 0; e < 8; ++e) v[e] = bo * 8 + e < M ? __ldcg(x_cur + (size_t)(bo * 8 + e) * D + f) : 0.f;
+      put_unit(p.x_t + ((size_t)(f >> 7) * 2 + (bo >> 3)) * 2 * TBA + unit_off(f & 127, bo & 7), TBA, v);
+    }
   }
 }
 
@@ -375,15 +379,22 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned l
 // cluster items
 // =================================================================================================================
 // P1: h_e[:, 16t .. 16t+15] = tanh(x.W3 + b3)                                               VAEB.py:246
-__device__ __forceinline__ void item_enc1(Ctx& c, const Params& p, const float* x, float* he, uint8_t* he_t, int t, bool a_staged, bool more) {
+// a_mode: where the A tile (this rank's k chunks of x) comes from
+enum { A_BULK = 0,       // one bulk copy from x_km (written in P2 of the previous step), issued here
+       A_PREFETCHED = 1, // that bulk copy was issued before the grid barrier that opened the phase (x_bar)
+       A_STAGED = 2,     // already converted into shared memory by this CTA (first step of a launch)
+       A_SOFTWARE = 3 }; // convert from the fp32 rows now (first step of a launch, second item of a cluster)
+__device__ __forceinline__ void item_enc1(Ctx& c, const Params& p, const float* x, float* he, uint8_t* he_t, int t, int a_mode, bool more) {
   ST2_TRACE(c, 10);
   const int c0 = c.rank * p.KD / CL, c1 = (c.rank + 1) * p.KD / CL, nch = c1 - c0;
   constexpr int TB = TR_ENC1 * 128;
   if (threadIdx.x == 0 && nch > 0) {
-    ops_begin(c, (uint32_t)(nch * 2 * TB));
+    ops_begin(c, (uint32_t)(nch * 2 * TB + (a_mode == A_BULK ? nch * 2 * TBA : 0)));
+    if (a_mode == A_BULK) bulk_g2s(c.sm + SM_A, p.x_km + (size_t)c0 * 2 * TBA, (uint32_t)(nch * 2 * TBA), c.op_bar);
     bulk_g2s(c.sm + SM_B, p.m_enc1 + ((size_t)t * p.KD + c0) * 2 * TB, (uint32_t)(nch * 2 * TB), c.op_bar);
+    if (a_mode == A_PREFETCHED) { tc::mbar_wait(c.x_bar, c.x_phase); c.x_phase ^= 1u; }
   }
-  if (!a_staged) stage_x_rows(c.sm, x, p.D, p.M, c0, nch);
+  if (a_mode == A_SOFTWARE) stage_x_rows(c.sm, x, p.D, p.M, c0, nch);
   const int row = threadIdx.x >> 4, col = threadIdx.x & 15;
   const int gr = c.rank * 32 + row, j = t * 16 + col;
   const float bias = j < p.H ? __ldcg(p.P + p.ob3 + j) : 0.f;
@@ -475,7 +486,7 @@ __device__ __forceinline__ void item_heads(Ctx& c, const Params& p, uint32_t ste
 
 // P3: h_d = tanh(z.W1 + b1) recomputed into the A tile, a = h_d.W2 + b2, x a - softplus(a), da2 = w (x - sigmoid a)
 //                                                                                           VAEB.py:254,263,311
-__device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* x, int t, bool more) {
+__device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* x, int t, bool more, bool publish) {
   ST2_TRACE(c, 30);
   const int c0 = c.rank * p.KH / CL, c1 = (c.rank + 1) * p.KH / CL, nch = c1 - c0;
   constexpr int TB = TR_DEC2 * 128;
@@ -547,7 +558,7 @@ __device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* 
         const int k0 = c0 * 64 + kl;
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = (r < M && k0 + e < H) ? tanh_fast(v[e] * WUNSCALE) : 0.f;
-        if (r < M && r % p.n_tiles3 == t) {                      // every cluster publishes a few rows of h_d for P4 / P5
+        if (publish && r < M && r % p.n_tiles3 == t) {           // no spare cluster: every cluster publishes a few rows of h_d
           float* o = p.hd + (size_t)r * p.HP + k0;
           *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -608,6 +619,62 @@ __device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* 
   if (more) cluster_sync();          // the receive buffer is reused by this cluster's next item of the phase
   else __syncthreads();
   ST2_TRACE(c, 35);
+}
+
+// P3, spare clusters: h_d = tanh([z|1].[W1^T|b1]^T) for 16 hidden units per CTA, published for P4 (fp32, the tanh'
+// factor) and P5 (transposed operand of the W2 gradient).  The dec2 items recompute h_d for themselves.
+__device__ __forceinline__ void item_hd(Ctx& c, const Params& p, int g) {
+  constexpr int T1 = 64 * 128;
+  uint8_t* z_sm = c.sm + SM_A;
+  uint8_t* w_sm = c.sm + SM_B;                                  // [hi 16 rows x 128 B][lo]
+  const uint8_t* src = p.m_dec1 + (size_t)(g >> 2) * 2 * T1 + (size_t)(g & 3) * 2048;
+  if (threadIdx.x == 0) {
+    ops_begin(c, (uint32_t)(2 * TBA + 4096));
+    bulk_g2s(z_sm, p.z_km, (uint32_t)(2 * TBA), c.op_bar);
+    bulk_g2s(w_sm, src, 2048u, c.op_bar);
+    bulk_g2s(w_sm + 2048, src + T1, 2048u, c.op_bar);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  if (threadIdx.x == 0) {
+    tc::mbar_wait(c.op_bar, c.op_phase);
+    c.op_phase ^= 1u;
+    tc::tc_fence_after();
+    const uint32_t idesc = tc::make_idesc_f16(MP, 16, 0, 0);
+    const uint64_t d0 = tc::make_smem_desc(0u, 16u, 1024u);
+    const uint64_t a = d0 | (uint64_t)(tc::smem_u32(z_sm) >> 4), b = d0 | (uint64_t)(tc::smem_u32(w_sm) >> 4);
+    const uint32_t a_lo = TBA >> 4, b_lo = 2048u >> 4;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      tc::umma_bf16(c.tmem, a + 2 * k, b + 2 * k, idesc, k ? 1u : 0u);
+      tc::umma_bf16(c.tmem, a + 2 * k, b + b_lo + 2 * k, idesc, 1u);
+      tc::umma_bf16(c.tmem, a + a_lo + 2 * k, b + 2 * k, idesc, 1u);
+    }
+    tc::umma_commit(c.mma_bar);
+  }
+  tc::mbar_wait(c.mma_bar, c.mma_phase);
+  c.mma_phase ^= 1u;
+  tc::tc_fence_after();
+  const int q = c.warp & 3, u = c.warp >> 2;
+  if (u < 2) {
+    float v[8];
+    tmem_ld8(c.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * 8), v);
+    tc::tmem_ld_wait();
+    const int r = q * 32 + c.lane, k0 = g * 16 + u * 8;
+    if (r < p.M) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = k0 + e < p.H ? tanh_fast(v[e] * WUNSCALE) : 0.f;
+      float* o = p.hd + (size_t)r * p.HP + k0;
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)                               // lanes = consecutive batch rows: 64 contiguous bytes per store
+        if (k0 + e < p.H) put_hl(t_addr(p.hd_t, (k0 + e) >> 7, TBA, (k0 + e) & 127, r), TBA, v[e]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
 }
 
 // P4: da1[:, 16t..] = (da2.W2^T) * (1 - h_d^2)                                              T.grad, VAEB.py:397
@@ -685,8 +752,8 @@ __device__ __forceinline__ void item_dz(Ctx& c, const Params& p, bool more) {
         a -= zm_[i];
         b += 0.5f * (1.0f - expf(ls_[i]));
       }
-      p.ddT[(size_t)j * MP + gr] = a;
-      p.ddT[(size_t)(Z + j) * MP + gr] = b;
+      put_hl(km_addr(p.dd_km, gr, j), TBA, a);                                   // A operand of the dh_e GEMMs (P6)
+      put_hl(km_addr(p.dd_km, gr, Z + j), TBA, b);
       put_hl(t_addr(p.dd_t, j >> 4, 2048, j & 15, gr), 2048, a);                 // [dmu|dls]^T in tiles of 16 columns
       put_hl(t_addr(p.dd_t, (Z + j) >> 4, 2048, (Z + j) & 15, gr), 2048, b);
     }
@@ -814,60 +881,29 @@ __device__ __forceinline__ void item_wg2(Ctx& c, const Params& p, const Hyper& h
   ST2_TRACE(c, 62);
 }
 
-// W3, b3 <- Adagrad([x | 1]^T . da3), da3 = ([dmu|dls].[W4|W5]^T) * (1 - h_e^2) recomputed into the B tile;
-// tile = 128 pixels x 32 hidden units
-__device__ __forceinline__ void item_wg3(Ctx& c, const Params& p, const Hyper& hy, const float* x, const float* he, int mt, int nt,
-                                      bool a_staged) {
+// W3, b3 <- Adagrad([x | 1]^T . da3), da3 = ([dmu|dls].[W4|W5]^T) * (1 - h_e^2) recomputed on the tensor cores (K = one
+// chunk) and written, transposed, into the B tile; tile = 128 pixels x 32 hidden units
+__device__ __forceinline__ void item_wg3(Ctx& c, const Params& p, const Hyper& hy, const float* he, int mt, int nt, int par) {
   ST2_TRACE(c, 70);
-  const int Z = p.Z, Z2 = 2 * p.Z, H = p.H, M = p.M, D = p.D;
-  float* ddsT = reinterpret_cast<float*>(c.sm + SM_SCR);        // [2Z][128]  (scratch region + receive buffer: 48 KB)
-  float* w45 = ddsT + Z2 * MP;                                  // [2Z][32]
-  const int jj = threadIdx.x & 31, bo = threadIdx.x >> 5;        // 32 hidden units x 16 batch octets
-  const int j = nt * 32 + jj;
+  const int H = p.H, M = p.M, D = p.D;
+  constexpr int TB = 32 * 128;                                  // one half (hi or lo) of a 32-row tile
+  uint8_t* dd_sm = c.sm + SM_A + 2 * 2 * TBA;                   // [dmu|dls]: the chunk slot behind the two chunks of x^T
+  uint8_t* w45_sm = c.sm + SM_B + 16384;                        // this tile's rows of [W4|W5] behind the B tile
+  if (threadIdx.x == 0) {
+    ops_begin(c, (uint32_t)(4 * TBA + 2 * TBA + 2 * TB));
+    bulk_g2s(dd_sm, p.dd_km, (uint32_t)(2 * TBA), c.op_bar);
+    bulk_g2s(w45_sm, p.m_w45k + (size_t)par * p.w45k_bytes + (size_t)nt * 2 * TB, (uint32_t)(2 * TB), c.op_bar);
+    bulk_g2s(c.sm + SM_A, p.x_t + (size_t)mt * 4 * TBA, (uint32_t)(4 * TBA), c.op_bar);
+  }
+  // this thread's share of the tanh' factors: batch row = TMEM lane, eight hidden units
+  const int q = c.warp & 3, cg = c.warp >> 2;
+  const int b = q * 32 + c.lane, j0 = nt * 32 + cg * 8;
   float hv[8];
   {
-    // [dmu|dls]^T and the 32 columns of the [W4|W5]^T snapshot this tile needs: loads first, stores second
-    float dr[12], wr[3];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      const int e = threadIdx.x + i * NT;
-      dr[i] = e < Z2 * MP ? __ldcg(p.ddT + e) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int e = threadIdx.x + i * NT;                        // (q, jj): 2Z x 32
-      wr[i] = e < Z2 * 32 ? __ldcg(p.w45s + (size_t)(e >> 5) * p.HP + nt * 32 + (e & 31)) : 0.f;
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int b = bo * 8 + e;
-      hv[e] = (b < M && j < H) ? __ldcg(he + (size_t)b * p.HP + j) : 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 12; ++i)
-      if ((int)threadIdx.x + i * NT < Z2 * MP) ddsT[threadIdx.x + i * NT] = dr[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-      if ((int)threadIdx.x + i * NT < Z2 * 32) w45[threadIdx.x + i * NT] = wr[i];
-  }
-  if (!a_staged) stage_x_T(c.sm, x, D, M, mt * MP);
-  __syncthreads();
-  {
-    constexpr int TB = 32 * 128;
-    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (bo * 8 < M) {
-#pragma unroll 4
-      for (int q = 0; q < Z2; ++q) {
-        const float wv = w45[q * 32 + jj];
-        const float4 d0 = *reinterpret_cast<const float4*>(ddsT + q * MP + bo * 8);
-        const float4 d1 = *reinterpret_cast<const float4*>(ddsT + q * MP + bo * 8 + 4);
-        v[0] = fmaf(d0.x, wv, v[0]); v[1] = fmaf(d0.y, wv, v[1]); v[2] = fmaf(d0.z, wv, v[2]); v[3] = fmaf(d0.w, wv, v[3]);
-        v[4] = fmaf(d1.x, wv, v[4]); v[5] = fmaf(d1.y, wv, v[5]); v[6] = fmaf(d1.z, wv, v[6]); v[7] = fmaf(d1.w, wv, v[7]);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = (bo * 8 + e < M && j < H) ? v[e] * (1.0f - hv[e] * hv[e]) : 0.f;
-    put_unit(c.sm + SM_B + (size_t)(bo >> 3) * 2 * TB + unit_off(jj, bo & 7), TB, v);
+    const bool ok = b < M;
+    const float4 h0 = ok ? __ldcg(reinterpret_cast<const float4*>(he + (size_t)b * p.HP + j0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 h1 = ok ? __ldcg(reinterpret_cast<const float4*>(he + (size_t)b * p.HP + j0 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    hv[0] = h0.x; hv[1] = h0.y; hv[2] = h0.z; hv[3] = h0.w; hv[4] = h1.x; hv[5] = h1.y; hv[6] = h1.z; hv[7] = h1.w;
   }
   WgPre<32> pre;
   wgrad_prefetch<32>(c, p, [&](int row, int col) -> long long {
@@ -875,22 +911,59 @@ __device__ __forceinline__ void item_wg3(Ctx& c, const Params& p, const Hyper& h
     if (i > D || jc >= H) return -1;
     return i < D ? p.oW3 + (long long)i * H + jc : p.ob3 + jc;
   }, pre);
+  // ---- dh_e pre-activation on the tensor cores: D1[128 x 32] = [dmu|dls] . [W4|W5]^T (tile rows) -----------------
+  tc::tc_fence_before();
+  __syncthreads();                                              // the previous item's TMEM reads are complete
+  tc::tc_fence_after();
+  if (threadIdx.x == 0) {
+    tc::mbar_wait(c.op_bar, c.op_phase);
+    c.op_phase ^= 1u;
+    tc::tc_fence_after();
+    const uint32_t idesc = tc::make_idesc_f16(MP, 32, 0, 0);
+    const uint64_t d0 = tc::make_smem_desc(0u, 16u, 1024u);
+    const uint64_t a = d0 | (uint64_t)(tc::smem_u32(dd_sm) >> 4), bdesc = d0 | (uint64_t)(tc::smem_u32(w45_sm) >> 4);
+    const uint32_t a_lo = TBA >> 4, b_lo = TB >> 4;
+    const int ks = (2 * p.Z + 15) / 16;
+    for (int k = 0; k < ks; ++k) {
+      tc::umma_bf16(c.tmem + 64u, a + 2 * k, bdesc + 2 * k, idesc, k ? 1u : 0u);
+      tc::umma_bf16(c.tmem + 64u, a + 2 * k, bdesc + b_lo + 2 * k, idesc, 1u);
+      tc::umma_bf16(c.tmem + 64u, a + a_lo + 2 * k, bdesc + 2 * k, idesc, 1u);
+    }
+    tc::umma_commit(c.mma_bar);
+  }
+  tc::mbar_wait(c.mma_bar, c.mma_phase);
+  c.mma_phase ^= 1u;
+  tc::tc_fence_after();
+  ST2_TRACE(c, 74);
+  {
+    float v[8];
+    tmem_ld8(c.tmem + ((uint32_t)(q * 32) << 16) + 64u + (uint32_t)(cg * 8), v);
+    tc::tmem_ld_wait();
+    // B tile of the weight gradient: row = hidden unit, k = batch row -> 2-byte stores, a warp writes 64 contiguous bytes
+    uint8_t* bt = c.sm + SM_B + (size_t)(b >> 6) * 2 * TB;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float d = (b < M && j0 + e < H) ? v[e] * WUNSCALE * (1.0f - hv[e] * hv[e]) : 0.f;
+      put_hl(bt + tc::sw128_offset(cg * 8 + e, b & 63), TB, d);
+    }
+  }
   ST2_TRACE(c, 71);
-  mma_run(c, 2, (M + 15) / 16, 32 * 128, 32, false);
+  mma_run(c, 2, (M + 15) / 16, TB, 32, false);
   ST2_TRACE(c, 72);
   wgrad_epilogue_coalesced<32>(
       c, p, hy, pre,
       [&](int row, int col0, float* nv) {
-        const int i = mt * MP + row, j0 = nt * 32 + col0;
+        const int i = mt * MP + row, j0_ = nt * 32 + col0;
         if (i >= D) return;
 #pragma unroll
         for (int e = 0; e < 8; ++e)
-          if (j0 + e < H) mirror_put(p.m_enc1, TR_ENC1, p.KD, (j0 + e) >> 4, (j0 + e) & 15, i, nv[e]);
+          if (j0_ + e < H) mirror_put(p.m_enc1, TR_ENC1, p.KD, (j0_ + e) >> 4, (j0_ + e) & 15, i, nv[e]);
       });
   ST2_TRACE(c, 73);
 }
 
-// W1, b1 <- Adagrad([z | 1]^T . da1), computed transposed: tile = 128 hidden units x (Z + 1) latent columns
+// W1, b1 <- Adagrad([z | 1]^T . da1), computed transposed: tile = 128 hidden units x (Z + 1) latent columns.  W1 is
+// [Z][H]: with the thread = hidden unit mapping of the accumulator every access below is coalesced along the lanes.
 __device__ __forceinline__ void item_wg1(Ctx& c, const Params& p, const Hyper& hy, int mt) {
   const int Z = p.Z, H = p.H, N = p.NZ;
   const int TB = N * 128;
@@ -899,28 +972,52 @@ __device__ __forceinline__ void item_wg1(Ctx& c, const Params& p, const Hyper& h
     bulk_g2s(c.sm + SM_A, p.da1_t + (size_t)mt * 4 * TBA, (uint32_t)(4 * TBA), c.op_bar);
     bulk_g2s(c.sm + SM_B, p.z_t, (uint32_t)(4 * TB), c.op_bar);
   }
+  // this thread's unit: hidden unit i, latent columns col0 .. col0 + 7 (column Z = the bias); loads before the GEMM
+  const int qq = c.warp & 3, u = c.warp >> 2;
+  const int i = mt * MP + qq * 32 + c.lane, col0 = u * 8;
+  const bool mine = u < N / 8 && i < H && col0 <= Z;
+  size_t off[8]; bool ok[8]; float pv[8], av[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int q = col0 + e;
+    ok[e] = mine && q <= Z;
+    off[e] = q < Z ? (size_t)p.oW1 + (size_t)q * H + i : (size_t)p.ob1 + i;
+    pv[e] = ok[e] ? __ldcg(p.P + off[e]) : 0.f;
+    av[e] = ok[e] ? __ldcg(p.ada + off[e]) : 0.f;
+  }
   mma_run(c, 2, (p.M + 15) / 16, TB, N, true);
-  wgrad_epilogue(c, N, [&](int row, int col0, const float* v) {
-    const int i = mt * MP + row;
-    if (i >= H || col0 > Z) return;
-    size_t off[8]; bool ok[8]; float nv[8];
+  if (u < N / 8) {
+    float v[8], nv[8];
+    tmem_ld8(c.tmem + ((uint32_t)(qq * 32) << 16) + (uint32_t)col0, v);
+    tc::tmem_ld_wait();
+    if (mine) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int q = col0 + e;
-      ok[e] = q <= Z;
-      off[e] = q < Z ? (size_t)p.oW1 + (size_t)q * H + i : (size_t)p.ob1 + i;
-    }
-    adagrad8(p.P, p.ada, off, ok, v, hy, nv);
+      for (int e = 0; e < 8; ++e) {
+        nv[e] = 0.f;
+        if (ok[e]) {
+          const float gg = fmaf(v[e], hy.w, -hy.prior * pv[e]);   // VAEB.py:389-390
+          const float a = av[e] + gg * gg;                        // VAEB.py:439
+          float n_ = pv[e] + hy.lr * gg / (sqrtf(a) + hy.eps);    // VAEB.py:441
+          if (hy.p2 != 0.f) n_ -= hy.p2 * pv[e] * pv[e];          // VAEBfullbayes.py:183-184
+          p.P[off[e]] = n_;
+          p.ada[off[e]] = a;
+          nv[e] = n_;
+          if (col0 + e < Z) mirror_put(p.m_dz, N, p.KH, 0, col0 + e, i, n_);
+        }
+      }
+      // [W1^T | b1] of the decoder hidden layer: row = hidden unit, the eight latent columns are one 16-byte unit
+      constexpr int T1 = 64 * 128;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      if (col0 + e < Z) mirror_put(p.m_dz, N, p.KH, 0, col0 + e, i, nv[e]);
-      if (col0 + e <= Z) mirror_put(p.m_dec1, 64, 1, i >> 6, i & 63, col0 + e, nv[e]);      // [W1^T | b1] of the hidden layer
+      for (int e = 0; e < 8; ++e) nv[e] *= WSCALE;
+      put_unit<true>(p.m_dec1 + (size_t)(i >> 6) * 2 * T1 + unit_off(i & 63, col0 >> 3), T1, nv);
     }
-  });
+  }
+  tc::tc_fence_before();
+  __syncthreads();
 }
 
 // W4, b4, W5, b5 <- Adagrad([h_e | 1]^T . [dmu | dls]); tile = 128 hidden units x 16 columns of [dmu | dls]
-__device__ __forceinline__ void item_wg45(Ctx& c, const Params& p, const Hyper& hy, int mt, int nt) {
+__device__ __forceinline__ void item_wg45(Ctx& c, const Params& p, const Hyper& hy, int mt, int nt, int par) {
   const int Z = p.Z, H = p.H;
   constexpr int N = 16, TB = N * 128;
   if (threadIdx.x == 0) {
@@ -943,8 +1040,13 @@ __device__ __forceinline__ void item_wg45(Ctx& c, const Params& p, const Hyper& 
         const int i = mt * MP + row, cc0 = nt * N + col0;
         if (i >= H) return;
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
+        for (int e = 0; e < 8; ++e) {
           if (cc0 + e < 2 * Z) mirror_put(p.m_heads, p.NH, p.KH, 0, cc0 + e, i, nv[e]);
+          nv[e] = cc0 + e < 2 * Z ? nv[e] * WSCALE : 0.f;
+        }
+        // the copy the NEXT step's dh_e GEMMs read (row = hidden unit, k = column of [dmu|dls]: one 16-byte unit)
+        constexpr int T32 = 32 * 128;
+        put_unit<true>(p.m_w45k + (size_t)(par ^ 1) * p.w45k_bytes + (size_t)(i >> 5) * 2 * T32 + unit_off(i & 31, cc0 >> 3), T32, nv);
       });
 }
 
@@ -956,21 +1058,6 @@ __device__ __forceinline__ void item_eps(const Params& p, uint32_t step, int par
   if (part == 0)
     for (int e2 = CL * NT + threadIdx.x; e2 < p.M * p.Z; e2 += NT)
       p.eps[e2] = philox_normal1(p.seed, VAEB_STREAM_TRAIN, step, 0u, (uint64_t)(p.row_offset * p.Z + e2));
-}
-
-// snapshot of [W4|W5]^T for the W3-gradient producers of P6: w45s[q][j], one CTA per quarter of the hidden units
-__device__ __forceinline__ void item_snap45(const Params& p, int part) {
-  const int Z = p.Z, Z2 = 2 * p.Z, H = p.H;
-  const int per = (p.HP + CL - 1) / CL;
-  for (int e = threadIdx.x; e < per * Z2; e += NT) {
-    const int jl = e / Z2, q = e - jl * Z2;
-    const int j = part * per + jl;
-    if (j < p.HP) {
-      float v = 0.f;
-      if (j < H) v = q < Z ? __ldcg(p.P + p.oW4 + (size_t)j * Z + q) : __ldcg(p.P + p.oW5 + (size_t)j * Z + q - Z);
-      p.w45s[(size_t)q * p.HP + j] = v;
-    }
-  }
 }
 
 // the bound of step s: fixed-order sum of the row partials (VAEB.py:340-344) / Mg
@@ -1001,14 +1088,16 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
   c.sm = smem_base();
   c.mma_bar = reinterpret_cast<uint64_t*>(c.sm + SM_MISC);
   c.op_bar = c.mma_bar + 1;
+  c.x_bar = c.mma_bar + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.sm + SM_MISC + 16);
-  c.mma_phase = 0; c.op_phase = 0;
+  c.mma_phase = 0; c.op_phase = 0; c.x_phase = 0;
   c.rank = (int)cluster_ctarank(); c.cid = (int)cluster_idx(); c.ncl = (int)cluster_count();
   c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
   c.trace = nullptr; c.tn = 0;
   if (threadIdx.x == 0) {
     tc::mbar_init(c.mma_bar, 1);
     tc::mbar_init(c.op_bar, 1);
+    tc::mbar_init(c.x_bar, 1);
     tc::fence_barrier_init();
   }
   if (c.warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -1035,12 +1124,20 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
   auto x_of = [&](int s) { return p.batch_order ? p.x_base + (size_t)__ldg(p.batch_order + s) * p.M * p.D : p.x_direct; };
   const int kd0 = c.rank * p.KD / CL, kdn = (c.rank + 1) * p.KD / CL - kd0;
 
-  // the A tile of this CTA's first enc1 item is staged ahead of the barrier that opens P1 (x depends on nothing)
-  bool p1_staged = false;
-  if (c.cid < n1) { stage_x_rows(c.sm, x_of(0), p.D, p.M, kd0, kdn); p1_staged = true; }
+  // the A tile of this CTA's first enc1 item: converted from the fp32 rows for the first step of a launch (x depends
+  // on nothing), one bulk copy of x_km -- issued before the barrier that closes the previous step -- afterwards
+  const bool has_p1 = c.cid < n1;
+  if (has_p1) stage_x_rows(c.sm, x_of(0), p.D, p.M, kd0, kdn);
+  const int n_spare = c.ncl - n3;                   // clusters without a dec2 item: they publish h_d in P3
 
+#define ARRIVE(ph)                                                                                           \
+  do {                                                                                                       \
+    if (p.timing && threadIdx.x == 0 && s == p.n_steps - 1 && blockIdx.x < 256)                              \
+      p.timing[(size_t)p.n_steps * (N_PHASES + 1) + 128 + (size_t)blockIdx.x * N_PHASES + (ph)] = gtime();   \
+  } while (0)
   for (int s = 0; s < p.n_steps; ++s) {
     const float* x = x_of(s);
+    const int par = (int)((p.step0 + (uint32_t)s) & 1u);        // which copy of the k-major [W4|W5] mirror this step reads
     long long* tm = rec ? p.timing + (size_t)s * (N_PHASES + 1) : nullptr;
     if (tm) tm[0] = gtime();
     if (p.timing && blockIdx.x == 0 && s == p.n_steps - 1) c.trace = p.timing + (size_t)p.n_steps * (N_PHASES + 1);
@@ -1049,50 +1146,56 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     {
       const int n_e = p.eps_inj ? 0 : CL;
       for (int it = c.cid; it < n1 + n_groups(n_e); it += c.ncl) {
-        if (it < n1) { item_enc1(c, p, x, p.he, p.he_t, it, p1_staged && it == c.cid, it + c.ncl < n1); continue; }
+        if (it < n1) {
+          const int mode = it == c.cid ? (s == 0 ? A_STAGED : A_PREFETCHED) : (s == 0 ? A_SOFTWARE : A_BULK);
+          item_enc1(c, p, x, p.he, p.he_t, it, mode, it + c.ncl < n1);
+          continue;
+        }
         item_eps(p, p.step0 + (uint32_t)s, c.rank);
       }
-      p1_staged = false;
     }
     ST2_TRACE(c, 81);
+    ARRIVE(0);
     grid_barrier(p.bar, target += G);
     if (tm) tm[1] = gtime();
     ST2_TRACE(c, 91);
-    // ---- P2: latent heads ------------------------------------------------------------------------------------
+    // ---- P2: latent heads | the minibatch operands of P6 and of the next step's P1 ---------------------------------
     if (c.cid == 0) item_heads(c, p, p.step0 + (uint32_t)s, false);
+    else item_xmirrors(p, s + 1 < p.n_steps ? x_of(s + 1) : nullptr, x, (c.cid - 1) * CL + c.rank, (c.ncl - 1) * CL);
     ST2_TRACE(c, 82);
+    ARRIVE(1);
     grid_barrier(p.bar, target += G);
     if (tm) tm[2] = gtime();
     ST2_TRACE(c, 92);
-    // ---- P3: decoder + log-likelihood ------------------------------------------------------------------------
-    for (int it = c.cid; it < n3; it += c.ncl) item_dec2(c, p, x, it, it + c.ncl < n3);
+    // ---- P3: decoder + log-likelihood | h_d published by the spare clusters ------------------------------------------
+    for (int it = c.cid; it < n3; it += c.ncl) item_dec2(c, p, x, it, it + c.ncl < n3, n_spare <= 0);
+    if (c.cid >= n3)
+      for (int g = (c.cid - n3) * CL + c.rank; g < p.HP / 16; g += n_spare * CL) item_hd(c, p, g);
     ST2_TRACE(c, 83);
+    ARRIVE(2);
     grid_barrier(p.bar, target += G);
     if (tm) tm[3] = gtime();
     ST2_TRACE(c, 93);
     // ---- P4: back through the decoder output layer ---------------------------------------------------------------
     for (int it = c.cid; it < n1; it += c.ncl) item_dgrad(c, p, it, it + c.ncl < n1);
     ST2_TRACE(c, 84);
+    ARRIVE(3);
     grid_barrier(p.bar, target += G);
     if (tm) tm[4] = gtime();
     ST2_TRACE(c, 94);
-    // ---- P5: dz | W2 update | the bound | snapshot of [W4|W5]^T --------------------------------------------------
+    // ---- P5: dz | W2 update | the bound ---------------------------------------------------------------------------
     {
       const int n2 = m_h1 * n3;
       const int g2 = n_groups(n2 + 1);
-      for (int it = c.cid; it < 1 + g2 + 1; it += c.ncl) {
+      for (int it = c.cid; it < 1 + g2; it += c.ncl) {
         if (it == 0) { item_dz(c, p, false); continue; }
-        if (it == 1 + g2) { item_snap45(p, c.rank); continue; }
         const int i = (it - 1) * CL + c.rank;
         if (i < n2) item_wg2(c, p, hy, i / n3, i % n3);
         else if (i == n2) item_bound(c, p, s);
       }
     }
-    // the A tile (x^T) of this CTA's first W3-gradient item, staged ahead of the barrier that opens P6
-    const int i6 = c.cid * CL + c.rank;
-    const bool p6_staged = i6 < n3w;
-    if (p6_staged) stage_x_T(c.sm, x, p.D, p.M, (i6 / n_h32) * MP);
     ST2_TRACE(c, 85);
+    ARRIVE(4);
     grid_barrier(p.bar, target += G);
     if (tm) tm[5] = gtime();
     ST2_TRACE(c, 95);
@@ -1101,13 +1204,18 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
       const int n45 = m_h1 * n45t;
       for (int it = c.cid; it < n_groups(n3w + m_h + n45); it += c.ncl) {
         const int i = it * CL + c.rank;
-        if (i < n3w) item_wg3(c, p, hy, x, p.he, i / n_h32, i % n_h32, p6_staged && it == c.cid);
+        if (i < n3w) item_wg3(c, p, hy, p.he, i / n_h32, i % n_h32, par);
         else if (i < n3w + m_h) item_wg1(c, p, hy, i - n3w);
-        else if (i < n3w + m_h + n45) item_wg45(c, p, hy, (i - n3w - m_h) / n45t, (i - n3w - m_h) % n45t);
+        else if (i < n3w + m_h + n45) item_wg45(c, p, hy, (i - n3w - m_h) / n45t, (i - n3w - m_h) % n45t, par);
       }
     }
-    if (s + 1 < p.n_steps && c.cid < n1) { stage_x_rows(c.sm, x_of(s + 1), p.D, p.M, kd0, kdn); p1_staged = true; }
+    // the A tile of this CTA's first enc1 item of the next step (x_km was written in P2): in flight across the barrier
+    if (s + 1 < p.n_steps && has_p1 && threadIdx.x == 0 && kdn > 0) {
+      tc::mbar_expect_tx(c.x_bar, (uint32_t)(kdn * 2 * TBA));
+      bulk_g2s(c.sm + SM_A, p.x_km + (size_t)kd0 * 2 * TBA, (uint32_t)(kdn * 2 * TBA), c.x_bar);
+    }
     ST2_TRACE(c, 86);
+    ARRIVE(5);
     grid_barrier(p.bar, target += G);
     if (tm) tm[6] = gtime();
     ST2_TRACE(c, 96);
@@ -1121,7 +1229,7 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
 // ---- mirrors from the fp32 master parameters (after set_tensors / load / an update by another path) ----------------
 struct MirrorArgs {
   const float* P; int64_t oW3, oW4, oW5, oW1, oW2, ob1;
-  uint8_t *m_enc1, *m_heads, *m_dec2, *m_dgrad, *m_dz, *m_dec1;
+  uint8_t *m_enc1, *m_heads, *m_dec2, *m_dgrad, *m_dz, *m_dec1, *m_w45k;
   int D, H, Z, HP, KD, KH, NH, NZ;
 };
 __global__ void __launch_bounds__(256) build_mirrors_kernel(MirrorArgs a) {
@@ -1158,6 +1266,15 @@ __global__ void __launch_bounds__(256) build_mirrors_kernel(MirrorArgs a) {
       mirror_put(a.m_dgrad, TR_DGRAD, a.KD, n / TR_DGRAD, n % TR_DGRAD, k, (n < H && k < D) ? a.P[a.oW2 + (size_t)n * D + k] : 0.f);
       break;
     }
+    case 6: {   // [W4|W5] with the hidden unit as the row (tiles of 32), k = column of [dmu|dls]; both parity copies
+      if (i >= (int64_t)a.HP * 64) return;
+      const int n = (int)(i / 64), k = (int)(i % 64);
+      float v = 0.f;
+      if (n < H && k < 2 * Z) v = k < Z ? a.P[a.oW4 + (size_t)n * Z + k] : a.P[a.oW5 + (size_t)n * Z + k - Z];
+      mirror_put(a.m_w45k, 32, 1, n >> 5, n & 31, k, v);
+      mirror_put(a.m_w45k + (size_t)a.HP * 64 * 4, 32, 1, n >> 5, n & 31, k, v);
+      break;
+    }
     case 5: {   // dec1: n = hidden (tiles of 64), k = latent index, k = Z: the bias
       if (i >= (int64_t)a.HP * 64) return;
       const int n = (int)(i / 64), k = (int)(i % 64);
@@ -1178,7 +1295,7 @@ __global__ void __launch_bounds__(256) build_mirrors_kernel(MirrorArgs a) {
 
 // constant rows of the transposed activation mirrors: the "ones" feature that turns a weight-gradient GEMM's extra row /
 // column into the bias gradient (h_e and h_d: feature H; z: feature Z).  Everything else starts as zero.
-struct OnesArgs { uint8_t *he_t, *hd_t, *z_t, *z_km; int H, Z, NZ; };
+struct OnesArgs { uint8_t *he_t, *hd_t, *z_t, *z_km, *x_t; int H, Z, NZ, D; };
 __global__ void __launch_bounds__(128) init_ones_kernel(OnesArgs a) {
   const int b = threadIdx.x;                       // batch column 0..127
   const __half one = __float2half_rn(1.0f);
@@ -1187,6 +1304,7 @@ __global__ void __launch_bounds__(128) init_ones_kernel(OnesArgs a) {
     *reinterpret_cast<__half*>(t_addr(m[q], a.H >> 7, TBA, a.H & 127, b)) = one;
   *reinterpret_cast<__half*>(t_addr(a.z_t, 0, a.NZ * 128, a.Z, b)) = one;
   *reinterpret_cast<__half*>(km_addr(a.z_km, b, a.Z)) = one;      // [z | 1]: batch row b, column Z
+  *reinterpret_cast<__half*>(t_addr(a.x_t, a.D >> 7, TBA, a.D & 127, b)) = one;   // [x | 1]^T: the row of pixel D
 }
 
 }  // namespace st2
@@ -1205,7 +1323,7 @@ bool step_tc_supported(const vaeb_handle* h, int rows) {
 
 void step_tc_free(StepTcState& s) {
   void* ptrs[] = {s.bar, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz, s.m_dec1, s.act, s.he, s.hd, s.mu, s.ls,
-                  s.eps, s.z, s.ddT, s.w45s, s.partial, s.aux, s.d_order, s.d_timing};
+                  s.eps, s.z, s.m_w45k, s.partial, s.aux, s.d_order, s.d_timing};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   s = StepTcState();
@@ -1242,6 +1360,7 @@ static int step_tc_init(vaeb_handle* h) {
   VAEB_CUDA(alloc((void**)&s.m_dec2, (size_t)n3 * TR_DEC2 * KH * 64 * 4));
   VAEB_CUDA(alloc((void**)&s.m_dz, (size_t)NZ * KH * 64 * 4));
   VAEB_CUDA(alloc((void**)&s.m_dec1, (size_t)HP * 64 * 4));
+  VAEB_CUDA(alloc((void**)&s.m_w45k, (size_t)2 * HP * 64 * 4));       // two copies (step parity)
   // activation mirrors in one allocation (cleared together when the minibatch size changes)
   size_t o = 0;
   auto take = [&](size_t bytes) { const size_t at_ = o; o += (bytes + 1023) / 1024 * 1024; return at_; };
@@ -1255,12 +1374,13 @@ static int step_tc_init(vaeb_handle* h) {
   s.o_dd_t = take((size_t)4 * NH * 128);
   s.o_z_t = take((size_t)4 * NZ * 128);
   s.o_z_km = take((size_t)2 * TBA);
+  s.o_dd_km = take((size_t)2 * TBA);
+  s.o_x_km = take((size_t)KD * 2 * TBA);
+  s.o_x_t = take((size_t)((D + 1 + MP - 1) / MP) * 4 * TBA);
   s.act_bytes = o;
   VAEB_CUDA(alloc((void**)&s.act, s.act_bytes));
   VAEB_CUDA(alloc((void**)&s.he, (size_t)MP * HP * 4));
   VAEB_CUDA(alloc((void**)&s.hd, (size_t)MP * HP * 4));
-  VAEB_CUDA(alloc((void**)&s.ddT, (size_t)2 * Z * MP * 4));
-  VAEB_CUDA(alloc((void**)&s.w45s, (size_t)2 * Z * HP * 4));
   VAEB_CUDA(alloc((void**)&s.mu, (size_t)MP * Z * 4));
   VAEB_CUDA(alloc((void**)&s.ls, (size_t)MP * Z * 4));
   VAEB_CUDA(alloc((void**)&s.eps, (size_t)MP * Z * 4));
@@ -1304,18 +1424,19 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
   p.eps_inj = d_eps;
   p.seed = h->cfg.seed; p.step0 = h->step; p.row_offset = 0;
   p.he = s.he; p.hd = s.hd; p.mu = s.mu; p.ls = s.ls; p.eps = s.eps; p.z = s.z;
-  p.ddT = s.ddT; p.w45s = s.w45s;
+  p.dd_km = s.act + s.o_dd_km; p.x_km = s.act + s.o_x_km; p.x_t = s.act + s.o_x_t;
+  p.m_w45k = s.m_w45k; p.w45k_bytes = p.HP * 64 * 4;
   p.partial = s.partial; p.aux = s.aux;
   p.scalars = h->d_scalars + slot0; p.Mg = (float)rows; p.bmult = 1.0f;
   p.n_steps = n_steps;
+  { const char* e = getenv("VAEB_ST2_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.bar = s.bar; p.bar_base = s.bar_count;
   p.timing = d_timing;
   if (rows != s.rows_init) {
     // batch columns >= rows of every activation mirror must read as zero (they are contraction rows of the weight
     // gradients): clear everything when the minibatch size changes, then restore the constant "ones" features
     VAEB_CUDA(cudaMemsetAsync(s.act, 0, s.act_bytes, h->stream));
-    OnesArgs oa{p.he_t, p.hd_t, p.z_t, p.z_km, H, Z, p.NZ};
-    VAEB_CUDA(cudaMemsetAsync(s.ddT, 0, (size_t)2 * Z * MP * 4, h->stream));
+    OnesArgs oa{p.he_t, p.hd_t, p.z_t, p.z_km, p.x_t, H, Z, p.NZ, D};
     init_ones_kernel<<<1, 128, 0, h->stream>>>(oa);
     VAEB_CUDA(cudaGetLastError());
     ++h->launches;
@@ -1323,11 +1444,11 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
   }
   if (!s.mirrors_valid) {
     MirrorArgs a{h->d_params, p.oW3, p.oW4, p.oW5, p.oW1, p.oW2, p.ob1, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz,
-                 s.m_dec1, D, H, Z, p.HP, p.KD, p.KH, p.NH, p.NZ};
+                 s.m_dec1, s.m_w45k, D, H, Z, p.HP, p.KD, p.KH, p.NH, p.NZ};
     int64_t most = (int64_t)p.HP * p.KD * 64;
     most = std::max<int64_t>(most, (int64_t)p.n_tiles3 * TR_DEC2 * p.KH * 64);
     most = std::max<int64_t>(most, (int64_t)p.NH * p.KH * 64);
-    build_mirrors_kernel<<<dim3((unsigned)((most + 255) / 256), 6), 256, 0, h->stream>>>(a);
+    build_mirrors_kernel<<<dim3((unsigned)((most + 255) / 256), 7), 256, 0, h->stream>>>(a);
     VAEB_CUDA(cudaGetLastError());
     ++h->launches;
     s.mirrors_valid = true;

@@ -2,9 +2,9 @@
 //
 // The M = 100 update of the reference (VAEB.py:408-415 -- forward, bound, backward, prior, Adagrad; configs C2 and
 // the Bernoulli runs of scripts/pg_7_graphs.sh) as ONE persistent kernel of thread-block clusters: every contraction
-// runs on tcgen05 (bf16 hi+lo operands, three MMAs per k step, fp32 accumulation in TMEM: the fp32 parity tier), the
+// runs on tcgen05 (fp16 hi+lo operands, three MMAs per k step, fp32 accumulation in TMEM: the fp32 parity tier), the
 // split of a contraction over the four CTAs of a cluster is reduced through distributed shared memory, and EVERY
-// operand lives in global memory (L2) as a bf16 hi/lo mirror in the UMMA shared-memory image (pre-swizzled, K-major):
+// operand lives in global memory (L2) as an fp16 hi/lo mirror in the UMMA shared-memory image (pre-swizzled, K-major):
 // weights are rewritten by the Adagrad epilogues of the weight-gradient GEMMs, activations by the epilogue that
 // produces them -- so staging an operand is one cp.async.bulk.  Six grid barriers per update (the FFMA kernel of
 // fused_step.cu needs eight), no parameter double buffer.
@@ -40,17 +40,24 @@ struct Params {
   // *_t: [feature tile][batch chunk (2)][hi, lo][tile rows x 128 B] (operands of the weight gradients)
   uint8_t *he_km, *he_t, *hd_t, *da2_km, *da2_t, *da1_km, *da1_t, *dd_t, *z_t;
   uint8_t* z_km;                        // [z | 1]: one k chunk (column Z reads as 1: the bias of the decoder hidden layer)
+  uint8_t* dd_km;                       // [dmu | dls]: one k chunk (A operand of the dh_e GEMM inside the W3-gradient items)
+  uint8_t* m_w45k;                      // [W4 | W5] with the hidden unit as the row: tiles of 32 hidden units x one k chunk
+                                        // (k = column of [dmu|dls]); TWO copies selected by the parity of the step: the
+                                        // W4/W5 update of a step writes the copy the NEXT step's dh_e GEMMs read
+  int w45k_bytes;                       // bytes of one copy
+  // the minibatch as operands: x_km [k chunk][hi, lo][128 x 128 B] of the NEXT step (A of enc1) and x_t
+  // [pixel tile (+ the ones row at pixel D)][batch chunk (2)][hi, lo][128 x 128 B] of THIS step (A of the W3 gradient),
+  // both written during P2 by the clusters that have no latent-head item
+  uint8_t *x_km, *x_t;
   const float* x_base; const int* batch_order; const float* x_direct;
   const float* eps_inj;
   uint64_t seed; uint32_t step0; int64_t row_offset;
   float *he, *hd, *mu, *ls, *eps, *z;   // fp32 copies the epilogues read: [MP, HP], [MP, HP], [MP, Z] x 4
-  float* ddT;                           // [dmu|dls] transposed, fp32: [2Z][MP] (producer of the W3 gradient's B tile)
-  float* w45s;                          // snapshot of [W4|W5]^T taken in P5: [2Z][HP] (the W3-gradient producer reads it
-                                        // while the W4/W5 update of the same phase rewrites the parameters)
   float *partial, *aux;                 // [MP, tiles of dec2] log-likelihood row partials; [MP] KL / LA row terms
   int n_tiles3;                         // n tiles of dec2 (partial's leading dimension)
   float* scalars; float Mg; float bmult;
   int n_steps;
+  int dbg;                              // experiment switches (VAEB_ST2_DBG): timing studies only
   unsigned long long* bar; unsigned long long bar_base;
   long long* timing;                    // nullptr or [n_steps * (N_PHASES + 1) + 128] globaltimer stamps of CTA 0
 };
@@ -63,12 +70,14 @@ struct StepTcState {
   int n_cta = 0;
   int rows_init = -1;                   // minibatch rows the activation mirrors were cleared for
   unsigned long long* bar = nullptr; unsigned long long bar_count = 0;
-  uint8_t *m_enc1 = nullptr, *m_heads = nullptr, *m_dec2 = nullptr, *m_dgrad = nullptr, *m_dz = nullptr, *m_dec1 = nullptr;
+  uint8_t *m_enc1 = nullptr, *m_heads = nullptr, *m_dec2 = nullptr, *m_dgrad = nullptr, *m_dz = nullptr, *m_dec1 = nullptr,
+          *m_w45k = nullptr;
   uint8_t* act = nullptr; size_t act_bytes = 0;      // one allocation for every activation mirror
-  size_t o_he_km = 0, o_he_t = 0, o_hd_t = 0, o_da2_km = 0, o_da2_t = 0, o_da1_km = 0, o_da1_t = 0, o_dd_t = 0, o_z_t = 0, o_z_km = 0;
+  size_t o_he_km = 0, o_he_t = 0, o_hd_t = 0, o_da2_km = 0, o_da2_t = 0, o_da1_km = 0, o_da1_t = 0, o_dd_t = 0, o_z_t = 0, o_z_km = 0,
+         o_dd_km = 0, o_x_km = 0, o_x_t = 0;
   bool mirrors_valid = false;
   float *he = nullptr, *hd = nullptr, *mu = nullptr, *ls = nullptr, *eps = nullptr, *z = nullptr,
-        *ddT = nullptr, *w45s = nullptr, *partial = nullptr, *aux = nullptr;
+        *partial = nullptr, *aux = nullptr;
   int* d_order = nullptr; int order_cap = 0;
   long long* d_timing = nullptr; int timing_cap = 0;
 };
