@@ -56,8 +56,8 @@ __device__ __forceinline__ uint8_t* smem_base() {
 struct Ctx {
   uint8_t* sm;
   uint32_t tmem;
-  uint64_t *mma_bar, *op_bar, *x_bar;
-  uint32_t mma_phase, op_phase, x_phase;
+  uint64_t *mma_bar, *op_bar, *x_bar, *rs_bar;
+  uint32_t mma_phase, op_phase, x_phase, rs_phase;
   int rank, cid, ncl, warp, lane;
   long long* trace; int tn;            // optional sub-phase stamps (CTA 0, thread 0, last step of a profiling launch)
 };
@@ -74,8 +74,10 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+// 16 bytes into a peer CTA's shared memory; the peer's mbarrier counts them (no cluster barrier needed to hand them over)
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint32_t mbar, float a, float b, float c, float d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"(mbar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -287,11 +289,14 @@ __device__ __forceinline__ void mma_run(Ctx& c, int nch, int k16_total, int TBB,
 }
 
 // Partial accumulator [128 x N] -> the four CTAs of the cluster by row quarter: rows 32q..32q+31 go to CTA q, slot
-// `rank` of its receive buffer.  `have` == false sends zeros (this CTA had no k chunk).  Then a cluster barrier.
+// `rank` of its receive buffer, as asynchronous remote stores counted by the receiver's mbarrier (every CTA expects
+// CL x 32 x N floats per item).  `have` == false sends zeros (this CTA had no k chunk).  Returns when this CTA's own
+// receive buffer is complete.
 __device__ __forceinline__ void reduce_scatter(Ctx& c, int N, bool have) {
   const int q = c.warp & 3;
-  const uint32_t recv_local = tc::smem_u32(c.sm + SM_RECV);
-  const uint32_t dst0 = mapa(recv_local, (uint32_t)q);
+  if (threadIdx.x == 0) tc::mbar_expect_tx(c.rs_bar, (uint32_t)(CL * 32 * N * 4));
+  const uint32_t dst0 = mapa(tc::smem_u32(c.sm + SM_RECV), (uint32_t)q);
+  const uint32_t dbar = mapa(tc::smem_u32(c.rs_bar), (uint32_t)q);
   for (int u = c.warp >> 2; u < N / 8; u += 4) {
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (have) {
@@ -299,11 +304,12 @@ __device__ __forceinline__ void reduce_scatter(Ctx& c, int N, bool have) {
       tc::tmem_ld_wait();
     }
     const uint32_t d = dst0 + (uint32_t)(((c.rank * 32 + c.lane) * N + u * 8) * 4);
-    st_cluster_v4(d, v[0], v[1], v[2], v[3]);
-    st_cluster_v4(d + 16, v[4], v[5], v[6], v[7]);
+    st_async_v4(d, dbar, v[0], v[1], v[2], v[3]);
+    st_async_v4(d + 16, dbar, v[4], v[5], v[6], v[7]);
   }
   tc::tc_fence_before();
-  cluster_sync();
+  tc::mbar_wait(c.rs_bar, c.rs_phase);
+  c.rs_phase ^= 1u;
 }
 __device__ __forceinline__ float recv_sum(const float* recv, int N, int row, int col) {
   float s = 0.f;
@@ -556,8 +562,13 @@ __device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* 
         tc::tmem_ld_wait();
         const int kl = cg * 32 + u * 8;                          // column inside this rank's slice
         const int k0 = c0 * 64 + kl;
+        if (r < M && k0 + 8 <= H) {                              // the common case, without per-element predicates
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (r < M && k0 + e < H) ? tanh_fast(v[e] * WUNSCALE) : 0.f;
+          for (int e = 0; e < 8; ++e) v[e] = tanh_fast(v[e] * WUNSCALE);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = (r < M && k0 + e < H) ? tanh_fast(v[e] * WUNSCALE) : 0.f;
+        }
         if (publish && r < M && r % p.n_tiles3 == t) {           // no spare cluster: every cluster publishes a few rows of h_d
           float* o = p.hd + (size_t)r * p.HP + k0;
           *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
@@ -1089,8 +1100,9 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
   c.mma_bar = reinterpret_cast<uint64_t*>(c.sm + SM_MISC);
   c.op_bar = c.mma_bar + 1;
   c.x_bar = c.mma_bar + 3;
+  c.rs_bar = c.mma_bar + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c.sm + SM_MISC + 16);
-  c.mma_phase = 0; c.op_phase = 0; c.x_phase = 0;
+  c.mma_phase = 0; c.op_phase = 0; c.x_phase = 0; c.rs_phase = 0;
   c.rank = (int)cluster_ctarank(); c.cid = (int)cluster_idx(); c.ncl = (int)cluster_count();
   c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
   c.trace = nullptr; c.tn = 0;
@@ -1098,6 +1110,7 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     tc::mbar_init(c.mma_bar, 1);
     tc::mbar_init(c.op_bar, 1);
     tc::mbar_init(c.x_bar, 1);
+    tc::mbar_init(c.rs_bar, 1);
     tc::fence_barrier_init();
   }
   if (c.warp == 1) tc::tmem_alloc(tmem_slot, TMEM_COLS);
