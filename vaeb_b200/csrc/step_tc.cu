@@ -39,8 +39,8 @@ constexpr int SM_A = 0;                            // A_MAXCH chunks x (hi, lo) 
 constexpr int SM_B = A_MAXCH * 2 * TBA;            // B tiles: up to 32 KB (48 KB for the heads), scratch above
 constexpr int SM_B_BYTES = 57344;
 constexpr int SM_SCR = SM_B + 32768;               // 24 KB of producer scratch inside the B region
-constexpr int SM_RECV = SM_B + SM_B_BYTES;         // [CL][32 rows][<= 48 cols] fp32 partials from the cluster
-constexpr int SM_RECV_BYTES = CL * 32 * 48 * 4;
+constexpr int SM_RECV = SM_B + SM_B_BYTES;         // [CL][32 rows][<= 64 cols] fp32 partials from the cluster
+constexpr int SM_RECV_BYTES = CL * 32 * 64 * 4;
 constexpr int SM_MISC = SM_RECV + SM_RECV_BYTES;   // mbarriers, TMEM slot, small reductions
 constexpr int SMEM_BYTES = SM_MISC + 1024 + 1024;  // + slack for the 1024-byte alignment of the base
 constexpr uint32_t TMEM_COLS = 256;                // columns 0..63: a layer's accumulator; 64..191: the decoder hidden layer
@@ -138,6 +138,22 @@ __device__ __forceinline__ void put_unit(uint8_t* d, int half_bytes, const float
   split8<CLAMP>(v, hi, lo);
   *reinterpret_cast<uint4*>(d) = hi;
   *reinterpret_cast<uint4*>(d + half_bytes) = lo;
+}
+// one element of a DELTA tensor (da2, da1, [dmu|dls], dh_e).  Their magnitude is unbounded (d/da of a Gaussian
+// log-density scales with exp(-lv)) while fp16 ends at 65504, so the pair is (H, L) with v = 2^13 H + L: H = rn(v 2^-13)
+// covers |v| < 5.4e8, L = rn(v - 2^13 H) is the residual (|L| <= 2^-11 |v|, or the whole value while it is below the
+// spacing 2^-11 of H).  |error| <= max(2^-23 |v|, 2^-25) as for the other operands.  The two halves carry different
+// scales, so the MMAs that read H accumulate into a second TMEM accumulator (DH_COL columns further) and the reader
+// combines acc = 2^13 acc_H + acc_L.
+constexpr float DSCALE = 8192.0f, DUNSCALE = 1.0f / 8192.0f;
+// |da2|, |da1| above DLIMIT abort the step (Gaussian decoder): [dmu|dls] and dh_e, sums of at most 512 and 40 products
+// of these with weights, then stay inside 65504 x DSCALE for any weights below ~1 in magnitude
+constexpr float DLIMIT = 8192.0f;
+constexpr uint32_t DH_COL = 192;                   // TMEM column offset of the accumulator of the H products
+__device__ __forceinline__ void put_dl(uint8_t* d, int half_bytes, float v) {
+  const __half h = __float2half_rn(clamp_h(v * DUNSCALE));
+  *reinterpret_cast<__half*>(d) = h;
+  *reinterpret_cast<__half*>(d + half_bytes) = __float2half_rn(clamp_h(fmaf(-DSCALE, __half2float(h), v)));
 }
 // one element (hi at d, lo half_bytes later)
 __device__ __forceinline__ void put_hl(uint8_t* d, int half_bytes, float v) {
@@ -247,7 +263,10 @@ __device__ __forceinline__ void item_xmirrors(const Params& p, const float* __re
 __device__ __forceinline__ void ops_begin(Ctx& c, uint32_t bytes) { tc::mbar_expect_tx(c.op_bar, bytes); }
 // acc[128 x N] = sum over nch chunks / k16_total k steps of A.B^T (three MMAs per k step).  Called by EVERY thread; `wait_ops`: the
 // issuing thread first waits for the bulk copies announced by ops_begin.  Returns when the accumulator is complete.
-__device__ __forceinline__ void mma_run(Ctx& c, int nch, int k16_total, int TBB, int N, bool wait_ops) {
+// fa / fb = 1: the A / B operand is a delta tensor (put_dl): the products with its H half go to the accumulator at
+// DH_COL, the product with its L half to the main one.
+__device__ __forceinline__ void mma_run(Ctx& c, int nch, int k16_total, int TBB, int N, bool wait_ops, uint32_t acc0 = 0u,
+                                        int fa = 0, int fb = 0) {
   tc::fence_proxy_async();            // this thread's shared-memory stores -> visible to the tensor core (async proxy)
   tc::tc_fence_before();
   __syncthreads();
@@ -264,7 +283,8 @@ __device__ __forceinline__ void mma_run(Ctx& c, int nch, int k16_total, int TBB,
       const uint64_t d0 = tc::make_smem_desc(0u, 16u, 1024u);
       const uint64_t a0 = d0 | (uint64_t)(tc::smem_u32(c.sm + SM_A) >> 4), b0 = d0 | (uint64_t)(tc::smem_u32(c.sm + SM_B) >> 4);
       const uint32_t a_lo = TBA >> 4, b_lo = (uint32_t)TBB >> 4;
-      uint32_t acc = 0;
+      const uint32_t dL = c.tmem, dH = c.tmem + DH_COL;
+      uint32_t acc = acc0;                 // != 0: a later pass of a contraction that does not fit the A region at once
       int k16 = 0;
 #pragma unroll 1
       for (int ci = 0; ci < nch; ++ci) {
@@ -272,9 +292,19 @@ __device__ __forceinline__ void mma_run(Ctx& c, int nch, int k16_total, int TBB,
 #pragma unroll
         for (int k = 0; k < 4; ++k, ++k16) {
           if (k16 >= k16_total) break;
-          tc::umma_bf16(c.tmem, a + 2 * k, b + 2 * k, idesc, acc);
-          tc::umma_bf16(c.tmem, a + 2 * k, b + b_lo + 2 * k, idesc, 1u);
-          tc::umma_bf16(c.tmem, a + a_lo + 2 * k, b + 2 * k, idesc, 1u);
+          if (fa) {                        // A = (H, L)
+            tc::umma_bf16(dH, a + 2 * k, b + 2 * k, idesc, acc);
+            tc::umma_bf16(dH, a + 2 * k, b + b_lo + 2 * k, idesc, 1u);
+            tc::umma_bf16(dL, a + a_lo + 2 * k, b + 2 * k, idesc, acc);
+          } else if (fb) {                 // B = (H, L)
+            tc::umma_bf16(dH, a + 2 * k, b + 2 * k, idesc, acc);
+            tc::umma_bf16(dL, a + 2 * k, b + b_lo + 2 * k, idesc, acc);
+            tc::umma_bf16(dH, a + a_lo + 2 * k, b + 2 * k, idesc, 1u);
+          } else {
+            tc::umma_bf16(dL, a + 2 * k, b + 2 * k, idesc, acc);
+            tc::umma_bf16(dL, a + 2 * k, b + b_lo + 2 * k, idesc, 1u);
+            tc::umma_bf16(dL, a + a_lo + 2 * k, b + 2 * k, idesc, 1u);
+          }
           acc = 1u;
         }
       }
@@ -287,22 +317,32 @@ __device__ __forceinline__ void mma_run(Ctx& c, int nch, int k16_total, int TBB,
     tc::tc_fence_after();
   }
 }
+// eight accumulator columns of this thread's TMEM lane; delta: combined with the accumulator of the H products
+__device__ __forceinline__ void acc_ld8(const Ctx& c, int q, uint32_t col, float* v, bool delta) {
+  tmem_ld8(c.tmem + ((uint32_t)(q * 32) << 16) + col, v);
+  if (delta) {
+    float h[8];
+    tmem_ld8(c.tmem + ((uint32_t)(q * 32) << 16) + DH_COL + col, h);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaf(h[e], DSCALE, v[e]);
+  } else {
+    tc::tmem_ld_wait();
+  }
+}
 
 // Partial accumulator [128 x N] -> the four CTAs of the cluster by row quarter: rows 32q..32q+31 go to CTA q, slot
 // `rank` of its receive buffer, as asynchronous remote stores counted by the receiver's mbarrier (every CTA expects
 // CL x 32 x N floats per item).  `have` == false sends zeros (this CTA had no k chunk).  Returns when this CTA's own
 // receive buffer is complete.
-__device__ __forceinline__ void reduce_scatter(Ctx& c, int N, bool have) {
+__device__ __forceinline__ void reduce_scatter(Ctx& c, int N, bool have, bool delta = false) {
   const int q = c.warp & 3;
   if (threadIdx.x == 0) tc::mbar_expect_tx(c.rs_bar, (uint32_t)(CL * 32 * N * 4));
   const uint32_t dst0 = mapa(tc::smem_u32(c.sm + SM_RECV), (uint32_t)q);
   const uint32_t dbar = mapa(tc::smem_u32(c.rs_bar), (uint32_t)q);
   for (int u = c.warp >> 2; u < N / 8; u += 4) {
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (have) {
-      tmem_ld8(c.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * 8), v);
-      tc::tmem_ld_wait();
-    }
+    if (have) acc_ld8(c, q, (uint32_t)(u * 8), v, delta);
     const uint32_t d = dst0 + (uint32_t)(((c.rank * 32 + c.lane) * N + u * 8) * 4);
     st_async_v4(d, dbar, v[0], v[1], v[2], v[3]);
     st_async_v4(d + 16, dbar, v[4], v[5], v[6], v[7]);
@@ -490,33 +530,36 @@ __device__ __forceinline__ void item_heads(Ctx& c, const Params& p, uint32_t ste
   ST2_TRACE(c, 25);
 }
 
-// P3: h_d = tanh(z.W1 + b1) recomputed into the A tile, a = h_d.W2 + b2, x a - softplus(a), da2 = w (x - sigmoid a)
+// P3: h_d = tanh(z.W1 + b1) recomputed into the A tile, a = h_d.W2 + b2, x a - softplus(a), da2 = x - sigmoid a
 //                                                                                           VAEB.py:254,263,311
-__device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* x, int t, bool more, bool publish) {
+// Gaussian decoder: the tile holds [W2 | W6] for 32 pixels; mu = sigmoid(a), lv = h_d.W6 + b6, the log-density of
+// VAEB.py:306-307 and its two deltas.
+__device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* x, int t, bool more, bool publish, int s) {
   ST2_TRACE(c, 30);
   const int c0 = c.rank * p.KH / CL, c1 = (c.rank + 1) * p.KH / CL, nch = c1 - c0;
-  constexpr int TB = TR_DEC2 * 128;
-  const int Z = p.Z, H = p.H, M = p.M;
-  // Operands of BOTH GEMMs of the item in one transaction: [z|1] (A of the hidden layer) into the last chunk of the A
-  // region, this rank's 64-unit tiles of [W1^T|b1] behind the W2 blob in the B region.
+  const int TR = p.TR3, TB = TR * 128;
+  const int H = p.H, M = p.M;
+  // Operands of BOTH GEMMs of the item in one transaction: [z|1] (A of the hidden layer) into the last chunk slot of
+  // the A region, this rank's 64-unit tiles of [W1^T|b1] into the slot before it (nch <= 2: H <= 512).
   constexpr int T1 = 64 * 128;                                  // one half (hi or lo) of a [W1^T|b1] tile
   uint8_t* z_sm = c.sm + SM_A + 3 * 2 * TBA;
-  uint8_t* w1_sm = c.sm + SM_B + 16384;
+  uint8_t* w1_sm = c.sm + SM_A + 2 * 2 * TBA;
   if (threadIdx.x == 0 && nch > 0) {
     ops_begin(c, (uint32_t)(nch * 2 * TB + 2 * TBA + nch * 2 * T1));
     bulk_g2s(z_sm, p.z_km, (uint32_t)(2 * TBA), c.op_bar);
     bulk_g2s(w1_sm, p.m_dec1 + (size_t)c0 * 2 * T1, (uint32_t)(nch * 2 * T1), c.op_bar);
     bulk_g2s(c.sm + SM_B, p.m_dec2 + ((size_t)t * p.KH + c0) * 2 * TB, (uint32_t)(nch * 2 * TB), c.op_bar);
   }
-  // this thread's two elements of the final stage: x and the output bias (in flight during both GEMMs)
-  float xv_[2], b2_[2];
+  // this thread's two elements of the final stage: x and the output biases (in flight during both GEMMs)
+  float xv_[2], b2_[2], b6_[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int it = threadIdx.x + i * NT;
-    const int gr = c.rank * 32 + (it >> 5), n = t * TR_DEC2 + (it & 31);
+    const int gr = c.rank * 32 + (it >> 5), n = t * 32 + (it & 31);
     const bool ok = gr < M && n < p.D;
     xv_[i] = ok ? __ldcg(x + (size_t)gr * p.D + n) : 0.f;
     b2_[i] = ok ? __ldcg(p.P + p.ob2 + n) : 0.f;
+    b6_[i] = (ok && p.cont) ? __ldcg(p.P + p.ob6 + n) : 0.f;
   }
   ST2_TRACE(c, 36);
   // ---- hidden layer on the tensor cores: D1[128 x 64 nch] = [z|1] . [W1^T|b1]^T (K = 32: latent code + bias) --------
@@ -583,31 +626,44 @@ __device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* 
   }
   ST2_TRACE(c, 39);
   ST2_TRACE(c, 31);
-  mma_run(c, nch, nch * 4, TB, TR_DEC2, false);
+  mma_run(c, nch, nch * 4, TB, TR, false);
   ST2_TRACE(c, 32);
-  reduce_scatter(c, TR_DEC2, nch > 0);
+  reduce_scatter(c, TR, nch > 0);
   ST2_TRACE(c, 33);
   const float* recv = reinterpret_cast<const float*>(c.sm + SM_RECV);
   float* term = reinterpret_cast<float*>(c.sm + SM_B);          // [32][32]
-  float* dtile = term + 32 * 32;                                // [32][33]
+  float* dtile = term + 32 * 32;                                // [32][33] (+ a second one for the Gaussian lv deltas)
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int it = threadIdx.x + i * NT;
     const int row = it >> 5, col = it & 31;
-    const int gr = c.rank * 32 + row, n = t * TR_DEC2 + col;
-    float tv = 0.f, dval = 0.f;
+    const int gr = c.rank * 32 + row, n = t * 32 + col;
+    float tv = 0.f, dval = 0.f, dval2 = 0.f;
     if (gr < M && n < p.D) {
-      const float a = fmaf(recv_sum(recv, TR_DEC2, row, col), WUNSCALE, b2_[i]);
+      const float a = fmaf(recv_sum(recv, TR, row, col), WUNSCALE, b2_[i]);
       const float xv = xv_[i];
       float sp, sg;
       softplus_sigmoid(a, sp, sg);
-      const float d = xv - sg;                                 // deltas are carried without the factor w (applied with the weight gradients)
-      put_hl(km_addr(p.da2_km, gr, n), TBA, d);
-      dval = d;
-      tv = xv * a - sp;
+      if (!p.cont) {
+        dval = xv - sg;                                          // deltas are carried without the factor w (applied with the weight gradients)
+        put_dl(km_addr(p.da2_km, gr, n), TBA, dval);
+        tv = xv * a - sp;
+      } else {
+        const float lv = fmaf(recv_sum(recv, TR, row, 32 + col), WUNSCALE, b6_[i]);
+        float iv;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(iv) : "f"(-1.4426950408889634f * lv));   // exp(-lv)
+        const float d = xv - sg, r_ = d * iv;
+        dval = r_ * sg * (1.0f - sg);                            // d/da   of VAEB.py:306-307 through mu = sigmoid(a)
+        dval2 = fmaf(0.5f * d, r_, -0.5f);                       // d/dlv
+        if (!(fmaxf(fabsf(dval), fabsf(dval2)) <= DLIMIT)) *p.status = s;   // (also NaN) -> the launch stops before P5
+        put_dl(km_addr(p.da2_km, gr, t * 64 + col), TBA, dval);
+        put_dl(km_addr(p.da2_km, gr, t * 64 + 32 + col), TBA, dval2);
+        tv = -0.91893853320467274178f - 0.5f * lv - 0.5f * d * r_;
+      }
     }
     term[it] = tv;
     dtile[row * 33 + col] = dval;
+    if (p.cont) dtile[32 * 33 + row * 33 + col] = dval2;
   }
   __syncthreads();
   // the transposed mirror (operand of the W2 gradient) with the lanes along the batch rows: 64 contiguous bytes per store
@@ -615,14 +671,17 @@ __device__ __forceinline__ void item_dec2(Ctx& c, const Params& p, const float* 
   for (int i = 0; i < 2; ++i) {
     const int it = threadIdx.x + i * NT;
     const int col = it >> 5, row = it & 31;
-    const int gr = c.rank * 32 + row, n = t * TR_DEC2 + col;
-    if (gr < M && n < p.D) put_hl(t_addr(p.da2_t, t, TB, col, gr), TB, dtile[row * 33 + col]);
+    const int gr = c.rank * 32 + row, n = t * 32 + col;
+    if (gr < M && n < p.D) {
+      put_dl(t_addr(p.da2_t, t, TB, col, gr), TB, dtile[row * 33 + col]);
+      if (p.cont) put_dl(t_addr(p.da2_t, t, TB, 32 + col, gr), TB, dtile[32 * 33 + row * 33 + col]);
+    }
   }
   if (threadIdx.x < 32) {
     const int gr = c.rank * 32 + threadIdx.x;
     if (gr < M) {
       float s = 0.f;
-      for (int j = 0; j < TR_DEC2; ++j) s += term[threadIdx.x * TR_DEC2 + j];
+      for (int j = 0; j < 32; ++j) s += term[threadIdx.x * 32 + j];
       p.partial[(size_t)gr * p.n_tiles3 + t] = s;
     }
   }
@@ -689,28 +748,35 @@ __device__ __forceinline__ void item_hd(Ctx& c, const Params& p, int g) {
 }
 
 // P4: da1[:, 16t..] = (da2.W2^T) * (1 - h_d^2)                                              T.grad, VAEB.py:397
-__device__ __forceinline__ void item_dgrad(Ctx& c, const Params& p, int t, bool more) {
+// (Gaussian decoder: K runs over the virtual columns [da | dlv] against [W2 | W6]^T.)  A rank's share of K may exceed
+// the A region (Frey Face: 18 chunks over 4 ranks): further passes accumulate into the same TMEM columns.
+__device__ __forceinline__ void item_dgrad(Ctx& c, const Params& p, int t, bool more, int s) {
   ST2_TRACE(c, 40);
-  const int c0 = c.rank * p.KD / CL, c1 = (c.rank + 1) * p.KD / CL, nch = c1 - c0;
+  const int c0 = c.rank * p.KV / CL, c1 = (c.rank + 1) * p.KV / CL, nch = c1 - c0;
   constexpr int TB = TR_DGRAD * 128;
-  if (threadIdx.x == 0 && nch > 0) {
-    ops_begin(c, (uint32_t)(nch * 2 * (TBA + TB)));
-    bulk_g2s(c.sm + SM_A, p.da2_km + (size_t)c0 * 2 * TBA, (uint32_t)(nch * 2 * TBA), c.op_bar);
-    bulk_g2s(c.sm + SM_B, p.m_dgrad + ((size_t)t * p.KD + c0) * 2 * TB, (uint32_t)(nch * 2 * TB), c.op_bar);
-  }
   const int row = threadIdx.x >> 4, col = threadIdx.x & 15;
   const int gr = c.rank * 32 + row, j = t * 16 + col;
   const float hv = gr < p.M ? __ldcg(p.hd + (size_t)gr * p.HP + j) : 0.f;
-  ST2_TRACE(c, 41);
-  mma_run(c, nch, min(nch * 4, (p.D - c0 * 64 + 15) / 16), TB, TR_DGRAD, nch > 0);
+  for (int base = 0; base < nch || base == 0; base += A_MAXCH) {
+    const int n = min(nch - base, A_MAXCH);
+    if (threadIdx.x == 0 && n > 0) {
+      ops_begin(c, (uint32_t)(n * 2 * (TBA + TB)));
+      bulk_g2s(c.sm + SM_A, p.da2_km + (size_t)(c0 + base) * 2 * TBA, (uint32_t)(n * 2 * TBA), c.op_bar);
+      bulk_g2s(c.sm + SM_B, p.m_dgrad + ((size_t)t * p.KV + c0 + base) * 2 * TB, (uint32_t)(n * 2 * TB), c.op_bar);
+    }
+    ST2_TRACE(c, 41);
+    const int k16 = p.cont ? n * 4 : min(n * 4, (p.D - (c0 + base) * 64 + 15) / 16);
+    mma_run(c, max(n, 0), k16, TB, TR_DGRAD, n > 0, base ? 1u : 0u, 1, 0);
+  }
   ST2_TRACE(c, 42);
-  reduce_scatter(c, TR_DGRAD, nch > 0);
+  reduce_scatter(c, TR_DGRAD, nch > 0, true);
   ST2_TRACE(c, 43);
   const float* recv = reinterpret_cast<const float*>(c.sm + SM_RECV);
   if (gr < p.M) {
     const float d = recv_sum(recv, TR_DGRAD, row, col) * WUNSCALE * (1.0f - hv * hv);
-    put_hl(km_addr(p.da1_km, gr, j), TBA, d);
-    if (j < p.H) put_hl(t_addr(p.da1_t, j >> 7, TBA, j & 127, gr), TBA, d);
+    if (p.cont && !(fabsf(d) <= DLIMIT)) *p.status = s;
+    put_dl(km_addr(p.da1_km, gr, j), TBA, d);
+    if (j < p.H) put_dl(t_addr(p.da1_t, j >> 7, TBA, j & 127, gr), TBA, d);
   }
   ST2_TRACE(c, 44);
   if (more) cluster_sync();          // the receive buffer is reused by this cluster's next item of the phase
@@ -742,9 +808,9 @@ __device__ __forceinline__ void item_dz(Ctx& c, const Params& p, bool more) {
     }
   }
   ST2_TRACE(c, 51);
-  mma_run(c, nch, nch * 4, TB, N, nch > 0);
+  mma_run(c, nch, nch * 4, TB, N, nch > 0, 0u, 1, 0);
   ST2_TRACE(c, 52);
-  reduce_scatter(c, N, nch > 0);
+  reduce_scatter(c, N, nch > 0, true);
   ST2_TRACE(c, 53);
   const float* recv = reinterpret_cast<const float*>(c.sm + SM_RECV);
 #pragma unroll
@@ -763,10 +829,10 @@ __device__ __forceinline__ void item_dz(Ctx& c, const Params& p, bool more) {
         a -= zm_[i];
         b += 0.5f * (1.0f - expf(ls_[i]));
       }
-      put_hl(km_addr(p.dd_km, gr, j), TBA, a);                                   // A operand of the dh_e GEMMs (P6)
-      put_hl(km_addr(p.dd_km, gr, Z + j), TBA, b);
-      put_hl(t_addr(p.dd_t, j >> 4, 2048, j & 15, gr), 2048, a);                 // [dmu|dls]^T in tiles of 16 columns
-      put_hl(t_addr(p.dd_t, (Z + j) >> 4, 2048, (Z + j) & 15, gr), 2048, b);
+      put_dl(km_addr(p.dd_km, gr, j), TBA, a);                                   // A operand of the dh_e GEMMs (P6)
+      put_dl(km_addr(p.dd_km, gr, Z + j), TBA, b);
+      put_dl(t_addr(p.dd_t, j >> 4, 2048, j & 15, gr), 2048, a);                 // [dmu|dls]^T in tiles of 16 columns
+      put_dl(t_addr(p.dd_t, (Z + j) >> 4, 2048, (Z + j) & 15, gr), 2048, b);
     }
   }
   ST2_TRACE(c, 54);
@@ -818,13 +884,13 @@ __device__ __forceinline__ void wgrad_prefetch(Ctx& c, const Params& p, OffF off
 }
 template <int N, class MirF>
 __device__ __forceinline__ void wgrad_epilogue_coalesced(Ctx& c, const Params& p, const Hyper& hy, const WgPre<N>& w, MirF mir) {
+  // (every weight-gradient GEMM has a delta operand: the two accumulators are combined while they are parked)
   constexpr int GP = 33;
   float* gt = reinterpret_cast<float*>(c.sm + SM_RECV);            // 128 x 33 floats = 16.5 KB (no cluster item is active)
   const int q = c.warp & 3;
   for (int u = c.warp >> 2; u < N / 8; u += 4) {
     float v[8];
-    tmem_ld8(c.tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * 8), v);
-    tc::tmem_ld_wait();
+    acc_ld8(c, q, (uint32_t)(u * 8), v, true);
 #pragma unroll
     for (int e = 0; e < 8; ++e) gt[(q * 32 + c.lane) * GP + u * 8 + e] = v[e];
   }
@@ -856,38 +922,46 @@ __device__ __forceinline__ void wgrad_epilogue_coalesced(Ctx& c, const Params& p
   __syncthreads();
 }
 
-// W2, b2 <- Adagrad([h_d | 1]^T . da2); tile = 128 hidden units x 32 pixels
-__device__ __forceinline__ void item_wg2(Ctx& c, const Params& p, const Hyper& hy, int mt, int nt) {
+// W2, b2 <- Adagrad([h_d | 1]^T . da2); tile = 128 hidden units x 32 pixels.  Gaussian decoder: `which` = 1 selects
+// the W6 / b6 half of the tile (rows 32..63 of the transposed delta mirror, virtual columns 32..63 of the chunk).
+__device__ __forceinline__ void item_wg2(Ctx& c, const Params& p, const Hyper& hy, int mt, int nt, int which) {
   ST2_TRACE(c, 60);
-  constexpr int TB = TR_DEC2 * 128;
+  constexpr int TB = 32 * 128;                                  // the B tile of the item: 32 rows
+  const int TBM = p.TR3 * 128;                                  // one half (hi or lo) of a delta-mirror tile
   if (threadIdx.x == 0) {
     ops_begin(c, (uint32_t)(4 * TBA + 4 * TB));
     bulk_g2s(c.sm + SM_A, p.hd_t + (size_t)mt * 4 * TBA, (uint32_t)(4 * TBA), c.op_bar);
-    bulk_g2s(c.sm + SM_B, p.da2_t + (size_t)nt * 4 * TB, (uint32_t)(4 * TB), c.op_bar);
+    const uint8_t* src = p.da2_t + (size_t)nt * 4 * TBM + (size_t)which * TB;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)                                 // (batch chunk, hi / lo): 32 rows of each
+      bulk_g2s(c.sm + SM_B + q * TB, src + (size_t)q * TBM, (uint32_t)TB, c.op_bar);
   }
   const int H = p.H, D = p.D;
-  WgPre<TR_DEC2> pre;
-  wgrad_prefetch<TR_DEC2>(c, p, [&](int row, int col) -> long long {
-    const int i = mt * MP + row, n = nt * TR_DEC2 + col;
+  const long long oW = which ? p.oW6 : p.oW2, ob = which ? p.ob6 : p.ob2;
+  WgPre<32> pre;
+  wgrad_prefetch<32>(c, p, [&](int row, int col) -> long long {
+    const int i = mt * MP + row, n = nt * 32 + col;
     if (i > H || n >= D) return -1;
-    return i < H ? p.oW2 + (long long)i * D + n : p.ob2 + n;
+    return i < H ? oW + (long long)i * D + n : ob + n;
   }, pre);
-  mma_run(c, 2, (p.M + 15) / 16, TB, TR_DEC2, true);
+  mma_run(c, 2, (p.M + 15) / 16, TB, 32, true, 0u, 0, 1);
   ST2_TRACE(c, 61);
-  wgrad_epilogue_coalesced<TR_DEC2>(
+  wgrad_epilogue_coalesced<32>(
       c, p, hy, pre,
       [&](int row, int col0, float* nv) {
-        const int i = mt * MP + row, n0 = nt * TR_DEC2 + col0;
+        const int i = mt * MP + row, n0 = nt * 32 + col0;
         if (i >= H || n0 >= D) return;
+        const int vr = which * 32 + col0;                        // row of the dec2 tile = virtual column inside the chunk
 #pragma unroll
         for (int e = 0; e < 8; ++e)
-          if (n0 + e < D) mirror_put(p.m_dec2, TR_DEC2, p.KH, nt, col0 + e, i, nv[e]);
+          if (n0 + e < D) mirror_put(p.m_dec2, p.TR3, p.KH, nt, vr + e, i, nv[e]);
           else nv[e] = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) nv[e] *= WSCALE;
-        // dgrad mirror: row = hidden unit i, k = pixel: eight consecutive k = one 16-byte unit (n0 is a multiple of 8)
+        // dgrad mirror: row = hidden unit i, k = (virtual) output column: eight consecutive k = one 16-byte unit
         constexpr int TG = TR_DGRAD * 128;
-        put_unit<true>(p.m_dgrad + ((size_t)(i >> 4) * p.KD + (n0 >> 6)) * 2 * TG + unit_off(i & 15, (n0 & 63) >> 3), TG, nv);
+        const int kv = p.cont ? nt * 64 + vr : n0;
+        put_unit<true>(p.m_dgrad + ((size_t)(i >> 4) * p.KV + (kv >> 6)) * 2 * TG + unit_off(i & 15, (kv & 63) >> 3), TG, nv);
       });
   ST2_TRACE(c, 62);
 }
@@ -930,15 +1004,15 @@ __device__ __forceinline__ void item_wg3(Ctx& c, const Params& p, const Hyper& h
     tc::mbar_wait(c.op_bar, c.op_phase);
     c.op_phase ^= 1u;
     tc::tc_fence_after();
-    const uint32_t idesc = tc::make_idesc_f16(MP, 32, 0, 0);
+    const uint32_t idesc = tc::make_idesc_f16(MP, 32, 0, 0);    // A = a delta tensor: H products at +96, L product at +64
     const uint64_t d0 = tc::make_smem_desc(0u, 16u, 1024u);
     const uint64_t a = d0 | (uint64_t)(tc::smem_u32(dd_sm) >> 4), bdesc = d0 | (uint64_t)(tc::smem_u32(w45_sm) >> 4);
     const uint32_t a_lo = TBA >> 4, b_lo = TB >> 4;
     const int ks = (2 * p.Z + 15) / 16;
     for (int k = 0; k < ks; ++k) {
-      tc::umma_bf16(c.tmem + 64u, a + 2 * k, bdesc + 2 * k, idesc, k ? 1u : 0u);
-      tc::umma_bf16(c.tmem + 64u, a + 2 * k, bdesc + b_lo + 2 * k, idesc, 1u);
-      tc::umma_bf16(c.tmem + 64u, a + a_lo + 2 * k, bdesc + 2 * k, idesc, 1u);
+      tc::umma_bf16(c.tmem + 96u, a + 2 * k, bdesc + 2 * k, idesc, k ? 1u : 0u);
+      tc::umma_bf16(c.tmem + 96u, a + 2 * k, bdesc + b_lo + 2 * k, idesc, 1u);
+      tc::umma_bf16(c.tmem + 64u, a + a_lo + 2 * k, bdesc + 2 * k, idesc, k ? 1u : 0u);
     }
     tc::umma_commit(c.mma_bar);
   }
@@ -947,19 +1021,22 @@ __device__ __forceinline__ void item_wg3(Ctx& c, const Params& p, const Hyper& h
   tc::tc_fence_after();
   ST2_TRACE(c, 74);
   {
-    float v[8];
+    float v[8], vh[8];
     tmem_ld8(c.tmem + ((uint32_t)(q * 32) << 16) + 64u + (uint32_t)(cg * 8), v);
+    tmem_ld8(c.tmem + ((uint32_t)(q * 32) << 16) + 96u + (uint32_t)(cg * 8), vh);
     tc::tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaf(vh[e], DSCALE, v[e]);
     // B tile of the weight gradient: row = hidden unit, k = batch row -> 2-byte stores, a warp writes 64 contiguous bytes
     uint8_t* bt = c.sm + SM_B + (size_t)(b >> 6) * 2 * TB;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float d = (b < M && j0 + e < H) ? v[e] * WUNSCALE * (1.0f - hv[e] * hv[e]) : 0.f;
-      put_hl(bt + tc::sw128_offset(cg * 8 + e, b & 63), TB, d);
+      put_dl(bt + tc::sw128_offset(cg * 8 + e, b & 63), TB, d);
     }
   }
   ST2_TRACE(c, 71);
-  mma_run(c, 2, (M + 15) / 16, TB, 32, false);
+  mma_run(c, 2, (M + 15) / 16, TB, 32, false, 0u, 0, 1);
   ST2_TRACE(c, 72);
   wgrad_epilogue_coalesced<32>(
       c, p, hy, pre,
@@ -996,11 +1073,10 @@ __device__ __forceinline__ void item_wg1(Ctx& c, const Params& p, const Hyper& h
     pv[e] = ok[e] ? __ldcg(p.P + off[e]) : 0.f;
     av[e] = ok[e] ? __ldcg(p.ada + off[e]) : 0.f;
   }
-  mma_run(c, 2, (p.M + 15) / 16, TB, N, true);
+  mma_run(c, 2, (p.M + 15) / 16, TB, N, true, 0u, 1, 0);
   if (u < N / 8) {
     float v[8], nv[8];
-    tmem_ld8(c.tmem + ((uint32_t)(qq * 32) << 16) + (uint32_t)col0, v);
-    tc::tmem_ld_wait();
+    acc_ld8(c, qq, (uint32_t)col0, v, true);
     if (mine) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -1044,7 +1120,7 @@ __device__ __forceinline__ void item_wg45(Ctx& c, const Params& p, const Hyper& 
     if (i < H) return (cc < Z ? p.oW4 : p.oW5) + (long long)i * Z + jc;
     return (cc < Z ? p.ob4 : p.ob5) + jc;
   }, pre);
-  mma_run(c, 2, (p.M + 15) / 16, TB, N, true);
+  mma_run(c, 2, (p.M + 15) / 16, TB, N, true, 0u, 0, 1);
   wgrad_epilogue_coalesced<N>(
       c, p, hy, pre,
       [&](int row, int col0, float* nv) {
@@ -1181,7 +1257,7 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     if (tm) tm[2] = gtime();
     ST2_TRACE(c, 92);
     // ---- P3: decoder + log-likelihood | h_d published by the spare clusters ------------------------------------------
-    for (int it = c.cid; it < n3; it += c.ncl) item_dec2(c, p, x, it, it + c.ncl < n3, n_spare <= 0);
+    for (int it = c.cid; it < n3; it += c.ncl) item_dec2(c, p, x, it, it + c.ncl < n3, n_spare <= 0, s);
     if (c.cid >= n3)
       for (int g = (c.cid - n3) * CL + c.rank; g < p.HP / 16; g += n_spare * CL) item_hd(c, p, g);
     ST2_TRACE(c, 83);
@@ -1190,20 +1266,23 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     if (tm) tm[3] = gtime();
     ST2_TRACE(c, 93);
     // ---- P4: back through the decoder output layer ---------------------------------------------------------------
-    for (int it = c.cid; it < n1; it += c.ncl) item_dgrad(c, p, it, it + c.ncl < n1);
+    for (int it = c.cid; it < n1; it += c.ncl) item_dgrad(c, p, it, it + c.ncl < n1, s);
     ST2_TRACE(c, 84);
     ARRIVE(3);
     grid_barrier(p.bar, target += G);
     if (tm) tm[4] = gtime();
     ST2_TRACE(c, 94);
+    // Gaussian decoder: a delta left the operand range -> every CTA leaves before the first parameter update of step s
+    if (p.cont && __syncthreads_or(threadIdx.x == 0 && __ldcg(p.status) >= 0)) break;
     // ---- P5: dz | W2 update | the bound ---------------------------------------------------------------------------
     {
-      const int n2 = m_h1 * n3;
+      const int nw = p.cont ? 2 : 1;                              // Gaussian decoder: W2 and W6
+      const int n2 = m_h1 * n3 * nw;
       const int g2 = n_groups(n2 + 1);
       for (int it = c.cid; it < 1 + g2; it += c.ncl) {
         if (it == 0) { item_dz(c, p, false); continue; }
         const int i = (it - 1) * CL + c.rank;
-        if (i < n2) item_wg2(c, p, hy, i / n3, i % n3);
+        if (i < n2) item_wg2(c, p, hy, i / (n3 * nw), (i / nw) % n3, i % nw);
         else if (i == n2) item_bound(c, p, s);
       }
     }
@@ -1241,7 +1320,7 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
 
 // ---- mirrors from the fp32 master parameters (after set_tensors / load / an update by another path) ----------------
 struct MirrorArgs {
-  const float* P; int64_t oW3, oW4, oW5, oW1, oW2, ob1;
+  const float* P; int64_t oW3, oW4, oW5, oW1, oW2, ob1, oW6; int cont, TR3, KV;
   uint8_t *m_enc1, *m_heads, *m_dec2, *m_dgrad, *m_dz, *m_dec1, *m_w45k;
   int D, H, Z, HP, KD, KH, NH, NZ;
 };
@@ -1265,18 +1344,21 @@ __global__ void __launch_bounds__(256) build_mirrors_kernel(MirrorArgs a) {
       mirror_put(a.m_heads, a.NH, a.KH, 0, n, k, v);
       break;
     }
-    case 2: {   // dec2: n = pixel (tiles of 32), k = hidden
-      const int K = a.KH * 64, NR = (D + TR_DEC2 - 1) / TR_DEC2 * TR_DEC2;
+    case 2: {   // dec2: n = (virtual) output column (tiles of TR3), k = hidden
+      const int K = a.KH * 64, NR = (D + 31) / 32 * a.TR3;
       if (i >= (int64_t)NR * K) return;
       const int n = (int)(i / K), k = (int)(i % K);
-      mirror_put(a.m_dec2, TR_DEC2, a.KH, n / TR_DEC2, n % TR_DEC2, k, (n < D && k < H) ? a.P[a.oW2 + (size_t)k * D + n] : 0.f);
+      const int r = n % a.TR3, px = (n / a.TR3) * 32 + (r & 31);           // r >= 32: the W6 half (Gaussian decoder)
+      mirror_put(a.m_dec2, a.TR3, a.KH, n / a.TR3, r, k, (px < D && k < H) ? a.P[(r < 32 ? a.oW2 : a.oW6) + (size_t)k * D + px] : 0.f);
       break;
     }
-    case 3: {   // dgrad: n = hidden (HP rows), k = pixel
-      const int K = a.KD * 64;
+    case 3: {   // dgrad: n = hidden (HP rows), k = (virtual) output column
+      const int K = a.KV * 64;
       if (i >= (int64_t)a.HP * K) return;
       const int n = (int)(i / K), k = (int)(i % K);
-      mirror_put(a.m_dgrad, TR_DGRAD, a.KD, n / TR_DGRAD, n % TR_DGRAD, k, (n < H && k < D) ? a.P[a.oW2 + (size_t)n * D + k] : 0.f);
+      const int px = a.cont ? (k >> 6) * 32 + (k & 31) : k;
+      const int64_t oW = (a.cont && (k & 32)) ? a.oW6 : a.oW2;
+      mirror_put(a.m_dgrad, TR_DGRAD, a.KV, n / TR_DGRAD, n % TR_DGRAD, k, (n < H && px < D) ? a.P[oW + (size_t)n * D + px] : 0.f);
       break;
     }
     case 6: {   // [W4|W5] with the hidden unit as the row (tiles of 32), k = column of [dmu|dls]; both parity copies
@@ -1328,15 +1410,15 @@ __global__ void __launch_bounds__(128) init_ones_kernel(OnesArgs a) {
 bool step_tc_supported(const vaeb_handle* h, int rows) {
   const int e = h->cfg.estimator;
   if (h->steptc.unavailable || h->steptc_off) return false;
-  return (e == VAEB_EST_LB || e == VAEB_EST_LA) && !h->cont && h->L == 1 && h->world == 1 &&
+  return (e == VAEB_EST_LB || e == VAEB_EST_LA) && h->L == 1 && h->world == 1 &&
          h->cfg.precision != VAEB_PREC_BF16 && h->optimizer == VAEB_OPT_ADAGRAD && rows >= 1 && rows <= st2::MP &&
          (h->D % 8) == 0 && (h->H % 4) == 0 && h->D >= 64 && h->H >= 64 && h->D <= 1024 && h->H <= 512 && h->Z >= 1 &&
-         h->Z <= 20;
-}
+         h->Z <= 20 && (!h->cont || fused_step_supported(h, rows));   // Gaussian decoder: the fp32 kernel takes over a step
+}                                                                      // whose deltas leave the fp16 range
 
 void step_tc_free(StepTcState& s) {
   void* ptrs[] = {s.bar, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz, s.m_dec1, s.act, s.he, s.hd, s.mu, s.ls,
-                  s.eps, s.z, s.m_w45k, s.partial, s.aux, s.d_order, s.d_timing};
+                  s.eps, s.z, s.m_w45k, s.partial, s.aux, s.d_order, s.d_timing, s.d_status};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   s = StepTcState();
@@ -1348,7 +1430,8 @@ static int step_tc_init(vaeb_handle* h) {
   const int D = h->D, H = h->H, Z = h->Z;
   const int HP = (H + 63) / 64 * 64, KD = (D + 63) / 64, KH = HP / 64;
   const int NH = (2 * Z + 15) / 16 * 16, NZ = (Z + 1 + 15) / 16 * 16;
-  const int n3 = (D + TR_DEC2 - 1) / TR_DEC2;
+  const int n3 = (D + 31) / 32;
+  const int TR3 = h->cont ? 64 : 32, KV = h->cont ? n3 : KD;
   const int m_h1 = (H + 1 + MP - 1) / MP;
   VAEB_CUDA(cudaFuncSetAttribute(step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   // how many clusters of four fit at once: the grid must be co-resident (grid barriers)
@@ -1368,9 +1451,9 @@ static int step_tc_init(vaeb_handle* h) {
   };
   VAEB_CUDA(alloc((void**)&s.bar, sizeof(unsigned long long)));
   VAEB_CUDA(alloc((void**)&s.m_enc1, (size_t)HP * KD * 64 * 4));
-  VAEB_CUDA(alloc((void**)&s.m_dgrad, (size_t)HP * KD * 64 * 4));
+  VAEB_CUDA(alloc((void**)&s.m_dgrad, (size_t)HP * KV * 64 * 4));
   VAEB_CUDA(alloc((void**)&s.m_heads, (size_t)NH * KH * 64 * 4));
-  VAEB_CUDA(alloc((void**)&s.m_dec2, (size_t)n3 * TR_DEC2 * KH * 64 * 4));
+  VAEB_CUDA(alloc((void**)&s.m_dec2, (size_t)n3 * TR3 * KH * 64 * 4));
   VAEB_CUDA(alloc((void**)&s.m_dz, (size_t)NZ * KH * 64 * 4));
   VAEB_CUDA(alloc((void**)&s.m_dec1, (size_t)HP * 64 * 4));
   VAEB_CUDA(alloc((void**)&s.m_w45k, (size_t)2 * HP * 64 * 4));       // two copies (step parity)
@@ -1380,8 +1463,8 @@ static int step_tc_init(vaeb_handle* h) {
   s.o_he_km = take((size_t)KH * 2 * TBA);
   s.o_he_t = take((size_t)m_h1 * 4 * TBA);
   s.o_hd_t = take((size_t)m_h1 * 4 * TBA);
-  s.o_da2_km = take((size_t)KD * 2 * TBA);
-  s.o_da2_t = take((size_t)n3 * 4 * TR_DEC2 * 128);
+  s.o_da2_km = take((size_t)KV * 2 * TBA);
+  s.o_da2_t = take((size_t)n3 * 4 * TR3 * 128);
   s.o_da1_km = take((size_t)KH * 2 * TBA);
   s.o_da1_t = take((size_t)m_h1 * 4 * TBA);
   s.o_dd_t = take((size_t)4 * NH * 128);
@@ -1400,6 +1483,7 @@ static int step_tc_init(vaeb_handle* h) {
   VAEB_CUDA(alloc((void**)&s.z, (size_t)MP * Z * 4));
   VAEB_CUDA(alloc((void**)&s.partial, (size_t)MP * n3 * 4));
   VAEB_CUDA(alloc((void**)&s.aux, (size_t)MP * 4));
+  VAEB_CUDA(alloc((void**)&s.d_status, 2 * sizeof(int)));
   s.ready = true;
   return VAEB_OK;
 }
@@ -1418,7 +1502,9 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
   p.D = D; p.H = H; p.Z = Z; p.M = rows;
   p.HP = (H + 63) / 64 * 64; p.KD = (D + 63) / 64; p.KH = p.HP / 64;
   p.NH = (2 * Z + 15) / 16 * 16; p.NZ = (Z + 1 + 15) / 16 * 16;
-  p.n_tiles3 = (D + TR_DEC2 - 1) / TR_DEC2;
+  p.n_tiles3 = (D + 31) / 32;
+  p.cont = h->cont ? 1 : 0; p.TR3 = h->cont ? 64 : 32; p.KV = h->cont ? p.n_tiles3 : p.KD;
+  p.oW6 = h->cont ? l.off[l.iW6] : 0; p.ob6 = h->cont ? l.off[l.ib6] : 0;
   p.la = h->cfg.estimator == VAEB_EST_LA ? 1 : 0;
   const bool fb = h->cfg.variant == VAEB_VARIANT_FULLBAYES;
   p.w = fb ? 1.0f / (float)rows : 1.0f;
@@ -1445,6 +1531,8 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
   { const char* e = getenv("VAEB_ST2_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.bar = s.bar; p.bar_base = s.bar_count;
   p.timing = d_timing;
+  p.status = s.d_status;
+  if (h->cont) VAEB_CUDA(cudaMemsetAsync(s.d_status, 0xFF, sizeof(int), h->stream));      // -1
   if (rows != s.rows_init) {
     // batch columns >= rows of every activation mirror must read as zero (they are contraction rows of the weight
     // gradients): clear everything when the minibatch size changes, then restore the constant "ones" features
@@ -1456,10 +1544,11 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
     s.rows_init = rows;
   }
   if (!s.mirrors_valid) {
-    MirrorArgs a{h->d_params, p.oW3, p.oW4, p.oW5, p.oW1, p.oW2, p.ob1, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz,
+    MirrorArgs a{h->d_params, p.oW3, p.oW4, p.oW5, p.oW1, p.oW2, p.ob1, p.oW6, p.cont, p.TR3, p.KV, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz,
                  s.m_dec1, s.m_w45k, D, H, Z, p.HP, p.KD, p.KH, p.NH, p.NZ};
     int64_t most = (int64_t)p.HP * p.KD * 64;
-    most = std::max<int64_t>(most, (int64_t)p.n_tiles3 * TR_DEC2 * p.KH * 64);
+    most = std::max<int64_t>(most, (int64_t)p.n_tiles3 * p.TR3 * p.KH * 64);
+    most = std::max<int64_t>(most, (int64_t)p.HP * p.KV * 64);
     most = std::max<int64_t>(most, (int64_t)p.NH * p.KH * 64);
     build_mirrors_kernel<<<dim3((unsigned)((most + 255) / 256), 7), 256, 0, h->stream>>>(a);
     VAEB_CUDA(cudaGetLastError());
@@ -1474,9 +1563,23 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
   at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
   cfg.attrs = at; cfg.numAttrs = 2;
   VAEB_CUDA(cudaLaunchKernelEx(&cfg, step_tc_kernel, p));
-  s.bar_count += (unsigned long long)s.n_cta * (unsigned long long)N_PHASES * (unsigned long long)n_steps;
   ++h->launches;
-  h->step += (uint32_t)n_steps;
   h->grads_have_prior = false;
+  int done = n_steps;
+  if (h->cont) {
+    // the Gaussian decoder's deltas are unbounded: did a step leave the range of the fp16 operand pairs?
+    int st = -1;
+    VAEB_CUDA(cudaMemcpyAsync(&st, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    VAEB_CUDA(cudaStreamSynchronize(h->stream));
+    if (st >= 0) done = st;
+  }
+  // an aborted launch passed 4 of the grid barriers of step `done`
+  s.bar_count += (unsigned long long)s.n_cta * ((unsigned long long)N_PHASES * (unsigned long long)done + (done < n_steps ? 4ull : 0ull));
+  h->step += (uint32_t)done;
+  if (done < n_steps) {
+    // steps done .. n_steps-1 through the fp32 FFMA kernel (same contract; it invalidates the operand mirrors)
+    VAEB_REQUIRE(fused_step_supported(h, rows), "step_tc: delta overflow and no fp32 single-launch kernel for this configuration");
+    return fused_step_launch(h, d_order ? d_order + done : nullptr, d_xrows, rows, n_steps - done, d_eps, slot0 + done, nullptr);
+  }
   return VAEB_OK;
 }

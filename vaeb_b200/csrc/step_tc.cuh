@@ -29,10 +29,16 @@ struct Params {
   int NH;                               // 2Z rounded up to 16: UMMA N of the latent heads
   int NZ;                               // Z + 1 rounded up to 16: UMMA N of dz and of the W1 weight gradient
   int la;
+  // Gaussian decoder (VAEB.py:257-258): the output layer is [W2 | W6] seen as ONE layer of "virtual" columns -- a tile
+  // of 32 pixels is 64 virtual columns, [32 columns of W2 | the same 32 pixels of W6] -- so the decoder GEMM, its
+  // backward (K = the virtual columns) and the weight gradients keep the Bernoulli code with TR3 = 64 / KV = n_tiles3
+  int cont;
+  int TR3;                              // rows of a dec2 B tile (UMMA N of the output layer): 32, or 64 (Gaussian)
+  int KV;                               // 64-wide k chunks over the virtual output columns (Bernoulli: KD)
   float w, lr, ada_eps, prior, p2;
   float* P;                             // flat fp32 parameters (reference tensor order), updated in place
   float* ada;
-  int64_t oW3, oW4, oW5, oW1, oW2, ob3, ob4, ob5, ob1, ob2;
+  int64_t oW3, oW4, oW5, oW1, oW2, ob3, ob4, ob5, ob1, ob2, oW6, ob6;
   // weight mirrors: [n tile][k chunk][hi, lo][rows x 128 B], K-major SWIZZLE_128B
   uint8_t *m_enc1, *m_heads, *m_dec2, *m_dgrad, *m_dz;
   uint8_t* m_dec1;                      // [W1^T | b1]: tiles of 64 hidden units x one k chunk (k = latent index, k = Z: the bias)
@@ -58,6 +64,10 @@ struct Params {
   float* scalars; float Mg; float bmult;
   int n_steps;
   int dbg;                              // experiment switches (VAEB_ST2_DBG): timing studies only
+  // Gaussian decoder only: its deltas scale with exp(-log variance) and can leave the range of the fp16 operand
+  // pairs.  A step whose da2 / da1 exceed DLIMIT writes its index here (-1 otherwise) and the launch stops BEFORE
+  // that step's first parameter update; the host finishes the remaining steps with the fp32 FFMA kernel.
+  int* status;
   unsigned long long* bar; unsigned long long bar_base;
   long long* timing;                    // nullptr or [n_steps * (N_PHASES + 1) + 128] globaltimer stamps of CTA 0
 };
@@ -80,6 +90,7 @@ struct StepTcState {
         *partial = nullptr, *aux = nullptr;
   int* d_order = nullptr; int order_cap = 0;
   long long* d_timing = nullptr; int timing_cap = 0;
+  int* d_status = nullptr;
 };
 
 // true if this configuration / minibatch is served by the tensor-core step kernel

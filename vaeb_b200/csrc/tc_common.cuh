@@ -174,7 +174,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// the same with fp16 operands (format field 0)
+// the same with fp16 operands (format field 0).  (The two format fields cannot differ: an fp16 x bf16 kind::f16 MMA
+// is an illegal instruction on sm_100a.)
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
