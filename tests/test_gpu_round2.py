@@ -57,7 +57,8 @@ def test_c4_full_vb_at_baseline_size(est, Z):
         got = float(m.update(idx, eps=eps))
         ref = o.update(idx, eps, zeta)
         assert got == pytest.approx(ref, rel=RTOL), (est, Z, step)
-    assert m.launch_count() - l0 == 3            # one single-launch step kernel per update
+    # one single-launch step kernel per update (+ the two one-time operand-mirror launches of the tensor-core kernel)
+    assert m.launch_count() - l0 in (3, 5)
     fv = [p.get_value() for p in m.full_variational_params]
     assert len(fv) == len(o.fvp) == 2 * len(params)
     for i, (a, b, f0, w) in enumerate(zip(fv, o.fvp, fv0, well)):

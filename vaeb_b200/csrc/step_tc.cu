@@ -1164,7 +1164,53 @@ __device__ __forceinline__ void item_bound(Ctx& c, const Params& p, int s) {
   if (threadIdx.x == 0) {
     float b = 0.f;
     for (int w = 0; w < NT / 32; ++w) b += red[w];
-    p.scalars[s] = p.bmult * b / p.Mg;
+    float tp = 0.f;                                  // thetaPrior (full VB), fixed order
+    if (p.fvb) {
+      const float* part = p.tprior_part + (size_t)(s & 1) * gridDim.x;
+      for (int q = 0; q < (int)gridDim.x; ++q) tp += __ldcg(part + q);
+    }
+    p.scalars[s] = (p.bmult * b + tp) / p.Mg;        // VAEB.py:364,412
+  }
+  __syncthreads();
+}
+
+// Full VB, reference-faithful: thetaPrior (VAEB.py:359-363) and the whole (mu, sigma) update in one pass over the flat
+// buffers -- d/dmu = -mu - prior mu, d/dsigma = 1/s - s - prior s (VAEB.py:391-393), Adagrad (:426-444)
+// part / nparts: this CTA's share (the CTAs of cluster 0 run the latent heads meanwhile and contribute 0)
+__device__ __forceinline__ void item_fvb_prior(Ctx& c, const Params& p, const Hyper& hy, int s, int part, int nparts) {
+  float tp = 0.f;
+  for (int64_t g4 = (int64_t)part * NT + threadIdx.x; part >= 0 && 4 * g4 < p.total; g4 += (int64_t)nparts * NT) {
+    float4 m4 = __ldcg(reinterpret_cast<const float4*>(p.vmu) + g4);
+    float4 s4 = __ldcg(reinterpret_cast<const float4*>(p.vsig) + g4);
+    float4 am4 = __ldcg(reinterpret_cast<const float4*>(p.ada_mu) + g4);
+    float4 as4 = __ldcg(reinterpret_cast<const float4*>(p.ada_sig) + g4);
+    float* mm = &m4.x; float* ss = &s4.x; float* am = &am4.x; float* as = &as4.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (4 * g4 + j < p.total) {
+        const float m = mm[j], sg = ss[j];
+        tp += 0.5f * (1.0f + logf(sg * sg) - m * m - sg * sg);
+        const float gm = -m - hy.prior * m, gs = 1.0f / sg - sg - hy.prior * sg;
+        am[j] += gm * gm; as[j] += gs * gs;
+        mm[j] = m + hy.lr * gm / (sqrtf(am[j]) + hy.eps);
+        ss[j] = sg + hy.lr * gs / (sqrtf(as[j]) + hy.eps);
+      }
+    }
+    reinterpret_cast<float4*>(p.vmu)[g4] = m4;
+    reinterpret_cast<float4*>(p.vsig)[g4] = s4;
+    reinterpret_cast<float4*>(p.ada_mu)[g4] = am4;
+    reinterpret_cast<float4*>(p.ada_sig)[g4] = as4;
+  }
+  float* red = reinterpret_cast<float*>(c.sm + SM_MISC + 256);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tp += __shfl_xor_sync(0xffffffffu, tp, o);
+  __syncthreads();
+  if (c.lane == 0) red[c.warp] = tp;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = 0.f;
+    for (int w = 0; w < NT / 32; ++w) b += red[w];
+    p.tprior_part[(size_t)(s & 1) * gridDim.x + blockIdx.x] = b;
   }
   __syncthreads();
 }
@@ -1251,6 +1297,7 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     // ---- P2: latent heads | the minibatch operands of P6 and of the next step's P1 ---------------------------------
     if (c.cid == 0) item_heads(c, p, p.step0 + (uint32_t)s, false);
     else item_xmirrors(p, s + 1 < p.n_steps ? x_of(s + 1) : nullptr, x, (c.cid - 1) * CL + c.rank, (c.ncl - 1) * CL);
+    if (p.fvb) item_fvb_prior(c, p, hy, s, c.cid == 0 ? -1 : (c.cid - 1) * CL + c.rank, (c.ncl - 1) * CL);   // nothing downstream reads (mu, sigma)
     ST2_TRACE(c, 82);
     ARRIVE(1);
     grid_barrier(p.bar, target += G);
@@ -1265,6 +1312,16 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     grid_barrier(p.bar, target += G);
     if (tm) tm[3] = gtime();
     ST2_TRACE(c, 93);
+    if (p.fvb) {
+      // reference-faithful full VB: the bound is all the layers are needed for.  One CTA (rotating) sums it; the
+      // partials it reads are overwritten two barriers into the next step at the earliest.
+      if ((int)blockIdx.x == (c.ncl > n1 ? G - 1 - (s & 3) : s % G)) item_bound(c, p, s);   // a CTA without an enc1 item
+      if (s + 1 < p.n_steps && has_p1 && threadIdx.x == 0 && kdn > 0) {
+        tc::mbar_expect_tx(c.x_bar, (uint32_t)(kdn * 2 * TBA));
+        bulk_g2s(c.sm + SM_A, p.x_km + (size_t)kd0 * 2 * TBA, (uint32_t)(kdn * 2 * TBA), c.x_bar);
+      }
+      continue;
+    }
     // ---- P4: back through the decoder output layer ---------------------------------------------------------------
     for (int it = c.cid; it < n1; it += c.ncl) item_dgrad(c, p, it, it + c.ncl < n1, s);
     ST2_TRACE(c, 84);
@@ -1410,7 +1467,7 @@ __global__ void __launch_bounds__(128) init_ones_kernel(OnesArgs a) {
 bool step_tc_supported(const vaeb_handle* h, int rows) {
   const int e = h->cfg.estimator;
   if (h->steptc.unavailable || h->steptc_off) return false;
-  return (e == VAEB_EST_LB || e == VAEB_EST_LA) && h->L == 1 && h->world == 1 &&
+  return (e == VAEB_EST_LB || e == VAEB_EST_LA || e == VAEB_EST_FVB) && h->L == 1 && h->world == 1 &&
          h->cfg.precision != VAEB_PREC_BF16 && h->optimizer == VAEB_OPT_ADAGRAD && rows >= 1 && rows <= st2::MP &&
          (h->D % 8) == 0 && (h->H % 4) == 0 && h->D >= 64 && h->H >= 64 && h->D <= 1024 && h->H <= 512 && h->Z >= 1 &&
          h->Z <= 20 && (!h->cont || fused_step_supported(h, rows));   // Gaussian decoder: the fp32 kernel takes over a step
@@ -1418,7 +1475,7 @@ bool step_tc_supported(const vaeb_handle* h, int rows) {
 
 void step_tc_free(StepTcState& s) {
   void* ptrs[] = {s.bar, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz, s.m_dec1, s.act, s.he, s.hd, s.mu, s.ls,
-                  s.eps, s.z, s.m_w45k, s.partial, s.aux, s.d_order, s.d_timing, s.d_status};
+                  s.eps, s.z, s.m_w45k, s.partial, s.aux, s.d_order, s.d_timing, s.d_status, s.tprior_part};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   s = StepTcState();
@@ -1484,6 +1541,7 @@ static int step_tc_init(vaeb_handle* h) {
   VAEB_CUDA(alloc((void**)&s.partial, (size_t)MP * n3 * 4));
   VAEB_CUDA(alloc((void**)&s.aux, (size_t)MP * 4));
   VAEB_CUDA(alloc((void**)&s.d_status, 2 * sizeof(int)));
+  VAEB_CUDA(alloc((void**)&s.tprior_part, (size_t)2 * s.n_cta * sizeof(float)));
   s.ready = true;
   return VAEB_OK;
 }
@@ -1532,7 +1590,15 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
   p.bar = s.bar; p.bar_base = s.bar_count;
   p.timing = d_timing;
   p.status = s.d_status;
-  if (h->cont) VAEB_CUDA(cudaMemsetAsync(s.d_status, 0xFF, sizeof(int), h->stream));      // -1
+  p.fvb = h->cfg.estimator == VAEB_EST_FVB ? 1 : 0;
+  if (p.fvb) {
+    // SGVB = x.shape[0] * (sum logp + sum KL) + thetaPrior, update returns SGVB / M (VAEB.py:364,412)
+    p.bmult = (float)rows; p.prior = h->cfg.prior_scale; p.p2 = 0.f;
+    p.vmu = h->d_vmu; p.vsig = h->d_vsig; p.ada_mu = h->d_ada_mu; p.ada_sig = h->d_ada_sig; p.total = l.total;
+    p.tprior_part = s.tprior_part;
+  }
+  const bool can_abort = h->cont && !p.fvb;               // forward-only full VB writes no deltas
+  if (can_abort) VAEB_CUDA(cudaMemsetAsync(s.d_status, 0xFF, sizeof(int), h->stream));      // -1
   if (rows != s.rows_init) {
     // batch columns >= rows of every activation mirror must read as zero (they are contraction rows of the weight
     // gradients): clear everything when the minibatch size changes, then restore the constant "ones" features
@@ -1566,7 +1632,7 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
   ++h->launches;
   h->grads_have_prior = false;
   int done = n_steps;
-  if (h->cont) {
+  if (can_abort) {
     // the Gaussian decoder's deltas are unbounded: did a step leave the range of the fp16 operand pairs?
     int st = -1;
     VAEB_CUDA(cudaMemcpyAsync(&st, s.d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -1574,7 +1640,7 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
     if (st >= 0) done = st;
   }
   // an aborted launch passed 4 of the grid barriers of step `done`
-  s.bar_count += (unsigned long long)s.n_cta * ((unsigned long long)N_PHASES * (unsigned long long)done + (done < n_steps ? 4ull : 0ull));
+  s.bar_count += (unsigned long long)s.n_cta * ((unsigned long long)(p.fvb ? 3 : N_PHASES) * (unsigned long long)done + (done < n_steps ? 4ull : 0ull));
   h->step += (uint32_t)done;
   if (done < n_steps) {
     // steps done .. n_steps-1 through the fp32 FFMA kernel (same contract; it invalidates the operand mirrors)

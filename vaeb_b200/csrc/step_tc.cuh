@@ -68,6 +68,11 @@ struct Params {
   // pairs.  A step whose da2 / da1 exceed DLIMIT writes its index here (-1 otherwise) and the launch stops BEFORE
   // that step's first parameter update; the host finishes the remaining steps with the fp32 FFMA kernel.
   int* status;
+  // Full VB as the reference runs it (getFVBL, VAEB.py:349-367: the weights are never sampled): an update is the
+  // forward phases P1-P3 on the frozen MAP parameters, thetaPrior, and the prior-only Adagrad step on (mu, sigma).
+  int fvb;
+  float *vmu, *vsig, *ada_mu, *ada_sig; int64_t total;
+  float* tprior_part;                   // [2][gridDim.x] per-CTA partial sums of thetaPrior (step parity)
   unsigned long long* bar; unsigned long long bar_base;
   long long* timing;                    // nullptr or [n_steps * (N_PHASES + 1) + 128] globaltimer stamps of CTA 0
 };
@@ -91,6 +96,7 @@ struct StepTcState {
   int* d_order = nullptr; int order_cap = 0;
   long long* d_timing = nullptr; int timing_cap = 0;
   int* d_status = nullptr;
+  float* tprior_part = nullptr;
 };
 
 // true if this configuration / minibatch is served by the tensor-core step kernel
