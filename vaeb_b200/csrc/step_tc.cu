@@ -1627,7 +1627,10 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
-  cfg.attrs = at; cfg.numAttrs = 2;
+  // (ncu cannot launch a cluster kernel with the cooperative attribute: VAEB_ST2_NOCOOP=1 drops it for profiling runs;
+  // the grid is sized to be co-resident either way)
+  static const bool no_coop = getenv("VAEB_ST2_NOCOOP") != nullptr;
+  cfg.attrs = at; cfg.numAttrs = no_coop ? 1 : 2;
   VAEB_CUDA(cudaLaunchKernelEx(&cfg, step_tc_kernel, p));
   ++h->launches;
   h->grads_have_prior = false;
