@@ -57,13 +57,14 @@ def test_c4_full_vb_at_baseline_size(est, Z):
         got = float(m.update(idx, eps=eps))
         ref = o.update(idx, eps, zeta)
         assert got == pytest.approx(ref, rel=RTOL), (est, Z, step)
-    # one single-launch step kernel per update (+ the two one-time operand-mirror launches of the tensor-core kernel)
-    assert m.launch_count() - l0 in (3, 5)
+    # one single-launch step kernel per update (+ the one-time operand-mirror launches of the tensor-core kernel)
+    assert m.launch_count() - l0 in (3, 5, 6)         # (sampled weights: + the first draw of theta)
     fv = [p.get_value() for p in m.full_variational_params]
     assert len(fv) == len(o.fvp) == 2 * len(params)
     for i, (a, b, f0, w) in enumerate(zip(fv, o.fvp, fv0, well)):
         assert w.mean() > 0.25, "mask %d keeps %.3f" % (i, w.mean())   # the well-conditioned subset is not vacuous
-        np.testing.assert_allclose((a - f0)[w], (b - f0)[w], rtol=2e-3, atol=1e-7, err_msg="fvp %d step" % i)
+        # atol: three Adagrad steps of up to +-lr each can cancel to a net move far below lr (2e-6 = 0.02 % of lr)
+        np.testing.assert_allclose((a - f0)[w], (b - f0)[w], rtol=2e-3, atol=2e-6, err_msg="fvp %d step" % i)
         assert_close_tensor(a, b, 1e-2, floor=1.0, name="fvp %d" % i)   # nothing off by more than 1 % of the scale
     if est == "FVB":
         for a, b in zip(m.get_params(), params):

@@ -546,6 +546,8 @@ float* flat_by_which(vaeb_handle* h, int which) {
     case 7: return h->d_gmu;
     case 8: return h->d_gsig;
     case 9: return h->d_ada2;
+    case 10: return h->d_theta;     // sampled full VB: theta of the next step (debug / tests)
+    case 11: return h->d_zeta;
     default: return nullptr;
   }
 }

@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "launchers.h"
 #include "philox.cuh"
 #include "step_tc.cuh"
 #include "tc_common.cuh"
@@ -60,6 +61,8 @@ struct Ctx {
   uint32_t mma_phase, op_phase, x_phase, rs_phase;
   int rank, cid, ncl, warp, lane;
   long long* trace; int tn;            // optional sub-phase stamps (CTA 0, thread 0, last step of a profiling launch)
+  float tp;                            // sampled full VB: this thread's share of thetaPrior of the running step
+  uint32_t step;                       // global index of the running step (Philox key of the weight noise)
 };
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------------
@@ -865,6 +868,23 @@ __device__ __forceinline__ void wgrad_epilogue(Ctx& c, int N, F fn) {
 //      3.6 us per tile measured), Adagrad, the new values go back into the tile;
 //   C  thread = row again: `mir(row, col0, nv[8])` writes the fp16 mirrors (their k index runs along the rows).
 // off(row, col) = flat offset of the parameter behind accumulator element (row, col), or -1.
+// Sampled full VB: one parameter.  g = d(data term)/d theta; (m, sg) = (mu, sigma); returns theta' of the NEXT step.
+// VAEB.py:359-363 (thetaPrior), :391-393 (its gradient), :127-129 (the reparameterisation), :426-444 (Adagrad)
+__device__ __forceinline__ float fvb_element(Ctx& c, const Params& p, const Hyper& hy, long long o, float g, float m, float sg,
+                                             float am0, float as0, float zt) {
+  c.tp += 0.5f * (1.0f + logf(sg * sg) - m * m - sg * sg);
+  const float sn = (sg > 0.f) ? 1.f : ((sg < 0.f) ? -1.f : 0.f);
+  const float gm = g - m - hy.prior * m;
+  const float gs = 1.0f / sg - sg - hy.prior * sg + g * zt * sn;
+  const float am = am0 + gm * gm, as = as0 + gs * gs;
+  const float m1 = m + hy.lr * gm / (sqrtf(am) + hy.eps);
+  const float s1 = sg + hy.lr * gs / (sqrtf(as) + hy.eps);
+  p.vmu[o] = m1; p.vsig[o] = s1; p.ada_mu[o] = am; p.ada_sig[o] = as;
+  const float z1 = philox_normal_only(p.seed, VAEB_STREAM_ZETA, c.step + 1u, 0u, (uint64_t)o);
+  p.zeta[o] = z1;
+  return m1 + fabsf(s1) * z1;
+}
+
 template <int N>
 struct WgPre {                                                     // parameters / accumulators of phase B, loaded early
   static constexpr int RPP = 32 / N, NP = 8 / RPP;                 // rows per warp pass; passes (a warp owns 8 rows)
@@ -878,8 +898,8 @@ __device__ __forceinline__ void wgrad_prefetch(Ctx& c, const Params& p, OffF off
   for (int r = 0; r < WgPre<N>::NP; ++r) {
     const int row = c.warp * 8 + r * WgPre<N>::RPP + rsub;
     w.o[r] = off(row, col);
-    w.pv[r] = w.o[r] >= 0 ? __ldcg(p.P + w.o[r]) : 0.f;
-    w.av[r] = w.o[r] >= 0 ? __ldcg(p.ada + w.o[r]) : 0.f;
+    w.pv[r] = w.o[r] >= 0 ? __ldcg((p.fvb == 2 ? p.vmu : p.P) + w.o[r]) : 0.f;       // sampled full VB: (mu, sigma)
+    w.av[r] = w.o[r] >= 0 ? __ldcg((p.fvb == 2 ? p.vsig : p.ada) + w.o[r]) : 0.f;
   }
 }
 template <int N, class MirF>
@@ -896,7 +916,26 @@ __device__ __forceinline__ void wgrad_epilogue_coalesced(Ctx& c, const Params& p
   }
   tc::tc_fence_before();
   __syncthreads();
-  {
+  if (p.fvb == 2) {
+    const int col = c.lane % N, rsub = c.lane / N;
+    float am0[WgPre<N>::NP], as0[WgPre<N>::NP], zt[WgPre<N>::NP];
+#pragma unroll
+    for (int r = 0; r < WgPre<N>::NP; ++r) {                       // every load before the first store
+      const bool ok = w.o[r] >= 0;
+      am0[r] = ok ? __ldcg(p.ada_mu + w.o[r]) : 0.f;
+      as0[r] = ok ? __ldcg(p.ada_sig + w.o[r]) : 0.f;
+      zt[r] = ok ? __ldcg(p.zeta + w.o[r]) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < WgPre<N>::NP; ++r) {
+      const int row = c.warp * 8 + r * WgPre<N>::RPP + rsub;
+      if (w.o[r] >= 0) {
+        const float nv = fvb_element(c, p, hy, w.o[r], gt[row * GP + col] * hy.w, w.pv[r], w.av[r], am0[r], as0[r], zt[r]);
+        p.P[w.o[r]] = nv;
+        gt[row * GP + col] = nv;
+      }
+    }
+  } else {
     const int col = c.lane % N, rsub = c.lane / N;
 #pragma unroll
     for (int r = 0; r < WgPre<N>::NP; ++r) {
@@ -1070,14 +1109,35 @@ __device__ __forceinline__ void item_wg1(Ctx& c, const Params& p, const Hyper& h
     const int q = col0 + e;
     ok[e] = mine && q <= Z;
     off[e] = q < Z ? (size_t)p.oW1 + (size_t)q * H + i : (size_t)p.ob1 + i;
-    pv[e] = ok[e] ? __ldcg(p.P + off[e]) : 0.f;
-    av[e] = ok[e] ? __ldcg(p.ada + off[e]) : 0.f;
+    pv[e] = ok[e] ? __ldcg((p.fvb == 2 ? p.vmu : p.P) + off[e]) : 0.f;
+    av[e] = ok[e] ? __ldcg((p.fvb == 2 ? p.vsig : p.ada) + off[e]) : 0.f;
   }
   mma_run(c, 2, (p.M + 15) / 16, TB, N, true, 0u, 1, 0);
   if (u < N / 8) {
     float v[8], nv[8];
     acc_ld8(c, qq, (uint32_t)col0, v, true);
-    if (mine) {
+    if (mine && p.fvb == 2) {
+      float am0[8], as0[8], zt[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        am0[e] = ok[e] ? __ldcg(p.ada_mu + off[e]) : 0.f;
+        as0[e] = ok[e] ? __ldcg(p.ada_sig + off[e]) : 0.f;
+        zt[e] = ok[e] ? __ldcg(p.zeta + off[e]) : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        nv[e] = 0.f;
+        if (ok[e]) {
+          nv[e] = fvb_element(c, p, hy, (long long)off[e], v[e] * hy.w, pv[e], av[e], am0[e], as0[e], zt[e]);
+          p.P[off[e]] = nv[e];
+          if (col0 + e < Z) mirror_put(p.m_dz, N, p.KH, 0, col0 + e, i, nv[e]);
+        }
+      }
+      constexpr int T1 = 64 * 128;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) nv[e] *= WSCALE;
+      put_unit<true>(p.m_dec1 + (size_t)(i >> 6) * 2 * T1 + unit_off(i & 63, col0 >> 3), T1, nv);
+    } else if (mine) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         nv[e] = 0.f;
@@ -1174,6 +1234,22 @@ __device__ __forceinline__ void item_bound(Ctx& c, const Params& p, int s) {
   __syncthreads();
 }
 
+// this CTA's partial sum of thetaPrior (fixed order) into the step's half of tprior_part
+__device__ __forceinline__ void store_tprior(Ctx& c, const Params& p, int s, float tp) {
+  float* red = reinterpret_cast<float*>(c.sm + SM_MISC + 256);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tp += __shfl_xor_sync(0xffffffffu, tp, o);
+  __syncthreads();
+  if (c.lane == 0) red[c.warp] = tp;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = 0.f;
+    for (int w = 0; w < NT / 32; ++w) b += red[w];
+    p.tprior_part[(size_t)(s & 1) * gridDim.x + blockIdx.x] = b;
+  }
+  __syncthreads();
+}
+
 // Full VB, reference-faithful: thetaPrior (VAEB.py:359-363) and the whole (mu, sigma) update in one pass over the flat
 // buffers -- d/dmu = -mu - prior mu, d/dsigma = 1/s - s - prior s (VAEB.py:391-393), Adagrad (:426-444)
 // part / nparts: this CTA's share (the CTAs of cluster 0 run the latent heads meanwhile and contribute 0)
@@ -1201,18 +1277,7 @@ __device__ __forceinline__ void item_fvb_prior(Ctx& c, const Params& p, const Hy
     reinterpret_cast<float4*>(p.ada_mu)[g4] = am4;
     reinterpret_cast<float4*>(p.ada_sig)[g4] = as4;
   }
-  float* red = reinterpret_cast<float*>(c.sm + SM_MISC + 256);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tp += __shfl_xor_sync(0xffffffffu, tp, o);
-  __syncthreads();
-  if (c.lane == 0) red[c.warp] = tp;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float b = 0.f;
-    for (int w = 0; w < NT / 32; ++w) b += red[w];
-    p.tprior_part[(size_t)(s & 1) * gridDim.x + blockIdx.x] = b;
-  }
-  __syncthreads();
+  store_tprior(c, p, s, tp);
 }
 
 // =================================================================================================================
@@ -1264,6 +1329,7 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
   const bool has_p1 = c.cid < n1;
   if (has_p1) stage_x_rows(c.sm, x_of(0), p.D, p.M, kd0, kdn);
   const int n_spare = c.ncl - n3;                   // clusters without a dec2 item: they publish h_d in P3
+  int last_done = -1;                               // last step whose updates were applied (a Gaussian launch may stop early)
 
 #define ARRIVE(ph)                                                                                           \
   do {                                                                                                       \
@@ -1273,6 +1339,10 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
   for (int s = 0; s < p.n_steps; ++s) {
     const float* x = x_of(s);
     const int par = (int)((p.step0 + (uint32_t)s) & 1u);        // which copy of the k-major [W4|W5] mirror this step reads
+    c.step = p.step0 + (uint32_t)s; c.tp = 0.f;
+    // sampled full VB: the bound of the previous step needs the thetaPrior sums of ITS update epilogues (P5, P6): it is
+    // summed here, by a CTA that has no enc1 item, before P2 / P3 overwrite the row partials
+    if (p.fvb == 2 && s > 0 && (int)blockIdx.x == G - 1) item_bound(c, p, s - 1);
     long long* tm = rec ? p.timing + (size_t)s * (N_PHASES + 1) : nullptr;
     if (tm) tm[0] = gtime();
     if (p.timing && blockIdx.x == 0 && s == p.n_steps - 1) c.trace = p.timing + (size_t)p.n_steps * (N_PHASES + 1);
@@ -1297,7 +1367,7 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     // ---- P2: latent heads | the minibatch operands of P6 and of the next step's P1 ---------------------------------
     if (c.cid == 0) item_heads(c, p, p.step0 + (uint32_t)s, false);
     else item_xmirrors(p, s + 1 < p.n_steps ? x_of(s + 1) : nullptr, x, (c.cid - 1) * CL + c.rank, (c.ncl - 1) * CL);
-    if (p.fvb) item_fvb_prior(c, p, hy, s, c.cid == 0 ? -1 : (c.cid - 1) * CL + c.rank, (c.ncl - 1) * CL);   // nothing downstream reads (mu, sigma)
+    if (p.fvb == 1) item_fvb_prior(c, p, hy, s, c.cid == 0 ? -1 : (c.cid - 1) * CL + c.rank, (c.ncl - 1) * CL);   // nothing downstream reads (mu, sigma)
     ST2_TRACE(c, 82);
     ARRIVE(1);
     grid_barrier(p.bar, target += G);
@@ -1312,7 +1382,7 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     grid_barrier(p.bar, target += G);
     if (tm) tm[3] = gtime();
     ST2_TRACE(c, 93);
-    if (p.fvb) {
+    if (p.fvb == 1) {
       // reference-faithful full VB: the bound is all the layers are needed for.  One CTA (rotating) sums it; the
       // partials it reads are overwritten two barriers into the next step at the earliest.
       if ((int)blockIdx.x == (c.ncl > n1 ? G - 1 - (s & 3) : s % G)) item_bound(c, p, s);   // a CTA without an enc1 item
@@ -1340,7 +1410,7 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
         if (it == 0) { item_dz(c, p, false); continue; }
         const int i = (it - 1) * CL + c.rank;
         if (i < n2) item_wg2(c, p, hy, i / (n3 * nw), (i / nw) % n3, i % nw);
-        else if (i == n2) item_bound(c, p, s);
+        else if (i == n2 && p.fvb != 2) item_bound(c, p, s);
       }
     }
     ST2_TRACE(c, 85);
@@ -1358,6 +1428,7 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
         else if (i < n3w + m_h + n45) item_wg45(c, p, hy, (i - n3w - m_h) / n45t, (i - n3w - m_h) % n45t, par);
       }
     }
+    if (p.fvb == 2) store_tprior(c, p, s, c.tp);
     // the A tile of this CTA's first enc1 item of the next step (x_km was written in P2): in flight across the barrier
     if (s + 1 < p.n_steps && has_p1 && threadIdx.x == 0 && kdn > 0) {
       tc::mbar_expect_tx(c.x_bar, (uint32_t)(kdn * 2 * TBA));
@@ -1368,7 +1439,9 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     grid_barrier(p.bar, target += G);
     if (tm) tm[6] = gtime();
     ST2_TRACE(c, 96);
+    last_done = s;
   }
+  if (p.fvb == 2 && last_done >= 0 && (int)blockIdx.x == G - 1) item_bound(c, p, last_done);
   tc::tc_fence_before();
   __syncthreads();
   cluster_sync();                                   // no CTA leaves while a peer may still write its shared memory
@@ -1467,7 +1540,7 @@ __global__ void __launch_bounds__(128) init_ones_kernel(OnesArgs a) {
 bool step_tc_supported(const vaeb_handle* h, int rows) {
   const int e = h->cfg.estimator;
   if (h->steptc.unavailable || h->steptc_off) return false;
-  return (e == VAEB_EST_LB || e == VAEB_EST_LA || e == VAEB_EST_FVB) && h->L == 1 && h->world == 1 &&
+  return (e == VAEB_EST_LB || e == VAEB_EST_LA || e == VAEB_EST_FVB || e == VAEB_EST_FVB_SAMPLED) && h->L == 1 && h->world == 1 &&
          h->cfg.precision != VAEB_PREC_BF16 && h->optimizer == VAEB_OPT_ADAGRAD && rows >= 1 && rows <= st2::MP &&
          (h->D % 8) == 0 && (h->H % 4) == 0 && h->D >= 64 && h->H >= 64 && h->D <= 1024 && h->H <= 512 && h->Z >= 1 &&
          h->Z <= 20 && (!h->cont || fused_step_supported(h, rows));   // Gaussian decoder: the fp32 kernel takes over a step
@@ -1590,14 +1663,23 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
   p.bar = s.bar; p.bar_base = s.bar_count;
   p.timing = d_timing;
   p.status = s.d_status;
-  p.fvb = h->cfg.estimator == VAEB_EST_FVB ? 1 : 0;
+  p.fvb = h->cfg.estimator == VAEB_EST_FVB ? 1 : (h->cfg.estimator == VAEB_EST_FVB_SAMPLED ? 2 : 0);
+  if (p.fvb == 2) {
+    // the layers run on the sampled theta; the data term of the gradient carries the factor M of VAEB.py:364
+    p.P = h->d_theta; p.zeta = h->d_zeta; p.w = (float)rows;
+    if (!s.mirrors_valid || s.theta_step != (long long)h->step) {
+      VAEB_CUDA(launch_sample_theta(h->stream, &h->launches, h->d_vmu, h->d_vsig, nullptr, h->cfg.seed, h->step, l.total,
+                                    h->d_theta, h->d_zeta));
+      s.mirrors_valid = false;
+    }
+  }
   if (p.fvb) {
     // SGVB = x.shape[0] * (sum logp + sum KL) + thetaPrior, update returns SGVB / M (VAEB.py:364,412)
     p.bmult = (float)rows; p.prior = h->cfg.prior_scale; p.p2 = 0.f;
     p.vmu = h->d_vmu; p.vsig = h->d_vsig; p.ada_mu = h->d_ada_mu; p.ada_sig = h->d_ada_sig; p.total = l.total;
     p.tprior_part = s.tprior_part;
   }
-  const bool can_abort = h->cont && !p.fvb;               // forward-only full VB writes no deltas
+  const bool can_abort = h->cont && p.fvb != 1;           // forward-only full VB writes no deltas
   if (can_abort) VAEB_CUDA(cudaMemsetAsync(s.d_status, 0xFF, sizeof(int), h->stream));      // -1
   if (rows != s.rows_init) {
     // batch columns >= rows of every activation mirror must read as zero (they are contraction rows of the weight
@@ -1610,7 +1692,7 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
     s.rows_init = rows;
   }
   if (!s.mirrors_valid) {
-    MirrorArgs a{h->d_params, p.oW3, p.oW4, p.oW5, p.oW1, p.oW2, p.ob1, p.oW6, p.cont, p.TR3, p.KV, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz,
+    MirrorArgs a{p.P, p.oW3, p.oW4, p.oW5, p.oW1, p.oW2, p.ob1, p.oW6, p.cont, p.TR3, p.KV, s.m_enc1, s.m_heads, s.m_dec2, s.m_dgrad, s.m_dz,
                  s.m_dec1, s.m_w45k, D, H, Z, p.HP, p.KD, p.KH, p.NH, p.NZ};
     int64_t most = (int64_t)p.HP * p.KD * 64;
     most = std::max<int64_t>(most, (int64_t)p.n_tiles3 * p.TR3 * p.KH * 64);
@@ -1643,8 +1725,9 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
     if (st >= 0) done = st;
   }
   // an aborted launch passed 4 of the grid barriers of step `done`
-  s.bar_count += (unsigned long long)s.n_cta * ((unsigned long long)(p.fvb ? 3 : N_PHASES) * (unsigned long long)done + (done < n_steps ? 4ull : 0ull));
+  s.bar_count += (unsigned long long)s.n_cta * ((unsigned long long)(p.fvb == 1 ? 3 : N_PHASES) * (unsigned long long)done + (done < n_steps ? 4ull : 0ull));
   h->step += (uint32_t)done;
+  s.theta_step = (long long)h->step;
   if (done < n_steps) {
     // steps done .. n_steps-1 through the fp32 FFMA kernel (same contract; it invalidates the operand mirrors)
     VAEB_REQUIRE(fused_step_supported(h, rows), "step_tc: delta overflow and no fp32 single-launch kernel for this configuration");

@@ -70,8 +70,14 @@ struct Params {
   int* status;
   // Full VB as the reference runs it (getFVBL, VAEB.py:349-367: the weights are never sampled): an update is the
   // forward phases P1-P3 on the frozen MAP parameters, thetaPrior, and the prior-only Adagrad step on (mu, sigma).
+  // fvb = 2: the sampled-weights estimator (VAEB.py:127-129 live inside getFVBL).  P is then the buffer of the sampled
+  // theta = mu + |sigma| zeta: the Adagrad epilogue of every weight-gradient tile updates (mu, sigma) with their own
+  // accumulators, DRAWS the next step's zeta there (Philox, keyed by the step and the flat parameter index), and
+  // writes theta' = mu' + |sigma'| zeta' both as fp32 (biases, rebuilds) and into the fp16 operand mirrors -- the
+  // weights are sampled where the next step's GEMM operands are produced; no pass over the parameters.
   int fvb;
   float *vmu, *vsig, *ada_mu, *ada_sig; int64_t total;
+  float* zeta;                          // the draws of the current step (written by the previous step's epilogues)
   float* tprior_part;                   // [2][gridDim.x] per-CTA partial sums of thetaPrior (step parity)
   unsigned long long* bar; unsigned long long bar_base;
   long long* timing;                    // nullptr or [n_steps * (N_PHASES + 1) + 128] globaltimer stamps of CTA 0
@@ -97,6 +103,7 @@ struct StepTcState {
   long long* d_timing = nullptr; int timing_cap = 0;
   int* d_status = nullptr;
   float* tprior_part = nullptr;
+  long long theta_step = -1;            // sampled full VB: the step the theta buffer / mirrors were drawn for
 };
 
 // true if this configuration / minibatch is served by the tensor-core step kernel
