@@ -868,21 +868,49 @@ __device__ __forceinline__ void wgrad_epilogue(Ctx& c, int N, F fn) {
 //      3.6 us per tile measured), Adagrad, the new values go back into the tile;
 //   C  thread = row again: `mir(row, col0, nv[8])` writes the fp16 mirrors (their k index runs along the rows).
 // off(row, col) = flat offset of the parameter behind accumulator element (row, col), or -1.
-// Sampled full VB: one parameter.  g = d(data term)/d theta; (m, sg) = (mu, sigma); returns theta' of the NEXT step.
-// VAEB.py:359-363 (thetaPrior), :391-393 (its gradient), :127-129 (the reparameterisation), :426-444 (Adagrad)
-__device__ __forceinline__ float fvb_element(Ctx& c, const Params& p, const Hyper& hy, long long o, float g, float m, float sg,
-                                             float am0, float as0, float zt) {
-  c.tp += 0.5f * (1.0f + logf(sg * sg) - m * m - sg * sg);
+// ---- sampled full VB (VAEB.py:127-129 live inside getFVBL) ------------------------------------------------------------
+// The update epilogues are issue bound (per parameter: thetaPrior, two Adagrad rules, a Philox draw), so they use the
+// MUFU forms: relative error ~2^-22 each, far inside the parity tier; zeta' is stored and the stored value is what
+// both theta' and the next step's d/dsigma use, so nothing has to reproduce it bit for bit.
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// the four N(0,1) draws of Philox group g (flat parameters 4g .. 4g+3): philox_normal4 with MUFU log / sqrt / sin / cos
+__device__ __forceinline__ void zeta_group(const Params& p, uint32_t step, uint64_t g, float n[4]) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)g, ((uint32_t)(g >> 32) & 0x00FFFFFFu) | ((VAEB_STREAM_ZETA & 0xFFu) << 24), 0u, step,
+                (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r);
+  const float u0 = ((float)(r[0] >> 8) + 0.5f) * 5.9604644775390625e-8f, u1 = ((float)(r[1] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+  const float u2 = ((float)(r[2] >> 8) + 0.5f) * 5.9604644775390625e-8f, u3 = ((float)(r[3] >> 8) + 0.5f) * 5.9604644775390625e-8f;
+  const float rad0 = fast_sqrt(-1.3862943611198906f * fast_lg2(u0)), rad1 = fast_sqrt(-1.3862943611198906f * fast_lg2(u2));
+  // angles in (-pi, pi): the same point of the circle as 2 pi u, where sin.approx / cos.approx are most accurate
+  const float a0 = 6.283185307179586f * (u1 - (u1 >= 0.5f ? 1.0f : 0.0f)), a1 = 6.283185307179586f * (u3 - (u3 >= 0.5f ? 1.0f : 0.0f));
+  n[0] = rad0 * __cosf(a0); n[1] = rad0 * __sinf(a0); n[2] = rad1 * __cosf(a1); n[3] = rad1 * __sinf(a1);
+}
+// One parameter.  g = d(data term)/d theta, (m, sg) = (mu, sigma), zt = this step's zeta, z1 = the next step's.
+// VAEB.py:359-363 (thetaPrior), :391-393 (its gradient), :426-444 (Adagrad).  Returns theta' of the next step.
+__device__ __forceinline__ float fvb_math(Ctx& c, const Hyper& hy, float g, float m, float sg, float am0, float as0, float zt,
+                                         float z1, float& m1, float& s1, float& am, float& as) {
+  c.tp += 0.5f * (1.0f + 0.6931471805599453f * fast_lg2(sg * sg) - m * m - sg * sg);
   const float sn = (sg > 0.f) ? 1.f : ((sg < 0.f) ? -1.f : 0.f);
   const float gm = g - m - hy.prior * m;
-  const float gs = 1.0f / sg - sg - hy.prior * sg + g * zt * sn;
-  const float am = am0 + gm * gm, as = as0 + gs * gs;
-  const float m1 = m + hy.lr * gm / (sqrtf(am) + hy.eps);
-  const float s1 = sg + hy.lr * gs / (sqrtf(as) + hy.eps);
-  p.vmu[o] = m1; p.vsig[o] = s1; p.ada_mu[o] = am; p.ada_sig[o] = as;
-  const float z1 = philox_normal_only(p.seed, VAEB_STREAM_ZETA, c.step + 1u, 0u, (uint64_t)o);
-  p.zeta[o] = z1;
+  const float gs = fast_rcp(sg) - sg - hy.prior * sg + g * zt * sn;
+  am = am0 + gm * gm; as = as0 + gs * gs;
+  m1 = m + hy.lr * gm * fast_rcp(fast_sqrt(am) + hy.eps);
+  s1 = sg + hy.lr * gs * fast_rcp(fast_sqrt(as) + hy.eps);
   return m1 + fabsf(s1) * z1;
+}
+// scalar form (the thin tensors, whose rows are not 16-byte aligned runs): one Philox group per parameter
+__device__ __forceinline__ float fvb_element(Ctx& c, const Params& p, const Hyper& hy, long long o, float g, float m, float sg,
+                                             float am0, float as0, float zt) {
+  float zn[4];
+  zeta_group(p, c.step + 1u, (uint64_t)o >> 2, zn);
+  const uint32_t q = (uint32_t)o & 3u;
+  const float z1 = q == 0 ? zn[0] : (q == 1 ? zn[1] : (q == 2 ? zn[2] : zn[3]));
+  float m1, s1, am, as;
+  const float th = fvb_math(c, hy, g, m, sg, am0, as0, zt, z1, m1, s1, am, as);
+  p.vmu[o] = m1; p.vsig[o] = s1; p.ada_mu[o] = am; p.ada_sig[o] = as; p.zeta[o] = z1;
+  return th;
 }
 
 template <int N>
@@ -891,19 +919,38 @@ struct WgPre {                                                     // parameters
   long long o[NP]; float pv[NP], av[NP];
 };
 // issue the phase-B loads (they do not depend on the GEMM): called BEFORE waiting for the operands and the MMAs
-template <int N, class OffF>
-__device__ __forceinline__ void wgrad_prefetch(Ctx& c, const Params& p, OffF off, WgPre<N>& w) {
+// vec4 (sampled full VB, N = 32, rows of the tensor are 16-byte aligned runs): a thread owns FOUR consecutive
+// parameters = one Philox group, 16-byte accesses; pv / av then hold (mu, sigma) of its two groups, o their offsets.
+// SV: the sampled-weights full-VB instantiation of the kernel (its epilogues need ~30 more registers: kept out of the
+// code of the plain step)
+template <int N, bool SV, class OffF>
+__device__ __forceinline__ void wgrad_prefetch(Ctx& c, const Params& p, OffF off, WgPre<N>& w, bool vec4 = false) {
+  if (SV && N == 32 && vec4) {
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+      const int row = c.warp * 8 + ps * 4 + (c.lane >> 3), col = (c.lane & 7) * 4;
+      const long long o = off(row, col);
+      w.o[ps] = o;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 m4 = o >= 0 ? __ldcg(reinterpret_cast<const float4*>(p.vmu + o)) : z4;
+      const float4 s4 = o >= 0 ? __ldcg(reinterpret_cast<const float4*>(p.vsig + o)) : z4;
+      w.pv[ps * 4] = m4.x; w.pv[ps * 4 + 1] = m4.y; w.pv[ps * 4 + 2] = m4.z; w.pv[ps * 4 + 3] = m4.w;
+      w.av[ps * 4] = s4.x; w.av[ps * 4 + 1] = s4.y; w.av[ps * 4 + 2] = s4.z; w.av[ps * 4 + 3] = s4.w;
+    }
+    return;
+  }
   const int col = c.lane % N, rsub = c.lane / N;
 #pragma unroll
   for (int r = 0; r < WgPre<N>::NP; ++r) {
     const int row = c.warp * 8 + r * WgPre<N>::RPP + rsub;
     w.o[r] = off(row, col);
-    w.pv[r] = w.o[r] >= 0 ? __ldcg((p.fvb == 2 ? p.vmu : p.P) + w.o[r]) : 0.f;       // sampled full VB: (mu, sigma)
-    w.av[r] = w.o[r] >= 0 ? __ldcg((p.fvb == 2 ? p.vsig : p.ada) + w.o[r]) : 0.f;
+    w.pv[r] = w.o[r] >= 0 ? __ldcg((SV ? p.vmu : p.P) + w.o[r]) : 0.f;       // sampled full VB: (mu, sigma)
+    w.av[r] = w.o[r] >= 0 ? __ldcg((SV ? p.vsig : p.ada) + w.o[r]) : 0.f;
   }
 }
-template <int N, class MirF>
-__device__ __forceinline__ void wgrad_epilogue_coalesced(Ctx& c, const Params& p, const Hyper& hy, const WgPre<N>& w, MirF mir) {
+template <int N, bool SV, class MirF>
+__device__ __forceinline__ void wgrad_epilogue_coalesced(Ctx& c, const Params& p, const Hyper& hy, const WgPre<N>& w, MirF mir,
+                                                         bool vec4 = false) {
   // (every weight-gradient GEMM has a delta operand: the two accumulators are combined while they are parked)
   constexpr int GP = 33;
   float* gt = reinterpret_cast<float*>(c.sm + SM_RECV);            // 128 x 33 floats = 16.5 KB (no cluster item is active)
@@ -916,7 +963,41 @@ __device__ __forceinline__ void wgrad_epilogue_coalesced(Ctx& c, const Params& p
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (p.fvb == 2) {
+  if (SV && N == 32 && vec4) {
+    // sampled full VB, one Philox group per thread and pass (see wgrad_prefetch)
+    float4 am4[2], as4[2], zt4[2];
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {                               // every load before the first store
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const long long o = w.o[ps];
+      am4[ps] = o >= 0 ? __ldcg(reinterpret_cast<const float4*>(p.ada_mu + o)) : z4;
+      as4[ps] = o >= 0 ? __ldcg(reinterpret_cast<const float4*>(p.ada_sig + o)) : z4;
+      zt4[ps] = o >= 0 ? __ldcg(reinterpret_cast<const float4*>(p.zeta + o)) : z4;
+    }
+#pragma unroll
+    for (int ps = 0; ps < 2; ++ps) {
+      const long long o = w.o[ps];
+      if (o >= 0) {
+        const int row = c.warp * 8 + ps * 4 + (c.lane >> 3), col = (c.lane & 7) * 4;
+        float zn[4], m1[4], s1[4], am[4], as[4], th[4];
+        zeta_group(p, c.step + 1u, (uint64_t)o >> 2, zn);
+        const float a0[4] = {am4[ps].x, am4[ps].y, am4[ps].z, am4[ps].w}, b0[4] = {as4[ps].x, as4[ps].y, as4[ps].z, as4[ps].w};
+        const float z0[4] = {zt4[ps].x, zt4[ps].y, zt4[ps].z, zt4[ps].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          th[j] = fvb_math(c, hy, gt[row * GP + col + j] * hy.w, w.pv[ps * 4 + j], w.av[ps * 4 + j], a0[j], b0[j], z0[j], zn[j],
+                           m1[j], s1[j], am[j], as[j]);
+          gt[row * GP + col + j] = th[j];
+        }
+        *reinterpret_cast<float4*>(p.vmu + o) = make_float4(m1[0], m1[1], m1[2], m1[3]);
+        *reinterpret_cast<float4*>(p.vsig + o) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+        *reinterpret_cast<float4*>(p.ada_mu + o) = make_float4(am[0], am[1], am[2], am[3]);
+        *reinterpret_cast<float4*>(p.ada_sig + o) = make_float4(as[0], as[1], as[2], as[3]);
+        *reinterpret_cast<float4*>(p.zeta + o) = make_float4(zn[0], zn[1], zn[2], zn[3]);
+        *reinterpret_cast<float4*>(p.P + o) = make_float4(th[0], th[1], th[2], th[3]);
+      }
+    }
+  } else if (SV) {
     const int col = c.lane % N, rsub = c.lane / N;
     float am0[WgPre<N>::NP], as0[WgPre<N>::NP], zt[WgPre<N>::NP];
 #pragma unroll
@@ -963,6 +1044,7 @@ __device__ __forceinline__ void wgrad_epilogue_coalesced(Ctx& c, const Params& p
 
 // W2, b2 <- Adagrad([h_d | 1]^T . da2); tile = 128 hidden units x 32 pixels.  Gaussian decoder: `which` = 1 selects
 // the W6 / b6 half of the tile (rows 32..63 of the transposed delta mirror, virtual columns 32..63 of the chunk).
+template <bool SV>
 __device__ __forceinline__ void item_wg2(Ctx& c, const Params& p, const Hyper& hy, int mt, int nt, int which) {
   ST2_TRACE(c, 60);
   constexpr int TB = 32 * 128;                                  // the B tile of the item: 32 rows
@@ -978,14 +1060,15 @@ __device__ __forceinline__ void item_wg2(Ctx& c, const Params& p, const Hyper& h
   const int H = p.H, D = p.D;
   const long long oW = which ? p.oW6 : p.oW2, ob = which ? p.ob6 : p.ob2;
   WgPre<32> pre;
-  wgrad_prefetch<32>(c, p, [&](int row, int col) -> long long {
+  const bool vec4 = SV && ((oW | ob | (long long)D) & 3) == 0;     // rows are 16-byte aligned runs
+  wgrad_prefetch<32, SV>(c, p, [&](int row, int col) -> long long {
     const int i = mt * MP + row, n = nt * 32 + col;
     if (i > H || n >= D) return -1;
     return i < H ? oW + (long long)i * D + n : ob + n;
-  }, pre);
+  }, pre, vec4);
   mma_run(c, 2, (p.M + 15) / 16, TB, 32, true, 0u, 0, 1);
   ST2_TRACE(c, 61);
-  wgrad_epilogue_coalesced<32>(
+  wgrad_epilogue_coalesced<32, SV>(
       c, p, hy, pre,
       [&](int row, int col0, float* nv) {
         const int i = mt * MP + row, n0 = nt * 32 + col0;
@@ -1001,12 +1084,13 @@ __device__ __forceinline__ void item_wg2(Ctx& c, const Params& p, const Hyper& h
         constexpr int TG = TR_DGRAD * 128;
         const int kv = p.cont ? nt * 64 + vr : n0;
         put_unit<true>(p.m_dgrad + ((size_t)(i >> 4) * p.KV + (kv >> 6)) * 2 * TG + unit_off(i & 15, (kv & 63) >> 3), TG, nv);
-      });
+      }, vec4);
   ST2_TRACE(c, 62);
 }
 
 // W3, b3 <- Adagrad([x | 1]^T . da3), da3 = ([dmu|dls].[W4|W5]^T) * (1 - h_e^2) recomputed on the tensor cores (K = one
 // chunk) and written, transposed, into the B tile; tile = 128 pixels x 32 hidden units
+template <bool SV>
 __device__ __forceinline__ void item_wg3(Ctx& c, const Params& p, const Hyper& hy, const float* he, int mt, int nt, int par) {
   ST2_TRACE(c, 70);
   const int H = p.H, M = p.M, D = p.D;
@@ -1030,11 +1114,12 @@ __device__ __forceinline__ void item_wg3(Ctx& c, const Params& p, const Hyper& h
     hv[0] = h0.x; hv[1] = h0.y; hv[2] = h0.z; hv[3] = h0.w; hv[4] = h1.x; hv[5] = h1.y; hv[6] = h1.z; hv[7] = h1.w;
   }
   WgPre<32> pre;
-  wgrad_prefetch<32>(c, p, [&](int row, int col) -> long long {
+  const bool vec4 = SV && ((p.oW3 | p.ob3 | (long long)H) & 3) == 0;   // rows are 16-byte aligned runs
+  wgrad_prefetch<32, SV>(c, p, [&](int row, int col) -> long long {
     const int i = mt * MP + row, jc = nt * 32 + col;
     if (i > D || jc >= H) return -1;
     return i < D ? p.oW3 + (long long)i * H + jc : p.ob3 + jc;
-  }, pre);
+  }, pre, vec4);
   // ---- dh_e pre-activation on the tensor cores: D1[128 x 32] = [dmu|dls] . [W4|W5]^T (tile rows) -----------------
   tc::tc_fence_before();
   __syncthreads();                                              // the previous item's TMEM reads are complete
@@ -1077,7 +1162,7 @@ __device__ __forceinline__ void item_wg3(Ctx& c, const Params& p, const Hyper& h
   ST2_TRACE(c, 71);
   mma_run(c, 2, (M + 15) / 16, TB, 32, false, 0u, 0, 1);
   ST2_TRACE(c, 72);
-  wgrad_epilogue_coalesced<32>(
+  wgrad_epilogue_coalesced<32, SV>(
       c, p, hy, pre,
       [&](int row, int col0, float* nv) {
         const int i = mt * MP + row, j0_ = nt * 32 + col0;
@@ -1085,12 +1170,13 @@ __device__ __forceinline__ void item_wg3(Ctx& c, const Params& p, const Hyper& h
 #pragma unroll
         for (int e = 0; e < 8; ++e)
           if (j0_ + e < H) mirror_put(p.m_enc1, TR_ENC1, p.KD, (j0_ + e) >> 4, (j0_ + e) & 15, i, nv[e]);
-      });
+      }, vec4);
   ST2_TRACE(c, 73);
 }
 
 // W1, b1 <- Adagrad([z | 1]^T . da1), computed transposed: tile = 128 hidden units x (Z + 1) latent columns.  W1 is
 // [Z][H]: with the thread = hidden unit mapping of the accumulator every access below is coalesced along the lanes.
+template <bool SV>
 __device__ __forceinline__ void item_wg1(Ctx& c, const Params& p, const Hyper& hy, int mt) {
   const int Z = p.Z, H = p.H, N = p.NZ;
   const int TB = N * 128;
@@ -1109,14 +1195,14 @@ __device__ __forceinline__ void item_wg1(Ctx& c, const Params& p, const Hyper& h
     const int q = col0 + e;
     ok[e] = mine && q <= Z;
     off[e] = q < Z ? (size_t)p.oW1 + (size_t)q * H + i : (size_t)p.ob1 + i;
-    pv[e] = ok[e] ? __ldcg((p.fvb == 2 ? p.vmu : p.P) + off[e]) : 0.f;
-    av[e] = ok[e] ? __ldcg((p.fvb == 2 ? p.vsig : p.ada) + off[e]) : 0.f;
+    pv[e] = ok[e] ? __ldcg((SV ? p.vmu : p.P) + off[e]) : 0.f;
+    av[e] = ok[e] ? __ldcg((SV ? p.vsig : p.ada) + off[e]) : 0.f;
   }
   mma_run(c, 2, (p.M + 15) / 16, TB, N, true, 0u, 1, 0);
   if (u < N / 8) {
     float v[8], nv[8];
     acc_ld8(c, qq, (uint32_t)col0, v, true);
-    if (mine && p.fvb == 2) {
+    if (SV && mine) {
       float am0[8], as0[8], zt[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -1164,6 +1250,7 @@ __device__ __forceinline__ void item_wg1(Ctx& c, const Params& p, const Hyper& h
 }
 
 // W4, b4, W5, b5 <- Adagrad([h_e | 1]^T . [dmu | dls]); tile = 128 hidden units x 16 columns of [dmu | dls]
+template <bool SV>
 __device__ __forceinline__ void item_wg45(Ctx& c, const Params& p, const Hyper& hy, int mt, int nt, int par) {
   const int Z = p.Z, H = p.H;
   constexpr int N = 16, TB = N * 128;
@@ -1173,7 +1260,7 @@ __device__ __forceinline__ void item_wg45(Ctx& c, const Params& p, const Hyper& 
     bulk_g2s(c.sm + SM_B, p.dd_t + (size_t)nt * 4 * TB, (uint32_t)(4 * TB), c.op_bar);
   }
   WgPre<N> pre;
-  wgrad_prefetch<N>(c, p, [&](int row, int col) -> long long {
+  wgrad_prefetch<N, SV>(c, p, [&](int row, int col) -> long long {
     const int i = mt * MP + row, cc = nt * N + col;
     if (i > H || cc >= 2 * Z) return -1;
     const int jc = cc < Z ? cc : cc - Z;
@@ -1181,7 +1268,7 @@ __device__ __forceinline__ void item_wg45(Ctx& c, const Params& p, const Hyper& 
     return (cc < Z ? p.ob4 : p.ob5) + jc;
   }, pre);
   mma_run(c, 2, (p.M + 15) / 16, TB, N, true, 0u, 0, 1);
-  wgrad_epilogue_coalesced<N>(
+  wgrad_epilogue_coalesced<N, SV>(
       c, p, hy, pre,
       [&](int row, int col0, float* nv) {
         const int i = mt * MP + row, cc0 = nt * N + col0;
@@ -1281,6 +1368,7 @@ __device__ __forceinline__ void item_fvb_prior(Ctx& c, const Params& p, const Hy
 }
 
 // =================================================================================================================
+template <bool SV>
 __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ Params p) {
   Ctx c;
   c.sm = smem_base();
@@ -1342,7 +1430,7 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     c.step = p.step0 + (uint32_t)s; c.tp = 0.f;
     // sampled full VB: the bound of the previous step needs the thetaPrior sums of ITS update epilogues (P5, P6): it is
     // summed here, by a CTA that has no enc1 item, before P2 / P3 overwrite the row partials
-    if (p.fvb == 2 && s > 0 && (int)blockIdx.x == G - 1) item_bound(c, p, s - 1);
+    if (SV && s > 0 && (int)blockIdx.x == G - 1) item_bound(c, p, s - 1);
     long long* tm = rec ? p.timing + (size_t)s * (N_PHASES + 1) : nullptr;
     if (tm) tm[0] = gtime();
     if (p.timing && blockIdx.x == 0 && s == p.n_steps - 1) c.trace = p.timing + (size_t)p.n_steps * (N_PHASES + 1);
@@ -1409,8 +1497,8 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
       for (int it = c.cid; it < 1 + g2; it += c.ncl) {
         if (it == 0) { item_dz(c, p, false); continue; }
         const int i = (it - 1) * CL + c.rank;
-        if (i < n2) item_wg2(c, p, hy, i / (n3 * nw), (i / nw) % n3, i % nw);
-        else if (i == n2 && p.fvb != 2) item_bound(c, p, s);
+        if (i < n2) item_wg2<SV>(c, p, hy, i / (n3 * nw), (i / nw) % n3, i % nw);
+        else if (i == n2 && !SV) item_bound(c, p, s);
       }
     }
     ST2_TRACE(c, 85);
@@ -1423,12 +1511,12 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
       const int n45 = m_h1 * n45t;
       for (int it = c.cid; it < n_groups(n3w + m_h + n45); it += c.ncl) {
         const int i = it * CL + c.rank;
-        if (i < n3w) item_wg3(c, p, hy, p.he, i / n_h32, i % n_h32, par);
-        else if (i < n3w + m_h) item_wg1(c, p, hy, i - n3w);
-        else if (i < n3w + m_h + n45) item_wg45(c, p, hy, (i - n3w - m_h) / n45t, (i - n3w - m_h) % n45t, par);
+        if (i < n3w) item_wg3<SV>(c, p, hy, p.he, i / n_h32, i % n_h32, par);
+        else if (i < n3w + m_h) item_wg1<SV>(c, p, hy, i - n3w);
+        else if (i < n3w + m_h + n45) item_wg45<SV>(c, p, hy, (i - n3w - m_h) / n45t, (i - n3w - m_h) % n45t, par);
       }
     }
-    if (p.fvb == 2) store_tprior(c, p, s, c.tp);
+    if (SV) store_tprior(c, p, s, c.tp);
     // the A tile of this CTA's first enc1 item of the next step (x_km was written in P2): in flight across the barrier
     if (s + 1 < p.n_steps && has_p1 && threadIdx.x == 0 && kdn > 0) {
       tc::mbar_expect_tx(c.x_bar, (uint32_t)(kdn * 2 * TBA));
@@ -1441,7 +1529,7 @@ __global__ void __launch_bounds__(NT, 1) step_tc_kernel(const __grid_constant__ 
     ST2_TRACE(c, 96);
     last_done = s;
   }
-  if (p.fvb == 2 && last_done >= 0 && (int)blockIdx.x == G - 1) item_bound(c, p, last_done);
+  if (SV && last_done >= 0 && (int)blockIdx.x == G - 1) item_bound(c, p, last_done);
   tc::tc_fence_before();
   __syncthreads();
   cluster_sync();                                   // no CTA leaves while a peer may still write its shared memory
@@ -1563,7 +1651,8 @@ static int step_tc_init(vaeb_handle* h) {
   const int n3 = (D + 31) / 32;
   const int TR3 = h->cont ? 64 : 32, KV = h->cont ? n3 : KD;
   const int m_h1 = (H + 1 + MP - 1) / MP;
-  VAEB_CUDA(cudaFuncSetAttribute(step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  VAEB_CUDA(cudaFuncSetAttribute(step_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  VAEB_CUDA(cudaFuncSetAttribute(step_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   // how many clusters of four fit at once: the grid must be co-resident (grid barriers)
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(CL * 64); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = SMEM_BYTES;
@@ -1571,7 +1660,7 @@ static int step_tc_init(vaeb_handle* h) {
   at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
   cfg.attrs = &at; cfg.numAttrs = 1;
   int ncl = 0;
-  VAEB_CUDA(cudaOccupancyMaxActiveClusters(&ncl, step_tc_kernel, &cfg));
+  VAEB_CUDA(cudaOccupancyMaxActiveClusters(&ncl, step_tc_kernel<true>, &cfg));
   if (ncl < 8) { s.unavailable = true; return VAEB_OK; }
   s.n_cta = CL * std::min(ncl, 33);
   auto alloc = [](void** q, size_t bytes) -> cudaError_t {
@@ -1713,7 +1802,8 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
   // the grid is sized to be co-resident either way)
   static const bool no_coop = getenv("VAEB_ST2_NOCOOP") != nullptr;
   cfg.attrs = at; cfg.numAttrs = no_coop ? 1 : 2;
-  VAEB_CUDA(cudaLaunchKernelEx(&cfg, step_tc_kernel, p));
+  if (p.fvb == 2) VAEB_CUDA(cudaLaunchKernelEx(&cfg, step_tc_kernel<true>, p));
+  else VAEB_CUDA(cudaLaunchKernelEx(&cfg, step_tc_kernel<false>, p));
   ++h->launches;
   h->grads_have_prior = false;
   int done = n_steps;
