@@ -243,6 +243,11 @@ int vaeb_tc_gemm_test(int32_t device, int32_t M, int32_t N, int32_t K, int32_t a
 /* Counters for the bench: kernels launched by this handle since creation. */
 int vaeb_launch_count(vaeb_handle* h, int64_t* n_launches);
 
+/* Which kernel serves update() for a minibatch of `rows` rows with this handle's configuration: 2 = the tensor-core
+ * single-launch step kernel (step_tc.cu: M <= 128, L = 1, one GPU), 1 = the fp32 FFMA single-launch kernel
+ * (fused_step.cu), 0 = one launch per layer (kernels_*.cu / tc_layers.cu). */
+int vaeb_step_kernel(vaeb_handle* h, int64_t rows, int32_t* which);
+
 #ifdef __cplusplus
 }
 #endif

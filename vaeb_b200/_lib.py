@@ -69,6 +69,7 @@ EXPORTS = {
     "vaeb_tc_gemm_test": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "vaeb_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "vaeb_step_kernel": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]),
     "vaeb_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "vaeb_host_free": (C.c_int, [C.c_void_p]),
 }

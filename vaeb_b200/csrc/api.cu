@@ -1633,4 +1633,10 @@ int vaeb_launch_count(vaeb_handle* h, int64_t* n_launches) {
   return VAEB_OK;
 }
 
+int vaeb_step_kernel(vaeb_handle* h, int64_t rows, int32_t* which) {
+  VAEB_REQUIRE(h && which && rows > 0, "null argument");
+  *which = step_tc_supported(h, (int)rows) ? 2 : (fused_step_supported(h, (int)rows) ? 1 : 0);
+  return VAEB_OK;
+}
+
 }  // extern "C"

@@ -368,6 +368,13 @@ class VAEB(object):
         _lib.check(self._lib.vaeb_profile_optimizer(self._h, int(iters), int(variant), C.byref(ms), C.byref(by)))
         return ms.value, by.value
 
+    def step_kernel_name(self, rows=None):
+        """The kernel update() runs for `rows` rows (default: the batch size)."""
+        w = C.c_int32()
+        _lib.check(self._lib.vaeb_step_kernel(self._h, int(rows or self.batch_size), C.byref(w)))
+        return {2: "step_tc_kernel (tcgen05, one launch per update)", 1: "fused_step_kernel (fp32 FFMA, one launch per update)",
+                0: "per-layer kernels"}[w.value]
+
     def launch_count(self):
         n = C.c_int64()
         _lib.check(self._lib.vaeb_launch_count(self._h, C.byref(n)))
