@@ -256,11 +256,22 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   const bool tcp = h->tc.active;
   TcState& t = h->tc;
   int x_row_off = 0, bn = 64, bna = 64;   // UMMA N of the weight-gradient / of the activation layers
+  bool chain = false, chain_pair = false;
   const void *x_mirror_hi = nullptr, *x_mirror_lo = nullptr;
   if (tcp) {
     VAEB_TRY(tc_ensure(h, rows, R));
     bn = R >= 1024 ? 128 : 64;
     bna = tc_act_bn(rows, std::min(H, D));
+    static const int env_bn = getenv("VAEB_TC_BN") ? atoi(getenv("VAEB_TC_BN")) : 0;     // measurement switch
+    if (env_bn == 64 || env_bn == 128 || env_bn == 256) bna = env_bn;
+    // the activation chain as ONE launch (tc_chain.cu): large-batch training steps of the Bernoulli model.  In its CTA-pair
+    // form (cta_group::2) a CTA stages half of a 256-wide B tile: the maps carry 128-wide boxes.
+    static const int env_chain = getenv("VAEB_TC_CHAIN") ? atoi(getenv("VAEB_TC_CHAIN")) : -1;   // measurement switches
+    static const int env_pair = getenv("VAEB_TC_PAIR") ? atoi(getenv("VAEB_TC_PAIR")) : -1;
+    chain = want_grads && !h->cont && L == 1 && latent_large_batch(rows, H, Z, L) && 4 * ((2 * Z + 63) / 64) <= Z &&
+            (env_chain >= 0 ? env_chain != 0 : rows >= 16384);
+    chain_pair = chain && (env_pair >= 0 ? env_pair != 0 : rows >= 4096);
+    if (chain_pair) bna = 128;
     // Programmatic dependent launch for the one-tile-per-CTA kernels: bf16x3 (one CTA per SM: an early dependent grid
     // never takes slots from the running one; 16384 rows: 523 -> 499 us per update) and, in plain bf16, whenever the
     // activation layers are NOT in the persistent form (8192 rows: 215 -> 196 us); next to the persistent kernels the
@@ -309,6 +320,63 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   TcReduceJobs reduce_jobs;
   TcReduceJobs* defer = tcl ? &reduce_jobs : nullptr;
   const size_t wg_region = tcp ? tc_wgrad_scratch_elems(D, H) : 0;
+  // few rows per GPU (the data-parallel split): the four weight-gradient GEMMs are one launch after the last dgrad
+  const bool merged_wgrad = tcl && tc_wgrad_merged_supported(rows);
+  if (merged_wgrad && t.n_sm == 0) VAEB_CUDA(cudaDeviceGetAttribute(&t.n_sm, cudaDevAttrMultiProcessorCount, h->cfg.device));
+#define WGRAD_ALL_CALL                                                                                                  \
+  tc_wgrad_all(st, lc, t.maps, t.ns, bn, R, rows, D, H, Z, x_row_off, T_(h, grads, l.iW2), T_(h, grads, l.ib2),        \
+               T_(h, grads, l.iW1), T_(h, grads, l.ib1), T_(h, grads, l.iW4), T_(h, grads, l.ib4), T_(h, grads, l.iW5), \
+               T_(h, grads, l.ib5), T_(h, grads, l.iW3), T_(h, grads, l.ib3), tb.wg_scratch, wg_region, defer, t.n_sm)
+  // ---- large-batch training step: the seven activation layers are ONE persistent launch (tc_chain.cu) ----------
+  if (tcl && chain) {
+    const int cbn = chain_pair ? 256 : bna;
+    if (t.n_sm == 0) VAEB_CUDA(cudaDeviceGetAttribute(&t.n_sm, cudaDevAttrMultiProcessorCount, h->cfg.device));
+    const int need = tc_chain_ready_elems(rows);
+    if (need > t.chain_ready_cap) {
+      VAEB_CUDA(cudaStreamSynchronize(st));
+      if (t.chain_ready) VAEB_CUDA(cudaFree(t.chain_ready));
+      t.chain_ready = nullptr;
+      VAEB_CUDA(cudaMalloc((void**)&t.chain_ready, (size_t)need * sizeof(unsigned int)));
+      t.chain_ready_cap = need;
+      t.chain_key_rows = -1;
+    }
+    if (t.chain_key_rows != rows || t.chain_key_bn != cbn + (chain_pair ? 1 : 0)) {
+      VAEB_CUDA(cudaMemsetAsync(t.chain_ready, 0, (size_t)t.chain_ready_cap * sizeof(unsigned int), st));
+      t.chain_epoch = 0;
+      t.chain_key_rows = rows; t.chain_key_bn = cbn + (chain_pair ? 1 : 0);
+    }
+    int n_aux = 0;
+    TcBuffers cb = tb;
+    PH("activation chain enc1..dgrad h_e [tcgen05, one launch]", 6 * dr * dD * dH + 12 * dr * dH * dZ,
+       2.0 * t.ns * (2 * dr * dD + 6 * dr * dH + 3 * dD * dH) + 60 * dr * dZ,
+       tc_chain_step(st, lc, t.maps, t.ns, cbn, rows, D, H, Z, la, x_row_off, T_(h, theta, l.ib3), T_(h, theta, l.ib4),
+                     T_(h, theta, l.ib5), T_(h, theta, l.ib1), T_(h, theta, l.ib2), src, w / (float)L, w, s.mu, s.ls, s.eps,
+                     s.z, s.dmu, s.dls, s.dz, &n_aux, s.partial, &tiles, cb, x_mirror_hi, x_mirror_lo, t.chain_ready,
+                     ++t.chain_epoch, t.n_sm, chain_pair ? 1 : 0));
+    VAEB_LAUNCH(launch_row_partials_sum(st, lc, s.dz, n_aux, rows, s.row_aux));
+    PH("bound (per row + total)", 0, 4 * (dR * tiles + 2 * dr),
+       launch_finalize(st, lc, s.partial, tiles, s.row_aux, rows, L, s.per_row, bo.base_out, bo.mult, bo.tprior,
+                       bo.n_tprior, bo.div, bo.scalar_out, h->d_counter, s.dec_aux));
+    if (merged_wgrad) {
+      PH("wgrad W2,W1,W4|W5,W3 (+ biases) [tcgen05, one launch]", 4 * dR * dH * dD + 2 * dR * dZ * dH + 4 * dr * dH * dZ,
+         2.0 * t.ns * (2 * dR * dH + 2 * dR * dD) + 8 * dH * dD, WGRAD_ALL_CALL);
+    } else {
+    PH("wgrad W2,b2 [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dH + dR * dD) + 4 * dH * dD,
+       tc_wgrad2(st, lc, t.maps, t.ns, bn, R, H, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2), tb.wg_scratch, defer));
+    PH("wgrad W1,b1 [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * 32 + dR * dH) + 4 * dZ * dH,
+       tc_wgrad1(st, lc, t.maps, t.ns, bn, R, Z, H, T_(h, grads, l.iW1), T_(h, grads, l.ib1), tb.wg_scratch + wg_region,
+                 defer));
+    PH("wgrad W4,b4,W5,b5 [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * dH + dr * 64) + 8 * dZ * dH,
+       tc_wgrad45(st, lc, t.maps, t.ns, rows, H, Z, T_(h, grads, l.iW4), T_(h, grads, l.ib4), T_(h, grads, l.iW5),
+                  T_(h, grads, l.ib5), tb.wg_scratch + 2 * wg_region, defer));
+    PH("wgrad W3,b3 [tcgen05]", 2 * dr * dD * dH, 2.0 * t.ns * (dr * dD + dr * dH) + 4 * dD * dH,
+       tc_wgrad3(st, lc, t.maps, t.ns, bn, rows, D, H, x_row_off, T_(h, grads, l.iW3), T_(h, grads, l.ib3),
+                 tb.wg_scratch + 3 * wg_region, defer));
+    }
+    if (reduce_jobs.n > 0)
+      PH("sum of the split-K weight-gradient slices (one launch)", 0, 0, tc_wgrad_reduce_all(st, lc, reduce_jobs));
+    return VAEB_OK;
+  }
   // encoder hidden layer, VAEB.py:246
   if (tcp)
     PH("enc1 x.W3+tanh [tcgen05]", 2 * dr * dD * dH, 2.0 * t.ns * (dr * dD + dD * dH) + 4 * dr * dH,
@@ -360,8 +428,9 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   }
   // backward (T.grad, VAEB.py:397); formulas in SURVEY.md 8a
   if (tcp) {
-    PH("wgrad W2,b2 [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dH + dR * dD) + 4 * dH * dD,
-       tc_wgrad2(st, lc, t.maps, t.ns, bn, R, H, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2), tb.wg_scratch, defer));
+    if (!merged_wgrad)
+      PH("wgrad W2,b2 [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dH + dR * dD) + 4 * dH * dD,
+         tc_wgrad2(st, lc, t.maps, t.ns, bn, R, H, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2), tb.wg_scratch, defer));
     PH("dgrad h_d (.W2^T)*(1-h^2) [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dD + dH * dD) + 8 * dR * dH,
        tc_dgrad_hd(st, lc, t.maps, t.ns, bna, R, D, H, tcl ? nullptr : s.h_d, tcl ? nullptr : s.da1,
                    tcl ? tb.d1h : nullptr, tcl ? tb.d1l : nullptr, tb.ldh, tb.hdh, tb.hdl));
@@ -391,19 +460,26 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   if (tcl) {
     PH("dgrad h_e ([dmu|dls].W45^T)*(1-h^2) [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * 64 + 2 * dZ * dH) + 8 * dr * dH,
        tc_dgrad_he(st, lc, t.maps, t.ns, bna, rows, Z, H, nullptr, nullptr, tb.da3h, tb.da3l, tb.ldh, tb.heh, tb.hel));
+    if (merged_wgrad) {
+      PH("wgrad W2,W1,W4|W5,W3 (+ biases) [tcgen05, one launch]", 4 * dR * dH * dD + 2 * dR * dZ * dH + 4 * dr * dH * dZ,
+         2.0 * t.ns * (2 * dR * dH + 2 * dR * dD) + 8 * dH * dD, WGRAD_ALL_CALL);
+    } else {
     PH("wgrad W1,b1 [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * 32 + dR * dH) + 4 * dZ * dH,
        tc_wgrad1(st, lc, t.maps, t.ns, bn, R, Z, H, T_(h, grads, l.iW1), T_(h, grads, l.ib1), tb.wg_scratch + wg_region,
                  defer));
     PH("wgrad W4,b4,W5,b5 [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * dH + dr * 64) + 8 * dZ * dH,
        tc_wgrad45(st, lc, t.maps, t.ns, rows, H, Z, T_(h, grads, l.iW4), T_(h, grads, l.ib4), T_(h, grads, l.iW5),
                   T_(h, grads, l.ib5), tb.wg_scratch + 2 * wg_region, defer));
+    }
   } else
   PH("wgrad W1,b1,W4,b4,W5,b5", 2 * dR * dZ * dH + 4 * dr * dH * dZ,
      4 * (dR * dZ + dR * dH + dr * dH + 2 * dr * dZ + 3 * dH * dZ),
      launch_small_wgrad(st, lc, s.z, s.da1, R, s.h_e, s.dmu, s.dls, rows, H, Z, T_(h, grads, l.iW1),
                         T_(h, grads, l.ib1), T_(h, grads, l.iW4), T_(h, grads, l.ib4), T_(h, grads, l.iW5),
                         T_(h, grads, l.ib5), s.wg_scratch));
-  if (tcp)
+  if (tcp && merged_wgrad) {
+    // (launched above, with the other weight gradients)
+  } else if (tcp)
     PH("wgrad W3,b3 [tcgen05]", 2 * dr * dD * dH, 2.0 * t.ns * (dr * dD + dr * dH) + 4 * dD * dH,
        tc_wgrad3(st, lc, t.maps, t.ns, bn, rows, D, H, x_row_off, T_(h, grads, l.iW3), T_(h, grads, l.ib3),
                  tcl ? tb.wg_scratch + 3 * wg_region : tb.wg_scratch, defer));

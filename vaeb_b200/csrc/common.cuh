@@ -76,6 +76,10 @@ struct TcState {
   int64_t cap_data = 0, cap_stage = 0, cap_R = 0, cap_rows = 0;
   TcMaps maps;
   int64_t key_rows = -1, key_R = -1, key_data = -1; int key_bn = 0; const void* key_x = nullptr;
+  // the activation chain as one launch (tc_chain.cu): arrival counters, launches since they were zeroed
+  unsigned int* chain_ready = nullptr; int chain_ready_cap = 0; unsigned int chain_epoch = 0;
+  int64_t chain_key_rows = -1; int chain_key_bn = 0;
+  int n_sm = 0;
 };
 
 // State of the fused single-launch step (fused_step.cu).

@@ -33,6 +33,7 @@ struct TcMaps {
   alignas(64) unsigned char wgrad3[TC_LAYER_MAPS_BYTES];
   alignas(64) unsigned char wgrad1[TC_LAYER_MAPS_BYTES];    // gW1|gb1 = [z|1]^T . da1
   alignas(64) unsigned char wgrad45[TC_LAYER_MAPS_BYTES];   // gW4|gW5 (+ bias row) = [h_e|1]^T . [dmu|dls]
+  alignas(64) unsigned char wgrad45w[TC_LAYER_MAPS_BYTES];  // the same with B boxes as wide as the other weight gradients'
   alignas(64) unsigned char dhe[TC_LAYER_MAPS_BYTES];       // da3 = ([dmu|dls] . [W4^T;W5^T]) * (1 - h_e^2)
   alignas(64) unsigned char dz[TC_LAYER_MAPS_BYTES];        // dz = da1 . W1^T (+ dmu, dls in the epilogue)
   alignas(64) unsigned char enc2[TC_LAYER_MAPS_BYTES];      // (mu, ls) = h_e . [W4|W5] (+ reparameterisation in the epilogue)
@@ -102,3 +103,23 @@ cudaError_t tc_wgrad2(cudaStream_t st, int64_t* launches, const TcMaps& m, int n
                       float* gW2, float* gb2, float* scratch, TcReduceJobs* defer = nullptr);
 cudaError_t tc_wgrad3(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int D, int H,
                       int x_row_off, float* gW3, float* gb3, float* scratch, TcReduceJobs* defer = nullptr);
+
+// ---- the activation chain as one persistent launch (tc_chain.cu) -------------------------------------------------
+// enc1 -> enc2 -> dec1 -> dec2 -> dgrad h_d -> dz -> dgrad h_e for `rows` rows (L = 1, Bernoulli decoder) as items of ONE
+// launch; row blocks are handed from layer to layer through arrival counters in `ready` (tc_chain_ready_elems(rows)
+// unsigned ints, zeroed when the shapes change; `epoch` = launches since then, starting at 1).
+int tc_chain_ready_elems(int rows);
+cudaError_t tc_chain_step(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int D, int H,
+                          int Z, int la, int x_row_off, const float* b3, const float* b4, const float* b5, const float* b1,
+                          const float* b2, const EpsSource& src, float scale, float w, float* mu, float* ls, float* eps,
+                          float* z, float* dmu, float* dls, float* aux_part, int* n_aux, float* partial, int* n_tiles,
+                          const TcBuffers& b, const void* xm_hi, const void* xm_lo, unsigned int* ready,
+                          unsigned int epoch, int n_sm, int pair);   // pair: cta_group::2 form, bn = 256 over maps built for 128
+
+// every weight-gradient GEMM of the step in ONE launch (W2, W1, [W4|W5], W3); the split-K slices stay in `scratch`
+// (four regions of `region` floats) and their reductions are appended to `jobs`
+bool tc_wgrad_merged_supported(int rows);
+cudaError_t tc_wgrad_all(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int rows, int D, int H,
+                         int Z, int x_row_off, float* gW2, float* gb2, float* gW1, float* gb1, float* gW4, float* gb4,
+                         float* gW5, float* gb5, float* gW3, float* gb3, float* scratch, size_t region, TcReduceJobs* jobs,
+                         int n_sm);
