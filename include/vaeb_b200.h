@@ -218,6 +218,14 @@ int vaeb_comm_unique_id(const char* nccl_library, uint8_t id_out[128]);
 int vaeb_comm_attach(vaeb_handle* h, const char* nccl_library, const uint8_t id[128],
                      int32_t rank, int32_t world_size);
 int vaeb_comm_detach(vaeb_handle* h);
+/* Data parallel over PEER MEMORY (NVLink / NVSwitch, ranks = processes of one box): after vaeb_comm_attach every rank
+ * exports three CUDA IPC handles (its gradient staging buffer + flags, its parameters, its Adagrad accumulators), the
+ * host plumbing all-gathers the 192 bytes per rank, every rank attaches all of them.  From then on the tail of a
+ * large-batch tensor-core update (tc_tail.cu) IS the collective: each rank sums ITS slice of the flat gradient from
+ * every rank's staging buffer with peer loads, applies prior + Adagrad, and stores the new parameters into every rank's
+ * buffers -- one launch, no NCCL kernel.  Other update paths keep using ncclAllReduce.  vaeb_comm_detach unmaps. */
+int vaeb_comm_p2p_export(vaeb_handle* h, uint8_t handles_out[192]);
+int vaeb_comm_p2p_attach(vaeb_handle* h, const uint8_t* all_handles, int32_t world_size);
 
 /* Measurement aid for bench.py: runs the phases of one update on batch `index` one at a time,
  * each launched `iters` times back to back between two CUDA events on the handle's stream.

@@ -26,7 +26,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     D, H, Z = 784, 500, 20
-    res = {"world": world, "cases": []}
+    res = {"world": world, "p2p": os.environ.get("VAEB_DP_P2P", "1"), "cases": []}
     for prec, MG, tol, floor in (("fp32", 512, 1e-4, 0.05), ("bf16x3", 2048, 1e-4, 0.1), ("bf16", 2048, 3e-2, 1.0)):
         per = MG // world
         x = O.synthetic_mnist(MG, seed=99)
@@ -57,7 +57,9 @@ def main():
             assert abs(ret - ret_ref) <= btol * abs(ret_ref), (prec, ret, ret_ref)
             # first Adagrad step: lr*g/(|g|+1e-6); compare the step where it is well conditioned (tests/test_gpu_parity.py)
             for a, b, p0, gr, n in zip(after, o.params, params, g_ref, O.param_names(False)):
-                well = np.abs(gr) > 1e-3 * np.abs(gr).max()
+                # (bf16 tier: gradients are held to 3e-2 of the tensor's max norm above, so the SIGN of an entry -- which is all
+                # the first Adagrad step keeps of it -- is only determined for entries well above that)
+                well = np.abs(gr) > (1e-3 if prec != "bf16" else 1e-1) * np.abs(gr).max()
                 np.testing.assert_allclose((a - p0)[well], (b - p0)[well], rtol=2e-3 if prec != "bf16" else 5e-2,
                                            atol=1e-7, err_msg="%s dp step %s" % (prec, n))
             assert same, "ranks hold different parameters after the replicated Adagrad step"

@@ -21,8 +21,9 @@ def _free_port():
     return p
 
 
+@pytest.mark.parametrize("p2p", ["1", "0"])       # 1: the tail kernel is the collective (peer memory); 0: ncclAllReduce
 @pytest.mark.parametrize("world", [2])
-def test_dp_step_matches_oracle_over_nccl(tmp_path, world):
+def test_dp_step_matches_oracle_over_nccl(tmp_path, world, p2p):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs (run under `gpurun --gpus %d`)" % (world, world))
@@ -30,7 +31,7 @@ def test_dp_step_matches_oracle_over_nccl(tmp_path, world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "dp_gpu_worker.py"), str(out)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, VAEB_DP_P2P=p2p))
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
     res = json.load(open(out))
     assert res["world"] == world and len(res["cases"]) == 3

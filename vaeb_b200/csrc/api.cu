@@ -207,7 +207,11 @@ int tc_ensure(vaeb_handle* h, int64_t rows, int64_t R) {
         VAEB_CUDA(cudaMemsetAsync(b.w45h, 0, (size_t)2 * h->Z * b.ldh * 2, h->stream));
         VAEB_CUDA(cudaMemsetAsync(b.w1h, 0, (size_t)h->Z * b.ldh * 2, h->stream));
         VAEB_TRY(grow_bytes(&b.whh, (size_t)H * b.ldq * 2));
-        if (lo) VAEB_TRY(grow_bytes(&b.whl, (size_t)H * b.ldq * 2));
+        VAEB_CUDA(cudaMemsetAsync(b.whh, 0, (size_t)H * b.ldq * 2, h->stream));
+        if (lo) {
+          VAEB_TRY(grow_bytes(&b.whl, (size_t)H * b.ldq * 2));
+          VAEB_CUDA(cudaMemsetAsync(b.whl, 0, (size_t)H * b.ldq * 2, h->stream));
+        }
         if (lo) {
           VAEB_TRY(grow_bytes(&b.w45l, (size_t)2 * h->Z * b.ldh * 2));
           VAEB_TRY(grow_bytes(&b.w1l, (size_t)h->Z * b.ldh * 2));
@@ -241,8 +245,10 @@ struct BoundOut {
 };
 
 // Forward (+ backward into `grads`) of the graph of VAEB.getGradient for x[rows,D] on device.
+// `tail` != nullptr (training update whose tail is one launch, tc_tail.cu): on the large-batch tensor-core path the bound
+// and the split-K reductions are NOT launched here; what they need is recorded in *tail (tail->rows > 0 says so).
 int forward_backward(vaeb_handle* h, const float* theta, const float* x, int rows, int L, bool want_grads, float w,
-                     EpsSource src, float* grads, const BoundOut& bo) {
+                     EpsSource src, float* grads, const BoundOut& bo, TcTailArgs* tail = nullptr) {
   const Layout& l = h->lay;
   Workspace& s = h->ws;
   const int D = h->D, H = h->H, Z = h->Z;
@@ -302,7 +308,10 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
       VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bna, Z, bn));
       t.key_rows = rows; t.key_R = R; t.key_data = rows_data; t.key_bn = bna * 1024 + bn; t.key_x = b.xh;
     }
-    if (want_grads && b.heh && b.zh && b.d1h && b.ddh && latent_large_batch(rows, H, Z, L))
+    if (want_grads && b.heh && b.zh && b.d1h && b.ddh && latent_large_batch(rows, H, Z, L) && t.weights_ready &&
+        theta == h->d_params) {
+      // the tail of the previous update wrote the mirrors of these very parameters
+    } else if (want_grads && b.heh && b.zh && b.d1h && b.ddh && latent_large_batch(rows, H, Z, L))
       PH("weight mirrors / transposes -> bf16 (one launch)", 0, 12.0 * dD * dH + 60.0 * dZ * dH,
          tc_prepare_weights(st, lc, T_(h, theta, l.iW3), T_(h, theta, l.iW2), T_(h, theta, l.iW4), T_(h, theta, l.iW5),
                             T_(h, theta, l.iW1), b, h->d_w45t, D, H, Z));
@@ -353,10 +362,15 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
                      T_(h, theta, l.ib5), T_(h, theta, l.ib1), T_(h, theta, l.ib2), src, w / (float)L, w, s.mu, s.ls, s.eps,
                      s.z, s.dmu, s.dls, s.dz, &n_aux, s.partial, &tiles, cb, x_mirror_hi, x_mirror_lo, t.chain_ready,
                      ++t.chain_epoch, t.n_sm, chain_pair ? 1 : 0));
-    VAEB_LAUNCH(launch_row_partials_sum(st, lc, s.dz, n_aux, rows, s.row_aux));
-    PH("bound (per row + total)", 0, 4 * (dR * tiles + 2 * dr),
-       launch_finalize(st, lc, s.partial, tiles, s.row_aux, rows, L, s.per_row, bo.base_out, bo.mult, bo.tprior,
-                       bo.n_tprior, bo.div, bo.scalar_out, h->d_counter, s.dec_aux));
+    if (tail) {
+      tail->partial = s.partial; tail->n_tiles = tiles; tail->aux_part = s.dz; tail->n_aux = n_aux; tail->row_aux = nullptr;
+      tail->rows = rows;
+    } else {
+      VAEB_LAUNCH(launch_row_partials_sum(st, lc, s.dz, n_aux, rows, s.row_aux));
+      PH("bound (per row + total)", 0, 4 * (dR * tiles + 2 * dr),
+         launch_finalize(st, lc, s.partial, tiles, s.row_aux, rows, L, s.per_row, bo.base_out, bo.mult, bo.tprior,
+                         bo.n_tprior, bo.div, bo.scalar_out, h->d_counter, s.dec_aux));
+    }
     if (merged_wgrad) {
       PH("wgrad W2,W1,W4|W5,W3 (+ biases) [tcgen05, one launch]", 4 * dR * dH * dD + 2 * dR * dZ * dH + 4 * dr * dH * dZ,
          2.0 * t.ns * (2 * dR * dH + 2 * dR * dD) + 8 * dH * dD, WGRAD_ALL_CALL);
@@ -373,7 +387,8 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
        tc_wgrad3(st, lc, t.maps, t.ns, bn, rows, D, H, x_row_off, T_(h, grads, l.iW3), T_(h, grads, l.ib3),
                  tb.wg_scratch + 3 * wg_region, defer));
     }
-    if (reduce_jobs.n > 0)
+    if (tail) tail->jobs = reduce_jobs;
+    else if (reduce_jobs.n > 0)
       PH("sum of the split-K weight-gradient slices (one launch)", 0, 0, tc_wgrad_reduce_all(st, lc, reduce_jobs));
     return VAEB_OK;
   }
@@ -446,6 +461,10 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   if (tcl) {
     PH("dz da1.W1^T + dmu,dls [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * dH + dZ * dH) + 28 * dR * dZ,
        tc_dz_dprep(st, lc, t.maps, t.ns, R, H, Z, la, w, s.z, s.eps, s.mu, s.ls, s.dmu, s.dls, tb.ddh, tb.ddl, tb.ldq));
+    if (tail) {
+      tail->partial = s.partial; tail->n_tiles = tiles; tail->aux_part = nullptr; tail->n_aux = 0; tail->row_aux = s.row_aux;
+      tail->rows = rows;
+    } else
     PH("bound (per row + total)", 0, 4 * (dR * tiles + 2 * dr),
        launch_finalize(st, lc, s.partial, tiles, s.row_aux, rows, L, s.per_row, bo.base_out, bo.mult, bo.tprior,
                        bo.n_tprior, bo.div, bo.scalar_out, h->d_counter, s.dec_aux));   // dec_aux: idle outside the IS path
@@ -486,7 +505,8 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   else
     PH("wgrad W3,b3", 2 * dr * dD * dH, 4 * (dr * dD + dr * dH + dD * dH),
        launch_wgrad(st, lc, x, rows, D, s.da3, H, T_(h, grads, l.iW3), T_(h, grads, l.ib3)));
-  if (reduce_jobs.n > 0)
+  if (tail && tail->rows > 0) tail->jobs = reduce_jobs;
+  else if (reduce_jobs.n > 0)
     PH("sum of the split-K weight-gradient slices (one launch)", 0, 0, tc_wgrad_reduce_all(st, lc, reduce_jobs));
   return VAEB_OK;
 }
@@ -522,7 +542,7 @@ int all_reduce_grads(vaeb_handle* h) {
 // One update on device-resident rows; the scalar lands in d_scalars[slot].
 int enqueue_update(vaeb_handle* h, const float* d_xrows, int rows, const float* d_eps, const float* d_zeta,
                    int slot, bool apply) {
-  if (apply) h->steptc.mirrors_valid = false;       // the parameters change behind the step kernel's bf16 mirrors
+  if (apply) h->steptc.mirrors_valid = false; h->tc.weights_ready = false;       // the parameters change behind the step kernel's bf16 mirrors
   const Layout& l = h->lay;
   const int L = h->L;
   VAEB_TRY(ensure_ws(h, rows, (int64_t)rows * L, true));
@@ -537,9 +557,54 @@ int enqueue_update(vaeb_handle* h, const float* d_xrows, int rows, const float* 
     const float w = fb ? 1.0f / Mg : 1.0f;
     const bool dp = h->world > 1;
     BoundOut bo{base, 1.0f, nullptr, 0, Mg, dp ? nullptr : h->d_scalars + slot};
-    VAEB_TRY(forward_backward(h, h->d_params, d_xrows, rows, L, true, w, src, h->d_grads, bo));
-    VAEB_TRY(all_reduce_grads(h));
     const float prior = fb ? 0.f : h->cfg.prior_scale;
+    // Large-batch tensor-core path: everything after the last GEMM is ONE launch (tc_tail.cu) -- and in data-parallel
+    // runs whose ranks mapped each other's buffers (vaeb_comm_p2p_attach) that launch is also the gradient all-reduce.
+    static const bool tail_off = getenv("VAEB_TC_TAIL") && getenv("VAEB_TC_TAIL")[0] == '0';      // measurement switch
+    TcTailArgs tail{};
+    const bool want_tail = apply && h->optimizer != VAEB_OPT_ADADELTA && h->tc.active && !tail_off && L == 1 &&
+                           (!dp || h->tc.p2p_ready);
+    VAEB_TRY(forward_backward(h, h->d_params, d_xrows, rows, L, true, w, src, h->d_grads, bo, want_tail ? &tail : nullptr));
+    if (tail.rows > 0) {
+      TcState& t = h->tc;
+      const TcBuffers& b = t.data;
+      if (!t.tail_bar) {
+        VAEB_CUDA(cudaMalloc((void**)&t.tail_bar, sizeof(unsigned int)));
+        VAEB_CUDA(cudaMemsetAsync(t.tail_bar, 0, sizeof(unsigned int), st));
+        t.tail_bar_count = 0;
+      }
+      if (t.n_sm == 0) VAEB_CUDA(cudaDeviceGetAttribute(&t.n_sm, cudaDevAttrMultiProcessorCount, h->cfg.device));
+      tail.params = h->d_params; tail.ada = h->d_ada; tail.grads = h->d_grads; tail.padded = l.padded;
+      tail.lr = h->cfg.learning_rate; tail.eps = h->cfg.adagrad_eps; tail.prior = prior;
+      tail.p2 = fb ? h->cfg.learning_rate * 1e-6f : 0.f;
+      tail.per_row = h->ws.per_row; tail.block_part = h->ws.dec_aux; tail.base_out = base;
+      tail.mult = 1.0f; tail.div = Mg; tail.scalar_out = h->d_scalars + slot;
+      tail.w3h = b.w3h; tail.w3l = b.w3l; tail.w2h = b.w2h; tail.w2l = b.w2l; tail.w45h = b.w45h; tail.w45l = b.w45l;
+      tail.whh = b.whh; tail.whl = b.whl; tail.w1h = b.w1h; tail.w1l = b.w1l; tail.w45t = h->d_w45t;
+      tail.D = h->D; tail.H = h->H; tail.Z = h->Z; tail.ldh = b.ldh; tail.ldd = b.ldd; tail.ldq = b.ldq;
+      tail.oW3 = l.off[l.iW3]; tail.oW4 = l.off[l.iW4]; tail.oW5 = l.off[l.iW5]; tail.oW1 = l.off[l.iW1];
+      tail.oW2 = l.off[l.iW2];
+      tail.bar = t.tail_bar;
+      tail.world = h->world; tail.rank = h->rank;
+      for (int r = 0; r < h->world && dp; ++r) {
+        tail.gsum[r] = t.p2p_gsum[r]; tail.flags[r] = t.p2p_flags[r];
+        tail.peer_params[r] = t.p2p_params[r]; tail.peer_ada[r] = t.p2p_ada[r];
+      }
+      const int grid = tc_tail_grid(t.n_sm);
+      auto launch_tail = [&]() -> cudaError_t {
+        tail.bar_base = t.tail_bar_count;
+        tail.epoch = ++t.p2p_epoch;
+        t.tail_bar_count += (unsigned int)grid * (dp ? 2u : 1u);
+        return tc_tail_launch(st, lc, tail, grid);
+      };
+      PH("tail: slices -> gradient, bound, (all-reduce over peer memory,) prior + Adagrad, weight mirrors (one launch)", 0,
+         28.0 * (double)l.total, launch_tail());
+      h->tc.weights_ready = true;
+      h->grads_have_prior = false;
+      ++h->step;
+      return VAEB_OK;
+    }
+    VAEB_TRY(all_reduce_grads(h));
     if (apply && h->optimizer == VAEB_OPT_ADADELTA) {
       PH("adadelta+prior (flat)", 0, 28.0 * (double)l.total,
          launch_adadelta(st, lc, h->d_params, h->d_ada, h->d_ada2, h->d_grads, n4, h->rho, h->cfg.adagrad_eps, prior,
@@ -660,7 +725,7 @@ struct StateBackup {
     return e;
   }
   ~StateBackup() {
-    h->steptc.mirrors_valid = false;
+    h->steptc.mirrors_valid = false; h->tc.weights_ready = false;
     h->step = step0;
     h->launches = launches0;
     if (bp && ba) {
@@ -673,7 +738,8 @@ struct StateBackup {
   }
 };
 
-static int async_flush(vaeb_handle* h);   // launches streaming updates that were copied but not yet started
+static int async_flush(vaeb_handle* h);
+static void p2p_release(vaeb_handle* h);   // unmaps the peers' buffers (data parallel over peer memory)   // launches streaming updates that were copied but not yet started
 
 const char* vaeb_last_error(void) { return g_last_error.c_str(); }
 int vaeb_version(void) { return 100; }
@@ -737,6 +803,9 @@ int vaeb_destroy(vaeb_handle* h) {
   if (!h) return VAEB_OK;
   cudaSetDevice(h->cfg.device);
   cudaStreamSynchronize(h->stream);
+  p2p_release(h);
+  if (h->tc.chain_ready) cudaFree(h->tc.chain_ready);
+  if (h->tc.tail_bar) cudaFree(h->tc.tail_bar);
   if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
   free_ws(h->ws);
   float* bufs[] = {h->d_params, h->d_ada, h->d_grads, h->d_vmu, h->d_vsig, h->d_ada_mu, h->d_ada_sig, h->d_gmu,
@@ -819,7 +888,7 @@ int vaeb_set_tensors(vaeb_handle* h, int32_t which, const float* const* tensors)
   float* flat = flat_by_which(h, which);
   VAEB_REQUIRE(flat, "buffer not available for this estimator");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
-  h->steptc.mirrors_valid = false;
+  h->steptc.mirrors_valid = false; h->tc.weights_ready = false;
   for (int t = 0; t < h->lay.n; ++t) {
     const size_t n = (size_t)h->lay.rows[t] * h->lay.cols[t];
     VAEB_CUDA(cudaMemcpyAsync(flat + h->lay.off[t], tensors[t], n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
@@ -916,7 +985,7 @@ int vaeb_ae_train(vaeb_handle* h, int32_t kind, const int32_t* idx, int32_t n, f
   VAEB_REQUIRE(!(kind == VAEB_AE_VANILLA && h->cont), "the vanilla AE has sigmoid outputs only (vanilla-ae/ae.py:62-67)");
   VAEB_REQUIRE(h->L == 1 && !is_fvb(h) && h->world == 1, "AE baselines: L = 1, single GPU");
   if (!h->d_x) { vaeb_set_error("vaeb_ae_train before vaeb_upload_data"); return VAEB_ESTATE; }
-  h->steptc.mirrors_valid = false;
+  h->steptc.mirrors_valid = false; h->tc.weights_ready = false;
   for (int i = 0; i < n; ++i) VAEB_REQUIRE(idx[i] >= 0 && idx[i] < h->n_data, "row index outside the resident data");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
   const Layout& l = h->lay;
@@ -1182,7 +1251,7 @@ int vaeb_apply_update(vaeb_handle* h) {
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
   const bool fb = h->cfg.variant == VAEB_VARIANT_FULLBAYES;
   const float prior = (fb || h->grads_have_prior) ? 0.f : h->cfg.prior_scale;
-  h->steptc.mirrors_valid = false;
+  h->steptc.mirrors_valid = false; h->tc.weights_ready = false;
   VAEB_LAUNCH(launch_adagrad(h->stream, &h->launches, h->d_params, h->d_ada, h->d_grads, h->lay.padded / 4,
                              h->cfg.learning_rate, h->cfg.adagrad_eps, prior,
                              fb ? h->cfg.learning_rate * 1e-6f : 0.f, h->d_grads + h->lay.padded, 1.f, 1.f, nullptr));
@@ -1496,8 +1565,68 @@ int vaeb_comm_attach(vaeb_handle* h, const char* nccl_library, const uint8_t id[
   return VAEB_OK;
 }
 
+static void p2p_release(vaeb_handle* h) {
+  TcState& t = h->tc;
+  for (int i = 0; i < t.p2p_n_opened; ++i) cudaIpcCloseMemHandle(t.p2p_opened[i]);
+  t.p2p_n_opened = 0;
+  if (t.p2p_buf) cudaFree(t.p2p_buf);
+  t.p2p_buf = nullptr;
+  t.p2p_ready = false;
+}
+
+int vaeb_comm_p2p_export(vaeb_handle* h, uint8_t handles_out[192]) {
+  VAEB_REQUIRE(h && handles_out, "null argument");
+  VAEB_REQUIRE(h->world > 1 && h->world <= TC_MAX_PEERS, "attach the communicator first (2..8 ranks)");
+  VAEB_REQUIRE(!is_fvb(h), "full-VB estimators are single-GPU (replicas only)");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  VAEB_CUDA(cudaStreamSynchronize(h->stream));
+  TcState& t = h->tc;
+  p2p_release(h);
+  const size_t bytes = (size_t)(h->lay.padded + 4) * sizeof(float) + 2 * TC_MAX_PEERS * sizeof(unsigned int);
+  VAEB_CUDA(cudaMalloc((void**)&t.p2p_buf, bytes));
+  VAEB_CUDA(cudaMemset(t.p2p_buf, 0, bytes));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t hh[3];
+  VAEB_CUDA(cudaIpcGetMemHandle(&hh[0], t.p2p_buf));
+  VAEB_CUDA(cudaIpcGetMemHandle(&hh[1], h->d_params));
+  VAEB_CUDA(cudaIpcGetMemHandle(&hh[2], h->d_ada));
+  std::memcpy(handles_out, hh, 192);
+  return VAEB_OK;
+}
+
+int vaeb_comm_p2p_attach(vaeb_handle* h, const uint8_t* all_handles, int32_t world_size) {
+  VAEB_REQUIRE(h && all_handles, "null argument");
+  VAEB_REQUIRE(world_size == h->world && h->tc.p2p_buf, "vaeb_comm_p2p_export first, with the attached world size");
+  VAEB_CUDA(cudaSetDevice(h->cfg.device));
+  TcState& t = h->tc;
+  for (int r = 0; r < world_size; ++r) {
+    float *buf = t.p2p_buf, *par = h->d_params, *ada = h->d_ada;
+    if (r != h->rank) {
+      cudaIpcMemHandle_t hh[3];
+      std::memcpy(hh, all_handles + (size_t)r * 192, 192);
+      void* p[3] = {nullptr, nullptr, nullptr};
+      for (int q = 0; q < 3; ++q) {
+        VAEB_CUDA(cudaIpcOpenMemHandle(&p[q], hh[q], cudaIpcMemLazyEnablePeerAccess));
+        t.p2p_opened[t.p2p_n_opened++] = p[q];
+      }
+      buf = (float*)p[0]; par = (float*)p[1]; ada = (float*)p[2];
+    }
+    t.p2p_gsum[r] = buf;
+    t.p2p_flags[r] = reinterpret_cast<unsigned int*>(buf + h->lay.padded + 4);
+    t.p2p_params[r] = par;
+    t.p2p_ada[r] = ada;
+  }
+  t.p2p_epoch = 0;
+  t.p2p_ready = true;
+  return VAEB_OK;
+}
+
 int vaeb_comm_detach(vaeb_handle* h) {
   VAEB_REQUIRE(h, "null handle");
+  if (h->tc.p2p_buf || h->tc.p2p_n_opened) {
+    VAEB_CUDA(cudaStreamSynchronize(h->stream));
+    p2p_release(h);
+  }
   if (h->comm) {
     VAEB_CUDA(cudaStreamSynchronize(h->stream));
     h->nccl.CommDestroy(h->comm);

@@ -80,6 +80,13 @@ struct TcState {
   unsigned int* chain_ready = nullptr; int chain_ready_cap = 0; unsigned int chain_epoch = 0;
   int64_t chain_key_rows = -1; int chain_key_bn = 0;
   int n_sm = 0;
+  // the fused tail of an update (tc_tail.cu)
+  bool weights_ready = false;              // the weight mirrors hold the CURRENT parameters (written by the tail)
+  unsigned int* tail_bar = nullptr; unsigned int tail_bar_count = 0;
+  // data parallel over peer memory: this rank's comm buffer [padded + 4 floats | 2 * world flags], everybody's mappings
+  float* p2p_buf = nullptr; bool p2p_ready = false; unsigned int p2p_epoch = 0;
+  float* p2p_gsum[8] = {}; unsigned int* p2p_flags[8] = {}; float* p2p_params[8] = {}; float* p2p_ada[8] = {};
+  void* p2p_opened[24] = {}; int p2p_n_opened = 0;
 };
 
 // State of the fused single-launch step (fused_step.cu).

@@ -1714,6 +1714,7 @@ int step_tc_launch(vaeb_handle* h, const int* d_order, const float* d_xrows, int
   StepTcState& s = h->steptc;
   const Layout& l = h->lay;
   const int D = h->D, H = h->H, Z = h->Z;
+  h->tc.weights_ready = false;        // this kernel updates the parameters behind the large-batch path's mirrors
   if (!s.ready) {
     VAEB_TRY(step_tc_init(h));
     if (s.unavailable) { vaeb_set_error("step_tc: thread-block clusters of 4 are not available on this device"); return VAEB_ESTATE; }

@@ -123,3 +123,25 @@ cudaError_t tc_wgrad_all(cudaStream_t st, int64_t* launches, const TcMaps& m, in
                          int Z, int x_row_off, float* gW2, float* gb2, float* gW1, float* gb1, float* gW4, float* gb4,
                          float* gW5, float* gb5, float* gW3, float* gb3, float* scratch, size_t region, TcReduceJobs* jobs,
                          int n_sm);
+
+// ---- the tail of a large-batch update as one launch (tc_tail.cu) --------------------------------------------------
+// split-K slices -> gradient, bound, (N GPUs: reduce-scatter + all-gather over peer memory), prior + Adagrad, weight mirrors
+constexpr int TC_MAX_PEERS = 8;
+struct TcTailArgs {
+  TcReduceJobs jobs;
+  float* params; float* ada; float* grads; int64_t padded;
+  float lr, eps, prior, p2;
+  // bound: partial[rows, n_tiles] + (aux_part[rows, n_aux] or row_aux[rows])
+  const float* partial; int n_tiles; const float* aux_part; int n_aux; const float* row_aux; int rows;
+  float* per_row; float* block_part; float* base_out; float mult, div; float* scalar_out;
+  // weight mirrors (w3h == nullptr: none)
+  void *w3h, *w3l, *w2h, *w2l, *w45h, *w45l, *whh, *whl, *w1h, *w1l; float* w45t;
+  int D, H, Z, ldh, ldd, ldq; int64_t oW3, oW4, oW5, oW1, oW2;
+  // grid barrier (monotonic counter; bar_base = arrivals before this launch)
+  unsigned int* bar; unsigned int bar_base;
+  // data parallel over peer memory (world == 1: unused)
+  int world, rank; unsigned int epoch;
+  float* gsum[TC_MAX_PEERS]; unsigned int* flags[TC_MAX_PEERS]; float* peer_params[TC_MAX_PEERS]; float* peer_ada[TC_MAX_PEERS];
+};
+int tc_tail_grid(int n_sm);
+cudaError_t tc_tail_launch(cudaStream_t st, int64_t* launches, const TcTailArgs& a, int grid);

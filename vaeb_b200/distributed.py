@@ -29,6 +29,14 @@ def attach_data_parallel(model):
     uid = comm_unique_id() if rank == 0 else None
     uid = broadcast_bytes(uid, 0)
     model.attach_comm(uid, rank, world)
+    # ranks of one box map each other's buffers (CUDA IPC over NVLink): the tail kernel of a large-batch tensor-core
+    # update then IS the gradient all-reduce (vaeb_comm_p2p_attach); VAEB_DP_P2P=0 keeps ncclAllReduce
+    if world > 1 and os.environ.get("VAEB_DP_P2P", "1") != "0" and getattr(model, "precision", "fp32") != "fp32":
+        mine = model.p2p_export()
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        model.p2p_attach(handles)
+        dist.barrier()
     return rank, world
 
 

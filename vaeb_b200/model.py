@@ -112,6 +112,7 @@ class VAEB(object):
         self.srng = RandomStreams(seed=10)              # VAEB.py:158
         self._eps_nodes = [self.srng.new_node() for _ in range(L)]
 
+        self.precision = precision
         self._lib = _lib.load()
         cfg = _lib.Config(
             input_dim=self.input_size, hidden_units=hidden_units, latent_size=latent_size, batch_size=batch_size,
@@ -384,6 +385,18 @@ class VAEB(object):
         path = (nccl_library or _lib.nccl_library_path()).encode()
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
         _lib.check(self._lib.vaeb_comm_attach(self._h, path, buf, rank, world_size))
+
+    def p2p_export(self):
+        """CUDA IPC handles (192 bytes) of this rank's gradient staging buffer, parameters and accumulators."""
+        buf = (C.c_uint8 * 192)()
+        _lib.check(self._lib.vaeb_comm_p2p_export(self._h, buf))
+        return bytes(buf)
+
+    def p2p_attach(self, all_handles):
+        """`all_handles`: the p2p_export() bytes of every rank, in rank order."""
+        blob = b"".join(all_handles)
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _lib.check(self._lib.vaeb_comm_p2p_attach(self._h, buf, len(all_handles)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
