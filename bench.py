@@ -463,7 +463,12 @@ def run_own(args):
                            "l2": "inputs larger than L2: %d minibatches (%.0f MB) resident per GPU, visited in turn"
                                  % (nb3, per * nb3 * D * 4 / 1e6),
                            "eps": "Philox4x32-10 on device", "precision": args.precision,
-                           "collective": "ncclAllReduce(sum) of the flat gradient + bound" if world > 1 else "none (1 GPU)"},
+                           "collective": ("none (1 GPU)" if world == 1 else
+                                          "ncclAllReduce(sum) of the flat gradient + bound" if os.environ.get("VAEB_DP_P2P", "1") == "0" else
+                                          "inside the tail kernel, over peer memory (CUDA IPC / NVLink): reduce-scatter by peer "
+                                          "loads, prior + Adagrad on the owner's slice, all-gather by peer stores (tc_tail.cu)"),
+                           "launch_structure": "seven layer launches (VAEB_TC_CHAIN=1: one chain launch, tc_chain.cu), one weight-"
+                                               "gradient launch up to 4096 rows per GPU (four above), one tail launch (tc_tail.cu)"},
                 "clocks": clocks_summary, "warmup_probe_ms_per_step": probe_ms_per_step,
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": per * D * 4 * world, "d2h_bytes_per_step": 4 * world,
                         "steps": Ke, "ms_per_step": ms_e2e / Ke,

@@ -38,6 +38,7 @@ struct PhaseProf {
   std::vector<double> flops, bytes;
 };
 static thread_local PhaseProf* g_prof = nullptr;
+static long long* g_tail_stamps = nullptr;   // debug (VAEB_TAIL_STAMPS)
 
 #define PH(NAME, FLOPS, BYTES, EXPR)                                                   \
   do {                                                                                 \
@@ -270,12 +271,12 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
     bna = tc_act_bn(rows, std::min(H, D));
     static const int env_bn = getenv("VAEB_TC_BN") ? atoi(getenv("VAEB_TC_BN")) : 0;     // measurement switch
     if (env_bn == 64 || env_bn == 128 || env_bn == 256) bna = env_bn;
-    // the activation chain as ONE launch (tc_chain.cu): large-batch training steps of the Bernoulli model.  In its CTA-pair
-    // form (cta_group::2) a CTA stages half of a 256-wide B tile: the maps carry 128-wide boxes.
+    // the activation chain as ONE launch (tc_chain.cu, VAEB_TC_CHAIN=1): large-batch training steps of the Bernoulli model.
+    // In its CTA-pair form (cta_group::2) a CTA stages half of a 256-wide B tile: the maps carry 128-wide boxes.
     static const int env_chain = getenv("VAEB_TC_CHAIN") ? atoi(getenv("VAEB_TC_CHAIN")) : -1;   // measurement switches
     static const int env_pair = getenv("VAEB_TC_PAIR") ? atoi(getenv("VAEB_TC_PAIR")) : -1;
     chain = want_grads && !h->cont && L == 1 && latent_large_batch(rows, H, Z, L) && 4 * ((2 * Z + 63) / 64) <= Z &&
-            (env_chain >= 0 ? env_chain != 0 : rows >= 16384);
+            env_chain > 0;      // measured: not faster than the seven layer launches at any size -> opt-in
     chain_pair = chain && (env_pair >= 0 ? env_pair != 0 : rows >= 4096);
     if (chain_pair) bna = 128;
     // Programmatic dependent launch for the one-tile-per-CTA kernels: bf16x3 (one CTA per SM: an early dependent grid
@@ -591,7 +592,15 @@ int enqueue_update(vaeb_handle* h, const float* d_xrows, int rows, const float* 
         tail.peer_params[r] = t.p2p_params[r]; tail.peer_ada[r] = t.p2p_ada[r];
       }
       const int grid = tc_tail_grid(t.n_sm);
+      static const char* stamp_path = getenv("VAEB_TAIL_STAMPS");      // debug: time stamps of the last 2048 tail launches
+      static long long* d_stamps = nullptr;
+      if (stamp_path && !d_stamps) {
+        VAEB_CUDA(cudaMalloc((void**)&d_stamps, 2048 * 8 * sizeof(long long)));
+        VAEB_CUDA(cudaMemset(d_stamps, 0, 2048 * 8 * sizeof(long long)));
+        g_tail_stamps = d_stamps;
+      }
       auto launch_tail = [&]() -> cudaError_t {
+        tail.stamps = d_stamps ? d_stamps + 8 * (size_t)(t.p2p_epoch % 2048) : nullptr;
         tail.bar_base = t.tail_bar_count;
         tail.epoch = ++t.p2p_epoch;
         t.tail_bar_count += (unsigned int)grid * (dp ? 2u : 1u);
@@ -1567,6 +1576,13 @@ int vaeb_comm_attach(vaeb_handle* h, const char* nccl_library, const uint8_t id[
 
 static void p2p_release(vaeb_handle* h) {
   TcState& t = h->tc;
+  if (g_tail_stamps && getenv("VAEB_TAIL_STAMPS")) {      // debug dump: <path>.<rank>
+    std::vector<long long> hs(2048 * 8);
+    cudaDeviceSynchronize();
+    cudaMemcpy(hs.data(), g_tail_stamps, hs.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    const std::string fn = std::string(getenv("VAEB_TAIL_STAMPS")) + "." + std::to_string(h->rank);
+    if (FILE* f = fopen(fn.c_str(), "wb")) { fwrite(hs.data(), sizeof(long long), hs.size(), f); fclose(f); }
+  }
   for (int i = 0; i < t.p2p_n_opened; ++i) cudaIpcCloseMemHandle(t.p2p_opened[i]);
   t.p2p_n_opened = 0;
   if (t.p2p_buf) cudaFree(t.p2p_buf);

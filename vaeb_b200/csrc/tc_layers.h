@@ -142,6 +142,7 @@ struct TcTailArgs {
   // data parallel over peer memory (world == 1: unused)
   int world, rank; unsigned int epoch;
   float* gsum[TC_MAX_PEERS]; unsigned int* flags[TC_MAX_PEERS]; float* peer_params[TC_MAX_PEERS]; float* peer_ada[TC_MAX_PEERS];
+  long long* stamps;       // debug (VAEB_TAIL_STAMPS): 8 %globaltimer values of this launch, written by block 0
 };
 int tc_tail_grid(int n_sm);
 cudaError_t tc_tail_launch(cudaStream_t st, int64_t* launches, const TcTailArgs& a, int grid);

@@ -33,17 +33,21 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+// flag stores: ONE system-scope fence, then relaxed stores to every peer (a st.release.sys per peer would wait for the
+// acknowledgement of the previous remote store each time: ~2.5 us x 8 peers, measured)
+__device__ __forceinline__ void st_relaxed_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ float4 ld_peer4(const float* p) {      // another GPU's memory: never through L1
+// another GPU's memory: system-scope relaxed loads (never served by L1; unlike ld.volatile they are not ordered among
+// themselves, so eight of them overlap -- with ld.volatile the eight peers' loads of P2 took 8 x 2.2 us)
+__device__ __forceinline__ float4 ld_peer4(const float* p) {
   float4 v;
-  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  asm("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ float ld_peer1(const float* p) {
   float v;
-  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
 
@@ -91,9 +95,18 @@ __device__ __forceinline__ void put_pair(__nv_bfloat16* hi, __nv_bfloat16* lo, s
   if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
+__device__ __forceinline__ void stamp(const TcTailArgs& a, int k) {
+  if (a.stamps && blockIdx.x == 0 && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.stamps[k] = t;
+  }
+}
+
 __global__ void __launch_bounds__(TAIL_THREADS)
 tc_tail_kernel(const TcTailArgs a) {
   __shared__ float red[32];
+  stamp(a, 0);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
   unsigned int bar_target = a.bar_base;
@@ -187,8 +200,10 @@ tc_tail_kernel(const TcTailArgs a) {
   }
   const float bs = block_sum(v, red);
   if (threadIdx.x == 0) a.block_part[blockIdx.x] = bs;
+  stamp(a, 1);
   bar_target += gridDim.x;
   grid_barrier(a.bar, bar_target);
+  stamp(a, 2);
 
   // total bound of this rank: block 0, fixed order
   float base = 0.f;
@@ -202,8 +217,13 @@ tc_tail_kernel(const TcTailArgs a) {
         if (a.scalar_out) *a.scalar_out = (a.mult * base) / a.div;
       } else {
         a.gsum[a.rank][a.padded] = base;              // travels with the gradient
+      }
+    }
+    if (dp) {                                         // "staged": thread r tells peer r
+      __syncthreads();
+      if (threadIdx.x < a.world) {
         __threadfence_system();
-        for (int r = 0; r < a.world; ++r) st_release_sys(a.flags[r] + a.rank, a.epoch);      // "staged"
+        st_relaxed_sys(a.flags[threadIdx.x] + a.rank, a.epoch);
       }
     }
   }
@@ -219,15 +239,20 @@ tc_tail_kernel(const TcTailArgs a) {
       }
     }
     __syncthreads();
+    stamp(a, 3);
     const int64_t n4 = a.padded / 4;
     const int64_t per = (n4 + a.world - 1) / a.world;
     const int64_t lo = per * a.rank, hi = lo + per < n4 ? lo + per : n4;
     for (int64_t i = lo + tid; i < hi; i += nth) {
+      // every peer's copy of the four elements is requested before the first one is used (a remote load is ~2.5 us)
+      float4 t[TC_MAX_PEERS];
+#pragma unroll
+      for (int r = 0; r < TC_MAX_PEERS; ++r)
+        if (r < a.world) t[r] = ld_peer4(a.gsum[r] + 4 * i);
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < a.world; ++r) {
-        const float4 t = ld_peer4(a.gsum[r] + 4 * i);
-        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
-      }
+#pragma unroll
+      for (int r = 0; r < TC_MAX_PEERS; ++r)
+        if (r < a.world) { g.x += t[r].x; g.y += t[r].y; g.z += t[r].z; g.w += t[r].w; }
       float4 p = reinterpret_cast<const float4*>(a.params)[i], ac = reinterpret_cast<const float4*>(a.ada)[i];
       adagrad_one(p.x, ac.x, g.x, a.lr, a.eps, a.prior, a.p2);
       adagrad_one(p.y, ac.y, g.y, a.lr, a.eps, a.prior, a.p2);
@@ -244,11 +269,13 @@ tc_tail_kernel(const TcTailArgs a) {
       *a.scalar_out = (a.mult * t) / a.div;
     }
     __threadfence_system();
+    stamp(a, 4);
     bar_target += gridDim.x;
     grid_barrier(a.bar, bar_target);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    stamp(a, 5);
+    if (blockIdx.x == 0 && threadIdx.x < a.world) {      // "my slice is everywhere": thread r tells peer r
       __threadfence_system();
-      for (int r = 0; r < a.world; ++r) st_release_sys(a.flags[r] + a.world + a.rank, a.epoch);   // "my slice is everywhere"
+      st_relaxed_sys(a.flags[threadIdx.x] + a.world + a.rank, a.epoch);
     }
     if (threadIdx.x == 0) {
       for (int r = 0; r < a.world; ++r) {
@@ -259,6 +286,7 @@ tc_tail_kernel(const TcTailArgs a) {
       }
     }
     __syncthreads();
+    stamp(a, 6);
   }
 
   // ---- P3: bf16 (hi, lo) operand mirrors of the new weights, in the layouts the TMA maps of the next step read --------
@@ -298,6 +326,7 @@ tc_tail_kernel(const TcTailArgs a) {
   mirror(W3, w3h, w3l, D, H, a.ldh);
   mirror(W2, w2h, w2l, H, D, a.ldd);
   mirror(W1, w1h, w1l, Z, H, a.ldh);
+  stamp(a, 7);
   for (int i = t32; i < H * Z; i += n32) {      // W4[k, j], W5[k, j]
     const int k = i / Z, j = i - k * Z;
     const float v4 = __ldcg(W4 + i), v5 = __ldcg(W5 + i);
