@@ -20,7 +20,7 @@ VARIANTS = [
     ("layers", {"VAEB_TC_CHAIN": "0"}),
     ("wgrad-separate", {"VAEB_TC_WGRAD_MERGE": "0"}),
     ("wgrad-merged", {"VAEB_TC_WGRAD_MERGE": "1"}),
-    ("tail-separate", {"VAEB_TC_TAIL": "0"}),
+    ("tail-fused", {"VAEB_TC_TAIL": "1"}),
 ]
 
 
@@ -53,6 +53,6 @@ def test_launch_structures_agree(tmp_path, prec, rows):
             # Adagrad's first steps are lr * sign(g) where |g| is tiny: compare on the tensor's scale
             assert np.abs(a - b).max() <= (2e-3 if prec == "bf16x3" else 5e-2) * scale, (name, k, np.abs(a - b).max(), scale)
     # fewer launches is the point of the fused structures
-    chain = _run(tmp_path, "chain-count", {"VAEB_TC_CHAIN": "1", "VAEB_TC_WGRAD_MERGE": "1"}, prec, rows)
+    chain = _run(tmp_path, "chain-count", {"VAEB_TC_CHAIN": "1", "VAEB_TC_WGRAD_MERGE": "1", "VAEB_TC_TAIL": "1"}, prec, rows)
     layers = _run(tmp_path, "layers-count", {"VAEB_TC_CHAIN": "0", "VAEB_TC_WGRAD_MERGE": "0", "VAEB_TC_TAIL": "0"}, prec, rows)
     assert int(chain["launches"]) < int(layers["launches"])

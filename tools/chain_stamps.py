@@ -25,6 +25,9 @@ for l in range(nl):
     print("%-6s items %4d  dep met %7.1f..%7.1f  acc ready %7.1f..%7.1f  done %7.1f..%7.1f | load+mma %5.1f (med) epilogue %5.1f (med)"
           % (names[l], len(a), dep.min(), dep.max(), acc.min(), acc.max(), done.min(), done.max(),
              np.median(acc - dep), np.median(done - acc)))
+    if (a[:, 7] > 0).all():
+        print("         MMA thread: operands of the first k block ready -> all MMAs complete %5.2f (median, us); epilogue start - MMA complete %5.2f"
+              % (np.median(a[:, 7] - a[:, 6]) / 1e3, np.median(a[:, 1] - a[:, 7]) / 1e3))
     print("         epilogue warp 4: wait for the accumulator %5.2f  chunks %5.2f  published after %5.2f (medians, us)"
           % (np.median(a[:, 1] - a[:, 4]) / 1e3, np.median(a[:, 2] - a[:, 1]) / 1e3, np.median(a[:, 5] - a[:, 2]) / 1e3))
 # per CTA: busy vs idle

@@ -263,6 +263,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   const bool tcp = h->tc.active;
   TcState& t = h->tc;
   int x_row_off = 0, bn = 64, bna = 64;   // UMMA N of the weight-gradient / of the activation layers
+  int bnd = 64;                           // ... of dec2 (D wide: more column tiles per row block than the H-wide layers)
   bool chain = false, chain_pair = false;
   const void *x_mirror_hi = nullptr, *x_mirror_lo = nullptr;
   if (tcp) {
@@ -279,6 +280,15 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
             env_chain > 0;      // measured: not faster than the seven layer launches at any size -> opt-in
     chain_pair = chain && (env_pair >= 0 ? env_pair != 0 : rows >= 4096);
     if (chain_pair) bna = 128;
+    bnd = bna;
+    // few row blocks (the data-parallel split): one tile per CTA, and a layer should fill most of the SMs in ONE wave --
+    // 64-wide tiles for the H-wide layers when 128-wide ones give fewer than 96 CTAs (2048 rows: 64 -> 128 CTAs, enc1
+    // 14.5 -> 12.2 us, dgrad 15.6 -> 13.1), dec2 keeps 128 (7 column tiles per row block: 112 CTAs)
+    if (bna == 128 && env_bn == 0 && !chain) {
+      const int rb = (rows + 127) / 128;
+      if (rb * ((H + 127) / 128) < 96) bna = 64;
+      if (rb * ((D + 127) / 128) < 96) bnd = 64;
+    }
     // Programmatic dependent launch for the one-tile-per-CTA kernels: bf16x3 (one CTA per SM: an early dependent grid
     // never takes slots from the running one; 16384 rows: 523 -> 499 us per update) and, in plain bf16, whenever the
     // activation layers are NOT in the persistent form (8192 rows: 215 -> 196 us); next to the persistent kernels the
@@ -305,9 +315,9 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
       rows_data = rows;
     }
     x_mirror_hi = b.xh; x_mirror_lo = t.ns == 2 ? b.xl : nullptr;
-    if (t.key_rows != rows || t.key_R != R || t.key_data != rows_data || t.key_bn != bna * 1024 + bn || t.key_x != b.xh) {
-      VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bna, Z, bn));
-      t.key_rows = rows; t.key_R = R; t.key_data = rows_data; t.key_bn = bna * 1024 + bn; t.key_x = b.xh;
+    if (t.key_rows != rows || t.key_R != R || t.key_data != rows_data || t.key_bn != (bna * 1024 + bn) * 1024 + bnd || t.key_x != b.xh) {
+      VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bna, Z, bn, bnd));
+      t.key_rows = rows; t.key_R = R; t.key_data = rows_data; t.key_bn = (bna * 1024 + bn) * 1024 + bnd; t.key_x = b.xh;
     }
     if (want_grads && b.heh && b.zh && b.d1h && b.ddh && latent_large_batch(rows, H, Z, L) && t.weights_ready &&
         theta == h->d_params) {
@@ -427,7 +437,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   if (tcp)
     PH("dec2 h.W2+loglik [tcgen05]", 2 * dR * dH * dD,
        2.0 * t.ns * (dR * dH + dH * dD) + 4 * dr * dD + (want_grads ? 2.0 * t.ns * dR * dD : 0.0),
-       tc_dec2_bernoulli(st, lc, t.maps, t.ns, bna, R, H, D, T_(h, theta, l.ib2), tcl ? nullptr : x, 1, rows, scale,
+       tc_dec2_bernoulli(st, lc, t.maps, t.ns, bnd, R, H, D, T_(h, theta, l.ib2), tcl ? nullptr : x, 1, rows, scale,
                          want_grads ? tb.da2h : nullptr, want_grads ? tb.da2l : nullptr, tb.ldd, s.partial, &tiles,
                          x_mirror_hi, x_mirror_lo, tb.ldx, x_row_off));   // tcl: x from the mirror enc1 reads
   else
@@ -561,10 +571,12 @@ int enqueue_update(vaeb_handle* h, const float* d_xrows, int rows, const float* 
     const float prior = fb ? 0.f : h->cfg.prior_scale;
     // Large-batch tensor-core path: everything after the last GEMM is ONE launch (tc_tail.cu) -- and in data-parallel
     // runs whose ranks mapped each other's buffers (vaeb_comm_p2p_attach) that launch is also the gradient all-reduce.
-    static const bool tail_off = getenv("VAEB_TC_TAIL") && getenv("VAEB_TC_TAIL")[0] == '0';      // measurement switch
+    // On one GPU it measures equal to the five separate launches up to 4096 rows and ~10 us slower at 16384 (their launch
+    // latencies overlap, its grid barrier does not), so it serves the data-parallel case; VAEB_TC_TAIL=1 / 0 forces it.
+    static const int env_tail = getenv("VAEB_TC_TAIL") ? atoi(getenv("VAEB_TC_TAIL")) : -1;      // measurement switch
     TcTailArgs tail{};
-    const bool want_tail = apply && h->optimizer != VAEB_OPT_ADADELTA && h->tc.active && !tail_off && L == 1 &&
-                           (!dp || h->tc.p2p_ready);
+    const bool want_tail = apply && h->optimizer != VAEB_OPT_ADADELTA && h->tc.active && L == 1 &&
+                           (dp ? (h->tc.p2p_ready && env_tail != 0) : env_tail > 0);
     VAEB_TRY(forward_backward(h, h->d_params, d_xrows, rows, L, true, w, src, h->d_grads, bo, want_tail ? &tail : nullptr));
     if (tail.rows > 0) {
       TcState& t = h->tc;

@@ -52,6 +52,9 @@ struct ChainArgs {
   unsigned int epoch;           // this launch's number (1, 2, ...): a row block is complete at epoch * dep_count
   int stages, stage_bytes;      // operand ring of this launch
   long long* stamps;            // debug (VAEB_CHAIN_STAMPS): per item {dependency met, accumulator complete, stores done, SM}
+  int throttle;                 // measurement switch (VAEB_CHAIN_THROTTLE): the MMA thread waits for a stage's MMAs before the next stage
+  int ld32;                     // measurement switch (VAEB_CHAIN_LD32): 32 accumulator columns per TMEM read in the epilogue
+  int diag;                     // debug (VAEB_CHAIN_DIAG): the MMA thread also waits for each item's accumulator and stamps it
 };
 
 // Operand ring: a stage holds NS x (A 128 x 64 | B bn_max x 64) bf16; the ring takes 192 KB whatever bn_max is, so a launch
@@ -186,11 +189,45 @@ __device__ __forceinline__ void chain_epi_tile(Epi& epi, uint32_t acc, uint64_t*
   epi.end(row, ok, tn * (EPI_WARPS / 4) + cs, tiles_n * (EPI_WARPS / 4));
 }
 
+// the same with 32 accumulator columns per TMEM read (BN >= 128): half as many tcgen05.ld per tile
+template <class Epi, int BN, bool PAIR = false>
+__device__ __forceinline__ void chain_epi_tile32(Epi& epi, uint32_t acc, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                                 uint32_t use, int tm, int tn, int tiles_n, int M, int N, int q, int cs,
+                                                 int lane) {
+  constexpr int SLICE = BN / (EPI_WARPS / 4);
+  constexpr int NCH = SLICE / 32;
+  const int n0 = tn * BN;
+  const int row = tm * BM + q * 32 + lane;
+  const bool ok = row < M;
+  epi.begin();
+  tc::mbar_wait(tmem_full, use & 1);
+  tc::tc_fence_after();
+#pragma unroll 1
+  for (int i = 0; i < NCH; ++i) {
+    const int c = cs * SLICE + 32 * i;
+    float v[32];
+    tc::tmem_ld32(acc + (uint32_t)c, v);
+    tc::tmem_ld_wait();
+    if (i == NCH - 1) {
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_even_cta(tmem_empty); else tc::mbar_arrive(tmem_empty);
+      }
+    }
+    if (n0 + c < N) epi.chunk(row, ok, n0 + c, N, v);
+    if (n0 + c + 16 < N) epi.chunk(row, ok, n0 + c + 16, N, v + 16);
+  }
+  epi.end(row, ok, tn * (EPI_WARPS / 4) + cs, tiles_n * (EPI_WARPS / 4));
+}
+
 template <bool PAIR, class Epi>
 __device__ __forceinline__ void chain_epi(Epi epi, int bn, uint32_t acc, uint64_t* tmem_full, uint64_t* tmem_empty,
                                           uint32_t use, int tm, int tn, int tiles_n, int M, int N, int q, int cs,
                                           int lane) {
-  if (PAIR || bn == 256)      // the pair form runs its wide layers 256 wide only
+  if (bn < 0)                 // (measurement switch: 32 columns per TMEM read, 256-wide tiles)
+    chain_epi_tile32<Epi, 256, PAIR>(epi, acc, tmem_full, tmem_empty, use, tm, tn, tiles_n, M, N, q, cs, lane);
+  else if (PAIR || bn == 256)      // the pair form runs its wide layers 256 wide only
     chain_epi_tile<Epi, 256, PAIR>(epi, acc, tmem_full, tmem_empty, use, tm, tn, tiles_n, M, N, q, cs, lane);
   else if (bn == 128) chain_epi_tile<Epi, 128, PAIR>(epi, acc, tmem_full, tmem_empty, use, tm, tn, tiles_n, M, N, q, cs, lane);
   else chain_epi_tile<Epi, 64, PAIR>(epi, acc, tmem_full, tmem_empty, use, tm, tn, tiles_n, M, N, q, cs, lane);
@@ -324,6 +361,7 @@ tc_chain_kernel(const __grid_constant__ ChainArgs args) {
       for (int kb = 0; kb < nkb; ++kb) {
         tc::mbar_wait(&full[s], ph);
         tc::tc_fence_after();
+        if (kb == 0 && args.stamps) args.stamps[8 * (size_t)(PAIR ? 2 * g + rank : g) + 6] = gtimer();
         const uint32_t a = smem0 + (uint32_t)s * stage_bytes;
         const uint32_t b = a + NS * CH_A_BYTES;
         uint64_t dah = a_bits | (uint64_t)((a & 0x3FFFFu) >> 4), dbh = b_bits | (uint64_t)((b & 0x3FFFFu) >> 4);
@@ -350,9 +388,14 @@ tc_chain_kernel(const __grid_constant__ ChainArgs args) {
           dah += 2; dbh += b_step;
         }
         if constexpr (PAIR) umma_commit_2(&empty[s]); else tc::umma_commit(&empty[s]);
+        if (args.throttle) tc::mbar_wait(&empty[s], ph);      // (measurement) at most one stage of MMAs in the tensor pipe's queue
         if (++s == stages) { s = 0; ph ^= 1; }
       }
       if constexpr (PAIR) umma_commit_2(&tmem_full[buf]); else tc::umma_commit(&tmem_full[buf]);
+      if (args.stamps && args.diag) {                  // debug: when this item's MMAs really completed
+        tc::mbar_wait(&tmem_full[buf], use & 1);
+        args.stamps[8 * (size_t)(PAIR ? 2 * g + rank : g) + 7] = gtimer();
+      }
     }
   } else if (warp >= 3) {
     // ===== epilogue: warp w reads TMEM lane quarter w % 4 (the hardware's rule), column slice (w - 3) / 4 of the tile =====
@@ -375,7 +418,7 @@ tc_chain_kernel(const __grid_constant__ ChainArgs args) {
       }
       switch (L.kind) {
         case CK_TANH:
-          chain_epi<PAIR>(args.tanh_[L.epi], L.bn, acc, tf, te, use, tm, tn, L.tiles_n, L.M, L.N, q, cs, lane);
+          chain_epi<PAIR>(args.tanh_[L.epi], (args.ld32 && L.bn == 256) ? -256 : L.bn, acc, tf, te, use, tm, tn, L.tiles_n, L.M, L.N, q, cs, lane);
           break;
         case CK_HEADS: {                                 // enc2 and dz are always 64 wide
           EpiHeads e = args.heads;
@@ -383,10 +426,10 @@ tc_chain_kernel(const __grid_constant__ ChainArgs args) {
           break;
         }
         case CK_BERN:
-          chain_epi<PAIR>(args.bern, L.bn, acc, tf, te, use, tm, tn, L.tiles_n, L.M, L.N, q, cs, lane);
+          chain_epi<PAIR>(args.bern, (args.ld32 && L.bn == 256) ? -256 : L.bn, acc, tf, te, use, tm, tn, L.tiles_n, L.M, L.N, q, cs, lane);
           break;
         case CK_DGRAD:
-          chain_epi<PAIR>(args.dgrad[L.epi], L.bn, acc, tf, te, use, tm, tn, L.tiles_n, L.M, L.N, q, cs, lane);
+          chain_epi<PAIR>(args.dgrad[L.epi], (args.ld32 && L.bn == 256) ? -256 : L.bn, acc, tf, te, use, tm, tn, L.tiles_n, L.M, L.N, q, cs, lane);
           break;
         default: {
           EpiDzPrep e = args.dz;
@@ -455,14 +498,15 @@ cudaError_t tc_chain_step(cudaStream_t st, int64_t* launches, const TcMaps& m, i
                 *da3h = (__nv_bfloat16*)b.da3h, *da3l = (__nv_bfloat16*)b.da3l;
   // layer 0 enc1: h_e = tanh(x.W3 + b3)                                   VAEB.py:246
   fill_layer(a.layer[0], m.enc1, rows, H, D, bn, 1, x_row_off, CK_TANH, 0, -1);
-  a.tanh_[0] = EpiTanh{b3, nullptr, H, heh, hel, b.ldh, fast};
+  static const int epi_dbg = getenv("VAEB_EPI_DBG") ? atoi(getenv("VAEB_EPI_DBG")) : 0;     // measurement switch
+  a.tanh_[0] = EpiTanh{b3, nullptr, H, heh, hel, b.ldh, fast, epi_dbg};
   // layer 1 enc2: (mu, ls) = h_e.[W4|W5] + b, eps, z, KL / L^A row term    VAEB.py:248-249, 41-47, 343, 322-325
   fill_layer(a.layer[1], m.enc2, rows, 2 * Z, H, 64, 1, 0, CK_HEADS, 0, 0);
   a.heads = EpiHeads{b4, b5, Z, la, src, mu, ls, eps, z, (__nv_bfloat16*)b.zh, (__nv_bfloat16*)b.zl, b.ldz, aux_part, 0.f};
   *n_aux = a.layer[1].tiles_n * (EPI_WARPS / 4);
   // layer 2 dec1: h_d = tanh(z.W1 + b1)                                   VAEB.py:254
   fill_layer(a.layer[2], m.dec1, rows, H, Z, bn, 1, 0, CK_TANH, 1, 1);
-  a.tanh_[1] = EpiTanh{b1, nullptr, H, hdh, hdl, b.ldh, fast};
+  a.tanh_[1] = EpiTanh{b1, nullptr, H, hdh, hdl, b.ldh, fast, epi_dbg};
   // layer 3 dec2: a = h_d.W2 + b2, Bernoulli log-likelihood, delta        VAEB.py:263, 311
   fill_layer(a.layer[3], m.dec2, rows, D, H, bn, 1, 0, CK_BERN, 0, 2);
   a.bern = EpiBernoulliTc{b2, nullptr, D, 1, rows, scale, (__nv_bfloat16*)b.da2h, (__nv_bfloat16*)b.da2l, b.ldd, partial,
@@ -533,6 +577,9 @@ cudaError_t tc_chain_step(cudaStream_t st, int64_t* launches, const TcMaps& m, i
     return ns == 2 ? cudaLaunchKernelEx(&cfg, tc_chain_kernel<2, false>, a) : cudaLaunchKernelEx(&cfg, tc_chain_kernel<1, false>, a);
   };
   a.stamps = nullptr;
+  a.diag = getenv("VAEB_CHAIN_DIAG") ? 1 : 0;
+  a.throttle = getenv("VAEB_CHAIN_THROTTLE") ? 1 : 0;
+  a.ld32 = (getenv("VAEB_CHAIN_LD32") && getenv("VAEB_CHAIN_LD32")[0] == '0') ? 0 : 1;   // measured: 256-wide tiles 5-30 % shorter epilogues
   static const char* stamp_path = getenv("VAEB_CHAIN_STAMPS");      // debug: dump the per-item time stamps of every launch
   if (stamp_path) {
     static long long* d_st = nullptr; static int cap = 0;

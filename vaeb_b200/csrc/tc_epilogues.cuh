@@ -130,6 +130,7 @@ struct EpiTanh {            // out[row, col] = tanh(acc + bias[col]) (+ optional
   static constexpr bool PREFETCH = true;   // persistent kernel: unrolled epilogue with the next chunk's operand in flight
   const float* bias; float* out; int ld;
   __nv_bfloat16* mh; __nv_bfloat16* ml; int ldm; int fast;
+  int dbg;   // measurement switch (VAEB_EPI_DBG, chain kernel only): 1 no stores, 2 no tanh, 4 no bias load
   __device__ __forceinline__ void begin() {}
   __device__ __forceinline__ void split(int) {}
   __device__ __forceinline__ bool preload(int, bool, int, int, uint32_t*) const { return false; }   // bias only: L1 hits
@@ -138,9 +139,20 @@ struct EpiTanh {            // out[row, col] = tanh(acc + bias[col]) (+ optional
     float* o = out ? out + (size_t)row * ld + col0 : nullptr;
     if (vec_ok(o, col0, N) && vec_ok(bias + col0, col0, N) && vec_ok(mh ? mh + (size_t)row * ldm + col0 : nullptr, col0, N)) {
       float b[16], r[16];
-      ld16f(bias + col0, b);
+      if (dbg & 4) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) r[j] = tanh_tc(v[j] + b[j], fast);
+        for (int j = 0; j < 16; ++j) b[j] = 0.25f;
+      } else {
+        ld16f(bias + col0, b);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = (dbg & 2) ? v[j] + b[j] : tanh_tc(v[j] + b[j], fast);
+      if (dbg & 1) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) t += r[j];
+        if (t != 123456.789f) return;       // (never false in practice: keeps the math alive without the stores)
+      }
       if (out) st16f(o, r);
       if (mh) st16_split(mh + (size_t)row * ldm + col0, ml ? ml + (size_t)row * ldm + col0 : nullptr, r);
       return;

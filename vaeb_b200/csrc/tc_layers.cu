@@ -710,7 +710,9 @@ static int make_pair_mn(CUtensorMap* hi, CUtensorMap* lo, const void* bh, const 
 }
 
 // bn: UMMA N of the activation layers (tc_act_bn); bn_w: of the weight-gradient GEMMs
-int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z, int bn_w) {
+int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z, int bn_w,
+                  int bn_d) {
+  const uint32_t gd = (uint32_t)(bn_d > 0 ? bn_d : bn) / 64;
   const uint32_t ga = BM / 64, gb = (uint32_t)bn / 64, gw = (uint32_t)bn_w / 64;
   const uint32_t kw = b.w3l ? BK : 2 * BK;      // contraction rows per box of the weight-gradient operands (stage_k)
   // enc1: A = x mirror [rows_data, D] K-major (the ones column at D stays out of the map), B = W3 [D, H] MN-major
@@ -720,7 +722,7 @@ int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows,
   // dec2: A = h_d mirror [R, H] K-major, B = W2 [H, D] MN-major
   LayerMaps* d2 = reinterpret_cast<LayerMaps*>(m->dec2);
   VAEB_TRY(make_pair(&d2->a_hi, &d2->a_lo, b.hdh, b.hdl, R, H, b.ldh, BM));
-  VAEB_TRY(make_pair_mn(&d2->b_hi, &d2->b_lo, b.w2h, b.w2l, H, D, b.ldd, gb));
+  VAEB_TRY(make_pair_mn(&d2->b_hi, &d2->b_lo, b.w2h, b.w2l, H, D, b.ldd, gd));
   // dgrad h_d: A = da2 mirror [R, D] K-major, B = W2 [H, D] K-major (N = H rows)
   LayerMaps* dg = reinterpret_cast<LayerMaps*>(m->dgrad);
   VAEB_TRY(make_pair(&dg->a_hi, &dg->a_lo, b.da2h, b.da2l, R, D, b.ldd, BM));

@@ -46,7 +46,9 @@ void tc_set_pdl(bool on);
 // UMMA N of the activation layers (A K-major) for `rows` rows and outputs at least n_min wide: 256 selects the
 // persistent kernel (large batches), else 128 / 64 with one tile per CTA
 int tc_act_bn(int rows, int n_min);
-int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z, int bn_w);
+// bn: UMMA N of the H-wide activation layers (enc1, dec1, both dgrads); bn_d (0: = bn): of dec2 (D wide)
+int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z, int bn_w,
+                  int bn_d = 0);
 
 cudaError_t tc_split_matrix(cudaStream_t st, int64_t* launches, const float* src, int64_t rows, int cols, int ld_src,
                             void* hi, void* lo, int ld_dst, int ones_col);
