@@ -76,6 +76,10 @@ typedef struct vaeb_config {
 #define VAEB_OPT_ADAGRAD 0   /* getUpdates          VAEB.py:426-444 (the path the reference runs) */
 #define VAEB_OPT_ADADELTA 1  /* getAdaDeltaUpdates  VAEB.py:449-469 (the alternative commented out at :404) */
 
+#define VAEB_ACT_TANH 1      /* the reference's hidden layers (VAEB.py:246,254) */
+#define VAEB_ACT_SIGMOID 2   /* alternatives compared in Report/replication/replic.tex:73-82 */
+#define VAEB_ACT_RELU 3
+
 const char* vaeb_last_error(void);
 int vaeb_version(void);
 
@@ -126,6 +130,9 @@ int vaeb_ae_forward(vaeb_handle* h, int32_t kind, int32_t what, const float* in,
  * getAdaDeltaUpdates (VAEB.py:449-469): g_ac = rho g_ac + (1-rho) g^2; dx = sqrt(dx_ac + eps) g / sqrt(g_ac + eps);
  * p += dx; dx_ac = rho dx_ac + (1-rho) dx^2, with eps = adagrad_eps (VAEB.py:144) and rho = 0.95 (VAEB.py:145).
  * Both accumulators restart at zero.  Not available for the full-VB estimators. */
+/* Activation of both hidden layers (encoder VAEB.py:246, decoder :254).  tanh (default) runs everywhere; sigmoid and ReLU
+ * (Report/replication/replic.tex:73-82) run on the fp32 per-layer kernels (L^A / L^B estimators, one GPU). */
+int vaeb_set_hidden_activation(vaeb_handle* h, int32_t act);
 int vaeb_set_optimizer(vaeb_handle* h, int32_t optimizer, float rho);
 
 /* `x_train = th.shared(...)` (VAEB.py:184): copies x[N,D] to the device once. */

@@ -195,9 +195,32 @@ def sigmoid(a):
     return 0.5 * (np.tanh(0.5 * a) + 1.0)
 
 
-def encoder(p, x):
+def hidden_act(a, act="tanh"):
+    """Hidden-layer activation: tanh in the reference (VAEB.py:246,254); sigmoid / ReLU are the alternatives its
+    report compares (Report/replication/replic.tex:73-82)."""
+    if act == "tanh":
+        return np.tanh(a)
+    if act == "sigmoid":
+        return sigmoid(a)
+    if act == "relu":
+        return np.maximum(a, 0)
+    raise ValueError("unknown activation %r" % (act,))
+
+
+def hidden_act_grad(h, act="tanh"):
+    """Derivative of the activation in terms of its VALUE h."""
+    if act == "tanh":
+        return 1.0 - h ** 2
+    if act == "sigmoid":
+        return h * (1.0 - h)
+    if act == "relu":
+        return (h > 0).astype(h.dtype)
+    raise ValueError("unknown activation %r" % (act,))
+
+
+def encoder(p, x, act="tanh"):
     """VAEB.py:245-251."""
-    h = np.tanh(x @ p["W3"] + p["b3"])
+    h = hidden_act(x @ p["W3"] + p["b3"], act)
     mu = h @ p["W4"] + p["b4"]
     ls = h @ p["W5"] + p["b5"]
     return h, mu, ls
@@ -208,10 +231,10 @@ def reparam(mu, ls, eps):
     return mu + np.exp(0.5 * ls) * eps
 
 
-def decoder(p, z, continuous):
+def decoder(p, z, continuous, act="tanh"):
     """VAEB.py:253-265.  Returns (h, a, lv): a is the PRE-sigmoid activation
     (y = sigmoid(a)); lv = h.W6+b6 only for the continuous model."""
-    h = np.tanh(z @ p["W1"] + p["b1"])
+    h = hidden_act(z @ p["W1"] + p["b1"], act)
     a = h @ p["W2"] + p["b2"]
     lv = (h @ p["W6"] + p["b6"]) if continuous else None
     return h, a, lv
@@ -252,7 +275,7 @@ def _zeros_like_list(params):
 
 
 def elbo_and_grads(params, x, eps, continuous, estimator="LB", want_grads=True,
-                   prior_scale=1.0, row_weight=None):
+                   prior_scale=1.0, row_weight=None, act="tanh"):
     """The symbolic graph of ``getGradient`` (VAEB.py:370-399) for the LB (VAEB.py:332-346)
     and LA (VAEB.py:315-330) estimators with the weight prior of VAEB.py:386-390.
 
@@ -263,7 +286,7 @@ def elbo_and_grads(params, x, eps, continuous, estimator="LB", want_grads=True,
     dt = x.dtype
     L, M, Z = eps.shape
     w = dt.type(1.0 if row_weight is None else row_weight)
-    h_e, mu, ls = encoder(p, x)
+    h_e, mu, ls = encoder(p, x, act)
     sd = np.exp(0.5 * ls)
     per_row = np.zeros(M, dtype=dt)
     g = {n: np.zeros_like(q) for n, q in p.items()}
@@ -273,7 +296,7 @@ def elbo_and_grads(params, x, eps, continuous, estimator="LB", want_grads=True,
     for l in range(L):
         e = eps[l]
         z = mu + sd * e
-        h_d, a, lv = decoder(p, z, continuous)
+        h_d, a, lv = decoder(p, z, continuous, act)
         lp = log_px_given_z(x, a, lv, continuous)
         if estimator == "LA":
             prior = (-0.5 * LOG2PI - 0.5 * z ** 2).sum(axis=1)                       # VAEB.py:322
@@ -299,7 +322,7 @@ def elbo_and_grads(params, x, eps, continuous, estimator="LB", want_grads=True,
             g["W6"] += h_d.T @ d_lv
             g["b6"] += d_lv.sum(axis=0)
             d_h += d_lv @ p["W6"].T
-        d_a1 = d_h * (1.0 - h_d ** 2)
+        d_a1 = d_h * hidden_act_grad(h_d, act)
         g["W1"] += z.T @ d_a1
         g["b1"] += d_a1.sum(axis=0)
         d_z = d_a1 @ p["W1"].T
@@ -323,7 +346,7 @@ def elbo_and_grads(params, x, eps, continuous, estimator="LB", want_grads=True,
     g["W5"] = h_e.T @ d_ls
     g["b5"] = d_ls.sum(axis=0)
     d_he = d_mu @ p["W4"].T + d_ls @ p["W5"].T
-    d_a3 = d_he * (1.0 - h_e ** 2)
+    d_a3 = d_he * hidden_act_grad(h_e, act)
     g["W3"] = x.T @ d_a3
     g["b3"] = d_a3.sum(axis=0)
     ps = dt.type(prior_scale)
@@ -370,7 +393,8 @@ class OracleVAEB:
     prior in the criterion, extra -lr*1e-6*p**2 in the update)."""
 
     def __init__(self, x_train, continuous, H, Z, batch_size, L=1, lr=0.01, estimator="LB",
-                 params=None, dtype=np.float64, variant="vaeb", optimizer="adagrad", rho=0.95):
+                 params=None, dtype=np.float64, variant="vaeb", optimizer="adagrad", rho=0.95, activation="tanh"):
+        self.activation = activation
         self.x = np.asarray(x_train, dtype=dtype)
         self.N, self.D = self.x.shape
         self.continuous, self.H, self.Z = continuous, H, Z
@@ -398,7 +422,7 @@ class OracleVAEB:
                                  prior_scale=0.0, row_weight=1.0 / M)
             return out.sgvb / M, out.per_row, out.grads
         if est in ("LB", "LA"):
-            out = elbo_and_grads(self.params, x, eps, self.continuous, est, want_grads)
+            out = elbo_and_grads(self.params, x, eps, self.continuous, est, want_grads, act=self.activation)
             return out.sgvb, out.per_row, out.grads
         # ---- full VB, VAEB.py:349-367 + :391-393, :399 ----
         if self.L != 1:

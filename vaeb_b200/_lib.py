@@ -63,6 +63,7 @@ EXPORTS = {
     "vaeb_comm_unique_id": (C.c_int, [C.c_char_p, C.c_void_p]),
     "vaeb_comm_attach": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int32, C.c_int32]),
     "vaeb_comm_detach": (C.c_int, [C.c_void_p]),
+    "vaeb_set_hidden_activation": (C.c_int, [C.c_void_p, C.c_int32]),
     "vaeb_comm_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vaeb_comm_p2p_attach": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "vaeb_profile_update": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_void_p,

@@ -410,7 +410,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
                tcl ? tb.heh : nullptr, tcl ? tb.hel : nullptr, tb.ldh));   // tcl: every consumer of h_e reads its mirror
   else
     PH("enc1 x.W3+tanh", 2 * dr * dD * dH, 4 * (dr * dD + dD * dH + dr * dH),
-       launch_dense_act(st, lc, x, rows, D, T_(h, theta, l.iW3), T_(h, theta, l.ib3), H, 1, s.h_e));
+       launch_dense_act(st, lc, x, rows, D, T_(h, theta, l.iW3), T_(h, theta, l.ib3), H, h->hidden_act, s.h_e));
   // latent heads + reparameterisation + row terms + decoder hidden layer, VAEB.py:248-254,41-47,343
   if (!tcl)
     PH("transpose W4,W5", 0, 16 * dH * dZ,
@@ -429,7 +429,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
      launch_latent_fwd(st, lc, s.h_e, rows, H, h->d_w45t, T_(h, theta, l.ib4),
                        T_(h, theta, l.ib5), T_(h, theta, l.iW1), T_(h, theta, l.ib1), Z, L, la, src, s.mu, s.ls,
                        s.eps, s.z, s.row_aux, s.h_d, tcp ? tb.hdh : nullptr, tcp ? tb.hdl : nullptr, tb.ldh,
-                       tcl ? tb.zh : nullptr, tcl ? tb.zl : nullptr, tb.ldz));
+                       tcl ? tb.zh : nullptr, tcl ? tb.zl : nullptr, tb.ldz, h->hidden_act));
   // decoder output layer + log-likelihood, VAEB.py:257-263,302-313
   const float scale = w / (float)L;
   const float* W6 = h->cont ? T_(h, theta, l.iW6) : nullptr;
@@ -467,7 +467,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
       PH("wgrad W6,b6", 2 * dR * dH * dD, 4 * (dR * dH + dR * dD + dH * dD),
          launch_wgrad(st, lc, s.h_d, R, H, s.dlv, D, T_(h, grads, l.iW6), T_(h, grads, l.ib6)));
     PH("dgrad h_d (.W2^T)*(1-h^2)", 2 * dR * dH * dD * c, 4 * (c * dR * dD + c * dH * dD + 2 * dR * dH),
-       launch_dgrad_tanh(st, lc, s.da2, T_(h, theta, l.iW2), h->cont ? s.dlv : nullptr, W6, R, D, H, s.h_d, s.da1));
+       launch_dgrad_tanh(st, lc, s.da2, T_(h, theta, l.iW2), h->cont ? s.dlv : nullptr, W6, R, D, H, s.h_d, s.da1, h->hidden_act));
   }
   if (tcl) {
     PH("dz da1.W1^T + dmu,dls [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * dH + dZ * dH) + 28 * dR * dZ,
@@ -486,7 +486,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
                        s.mu, s.ls, rows, H, Z, L, la, w, s.dmu, s.dls, s.da3, tcp ? tb.da3h : nullptr,
                        tcp ? tb.da3l : nullptr, tb.ldh, s.partial, tiles,
                        s.row_aux, s.per_row, h->d_counter, bo.base_out, bo.mult, bo.tprior, bo.n_tprior, bo.div,
-                       bo.scalar_out, tcl ? tb.ddh : nullptr, tcl ? tb.ddl : nullptr, tb.ldq));
+                       bo.scalar_out, tcl ? tb.ddh : nullptr, tcl ? tb.ddl : nullptr, tb.ldq, h->hidden_act));
   if (tcl) {
     PH("dgrad h_e ([dmu|dls].W45^T)*(1-h^2) [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * 64 + 2 * dZ * dH) + 8 * dr * dH,
        tc_dgrad_he(st, lc, t.maps, t.ns, bna, rows, Z, H, nullptr, nullptr, tb.da3h, tb.da3l, tb.ldh, tb.heh, tb.hel));
@@ -1023,10 +1023,10 @@ int vaeb_ae_train(vaeb_handle* h, int32_t kind, const int32_t* idx, int32_t n, f
   VAEB_LAUNCH(launch_gather_rows(st, lc, h->d_x, (const int*)h->d_stage2, rows, D, h->d_stage));
   const float* x = h->d_stage;
   // forward (ae.py:48-58)
-  VAEB_LAUNCH(launch_dense_act(st, lc, x, rows, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, 1, s.h_e));
+  VAEB_LAUNCH(launch_dense_act(st, lc, x, rows, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, h->hidden_act, s.h_e));
   VAEB_LAUNCH(launch_dense_act(st, lc, s.h_e, rows, H, T_(h, th, l.iW4), T_(h, th, l.ib4), Z,
                                kind == VAEB_AE_VANILLA ? 1 : 0, s.z));
-  VAEB_LAUNCH(launch_dense_act(st, lc, s.z, rows, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, 1, s.h_d));
+  VAEB_LAUNCH(launch_dense_act(st, lc, s.z, rows, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, h->hidden_act, s.h_d));
   int tiles = 0;
   if (h->cont)     // otype 'cont': OutToProbs mean, OutToReal log-variance, indep_normal (ae.py:64-72) = the Gaussian head
     VAEB_LAUNCH(launch_dec2_loglik(st, lc, true, s.h_d, rows, H, T_(h, th, l.iW2), T_(h, th, l.ib2), T_(h, th, l.iW6),
@@ -1080,17 +1080,30 @@ int vaeb_ae_forward(vaeb_handle* h, int32_t kind, int32_t what, const float* in,
   const float* th = h->d_params;
   const float* z = h->d_stage;
   if (what != 2) {
-    VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage, r, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, 1, s.h_e));
+    VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage, r, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, h->hidden_act, s.h_e));
     VAEB_LAUNCH(launch_dense_act(st, lc, s.h_e, r, H, T_(h, th, l.iW4), T_(h, th, l.ib4), Z,
                                  kind == VAEB_AE_VANILLA ? 1 : 0, what == 1 ? h->d_out : s.z));
     z = s.z;
   }
   if (what != 1) {
-    VAEB_LAUNCH(launch_dense_act(st, lc, z, r, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, 1, s.h_d));
+    VAEB_LAUNCH(launch_dense_act(st, lc, z, r, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, h->hidden_act, s.h_d));
     VAEB_LAUNCH(launch_dense_act(st, lc, s.h_d, r, H, T_(h, th, l.iW2), T_(h, th, l.ib2), D, 2, h->d_out));   // OutToProbs
   }
   VAEB_CUDA(cudaMemcpyAsync(out, h->d_out, (size_t)rows * out_w * sizeof(float), cudaMemcpyDeviceToHost, st));
   VAEB_CUDA(cudaStreamSynchronize(st));
+  return VAEB_OK;
+}
+
+int vaeb_set_hidden_activation(vaeb_handle* h, int32_t act) {
+  if (h && h->a_pending) VAEB_TRY(async_flush(h));
+  VAEB_REQUIRE(h, "null handle");
+  VAEB_REQUIRE(act == VAEB_ACT_TANH || act == VAEB_ACT_SIGMOID || act == VAEB_ACT_RELU, "unknown activation");
+  VAEB_REQUIRE(act == VAEB_ACT_TANH || (h->cfg.precision == VAEB_PREC_FP32 && !is_fvb(h) && h->world == 1),
+               "sigmoid / ReLU hidden layers: fp32 per-layer kernels, L^A / L^B estimators, one GPU");
+  h->hidden_act = act;
+  // the single-launch step kernels and the tensor-core estimators are tanh-only
+  h->fused_off = (act != VAEB_ACT_TANH || h->optimizer != VAEB_OPT_ADAGRAD) ? true : h->fused_off_user;
+  h->steptc.mirrors_valid = false; h->tc.weights_ready = false;
   return VAEB_OK;
 }
 
@@ -1108,7 +1121,7 @@ int vaeb_set_optimizer(vaeb_handle* h, int32_t optimizer, float rho) {
   VAEB_CUDA(cudaMemsetAsync(h->d_ada, 0, nb, h->stream));
   h->optimizer = optimizer;
   h->rho = rho;
-  h->fused_off = optimizer != VAEB_OPT_ADAGRAD ? true : h->fused_off_user;
+  h->fused_off = (optimizer != VAEB_OPT_ADAGRAD || h->hidden_act != VAEB_ACT_TANH) ? true : h->fused_off_user;
   return VAEB_OK;
 }
 
@@ -1383,7 +1396,7 @@ int vaeb_is_logpx(vaeb_handle* h, const float* x, int64_t n, int32_t L, const fl
       VAEB_CUDA(cudaStreamWaitEvent(st, q.copied[k & 1], 0));
       EpsSource src{nullptr, h->cfg.seed, VAEB_STREAM_IS, 0u, row_offset + i0};
       Workspace& s = h->ws;
-      VAEB_LAUNCH(launch_dense_act(st, lc, dx, c, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, 1, s.h_e));
+      VAEB_LAUNCH(launch_dense_act(st, lc, dx, c, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, h->hidden_act, s.h_e));
       VAEB_LAUNCH(launch_enc2(st, lc, s.h_e, c, H, T_(h, th, l.iW4), T_(h, th, l.ib4), T_(h, th, l.iW5),
                               T_(h, th, l.ib5), Z, 0, 0, src, s.mu, s.ls, s.eps, s.z, s.row_aux));
       VAEB_TRY(is_tc_run(h, dx, s.mu, s.ls, c, L, nullptr, row_offset + i0, h->d_out, nullptr));
@@ -1403,7 +1416,7 @@ int vaeb_is_logpx(vaeb_handle* h, const float* x, int64_t n, int32_t L, const fl
     if (eps) { VAEB_TRY(stage_in(h, &h->d_stage2, &h->stage2_cap, eps + i0 * L * Z, (int64_t)R * Z)); d_eps = h->d_stage2; }
     EpsSource src{d_eps, h->cfg.seed, VAEB_STREAM_IS, 0u, row_offset + i0};
     Workspace& s = h->ws;
-    VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage, c, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, 1, s.h_e));
+    VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage, c, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, h->hidden_act, s.h_e));
     VAEB_LAUNCH(launch_enc2(st, lc, s.h_e, c, H, T_(h, th, l.iW4), T_(h, th, l.ib4), T_(h, th, l.iW5),
                             T_(h, th, l.ib5), Z, 0, 0, src, s.mu, s.ls, s.eps, s.z, s.row_aux));
     if (tcp) {
@@ -1416,7 +1429,7 @@ int vaeb_is_logpx(vaeb_handle* h, const float* x, int64_t n, int32_t L, const fl
       continue;
     }
     VAEB_LAUNCH(launch_is_sample(st, lc, s.mu, s.ls, c, L, Z, src, s.z, s.dec_aux));
-    VAEB_LAUNCH(launch_dense_act(st, lc, s.z, R, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, 1, s.h_d));
+    VAEB_LAUNCH(launch_dense_act(st, lc, s.z, R, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, h->hidden_act, s.h_d));
     int tiles = 0;
     VAEB_LAUNCH(launch_dec2_loglik(st, lc, h->cont, s.h_d, R, H, T_(h, th, l.iW2), T_(h, th, l.ib2),
                                    h->cont ? T_(h, th, l.iW6) : nullptr, h->cont ? T_(h, th, l.ib6) : nullptr, D,
@@ -1451,7 +1464,7 @@ int vaeb_reconstruct(vaeb_handle* h, const float* x, int64_t n, int32_t n_sample
   const float* th = h->d_params;
   Workspace& s = h->ws;
   EpsSource src{d_eps, h->cfg.seed, VAEB_STREAM_RECON, h->step, 0};
-  VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage, (int)n, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, 1, s.h_e));
+  VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage, (int)n, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, h->hidden_act, s.h_e));
   VAEB_LAUNCH(launch_enc2(st, lc, s.h_e, (int)n, H, T_(h, th, l.iW4), T_(h, th, l.ib4), T_(h, th, l.iW5),
                           T_(h, th, l.ib5), Z, 0, 0, src, s.mu, s.ls, s.eps, s.z, s.row_aux));
   const float* W6 = h->cont ? T_(h, th, l.iW6) : nullptr;
@@ -1463,7 +1476,7 @@ int vaeb_reconstruct(vaeb_handle* h, const float* x, int64_t n, int32_t n_sample
       VAEB_LAUNCH(launch_recon_sample(st, lc, s.mu, s.ls, (int)n, Z, src, sidx, (int)n, s.z));
       zin = s.z;
     }
-    VAEB_LAUNCH(launch_dense_act(st, lc, zin, (int)n, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, 1, s.h_d));
+    VAEB_LAUNCH(launch_dense_act(st, lc, zin, (int)n, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, h->hidden_act, s.h_d));
     VAEB_LAUNCH(launch_dec2_recon(st, lc, h->cont, s.h_d, (int)n, H, T_(h, th, l.iW2), T_(h, th, l.ib2), W6, b6, D,
                                   d_y, d_lv, 1.0f / (float)passes, sidx == 0));
   }
@@ -1492,7 +1505,7 @@ int vaeb_decode(vaeb_handle* h, const float* z, int64_t n, float* y_out, float* 
   int64_t* lc = &h->launches;
   const float* th = h->d_params;
   Workspace& s = h->ws;
-  VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage2, (int)n, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, 1, s.h_d));
+  VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage2, (int)n, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, h->hidden_act, s.h_d));
   VAEB_LAUNCH(launch_dec2_recon(st, lc, h->cont, s.h_d, (int)n, H, T_(h, th, l.iW2), T_(h, th, l.ib2),
                                 h->cont ? T_(h, th, l.iW6) : nullptr, h->cont ? T_(h, th, l.ib6) : nullptr, D, d_y, d_lv,
                                 1.0f, true));

@@ -160,6 +160,7 @@ struct vaeb_handle {
   bool steptc_off = false;            // VAEB_B200_STEP_TC=0: the FFMA kernel of fused_step.cu serves M <= 128 too
   bool fused_off = false;             // VAEB_B200_FUSED=0: always use the per-layer kernels
   bool fused_off_user = false;        // what the environment asked for (AdaDelta also turns the fused kernel off)
+  int hidden_act = 1;                 // VAEB_ACT_*: activation of both hidden layers (tanh in the reference's VAEB.py:246,254)
   // data parallel
   NcclApi nccl; void* comm = nullptr; int rank = 0, world = 1;
 };

@@ -4,6 +4,7 @@
 // one kernel.  256 threads, BK = 16, register-prefetch double buffering, float4 LDS.
 #pragma once
 #include <cuda_runtime.h>
+#include "activations.cuh"
 #include <cstdint>
 
 struct GemmOperands {
@@ -27,14 +28,11 @@ struct EpiStore {  // out = acc
   }
 };
 
-struct EpiBiasAct {  // out = f(acc + bias[n]); act: 0 identity, 1 tanh, 2 sigmoid
+struct EpiBiasAct {  // out = f(acc + bias[n]); act: 0 identity, 1 tanh, 2 sigmoid, 3 ReLU
   static constexpr bool kRowReduce = false;
   const float* bias; float* out; int ld; int act;
   __device__ __forceinline__ float operator()(int m, int n, float acc, float) const {
-    float v = acc + bias[n];
-    if (act == 1) v = tanhf(v);
-    else if (act == 2) v = 1.0f / (1.0f + expf(-v));
-    out[(size_t)m * ld + n] = v; return 0.f;
+    out[(size_t)m * ld + n] = act_fwd(acc + bias[n], act); return 0.f;
   }
 };
 
@@ -47,12 +45,12 @@ struct EpiWgrad {  // rows < H go to gW[H,N], the ones-row (m == H) is the bias 
   }
 };
 
-struct EpiMulOneMinusSq {  // out = acc * (1 - h^2): backprop through tanh
+struct EpiMulOneMinusSq {  // out = acc * f'(h): backprop through the hidden activation (tanh: 1 - h^2)
   static constexpr bool kRowReduce = false;
-  const float* h; float* out; int ld;
+  const float* h; float* out; int ld; int act;
   __device__ __forceinline__ float operator()(int m, int n, float acc, float) const {
     const float hv = h[(size_t)m * ld + n];
-    out[(size_t)m * ld + n] = acc * (1.0f - hv * hv); return 0.f;
+    out[(size_t)m * ld + n] = acc * act_bwd(hv, act); return 0.f;
   }
 };
 

@@ -84,10 +84,10 @@ cudaError_t launch_wgrad(cudaStream_t st, int64_t* launches, const float* in, in
 }
 
 cudaError_t launch_dgrad_tanh(cudaStream_t st, int64_t* launches, const float* d, const float* W, const float* d2,
-                              const float* W2, int rows, int N, int K, const float* h, float* out) {
+                              const float* W2, int rows, int N, int K, const float* h, float* out, int act) {
   // out[rows,K] = d[rows,N] . W[K,N]^T : B(k'=n, n'=k) = W[k*N + n] -> TB with ldb = N
   GemmOperands g{d, W, d2, W2, N, N, rows, K, N};
-  EpiMulOneMinusSq epi{h, out, K};
+  EpiMulOneMinusSq epi{h, out, K, act};
   if (d2) return run_gemm<false, true, false, false, true>(st, launches, g, epi, nullptr, nullptr);
   return run_gemm<false, true, false, false, false>(st, launches, g, epi, nullptr, nullptr);
 }

@@ -9,6 +9,7 @@
 // Optional bf16 hi/lo mirrors of h_d and da3 feed the tcgen05 GEMMs of the wide layers.
 #include <cuda_bf16.h>
 
+#include "activations.cuh"
 #include "launchers.h"
 #include "philox.cuh"
 
@@ -56,7 +57,7 @@ latent_fwd_kernel(const float* __restrict__ h_e, int rows, int H, const float* _
                   const float* __restrict__ b1, int Z, int L, int la, EpsSource src, float* __restrict__ mu,
                   float* __restrict__ ls, float* __restrict__ eps, float* __restrict__ z,
                   float* __restrict__ row_aux, float* __restrict__ h_d, __nv_bfloat16* __restrict__ hd_hi,
-                  __nv_bfloat16* __restrict__ hd_lo, int ld_mirror, int KS) {
+                  __nv_bfloat16* __restrict__ hd_lo, int ld_mirror, int KS, int act) {
   extern __shared__ float sm[];
   const int Z2 = 2 * Z;
   float* part = sm;                         // [KS][RB][2Z]
@@ -145,7 +146,7 @@ latent_fwd_kernel(const float* __restrict__ h_e, int rows, int H, const float* _
       for (int r = 0; r < RB; ++r) {
         if (m0 + r < rows) {
           const size_t rr = (size_t)l * rows + m0 + r;
-          const float hv = tanhf(a[r]);
+          const float hv = act_fwd(a[r], act);
           h_d[rr * H + n] = hv;
           if (hd_hi) store_split(hd_hi, hd_lo, rr * ld_mirror + n, hv);
         }
@@ -189,7 +190,7 @@ latent_bwd_kernel(const float* __restrict__ da1, const float* __restrict__ W1, c
                   const float* __restrict__ partial, int n_tiles, const float* __restrict__ row_aux,
                   float* __restrict__ per_row, unsigned int* __restrict__ counter, float* __restrict__ base_out,
                   float mult, const float* __restrict__ tprior, int n_tprior, float div,
-                  float* __restrict__ scalar_out, int NSL) {
+                  float* __restrict__ scalar_out, int NSL, int act) {
   extern __shared__ float sm[];
   __shared__ float red[NWARPS];
   __shared__ int is_last;
@@ -279,7 +280,7 @@ latent_bwd_kernel(const float* __restrict__ da1, const float* __restrict__ W1, c
       const int m = m0 + r;
       if (m < rows) {
         const float hv = h_e[(size_t)m * H + n];
-        const float v = a[r] * (1.0f - hv * hv);
+        const float v = a[r] * act_bwd(hv, act);
         da3[(size_t)m * H + n] = v;
         if (da3_hi) store_split(da3_hi, da3_lo, (size_t)m * ld_mirror + n, v);
       }
@@ -428,7 +429,7 @@ lb_latent_fwd_kernel(const float* __restrict__ h_e, int rows, int H, const float
                      float* __restrict__ ls, float* __restrict__ eps, float* __restrict__ z,
                      float* __restrict__ row_aux, float* __restrict__ h_d, __nv_bfloat16* __restrict__ hd_hi,
                      __nv_bfloat16* __restrict__ hd_lo, int ld_mirror, __nv_bfloat16* __restrict__ z_hi,
-                     __nv_bfloat16* __restrict__ z_lo, int ldz) {
+                     __nv_bfloat16* __restrict__ z_lo, int ldz, int act) {
   __shared__ __align__(16) float hs[LB_ROWS][LB_KC + 1];
   __shared__ __align__(16) float ws[LB_KC][LB_WS];
   __shared__ __align__(16) float outs[LB_ROWS][LB_NC];
@@ -531,7 +532,7 @@ lb_latent_fwd_kernel(const float* __restrict__ h_e, int rows, int H, const float
         a = fmaf(zq.x, w[4 * q], a); a = fmaf(zq.y, w[4 * q + 1], a);
         a = fmaf(zq.z, w[4 * q + 2], a); a = fmaf(zq.w, w[4 * q + 3], a);
       }
-      const float hv = tanhf(a);
+      const float hv = act_fwd(a, act);
       h_d[(size_t)m * H + n] = hv;
       if (hd_hi) store_split(hd_hi, hd_lo, (size_t)m * ld_mirror + n, hv);
     }
@@ -549,7 +550,7 @@ lb_latent_bwd_kernel(const float* __restrict__ da1, const float* __restrict__ W1
                      float* __restrict__ per_row, unsigned int* __restrict__ counter, float* __restrict__ base_out,
                      float mult, const float* __restrict__ tprior, int n_tprior, float div,
                      float* __restrict__ scalar_out, __nv_bfloat16* __restrict__ dd_hi, __nv_bfloat16* __restrict__ dd_lo,
-                     int ldq) {
+                     int ldq, int act) {
   __shared__ __align__(16) float ds[LB_ROWS][LB_KC + 1];
   __shared__ __align__(16) float ws[LB_KC][28];
   __shared__ __align__(16) float psum[2][LB_ROWS][LB_ZP];
@@ -638,7 +639,7 @@ lb_latent_bwd_kernel(const float* __restrict__ da1, const float* __restrict__ W1
         a = fmaf(dq.z, wr[4 * q + 2], a); a = fmaf(dq.w, wr[4 * q + 3], a);
       }
       const float hv = h_e[(size_t)m * H + n];
-      const float v = a * (1.0f - hv * hv);
+      const float v = a * act_bwd(hv, act);
       da3[(size_t)m * H + n] = v;
       if (da3_hi) store_split(da3_hi, da3_lo, (size_t)m * ld_mirror + n, v);
     }
@@ -768,25 +769,25 @@ cudaError_t launch_latent_fwd(cudaStream_t st, int64_t* launches, const float* h
                               const float* w45t, const float* b4, const float* b5, const float* W1, const float* b1,
                               int Z, int L, int la, EpsSource src, float* mu, float* ls, float* eps, float* z,
                               float* row_aux, float* h_d, void* hd_hi, void* hd_lo, int ld_mirror, void* z_hi,
-                              void* z_lo, int ldz) {
+                              void* z_lo, int ldz, int act) {
   const int nchunks = (2 * Z + 7) / 8;
   const int KS = max(1, NWARPS / nchunks);
   ++*launches;
   if (latent_lb_supported(rows, H, Z, L)) {
     lb_latent_fwd_kernel<<<(rows + LB_ROWS - 1) / LB_ROWS, LB_T, 0, st>>>(
         h_e, rows, H, w45t, b4, b5, W1, b1, Z, la, src, mu, ls, eps, z, row_aux, h_d, (__nv_bfloat16*)hd_hi,
-        (__nv_bfloat16*)hd_lo, ld_mirror, (__nv_bfloat16*)z_hi, (__nv_bfloat16*)z_lo, ldz);
+        (__nv_bfloat16*)hd_lo, ld_mirror, (__nv_bfloat16*)z_hi, (__nv_bfloat16*)z_lo, ldz, act);
   } else if (rows <= 512) {
     const size_t smem = (size_t)((KS + 1) * 2 * Z + 2 * Z) * sizeof(float);
     latent_fwd_kernel<1><<<rows, NTHREADS, smem, st>>>(h_e, rows, H, w45t, b4, b5, W1, b1, Z, L, la, src, mu, ls, eps,
                                                       z, row_aux, h_d, (__nv_bfloat16*)hd_hi, (__nv_bfloat16*)hd_lo,
-                                                      ld_mirror, KS);
+                                                      ld_mirror, KS, act);
   } else {
     constexpr int RB = 8;
     const size_t smem = (size_t)RB * ((KS + 1) * 2 * Z + 2 * Z) * sizeof(float);
     latent_fwd_kernel<RB><<<(rows + RB - 1) / RB, NTHREADS, smem, st>>>(
         h_e, rows, H, w45t, b4, b5, W1, b1, Z, L, la, src, mu, ls, eps, z, row_aux, h_d, (__nv_bfloat16*)hd_hi,
-        (__nv_bfloat16*)hd_lo, ld_mirror, KS);
+        (__nv_bfloat16*)hd_lo, ld_mirror, KS, act);
   }
   return cudaGetLastError();
 }
@@ -797,7 +798,7 @@ cudaError_t launch_latent_bwd(cudaStream_t st, int64_t* launches, const float* d
                               float* da3, void* da3_hi, void* da3_lo, int ld_mirror, const float* partial,
                               int n_tiles, const float* row_aux, float* per_row, unsigned int* counter,
                               float* base_out, float mult, const float* tprior, int n_tprior, float div,
-                              float* scalar_out, void* dd_hi, void* dd_lo, int ldq) {
+                              float* scalar_out, void* dd_hi, void* dd_lo, int ldq, int act) {
   const int nchunks = (Z + 7) / 8;
   const int NSL = max(1, (NWARPS - 2) / nchunks);
   ++*launches;
@@ -805,20 +806,20 @@ cudaError_t launch_latent_bwd(cudaStream_t st, int64_t* launches, const float* d
     lb_latent_bwd_kernel<<<(rows + LB_ROWS - 1) / LB_ROWS, LB_T, 0, st>>>(
         da1, W1, w45t, h_e, z, eps, mu, ls, rows, H, Z, la, w, dmu, dls, da3, (__nv_bfloat16*)da3_hi,
         (__nv_bfloat16*)da3_lo, ld_mirror, partial, n_tiles, row_aux, per_row, counter, base_out, mult, tprior,
-        n_tprior, div, scalar_out, (__nv_bfloat16*)dd_hi, (__nv_bfloat16*)dd_lo, ldq);
+        n_tprior, div, scalar_out, (__nv_bfloat16*)dd_hi, (__nv_bfloat16*)dd_lo, ldq, act);
   } else if (rows <= 512) {
     const size_t smem = (size_t)(NSL + 2) * Z * sizeof(float);
     latent_bwd_kernel<1><<<rows, NTHREADS, smem, st>>>(
         da1, W1, w45t, h_e, z, eps, mu, ls, rows, H, Z, L, la, w, dmu, dls, da3, (__nv_bfloat16*)da3_hi,
         (__nv_bfloat16*)da3_lo, ld_mirror, partial, n_tiles, row_aux, per_row, counter, base_out, mult, tprior,
-        n_tprior, div, scalar_out, NSL);
+        n_tprior, div, scalar_out, NSL, act);
   } else {
     constexpr int RB = 8;
     const size_t smem = (size_t)RB * (NSL + 2) * Z * sizeof(float);
     latent_bwd_kernel<RB><<<(rows + RB - 1) / RB, NTHREADS, smem, st>>>(
         da1, W1, w45t, h_e, z, eps, mu, ls, rows, H, Z, L, la, w, dmu, dls, da3, (__nv_bfloat16*)da3_hi,
         (__nv_bfloat16*)da3_lo, ld_mirror, partial, n_tiles, row_aux, per_row, counter, base_out, mult, tprior,
-        n_tprior, div, scalar_out, NSL);
+        n_tprior, div, scalar_out, NSL, act);
   }
   return cudaGetLastError();
 }

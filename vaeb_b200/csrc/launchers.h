@@ -29,7 +29,8 @@ cudaError_t launch_wgrad(cudaStream_t st, int64_t* launches, const float* in, in
                          int N, float* gW, float* gb);
 // out[rows,K] = (d[rows,N] . W[K,N]^T (+ d2 . W2^T)) * (1 - h^2)
 cudaError_t launch_dgrad_tanh(cudaStream_t st, int64_t* launches, const float* d, const float* W,
-                              const float* d2, const float* W2, int rows, int N, int K, const float* h, float* out);
+                              const float* d2, const float* W2, int rows, int N, int K, const float* h, float* out,
+                              int act = 1);   // act: the hidden activation whose derivative multiplies (VAEB_ACT_*)
 // out[rows,K] = d[rows,N] . W[K,N]^T
 cudaError_t launch_dgrad(cudaStream_t st, int64_t* launches, const float* d, const float* W, int rows, int N,
                          int K, float* out);
@@ -108,7 +109,7 @@ cudaError_t launch_latent_fwd(cudaStream_t st, int64_t* launches, const float* h
                               const float* w45t, const float* b4, const float* b5, const float* W1, const float* b1,
                               int Z, int L, int la, EpsSource src, float* mu, float* ls, float* eps, float* z,
                               float* row_aux, float* h_d, void* hd_hi, void* hd_lo, int ld_mirror,
-                              void* z_hi = nullptr, void* z_lo = nullptr, int ldz = 0);
+                              void* z_hi = nullptr, void* z_lo = nullptr, int ldz = 0, int act = 1);
 // true when the 64-row large-batch kernels serve this shape (they also emit the z / [dmu|dls] mirrors)
 bool latent_large_batch(int rows, int H, int Z, int L);
 // dz, dmu/dls, da3 and the bound (per row + deterministic total by the last block to finish).
@@ -118,7 +119,7 @@ cudaError_t launch_latent_bwd(cudaStream_t st, int64_t* launches, const float* d
                               float* da3, void* da3_hi, void* da3_lo, int ld_mirror, const float* partial,
                               int n_tiles, const float* row_aux, float* per_row, unsigned int* counter,
                               float* base_out, float mult, const float* tprior, int n_tprior, float div,
-                              float* scalar_out, void* dd_hi = nullptr, void* dd_lo = nullptr, int ldq = 0);
+                              float* scalar_out, void* dd_hi = nullptr, void* dd_lo = nullptr, int ldq = 0, int act = 1);
 size_t small_wgrad_scratch_elems(int rows, int H, int Z);
 // gW1,gb1,gW4,gb4,gW5,gb5 in one launch (two for large batches: row chunks + deterministic reduce)
 cudaError_t launch_small_wgrad(cudaStream_t st, int64_t* launches, const float* z, const float* da1, int R,

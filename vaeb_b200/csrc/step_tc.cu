@@ -1627,7 +1627,7 @@ __global__ void __launch_bounds__(128) init_ones_kernel(OnesArgs a) {
 // =====================================================================================================================
 bool step_tc_supported(const vaeb_handle* h, int rows) {
   const int e = h->cfg.estimator;
-  if (h->steptc.unavailable || h->steptc_off) return false;
+  if (h->steptc.unavailable || h->steptc_off || h->hidden_act != 1) return false;   // tanh hidden layers only
   return (e == VAEB_EST_LB || e == VAEB_EST_LA || e == VAEB_EST_FVB || e == VAEB_EST_FVB_SAMPLED) && h->L == 1 && h->world == 1 &&
          h->cfg.precision != VAEB_PREC_BF16 && h->optimizer == VAEB_OPT_ADAGRAD && rows >= 1 && rows <= st2::MP &&
          (h->D % 8) == 0 && (h->H % 4) == 0 && h->D >= 64 && h->H >= 64 && h->D <= 1024 && h->H <= 512 && h->Z >= 1 &&

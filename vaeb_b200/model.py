@@ -72,10 +72,12 @@ class VAEB(object):
     #   variant        'vaeb' | 'fullbayes' (VAEBfullbayes.py objective/update scalars)
     #   optimizer      'adagrad' (getUpdates, VAEB.py:426-444) | 'adadelta' (getAdaDeltaUpdates, VAEB.py:449-469,
     #                  the alternative the reference keeps commented out at VAEB.py:404; rho = self.rho = 0.95)
+    #   activation     'tanh' (the reference's hidden layers, VAEB.py:246,254) | 'sigmoid' | 'relu' (the alternatives of
+    #                  Report/replication/replic.tex:73-82; fp32 per-layer kernels, L^A / L^B estimators)
     def __init__(self, x_train, continuous, hidden_units, latent_size, batch_size,
                  L, learning_rate, genericEstimator, fullVariational, params=None, prng=None, sigmaInit=None,
                  *, device=0, precision="fp32", eps_mode="philox", sample_weights=False, variant="vaeb", seed=10,
-                 optimizer="adagrad"):
+                 optimizer="adagrad", activation="tanh"):
         x_train = np.asarray(x_train)
         [self.N, self.input_size] = x_train.shape       # VAEB.py:135
         self.n_hidden_units = hidden_units
@@ -159,6 +161,11 @@ class VAEB(object):
         self.optimizer = optimizer
         if optimizer == "adadelta":
             _lib.check(self._lib.vaeb_set_optimizer(self._h, _lib.OPT_ADADELTA, self.rho))
+        if activation not in ("tanh", "sigmoid", "relu"):
+            raise ValueError("activation must be 'tanh', 'sigmoid' or 'relu'")
+        self.activation = activation
+        if activation != "tanh":
+            _lib.check(self._lib.vaeb_set_hidden_activation(self._h, {"sigmoid": 2, "relu": 3}[activation]))
         _lib.check(self._lib.vaeb_upload_data(self._h, _ptr(_f32(x_train)), self.N))   # VAEB.py:184
 
     # ---- parameters -------------------------------------------------------------------
