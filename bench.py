@@ -344,7 +344,10 @@ def run_own(args):
                                         for p in phases]})
         except Exception as ex:                          # profiling is evidence, never a reason to lose the line
             roofline["phases_error"] = str(ex)[:200]
-    m3.close()
+    if world > 1:
+        vd.close_data_parallel(m3)
+    else:
+        m3.close()
     del pinned, xp, xs
 
     # ================= also: the other configurations, c5 and c2 last ==============================================
@@ -362,7 +365,7 @@ def run_own(args):
         tfb = MG * kb / (msb * 1e-3) * FLOPS_PER_DATAPOINT / 1e12
         also["c3_bf16"] = {"value": MG * kb / (msb * 1e-3), "unit": UNIT, "ms_per_step": msb / kb,
                            "frac_bf16_sustained_per_gpu": tfb / world / peak_tf}
-        mb.close()
+        vd.close_data_parallel(mb) if world > 1 else mb.close()
         x = make_problem()
         # c4: full VB (VAEB.py --full_varational, getFVBL), MNIST Nz = 2 / 10, M = 100; replicas when N > 1
         for zz in (2, 10):

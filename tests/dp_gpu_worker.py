@@ -65,7 +65,7 @@ def main():
             assert same, "ranks hold different parameters after the replicated Adagrad step"
             res["cases"].append({"precision": prec, "global_rows": MG, "bound_rel_err": abs(sg - sg_ref) / abs(sg_ref),
                                  "worst_grad_violation_ratio": worst, "ranks_bit_identical": same})
-        m.close()
+        vd.close_data_parallel(m)
     if rank == 0:
         with open(out_path, "w") as f:
             json.dump(res, f)

@@ -13,9 +13,9 @@ from tests.util import assert_close_tensor
 pytestmark = pytest.mark.gpu
 
 
-def _model(x, H, Z, M, L, est, params, precision):
+def _model(x, H, Z, M, L, est, params, precision, continuous=False):
     import vaeb_b200
-    return vaeb_b200.VAEB(x, False, H, Z, M, L, 0.01, est == "LA", False, params, precision=precision)
+    return vaeb_b200.VAEB(x, continuous, H, Z, M, L, 0.01, est == "LA", False, params, precision=precision)
 
 
 def _rand_params(D, H, Z, seed, scale):
@@ -23,23 +23,23 @@ def _rand_params(D, H, Z, seed, scale):
     return [rng.normal(0, scale, s).astype(np.float32) for s in O.param_shapes(D, H, Z, False)]
 
 
-def _check(x, H, Z, M, L, est, params, precision, seed, idx=1):
+def _check(x, H, Z, M, L, est, params, precision, seed, idx=1, continuous=False):
     rng = np.random.RandomState(seed)
     eps = rng.normal(size=(L, M, Z)).astype(np.float32)
-    m = _model(x, H, Z, M, L, est, params, precision)
-    o = O.OracleVAEB(x, False, H, Z, M, L=L, estimator=est, params=params, dtype=np.float64)
+    m = _model(x, H, Z, M, L, est, params, precision, continuous)
+    o = O.OracleVAEB(x, continuous, H, Z, M, L=L, estimator=est, params=params, dtype=np.float64)
     xb = x[idx * M:(idx + 1) * M]
     sg_ref, rows_ref, g_ref = o.grads(xb, eps)
     sg, rows, g = m.gradients(index=idx, eps=eps)
     if precision == "bf16x3":
         assert sg == pytest.approx(sg_ref, rel=1e-4)
         np.testing.assert_allclose(rows, rows_ref, rtol=1e-4)
-        for a, b, n in zip(g, g_ref, O.param_names(False)):
+        for a, b, n in zip(g, g_ref, O.param_names(continuous)):
             assert_close_tensor(a, b, 1e-4, floor=0.1, name="grad " + n)
     else:
         assert sg == pytest.approx(sg_ref, rel=1e-2)
         np.testing.assert_allclose(rows, rows_ref, rtol=1e-2)
-        for a, b, n in zip(g, g_ref, O.param_names(False)):
+        for a, b, n in zip(g, g_ref, O.param_names(continuous)):
             assert_close_tensor(a, b, 3e-2, floor=1.0, name="grad " + n)
     # the same numbers through the host-staged path (x mirrored per call) and through validate
     sg2, rows2, g2 = m.gradients(x=xb, eps=eps)
@@ -47,7 +47,8 @@ def _check(x, H, Z, M, L, est, params, precision, seed, idx=1):
     for a, b in zip(g, g2):
         np.testing.assert_array_equal(a, b)
     v, vr = m.validate(xb, eps=eps, per_row=True)
-    np.testing.assert_allclose(vr, rows, rtol=1e-6)
+    # (bf16 tier at large batch: validate runs the latent layers in fp32, the training step on the tensor cores in bf16)
+    np.testing.assert_allclose(vr, rows, rtol=1e-6 if precision == "bf16x3" else 1e-3)
     ret = m.update(idx, eps=eps)
     assert float(ret) == pytest.approx(sg_ref / M, rel=1e-4 if precision == "bf16x3" else 1e-2)
     m.close()
@@ -128,34 +129,40 @@ def test_tc_training_tracks_fp32_training():
     np.testing.assert_allclose(out["bf16"], out["fp32"], rtol=2e-2)
 
 
-def test_tc_rejects_gaussian_decoder():
-    import vaeb_b200
-    with pytest.raises(ValueError, match="Bernoulli"):
-        vaeb_b200.VAEB(np.zeros((8, 6), np.float32), True, 4, 2, 4, 1, 0.01, False, False, precision="bf16")
+@pytest.mark.parametrize("precision,M,est", [("bf16x3", 100, "LB"), ("bf16x3", 4096, "LB"), ("bf16x3", 1152, "LA"),
+                                              ("bf16", 1152, "LB"), ("bf16", 100, "LB")])
+def test_tc_step_gaussian_decoder(precision, M, est):
+    """Gaussian decoder on the tensor cores: the output layer is ONE GEMM over the interleaved
+    columns [W2|W6]' (VAEB.py:257-263), log-density and both deltas in its epilogue (:304-307), dgrad over K = 2D, the
+    [W2|W6]' weight gradient de-interleaved by the slice reduction.  C1's shape (Frey 560-200-2), M = 100 (layer
+    launches) and large batches (every contraction on tcgen05, one weight-gradient launch up to 4096 rows)."""
+    D, H, Z = 560, 200, 2
+    rng = np.random.RandomState(77)
+    x = np.clip(rng.normal(0.5, 0.2, (2 * M, D)), 0.01, 0.99).astype(np.float32)
+    params = [rng.normal(0, 0.05, s).astype(np.float32) for s in O.param_shapes(D, H, Z, True)]
+    _check(x, H, Z, M, 1, est, params, precision, 31, idx=1, continuous=True)
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
-def test_c3_full_size_persistent_kernels_match_oracle(precision):
-    """BASELINE config C3 at its full per-GPU size (M = 16384 rows, 784-500-20): at this size the activation layers
-    run in the persistent tcgen05 kernel (128 x 256 tiles, two TMEM accumulators) and no fp32 activations are kept.
-    Bound, per-row bounds and every gradient tensor against the fp64 oracle; the bound is also the sum of its rows
-    (size-independent property)."""
+def test_tc_gaussian_updates_match_fp32_path():
+    """Updates at the C1 shape, M = 2048: the tensor-core Gaussian path (bf16x3) lands where the fp32 kernels do -- the
+    bounds of three consecutive updates, and the first Adagrad step wherever it is well conditioned (it is
+    lr * g / (|g| + 1e-6): entries with |g| ~ 0 keep only a sign that rounding decides; tests/test_gpu_parity.py)."""
     import vaeb_b200
-    M, Z = 16384, 20
-    x = O.synthetic_mnist(M)
-    params = _rand_params(784, 500, Z, 7, 0.05)
-    eps = np.random.RandomState(41).normal(size=(1, M, Z)).astype(np.float32)
-    m = vaeb_b200.VAEB(x, False, 500, Z, M, 1, 0.01, False, False, params, precision=precision)
-    o = O.OracleVAEB(x, False, 500, Z, M, L=1, estimator="LB", params=params, dtype=np.float64)
-    sg_ref, rows_ref, g_ref = o.grads(x, eps)
-    sg, rows, g = m.gradients(index=0, eps=eps)
-    tol, gtol, floor = (1e-2, 3e-2, 1.0) if precision == "bf16" else (1e-4, 1e-4, 0.1)
-    assert sg == pytest.approx(sg_ref, rel=tol)
-    assert float(np.sum(rows, dtype=np.float64)) == pytest.approx(sg, rel=1e-5)
-    np.testing.assert_allclose(rows, rows_ref, rtol=tol)
-    for a, b, n in zip(g, g_ref, O.param_names(False)):
-        assert_close_tensor(a, b, gtol, floor=floor, name="grad " + n)
-    # one update through the same kernels moves the parameters like the oracle's Adagrad step
-    before = float(m.update(0, eps=eps))
-    assert before == pytest.approx(o.update(0, eps), rel=tol)
-    m.close()
+    D, H, Z, M = 560, 200, 2, 2048
+    rng = np.random.RandomState(78)
+    x = np.clip(rng.normal(0.5, 0.2, (2 * M, D)), 0.01, 0.99).astype(np.float32)
+    params = [rng.normal(0, 0.05, s).astype(np.float32) for s in O.param_shapes(D, H, Z, True)]
+    eps = rng.normal(size=(1, M, Z)).astype(np.float32)
+    out = {}
+    for prec in ("fp32", "bf16x3"):
+        m = vaeb_b200.VAEB(x, True, H, Z, M, 1, 0.01, False, False, params, precision=prec)
+        _, _, g = m.gradients(index=0, eps=eps)
+        b0 = float(m.update(0, eps=eps))
+        after = m.get_params()
+        bounds = [b0] + [float(m.update(i % 2, eps=eps)) for i in (1, 2)]
+        out[prec] = (bounds, after, g)
+        m.close()
+    np.testing.assert_allclose(out["bf16x3"][0], out["fp32"][0], rtol=2e-4)
+    for a, b, q0, gr in zip(out["bf16x3"][1], out["fp32"][1], params, out["fp32"][2]):
+        well = np.abs(gr) > 1e-2 * np.abs(gr).max()
+        np.testing.assert_allclose((a - q0)[well], (b - q0)[well], rtol=5e-3, atol=1e-7)

@@ -24,6 +24,6 @@ for prec in sys.argv[1].split(","):
         if rank == 0:
             print("%s global M=%d on %d GPUs (p2p %s): %.1f us/update (%.1f M datapoints/s) bound %.3f" %
                   (prec, MG, world, os.environ.get("VAEB_DP_P2P", "1"), 1e6 * dt, MG / dt / 1e6, float(out[-1])), flush=True)
-        m.close()
+        vd.close_data_parallel(m)
 dist.barrier()
 dist.destroy_process_group()

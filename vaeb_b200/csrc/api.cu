@@ -116,7 +116,8 @@ int ensure_ws(vaeb_handle* h, int64_t enc, int64_t dec, bool grads) {
   grads = grads || w.with_grads;
   free_ws(w);
   const int D = h->D, H = h->H, Z = h->Z;
-  const int64_t T = std::max<int64_t>((D + 31) / 32, 4 * ((D + 63) / 64));   // row-sum partials per row
+  const int Dd = h->cont && h->tc.active ? 2 * D : D;      // tensor-core Gaussian head: 2 D interleaved columns
+  const int64_t T = std::max<int64_t>((D + 31) / 32, 4 * ((Dd + 63) / 64));   // row-sum partials per row
   auto A = [&](float** p, int64_t n) -> int {
     VAEB_CUDA(cudaMalloc((void**)p, (size_t)std::max<int64_t>(n, 1) * sizeof(float)));
     return VAEB_OK;
@@ -152,7 +153,8 @@ int tc_ensure(vaeb_handle* h, int64_t rows, int64_t R) {
   if (b.ldh == 0) {
     // rows of the mirrors start on 32-byte sectors: a thread of a tcgen05 epilogue writes 16 bf16 = one whole sector
     // (and on whole 64-element column groups: the MN-major operands are loaded with one 3-D TMA box per tile)
-    b.ldh = (H + 1 + 63) / 64 * 64; b.ldd = (D + 1 + 63) / 64 * 64; b.ldx = b.ldd;
+    const int Dd = h->cont ? 2 * D : D;        // Gaussian decoder: [W2|W6]' and its deltas, interleaved
+    b.ldh = (H + 1 + 63) / 64 * 64; b.ldd = (Dd + 1 + 63) / 64 * 64; b.ldx = (D + 1 + 63) / 64 * 64;
     VAEB_TRY(grow_bytes(&b.w3h, (size_t)D * b.ldh * 2));
     VAEB_TRY(grow_bytes(&b.w2h, (size_t)H * b.ldd * 2));
     VAEB_CUDA(cudaMemsetAsync(b.w3h, 0, (size_t)D * b.ldh * 2, h->stream));
@@ -287,7 +289,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
     if (bna == 128 && env_bn == 0 && !chain) {
       const int rb = (rows + 127) / 128;
       if (rb * ((H + 127) / 128) < 96) bna = 64;
-      if (rb * ((D + 127) / 128) < 96) bnd = 64;
+      if (rb * (((h->cont ? 2 * D : D) + 127) / 128) < 96) bnd = 64;
     }
     // Programmatic dependent launch for the one-tile-per-CTA kernels: bf16x3 (one CTA per SM: an early dependent grid
     // never takes slots from the running one; 16384 rows: 523 -> 499 us per update) and, in plain bf16, whenever the
@@ -316,7 +318,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
     }
     x_mirror_hi = b.xh; x_mirror_lo = t.ns == 2 ? b.xl : nullptr;
     if (t.key_rows != rows || t.key_R != R || t.key_data != rows_data || t.key_bn != (bna * 1024 + bn) * 1024 + bnd || t.key_x != b.xh) {
-      VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bna, Z, bn, bnd));
+      VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bna, Z, bn, bnd, h->cont ? 2 * D : D));
       t.key_rows = rows; t.key_R = R; t.key_data = rows_data; t.key_bn = (bna * 1024 + bn) * 1024 + bnd; t.key_x = b.xh;
     }
     if (want_grads && b.heh && b.zh && b.d1h && b.ddh && latent_large_batch(rows, H, Z, L) && t.weights_ready &&
@@ -325,11 +327,11 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
     } else if (want_grads && b.heh && b.zh && b.d1h && b.ddh && latent_large_batch(rows, H, Z, L))
       PH("weight mirrors / transposes -> bf16 (one launch)", 0, 12.0 * dD * dH + 60.0 * dZ * dH,
          tc_prepare_weights(st, lc, T_(h, theta, l.iW3), T_(h, theta, l.iW2), T_(h, theta, l.iW4), T_(h, theta, l.iW5),
-                            T_(h, theta, l.iW1), b, h->d_w45t, D, H, Z));
+                            T_(h, theta, l.iW1), b, h->d_w45t, D, H, Z, h->cont ? T_(h, theta, l.iW6) : nullptr));
     else
       PH("mirror W3,W2 -> bf16", 0, 12.0 * dD * dH,
          tc_mirror_weights(st, lc, T_(h, theta, l.iW3), b.w3h, b.w3l, D, H, b.ldh, T_(h, theta, l.iW2), b.w2h, b.w2l,
-                           b.ldd));
+                           b.ldd, h->cont ? T_(h, theta, l.iW6) : nullptr));
   }
   const TcBuffers& tb = t.data;
   // large-batch training on the tensor-core path: the thin weight gradients also run on tcgen05 (their operands'
@@ -346,7 +348,8 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
 #define WGRAD_ALL_CALL                                                                                                  \
   tc_wgrad_all(st, lc, t.maps, t.ns, bn, R, rows, D, H, Z, x_row_off, T_(h, grads, l.iW2), T_(h, grads, l.ib2),        \
                T_(h, grads, l.iW1), T_(h, grads, l.ib1), T_(h, grads, l.iW4), T_(h, grads, l.ib4), T_(h, grads, l.iW5), \
-               T_(h, grads, l.ib5), T_(h, grads, l.iW3), T_(h, grads, l.ib3), tb.wg_scratch, wg_region, defer, t.n_sm)
+               T_(h, grads, l.ib5), T_(h, grads, l.iW3), T_(h, grads, l.ib3), tb.wg_scratch, wg_region, defer, t.n_sm,    \
+               h->cont ? T_(h, grads, l.iW6) : nullptr, h->cont ? T_(h, grads, l.ib6) : nullptr)
   // ---- large-batch training step: the seven activation layers are ONE persistent launch (tc_chain.cu) ----------
   if (tcl && chain) {
     const int cbn = chain_pair ? 256 : bna;
@@ -434,7 +437,13 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   const float scale = w / (float)L;
   const float* W6 = h->cont ? T_(h, theta, l.iW6) : nullptr;
   const float* b6 = h->cont ? T_(h, theta, l.ib6) : nullptr;
-  if (tcp)
+  if (tcp && h->cont)
+    PH("dec2 h.[W2|W6]+Gaussian loglik [tcgen05]", 4 * dR * dH * dD,
+       2.0 * t.ns * (dR * dH + 2 * dH * dD) + 4 * dr * dD + (want_grads ? 4.0 * t.ns * dR * dD : 0.0),
+       tc_dec2_gaussian(st, lc, t.maps, t.ns, bnd, R, H, D, T_(h, theta, l.ib2), b6, tcl ? nullptr : x, 1, rows, scale,
+                        want_grads ? tb.da2h : nullptr, want_grads ? tb.da2l : nullptr, tb.ldd, s.partial, &tiles,
+                        x_mirror_hi, x_mirror_lo, tb.ldx, x_row_off));
+  else if (tcp)
     PH("dec2 h.W2+loglik [tcgen05]", 2 * dR * dH * dD,
        2.0 * t.ns * (dR * dH + dH * dD) + 4 * dr * dD + (want_grads ? 2.0 * t.ns * dR * dD : 0.0),
        tc_dec2_bernoulli(st, lc, t.maps, t.ns, bnd, R, H, D, T_(h, theta, l.ib2), tcl ? nullptr : x, 1, rows, scale,
@@ -456,9 +465,10 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   if (tcp) {
     if (!merged_wgrad)
       PH("wgrad W2,b2 [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dH + dR * dD) + 4 * dH * dD,
-         tc_wgrad2(st, lc, t.maps, t.ns, bn, R, H, D, T_(h, grads, l.iW2), T_(h, grads, l.ib2), tb.wg_scratch, defer));
-    PH("dgrad h_d (.W2^T)*(1-h^2) [tcgen05]", 2 * dR * dH * dD, 2.0 * t.ns * (dR * dD + dH * dD) + 8 * dR * dH,
-       tc_dgrad_hd(st, lc, t.maps, t.ns, bna, R, D, H, tcl ? nullptr : s.h_d, tcl ? nullptr : s.da1,
+         tc_wgrad2(st, lc, t.maps, t.ns, bn, R, H, h->cont ? 2 * D : D, T_(h, grads, l.iW2), T_(h, grads, l.ib2), tb.wg_scratch,
+                   defer, h->cont ? T_(h, grads, l.iW6) : nullptr, h->cont ? T_(h, grads, l.ib6) : nullptr));
+    PH("dgrad h_d (.W2^T)*(1-h^2) [tcgen05]", 2 * dR * dH * dD * c, 2.0 * t.ns * c * (dR * dD + dH * dD) + 8 * dR * dH,
+       tc_dgrad_hd(st, lc, t.maps, t.ns, bna, R, h->cont ? 2 * D : D, H, tcl ? nullptr : s.h_d, tcl ? nullptr : s.da1,
                    tcl ? tb.d1h : nullptr, tcl ? tb.d1l : nullptr, tb.ldh, tb.hdh, tb.hdl));
   } else {
     PH("wgrad W2,b2", 2 * dR * dH * dD, 4 * (dR * dH + dR * dD + dH * dD),
@@ -597,6 +607,7 @@ int enqueue_update(vaeb_handle* h, const float* d_xrows, int rows, const float* 
       tail.D = h->D; tail.H = h->H; tail.Z = h->Z; tail.ldh = b.ldh; tail.ldd = b.ldd; tail.ldq = b.ldq;
       tail.oW3 = l.off[l.iW3]; tail.oW4 = l.off[l.iW4]; tail.oW5 = l.off[l.iW5]; tail.oW1 = l.off[l.iW1];
       tail.oW2 = l.off[l.iW2];
+      tail.oW6 = h->cont ? l.off[l.iW6] : -1;
       tail.bar = t.tail_bar;
       tail.world = h->world; tail.rank = h->rank;
       for (int r = 0; r < h->world && dp; ++r) {
@@ -772,8 +783,6 @@ int vaeb_create(const vaeb_config* cfg, vaeb_handle** out) {
   VAEB_REQUIRE(cfg->estimator >= 0 && cfg->estimator <= 3, "unknown estimator");
   VAEB_REQUIRE(cfg->variant == 0 || cfg->variant == 1, "unknown variant");
   VAEB_REQUIRE(cfg->precision >= VAEB_PREC_FP32 && cfg->precision <= VAEB_PREC_BF16X3, "unknown precision");
-  VAEB_REQUIRE(cfg->precision == VAEB_PREC_FP32 || !cfg->continuous,
-               "the tensor-core precisions cover the Bernoulli decoder; use fp32 for the Gaussian decoder");
   const bool fvb = cfg->estimator >= VAEB_EST_FVB;
   // getFVBL overwrites `mu` inside the sample loop (VAEB.py:361): undefined for L > 1
   VAEB_REQUIRE(!(fvb && cfg->L != 1), "full-VB bound is only defined for L == 1 (VAEB.py:361)");

@@ -233,6 +233,57 @@ struct EpiBernoulliTc {     // VAEB.py:263,311: term = x*a - softplus(a); da = s
   }
 };
 
+// Gaussian decoder on the tensor cores (VAEB.py:257-258, 306-307): the output layer is ONE GEMM over the interleaved
+// columns [W2|W6]' (column 2d = W2[:, d], 2d + 1 = W6[:, d]), so the thread that owns an accumulator row holds
+// (a_d, lv_d) of eight pixels per 16-column chunk.  term = -log(2 pi)/2 - lv/2 - (x - mu)^2 e^{-lv} / 2, mu = sigmoid(a);
+// deltas scale * (x - mu) e^{-lv} mu (1 - mu) and scale * (-1/2 + (x - mu)^2 e^{-lv} / 2) go to the interleaved mirror
+// [rows, ldda] that the backward GEMMs (dgrad over K = 2D, the [W2|W6]' weight gradient) read.
+struct EpiGaussianTc {
+  static constexpr bool PREFETCH = false;
+  const float* b2; const float* b6; const float* x; int ldx; int x_div; int x_mod; float scale;
+  __nv_bfloat16* da_hi; __nv_bfloat16* da_lo; int ldda; float* partial;
+  const __nv_bfloat16* xm_hi; const __nv_bfloat16* xm_lo; int ldxm; int xm_off;      // x == nullptr: x from its bf16 mirror
+  float acc;
+  __device__ __forceinline__ void begin() { acc = 0.f; }
+  __device__ __forceinline__ void split(int) {}
+  __device__ __forceinline__ void one(float a, float lv, float xv, float& d_a, float& d_lv) {
+    const float mu = 1.0f / (1.0f + __expf(-a));
+    const float d = xv - mu;
+    const float r = d * __expf(-lv);
+    acc += -0.91893853320467274178f - 0.5f * lv - 0.5f * d * r;
+    d_a = scale * r * mu * (1.0f - mu);
+    d_lv = scale * (-0.5f + 0.5f * d * r);
+  }
+  __device__ __forceinline__ void chunk(int row, bool ok, int col0, int N, const float* v, const uint32_t* = nullptr) {
+    if (!ok) return;
+    const int xrow = (row / x_div) % x_mod;
+    const int d0 = col0 >> 1;                               // first pixel of the chunk; N = 2 D
+    float out[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int d = d0 + j;
+      out[2 * j] = out[2 * j + 1] = 0.f;
+      if (2 * d + 1 < N) {
+        float xv;
+        if (x) xv = x[(size_t)xrow * ldx + d];
+        else xv = __bfloat162float(xm_hi[(size_t)(xm_off + xrow) * ldxm + d]) +
+                  (xm_lo ? __bfloat162float(xm_lo[(size_t)(xm_off + xrow) * ldxm + d]) : 0.f);
+        one(v[2 * j] + b2[d], v[2 * j + 1] + b6[d], xv, out[2 * j], out[2 * j + 1]);
+      }
+    }
+    if (!da_hi) return;
+    __nv_bfloat16* dh = da_hi + (size_t)row * ldda + col0;
+    __nv_bfloat16* dl = da_lo ? da_lo + (size_t)row * ldda + col0 : nullptr;
+    if (vec_ok(dh, col0, N) && vec_ok(dl, col0, N)) { st16_split(dh, dl, out); return; }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (col0 + j < N) put_split(dh, dl, (size_t)j, out[j]);
+  }
+  __device__ __forceinline__ void end(int row, bool ok, int tile_n, int n_tiles) {
+    if (ok) partial[(size_t)row * n_tiles + tile_n] = acc;
+  }
+};
+
 struct EpiWgradTc {         // rows < Hreal -> gW[Hreal, N]; row == Hreal (the ones column of A) -> gb
   float* gW; float* gb; int Hreal; int ld;
   float* scratch; size_t split_stride;   // split-K: slice z writes [gW | gb] at scratch + z * split_stride

@@ -513,6 +513,12 @@ wgrad_reduce_all_kernel(TcReduceJobs jobs) {
   for (int z = 0; z < j.splits; ++z) a += j.scratch[(size_t)z * j.stride + i];
   if (j.kind == 0) {
     if (i < j.n_w) j.gW[i] = a; else j.gb[i - j.n_w] = a;
+  } else if (j.kind == 2) {            // interleaved Gaussian head [(H+1) x 2D]: column 2d -> W2 / b2, 2d + 1 -> W6 / b6
+    const int D = j.Z, H = j.H;
+    const int k = i / (2 * D), c = i - k * 2 * D, d = c >> 1;
+    float* gW = (c & 1) ? j.gW2 : j.gW;
+    float* gb = (c & 1) ? j.gb2 : j.gb;
+    if (k < H) gW[(size_t)k * D + d] = a; else gb[d] = a;
   } else {
     const int Z = j.Z, H = j.H;
     const int k = i / (2 * Z), c = i - k * 2 * Z;
@@ -543,9 +549,25 @@ bool add_reduce_job(TcReduceJobs* jobs, const TcReduceJob& j) {
 
 // `defer` != nullptr: the slices stay in `scratch` (a region of its own) and their reduction is appended to the list
 cudaError_t tc_wgrad_generic(cudaStream_t st, int64_t* launches, const LayerMaps& maps, int ns, int bn, int Kred,
-                             int Hreal, int N, int a_row_off, float* gW, float* gb, float* scratch, TcReduceJobs* defer) {
-  const int splits = scratch ? tc_wgrad_splits(Hreal + 1, N, Kred, bn, ns) : 1;
+                             int Hreal, int N, int a_row_off, float* gW, float* gb, float* scratch, TcReduceJobs* defer,
+                             float* gW6 = nullptr, float* gb6 = nullptr) {
+  int splits = scratch ? tc_wgrad_splits(Hreal + 1, N, Kred, bn, ns) : 1;
   const size_t stride = (size_t)(Hreal + 1) * N;
+  if (gW6) {
+    // Gaussian head: the slice holds the interleaved columns of [W2|W6]' -- always through scratch, the reduction
+    // also de-interleaves (N = 2D)
+    if (!scratch) return cudaErrorInvalidValue;
+    while (splits > 1 && (size_t)splits * stride > tc_wgrad_scratch_elems(0, 0)) --splits;
+    EpiWgradTc epi{nullptr, nullptr, Hreal, N, scratch, stride};
+    ++*launches;
+    cudaError_t e = dispatch_layer<true, true>(st, ns, bn, maps, epi, Hreal + 1, N, Kred, a_row_off, splits);
+    if (e != cudaSuccess) return e;
+    const TcReduceJob job{scratch, splits, stride, (Hreal + 1) * N, 0, gW, gb, gW6, gb6, 2, Hreal, N / 2};
+    if (defer && add_reduce_job(defer, job)) return cudaSuccess;
+    TcReduceJobs one;
+    one.job[0] = job; one.n = 1;
+    return reduce_all_impl(st, launches, one);
+  }
   EpiWgradTc epi{gW, gb, Hreal, N, splits > 1 ? scratch : nullptr, stride};
   ++*launches;
   cudaError_t e = dispatch_layer<true, true>(st, ns, bn, maps, epi, Hreal + 1, N, Kred, a_row_off, splits);
@@ -573,20 +595,26 @@ split_matrix_kernel(const float* __restrict__ src, int64_t rows, int cols, int l
   put_split(hi, lo, (size_t)i, v);
 }
 
-struct MirrorSeg { const float* src; __nv_bfloat16* hi; __nv_bfloat16* lo; int rows, cols, ld; };
+// src2 != nullptr: the mirror interleaves two matrices column-wise (column 2c = src, 2c + 1 = src2: the Gaussian head)
+struct MirrorSeg { const float* src; __nv_bfloat16* hi; __nv_bfloat16* lo; int rows, cols, ld; const float* src2; };
 __global__ void __launch_bounds__(256)
 mirror_weights_kernel(MirrorSeg s0, MirrorSeg s1) {
   const MirrorSeg& s = blockIdx.y == 0 ? s0 : s1;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s.src == nullptr || i >= (int64_t)s.rows * s.cols) return;
   const int r = (int)(i / s.cols), c = (int)(i % s.cols);
-  put_split(s.hi, s.lo, (size_t)r * s.ld + c, s.src[i]);
+  if (s.src2) {
+    put_split(s.hi, s.lo, (size_t)r * s.ld + 2 * c, s.src[i]);
+    put_split(s.hi, s.lo, (size_t)r * s.ld + 2 * c + 1, s.src2[i]);
+  } else {
+    put_split(s.hi, s.lo, (size_t)r * s.ld + c, s.src[i]);
+  }
 }
 
 // Every per-step weight preparation of the large-batch path in ONE launch (blockIdx.y = task):
 //   0: W3 -> bf16 mirror   1: W2 -> mirror   2: [W4^T;W5^T] fp32 + mirror   3: interleaved heads mirror   4: W1 -> mirror
 struct PrepArgs {
-  const float *W3, *W2, *W4, *W5, *W1;
+  const float *W3, *W2, *W4, *W5, *W1, *W6;      // W6 != nullptr (Gaussian decoder): the W2 mirror holds [W2|W6]' interleaved
   __nv_bfloat16 *w3h, *w3l, *w2h, *w2l, *w45h, *w45l, *whh, *whl, *w1h, *w1l;
   float* w45t;
   int D, H, Z, ldh, ldd, ldq;
@@ -621,7 +649,15 @@ prepare_weights_kernel(PrepArgs a) {
       mirror_quad(a.W3, a.w3h, a.w3l, i, D, H, a.ldh);
       break;
     case 1:
-      mirror_quad(a.W2, a.w2h, a.w2l, i, H, D, a.ldd);
+      if (a.W6) {                        // column 2d = W2[:, d], 2d + 1 = W6[:, d]
+        for (int64_t e = 4 * i; e < 4 * i + 4 && e < (int64_t)H * D; ++e) {
+          const int k = (int)(e / D), d = (int)(e % D);
+          put_split(a.w2h, a.w2l, (size_t)k * a.ldd + 2 * d, a.W2[e]);
+          put_split(a.w2h, a.w2l, (size_t)k * a.ldd + 2 * d + 1, a.W6[e]);
+        }
+      } else {
+        mirror_quad(a.W2, a.w2h, a.w2l, i, H, D, a.ldd);
+      }
       break;
     case 2:
       if (i < (int64_t)2 * Z * H) {
@@ -648,8 +684,9 @@ prepare_weights_kernel(PrepArgs a) {
 }  // namespace
 
 cudaError_t tc_prepare_weights(cudaStream_t st, int64_t* launches, const float* W3, const float* W2, const float* W4,
-                               const float* W5, const float* W1, const TcBuffers& b, float* w45t, int D, int H, int Z) {
-  PrepArgs a{W3, W2, W4, W5, W1,
+                               const float* W5, const float* W1, const TcBuffers& b, float* w45t, int D, int H, int Z,
+                               const float* W6) {
+  PrepArgs a{W3, W2, W4, W5, W1, W6,
              (__nv_bfloat16*)b.w3h, (__nv_bfloat16*)b.w3l, (__nv_bfloat16*)b.w2h, (__nv_bfloat16*)b.w2l,
              (__nv_bfloat16*)b.w45h, (__nv_bfloat16*)b.w45l, (__nv_bfloat16*)b.whh, (__nv_bfloat16*)b.whl,
              (__nv_bfloat16*)b.w1h, (__nv_bfloat16*)b.w1l, w45t, D, H, Z, b.ldh, b.ldd, b.ldq};
@@ -683,9 +720,9 @@ cudaError_t tc_split_matrix(cudaStream_t st, int64_t* launches, const float* src
 }
 
 cudaError_t tc_mirror_weights(cudaStream_t st, int64_t* launches, const float* w3, void* w3h, void* w3l, int D, int H,
-                              int ldh, const float* w2, void* w2h, void* w2l, int ldd) {
-  MirrorSeg s0{w3, (__nv_bfloat16*)w3h, (__nv_bfloat16*)w3l, D, H, ldh};
-  MirrorSeg s1{w2, (__nv_bfloat16*)w2h, (__nv_bfloat16*)w2l, H, D, ldd};
+                              int ldh, const float* w2, void* w2h, void* w2l, int ldd, const float* w6) {
+  MirrorSeg s0{w3, (__nv_bfloat16*)w3h, (__nv_bfloat16*)w3l, D, H, ldh, nullptr};
+  MirrorSeg s1{w2, (__nv_bfloat16*)w2h, (__nv_bfloat16*)w2l, H, D, ldd, w6};
   const int64_t n = (int64_t)D * H;
   mirror_weights_kernel<<<dim3((unsigned)((n + 255) / 256), 2), 256, 0, st>>>(s0, s1);
   ++*launches;
@@ -711,8 +748,9 @@ static int make_pair_mn(CUtensorMap* hi, CUtensorMap* lo, const void* bh, const 
 
 // bn: UMMA N of the activation layers (tc_act_bn); bn_w: of the weight-gradient GEMMs
 int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z, int bn_w,
-                  int bn_d) {
+                  int bn_d, int Dd) {
   const uint32_t gd = (uint32_t)(bn_d > 0 ? bn_d : bn) / 64;
+  if (Dd <= 0) Dd = D;      // width of the decoder output layer: D, or 2 D for the interleaved Gaussian head
   const uint32_t ga = BM / 64, gb = (uint32_t)bn / 64, gw = (uint32_t)bn_w / 64;
   const uint32_t kw = b.w3l ? BK : 2 * BK;      // contraction rows per box of the weight-gradient operands (stage_k)
   // enc1: A = x mirror [rows_data, D] K-major (the ones column at D stays out of the map), B = W3 [D, H] MN-major
@@ -722,15 +760,15 @@ int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows,
   // dec2: A = h_d mirror [R, H] K-major, B = W2 [H, D] MN-major
   LayerMaps* d2 = reinterpret_cast<LayerMaps*>(m->dec2);
   VAEB_TRY(make_pair(&d2->a_hi, &d2->a_lo, b.hdh, b.hdl, R, H, b.ldh, BM));
-  VAEB_TRY(make_pair_mn(&d2->b_hi, &d2->b_lo, b.w2h, b.w2l, H, D, b.ldd, gd));
+  VAEB_TRY(make_pair_mn(&d2->b_hi, &d2->b_lo, b.w2h, b.w2l, H, Dd, b.ldd, gd));
   // dgrad h_d: A = da2 mirror [R, D] K-major, B = W2 [H, D] K-major (N = H rows)
   LayerMaps* dg = reinterpret_cast<LayerMaps*>(m->dgrad);
-  VAEB_TRY(make_pair(&dg->a_hi, &dg->a_lo, b.da2h, b.da2l, R, D, b.ldd, BM));
-  VAEB_TRY(make_pair(&dg->b_hi, &dg->b_lo, b.w2h, b.w2l, H, D, b.ldd, (uint32_t)bn));
+  VAEB_TRY(make_pair(&dg->a_hi, &dg->a_lo, b.da2h, b.da2l, R, Dd, b.ldd, BM));
+  VAEB_TRY(make_pair(&dg->b_hi, &dg->b_lo, b.w2h, b.w2l, H, Dd, b.ldd, (uint32_t)bn));
   // wgrad W2: A = h_d mirror [R, H+1] MN-major (ones column -> bias row), B = da2 mirror [R, D] MN-major
   LayerMaps* w2 = reinterpret_cast<LayerMaps*>(m->wgrad2);
   VAEB_TRY(make_pair_mn(&w2->a_hi, &w2->a_lo, b.hdh, b.hdl, R, H + 1, b.ldh, ga, kw));
-  VAEB_TRY(make_pair_mn(&w2->b_hi, &w2->b_lo, b.da2h, b.da2l, R, D, b.ldd, gw, kw));
+  VAEB_TRY(make_pair_mn(&w2->b_hi, &w2->b_lo, b.da2h, b.da2l, R, Dd, b.ldd, gw, kw));
   // wgrad W3: A = x mirror [rows_data, D+1] MN-major, B = da3 mirror [rows, H] MN-major
   LayerMaps* w3 = reinterpret_cast<LayerMaps*>(m->wgrad3);
   VAEB_TRY(make_pair_mn(&w3->a_hi, &w3->a_lo, b.xh, b.xl, rows_data, D + 1, b.ldx, ga, kw));
@@ -787,6 +825,17 @@ cudaError_t tc_dec2_bernoulli(cudaStream_t st, int64_t* launches, const TcMaps& 
   *n_tiles = ((D + bn - 1) / bn) * (EPI_WARPS / 4);
   ++*launches;
   return dispatch_layer<false, true>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.dec2), epi, R, D, H, 0);
+}
+
+cudaError_t tc_dec2_gaussian(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
+                             const float* b2, const float* b6, const float* x, int x_div, int x_mod, float scale, void* da_hi,
+                             void* da_lo, int ldda, float* partial, int* n_tiles, const void* xm_hi, const void* xm_lo,
+                             int ldxm, int xm_off) {
+  EpiGaussianTc epi{b2, b6, x, D, x_div, x_mod, scale, (__nv_bfloat16*)da_hi, (__nv_bfloat16*)da_lo, ldda, partial,
+                    (const __nv_bfloat16*)xm_hi, (const __nv_bfloat16*)xm_lo, ldxm, xm_off, 0.f};
+  *n_tiles = ((2 * D + bn - 1) / bn) * (EPI_WARPS / 4);
+  ++*launches;
+  return dispatch_layer<false, true>(st, ns, bn, *reinterpret_cast<const LayerMaps*>(m.dec2), epi, R, 2 * D, H, 0);
 }
 
 cudaError_t tc_dgrad_hd(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int D, int H,
@@ -892,10 +941,11 @@ size_t tc_wgrad_scratch_elems(int D, int H) {
   return (size_t)148 * BM * 128;          // splits * Mo * No <= (148 / tiles) * tiles * 128 * 128
 }
 
+// gW6 != nullptr (Gaussian decoder): D is the width of the interleaved head (2 x pixels); the reduction de-interleaves
 cudaError_t tc_wgrad2(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
-                      float* gW2, float* gb2, float* scratch, TcReduceJobs* defer) {
+                      float* gW2, float* gb2, float* scratch, TcReduceJobs* defer, float* gW6, float* gb6) {
   return tc_wgrad_generic(st, launches, *reinterpret_cast<const LayerMaps*>(m.wgrad2), ns, bn, R, H, D, 0, gW2, gb2,
-                          scratch, defer);
+                          scratch, defer, gW6, gb6);
 }
 
 cudaError_t tc_wgrad3(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int D, int H,
@@ -914,8 +964,9 @@ bool tc_wgrad_merged_supported(int rows) {
 cudaError_t tc_wgrad_all(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int rows, int D, int H,
                          int Z, int x_row_off, float* gW2, float* gb2, float* gW1, float* gb1, float* gW4, float* gb4,
                          float* gW5, float* gb5, float* gW3, float* gb3, float* scratch, size_t region, TcReduceJobs* jobs,
-                         int n_sm) {
+                         int n_sm, float* gW6, float* gb6) {
   WgradAllArgs a;
+  const int Dd = gW6 ? 2 * D : D;      // Gaussian decoder: the W2 job is the interleaved head [W2|W6]'
   const int sk = ns == 1 ? 2 * BK : BK;
   auto fill = [&](int j, const unsigned char* maps, int Hreal, int N, int K, int off, float* scr, int splits) {
     WgradJob& J = a.job[j];
@@ -928,19 +979,21 @@ cudaError_t tc_wgrad_all(cudaStream_t st, int64_t* launches, const TcMaps& m, in
   };
   // one wave: the two wide gradients (28 tiles each at 128 x 128) share the SMs the thin ones leave
   const int thin_splits = 4;
-  const int wide_tiles = ((D + bn - 1) / bn) * ((H + 1 + BM - 1) / BM) + ((H + bn - 1) / bn) * ((D + 1 + BM - 1) / BM);
+  const int wide_tiles = ((Dd + bn - 1) / bn) * ((H + 1 + BM - 1) / BM) + ((H + bn - 1) / bn) * ((D + 1 + BM - 1) / BM);
   const int thin_tiles = ((H + bn - 1) / bn) * ((Z + 1 + BM - 1) / BM) + ((2 * Z + bn - 1) / bn) * ((H + 1 + BM - 1) / BM);
   int wide_splits = (n_sm - thin_tiles * thin_splits) / (wide_tiles > 0 ? wide_tiles : 1);
   if (wide_splits < 1) wide_splits = 1;
-  fill(0, m.wgrad2, H, D, R, 0, scratch, wide_splits);
+  fill(0, m.wgrad2, H, Dd, R, 0, scratch, wide_splits);
   fill(1, m.wgrad1, Z, H, R, 0, scratch + region, thin_splits);
   fill(2, m.wgrad45w, H, 2 * Z, rows, 0, scratch + 2 * region, thin_splits);
   fill(3, m.wgrad3, D, H, rows, x_row_off, scratch + 3 * region, wide_splits);
   a.n_jobs = 4;
   int blocks = 0;
   for (int j = 0; j < 4; ++j) { a.job[j].first_block = blocks; blocks += a.job[j].tiles_n * a.job[j].tiles_m * a.job[j].splits; }
-  const size_t s2 = (size_t)(H + 1) * D, s1 = (size_t)(Z + 1) * H, s45 = (size_t)(H + 1) * 2 * Z, s3 = (size_t)(D + 1) * H;
-  if (!add_reduce_job(jobs, TcReduceJob{scratch, a.job[0].splits, s2, H * D, D, gW2, gb2, nullptr, nullptr, 0, 0, 0}) ||
+  const size_t s2 = (size_t)(H + 1) * Dd, s1 = (size_t)(Z + 1) * H, s45 = (size_t)(H + 1) * 2 * Z, s3 = (size_t)(D + 1) * H;
+  const TcReduceJob j2 = gW6 ? TcReduceJob{scratch, a.job[0].splits, s2, (H + 1) * Dd, 0, gW2, gb2, gW6, gb6, 2, H, D}
+                             : TcReduceJob{scratch, a.job[0].splits, s2, H * D, D, gW2, gb2, nullptr, nullptr, 0, 0, 0};
+  if (!add_reduce_job(jobs, j2) ||
       !add_reduce_job(jobs, TcReduceJob{scratch + region, a.job[1].splits, s1, Z * H, H, gW1, gb1, nullptr, nullptr, 0, 0, 0}) ||
       !add_reduce_job(jobs, TcReduceJob{scratch + 2 * region, a.job[2].splits, s45, (H + 1) * 2 * Z, 0, gW4, gb4, gW5, gb5, 1, H, Z}) ||
       !add_reduce_job(jobs, TcReduceJob{scratch + 3 * region, a.job[3].splits, s3, D * H, H, gW3, gb3, nullptr, nullptr, 0, 0, 0}))

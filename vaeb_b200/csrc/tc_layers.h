@@ -47,13 +47,19 @@ void tc_set_pdl(bool on);
 // persistent kernel (large batches), else 128 / 64 with one tile per CTA
 int tc_act_bn(int rows, int n_min);
 // bn: UMMA N of the H-wide activation layers (enc1, dec1, both dgrads); bn_d (0: = bn): of dec2 (D wide)
+// Dd (0: = D): width of the decoder output layer -- 2 D for the Gaussian head's interleaved columns [W2|W6]'
 int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z, int bn_w,
-                  int bn_d = 0);
+                  int bn_d = 0, int Dd = 0);
+// Gaussian decoder (VAEB.py:257-258, 306-307): a|lv = h_d.[W2|W6]' + b, log-density and both deltas in the epilogue
+cudaError_t tc_dec2_gaussian(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
+                             const float* b2, const float* b6, const float* x, int x_div, int x_mod, float scale, void* da_hi,
+                             void* da_lo, int ldda, float* partial, int* n_tiles, const void* xm_hi = nullptr,
+                             const void* xm_lo = nullptr, int ldxm = 0, int xm_off = 0);
 
 cudaError_t tc_split_matrix(cudaStream_t st, int64_t* launches, const float* src, int64_t rows, int cols, int ld_src,
                             void* hi, void* lo, int ld_dst, int ones_col);
 cudaError_t tc_mirror_weights(cudaStream_t st, int64_t* launches, const float* w3, void* w3h, void* w3l, int D, int H,
-                              int ldh, const float* w2, void* w2h, void* w2l, int ldd);
+                              int ldh, const float* w2, void* w2h, void* w2l, int ldd, const float* w6 = nullptr);
 cudaError_t tc_enc1(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int D, int H,
                     int x_row_off, const float* b3, float* h_e, void* he_hi, void* he_lo, int ldm);
 cudaError_t tc_dec2_bernoulli(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
@@ -77,7 +83,8 @@ cudaError_t tc_wgrad1(cudaStream_t st, int64_t* launches, const TcMaps& m, int n
 // all per-step weight mirrors / transposes of the large-batch path in one launch (W3, W2, [W4^T;W5^T] incl. its fp32
 // copy w45t, the interleaved heads, W1)
 cudaError_t tc_prepare_weights(cudaStream_t st, int64_t* launches, const float* W3, const float* W2, const float* W4,
-                               const float* W5, const float* W1, const TcBuffers& b, float* w45t, int D, int H, int Z);
+                               const float* W5, const float* W1, const TcBuffers& b, float* w45t, int D, int H, int Z,
+                               const float* W6 = nullptr);
 // interleaved bf16 mirror of the two head weight matrices (so that one epilogue thread holds mu_j and ls_j together)
 cudaError_t tc_mirror_heads(cudaStream_t st, int64_t* launches, const float* W4, const float* W5, int H, int Z, void* hi,
                             void* lo, int ldq);
@@ -102,7 +109,8 @@ cudaError_t tc_wgrad45(cudaStream_t st, int64_t* launches, const TcMaps& m, int 
 // scratch: device floats for the split-K slices of a weight gradient (tc_wgrad_scratch_elems), or nullptr
 size_t tc_wgrad_scratch_elems(int D, int H);
 cudaError_t tc_wgrad2(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
-                      float* gW2, float* gb2, float* scratch, TcReduceJobs* defer = nullptr);
+                      float* gW2, float* gb2, float* scratch, TcReduceJobs* defer = nullptr, float* gW6 = nullptr,
+                      float* gb6 = nullptr);
 cudaError_t tc_wgrad3(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int rows, int D, int H,
                       int x_row_off, float* gW3, float* gb3, float* scratch, TcReduceJobs* defer = nullptr);
 
@@ -124,7 +132,7 @@ bool tc_wgrad_merged_supported(int rows);
 cudaError_t tc_wgrad_all(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int rows, int D, int H,
                          int Z, int x_row_off, float* gW2, float* gb2, float* gW1, float* gb1, float* gW4, float* gb4,
                          float* gW5, float* gb5, float* gW3, float* gb3, float* scratch, size_t region, TcReduceJobs* jobs,
-                         int n_sm);
+                         int n_sm, float* gW6 = nullptr, float* gb6 = nullptr);
 
 // ---- the tail of a large-batch update as one launch (tc_tail.cu) --------------------------------------------------
 // split-K slices -> gradient, bound, (N GPUs: reduce-scatter + all-gather over peer memory), prior + Adagrad, weight mirrors
@@ -138,7 +146,7 @@ struct TcTailArgs {
   float* per_row; float* block_part; float* base_out; float mult, div; float* scalar_out;
   // weight mirrors (w3h == nullptr: none)
   void *w3h, *w3l, *w2h, *w2l, *w45h, *w45l, *whh, *whl, *w1h, *w1l; float* w45t;
-  int D, H, Z, ldh, ldd, ldq; int64_t oW3, oW4, oW5, oW1, oW2;
+  int D, H, Z, ldh, ldd, ldq; int64_t oW3, oW4, oW5, oW1, oW2, oW6;      // oW6 < 0: Bernoulli decoder
   // grid barrier (monotonic counter; bar_base = arrivals before this launch)
   unsigned int* bar; unsigned int bar_base;
   // data parallel over peer memory (world == 1: unused)

@@ -164,6 +164,10 @@ tc_tail_kernel(const TcTailArgs a) {
       float* dst;      // the element's place in the flat gradient buffer
       if (j.kind == 0) {
         dst = i < j.n_w ? j.gW + i : j.gb + (i - j.n_w);
+      } else if (j.kind == 2) {   // interleaved Gaussian head [(H+1) x 2D]: column 2d -> W2 / b2, 2d + 1 -> W6 / b6
+        const int D = j.Z, H = j.H;
+        const int k = i / (2 * D), c = i - k * 2 * D, d = c >> 1;
+        dst = k < H ? ((c & 1) ? j.gW2 : j.gW) + (size_t)k * D + d : ((c & 1) ? j.gb2 : j.gb) + d;
       } else {         // interleaved heads slice [(H+1) x 2Z]: column c < Z -> W4 / b4, else W5 / b5
         const int Z = j.Z, H = j.H;
         const int k = i / (2 * Z), c = i - k * 2 * Z;
@@ -324,7 +328,16 @@ tc_tail_kernel(const TcTailArgs a) {
     }
   };
   mirror(W3, w3h, w3l, D, H, a.ldh);
-  mirror(W2, w2h, w2l, H, D, a.ldd);
+  if (a.oW6 >= 0) {                  // Gaussian decoder: [W2|W6]' interleaved
+    const float* W6 = a.params + a.oW6;
+    for (int i = t32; i < H * D; i += n32) {
+      const int r = i / D, c = i - r * D;
+      put_pair(w2h, w2l, (size_t)r * a.ldd + 2 * c, __ldcg(W2 + i));
+      put_pair(w2h, w2l, (size_t)r * a.ldd + 2 * c + 1, __ldcg(W6 + i));
+    }
+  } else {
+    mirror(W2, w2h, w2l, H, D, a.ldd);
+  }
   mirror(W1, w1h, w1l, Z, H, a.ldh);
   stamp(a, 7);
   for (int i = t32; i < H * Z; i += n32) {      // W4[k, j], W5[k, j]

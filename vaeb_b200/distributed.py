@@ -40,6 +40,24 @@ def attach_data_parallel(model):
     return rank, world
 
 
+def close_data_parallel(model):
+    """Collective counterpart of model.close(): every rank stops using its peers' buffers (barrier) before any rank
+    unmaps and frees its own (the exported allocations must outlive every importer's mapping)."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+        _lib_detach(model)
+        dist.barrier()
+    model.close()
+
+
+def _lib_detach(model):
+    from . import _lib
+    _lib.check(model._lib.vaeb_comm_detach(model._h))
+
+
 def shard_rows(n, rank, world):
     """Contiguous block of rows owned by `rank` (N/G points per GPU)."""
     per = (n + world - 1) // world
