@@ -471,7 +471,7 @@ def run_own(args):
                                           "inside the tail kernel, over peer memory (CUDA IPC / NVLink): reduce-scatter by peer "
                                           "loads, prior + Adagrad on the owner's slice, all-gather by peer stores (tc_tail.cu)"),
                            "launch_structure": "seven layer launches (VAEB_TC_CHAIN=1: one chain launch, tc_chain.cu), one weight-"
-                                               "gradient launch up to 4096 rows per GPU (four above), one tail launch (tc_tail.cu)"},
+                                               "gradient launch, slice sum + bound + Adagrad (N > 1: one tail launch that is also the collective, tc_tail.cu)"},
                 "clocks": clocks_summary, "warmup_probe_ms_per_step": probe_ms_per_step,
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": per * D * 4 * world, "d2h_bytes_per_step": 4 * world,
                         "steps": Ke, "ms_per_step": ms_e2e / Ke,

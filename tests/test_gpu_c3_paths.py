@@ -20,7 +20,7 @@ VARIANTS = [
     ("layers", {"VAEB_TC_CHAIN": "0"}),
     ("wgrad-separate", {"VAEB_TC_WGRAD_MERGE": "0"}),
     ("wgrad-merged", {"VAEB_TC_WGRAD_MERGE": "1"}),
-    ("tail-fused", {"VAEB_TC_TAIL": "1"}),
+    ("tail-separate", {"VAEB_TC_TAIL": "0"}),
 ]
 
 

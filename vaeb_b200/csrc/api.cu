@@ -342,7 +342,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   TcReduceJobs reduce_jobs;
   TcReduceJobs* defer = tcl ? &reduce_jobs : nullptr;
   const size_t wg_region = tcp ? tc_wgrad_scratch_elems(D, H) : 0;
-  // few rows per GPU (the data-parallel split): the four weight-gradient GEMMs are one launch after the last dgrad
+  // the four weight-gradient GEMMs are one launch after the last dgrad (VAEB_TC_WGRAD_MERGE=0: four launches)
   const bool merged_wgrad = tcl && tc_wgrad_merged_supported(rows);
   if (merged_wgrad && t.n_sm == 0) VAEB_CUDA(cudaDeviceGetAttribute(&t.n_sm, cudaDevAttrMultiProcessorCount, h->cfg.device));
 #define WGRAD_ALL_CALL                                                                                                  \
@@ -581,12 +581,12 @@ int enqueue_update(vaeb_handle* h, const float* d_xrows, int rows, const float* 
     const float prior = fb ? 0.f : h->cfg.prior_scale;
     // Large-batch tensor-core path: everything after the last GEMM is ONE launch (tc_tail.cu) -- and in data-parallel
     // runs whose ranks mapped each other's buffers (vaeb_comm_p2p_attach) that launch is also the gradient all-reduce.
-    // On one GPU it measures equal to the five separate launches up to 4096 rows and ~10 us slower at 16384 (their launch
-    // latencies overlap, its grid barrier does not), so it serves the data-parallel case; VAEB_TC_TAIL=1 / 0 forces it.
+    // With the single weight-gradient launch in front of it, it measures equal to the five separate launches at 16384 rows
+    // and 1-3 % faster below on one GPU; VAEB_TC_TAIL=0 switches it off (then: slice sum, row sums, bound, Adagrad, mirrors).
     static const int env_tail = getenv("VAEB_TC_TAIL") ? atoi(getenv("VAEB_TC_TAIL")) : -1;      // measurement switch
     TcTailArgs tail{};
     const bool want_tail = apply && h->optimizer != VAEB_OPT_ADADELTA && h->tc.active && L == 1 &&
-                           (dp ? (h->tc.p2p_ready && env_tail != 0) : env_tail > 0);
+                           env_tail != 0 && (!dp || h->tc.p2p_ready);
     VAEB_TRY(forward_backward(h, h->d_params, d_xrows, rows, L, true, w, src, h->d_grads, bo, want_tail ? &tail : nullptr));
     if (tail.rows > 0) {
       TcState& t = h->tc;

@@ -954,11 +954,12 @@ cudaError_t tc_wgrad3(cudaStream_t st, int64_t* launches, const TcMaps& m, int n
                           gb3, scratch, defer);
 }
 
-// ---- every weight gradient of the step in one launch (small row counts: the data-parallel split) ----------------
+// ---- every weight gradient of the step in one launch ------------------------------------------------------------
 bool tc_wgrad_merged_supported(int rows) {
   static const int env = getenv("VAEB_TC_WGRAD_MERGE") ? atoi(getenv("VAEB_TC_WGRAD_MERGE")) : -1;   // measurement switch
   if (env >= 0) return env != 0;
-  return rows <= 4096;
+  (void)rows;
+  return true;      // measured faster at every size (16384 rows bf16x3: 354.7 -> 339.6 us per update, bf16 222 -> 203)
 }
 
 cudaError_t tc_wgrad_all(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int rows, int D, int H,
