@@ -336,6 +336,18 @@ def run_own(args):
             gemm = [p for p in phases if p[2] > 0]
             dom = max(gemm, key=lambda p: p[1])
             dom_tf = dom[2] / (dom[1] * 1e-3) / 1e12
+            # DRAM bytes of that kernel: NOT measured in this run -- dram__bytes_read.sum + dram__bytes_write.sum of one
+            # `ncu --set full` capture of the same kernel at this size (profiles/r2_c3_ncu_full.txt)
+            ncu_traffic = {"wgrad W2,W1,W4|W5,W3": 255.8e6, "dec2 h.W2+loglik": 107.9e6}
+            traffic = None
+            if args.precision == "bf16x3" and per == 16384:
+                traffic = next((v for k, v in ncu_traffic.items() if dom[0].startswith(k)), None)
+            roofline.update({"traffic": traffic,
+                             "traffic_note": "from profiles/r2_c3_ncu_full.txt (one ncu --set full capture of this kernel at this size), "
+                                             "not measured in this run" if traffic else roofline["traffic_note"],
+                             "mma_level_frac": (3.0 if args.precision == "bf16x3" else 1.0) * dom_tf / peak_tf,
+                             "mma_level_note": "bf16x3 issues three bf16 MMAs per algorithmic product: tensor-pipe work = 3 x the "
+                                               "algorithmic rate (ncu: sm__pipe_tensor_cycles_active 74 % in this kernel)"})
             roofline.update({"kernel": dom[0] + " (dominant kernel of the step)", "achieved": dom_tf, "frac": dom_tf / peak_tf,
                              "ms_per_launch": dom[1], "flops_per_launch": dom[2], "share_of_step": dom[1] / tot,
                              "whole_step": {"achieved": tf_step, "frac": tf_step / peak_tf, "ms": ms / K},

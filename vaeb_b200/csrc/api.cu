@@ -563,7 +563,9 @@ int all_reduce_grads(vaeb_handle* h) {
 // One update on device-resident rows; the scalar lands in d_scalars[slot].
 int enqueue_update(vaeb_handle* h, const float* d_xrows, int rows, const float* d_eps, const float* d_zeta,
                    int slot, bool apply) {
-  if (apply) h->steptc.mirrors_valid = false; h->tc.weights_ready = false;       // the parameters change behind the step kernel's bf16 mirrors
+  if (apply) h->steptc.mirrors_valid = false;       // the parameters change behind the step kernel's bf16 mirrors
+  // (h->tc.weights_ready -- the large-batch path's weight mirrors -- is cleared below by every update that does not
+  // end in the tail kernel, which rewrites them)
   const Layout& l = h->lay;
   const int L = h->L;
   VAEB_TRY(ensure_ws(h, rows, (int64_t)rows * L, true));
@@ -636,6 +638,7 @@ int enqueue_update(vaeb_handle* h, const float* d_xrows, int rows, const float* 
       ++h->step;
       return VAEB_OK;
     }
+    if (apply) h->tc.weights_ready = false;
     VAEB_TRY(all_reduce_grads(h));
     if (apply && h->optimizer == VAEB_OPT_ADADELTA) {
       PH("adadelta+prior (flat)", 0, 28.0 * (double)l.total,
@@ -655,6 +658,7 @@ int enqueue_update(vaeb_handle* h, const float* d_xrows, int rows, const float* 
     }
   } else {
     VAEB_REQUIRE(h->world == 1, "full-VB estimators are single-GPU (replicas only)");
+    if (apply) h->tc.weights_ready = false;
     const bool sampled = h->cfg.estimator == VAEB_EST_FVB_SAMPLED;
     const float* theta = h->d_params;  // VAEB.py:119,352: frozen MAP parameters, weights never sampled
     if (sampled) {
