@@ -418,12 +418,17 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   if (!tcl)
     PH("transpose W4,W5", 0, 16 * dH * dZ,
        launch_transpose_heads(st, lc, T_(h, theta, l.iW4), T_(h, theta, l.iW5), H, Z, h->d_w45t));
+  // the KL / L^A row partials of enc2: when the tail kernel ends the update it sums them itself (they are parked in the
+  // dz workspace, idle on this path: s.partial is overwritten by dec2), else a small launch folds them into row_aux now
+  const bool aux_to_tail = tcl && tail && 4 * ((2 * Z + 63) / 64) <= Z;
+  int n_aux_tail = 0;
   if (tcl) {
     int n_aux = 0;
     PH("enc2 h_e.[W4|W5] + reparam + KL [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * dH + 2 * dH * dZ) + 20 * dr * dZ,
        tc_enc2_heads(st, lc, t.maps, t.ns, rows, H, Z, la, T_(h, theta, l.ib4), T_(h, theta, l.ib5), src, s.mu, s.ls,
-                     s.eps, s.z, tb.zh, tb.zl, tb.ldz, s.partial, &n_aux));
-    VAEB_LAUNCH(launch_row_partials_sum(st, lc, s.partial, n_aux, rows, s.row_aux));
+                     s.eps, s.z, tb.zh, tb.zl, tb.ldz, aux_to_tail ? s.dz : s.partial, &n_aux));
+    if (aux_to_tail) n_aux_tail = n_aux;
+    else VAEB_LAUNCH(launch_row_partials_sum(st, lc, s.partial, n_aux, rows, s.row_aux));
     PH("dec1 tanh(z.W1+b1) [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * 32 + dZ * dH) + 4 * dR * dH + 2.0 * t.ns * dR * dH,
        tc_dec1(st, lc, t.maps, t.ns, bna, R, Z, H, T_(h, theta, l.ib1), nullptr, tb.hdh, tb.hdl, tb.ldh));
   } else
@@ -483,8 +488,8 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
     PH("dz da1.W1^T + dmu,dls [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * dH + dZ * dH) + 28 * dR * dZ,
        tc_dz_dprep(st, lc, t.maps, t.ns, R, H, Z, la, w, s.z, s.eps, s.mu, s.ls, s.dmu, s.dls, tb.ddh, tb.ddl, tb.ldq));
     if (tail) {
-      tail->partial = s.partial; tail->n_tiles = tiles; tail->aux_part = nullptr; tail->n_aux = 0; tail->row_aux = s.row_aux;
-      tail->rows = rows;
+      tail->partial = s.partial; tail->n_tiles = tiles; tail->rows = rows;
+      tail->aux_part = aux_to_tail ? s.dz : nullptr; tail->n_aux = n_aux_tail; tail->row_aux = aux_to_tail ? nullptr : s.row_aux;
     } else
     PH("bound (per row + total)", 0, 4 * (dR * tiles + 2 * dr),
        launch_finalize(st, lc, s.partial, tiles, s.row_aux, rows, L, s.per_row, bo.base_out, bo.mult, bo.tprior,
