@@ -487,6 +487,8 @@ def run_own(args):
                 "clocks": clocks_summary, "warmup_probe_ms_per_step": probe_ms_per_step,
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": per * D * 4 * world, "d2h_bytes_per_step": 4 * world,
                         "steps": Ke, "ms_per_step": ms_e2e / Ke,
+                        "h2d_gbs_per_gpu": per * D * 4 / (ms_e2e / Ke * 1e-3) / 1e9,
+                        "bound": "host-to-device copy of the minibatch (PCIe): the step itself takes ms_per_step of the headline",
                         "api": "VAEB.update_host_async + collect (pinned host minibatch per step, H2D on a copy stream "
                                "overlapping the previous step, 4-byte D2H of every bound)",
                         "sync_call": {"value": e2e_sync, "ms_per_step": ms_sync / Ks, "steps": Ks}},

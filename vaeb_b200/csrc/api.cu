@@ -266,6 +266,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
   TcState& t = h->tc;
   int x_row_off = 0, bn = 64, bna = 64;   // UMMA N of the weight-gradient / of the activation layers
   int bnd = 64;                           // ... of dec2 (D wide: more column tiles per row block than the H-wide layers)
+  int bnt = 0;                            // ... of the thin layers dec1 / dgrad h_e when they differ (persistent, narrow tiles)
   bool chain = false, chain_pair = false;
   const void *x_mirror_hi = nullptr, *x_mirror_lo = nullptr;
   if (tcp) {
@@ -286,6 +287,8 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
     // few row blocks (the data-parallel split): one tile per CTA, and a layer should fill most of the SMs in ONE wave --
     // 64-wide tiles for the H-wide layers when 128-wide ones give fewer than 96 CTAs (2048 rows: 64 -> 128 CTAs, enc1
     // 14.5 -> 12.2 us, dgrad 15.6 -> 13.1), dec2 keeps 128 (7 column tiles per row block: 112 CTAs)
+    static const int env_thin = getenv("VAEB_TC_THIN_BN") ? atoi(getenv("VAEB_TC_THIN_BN")) : 0;    // measurement switch
+    if (bna == 256 && !chain && (env_thin == 64 || env_thin == 128)) bnt = env_thin;
     if (bna == 128 && env_bn == 0 && !chain) {
       const int rb = (rows + 127) / 128;
       if (rb * ((H + 127) / 128) < 96) bna = 64;
@@ -317,9 +320,9 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
       rows_data = rows;
     }
     x_mirror_hi = b.xh; x_mirror_lo = t.ns == 2 ? b.xl : nullptr;
-    if (t.key_rows != rows || t.key_R != R || t.key_data != rows_data || t.key_bn != (bna * 1024 + bn) * 1024 + bnd || t.key_x != b.xh) {
-      VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bna, Z, bn, bnd, h->cont ? 2 * D : D));
-      t.key_rows = rows; t.key_R = R; t.key_data = rows_data; t.key_bn = (bna * 1024 + bn) * 1024 + bnd; t.key_x = b.xh;
+    if (t.key_rows != rows || t.key_R != R || t.key_data != rows_data || t.key_bn != (bna * 1024 + bn) * 1024 + bnd + bnt / 64 || t.key_x != b.xh) {
+      VAEB_TRY(tc_build_maps(&t.maps, b, (int)rows_data, R, rows, D, H, bna, Z, bn, bnd, h->cont ? 2 * D : D, bnt));
+      t.key_rows = rows; t.key_R = R; t.key_data = rows_data; t.key_bn = (bna * 1024 + bn) * 1024 + bnd + bnt / 64; t.key_x = b.xh;
     }
     if (want_grads && b.heh && b.zh && b.d1h && b.ddh && latent_large_batch(rows, H, Z, L) && t.weights_ready &&
         theta == h->d_params) {
@@ -430,7 +433,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
     if (aux_to_tail) n_aux_tail = n_aux;
     else VAEB_LAUNCH(launch_row_partials_sum(st, lc, s.partial, n_aux, rows, s.row_aux));
     PH("dec1 tanh(z.W1+b1) [tcgen05]", 2 * dR * dZ * dH, 2.0 * t.ns * (dR * 32 + dZ * dH) + 4 * dR * dH + 2.0 * t.ns * dR * dH,
-       tc_dec1(st, lc, t.maps, t.ns, bna, R, Z, H, T_(h, theta, l.ib1), nullptr, tb.hdh, tb.hdl, tb.ldh));
+       tc_dec1(st, lc, t.maps, t.ns, bnt ? 1000 + bnt : bna, R, Z, H, T_(h, theta, l.ib1), nullptr, tb.hdh, tb.hdl, tb.ldh));
   } else
   PH("latent fwd (enc2,reparam,KL,dec1)", 4 * dr * dH * dZ + 2 * dR * dZ * dH,
      4 * (dr * dH + 3 * dH * dZ + 2 * dr * dZ + 2 * dR * dZ + dR * dH),
@@ -504,7 +507,7 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
                        bo.scalar_out, tcl ? tb.ddh : nullptr, tcl ? tb.ddl : nullptr, tb.ldq, h->hidden_act));
   if (tcl) {
     PH("dgrad h_e ([dmu|dls].W45^T)*(1-h^2) [tcgen05]", 4 * dr * dH * dZ, 2.0 * t.ns * (dr * 64 + 2 * dZ * dH) + 8 * dr * dH,
-       tc_dgrad_he(st, lc, t.maps, t.ns, bna, rows, Z, H, nullptr, nullptr, tb.da3h, tb.da3l, tb.ldh, tb.heh, tb.hel));
+       tc_dgrad_he(st, lc, t.maps, t.ns, bnt ? 1000 + bnt : bna, rows, Z, H, nullptr, nullptr, tb.da3h, tb.da3l, tb.ldh, tb.heh, tb.hel));
     if (merged_wgrad) {
       PH("wgrad W2,W1,W4|W5,W3 (+ biases) [tcgen05, one launch]", 4 * dR * dH * dD + 2 * dR * dZ * dH + 4 * dr * dH * dZ,
          2.0 * t.ns * (2 * dR * dH + 2 * dR * dD) + 8 * dH * dD, WGRAD_ALL_CALL);

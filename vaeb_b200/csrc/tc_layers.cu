@@ -462,6 +462,16 @@ template <bool A_MN, bool B_MN, class Epi>
 cudaError_t dispatch_layer(cudaStream_t st, int ns, int bn, const LayerMaps& maps, const Epi& epi, int M, int N, int K,
                            int a_row_off, int splits = 1) {
   if constexpr (!A_MN) {
+    // the persistent form with narrower tiles (thin layers of large batches: pure epilogue, so small tiles only even out
+    // the last wave -- 256 tiles of 256 columns on 148 SMs are two rounds, 1024 tiles of 64 columns are 1.75)
+    if (bn == 1064) {
+      if (ns == 2) return launch_layer_persistent<64, B_MN, 2, Epi, 1>(st, maps, epi, M, N, K, a_row_off);
+      return launch_layer_persistent<64, B_MN, 1, Epi, 1>(st, maps, epi, M, N, K, a_row_off);
+    }
+    if (bn == 1128) {
+      if (ns == 2) return launch_layer_persistent<128, B_MN, 2, Epi, 1>(st, maps, epi, M, N, K, a_row_off);
+      return launch_layer_persistent<128, B_MN, 1, Epi, 1>(st, maps, epi, M, N, K, a_row_off);
+    }
     if (bn == 256) {                   // tc_act_bn chose the persistent form
       if (ns == 2) return launch_layer_persistent<256, B_MN, 2, Epi, 1>(st, maps, epi, M, N, K, a_row_off);
       // 256 x 256 tiles (VAEB_TC_MT=2): measured SLOWER at 16384 rows (275 vs 263 us per update; enc1 25.2 vs 23.2,
@@ -748,8 +758,9 @@ static int make_pair_mn(CUtensorMap* hi, CUtensorMap* lo, const void* bh, const 
 
 // bn: UMMA N of the activation layers (tc_act_bn); bn_w: of the weight-gradient GEMMs
 int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z, int bn_w,
-                  int bn_d, int Dd) {
+                  int bn_d, int Dd, int bn_thin) {
   const uint32_t gd = (uint32_t)(bn_d > 0 ? bn_d : bn) / 64;
+  const uint32_t gt = (uint32_t)(bn_thin > 0 ? bn_thin : bn) / 64;      // dec1, dgrad h_e (K <= 64: pure epilogue)
   if (Dd <= 0) Dd = D;      // width of the decoder output layer: D, or 2 D for the interleaved Gaussian head
   const uint32_t ga = BM / 64, gb = (uint32_t)bn / 64, gw = (uint32_t)bn_w / 64;
   const uint32_t kw = b.w3l ? BK : 2 * BK;      // contraction rows per box of the weight-gradient operands (stage_k)
@@ -793,7 +804,7 @@ int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows,
     // dec1: A = z mirror [R, Z] K-major (the ones column at Z stays out of the map), B = W1 mirror [Z, H] MN-major
     LayerMaps* d1 = reinterpret_cast<LayerMaps*>(m->dec1);
     VAEB_TRY(make_pair(&d1->a_hi, &d1->a_lo, b.zh, b.zl, R, Z, b.ldz, BM));
-    VAEB_TRY(make_pair_mn(&d1->b_hi, &d1->b_lo, b.w1h, b.w1l, Z, H, b.ldh, gb));
+    VAEB_TRY(make_pair_mn(&d1->b_hi, &d1->b_lo, b.w1h, b.w1l, Z, H, b.ldh, gt));
     // dz: A = da1 mirror [R, H] K-major, B = W1 mirror [Z, H] K-major (N = Z rows)
     LayerMaps* dzm = reinterpret_cast<LayerMaps*>(m->dz);
     VAEB_TRY(make_pair(&dzm->a_hi, &dzm->a_lo, b.d1h, b.d1l, R, H, b.ldh, BM));
@@ -801,7 +812,7 @@ int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows,
     // dgrad h_e: A = [dmu|dls] mirror [rows, 2Z] K-major, B = [W4^T;W5^T] mirror [2Z, H] MN-major
     LayerMaps* dh = reinterpret_cast<LayerMaps*>(m->dhe);
     VAEB_TRY(make_pair(&dh->a_hi, &dh->a_lo, b.ddh, b.ddl, rows, 2 * Z, b.ldq, BM));
-    VAEB_TRY(make_pair_mn(&dh->b_hi, &dh->b_lo, b.w45h, b.w45l, 2 * Z, H, b.ldh, gb));
+    VAEB_TRY(make_pair_mn(&dh->b_hi, &dh->b_lo, b.w45h, b.w45l, 2 * Z, H, b.ldh, gt));
   }
   return VAEB_OK;
 }

@@ -49,7 +49,7 @@ int tc_act_bn(int rows, int n_min);
 // bn: UMMA N of the H-wide activation layers (enc1, dec1, both dgrads); bn_d (0: = bn): of dec2 (D wide)
 // Dd (0: = D): width of the decoder output layer -- 2 D for the Gaussian head's interleaved columns [W2|W6]'
 int tc_build_maps(TcMaps* m, const TcBuffers& b, int rows_data, int R, int rows, int D, int H, int bn, int Z, int bn_w,
-                  int bn_d = 0, int Dd = 0);
+                  int bn_d = 0, int Dd = 0, int bn_thin = 0);   // bn_thin (0: = bn): tile width of dec1 / dgrad h_e
 // Gaussian decoder (VAEB.py:257-258, 306-307): a|lv = h_d.[W2|W6]' + b, log-density and both deltas in the epilogue
 cudaError_t tc_dec2_gaussian(cudaStream_t st, int64_t* launches, const TcMaps& m, int ns, int bn, int R, int H, int D,
                              const float* b2, const float* b6, const float* x, int x_div, int x_mod, float scale, void* da_hi,
