@@ -31,7 +31,7 @@ def attach_data_parallel(model):
     model.attach_comm(uid, rank, world)
     # ranks of one box map each other's buffers (CUDA IPC over NVLink): the tail kernel of a large-batch tensor-core
     # update then IS the gradient all-reduce (vaeb_comm_p2p_attach); VAEB_DP_P2P=0 keeps ncclAllReduce
-    if world > 1 and os.environ.get("VAEB_DP_P2P", "1") != "0" and getattr(model, "precision", "fp32") != "fp32":
+    if 1 < world <= 8 and os.environ.get("VAEB_DP_P2P", "1") != "0" and getattr(model, "precision", "fp32") != "fp32":
         mine = model.p2p_export()
         handles = [None] * world
         dist.all_gather_object(handles, mine)
