@@ -48,16 +48,20 @@ def test_tc_gemm_small_n_tile():
 
 
 # ---- importance-sampled log p(x) on the tensor cores (is_tc.cu), bf16 tier ---------------------------
-def _is_case(D, H, Z, n, L, seed, scale):
+def _is_case(D, H, Z, n, L, seed, scale, continuous=False):
     import vaeb_b200
     from oracle import vaeb_oracle as O
     rng = np.random.RandomState(seed)
-    x = (rng.uniform(size=(n, D)) * (rng.uniform(size=(n, D)) < 0.3)).astype(np.float32)
-    params = [rng.normal(0, scale, s).astype(np.float32) for s in O.param_shapes(D, H, Z, False)]
+    if continuous:
+        x = np.clip(rng.normal(0.5, 0.2, (n, D)), 0.01, 0.99).astype(np.float32)
+    else:
+        x = (rng.uniform(size=(n, D)) * (rng.uniform(size=(n, D)) < 0.3)).astype(np.float32)
+    params = [rng.normal(0, scale, s).astype(np.float32) for s in O.param_shapes(D, H, Z, continuous)]
     eps = rng.normal(size=(n, L, Z)).astype(np.float32)
-    m = vaeb_b200.VAEB(x, False, H, Z, max(1, min(n, 4)), 1, 0.01, False, False, params, precision="bf16")
+    m = vaeb_b200.VAEB(x, continuous, H, Z, max(1, min(n, 4)), 1, 0.01, False, False, params, precision="bf16")
     lp, lw = m.log_px(x, L=L, eps=eps, return_weights=True)
-    ref_lp, ref_lw = O.is_log_px([p.astype(np.float64) for p in params], x.astype(np.float64), eps.astype(np.float64), False)
+    ref_lp, ref_lw = O.is_log_px([p.astype(np.float64) for p in params], x.astype(np.float64), eps.astype(np.float64),
+                                 continuous)
     m.close()
     return lp, lw, ref_lp, ref_lw
 
@@ -68,6 +72,28 @@ def test_is_logpx_tensor_core_matches_oracle(D, H, Z, n, L):
     # bf16 operands, fp32 accumulation: the 1e-2 tier (north star), per sample and per point
     np.testing.assert_allclose(lw, ref_lw, rtol=1e-2, atol=1e-2)
     np.testing.assert_allclose(lp, ref_lp, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("D,H,Z,n,L", [(560, 200, 2, 5, 300), (784, 500, 20, 3, 130), (38, 29, 3, 4, 7)])
+def test_is_logpx_tensor_core_gaussian_decoder(D, H, Z, n, L):
+    """The importance-sampling kernel with the Gaussian decoder: the output sweep runs over the
+    interleaved head [W2|W6]' (2 D columns), the epilogue folds pixel pairs (a_d, lv_d) into the log-density of
+    VAEB.py:304-307.  C1's shape, the MNIST shape, a ragged one; bf16 tier."""
+    lp, lw, ref_lp, ref_lw = _is_case(D, H, Z, n, L, 12, 0.08, continuous=True)
+    np.testing.assert_allclose(lw, ref_lw, rtol=1e-2, atol=1e-2)
+    np.testing.assert_allclose(lp, ref_lp, rtol=1e-2, atol=1e-2)
+    # the Philox path (no injected noise, pipelined host input) agrees with itself across calls and stays finite
+    import vaeb_b200
+    from oracle import vaeb_oracle as O
+    rng = np.random.RandomState(5)
+    x = np.clip(rng.normal(0.5, 0.2, (700, D)), 0.01, 0.99).astype(np.float32)
+    params = [rng.normal(0, 0.08, s).astype(np.float32) for s in O.param_shapes(D, H, Z, True)]
+    m = vaeb_b200.VAEB(x[:4], True, H, Z, 4, 1, 0.01, False, False, params, precision="bf16")
+    a = m.log_px(x, L=64)
+    b = m.log_px(x[:300], L=64)
+    assert np.isfinite(a).all()
+    np.testing.assert_array_equal(a[:300], b)
+    m.close()
 
 
 def test_is_logpx_tensor_core_philox_sharding_invariance():

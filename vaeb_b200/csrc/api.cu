@@ -870,6 +870,7 @@ int vaeb_destroy(vaeb_handle* h) {
   }
   {
     IsTcState& q = h->istc;
+    if (q.bias26) cudaFree(q.bias26);
     if (q.copy) {
       cudaStreamSynchronize(q.copy);
       for (int i = 0; i < 2; ++i) { cudaEventDestroy(q.copied[i]); cudaEventDestroy(q.consumed[i]); if (q.xbuf[i]) cudaFree(q.xbuf[i]); }

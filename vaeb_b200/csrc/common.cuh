@@ -108,6 +108,7 @@ struct FusedState {
 struct IsTcState {
   void* w2t = nullptr;                               // W2^T [D, KP] bf16
   void* w1t = nullptr;                               // [W1^T | b1] [512, 64] bf16
+  float* bias26 = nullptr;                           // Gaussian decoder: b2 / b6 interleaved like the output columns
   alignas(64) unsigned char map_w1[128];             // CUtensorMap over w1t, boxes of 64 rows (one pass)
   alignas(64) unsigned char map_full[128];           // CUtensorMap over w2t, boxes of `tail_cols` rows (one output chunk)
   int n_sm = 0, n_chunks = 0, tail_cols = 0;         // tail_cols = chunk width NC (multiple of 16)

@@ -29,7 +29,7 @@ constexpr int BM = 128, BK = 64, NC_MAX = 160, STAGES = 3;
 constexpr int KB_MAX = 8;                       // hidden units padded to <= 512
 constexpr int ZMAX = 20;                        // latent size; the bias rides along as contraction index Z
 constexpr int ZG = 6;                           // groups of four contraction indices written per z row (24 >= Z + 1)
-constexpr int DMAX = 1024;
+constexpr int DMAX = 1600;                      // output columns (Gaussian head: 2 x pixels, interleaved)
 constexpr int PROD_WARPS = 8, EPI_WARPS = 16;     // epilogue: 4 TMEM lane quarters x (EPI_WARPS / 4) column slices
 constexpr int THREADS = (4 + PROD_WARPS + EPI_WARPS) * 32;
 constexpr int A_BLOCK = BM * 128;               // bytes of one 64-wide k block of the A tile
@@ -59,7 +59,8 @@ struct Params {
   int tiles_per_point, n_chunks, NC, zk;        // output chunks of NC columns (multiple of 16); zk = K=16 steps of [z|1]
   const float* x;                               // [n_points, D]
   const float* mu; const float* ls;             // [n_points, Z]
-  const float* b2;
+  const float* b2;                              // [D] output biases (Gaussian: b2 / b6 interleaved)
+  int cont, Dx;                                 // Gaussian decoder; pixels per point (D = 2 Dx columns then)
   const float* eps_inj;                         // [n_points, L, Z] or nullptr
   uint64_t seed; int64_t row_offset;
   float2* partial;                              // [n_points * tiles_per_point] (max, sum exp)
@@ -127,6 +128,27 @@ __device__ __forceinline__ void fold8(const float (&v)[8], uint32_t bx, uint32_t
     acc = fma2(a2, x[j], acc);
     acc = fma2(pk2(m0, m1), k.khalf, acc);
     acc = fma2(t2, q, acc);
+  }
+}
+// Gaussian decoder (VAEB.py:257-258, 304-307): the output columns are the interleaved head [W2|W6]' -- column 2d is the
+// logit a_d of the mean, 2d + 1 the log-variance lv_d -- so 8 accumulator columns are 4 pixels:
+//   -log(2 pi)/2 - lv/2 - (x - sigmoid(a))^2 e^{-lv} / 2.      bx: {b2, b6} interleaved; xh: x_d at both columns of a pair
+// Padded pairs carry biases (-30, -log(2 pi)) and x = 0: mu = 0, e^{-lv} finite, the term vanishes.
+__device__ __forceinline__ void fold8g(const float (&v)[8], uint32_t bx, uint32_t xh, float& acc) {
+  float b[8], x[8];
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3]) : "r"(bx));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[4]), "=f"(b[5]), "=f"(b[6]), "=f"(b[7]) : "r"(bx + 16u));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]) : "r"(xh));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[4]), "=f"(x[5]), "=f"(x[6]), "=f"(x[7]) : "r"(xh + 16u));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float a = v[2 * j] + b[2 * j], lv = v[2 * j + 1] + b[2 * j + 1];
+    float t, r, w;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-1.4426950408889634f * a));        // e^-a
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));                        // sigmoid(a)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(-1.4426950408889634f * lv));       // e^-lv
+    const float d = x[2 * j] - r;
+    acc += fmaf(-0.5f * d * d, w, fmaf(-0.5f, lv, -0.91893853320467274178f));
   }
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -373,7 +395,10 @@ is_tc_kernel(const __grid_constant__ CUtensorMap map_w2, const __grid_constant__
   if (warp == 2) tc::tmem_alloc(tmem_slot, TMEM_COLS);
   // columns past D: a = -30 (the W2^T rows are zero-filled), x - 1/2 = -1/2: a (x - 1/2) - |a|/2 = 15 - 15 and
   // ln(1 + e^-30) ~ 1e-13, so padding contributes nothing (no per-element bounds test)
-  for (int i = threadIdx.x; i < DMAX; i += THREADS) { bb_s[i] = i < p.D ? p.b2[i] : -30.f; xh_s[i] = -0.5f; }
+  for (int i = threadIdx.x; i < DMAX; i += THREADS) {
+    bb_s[i] = i < p.D ? p.b2[i] : ((p.cont && (i & 1)) ? -1.8378770664093453f : -30.f);
+    xh_s[i] = p.cont ? 0.f : -0.5f;
+  }
   for (int i = threadIdx.x; i < BM * 128 / 16; i += THREADS)          // [z|1] tile: k >= 24 stays zero
     reinterpret_cast<uint4*>(smem + Smem::ZB)[i] = make_uint4(0u, 0u, 0u, 0u);
   tc::fence_proxy_async();
@@ -512,9 +537,14 @@ is_tc_kernel(const __grid_constant__ CUtensorMap map_w2, const __grid_constant__
     uint32_t acc_it = 0, tile_it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
       const int pi = t / p.tiles_per_point, l0 = (t - pi * p.tiles_per_point) * BM;
-      for (int i = et; i < p.D; i += EPI_WARPS * 32) xh_s[i] = p.x[(size_t)pi * p.D + i] - 0.5f;
+      if (p.cont) {
+        for (int i = et; i < p.D; i += EPI_WARPS * 32) xh_s[i] = p.x[(size_t)pi * p.Dx + (i >> 1)];
+      } else {
+        for (int i = et; i < p.D; i += EPI_WARPS * 32) xh_s[i] = p.x[(size_t)pi * p.D + i] - 0.5f;
+      }
       named_bar(2, EPI_WARPS * 32);
       uint64_t acc = 0ull;                                             // two fp32 partial sums (even / odd columns)
+      float accg = 0.f;                                                // Gaussian decoder: one sum
       for (int c = 0; c < p.n_chunks; ++c, ++acc_it) {
         const uint32_t buf = acc_it & 1;
         tc::mbar_wait(&acc_full[buf], (acc_it >> 1) & 1);
@@ -526,6 +556,18 @@ is_tc_kernel(const __grid_constant__ CUtensorMap map_w2, const __grid_constant__
         // current 8 columns are folded
         float va[8], vb[8];
         tmem_ld8(taddr, va);
+        if (p.cont) {
+          for (int i = 0; i < n8; i += 2) {
+            tc::tmem_ld_wait();
+            if (i + 1 < n8) tmem_ld8(taddr + 8u * (i + 1), vb);
+            fold8g(va, ba + 32u * i, xa + 32u * i, accg);
+            if (i + 1 < n8) {
+              tc::tmem_ld_wait();
+              if (i + 2 < n8) tmem_ld8(taddr + 8u * (i + 2), va);
+              fold8g(vb, ba + 32u * (i + 1), xa + 32u * (i + 1), accg);
+            }
+          }
+        } else
         for (int i = 0; i < n8; i += 2) {
           tc::tmem_ld_wait();
           if (i + 1 < n8) tmem_ld8(taddr + 8u * (i + 1), vb);
@@ -542,7 +584,7 @@ is_tc_kernel(const __grid_constant__ CUtensorMap map_w2, const __grid_constant__
       }
       float rs0, rs1;
       upk2(acc, rs0, rs1);
-      const float rs = rs0 + rs1;
+      const float rs = rs0 + rs1 + accg;
       rowsum_s[ch * BM + row] = rs;
       named_bar(2, EPI_WARPS * 32);
       if (ch == 0) {
@@ -592,12 +634,18 @@ __global__ void is_tc_finish_kernel(const float2* __restrict__ partial, int n_po
 }
 
 // W2 [H, D] fp32 -> W2^T [D, KP] bf16 (k contiguous, zero padded to KP = 64*KB)
+// W6 != nullptr (Gaussian decoder): D output columns = the interleaved head, column 2d from W2[:, d], 2d + 1 from W6[:, d]
+// (both [H, D / 2]); bias26 receives the interleaved biases
 __global__ void is_tc_prep_kernel(const float* __restrict__ W2, int H, int D, int KP, int ld,
-                                  __nv_bfloat16* __restrict__ w2t) {
+                                  __nv_bfloat16* __restrict__ w2t, const float* __restrict__ W6, const float* __restrict__ b2,
+                                  const float* __restrict__ b6, float* __restrict__ bias26) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)D * KP) return;
   const int n = (int)(i / KP), k = (int)(i % KP);
-  w2t[(size_t)n * ld + k] = __float2bfloat16_rn(k < H ? W2[(size_t)k * D + n] : 0.f);
+  float v = 0.f;
+  if (k < H) v = W6 ? ((n & 1) ? W6 : W2)[(size_t)k * (D / 2) + (n >> 1)] : W2[(size_t)k * D + n];
+  w2t[(size_t)n * ld + k] = __float2bfloat16_rn(v);
+  if (W6 && k == 0) bias26[n] = (n & 1) ? b6[n >> 1] : b2[n >> 1];
 }
 
 // [W1^T | b1] as the B operand of the hidden-layer GEMM: w1t[n][k] bf16, n < KP hidden units, 64 contraction
@@ -615,8 +663,8 @@ __global__ void is_tc_prep_w1_kernel(const float* __restrict__ W1, const float* 
 }  // namespace istc
 
 bool is_tc_supported(const vaeb_handle* h) {
-  return h->cfg.precision == VAEB_PREC_BF16 && !h->cont && h->H <= 64 * istc::KB_MAX && h->Z <= istc::ZMAX &&
-         h->D <= istc::DMAX && h->D >= 16;
+  return h->cfg.precision == VAEB_PREC_BF16 && h->H <= 64 * istc::KB_MAX && h->Z <= istc::ZMAX &&
+         (h->cont ? 2 * h->D : h->D) <= istc::DMAX && h->D >= 16;      // Gaussian decoder: 2 D interleaved output columns
 }
 
 // mu, ls: device [n, Z] (fp32 encoder already run); d_x device [n, D]; logp_out device [n]; logw_out device or nullptr
@@ -624,13 +672,15 @@ int is_tc_run(vaeb_handle* h, const float* d_x, const float* d_mu, const float* 
               int64_t row_offset, float* d_logp, float* d_logw) {
   using namespace istc;
   const Layout& l = h->lay;
-  const int D = h->D, H = h->H, Z = h->Z;
+  const int Dx = h->D, H = h->H, Z = h->Z;
+  const int D = h->cont ? 2 * Dx : Dx;              // output columns of the decoder GEMM
   const int KB = (H + 63) / 64, KP = KB * 64;
   IsTcState& s = h->istc;
   cudaStream_t st = h->stream;
   if (!s.w2t) {
     VAEB_CUDA(cudaMalloc(&s.w2t, (size_t)D * (KP + W2T_PAD) * 2));
     VAEB_CUDA(cudaMalloc(&s.w1t, (size_t)(KB_MAX * 64) * 64 * 2));
+    if (h->cont) VAEB_CUDA(cudaMalloc((void**)&s.bias26, (size_t)D * sizeof(float)));
     VAEB_CUDA(cudaMemset(s.w1t, 0, (size_t)(KB_MAX * 64) * 64 * 2));
     VAEB_TRY(vaeb_make_tmap_bf16((CUtensorMap*)s.map_w1, s.w1t, (uint64_t)(KB_MAX * 64), 64, 64, MINI_N));
     VAEB_CUDA(cudaFuncSetAttribute(is_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::TOTAL));
@@ -645,8 +695,10 @@ int is_tc_run(vaeb_handle* h, const float* d_x, const float* d_mu, const float* 
   // the weights may have changed since the last call: refresh the bf16 transpose (0.8 MB)
   {
     const int64_t tot = (int64_t)D * KP;
-    is_tc_prep_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->d_params + l.off[l.iW2], H, D, KP,
-                                                                    KP + W2T_PAD, (__nv_bfloat16*)s.w2t);
+    is_tc_prep_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+        h->d_params + l.off[l.iW2], H, D, KP, KP + W2T_PAD, (__nv_bfloat16*)s.w2t,
+        h->cont ? h->d_params + l.off[l.iW6] : nullptr, h->d_params + l.off[l.ib2],
+        h->cont ? h->d_params + l.off[l.ib6] : nullptr, s.bias26);
     ++h->launches;
     VAEB_CUDA(cudaGetLastError());
     is_tc_prep_w1_kernel<<<(KP * 64 + 255) / 256, 256, 0, st>>>(h->d_params + l.off[l.iW1], h->d_params + l.off[l.ib1], H,
@@ -668,7 +720,8 @@ int is_tc_run(vaeb_handle* h, const float* d_x, const float* d_mu, const float* 
   p.n_points = n; p.L = L; p.D = D; p.H = H; p.Z = Z; p.KB = KB;
   p.tiles_per_point = tpp; p.n_chunks = s.n_chunks; p.NC = s.tail_cols; p.zk = (Z + 1 + 15) / 16;
   p.x = d_x; p.mu = d_mu; p.ls = d_ls;
-  p.b2 = h->d_params + l.off[l.ib2];
+  p.b2 = h->cont ? s.bias26 : h->d_params + l.off[l.ib2];
+  p.cont = h->cont ? 1 : 0; p.Dx = Dx;
   p.eps_inj = d_eps; p.seed = h->cfg.seed; p.row_offset = row_offset;
   p.partial = (float2*)s.partial; p.logw_out = d_logw;
   int grid = (int)std::min<int64_t>(n_tiles, s.n_sm);
