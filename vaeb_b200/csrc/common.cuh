@@ -111,6 +111,8 @@ struct IsTcState {
   float* bias26 = nullptr;                           // Gaussian decoder: b2 / b6 interleaved like the output columns
   alignas(64) unsigned char map_w1[128];             // CUtensorMap over w1t, boxes of 64 rows (one pass)
   alignas(64) unsigned char map_full[128];           // CUtensorMap over w2t, boxes of `tail_cols` rows (one output chunk)
+  alignas(64) unsigned char map_half[128];           // ... boxes of tail_cols / 2 rows, map_w1_half: 32 rows (CTA-pair form)
+  alignas(64) unsigned char map_w1_half[128];
   int n_sm = 0, n_chunks = 0, tail_cols = 0;         // tail_cols = chunk width NC (multiple of 16)
   void* partial = nullptr; int64_t partial_cap = 0;  // per-tile (max, sum exp)
   // pipelined host input of vaeb_is_logpx: the next chunk of points is copied on `copy` while this one is sampled
