@@ -71,6 +71,11 @@ typedef struct vaeb_config {
   float prior_scale;      /* 1.0: -0.5*scale*sum(p^2)                   (VAEB.py:386) */
   float sigma_vb_init;    /* 1e-3 fullVBSigmaInit                       (VAEB.py:146) */
   uint64_t seed;          /* Philox key (reference: RandomStreams(seed=10), VAEB.py:158) */
+  int32_t encoder_hidden_layers;   /* 0 or 1: one hidden layer, as VAEB.py:245-251 builds the encoder; 2..4: the deeper
+                                      encoders of Report/replication/replic.tex:46-57 (extra H x H tanh layers between the first
+                                      hidden layer and the heads; parameters W3_k, b3_k appended AFTER the reference's list;
+                                      fp32 per-layer kernels, L^A / L^B estimators, one GPU) */
+  int32_t reserved0;
 } vaeb_config;
 
 #define VAEB_OPT_ADAGRAD 0   /* getUpdates          VAEB.py:426-444 (the path the reference runs) */

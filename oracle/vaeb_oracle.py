@@ -47,23 +47,36 @@ PARAM_NAMES_DISCRETE = ["W3", "W4", "W5", "W1", "W2", "b3", "b4", "b5", "b1", "b
 PARAM_NAMES_CONTINUOUS = ["W3", "W4", "W5", "W1", "W2", "W6", "b3", "b4", "b5", "b1", "b2", "b6"]
 
 
-def param_names(continuous):
-    """Order of ``self.params`` -- VAEB.py:111-115."""
-    return list(PARAM_NAMES_CONTINUOUS if continuous else PARAM_NAMES_DISCRETE)
+def param_names(continuous, encoder_layers=1):
+    """Order of ``self.params`` -- VAEB.py:111-115.  Deeper encoders (Report/replication/replic.tex:46-57; no code in the
+    reference): the extra layers' W3_k, then b3_k, k = 2.., follow the reference's list."""
+    names = list(PARAM_NAMES_CONTINUOUS if continuous else PARAM_NAMES_DISCRETE)
+    names += ["W3_%d" % k for k in range(2, encoder_layers + 1)]
+    names += ["b3_%d" % k for k in range(2, encoder_layers + 1)]
+    return names
 
 
-def param_shapes(D, H, Z, continuous):
+def param_shapes(D, H, Z, continuous, encoder_layers=1):
     """Shapes behind VAEB.py:58-109."""
     s = {"W3": (D, H), "W4": (H, Z), "W5": (H, Z), "W1": (Z, H), "W2": (H, D),
          "b3": (H,), "b4": (Z,), "b5": (Z,), "b1": (H,), "b2": (D,)}
     if continuous:
         s["W6"] = (H, D)
         s["b6"] = (D,)
-    return [s[n] for n in param_names(continuous)]
+    for k in range(2, encoder_layers + 1):
+        s["W3_%d" % k] = (H, H)
+        s["b3_%d" % k] = (H,)
+    return [s[n] for n in param_names(continuous, encoder_layers)]
 
 
 def as_dict(params, continuous):
-    return dict(zip(param_names(continuous), params))
+    base = len(PARAM_NAMES_CONTINUOUS if continuous else PARAM_NAMES_DISCRETE)
+    layers = 1 + (len(params) - base) // 2          # the list's length says how deep the encoder is
+    return dict(zip(param_names(continuous, layers), params))
+
+
+def encoder_depth(p):
+    return 1 + sum(1 for n in p if n.startswith("W3_"))
 
 
 # --------------------------------------------------------------------------------------
@@ -218,9 +231,17 @@ def hidden_act_grad(h, act="tanh"):
     raise ValueError("unknown activation %r" % (act,))
 
 
+def encoder_hiddens(p, x, act="tanh"):
+    """Activations of every encoder hidden layer (one in VAEB.py:246; deeper encoders: replic.tex:46-57)."""
+    hs = [hidden_act(x @ p["W3"] + p["b3"], act)]
+    for k in range(2, encoder_depth(p) + 1):
+        hs.append(hidden_act(hs[-1] @ p["W3_%d" % k] + p["b3_%d" % k], act))
+    return hs
+
+
 def encoder(p, x, act="tanh"):
     """VAEB.py:245-251."""
-    h = hidden_act(x @ p["W3"] + p["b3"], act)
+    h = encoder_hiddens(p, x, act)[-1]
     mu = h @ p["W4"] + p["b4"]
     ls = h @ p["W5"] + p["b5"]
     return h, mu, ls
@@ -286,7 +307,9 @@ def elbo_and_grads(params, x, eps, continuous, estimator="LB", want_grads=True,
     dt = x.dtype
     L, M, Z = eps.shape
     w = dt.type(1.0 if row_weight is None else row_weight)
-    h_e, mu, ls = encoder(p, x, act)
+    hs = encoder_hiddens(p, x, act)
+    h_e = hs[-1]
+    mu, ls = h_e @ p["W4"] + p["b4"], h_e @ p["W5"] + p["b5"]
     sd = np.exp(0.5 * ls)
     per_row = np.zeros(M, dtype=dt)
     g = {n: np.zeros_like(q) for n, q in p.items()}
@@ -347,10 +370,15 @@ def elbo_and_grads(params, x, eps, continuous, estimator="LB", want_grads=True,
     g["b5"] = d_ls.sum(axis=0)
     d_he = d_mu @ p["W4"].T + d_ls @ p["W5"].T
     d_a3 = d_he * hidden_act_grad(h_e, act)
+    depth = len(hs)
+    for k in range(depth, 1, -1):                   # back through the extra encoder hidden layers
+        g["W3_%d" % k] = hs[k - 2].T @ d_a3
+        g["b3_%d" % k] = d_a3.sum(axis=0)
+        d_a3 = (d_a3 @ p["W3_%d" % k].T) * hidden_act_grad(hs[k - 2], act)
     g["W3"] = x.T @ d_a3
     g["b3"] = d_a3.sum(axis=0)
     ps = dt.type(prior_scale)
-    grads = [g[n] - ps * p[n] for n in param_names(continuous)]   # VAEB.py:389-390
+    grads = [g[n] - ps * p[n] for n in param_names(continuous, depth)]   # VAEB.py:389-390
     return StepOut(float(sgvb), per_row, grads)
 
 

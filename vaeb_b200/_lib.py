@@ -23,7 +23,8 @@ class Config(C.Structure):
                 ("batch_size", C.c_int32), ("L", C.c_int32), ("continuous", C.c_int32),
                 ("estimator", C.c_int32), ("variant", C.c_int32), ("precision", C.c_int32),
                 ("device", C.c_int32), ("learning_rate", C.c_float), ("adagrad_eps", C.c_float),
-                ("prior_scale", C.c_float), ("sigma_vb_init", C.c_float), ("seed", C.c_uint64)]
+                ("prior_scale", C.c_float), ("sigma_vb_init", C.c_float), ("seed", C.c_uint64),
+                ("encoder_hidden_layers", C.c_int32), ("reserved0", C.c_int32)]
 
 
 EXPORTS = {

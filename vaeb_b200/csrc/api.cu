@@ -60,7 +60,7 @@ static long long* g_tail_stamps = nullptr;   // debug (VAEB_TAIL_STAMPS)
 
 namespace {
 
-void build_layout(Layout& l, int D, int H, int Z, bool cont) {
+void build_layout(Layout& l, int D, int H, int Z, bool cont, int depth = 1) {
   int i = 0;
   auto add = [&](int& idx, int r, int c) { idx = i; l.rows[i] = r; l.cols[i] = c; ++i; };
   l.iW6 = l.ib6 = -1;
@@ -68,6 +68,10 @@ void build_layout(Layout& l, int D, int H, int Z, bool cont) {
   if (cont) add(l.iW6, H, D);
   add(l.ib3, 1, H); add(l.ib4, 1, Z); add(l.ib5, 1, Z); add(l.ib1, 1, H); add(l.ib2, 1, D);
   if (cont) add(l.ib6, 1, D);
+  // deeper encoders (replic.tex:46-57): the extra layers come AFTER the reference's list, weights first
+  l.depth = depth < 1 ? 1 : depth;
+  for (int k = 2; k <= l.depth; ++k) add(l.iW3x[k - 2], H, H);
+  for (int k = 2; k <= l.depth; ++k) add(l.ib3x[k - 2], 1, H);
   l.n = i;
   int64_t off = 0;
   for (int t = 0; t < l.n; ++t) { l.off[t] = off; off += (int64_t)l.rows[t] * l.cols[t]; }
@@ -101,7 +105,8 @@ int grow(float** p, int64_t* cap, int64_t need) {
 
 void free_ws(Workspace& w) {
   float** all[] = {&w.h_e, &w.mu, &w.ls, &w.eps, &w.z, &w.h_d, &w.da2, &w.dlv, &w.da1, &w.dz, &w.dmu, &w.dls,
-                   &w.da3, &w.partial, &w.row_aux, &w.per_row, &w.dec_aux, &w.logw, &w.wg_scratch};
+                   &w.da3, &w.partial, &w.row_aux, &w.per_row, &w.dec_aux, &w.logw, &w.wg_scratch,
+                   &w.h_x[0], &w.h_x[1], &w.h_x[2], &w.da3b};
   for (float** p : all) { if (*p) cudaFree(*p); *p = nullptr; }
   w.cap_enc = w.cap_dec = 0;
   w.with_grads = false;
@@ -123,6 +128,7 @@ int ensure_ws(vaeb_handle* h, int64_t enc, int64_t dec, bool grads) {
     return VAEB_OK;
   };
   VAEB_TRY(A(&w.h_e, enc * H)); VAEB_TRY(A(&w.mu, enc * Z)); VAEB_TRY(A(&w.ls, enc * Z));
+  for (int k = 0; k + 1 < h->lay.depth; ++k) VAEB_TRY(A(&w.h_x[k], enc * H));
   VAEB_TRY(A(&w.row_aux, enc)); VAEB_TRY(A(&w.per_row, enc));
   VAEB_TRY(A(&w.eps, dec * Z)); VAEB_TRY(A(&w.z, dec * Z)); VAEB_TRY(A(&w.h_d, dec * H));
   VAEB_TRY(A(&w.partial, dec * T)); VAEB_TRY(A(&w.dec_aux, dec)); VAEB_TRY(A(&w.logw, dec));
@@ -131,6 +137,7 @@ int ensure_ws(vaeb_handle* h, int64_t enc, int64_t dec, bool grads) {
     if (h->cont) VAEB_TRY(A(&w.dlv, dec * D));
     VAEB_TRY(A(&w.da1, dec * H)); VAEB_TRY(A(&w.dz, dec * Z));
     VAEB_TRY(A(&w.dmu, enc * Z)); VAEB_TRY(A(&w.dls, enc * Z)); VAEB_TRY(A(&w.da3, enc * H));
+    if (h->lay.depth > 1) VAEB_TRY(A(&w.da3b, enc * H));
     VAEB_TRY(A(&w.wg_scratch, (int64_t)small_wgrad_scratch_elems((int)enc, H, Z)));
   }
   w.cap_enc = enc; w.cap_dec = dec; w.with_grads = grads;
@@ -248,6 +255,24 @@ struct BoundOut {
 };
 
 // Forward (+ backward into `grads`) of the graph of VAEB.getGradient for x[rows,D] on device.
+// Hidden layers of the encoder (VAEB.py:246; deeper encoders: replic.tex:46-57) for x[rows, D] on the fp32 per-layer kernels:
+// the activations of layers 1 .. depth-1 go to ws.h_x[], the last one -- what the heads read -- to ws.h_e.
+int encoder_hidden(vaeb_handle* h, const float* theta, const float* x, int rows) {
+  const Layout& l = h->lay;
+  Workspace& s = h->ws;
+  const int D = h->D, H = h->H;
+  const float* in = x;
+  int K = D;
+  for (int k = 1; k <= l.depth; ++k) {
+    float* out = k == l.depth ? s.h_e : s.h_x[k - 1];
+    const float* W = k == 1 ? T_(h, theta, l.iW3) : T_(h, theta, l.iW3x[k - 2]);
+    const float* b = k == 1 ? T_(h, theta, l.ib3) : T_(h, theta, l.ib3x[k - 2]);
+    VAEB_LAUNCH(launch_dense_act(h->stream, &h->launches, in, rows, K, W, b, H, h->hidden_act, out));
+    in = out; K = H;
+  }
+  return VAEB_OK;
+}
+
 // `tail` != nullptr (training update whose tail is one launch, tc_tail.cu): on the large-batch tensor-core path the bound
 // and the split-K reductions are NOT launched here; what they need is recorded in *tail (tail->rows > 0 says so).
 int forward_backward(vaeb_handle* h, const float* theta, const float* x, int rows, int L, bool want_grads, float w,
@@ -415,6 +440,9 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
        tc_enc1(st, lc, t.maps, t.ns, bna, rows, D, H, x_row_off, T_(h, theta, l.ib3), tcl ? nullptr : s.h_e,
                tcl ? tb.heh : nullptr, tcl ? tb.hel : nullptr, tb.ldh));   // tcl: every consumer of h_e reads its mirror
   else
+  if (l.depth > 1)
+    VAEB_TRY(encoder_hidden(h, theta, x, rows));      // deeper encoders: replic.tex:46-57
+  else
     PH("enc1 x.W3+tanh", 2 * dr * dD * dH, 4 * (dr * dD + dD * dH + dr * dH),
        launch_dense_act(st, lc, x, rows, D, T_(h, theta, l.iW3), T_(h, theta, l.ib3), H, h->hidden_act, s.h_e));
   // latent heads + reparameterisation + row terms + decoder hidden layer, VAEB.py:248-254,41-47,343
@@ -531,9 +559,21 @@ int forward_backward(vaeb_handle* h, const float* theta, const float* x, int row
     PH("wgrad W3,b3 [tcgen05]", 2 * dr * dD * dH, 2.0 * t.ns * (dr * dD + dr * dH) + 4 * dD * dH,
        tc_wgrad3(st, lc, t.maps, t.ns, bn, rows, D, H, x_row_off, T_(h, grads, l.iW3), T_(h, grads, l.ib3),
                  tcl ? tb.wg_scratch + 3 * wg_region : tb.wg_scratch, defer));
-  else
+  else {
+    // deeper encoders: da3 is the gradient at the pre-activation of the LAST hidden layer; for k = depth .. 2 the layer's
+    // weight gradient is h_{k-1}^T . da_k and da_{k-1} = (da_k . W3_k^T) * f'(h_{k-1})
+    float* dcur = s.da3;
+    float* dnext = s.da3b;
+    for (int k = l.depth; k >= 2; --k) {
+      const float* hprev = s.h_x[k - 2];
+      VAEB_LAUNCH(launch_wgrad(st, lc, hprev, rows, H, dcur, H, T_(h, grads, l.iW3x[k - 2]), T_(h, grads, l.ib3x[k - 2])));
+      VAEB_LAUNCH(launch_dgrad_tanh(st, lc, dcur, T_(h, theta, l.iW3x[k - 2]), nullptr, nullptr, rows, H, H, hprev, dnext,
+                                    h->hidden_act));
+      float* t2 = dcur; dcur = dnext; dnext = t2;
+    }
     PH("wgrad W3,b3", 2 * dr * dD * dH, 4 * (dr * dD + dr * dH + dD * dH),
-       launch_wgrad(st, lc, x, rows, D, s.da3, H, T_(h, grads, l.iW3), T_(h, grads, l.ib3)));
+       launch_wgrad(st, lc, x, rows, D, dcur, H, T_(h, grads, l.iW3), T_(h, grads, l.ib3)));
+  }
   if (tail && tail->rows > 0) tail->jobs = reduce_jobs;
   else if (reduce_jobs.n > 0)
     PH("sum of the split-K weight-gradient slices (one launch)", 0, 0, tc_wgrad_reduce_all(st, lc, reduce_jobs));
@@ -796,6 +836,9 @@ int vaeb_create(const vaeb_config* cfg, vaeb_handle** out) {
   VAEB_REQUIRE(cfg->variant == 0 || cfg->variant == 1, "unknown variant");
   VAEB_REQUIRE(cfg->precision >= VAEB_PREC_FP32 && cfg->precision <= VAEB_PREC_BF16X3, "unknown precision");
   const bool fvb = cfg->estimator >= VAEB_EST_FVB;
+  VAEB_REQUIRE(cfg->encoder_hidden_layers >= 0 && cfg->encoder_hidden_layers <= 4, "encoder_hidden_layers must be 0..4");
+  VAEB_REQUIRE(cfg->encoder_hidden_layers <= 1 || (cfg->precision == VAEB_PREC_FP32 && !fvb),
+               "deeper encoders: fp32 per-layer kernels, L^A / L^B estimators");
   // getFVBL overwrites `mu` inside the sample loop (VAEB.py:361): undefined for L > 1
   VAEB_REQUIRE(!(fvb && cfg->L != 1), "full-VB bound is only defined for L == 1 (VAEB.py:361)");
   VAEB_REQUIRE(!(fvb && cfg->variant != VAEB_VARIANT_VAEB), "full-VB exists only in VAEB.py");
@@ -811,9 +854,13 @@ int vaeb_create(const vaeb_config* cfg, vaeb_handle** out) {
   h->cfg = *cfg;
   h->D = cfg->input_dim; h->H = cfg->hidden_units; h->Z = cfg->latent_size; h->M = cfg->batch_size; h->L = cfg->L;
   h->cont = cfg->continuous != 0;
-  build_layout(h->lay, h->D, h->H, h->Z, h->cont);
+  build_layout(h->lay, h->D, h->H, h->Z, h->cont, cfg->encoder_hidden_layers);
   { const char* e = getenv("VAEB_B200_FUSED"); h->fused_off = e && e[0] == '0'; h->fused_off_user = h->fused_off; }
   { const char* e = getenv("VAEB_B200_STEP_TC"); h->steptc_off = e && e[0] == '0'; }
+  if (h->lay.depth > 1) {      // deeper encoders run on the per-layer kernels only
+    h->fused_off = h->fused_off_user = true;
+    h->steptc_off = true;
+  }
   h->tc.active = cfg->precision != VAEB_PREC_FP32;
   h->tc.ns = cfg->precision == VAEB_PREC_BF16X3 ? 2 : 1;
   VAEB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -1045,10 +1092,10 @@ int vaeb_ae_train(vaeb_handle* h, int32_t kind, const int32_t* idx, int32_t n, f
   VAEB_LAUNCH(launch_gather_rows(st, lc, h->d_x, (const int*)h->d_stage2, rows, D, h->d_stage));
   const float* x = h->d_stage;
   // forward (ae.py:48-58)
-  VAEB_LAUNCH(launch_dense_act(st, lc, x, rows, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, h->hidden_act, s.h_e));
+  VAEB_LAUNCH(launch_dense_act(st, lc, x, rows, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, 1, s.h_e));
   VAEB_LAUNCH(launch_dense_act(st, lc, s.h_e, rows, H, T_(h, th, l.iW4), T_(h, th, l.ib4), Z,
                                kind == VAEB_AE_VANILLA ? 1 : 0, s.z));
-  VAEB_LAUNCH(launch_dense_act(st, lc, s.z, rows, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, h->hidden_act, s.h_d));
+  VAEB_LAUNCH(launch_dense_act(st, lc, s.z, rows, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, 1, s.h_d));
   int tiles = 0;
   if (h->cont)     // otype 'cont': OutToProbs mean, OutToReal log-variance, indep_normal (ae.py:64-72) = the Gaussian head
     VAEB_LAUNCH(launch_dec2_loglik(st, lc, true, s.h_d, rows, H, T_(h, th, l.iW2), T_(h, th, l.ib2), T_(h, th, l.iW6),
@@ -1102,13 +1149,13 @@ int vaeb_ae_forward(vaeb_handle* h, int32_t kind, int32_t what, const float* in,
   const float* th = h->d_params;
   const float* z = h->d_stage;
   if (what != 2) {
-    VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage, r, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, h->hidden_act, s.h_e));
+    VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage, r, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, 1, s.h_e));
     VAEB_LAUNCH(launch_dense_act(st, lc, s.h_e, r, H, T_(h, th, l.iW4), T_(h, th, l.ib4), Z,
                                  kind == VAEB_AE_VANILLA ? 1 : 0, what == 1 ? h->d_out : s.z));
     z = s.z;
   }
   if (what != 1) {
-    VAEB_LAUNCH(launch_dense_act(st, lc, z, r, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, h->hidden_act, s.h_d));
+    VAEB_LAUNCH(launch_dense_act(st, lc, z, r, Z, T_(h, th, l.iW1), T_(h, th, l.ib1), H, 1, s.h_d));
     VAEB_LAUNCH(launch_dense_act(st, lc, s.h_d, r, H, T_(h, th, l.iW2), T_(h, th, l.ib2), D, 2, h->d_out));   // OutToProbs
   }
   VAEB_CUDA(cudaMemcpyAsync(out, h->d_out, (size_t)rows * out_w * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -1418,7 +1465,7 @@ int vaeb_is_logpx(vaeb_handle* h, const float* x, int64_t n, int32_t L, const fl
       VAEB_CUDA(cudaStreamWaitEvent(st, q.copied[k & 1], 0));
       EpsSource src{nullptr, h->cfg.seed, VAEB_STREAM_IS, 0u, row_offset + i0};
       Workspace& s = h->ws;
-      VAEB_LAUNCH(launch_dense_act(st, lc, dx, c, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, h->hidden_act, s.h_e));
+      VAEB_TRY(encoder_hidden(h, th, dx, c));
       VAEB_LAUNCH(launch_enc2(st, lc, s.h_e, c, H, T_(h, th, l.iW4), T_(h, th, l.ib4), T_(h, th, l.iW5),
                               T_(h, th, l.ib5), Z, 0, 0, src, s.mu, s.ls, s.eps, s.z, s.row_aux));
       VAEB_TRY(is_tc_run(h, dx, s.mu, s.ls, c, L, nullptr, row_offset + i0, h->d_out, nullptr));
@@ -1438,7 +1485,7 @@ int vaeb_is_logpx(vaeb_handle* h, const float* x, int64_t n, int32_t L, const fl
     if (eps) { VAEB_TRY(stage_in(h, &h->d_stage2, &h->stage2_cap, eps + i0 * L * Z, (int64_t)R * Z)); d_eps = h->d_stage2; }
     EpsSource src{d_eps, h->cfg.seed, VAEB_STREAM_IS, 0u, row_offset + i0};
     Workspace& s = h->ws;
-    VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage, c, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, h->hidden_act, s.h_e));
+    VAEB_TRY(encoder_hidden(h, th, h->d_stage, c));
     VAEB_LAUNCH(launch_enc2(st, lc, s.h_e, c, H, T_(h, th, l.iW4), T_(h, th, l.ib4), T_(h, th, l.iW5),
                             T_(h, th, l.ib5), Z, 0, 0, src, s.mu, s.ls, s.eps, s.z, s.row_aux));
     if (tcp) {
@@ -1486,7 +1533,7 @@ int vaeb_reconstruct(vaeb_handle* h, const float* x, int64_t n, int32_t n_sample
   const float* th = h->d_params;
   Workspace& s = h->ws;
   EpsSource src{d_eps, h->cfg.seed, VAEB_STREAM_RECON, h->step, 0};
-  VAEB_LAUNCH(launch_dense_act(st, lc, h->d_stage, (int)n, D, T_(h, th, l.iW3), T_(h, th, l.ib3), H, h->hidden_act, s.h_e));
+  VAEB_TRY(encoder_hidden(h, th, h->d_stage, (int)n));
   VAEB_LAUNCH(launch_enc2(st, lc, s.h_e, (int)n, H, T_(h, th, l.iW4), T_(h, th, l.ib4), T_(h, th, l.iW5),
                           T_(h, th, l.ib5), Z, 0, 0, src, s.mu, s.ls, s.eps, s.z, s.row_aux));
   const float* W6 = h->cont ? T_(h, th, l.iW6) : nullptr;
@@ -1607,6 +1654,7 @@ int vaeb_comm_attach(vaeb_handle* h, const char* nccl_library, const uint8_t id[
                      int32_t world_size) {
   VAEB_REQUIRE(h && id && world_size >= 1 && rank >= 0 && rank < world_size, "bad communicator arguments");
   VAEB_REQUIRE(!is_fvb(h), "full-VB estimators are single-GPU (replicas only)");
+  VAEB_REQUIRE(h->lay.depth <= 1, "deeper encoders are single-GPU");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
   VAEB_TRY(load_nccl(h->nccl, nccl_library));
   NcclId nid;

@@ -38,12 +38,14 @@ void vaeb_set_error(const std::string& msg);
 
 // Tensor indices in the reference's list order (VAEB.py:111-115).
 struct Layout {
-  int n = 0;                 // 10 (Bernoulli) or 12 (Gaussian)
-  int rows[12], cols[12];
-  int64_t off[12];           // element offset inside the flat buffer (tightly packed)
+  int n = 0;                 // 10 (Bernoulli) or 12 (Gaussian), + 2 per extra encoder hidden layer
+  int rows[20], cols[20];
+  int64_t off[20];           // element offset inside the flat buffer (tightly packed)
   int64_t total = 0;         // P
   int64_t padded = 0;        // P rounded up to a multiple of 4 (float4 kernels)
   int iW3, iW4, iW5, iW1, iW2, iW6, ib3, ib4, ib5, ib1, ib2, ib6;
+  int depth = 1;             // encoder hidden layers; layer k = 2..depth: iW3x[k - 2] (H x H), ib3x[k - 2]
+  int iW3x[3] = {-1, -1, -1}, ib3x[3] = {-1, -1, -1};
 };
 
 // NCCL entry points resolved with dlopen (no link-time dependency; the host passes the path
@@ -65,6 +67,9 @@ struct Workspace {
   float *da2 = nullptr, *dlv = nullptr, *da1 = nullptr, *dz = nullptr, *dmu = nullptr, *dls = nullptr, *da3 = nullptr;
   float *partial = nullptr, *row_aux = nullptr, *per_row = nullptr, *dec_aux = nullptr, *logw = nullptr;
   float* wg_scratch = nullptr;        // row-chunk partials of the thin weight gradients (large batches)
+  // deeper encoders: activations of hidden layers 1 .. depth-1 (h_e holds the LAST one, which the heads read) and a second
+  // buffer for the gradient walking back through them
+  float* h_x[3] = {nullptr, nullptr, nullptr}; float* da3b = nullptr; int depth_alloc = 1;
 };
 
 // Tensor-core path state: bf16 (hi/lo) mirrors and their TMA descriptors.

@@ -105,8 +105,11 @@ def read_mdl(file_name):
             raise ValueError("%s: parameter object without an array" % file_name)
         params.append(np.ascontiguousarray(a, dtype=np.float32))
     n_expected = 12 if header["continuous"] else 10
-    if len(params) != n_expected:
-        raise ValueError("%s: expected %d parameter tensors, found %d" % (file_name, n_expected, len(params)))
+    extra = len(params) - n_expected                 # deeper encoders append (W3_k, b3_k) pairs after the reference's list
+    if extra < 0 or extra % 2 or extra > 6:
+        raise ValueError("%s: expected %d parameter tensors (+ 2 per extra encoder layer), found %d"
+                         % (file_name, n_expected, len(params)))
+    header["encoder_layers"] = 1 + extra // 2
     header["prng"] = None      # the constructor re-seeds RandomState(10) regardless (VAEB.py:148)
     return header, params
 

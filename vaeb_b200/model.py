@@ -72,12 +72,15 @@ class VAEB(object):
     #   variant        'vaeb' | 'fullbayes' (VAEBfullbayes.py objective/update scalars)
     #   optimizer      'adagrad' (getUpdates, VAEB.py:426-444) | 'adadelta' (getAdaDeltaUpdates, VAEB.py:449-469,
     #                  the alternative the reference keeps commented out at VAEB.py:404; rho = self.rho = 0.95)
+    #   encoder_layers 1 (VAEB.py:245-251) | 2..4: the deeper encoders of Report/replication/replic.tex:46-57 -- extra H x H
+    #                  hidden layers between the first one and the heads; their parameters W3_k, b3_k (k = 2..) follow the
+    #                  reference's list, weights first; fp32 per-layer kernels, L^A / L^B estimators
     #   activation     'tanh' (the reference's hidden layers, VAEB.py:246,254) | 'sigmoid' | 'relu' (the alternatives of
     #                  Report/replication/replic.tex:73-82; fp32 per-layer kernels, L^A / L^B estimators)
     def __init__(self, x_train, continuous, hidden_units, latent_size, batch_size,
                  L, learning_rate, genericEstimator, fullVariational, params=None, prng=None, sigmaInit=None,
                  *, device=0, precision="fp32", eps_mode="philox", sample_weights=False, variant="vaeb", seed=10,
-                 optimizer="adagrad", activation="tanh"):
+                 optimizer="adagrad", activation="tanh", encoder_layers=1):
         x_train = np.asarray(x_train)
         [self.N, self.input_size] = x_train.shape       # VAEB.py:135
         self.n_hidden_units = hidden_units
@@ -122,10 +125,13 @@ class VAEB(object):
             variant=_lib.VARIANT_FULLBAYES if variant == "fullbayes" else _lib.VARIANT_VAEB,
             precision={"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, "bf16x3": _lib.PREC_BF16X3}[precision], device=device,
             learning_rate=learning_rate, adagrad_eps=self.eps, prior_scale=1.0,
-            sigma_vb_init=self.fullVBSigmaInit, seed=seed)
+            sigma_vb_init=self.fullVBSigmaInit, seed=seed, encoder_hidden_layers=int(encoder_layers), reserved0=0)
+        self.encoder_layers = int(encoder_layers)
         self._h = C.c_void_p()
         _lib.check(self._lib.vaeb_create(C.byref(cfg), C.byref(self._h)))
         self._names = list(_NAMES_C if self.continuous else _NAMES_D)
+        self._names += ["W3_%d" % k for k in range(2, self.encoder_layers + 1)]
+        self._names += ["b3_%d" % k for k in range(2, self.encoder_layers + 1)]
         n = C.c_int32()
         _lib.check(self._lib.vaeb_num_tensors(self._h, C.byref(n), None))
         self._shapes = []
@@ -180,6 +186,8 @@ class VAEB(object):
         vals = {"W3": initW(D, H), "W4": initW(H, Z), "W5": initW(H, Z), "W1": initW(Z, H), "W2": initW(H, D)}
         if self.continuous:
             vals["W6"] = initW(H, D)
+        for k in range(2, getattr(self, "encoder_layers", 1) + 1):      # deeper encoders: drawn after the reference's list
+            vals["W3_%d" % k] = initW(H, H)
         return [vals[nm] if nm in vals else np.zeros(s, np.float32) for nm, s in zip(self._names, self._shapes)]
 
     def _get_buffer(self, which):
@@ -344,7 +352,8 @@ class VAEB(object):
         x_train = data[0]
         model = VAEB(x_train, header["continuous"], header["n_hidden_units"], header["n_latent"],
                      header["batch_size"], header["L"], header["learning_rate"], header["genericEstimator"], False,
-                     params, header["prng"], header["sigmaInit"], **kwargs)
+                     params, header["prng"], header["sigmaInit"],
+                     **dict({"encoder_layers": header.get("encoder_layers", 1)}, **kwargs))
         return model, data
 
     # ---- plumbing ------------------------------------------------------------------------
