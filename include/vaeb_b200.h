@@ -160,6 +160,13 @@ int vaeb_update_host(vaeb_handle* h, const float* x, int64_t rows, const float* 
  * ends.  The caller must not modify x until vaeb_collect returns.  Philox eps only. */
 int vaeb_update_host_async(vaeb_handle* h, const float* x, int64_t rows);
 
+/* The same for BYTE-VALUED data sets: the reference's two data sets are 8-bit images stored as pixel / 256
+ * (mnist.pkl.gz, freyfaces.pkl; loaded at VAEB.py:230-239, 544-555), so a host-side loader can keep them as bytes
+ * and send a quarter of the PCIe traffic.  x[rows,D] uint8 in PINNED host memory; the minibatch the update sees is
+ * (float)x * scale, one IEEE fp32 product per element computed on the device -- bit-identical to feeding
+ * vaeb_update_host_async the host array np.float32(x) * np.float32(scale) (tests/test_gpu_async.py). */
+int vaeb_update_host_async_u8(vaeb_handle* h, const uint8_t* x, int64_t rows, float scale);
+
 /* Page-locked host memory for vaeb_update_host_async (plain cudaMallocHost / cudaFreeHost, so that a host
  * without torch can feed the streaming path).  vaeb_update_host_async returns VAEB_EINVAL for pageable memory:
  * such a copy would be staged synchronously by the driver and the overlap would be lost without any sign. */

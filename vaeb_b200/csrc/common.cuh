@@ -148,6 +148,7 @@ struct vaeb_handle {
   static constexpr int ASYNC_BUFS = 4;
   cudaStream_t copy_stream = nullptr;
   float* a_stage[ASYNC_BUFS] = {nullptr, nullptr, nullptr, nullptr}; int64_t a_stage_cap = 0;
+  uint8_t* a_stage_u8[ASYNC_BUFS] = {nullptr, nullptr, nullptr, nullptr}; int64_t a_stage_u8_cap = 0;   // byte-valued inputs
   cudaEvent_t a_copied[ASYNC_BUFS] = {}, a_consumed[ASYNC_BUFS] = {};
   bool a_used[ASYNC_BUFS] = {false, false, false, false};
   static constexpr int ASYNC_GROUP = 4;                   // updates per launch of the fused kernel

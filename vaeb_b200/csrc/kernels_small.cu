@@ -582,3 +582,37 @@ cudaError_t launch_philox_fill(cudaStream_t st, int64_t* launches, uint64_t seed
   philox_fill_kernel<<<blocks_for(n, 256), 256, 0, st>>>(seed, stream, step, sample, first, n, out);
   return LAUNCHED();
 }
+
+namespace {
+// byte-valued inputs (MNIST / Frey pixels = k / 256): out = (float)in * scale, one IEEE product per element -- the same
+// bits as np.float32(in) * np.float32(scale) on the host.  16 bytes in, 64 bytes out per thread.
+__global__ void __launch_bounds__(256)
+expand_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int64_t n, float scale) {
+  const int64_t n16 = n >> 4;
+  const bool aligned = ((((uintptr_t)in) | ((uintptr_t)out)) & 15u) == 0;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if (aligned) {
+    for (int64_t i = tid; i < n16; i += nth) {
+      const uint4 v = __ldcs(reinterpret_cast<const uint4*>(in) + i);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      float4* o = reinterpret_cast<float4*>(out) + 4 * i;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        o[k] = make_float4(__fmul_rn((float)(w[k] & 0xffu), scale), __fmul_rn((float)((w[k] >> 8) & 0xffu), scale),
+                           __fmul_rn((float)((w[k] >> 16) & 0xffu), scale), __fmul_rn((float)(w[k] >> 24), scale));
+    }
+    for (int64_t i = (n16 << 4) + tid; i < n; i += nth) out[i] = __fmul_rn((float)in[i], scale);
+  } else {
+    for (int64_t i = tid; i < n; i += nth) out[i] = __fmul_rn((float)in[i], scale);
+  }
+}
+}  // namespace
+
+cudaError_t launch_expand_u8(cudaStream_t st, const uint8_t* in, float* out, int64_t n, float scale) {
+  const int64_t work = (n + 15) / 16;
+  int64_t blocks = (work + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  expand_u8_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, out, n, scale);
+  return cudaGetLastError();
+}

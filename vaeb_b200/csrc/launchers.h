@@ -126,3 +126,5 @@ cudaError_t launch_small_wgrad(cudaStream_t st, int64_t* launches, const float* 
                                const float* h_e, const float* dmu, const float* dls, int rows, int H, int Z,
                                float* gW1, float* gb1, float* gW4, float* gb4, float* gW5, float* gb5,
                                float* scratch);
+// byte-valued host inputs of vaeb_update_host_async_u8: out = (float)in * scale
+cudaError_t launch_expand_u8(cudaStream_t st, const uint8_t* in, float* out, int64_t n, float scale);

@@ -216,6 +216,35 @@ struct PersistSmem {
   static_assert(STAGES >= 2, "tile too large");
 };
 
+// Which tiles a CTA of the persistent kernel works on.  When the last column tile is a sliver (N = 784, BN = 256: 16 of 256
+// columns) it costs about a third of a full tile (its A operand still streams in; the MMAs are N = 16 and the epilogue
+// one chunk), and plain round-robin gives whole CTAs nothing but slivers (148 % 4 == 0) while the others run four full
+// tiles: 66 us for dec2 at 16384 rows.  So: full tiles round-robin first; slivers go, up to three each, to the CTAs that
+// got one full tile fewer, the rest round-robin.
+struct TileSeq {
+  int G, b, nfn, F, T, base, extra, nf, p1_ctas, p1_total, np1;
+  __device__ TileSeq(int tiles_m, int tiles_n, bool sliver, int grid, int cta) {
+    G = grid; b = cta;
+    nfn = tiles_n - (sliver ? 1 : 0);
+    F = tiles_m * nfn; T = sliver ? tiles_m : 0;
+    base = F / G; extra = F % G;
+    nf = base + (b < extra ? 1 : 0);
+    p1_ctas = G - extra;                                   // CTAs with `base` full tiles (all of them when extra == 0)
+    p1_total = T < 3 * p1_ctas ? T : 3 * p1_ctas;
+    np1 = 0;
+    if (b >= extra && b - extra < p1_total) np1 = (p1_total - (b - extra) + p1_ctas - 1) / p1_ctas;
+  }
+  __device__ bool get(int i, int& tm, int& tn) const {
+    if (i < nf) { const int f = b + i * G; tm = f / nfn; tn = f - tm * nfn; return true; }
+    i -= nf;
+    if (i < np1) { tm = (b - extra) + i * p1_ctas; tn = nfn; return true; }
+    i -= np1;
+    const int j = p1_total + b + i * G;
+    if (j < T) { tm = j; tn = nfn; return true; }
+    return false;
+  }
+};
+
 // MT = 2: a CTA tile is 256 x BN -- two 128-row blocks of A share every B stage (two MMAs per k step into two
 // accumulators that fill TMEM, so the epilogue of a tile overlaps only the operand loads of the next one).  ncu on
 // the MT = 1 kernels: tensor pipe 25 % active, L2 slices 25 %, 6.8 TB/s of L2 -> shared-memory fill (46 GB/s per SM,
@@ -237,7 +266,9 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
   const int nkb = (K + BK - 1) / BK;
   constexpr int TILE_M = MT * BM;
   const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + TILE_M - 1) / TILE_M;
-  const int n_tiles = tiles_m * tiles_n;
+  // a last column tile at most a quarter wide is a "sliver" (see TileSeq); MT = 2 keeps the plain order
+  const bool sliver = MT == 1 && tiles_n > 1 && (N - (tiles_n - 1) * BN) * 4 <= BN;
+  const TileSeq seq(tiles_m, tiles_n, sliver, (int)gridDim.x, (int)blockIdx.x);
   constexpr uint32_t ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   constexpr uint32_t NBUF = (512u / (MT * ACC_COLS)) >= 2u ? 2u : 1u;      // accumulator sets in TMEM
   constexpr uint32_t TMEM_COLS = NBUF * MT * ACC_COLS;
@@ -261,8 +292,9 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
     uint32_t it = 0;                                   // k blocks issued so far (ring position across tiles)
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * TILE_M, n0 = (tile % tiles_n) * BN;
+    int tm, tn;
+    for (int lt = 0; seq.get(lt, tm, tn); ++lt) {
+      const int m0 = tm * TILE_M, n0 = tn * BN;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % S::STAGES;
         tc::mbar_wait(&empty[s], ((it / S::STAGES) & 1) ^ 1);
@@ -287,10 +319,13 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
     }
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = tc::make_idesc_bf16(BM, BN, 0, B_MN ? 1 : 0);
     uint32_t it = 0, lt = 0;                           // ring position; tiles done by this CTA
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+    int tm, tn;
+    for (; seq.get((int)lt, tm, tn); ++lt) {
       const uint32_t buf = lt % NBUF, use = lt / NBUF;
+      // a sliver's MMAs are only as wide as its live columns (UMMA N: a multiple of 16)
+      const int n_live = N - tn * BN;
+      const uint32_t idesc = tc::make_idesc_bf16(BM, n_live >= BN ? BN : ((n_live + 15) & ~15), 0, B_MN ? 1 : 0);
       tc::mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);           // the epilogue drained this accumulator set
       tc::tc_fence_after();
       const uint32_t acc = tmem_base + buf * (MT * ACC_COLS);
@@ -324,8 +359,8 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
     const int q = warp & 3, cs = (warp - 4) >> 2;
     constexpr int SLICE = BN / (EPI_WARPS / 4);
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
-      const int tm = tile / tiles_n, tn = tile % tiles_n;
+    int tm, tn;
+    for (; seq.get((int)lt, tm, tn); ++lt) {
       const int n0 = tn * BN;
       const uint32_t buf = lt % NBUF, use = lt / NBUF;
 #pragma unroll 1
@@ -338,7 +373,16 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
         // 4 warps per scheduler, each a serial chain TMEM read -> global operand -> math -> store, cannot hide that
         // latency otherwise (ncu: 22 % of the samples on the first use of the load)
         constexpr int NCH = SLICE / 16;
-        if constexpr (Epi::PREFETCH) {
+        // chunks of this warp's column slice that hold live columns (a sliver tile: at most one warp group has any)
+        int live = (N - n0 - cs * SLICE + 15) >> 4;
+        live = live < 0 ? 0 : (live > NCH ? NCH : live);
+        if (live == 0) {                                      // nothing to read: hand the accumulators straight back
+          if (mt == 0) tc::mbar_wait(&tmem_full[buf], use & 1);
+          if (mt == MT - 1) {
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
+          }
+        } else if constexpr (Epi::PREFETCH) {
           uint32_t pw[2][8];
           bool ph[2];
           ph[0] = (n0 + cs * SLICE < N) && epi.preload(row, ok, n0 + cs * SLICE, N, pw[0]);
@@ -348,12 +392,13 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
           }
 #pragma unroll
           for (int i = 0; i < NCH; ++i) {
+            if (i >= live) break;
             const int c = cs * SLICE + 16 * i;
             if (i + 1 < NCH) ph[(i + 1) & 1] = (n0 + c + 16 < N) && epi.preload(row, ok, n0 + c + 16, N, pw[(i + 1) & 1]);
             float v[16];
             tc::tmem_ld16(acc + (uint32_t)c, v);
             tc::tmem_ld_wait();
-            if (mt == MT - 1 && i == NCH - 1) {               // last read of this warp: hand the accumulators back early
+            if (mt == MT - 1 && i == live - 1) {              // last read of this warp: hand the accumulators back early
               tc::tc_fence_before();
               __syncwarp();
               if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
@@ -366,17 +411,17 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
             tc::tc_fence_after();
           }
 #pragma unroll 1
-          for (int i = 0; i < NCH; ++i) {
+          for (int i = 0; i < live; ++i) {
             const int c = cs * SLICE + 16 * i;
             float v[16];
             tc::tmem_ld16(acc + (uint32_t)c, v);
             tc::tmem_ld_wait();
-            if (mt == MT - 1 && i == NCH - 1) {
+            if (mt == MT - 1 && i == live - 1) {
               tc::tc_fence_before();
               __syncwarp();
               if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
             }
-            if (n0 + c < N) epi.chunk(row, ok, n0 + c, N, v);
+            epi.chunk(row, ok, n0 + c, N, v);
           }
         }
         epi.end(row, ok, tn * (EPI_WARPS / 4) + cs, tiles_n * (EPI_WARPS / 4));
@@ -473,6 +518,8 @@ cudaError_t dispatch_layer(cudaStream_t st, int ns, int bn, const LayerMaps& map
       return launch_layer_persistent<128, B_MN, 1, Epi, 1>(st, maps, epi, M, N, K, a_row_off);
     }
     if (bn == 256) {                   // tc_act_bn chose the persistent form
+      // (32 accumulator columns per TMEM read, the chain kernel's default, measured slower here: the Bernoulli epilogue
+      // loses its operand prefetch, dec2 57.5 -> 62.6 us, and the tanh / dgrad epilogues gain nothing)
       if (ns == 2) return launch_layer_persistent<256, B_MN, 2, Epi, 1>(st, maps, epi, M, N, K, a_row_off);
       // 256 x 256 tiles (VAEB_TC_MT=2): measured SLOWER at 16384 rows (275 vs 263 us per update; enc1 25.2 vs 23.2,
       // dec2 44.1 vs 38.1 us) -- one wave of 128 tiles with the epilogue of both accumulators serialised behind the
