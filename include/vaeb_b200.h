@@ -275,6 +275,13 @@ int vaeb_launch_count(vaeb_handle* h, int64_t* n_launches);
  * (fused_step.cu), 0 = one launch per layer (kernels_*.cu / tc_layers.cu). */
 int vaeb_step_kernel(vaeb_handle* h, int64_t rows, int32_t* which);
 
+/* Diagnostic, host arithmetic only (no device needed): the (row tile, column tile) pairs that CTA `cta` of a `grid`-CTA
+ * launch of the persistent tensor-core layer kernel works on, in order, for a [rows x N] layer cut into 128 x bn tiles
+ * (full tiles round-robin first, then the sliver column tiles; tc_layers.cu `TileSeq`).  *n_out = number of pairs written;
+ * VAEB_EINVAL if `cap` is too small. */
+int vaeb_diag_tile_schedule(int32_t rows, int32_t N, int32_t bn, int32_t grid, int32_t cta, int32_t cap,
+                            int32_t* tm_out, int32_t* tn_out, int32_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -184,3 +184,37 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_persistent_layer_tile_schedule_covers_every_tile_once():
+    """The persistent tensor-core layer kernel's tile order (tc_layers.cu TileSeq: full tiles round-robin, sliver column
+    tiles to the CTAs with fewer full tiles).  Host arithmetic exported through vaeb_diag_tile_schedule: for every shape
+    the three warp roles of a CTA walk the same list, and over the grid every tile must appear exactly once."""
+    import ctypes as C
+    from vaeb_b200 import _lib
+    lib = _lib.load()
+    cap = 4096
+    tm, tn, n = (C.c_int32 * cap)(), (C.c_int32 * cap)(), C.c_int32()
+    shapes = [(16384, 784, 256), (8192, 784, 256), (16384, 500, 256), (16384, 1120, 256), (16384, 560, 256),
+              (128, 784, 256), (5000, 272, 256), (16384, 784, 128), (300, 130, 64), (16384, 40, 64), (77777, 784, 256),
+              (16384, 1040, 256)]
+    for rows, N, bn in shapes:
+        tiles_m, tiles_n = -(-rows // 128), -(-N // bn)
+        for grid in sorted({1, 7, 148, min(148, tiles_m * tiles_n)}):
+            seen, per_cta = {}, []
+            for cta in range(grid):
+                assert lib.vaeb_diag_tile_schedule(rows, N, bn, grid, cta, cap, tm, tn, C.byref(n)) == 0
+                per_cta.append(n.value)
+                for i in range(n.value):
+                    assert 0 <= tm[i] < tiles_m and 0 <= tn[i] < tiles_n
+                    key = (tm[i], tn[i])
+                    assert key not in seen, (rows, N, bn, grid, key)
+                    seen[key] = cta
+            assert len(seen) == tiles_m * tiles_n, (rows, N, bn, grid, len(seen))
+            sliver = tiles_n > 1 and (N - (tiles_n - 1) * bn) * 4 <= bn
+            if not sliver:                         # plain round-robin: tile t on CTA t % grid
+                assert all(seen[(t // tiles_n, t % tiles_n)] == t % grid for t in range(tiles_m * tiles_n))
+            else:                                  # no CTA holds more than one full tile above the others
+                full = [sum(1 for (a, b), c in seen.items() if c == cta and b < tiles_n - 1) for cta in range(grid)]
+                assert max(full) - min(full) <= 1
+    assert lib.vaeb_diag_tile_schedule(128, 784, 256, 4, 4, cap, tm, tn, C.byref(n)) != 0      # cta out of range

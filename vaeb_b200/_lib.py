@@ -46,6 +46,7 @@ EXPORTS = {
     "vaeb_update_many": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "vaeb_update_host_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "vaeb_update_host_async_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float]),
+    "vaeb_diag_tile_schedule": (C.c_int, [C.c_int32] * 6 + [C.c_void_p] * 3),
     "vaeb_set_optimizer": (C.c_int, [C.c_void_p, C.c_int32, C.c_float]),
     "vaeb_ae_train": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_float)]),
     "vaeb_ae_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -221,9 +221,12 @@ struct PersistSmem {
 // one chunk), and plain round-robin gives whole CTAs nothing but slivers (148 % 4 == 0) while the others run four full
 // tiles: 66 us for dec2 at 16384 rows.  So: full tiles round-robin first; slivers go, up to three each, to the CTAs that
 // got one full tile fewer, the rest round-robin.
+// a last column tile at most a quarter wide
+__host__ __device__ inline bool tile_sliver(int N, int bn, int tiles_n) { return tiles_n > 1 && (N - (tiles_n - 1) * bn) * 4 <= bn; }
+
 struct TileSeq {
   int G, b, nfn, F, T, base, extra, nf, p1_ctas, p1_total, np1;
-  __device__ TileSeq(int tiles_m, int tiles_n, bool sliver, int grid, int cta) {
+  __host__ __device__ TileSeq(int tiles_m, int tiles_n, bool sliver, int grid, int cta) {
     G = grid; b = cta;
     nfn = tiles_n - (sliver ? 1 : 0);
     F = tiles_m * nfn; T = sliver ? tiles_m : 0;
@@ -234,7 +237,7 @@ struct TileSeq {
     np1 = 0;
     if (b >= extra && b - extra < p1_total) np1 = (p1_total - (b - extra) + p1_ctas - 1) / p1_ctas;
   }
-  __device__ bool get(int i, int& tm, int& tn) const {
+  __host__ __device__ bool get(int i, int& tm, int& tn) const {
     if (i < nf) { const int f = b + i * G; tm = f / nfn; tn = f - tm * nfn; return true; }
     i -= nf;
     if (i < np1) { tm = (b - extra) + i * p1_ctas; tn = nfn; return true; }
@@ -267,7 +270,7 @@ tc_layer_persistent_kernel(const __grid_constant__ LayerMaps maps, Epi epi, int 
   constexpr int TILE_M = MT * BM;
   const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + TILE_M - 1) / TILE_M;
   // a last column tile at most a quarter wide is a "sliver" (see TileSeq); MT = 2 keeps the plain order
-  const bool sliver = MT == 1 && tiles_n > 1 && (N - (tiles_n - 1) * BN) * 4 <= BN;
+  const bool sliver = MT == 1 && tile_sliver(N, BN, tiles_n);
   const TileSeq seq(tiles_m, tiles_n, sliver, (int)gridDim.x, (int)blockIdx.x);
   constexpr uint32_t ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   constexpr uint32_t NBUF = (512u / (MT * ACC_COLS)) >= 2u ? 2u : 1u;      // accumulator sets in TMEM
@@ -739,6 +742,23 @@ prepare_weights_kernel(PrepArgs a) {
 }
 
 }  // namespace
+
+// Host arithmetic only (no device is touched): the tiles CTA `cta` of `grid` works on, in order, when the persistent layer
+// kernel runs a [rows x N] layer with bn-wide tiles -- the schedule of TileSeq, exported so that a CPU test can check that
+// every tile of every shape is visited exactly once (tests/test_golden_cpu.py).
+extern "C" int vaeb_diag_tile_schedule(int32_t rows, int32_t N, int32_t bn, int32_t grid, int32_t cta, int32_t cap,
+                                       int32_t* tm_out, int32_t* tn_out, int32_t* n_out) {
+  if (rows <= 0 || N <= 0 || bn <= 0 || grid <= 0 || cta < 0 || cta >= grid || !tm_out || !tn_out || !n_out) return VAEB_EINVAL;
+  const int tiles_m = (rows + BM - 1) / BM, tiles_n = (N + bn - 1) / bn;
+  const TileSeq seq(tiles_m, tiles_n, tile_sliver(N, bn, tiles_n), grid, cta);
+  int n = 0, tm, tn;
+  for (; seq.get(n, tm, tn); ++n) {
+    if (n >= cap) return VAEB_EINVAL;
+    tm_out[n] = tm; tn_out[n] = tn;
+  }
+  *n_out = n;
+  return VAEB_OK;
+}
 
 cudaError_t tc_prepare_weights(cudaStream_t st, int64_t* launches, const float* W3, const float* W2, const float* W4,
                                const float* W5, const float* W1, const TcBuffers& b, float* w45t, int D, int H, int Z,
