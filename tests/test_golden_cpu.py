@@ -218,3 +218,24 @@ def test_persistent_layer_tile_schedule_covers_every_tile_once():
                 full = [sum(1 for (a, b), c in seen.items() if c == cta and b < tiles_n - 1) for cta in range(grid)]
                 assert max(full) - min(full) <= 1
     assert lib.vaeb_diag_tile_schedule(128, 784, 256, 4, 4, cap, tm, tn, C.byref(n)) != 0      # cta out of range
+
+
+def test_mdl_round_trip_carries_deeper_encoder_layers(tmp_path):
+    """.mdl files (VAEB.py:204-226 layout) of deeper encoders: the extra (W3_k, b3_k) tensors follow the reference's list and
+    read_mdl infers the depth from their number; the reference's 10 / 12 tensor files still read as depth 1."""
+    from vaeb_b200 import io as vio
+    hdr = {"n_hidden_units": 9, "n_latent": 3, "continuous": True, "learning_rate": 0.01, "batch_size": 7, "prng": None,
+           "sigmaInit": 0.01, "L": 1, "genericEstimator": False}
+    rng = np.random.RandomState(4)
+    for depth in (1, 2, 4):
+        params = [rng.normal(size=s).astype(np.float32) for s in O.param_shapes(12, 9, 3, True, depth)]
+        f = str(tmp_path / ("d%d.mdl" % depth))
+        vio.write_mdl(f, hdr, params)
+        h2, p2 = vio.read_mdl(f)
+        assert h2["encoder_layers"] == depth and len(p2) == 12 + 2 * (depth - 1)
+        for a, b in zip(params, p2):
+            np.testing.assert_array_equal(a, b)
+    bad = str(tmp_path / "bad.mdl")
+    vio.write_mdl(bad, hdr, params[:13])                     # an odd number of extra tensors is not a model
+    with pytest.raises(ValueError):
+        vio.read_mdl(bad)
