@@ -86,7 +86,10 @@ typedef struct vaeb_config {
 #define VAEB_ACT_RELU 3
 
 const char* vaeb_last_error(void);
-int vaeb_version(void);
+int vaeb_version(void);      /* 101: vaeb_config ends with encoder_hidden_layers, reserved0 (100: it ended with seed) */
+/* sizeof(vaeb_config) as this library was compiled: a binding that declares the struct itself (ctypes, cgo) compares it
+ * with its own size before the first vaeb_create -- a shorter struct would be read past its end. */
+int vaeb_config_size(void);
 
 /* VAEB.__init__ (VAEB.py:132-187): allocates the flat params / ADA / grads buffers
  * (VAEB.py:178-182) and workspaces on cfg->device.  Parameters start at zero: the host

@@ -31,6 +31,7 @@ EXPORTS = {
     # name: (restype, argtypes)
     "vaeb_last_error": (C.c_char_p, []),
     "vaeb_version": (C.c_int, []),
+    "vaeb_config_size": (C.c_int, []),
     "vaeb_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "vaeb_destroy": (C.c_int, [C.c_void_p]),
     "vaeb_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -97,6 +98,10 @@ def load():
         fn = getattr(lib, name)       # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
+    if lib.vaeb_config_size() != C.sizeof(Config):
+        raise RuntimeError("vaeb_b200: %s was built from another include/vaeb_b200.h (struct vaeb_config is %d bytes there, "
+                           "%d here): rebuild it with `python -m vaeb_b200.build`"
+                           % (LIB_PATH, lib.vaeb_config_size(), C.sizeof(Config)))
     _lib = lib
     return lib
 
