@@ -106,6 +106,9 @@ __device__ __forceinline__ void stamp(const TcTailArgs& a, int k) {
 __global__ void __launch_bounds__(TAIL_THREADS)
 tc_tail_kernel(const TcTailArgs a) {
   __shared__ float red[32];
+  // programmatic dependent launch (VAEB_TAIL_PDL, default on): the grid is scheduled while the weight-gradient launch drains
+  // (its CTAs fill the SMs: nothing of this grid becomes resident before they exit); nothing is read before this point
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   stamp(a, 0);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
@@ -355,9 +358,19 @@ tc_tail_kernel(const TcTailArgs a) {
 }  // namespace
 
 cudaError_t tc_tail_launch(cudaStream_t st, int64_t* launches, const TcTailArgs& a, int grid) {
-  tc_tail_kernel<<<grid, TAIL_THREADS, 0, st>>>(a);
+  static const bool pdl = [] { const char* e = getenv("VAEB_TAIL_PDL"); return !(e && e[0] == '0') && !getenv("VAEB_NO_PDL"); }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TAIL_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl ? 1 : 0;
   ++*launches;
-  return cudaGetLastError();
+  return cudaLaunchKernelEx(&cfg, tc_tail_kernel, a);
 }
 
 // the grid must be co-resident (grid barriers): as many CTAs per SM as the kernel's registers allow
