@@ -6,13 +6,16 @@ Contract (driver): `python bench.py --gpus N --steps K --warmup W` prints ONE JS
 HEADLINE (every N; changed in round 2 as VERDICT r1 item 3 asks -- round 1's headline was c2, which is now the
 last entry of "also"): BASELINE.json configs[2] = "c3": MNIST Bernoulli 784-500-20, ONE global minibatch of
 M = 16384 rows per step, split over the N ranks (16384/N rows each), bf16x3 tensor-core precision (bf16 hi+lo
-operands, fp32 accumulation: the fp32 parity tier, 1e-4), NCCL sum all-reduce of the 3.26 MB gradient when N > 1,
-prior once after it, replicated Adagrad.  Total work per step is fixed => "scaling": "strong".
+operands, fp32 accumulation: the fp32 parity tier, 1e-4); when N > 1 the 3.26 MB gradient is summed inside the update's
+tail kernel over NVLink peer memory (reduce-scatter, prior + Adagrad on the owner's slice, all-gather: tc_tail.cu;
+VAEB_DP_P2P=0: ncclAllReduce + replicated Adagrad).  Total work per step is fixed => "scaling": "strong".
 
   value  device-resident: the rank's rows already in HBM (several minibatches, > L2 in total, visited in turn),
          K updates enqueued back to back, CUDA events on the launch stream, max over ranks.
   e2e    the reference-facing call with HOST inputs: every step copies ITS minibatch share from pinned host memory
          (H2D) and reads ITS bound back (D2H); streaming form (vaeb_update_host_async + vaeb_collect).
+         e2e.sync_call: the synchronous call; e2e.u8_host: the same streaming call fed uint8 pixels (a quarter of the
+         PCIe bytes, expanded on the device: exact for the reference's 8-bit data sets) -- reported beside, not as, e2e.
   roofline  tensor pipe: whole-step algorithmic flops (4,100,000 per datapoint) and the dominant kernel's
          own flops / its CUDA-event time (vaeb_profile_update), against the measured sustained bf16 peak.
   --impl reference  the reference's CPU path: it cannot run here (Python 2 + Theano), so this is the numpy fp32
