@@ -1076,6 +1076,7 @@ int vaeb_ae_train(vaeb_handle* h, int32_t kind, const int32_t* idx, int32_t n, f
   VAEB_REQUIRE(kind == VAEB_AE_DEGENERATE || kind == VAEB_AE_VANILLA, "unknown AE kind");
   VAEB_REQUIRE(!(kind == VAEB_AE_VANILLA && h->cont), "the vanilla AE has sigmoid outputs only (vanilla-ae/ae.py:62-67)");
   VAEB_REQUIRE(h->L == 1 && !is_fvb(h) && h->world == 1, "AE baselines: L = 1, single GPU");
+  VAEB_REQUIRE(h->lay.depth <= 1, "AE baselines have one hidden layer per side (degenerate-vae/ae.py:41-117)");
   if (!h->d_x) { vaeb_set_error("vaeb_ae_train before vaeb_upload_data"); return VAEB_ESTATE; }
   h->steptc.mirrors_valid = false; h->tc.weights_ready = false;
   for (int i = 0; i < n; ++i) VAEB_REQUIRE(idx[i] >= 0 && idx[i] < h->n_data, "row index outside the resident data");
@@ -1138,6 +1139,7 @@ int vaeb_ae_forward(vaeb_handle* h, int32_t kind, int32_t what, const float* in,
   VAEB_REQUIRE(h && in && out && rows > 0, "null argument");
   VAEB_REQUIRE(kind == VAEB_AE_DEGENERATE || kind == VAEB_AE_VANILLA, "unknown AE kind");
   VAEB_REQUIRE(what >= 0 && what <= 2, "what: 0 reconstruct, 1 encode, 2 decode");
+  VAEB_REQUIRE(h->lay.depth <= 1, "AE baselines have one hidden layer per side (degenerate-vae/ae.py:41-117)");
   VAEB_CUDA(cudaSetDevice(h->cfg.device));
   const Layout& l = h->lay;
   const int D = h->D, H = h->H, Z = h->Z, r = (int)rows;
